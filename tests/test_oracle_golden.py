@@ -1,0 +1,396 @@
+"""Pin the oracle: (1) against vectors produced by executing the reference's own functions
+(tests/golden/make_golden.py), (2) against the reference's own offline known-answer tests,
+restated here without xarray (each test cites the reference test it restates)."""
+
+import json
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import calibrate as ocal
+from oracle import clean as oclean
+from oracle import commongrid as ogrid
+from oracle import ek80_signal as osig
+from oracle import seawater as osea
+
+
+@pytest.fixture(scope="module")
+def vec(golden_dir):
+    return np.load(os.path.join(golden_dir, "reference_vectors.npz"))
+
+
+@pytest.fixture(scope="module")
+def cases(golden_dir):
+    with open(os.path.join(golden_dir, "reference_cases.json")) as fh:
+        return json.load(fh)
+
+
+# ---------------------------------------------------------------- executed-reference vectors ----
+def test_seawater_matches_reference_vectors(vec):
+    T, S, P, f = vec["uwa_T"], vec["uwa_S"], vec["uwa_P"], vec["uwa_f"]
+    for i, t in enumerate(T):
+        for j, s in enumerate(S):
+            for k, p in enumerate(P):
+                assert osea.sound_speed(t, s, p, "Mackenzie") == pytest.approx(vec["uwa_c_mackenzie"][i, j, k], rel=1e-14)
+                assert osea.sound_speed(t, s, p, "AZFP") == pytest.approx(vec["uwa_c_azfp"][i, j, k], rel=1e-14)
+                for src in ("AM", "FG", "AZFP"):
+                    got = osea.absorption(f, t, s, p, 8.1, None, src)
+                    np.testing.assert_allclose(got, vec[f"uwa_abs_{src}"][i, j, k], rtol=1e-13)
+    np.testing.assert_allclose(osea.absorption(f, 8.0, 33.0, 50.0, 7.8, 1500.0, "FG"), vec["uwa_abs_FG_c1500_pH78"], rtol=1e-13)
+
+
+def test_uwa_reference_tolerances():
+    """tests/utils/test_utils_uwa.py:13-67."""
+    rows = [(18e3, 27, 35, 10, 8, 2.11e-5, 2.3e-4), (18e3, 27, 35, 100, 8, 3e-5, 2.2e-4), (38e3, 27, 35, 10, 8, 1.8e-4, 8.5e-4),
+            (38e3, 10, 35, 10, 8, 2.1e-4, 2.4e-3), (120e3, 27, 35, 10, 8, 3e-5, 7.4e-3), (200e3, 27, 35, 10, 8, 3.1e-3, 0.02),
+            (455e3, 20, 35, 10, 8, 7.4e-3, 2.1e-2), (1e6, 10, 35, 10, 8, 2.49e-2, 1.4e-2)]
+    for f, t, s, p, ph, tol, tol_azfp in rows:
+        a = {fm: osea.absorption(f, t, s, p, ph, None, fm) for fm in ("AM", "FG", "AZFP")}
+        assert abs(a["AM"] - a["FG"]) < tol
+        assert abs(a["AM"] - a["AZFP"]) < tol_azfp and abs(a["FG"] - a["AZFP"]) < tol_azfp
+    for t, s, p, tol in [(27, 35, 10, 0.07), (27, 35, 100, 0.07), (5, 35, 3500, 0.5)]:
+        assert abs(osea.sound_speed(t, s, p, "Mackenzie") - osea.sound_speed(t, s, p, "AZFP")) < tol
+
+
+def test_db_helpers_and_parsers(vec, cases):
+    np.testing.assert_array_equal(oclean.log2lin(vec["dB_x"]), vec["log2lin"])
+    np.testing.assert_array_equal(oclean.lin2log(vec["log2lin"]), vec["lin2log"])
+    for s, v in cases["extract_dB"].items():
+        assert oclean.extract_dB(s) == v
+    for s, err in cases["extract_dB_errors"].items():
+        with pytest.raises(ValueError):
+            oclean.extract_dB(s)
+    with pytest.raises(TypeError):
+        oclean.extract_dB(3.0)
+    for lab, d in cases["parse_x_bin"].items():
+        for s, v in d.items():
+            assert ogrid.parse_x_bin(s, lab) == v
+    for key, (etype, msg) in cases["parse_x_bin_errors"].items():
+        s, lab = key.split("|")
+        with pytest.raises({"ValueError": ValueError, "KeyError": KeyError}[etype]) as ei:
+            ogrid.parse_x_bin(s, lab)
+        assert msg.strip("'\"") in str(ei.value).strip("'\"") or etype == "KeyError"
+    with pytest.raises(TypeError, match="must be a string"):
+        ogrid.parse_x_bin(10, "range_bin")
+
+
+def test_chirp_replica_matches_reference(vec, cases):
+    fs = 1.5e6
+    wbt, pcf = vec["ek80_wbt_fil"], vec["ek80_pc_fil"]
+    ytx = []
+    for i, (tau, slope, f0, f1, drop) in enumerate(cases["chirp_cases"]):
+        y, t = osig.tapered_chirp(fs, tau, slope, f0, f1, drop)
+        np.testing.assert_array_equal(y, vec[f"chirp{i}_y"])
+        np.testing.assert_array_equal(t, vec[f"chirp{i}_t"])
+        yd, td = osig.filter_decimate_chirp(y, fs, wbt, 6, pcf, 2)
+        np.testing.assert_array_equal(yd, vec[f"chirp{i}_ydeci"])
+        np.testing.assert_array_equal(td, vec[f"chirp{i}_tdeci"])
+        ytx.append(yd)
+    for mode in ("BB", "CW"):
+        got = np.array([osig.tau_effective(y, fs / 12, mode) for y in ytx])
+        np.testing.assert_allclose(got, vec[f"tau_eff_{mode}"], rtol=1e-14)
+    np.testing.assert_allclose([np.linalg.norm(y) ** 2 for y in ytx], vec["norm_fac"], rtol=1e-15)
+
+
+def test_compress_pulse_matches_reference_convolution(vec, cases):
+    slab = vec["conv_slab"]  # (R, 2) for channels ch0, ch2
+    chirp = [vec["chirp0_ydeci"], vec["chirp2_ydeci"]]
+    bs = slab.T[:, None, :, None]  # (C=2, P=1, R, B=1)
+    pc = osig.compress_pulse(bs, chirp)
+    np.testing.assert_array_equal(pc[:, 0, :, 0].T.astype(np.complex64), vec["conv_out"])
+    z = osig.compress_pulse(np.zeros((2, 1, 8, 1), complex), chirp)
+    np.testing.assert_array_equal(z[:, 0, :, 0].T.astype(np.complex64), vec["conv_zero_out"])
+    # NaN padding is zeroed before and restored after (ek80_complex.py:340-367)
+    bs2 = bs.copy()
+    bs2[:, :, 200:, :] = np.nan
+    pc2 = osig.compress_pulse(bs2, chirp)
+    assert np.isnan(pc2[:, :, 200:, :]).all()
+    np.testing.assert_array_equal(pc2[:, :, :200, :], pc[:, :, :200, :])
+
+
+# -------------------------------------------------------- reference known-answer tests, restated ----
+VEND_PL = np.array([[64, 128, 256, 512], [128, 256, 512, 1024]], float)
+VEND_TB = np.array([[10, 20, 30, 40], [110, 120, 130, 140]], float)
+
+
+@pytest.mark.parametrize(
+    "tau,expected",
+    [
+        ([[64, 256, 128, 512], [512, 1024, 256, 128]], [[10, 30, 20, 40], [130, 140, 120, 110]]),
+        ([[64, np.nan, 128, 512], [512, 1024, 256, np.nan]], [[10, np.nan, 20, 40], [130, 140, 120, np.nan]]),
+    ],
+)
+def test_pulse_length_lookup_tables(tau, expected):
+    """tests/calibrate/test_cal_params.py:751-868 (channel-order variants are a label-matching
+    concern handled by the host API, tested in tests/test_host_params.py)."""
+    got = ocal.vend_cal_params_power(np.array(tau, float), VEND_PL, VEND_TB)
+    np.testing.assert_allclose(got, np.array(expected, float), equal_nan=True)
+
+
+def test_harmonize_time1_interpolation():
+    """tests/calibrate/test_env_params.py:33-127: -> 0.5 and [0.5, 2880.5]."""
+    t1 = np.arange("2017-06-20T01:00:00", "2017-06-20T01:01:30", np.timedelta64(30, "s"), dtype="datetime64[ns]").astype(np.int64)
+    assert ocal.harmonize_time1([2], t1[:1], None) == 2
+    tp = np.array(["2017-06-20T01:00:15"], dtype="datetime64[ns]").astype(np.int64)
+    assert ocal.harmonize_time1([0, 1, 2], t1, tp)[0] == 0.5
+    np.testing.assert_array_equal(ocal.harmonize_time1([0, 1, 2], t1, t1), [0, 1, 2])
+    t1 = np.arange("2017-06-20T01:00:00", "2017-06-22T01:00:31", np.timedelta64(30, "s"), dtype="datetime64[ns]").astype(np.int64)
+    tp = np.array(["2017-06-20T01:00:15", "2017-06-21T01:00:15"], dtype="datetime64[ns]").astype(np.int64)
+    np.testing.assert_array_equal(ocal.harmonize_time1(np.arange(len(t1)), t1, tp), [0.5, 2880.5])
+
+
+def test_remove_background_noise_toy():
+    """tests/clean/test_noise.py:902-987: spikes at 30/60 -> NaN; seed-1 normal -> exactly 6 NaNs."""
+    nchan, npings, nrs = 1, 10, 100
+    data = np.ones(nrs)
+    data[30] = -30
+    data[60] = -30
+    Sv = np.array([[data] * npings])
+    rng = np.array([[np.linspace(0, 10, nrs)] * npings])
+    out = oclean.remove_background_noise(Sv, rng, 0.001, ping_num=2, range_sample_num=5, SNR_threshold="0dB")
+    assert np.isnan(out["Sv_corrected"][0, 0, 30]) and np.isnan(out["Sv_corrected"][0, 0, 60])
+    np.random.seed(1)
+    Sv = np.random.normal(loc=-100, scale=2, size=(nchan, npings, nrs))
+    rng = np.array([[np.linspace(0, 3, nrs)] * npings])
+    out = oclean.remove_background_noise(Sv, rng, 0.001, ping_num=2, range_sample_num=5, SNR_threshold="0dB")
+    assert np.count_nonzero(np.isnan(out["Sv_corrected"][0, :, :50])) == 6
+
+
+def test_estimate_noise_upsampling_pairs():
+    """tests/clean/test_noise.py:865-899 (property): Sv_noise - TL repeats in ping pairs."""
+    g = np.random.default_rng(3)
+    Sv = g.normal(-80, 5, size=(2, 7, 23))
+    rng = np.broadcast_to(np.linspace(0.2, 40, 23), (2, 7, 23)).copy()
+    noise = oclean.estimate_background_noise(Sv, rng, np.array([0.01, 0.04]), 2, 5)
+    base = noise - oclean.transmission_loss(rng, np.array([0.01, 0.04]))
+    np.testing.assert_allclose(base[:, 0:6:2, :], base[:, 1:6:2, :], rtol=0, atol=1e-12)
+
+
+def _ping_time(n, interval="0.3s", jitter_ms=0, g=None):
+    """tests/mock_data.py:17-24."""
+    pt = pd.Timestamp("2018-07-01") + pd.to_timedelta(np.arange(n) * pd.to_timedelta(interval))
+    if jitter_ms:
+        pt = (pt + pd.to_timedelta(g.integers(jitter_ms, size=n), unit="ms")).sort_values()
+    return pt.values.astype("datetime64[ns]").astype(np.int64)
+
+
+NAN_ILOCS = [(1, 1, 10), (1, 0, 16), (0, 3, 6), (0, 2, 11), (0, 2, 6), (1, 1, 14), (0, 1, 17), (1, 4, 19), (0, 3, 3),
+             (0, 0, 19), (0, 1, 5), (1, 2, 9), (1, 4, 18), (0, 1, 5), (0, 4, 4), (0, 1, 6), (1, 2, 2), (0, 1, 2), (0, 4, 8), (0, 1, 1)]
+
+
+def _mock_Sv(irregular, g):
+    """tests/commongrid/conftest.py:74-166 (mock_Sv_dataset_regular / _irregular), C=2,P=10,R=20."""
+    C, P, R = 2, 10, 20
+    Sv = np.tile(np.linspace(0, 1, R), (C, P, 1))
+    if irregular:
+        er = np.concatenate([np.tile(np.arange(R) * d, (C, n, 1)) for d, n in zip([0.5, 0.32, 0.2], [2, 3, 5])], axis=1)
+        pt = _ping_time(P, "0.3s", 30, g)
+    else:
+        er = np.tile(np.arange(R) * 0.5, (C, P, 1))
+        pt = _ping_time(P)
+    depth = 2.5 + er  # add_depth(depth_offset=2.5) BEFORE the NaNs are sprinkled
+    lat = np.linspace(42.48916859, 42.49071833, num=P)
+    lon = np.linspace(-124.88296688, -124.81919229, num=P)
+    if irregular:
+        for pos in NAN_ILOCS:
+            er[pos] = np.nan
+            Sv[pos] = np.nan
+    return Sv, er, depth, pt, lat, lon
+
+
+def _brute_mvbs(Sv, rng, pt, p_edges, r_edges, nan_aware):
+    """tests/mock_data.py:28-85 / tests/commongrid/conftest.py:553-615 (label-slice is inclusive)."""
+    C = Sv.shape[0]
+    sv = 10 ** (Sv / 10)
+    out = np.full((C, len(p_edges) - 1, len(r_edges) - 1), np.nan)
+    for c in range(C):
+        for i in range(len(p_edges) - 1):
+            sel = (pt >= p_edges[i]) & (pt <= p_edges[i + 1])
+            for j in range(len(r_edges) - 1):
+                act = (rng[c, sel] >= r_edges[j]) & (rng[c, sel] < r_edges[j + 1])
+                v = sv[c, sel][act]
+                if v.size:
+                    out[c, i, j] = np.nanmean(v) if nan_aware else np.mean(v)
+    return out
+
+
+@pytest.mark.parametrize("irregular", [False, True])
+def test_mvbs_values_vs_brute_force(irregular):
+    """tests/commongrid/test_commongrid_api.py:371-436 (atol=rtol=1e-10; NaN mask by histogram)."""
+    g = np.random.default_rng(11)
+    Sv, er, depth, pt, lat, lon = _mock_Sv(irregular, g)
+    got = ogrid.compute_MVBS(Sv, er, pt, range_bin="2m", ping_time_bin="1s")
+    p_edges = got["p_edges"]
+    r_edges_ref = np.arange(0, np.nanmax(er) + 2, 2)  # mock_data.py:58
+    expected = 10 * np.log10(_brute_mvbs(Sv, er, pt, p_edges, r_edges_ref, nan_aware=False))
+    assert got["Sv"].shape == expected.shape
+    np.testing.assert_allclose(got["Sv"], expected, atol=1e-10, rtol=1e-10, equal_nan=True)
+    # NaN mask == "no echo_range sample falls in the bin" (test_commongrid_api.py:374-418)
+    step = got["range"][1] - got["range"][0]
+    bins = np.append(got["range"], got["range"].max() + step)
+    for c in range(2):
+        for i in range(len(p_edges) - 1):
+            sel = (pt >= p_edges[i]) & ((pt <= p_edges[i + 1]) if i < len(p_edges) - 2 else True)
+            vals = er[c, sel]
+            hist, _ = np.histogram(vals[~np.isnan(vals)], bins=bins)
+            np.testing.assert_array_equal(np.isnan(got["Sv"][c, i]), hist == 0)
+
+
+@pytest.mark.parametrize("skipna", [True, False])
+@pytest.mark.parametrize("range_var", ["depth", "echo_range"])
+def test_mvbs_skipna_nan_patterns(skipna, range_var):
+    """tests/commongrid/test_commongrid_api.py:484-556 (first 2 pings of the irregular mock)."""
+    g = np.random.default_rng(5)
+    Sv, er, depth, pt, lat, lon = _mock_Sv(True, g)
+    rv = (depth if range_var == "depth" else er)[:, :2]
+    got = ogrid.compute_MVBS(Sv[:, :2], rv, pt[:2], range_bin="2m", ping_time_bin="20s", skipna=skipna)["Sv"]
+    mask = np.isnan(got)
+    if range_var == "echo_range":
+        exp = [[[False] * 5], [[False] * 5]]
+    elif skipna:
+        exp = [[[True, False, False, False, False, False]], [[True, False, False, False, False, False]]]
+    else:
+        exp = [[[True, True, True, False, False, True]], [[True, False, False, True, True, True]]]
+    np.testing.assert_array_equal(mask, np.array(exp))
+
+
+def test_mvbs_range_var_max_and_shapes():
+    """test_commongrid_api.py:580-592 (range_var_max='8m' -> last left edge 8) and :319-360 shapes."""
+    g = np.random.default_rng(7)
+    Sv, er, depth, pt, lat, lon = _mock_Sv(False, g)
+    got = ogrid.compute_MVBS(Sv, er, pt, range_bin="1m", range_var_max="8m")
+    assert got["range"].max() == 8
+    # regular 4ch x 100 pings x 4000 samples of 0.5 m, "5m"/"10s" -> (4, ceil(dt/10), ceil(max/5))
+    C, P, R = 4, 100, 4000
+    er = np.tile(np.arange(R) * 0.5, (C, P, 1))
+    pt = _ping_time(P)
+    got = ogrid.compute_MVBS(g.random((C, P, R)), er, pt, range_bin="5m", ping_time_bin="10s")
+    assert got["Sv"].shape == (C, int(np.ceil((pt[-1] - pt[0]) / 1e9 / 10)), int(np.ceil(er.max() / 5)))
+
+
+def test_mvbs_irregular_range_output_shape():
+    """test_commongrid_api.py:319-360 irregular: per-segment count of non-NaN range bins 10/7/3."""
+    g = np.random.default_rng(9)
+    C, R = 2, 100
+    er = np.concatenate([np.tile(np.arange(R) * d, (C, n, 1)) for d, n in zip([0.5, 0.32, 0.13], [100, 300, 200])], axis=1)
+    pt = _ping_time(600)
+    got = ogrid.compute_MVBS(g.random((C, 600, R)), er, pt, range_bin="5m", ping_time_bin="10s")["Sv"]
+    nn = lambda a: (~np.isnan(a).any(axis=(0, 1))).sum()  # noqa: E731  dropna(dim="echo_range")
+    assert got[:, :3].shape[1] == 3 and nn(got[:, :3]) == 10
+    assert nn(got[:, 3:12]) == 7
+    assert got[:, 12:].shape[1] == 6 and nn(got[:, 12:]) == 3
+
+
+def test_index_binning_equals_coarsen():
+    """test_commongrid_api.py:171-202: shape ceil((C, P/pn, R/rn)) and values == coarsen nanmean."""
+    g = np.random.default_rng(13)
+    C, P, R = 4, 100, 4000
+    Sv = g.random((C, P, R))
+    er = np.tile(np.arange(R) * 0.5, (C, P, 1))
+    out = ogrid.compute_MVBS_index_binning(Sv, er, range_sample_num=7, ping_num=3)
+    assert out["Sv"].shape == (4, 34, 572)
+    # independent brute-force of two tiles, including the padded last ones
+    lin = 10 ** (Sv / 10)
+    assert out["Sv"][1, 2, 5] == pytest.approx(10 * np.log10(lin[1, 6:9, 35:42].mean()), rel=1e-13)
+    assert out["Sv"][3, 33, 571] == pytest.approx(10 * np.log10(lin[3, 99:, 3997:].mean()), rel=1e-13)
+    assert out["echo_range"][0, 4, 10] == 35.0
+
+
+def _nasc_echoview(Sv, depth, ch, r0=2, r1=20):
+    """tests/commongrid/conftest.py:426-444 (depth is (C, range_sample, distance) there)."""
+    r = depth[ch, :, 0]
+    i0, i1 = np.argmin(abs(r - r0)), np.argmin(abs(r - r1))
+    sh = np.r_[np.diff(r), np.nan]
+    sv = 10 ** (Sv[ch] / 10)
+    return np.nanmean(sv[i0:i1]) * np.sum(sh[i0:i1]) * 4 * np.pi * 1852**2
+
+
+def test_nasc_echoview_closed_form():
+    """tests/commongrid/test_commongrid_api.py:154-167 with conftest.py:404-463."""
+    g = np.random.default_rng(17)
+    dim0 = np.array([0.5, 1.5, 2.5, 3.5, 9])
+    sv0 = np.array([[1.0, 2, 3, 4, np.nan], [6, 7, 8, 9, 10], [11, 12, 13, 14, 15], [16, 17, 18, 19, np.nan], [21, 22, 23, 24, 25]])
+    Sv_rd, depth_rd = [], []
+    for _ in range(2):
+        Sv_rd.append(10 * np.log10(sv0 + g.random() * 5))  # dims (range_sample, distance_nmi)
+        depth_rd.append(np.array([dim0] * 5).T)
+    Sv_rd, depth_rd = np.array(Sv_rd), np.array(depth_rd)
+    # oracle layout is (C, X=distance, R=range_sample)
+    Sv, depth = Sv_rd.transpose(0, 2, 1), depth_rd.transpose(0, 2, 1)
+    pt = pd.date_range("2020-01-01", periods=5, freq="1min").values.astype("datetime64[ns]").astype(np.int64)
+    raw = ogrid.compute_raw_NASC(Sv, depth, np.arange(5, dtype=float), pt, np.array([1, 5]), np.array([-5, 10]))
+    for ch in range(2):
+        assert raw["NASC"][ch, 0, 0] == pytest.approx(_nasc_echoview(Sv_rd, depth_rd, ch), rel=1e-10, abs=1e-10)
+
+
+@pytest.mark.parametrize("irregular", [False, True])
+def test_nasc_values_vs_brute_force(irregular):
+    """tests/commongrid/test_commongrid_api.py:447-469 with conftest.py:467-551."""
+    g = np.random.default_rng(19)
+    Sv, er, depth, pt, lat, lon = _mock_Sv(irregular, g)
+    got = ogrid.compute_NASC(Sv, depth, lat, lon, pt, range_bin="2m", dist_bin="0.5nmi")
+    dist, d_edges, r_edges = got["dist_nmi"], got["d_edges"], got["r_edges"]
+    sv_mean = _brute_mvbs(Sv, depth, dist, d_edges, r_edges, nan_aware=True)
+    C = 2
+    h_den = np.array([((dist >= d_edges[i]) & (dist <= d_edges[i + 1])).sum() for i in range(len(d_edges) - 1)], float)
+    diff, lower = np.diff(depth, axis=2), depth[:, :, :-1]
+    h_num = np.full((C, len(d_edges) - 1, len(r_edges) - 1), np.nan)
+    for c in range(C):
+        for i in range(len(d_edges) - 1):
+            sel = (dist >= d_edges[i]) & (dist <= d_edges[i + 1])
+            for j in range(len(r_edges) - 1):
+                act = (lower[c, sel] >= r_edges[j]) & (lower[c, sel] < r_edges[j + 1])
+                v = diff[c, sel][act]
+                if v.size:
+                    h_num[c, i, j] = v.sum()
+    expected = sv_mean * (h_num / h_den[None, :, None]) * 4 * np.pi * 1852**2
+    assert got["NASC"].shape == expected.shape
+    np.testing.assert_allclose(got["NASC"], expected, atol=1e-10, rtol=1e-10, equal_nan=True)
+
+
+def test_geodesic_known_values():
+    """geopy is absent; Vincenty restatement checked against published WGS-84 arc lengths."""
+    assert ogrid.geodesic_m(0, 0, 0, 1) == pytest.approx(111319.4908, abs=1e-3)  # 1 deg of equator
+    assert ogrid.geodesic_m(0, 0, 1, 0) == pytest.approx(110574.3886, abs=1e-3)  # meridian 0->1 deg
+    assert ogrid.geodesic_m(42.0, -124.0, 42.0, -124.0) == 0.0
+
+
+# ------------------------------------------------------------- closed-form guards for K1 (unpinned) ----
+def test_ek60_sv_closed_form_and_nan_rules():
+    """compute_Sv values are unpinned offline; guard the restatement with an analytic case
+    (constant power) and the n<=2 -> NaN rule (calibrate_ek.py:107, range.py:176-188)."""
+    C, P, R = 2, 3, 50
+    dt, c = 2.56e-4, 1500.0
+    bs = np.full((C, P, R), -70.0, dtype=np.float32)
+    bs[1, 2, 40:] = np.nan
+    f = np.array([38e3, 120e3])
+    alpha = np.array([0.0098, 0.0375])
+    res = ocal.ek_power_cal("Sv", "EK60", bs, np.full((C, P), dt), c, alpha, np.full((C, P), 1.024e-3), np.full((C, P), 2000.0),
+                            f, np.full((C, P), 26.0), np.full((C, P), -0.5), np.array([-20.6, -20.7]), np.full((C, P), 1.024e-3))
+    Sv, rng = res["out"], res["echo_range"]
+    assert np.isnan(Sv[:, :, :3]).all() and not np.isnan(Sv[0, :, 3:]).any()
+    assert np.isnan(Sv[1, 2, 40:]).all() and np.isnan(rng[1, 2, 40:]).all()
+    n = 10
+    Rm = n * dt * c / 2 - dt * c
+    lam = c / f[0]
+    expect = (-70.0 + 20 * np.log10(Rm) + 2 * alpha[0] * Rm - (10 * np.log10(2000.0) + 52.0 - 20.6
+              + 10 * np.log10(lam**2 * 1.024e-3 * c / (32 * np.pi**2))) + 1.0)
+    assert Sv[0, 1, n] == pytest.approx(expect, abs=1e-11)
+    assert rng[0, 0, n] == pytest.approx(n * dt * c / 2, rel=1e-15)
+    ts = ocal.ek_power_cal("TS", "EK60", bs, np.full((C, P), dt), c, alpha, np.full((C, P), 1.024e-3), np.full((C, P), 2000.0),
+                           f, np.full((C, P), 26.0), np.full((C, P), -0.5), np.array([-20.6, -20.7]), None)["out"]
+    expect_ts = -70.0 + 40 * np.log10(Rm) + 2 * alpha[0] * Rm - (10 * np.log10(2000.0) + 52.0 + 10 * np.log10(lam**2 / (16 * np.pi**2)))
+    assert ts[0, 1, n] == pytest.approx(expect_ts, abs=1e-11)
+
+
+def test_azfp_range_matches_manual_formula():
+    """range.py:77-89 against the operator's-manual expression evaluated by hand."""
+    c, tau, N, fd, L = 1480.0, 3e-4, 2, 64000.0, 10
+    r = ocal.azfp_echo_range(5, c, np.full((1, 2), tau), [N], [fd], [L], "Sv")
+    m = 3  # bin m (1-based) = n+1
+    expect = c * L / (2 * fd) + c / 4 * (((2 * m - 1) * N - 1) / fd + tau)
+    assert r[0, 1, 2] == pytest.approx(expect, rel=1e-15)
+    r_ts = ocal.azfp_echo_range(5, c, np.full((1, 2), tau), [N], [fd], [L], "TS")
+    assert (r - r_ts)[0, 0, 0] == pytest.approx(c * tau / 4, rel=1e-12)
