@@ -1,0 +1,88 @@
+"""ctypes binding of libepb200.so (include/epb200.h).  The product path has NO fallback: if the
+library is missing or a call fails, an exception is raised."""
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_longlong, c_ubyte, c_uint, c_ulonglong, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libepb200.so")
+
+
+class EpbError(RuntimeError):
+    pass
+
+
+class epb_cp(Structure):
+    _fields_ = [("ptr", c_void_p), ("sc", c_longlong), ("sp", c_longlong)]
+
+
+class epb_row(Structure):
+    _fields_ = (
+        [(n, c_double) for n in ("p0", "p1", "p2", "p3", "p4", "off1", "off2", "r0", "a", "two_alpha", "K", "fscale", "foff", "slog")]
+        + [("n_start", c_int), ("law", c_int), ("azfp_N", c_int), ("reserved", c_int)]
+    )
+
+
+assert ctypes.sizeof(epb_row) == 128
+
+i64, vp = c_longlong, c_void_p
+
+# name -> (restype, argtypes); mirrors include/epb200.h one to one
+SIGNATURES = {
+    "epb_last_error": (c_char_p, []),
+    "epb_version": (c_int, []),
+    "epb_rows_ek_power": (c_int, [vp, i64, i64, i64, c_int, c_int] + [epb_cp] * 10 + [vp, vp]),
+    "epb_rows_azfp": (c_int, [vp, i64, i64, i64, c_int, epb_cp, epb_cp, epb_cp] + [vp] * 9 + [vp]),
+    "epb_rows_ek80_complex": (c_int, [vp, i64, i64, i64, c_int, c_int, c_int] + [epb_cp] * 12 + [vp, vp]),
+    "epb_sv_power": (c_int, [vp, vp, vp, vp, vp, i64, i64, i64, vp]),
+    "epb_sv_complex": (c_int, [vp, vp, vp, vp, vp, vp, i64, i64, i64, c_int, vp]),
+    "epb_pulse_compress_sv": (c_int, [vp, vp, vp, POINTER(c_int), vp, vp, vp, vp, vp, vp, i64, i64, i64, c_int, vp]),
+    "epb_noise_estimate": (c_int, [vp, vp, epb_cp, vp, i64, i64, i64, c_int, c_int, c_float, vp]),
+    "epb_noise_apply": (c_int, [vp, vp, epb_cp, vp, vp, vp, vp, i64, i64, i64, c_int, c_float, vp]),
+    "epb_bin_reduce": (c_int, [vp, vp, c_int, vp, vp, c_int, c_int, c_int, vp, i64, i64, i64, i64, vp]),
+    "epb_bin_finalize": (c_int, [vp, vp, vp, i64, c_int, c_float, c_int, vp]),
+    "epb_coarsen": (c_int, [vp, vp, vp, vp, i64, i64, i64, c_int, c_int, vp]),
+    "epb_bin_bounds": (c_int, [vp, vp, c_int, c_int, vp, vp, c_double, vp, i64, i64, i64, vp]),
+    "epb_pipeline_power_mvbs": (
+        c_int,
+        [vp, vp, vp, vp, c_int, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, c_int, c_int, c_float, c_float, vp],
+    ),
+    "epb_pipeline_smem_bytes": (i64, [i64, c_int]),
+    "epb_zero": (c_int, [vp, i64, vp]),
+    "epb_minmax_init": (c_int, [vp, vp]),
+    "epb_synth_fill": (c_int, [vp, i64, i64, i64, i64, c_int, c_ulonglong, i64, c_uint, c_float, vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libepb200.so (once).  Raises EpbError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EpbError(
+            f"{LIB_PATH} not found: the CUDA library has not been built. "
+            "Run `python -m echopype_b200.build` (needs nvcc). There is no CPU fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().epb_last_error()
+        raise EpbError(f"{what} failed (rc={rc}): {msg.decode() if msg else ''}")
+
+
+def call(name, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    check(rc, name)

@@ -1,0 +1,242 @@
+// K1 / K2: fused per-sample Sv / TS.
+//
+// One pass over HBM: read the raw sample (power dB, AZFP counts, or 4-beam complex), evaluate
+//   out = front(x) + slog*log10(R') + 2*alpha*R' - K        
+// from the per-row record, write out (+ echo_range).  Replaces the ~10 full-size float64 temporaries of
+// calibrate_ek.py:98-171 / calibrate_azfp.py:64-96 / calibrate_ek.py:483-505,564-625 and range.py:138-148.
+//
+// Layout: rows are contiguous R-float runs; a CTA takes whole rows (grid-stride) so the 128-byte row
+// record is read once per row; threads stream float4 (LDG.128 nc / STG.128 cs), 4 independent loads in
+// flight per thread.  HBM-bound: 8 B/sample (12 with echo_range); see DESIGN.md for the roofline.
+#include "epb_common.cuh"
+
+namespace {
+using namespace epb;
+
+struct RowC {  // per-row constants hoisted into registers
+  double r0, a, off, two_alpha, K;
+  float fscale, foff, slog;
+  int n_start;
+  bool nanrange;
+  __device__ __forceinline__ explicit RowC(const epb_row& r)
+      : r0(r.r0), a(r.a), off(r.off1 + r.off2), two_alpha(r.two_alpha), K(r.K), fscale((float)r.fscale),
+        foff((float)r.foff), slog((float)r.slog), n_start(r.n_start), nanrange((r.law & EPB_LAW_NANRANGE) != 0) {}
+};
+
+// value of one sample given its dB-domain front end `fr` (NaN-propagating)
+__device__ __forceinline__ float sample_out(const RowC& rc, int n, float fr, float& range_out) {
+  double Rd = fma(rc.a, (double)n, rc.r0);
+  double Rp = Rd - rc.off;
+  float rp = (float)Rp;
+  float lin = (float)fma(rc.two_alpha, Rp, -rc.K);
+  float v = fr + fmaf(rc.slog, log10f(rp), lin);
+  range_out = (float)Rd;
+  return (n >= rc.n_start) ? v : CUDART_NAN_F;
+}
+
+template <bool kRange, bool kMinMax>
+__global__ void __launch_bounds__(256) sv_power_vec4(const float* __restrict__ x, const epb_row* __restrict__ rows,
+                                                     float* __restrict__ out, float* __restrict__ rng,
+                                                     float* __restrict__ minmax, long long nrows, int R) {
+  const int R4 = R >> 2;
+  MinMax mm_v, mm_r;
+  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const RowC rc(rows[row]);
+    const float4* xin = reinterpret_cast<const float4*>(x + row * (long long)R);
+    float4* o4 = reinterpret_cast<float4*>(out + row * (long long)R);
+    float4* r4 = kRange ? reinterpret_cast<float4*>(rng + row * (long long)R) : nullptr;
+    for (int j0 = threadIdx.x; j0 < R4; j0 += 4 * blockDim.x) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        int j = j0 + u * blockDim.x;
+        if (j < R4) v[u] = ld_stream4(xin + j);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        int j = j0 + u * blockDim.x;
+        if (j >= R4) break;
+        float in[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        float o[4], rr[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float fr = fmaf(in[k], rc.fscale, rc.foff);
+          o[k] = sample_out(rc, 4 * j + k, fr, rr[k]);
+          if (rc.nanrange && in[k] != in[k]) rr[k] = CUDART_NAN_F;  // range.py:143-148
+          if (kMinMax) {
+            mm_v.add(o[k]);
+            mm_r.add(rr[k]);
+          }
+        }
+        st_stream4(o4 + j, make_float4(o[0], o[1], o[2], o[3]));
+        if (kRange) st_stream4(r4 + j, make_float4(rr[0], rr[1], rr[2], rr[3]));
+      }
+    }
+  }
+  if (kMinMax) {
+    mm_v.flush(minmax + 0, minmax + 1);
+    mm_r.flush(minmax + 2, minmax + 3);
+  }
+}
+
+// scalar fallback for R % 4 != 0 or unaligned bases (ragged last dimension)
+template <bool kRange, bool kMinMax>
+__global__ void __launch_bounds__(256) sv_power_scalar(const float* __restrict__ x, const epb_row* __restrict__ rows,
+                                                       float* __restrict__ out, float* __restrict__ rng,
+                                                       float* __restrict__ minmax, long long nrows, int R) {
+  MinMax mm_v, mm_r;
+  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const RowC rc(rows[row]);
+    const long long base = row * (long long)R;
+    for (int n = threadIdx.x; n < R; n += blockDim.x) {
+      float in = ld_stream(x + base + n);
+      float rr;
+      float o = sample_out(rc, n, fmaf(in, rc.fscale, rc.foff), rr);
+      if (rc.nanrange && in != in) rr = CUDART_NAN_F;
+      out[base + n] = o;
+      if (kRange) rng[base + n] = rr;
+      if (kMinMax) {
+        mm_v.add(o);
+        mm_r.add(rr);
+      }
+    }
+  }
+  if (kMinMax) {
+    mm_v.flush(minmax + 0, minmax + 1);
+    mm_r.flush(minmax + 2, minmax + 3);
+  }
+}
+
+// K2: complex CW samples, beam innermost: one sample = B consecutive floats in each of re / im.
+// front = 10*log10(fscale * |nanmean_b x|^2); prx <= 0 -> NaN (calibrate_ek.py:581).
+template <int B, bool kRange, bool kMinMax>
+__global__ void __launch_bounds__(256) sv_complex_kernel(const float* __restrict__ re, const float* __restrict__ im,
+                                                         const epb_row* __restrict__ rows, float* __restrict__ out,
+                                                         float* __restrict__ rng, float* __restrict__ minmax,
+                                                         long long nrows, int R) {
+  MinMax mm_v, mm_r;
+  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const RowC rc(rows[row]);
+    const long long base = row * (long long)R;
+    for (int n = threadIdx.x; n < R; n += blockDim.x) {
+      float xr[B], xi[B];
+      if (B == 4) {
+        float4 a = ld_stream4(reinterpret_cast<const float4*>(re + (base + n) * 4));
+        float4 b = ld_stream4(reinterpret_cast<const float4*>(im + (base + n) * 4));
+        xr[0] = a.x, xr[1 % B] = a.y, xr[2 % B] = a.z, xr[3 % B] = a.w;
+        xi[0] = b.x, xi[1 % B] = b.y, xi[2 % B] = b.z, xi[3 % B] = b.w;
+      } else {
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+          xr[b] = ld_stream(re + (base + n) * B + b);
+          xi[b] = ld_stream(im + (base + n) * B + b);
+        }
+      }
+      float sr = 0.f, si = 0.f;
+      int cnt = 0;
+#pragma unroll
+      for (int b = 0; b < B; ++b) {
+        bool ok = (xr[b] == xr[b]) && (xi[b] == xi[b]);  // complex NaN if either part is NaN
+        sr += ok ? xr[b] : 0.f;
+        si += ok ? xi[b] : 0.f;
+        cnt += ok;
+      }
+      float inv = 1.f / (float)cnt;  // cnt == 0 -> inf*0 = NaN below, as nanmean of an all-NaN slice
+      float mr = sr * inv, mi = si * inv;
+      float prx = rc.fscale * (mr * mr + mi * mi);
+      float fr = (prx > 0.f) ? 10.f * log10f(prx) : CUDART_NAN_F;
+      float rr;
+      float o = sample_out(rc, n, fr, rr);
+      if (xr[0] != xr[0]) rr = CUDART_NAN_F;  // range.py:143-145 uses beam 0 of backscatter_r
+      out[base + n] = o;
+      if (kRange) rng[base + n] = rr;
+      if (kMinMax) {
+        mm_v.add(o);
+        mm_r.add(rr);
+      }
+    }
+  }
+  if (kMinMax) {
+    mm_v.flush(minmax + 0, minmax + 1);
+    mm_r.flush(minmax + 2, minmax + 3);
+  }
+}
+
+__global__ void minmax_init_kernel(float* m) {
+  m[0] = CUDART_INF_F;
+  m[1] = -CUDART_INF_F;
+  m[2] = CUDART_INF_F;
+  m[3] = -CUDART_INF_F;
+}
+
+}  // namespace
+
+extern "C" int epb_minmax_init(float* minmax, void* stream) {
+  EPB_REQUIRE(minmax, "NULL minmax");
+  minmax_init_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(minmax);
+  return epb_check_launch("epb_minmax_init");
+}
+
+extern "C" int epb_zero(void* ptr, epb_i64 nbytes, void* stream) {
+  EPB_REQUIRE(ptr && nbytes >= 0, "bad ptr/size");
+  if (cudaMemsetAsync(ptr, 0, (size_t)nbytes, (cudaStream_t)stream) != cudaSuccess)
+    return epb_check_launch("epb_zero");
+  return EPB_OK;
+}
+
+extern "C" int epb_sv_power(const float* x, const epb_row* rows, float* out, float* echo_range, float* minmax,
+                            epb_i64 C, epb_i64 P, epb_i64 R, void* stream) {
+  EPB_REQUIRE(x && rows && out, "NULL pointer");
+  EPB_REQUIRE(C > 0 && P > 0 && R > 0 && R < (1LL << 30), "bad shape");
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long nrows = C * P;
+  const int grid = (int)((nrows < (long long)epb_num_sms() * 8) ? nrows : (long long)epb_num_sms() * 8);
+  const bool vec = (R % 4 == 0) && (((uintptr_t)x | (uintptr_t)out | (uintptr_t)echo_range) % 16 == 0);
+#define EPB_LAUNCH(K)                                                                              \
+  do {                                                                                             \
+    if (echo_range && minmax)                                                                      \
+      K<true, true><<<grid, 256, 0, s>>>(x, rows, out, echo_range, minmax, nrows, (int)R);         \
+    else if (echo_range)                                                                           \
+      K<true, false><<<grid, 256, 0, s>>>(x, rows, out, echo_range, minmax, nrows, (int)R);        \
+    else if (minmax)                                                                               \
+      K<false, true><<<grid, 256, 0, s>>>(x, rows, out, echo_range, minmax, nrows, (int)R);        \
+    else                                                                                           \
+      K<false, false><<<grid, 256, 0, s>>>(x, rows, out, echo_range, minmax, nrows, (int)R);       \
+  } while (0)
+  if (vec)
+    EPB_LAUNCH(sv_power_vec4);
+  else
+    EPB_LAUNCH(sv_power_scalar);
+#undef EPB_LAUNCH
+  return epb_check_launch("epb_sv_power");
+}
+
+extern "C" int epb_sv_complex(const float* re, const float* im, const epb_row* rows, float* out, float* echo_range,
+                              float* minmax, epb_i64 C, epb_i64 P, epb_i64 R, int B, void* stream) {
+  EPB_REQUIRE(re && im && rows && out, "NULL pointer");
+  EPB_REQUIRE(C > 0 && P > 0 && R > 0 && R < (1LL << 30), "bad shape");
+  EPB_REQUIRE(B >= 1 && B <= 4, "B must be 1..4");
+  EPB_REQUIRE(B != 4 || (((uintptr_t)re | (uintptr_t)im) % 16 == 0), "4-beam planes must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long nrows = C * P;
+  const int grid = (int)((nrows < (long long)epb_num_sms() * 8) ? nrows : (long long)epb_num_sms() * 8);
+#define EPB_LAUNCH_B(BB)                                                                                   \
+  do {                                                                                                     \
+    if (echo_range && minmax)                                                                              \
+      sv_complex_kernel<BB, true, true><<<grid, 256, 0, s>>>(re, im, rows, out, echo_range, minmax, nrows, (int)R); \
+    else if (echo_range)                                                                                   \
+      sv_complex_kernel<BB, true, false><<<grid, 256, 0, s>>>(re, im, rows, out, echo_range, minmax, nrows, (int)R); \
+    else if (minmax)                                                                                       \
+      sv_complex_kernel<BB, false, true><<<grid, 256, 0, s>>>(re, im, rows, out, echo_range, minmax, nrows, (int)R); \
+    else                                                                                                   \
+      sv_complex_kernel<BB, false, false><<<grid, 256, 0, s>>>(re, im, rows, out, echo_range, minmax, nrows, (int)R); \
+  } while (0)
+  switch (B) {
+    case 1: EPB_LAUNCH_B(1); break;
+    case 2: EPB_LAUNCH_B(2); break;
+    case 3: EPB_LAUNCH_B(3); break;
+    default: EPB_LAUNCH_B(4); break;
+  }
+#undef EPB_LAUNCH_B
+  return epb_check_launch("epb_sv_complex");
+}

@@ -1,0 +1,508 @@
+"""Minimal labelled-array containers standing in for xarray.Dataset / DataArray / EchoData.
+
+xarray is not installable in this environment, so the drop-in API of
+``echopype_b200.calibrate / clean / commongrid`` is served through these duck-typed containers:
+``ds["Sv"]``, ``.dims``, ``.sizes``, ``.shape``, ``.attrs``, ``.coords``, ``.values``, ``.data``,
+``.isel``, ``.copy``, ``.assign_attrs``.  If a real xarray object is passed in, it is converted with
+:func:`as_dataset`; :meth:`Dataset.to_xarray` converts back when xarray is importable.
+
+A DataArray's ``.data`` is either a numpy array (host) or a torch CUDA tensor (device buffer).  Full-
+size products stay on the device until ``.values`` is read, mirroring how the reference returns lazy
+dask-backed arrays for chunked inputs.  ``.law`` optionally carries the exact range law of an
+``echo_range`` / ``depth`` variable produced by this package ("index-space decisions").
+"""
+
+from __future__ import annotations
+
+import copy as _copy
+
+import numpy as np
+
+try:  # torch is only used as the device-buffer type
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+def _is_tensor(x):
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+class DataArray:
+    __slots__ = ("data", "dims", "coords", "attrs", "name", "law")
+
+    def __init__(self, data, dims=None, coords=None, attrs=None, name=None, law=None):
+        if isinstance(data, DataArray):
+            dims = data.dims if dims is None else dims
+            coords = data.coords if coords is None else coords
+            attrs = data.attrs if attrs is None else attrs
+            name = data.name if name is None else name
+            data = data.data
+        if not _is_tensor(data):
+            data = np.asarray(data)
+        if dims is None:
+            if data.ndim != 0:
+                raise ValueError("dims are required for non-scalar data")
+            dims = ()
+        if isinstance(dims, str):
+            dims = (dims,)
+        dims = tuple(dims)
+        if len(dims) != data.ndim:
+            raise ValueError(f"dims {dims} do not match data of shape {tuple(data.shape)}")
+        self.data = data
+        self.dims = dims
+        self.coords = {}
+        if coords:
+            items = coords.items() if isinstance(coords, dict) else coords
+            for k, v in items:
+                if isinstance(v, DataArray):
+                    v = v.values
+                if isinstance(v, tuple) and len(v) >= 2 and isinstance(v[0], (str, tuple, list)):
+                    v = v[1]
+                v = np.asarray(v)
+                if k in dims and v.ndim == 1 and v.shape[0] != data.shape[dims.index(k)]:
+                    raise ValueError(f"coordinate {k!r} has length {v.shape[0]}, expected {data.shape[dims.index(k)]}")
+                self.coords[k] = v
+        self.attrs = dict(attrs) if attrs else {}
+        self.name = name
+        self.law = law
+
+    # ---- basic properties --------------------------------------------------------------------
+    @property
+    def shape(self):
+        return tuple(self.data.shape)
+
+    @property
+    def ndim(self):
+        return len(self.dims)
+
+    @property
+    def size(self):
+        return int(np.prod(self.shape)) if self.shape else 1
+
+    @property
+    def sizes(self):
+        return dict(zip(self.dims, self.shape))
+
+    @property
+    def dtype(self):
+        return self.data.dtype
+
+    @property
+    def nbytes(self):
+        if _is_tensor(self.data):
+            return self.data.numel() * self.data.element_size()
+        return self.data.nbytes
+
+    @property
+    def on_device(self):
+        return _is_tensor(self.data) and self.data.is_cuda
+
+    @property
+    def values(self):
+        if _is_tensor(self.data):
+            return self.data.detach().cpu().numpy()
+        return self.data
+
+    def __array__(self, dtype=None, copy=None):
+        v = self.values
+        return v.astype(dtype) if dtype is not None else v
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __repr__(self):
+        where = "cuda" if self.on_device else "host"
+        return f"<DataArray {self.name or ''} {self.sizes} {self.dtype} [{where}]>"
+
+    def item(self):
+        return self.values.item()
+
+    def __float__(self):
+        return float(self.values)
+
+    # ---- labelled access -----------------------------------------------------------------------
+    def __getitem__(self, key):
+        if isinstance(key, str):
+            if key in self.coords:
+                v = self.coords[key]
+                return DataArray(v, dims=(key,) if v.ndim == 1 else (), coords={key: v} if v.ndim == 1 else None, name=key)
+            raise KeyError(key)
+        out = self.values[key]
+        return out
+
+    def isel(self, **indexers):
+        idx = []
+        new_dims = []
+        new_coords = dict(self.coords)
+        for d in self.dims:
+            sel = indexers.get(d, slice(None))
+            idx.append(sel)
+            scalar = isinstance(sel, (int, np.integer))
+            if not scalar:
+                new_dims.append(d)
+            if d in new_coords and np.ndim(new_coords[d]) == 1:
+                new_coords[d] = new_coords[d][sel]
+                if scalar:
+                    new_coords.pop(d)
+        data = self.data[tuple(idx)]
+        return DataArray(data, dims=new_dims, coords=new_coords, attrs=self.attrs, name=self.name)
+
+    def sel(self, **labels):
+        indexers = {}
+        for d, lab in labels.items():
+            cv = self.coords[d]
+            if isinstance(lab, (list, tuple, np.ndarray)):
+                indexers[d] = [int(np.flatnonzero(cv == v)[0]) for v in lab]
+            else:
+                hit = np.flatnonzero(cv == lab)
+                if hit.size == 0:
+                    raise KeyError(lab)
+                indexers[d] = int(hit[0])
+        return self.isel(**indexers)
+
+    def transpose(self, *dims):
+        perm = [self.dims.index(d) for d in dims]
+        data = self.data.permute(*perm) if _is_tensor(self.data) else np.transpose(self.data, perm)
+        return DataArray(data, dims=dims, coords=self.coords, attrs=self.attrs, name=self.name)
+
+    def copy(self, deep=False):
+        data = self.data
+        if deep:
+            data = data.clone() if _is_tensor(data) else data.copy()
+        return DataArray(data, self.dims, dict(self.coords), dict(self.attrs), self.name, self.law)
+
+    def assign_attrs(self, *args, **kw):
+        out = self.copy()
+        for a in args:
+            out.attrs.update(a)
+        out.attrs.update(kw)
+        return out
+
+    def astype(self, dtype):
+        out = self.copy()
+        out.data = self.values.astype(dtype)
+        return out
+
+    def isnull(self):
+        v = self.values
+        m = np.isnan(v) if v.dtype.kind in "fc" else (np.isnat(v) if v.dtype.kind in "mM" else np.zeros(v.shape, bool))
+        return DataArray(m, self.dims, self.coords, name=self.name)
+
+    def _reduce(self, fn_host, fn_dev):
+        if _is_tensor(self.data):
+            return DataArray(np.asarray(fn_dev(self.data).item()))
+        return DataArray(np.asarray(fn_host(self.data)))
+
+    def min(self, skipna=True):
+        if _is_tensor(self.data):
+            d = self.data
+            if d.is_floating_point():
+                m = torch.isnan(d)
+                if bool(m.all()):
+                    return DataArray(np.asarray(np.nan))
+                d = torch.where(m, torch.full_like(d, float("inf")), d)
+            return DataArray(np.asarray(d.min().item()))
+        import warnings
+
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", category=RuntimeWarning)
+            return DataArray(np.asarray((np.nanmin if skipna and self.data.dtype.kind == "f" else np.min)(self.data)))
+
+    def max(self, skipna=True):
+        if _is_tensor(self.data):
+            d = self.data
+            if d.is_floating_point():
+                m = torch.isnan(d)
+                if bool(m.all()):
+                    return DataArray(np.asarray(np.nan))
+                d = torch.where(m, torch.full_like(d, float("-inf")), d)
+            return DataArray(np.asarray(d.max().item()))
+        import warnings
+
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", category=RuntimeWarning)
+            return DataArray(np.asarray((np.nanmax if skipna and self.data.dtype.kind == "f" else np.max)(self.data)))
+
+    # arithmetic for the small host-side parameter arrays (dims-aware broadcasting, no alignment)
+    def _binop(self, other, op):
+        a_dims, a = self.dims, self.values
+        if isinstance(other, DataArray):
+            b_dims, b = other.dims, other.values
+            coords = {**other.coords, **self.coords}
+        else:
+            b_dims, b = (), np.asarray(other)
+            coords = dict(self.coords)
+        out_dims = tuple(a_dims) + tuple(d for d in b_dims if d not in a_dims)
+
+        def expand(x, dims):
+            perm_src = [d for d in out_dims if d in dims]
+            x = np.transpose(x, [dims.index(d) for d in perm_src]) if x.ndim else x
+            shape = [x.shape[perm_src.index(d)] if d in dims else 1 for d in out_dims]
+            return x.reshape(shape) if x.ndim else x
+
+        with np.errstate(all="ignore"):
+            res = op(expand(a, a_dims), expand(b, b_dims))
+        coords = {k: v for k, v in coords.items() if k in out_dims or np.ndim(v) == 0}
+        return DataArray(res, out_dims, coords)
+
+    def __add__(self, o):
+        return self._binop(o, np.add)
+
+    def __radd__(self, o):
+        return self._binop(o, lambda a, b: b + a)
+
+    def __sub__(self, o):
+        return self._binop(o, np.subtract)
+
+    def __rsub__(self, o):
+        return self._binop(o, lambda a, b: b - a)
+
+    def __mul__(self, o):
+        return self._binop(o, np.multiply)
+
+    def __rmul__(self, o):
+        return self._binop(o, lambda a, b: b * a)
+
+    def __truediv__(self, o):
+        return self._binop(o, np.divide)
+
+    def __rtruediv__(self, o):
+        return self._binop(o, lambda a, b: b / a)
+
+    def __pow__(self, o):
+        return self._binop(o, np.power)
+
+    def __neg__(self):
+        return DataArray(-self.values, self.dims, self.coords, self.attrs, self.name)
+
+
+def _to_dataarray(value, name=None):
+    if isinstance(value, DataArray):
+        return value
+    if isinstance(value, tuple):
+        dims, data = value[0], value[1]
+        attrs = value[2] if len(value) > 2 else None
+        return DataArray(data, dims=dims, attrs=attrs, name=name)
+    if hasattr(value, "dims") and hasattr(value, "values"):  # real xarray.DataArray
+        coords = {k: np.asarray(v.values) for k, v in value.coords.items() if k in value.dims}
+        return DataArray(np.asarray(value.values), dims=tuple(value.dims), coords=coords, attrs=dict(value.attrs), name=name)
+    return DataArray(np.asarray(value), dims=(), name=name)
+
+
+class Dataset:
+    """Dict of named DataArrays sharing dimension coordinates (stand-in for xarray.Dataset)."""
+
+    def __init__(self, data_vars=None, coords=None, attrs=None):
+        self._vars = {}
+        self._coords = {}
+        self.attrs = dict(attrs) if attrs else {}
+        for k, v in (coords or {}).items():
+            self._set_coord(k, v)
+        for k, v in (data_vars or {}).items():
+            self[k] = v
+
+    def _set_coord(self, name, value):
+        if isinstance(value, tuple) and len(value) >= 2 and isinstance(value[0], (str, tuple, list)):
+            dims, data = value[0], value[1]
+            attrs = value[2] if len(value) > 2 else None
+            da = DataArray(np.asarray(data), dims=dims, attrs=attrs, name=name)
+        elif isinstance(value, DataArray):
+            da = DataArray(value.values, value.dims, attrs=value.attrs, name=name)
+        else:
+            arr = np.asarray(value)
+            da = DataArray(arr, dims=(name,) if arr.ndim == 1 else (), name=name)
+        self._coords[name] = da
+
+    # ---- mapping interface ------------------------------------------------------------------------
+    def __getitem__(self, key):
+        if isinstance(key, (list, tuple)):
+            return Dataset({k: self[k] for k in key}, coords=self._coords, attrs=self.attrs)
+        if key in self._vars:
+            da = self._vars[key]
+            cs = {d: self._coords[d].values for d in da.dims if d in self._coords}
+            cs.update({k: v for k, v in da.coords.items() if k not in cs})
+            out = DataArray(da.data, da.dims, cs, da.attrs, key, da.law)
+            out.attrs = da.attrs  # share, so ds["x"].attrs.update(...) sticks like xarray
+            return out
+        if key in self._coords:
+            c = self._coords[key]
+            out = DataArray(c.data, c.dims, {key: c.values} if c.dims == (key,) else None, None, key)
+            out.attrs = c.attrs
+            return out
+        raise KeyError(key)
+
+    def __setitem__(self, key, value):
+        da = _to_dataarray(value, key)
+        for d, n in zip(da.dims, da.shape):
+            if d in self._coords and self._coords[d].dims == (d,) and self._coords[d].shape[0] != n:
+                raise ValueError(f"conflicting sizes for dimension {d!r}: {n} vs {self._coords[d].shape[0]}")
+            have = self.sizes.get(d)
+            if have is not None and have != n:
+                raise ValueError(f"conflicting sizes for dimension {d!r}: {n} vs {have}")
+        for d in da.dims:
+            if d in da.coords and d not in self._coords:
+                self._set_coord(d, da.coords[d])
+        if key in self._coords and da.dims == (key,):
+            self._set_coord(key, da)
+            return
+        stored = DataArray(da.data, da.dims, None, None, key, da.law)
+        stored.attrs = da.attrs
+        self._vars[key] = stored
+
+    def __contains__(self, key):
+        return key in self._vars or key in self._coords
+
+    def __iter__(self):
+        return iter(self._vars)
+
+    def __repr__(self):
+        lines = [f"<Dataset sizes={self.sizes}>"]
+        for k, v in self._coords.items():
+            lines.append(f"  * {k} {v.dims} {v.dtype}")
+        for k, v in self._vars.items():
+            lines.append(f"    {k} {v.dims} {v.dtype}{' [cuda]' if v.on_device else ''}")
+        return "\n".join(lines)
+
+    def keys(self):
+        return self._vars.keys()
+
+    @property
+    def data_vars(self):
+        return {k: self[k] for k in self._vars}
+
+    @property
+    def variables(self):
+        return {**{k: self[k] for k in self._coords}, **self.data_vars}
+
+    @property
+    def coords(self):
+        return {k: self[k] for k in self._coords}
+
+    @property
+    def sizes(self):
+        out = {}
+        for da in list(self._vars.values()) + list(self._coords.values()):
+            for d, n in zip(da.dims, da.shape):
+                out.setdefault(d, n)
+        return out
+
+    dims = sizes
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def copy(self, deep=False):
+        out = Dataset(attrs=_copy.copy(self.attrs))
+        out._coords = {k: v.copy(deep) for k, v in self._coords.items()}
+        out._vars = {k: v.copy(deep) for k, v in self._vars.items()}
+        return out
+
+    def assign_attrs(self, *args, **kw):
+        out = self.copy()
+        for a in args:
+            out.attrs.update(a)
+        out.attrs.update(kw)
+        return out
+
+    def assign(self, **kw):
+        out = self.copy()
+        for k, v in kw.items():
+            out[k] = v
+        return out
+
+    def assign_coords(self, **kw):
+        out = self.copy()
+        for k, v in kw.items():
+            out._set_coord(k, v)
+        return out
+
+    def drop_vars(self, names, errors="raise"):
+        names = [names] if isinstance(names, str) else list(names)
+        out = self.copy()
+        for n in names:
+            if n in out._vars:
+                del out._vars[n]
+            elif n in out._coords:
+                del out._coords[n]
+            elif errors == "raise":
+                raise ValueError(f"cannot drop {n!r}: not found")
+        return out
+
+    def drop_dims(self, names):
+        names = [names] if isinstance(names, str) else list(names)
+        out = self.copy()
+        out._vars = {k: v for k, v in out._vars.items() if not set(v.dims) & set(names)}
+        out._coords = {k: v for k, v in out._coords.items() if not set(v.dims) & set(names)}
+        return out
+
+    def isel(self, **indexers):
+        out = Dataset(attrs=dict(self.attrs))
+        for k, c in self._coords.items():
+            if set(c.dims) & set(indexers):
+                c = c.isel(**{d: s for d, s in indexers.items() if d in c.dims})
+            out._coords[k] = c
+        for k, v in self._vars.items():
+            if set(v.dims) & set(indexers):
+                law = v.law
+                v = DataArray(v.data, v.dims, None, v.attrs, k).isel(**{d: s for d, s in indexers.items() if d in v.dims})
+                v.coords = {}
+                _ = law  # a sliced array no longer matches its row table
+            out._vars[k] = v
+        return out
+
+    def pipe(self, fn, *args, **kw):
+        return fn(self, *args, **kw)
+
+    def to_xarray(self):  # pragma: no cover - xarray is not installed in the build image
+        import xarray as xr
+
+        return xr.Dataset(
+            {k: (v.dims, v.values, v.attrs) for k, v in self._vars.items()},
+            coords={k: (v.dims, v.values, v.attrs) for k, v in self._coords.items()},
+            attrs=self.attrs,
+        )
+
+
+def as_dataset(obj):
+    """Accept a Dataset, a real xarray.Dataset, or a mapping name -> (dims, data[, attrs])."""
+    if isinstance(obj, Dataset):
+        return obj
+    if hasattr(obj, "data_vars") and hasattr(obj, "coords"):
+        ds = Dataset(attrs=dict(getattr(obj, "attrs", {})))
+        for k, c in obj.coords.items():
+            ds._set_coord(k, (tuple(c.dims), np.asarray(c.values), dict(c.attrs)))
+        for k, v in obj.data_vars.items():
+            ds[k] = (tuple(v.dims), np.asarray(v.values), dict(v.attrs))
+        return ds
+    if isinstance(obj, dict):
+        return Dataset(obj)
+    raise TypeError(f"cannot interpret {type(obj)} as a Dataset")
+
+
+class EchoData:
+    """Thin stand-in for echopype.echodata.EchoData (echodata/echodata.py:327-335): a dict of
+    SONAR-netCDF4 groups ("Sonar/Beam_group1", "Environment", "Vendor_specific", "Platform", "Sonar")."""
+
+    def __init__(self, sonar_model, groups=None, source_file=None, converted_raw_path=None):
+        self.sonar_model = sonar_model
+        self._groups = {k: as_dataset(v) for k, v in (groups or {}).items()}
+        self.source_file = source_file
+        self.converted_raw_path = converted_raw_path
+
+    def __getitem__(self, key):
+        if key not in self._groups:
+            if key in ("Platform", "Top-level", "Sonar", "Provenance"):
+                return Dataset()
+            raise KeyError(key)
+        return self._groups[key]
+
+    def __setitem__(self, key, value):
+        self._groups[key] = as_dataset(value)
+
+    def __contains__(self, key):
+        return key in self._groups
+
+    @property
+    def group_paths(self):
+        return list(self._groups)

@@ -1,0 +1,209 @@
+"""Thin typed wrappers around the C ABI (include/epb200.h): allocate outputs as torch CUDA tensors,
+pass raw pointers + the current torch stream, raise on any error.  No arithmetic happens here."""
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .device import ParamPack, empty, ptr, require_cuda, stream
+
+CAL = {"Sv": 0, "TS": 1}
+SONAR_EX60, SONAR_EX80 = 0, 1
+
+
+def alloc_rows(C, P, device=None):
+    return torch.empty(int(C) * int(P) * 128, dtype=torch.uint8, device=device or require_cuda())
+
+
+def rows_ek_power(C, P, R, sonar, cal_type, prm, is_gpt=None):
+    """prm: dict with sample_interval, sound_speed, sound_absorption, transmit_duration_nominal, transmit_power,
+    gain_correction, sa_correction, equivalent_beam_angle, frequency_nominal, tau_effective (host arrays)."""
+    dev = require_cuda()
+    pk = ParamPack(C, P, dev)
+    rows = alloc_rows(C, P, dev)
+    sv = cal_type == "Sv"
+    null = ParamPack.null()
+    gpt = pk.vec(np.asarray(is_gpt, dtype=np.uint8), torch.uint8) if is_gpt is not None else None
+    _lib.call(
+        "epb_rows_ek_power", ptr(rows), C, P, R, sonar, CAL[cal_type],
+        pk.cp(prm["sample_interval"]), pk.cp(prm["sound_speed"]), pk.cp(prm["sound_absorption"]),
+        pk.cp(prm["transmit_duration_nominal"]), pk.cp(prm["transmit_power"]), pk.cp(prm["gain_correction"]),
+        pk.cp(prm["sa_correction"]) if sv else null, pk.cp(prm["equivalent_beam_angle"]) if sv else null,
+        pk.cp(prm["frequency_nominal"]), pk.cp(prm["tau_effective"]) if sv else null, gpt, stream(),
+    )
+    rows._keep = pk  # parameters must outlive the asynchronous launch
+    return rows
+
+
+def rows_azfp(C, P, R, cal_type, prm):
+    dev = require_cuda()
+    pk = ParamPack(C, P, dev)
+    rows = alloc_rows(C, P, dev)
+    _lib.call(
+        "epb_rows_azfp", ptr(rows), C, P, R, CAL[cal_type], pk.cp(prm["sound_speed"]), pk.cp(prm["sound_absorption"]),
+        pk.cp(prm["transmit_duration_nominal"]), pk.vec(prm["N"]), pk.vec(prm["f_dig"]), pk.vec(prm["L"]),
+        pk.vec(prm["EL"]), pk.vec(prm["DS"]), pk.vec(prm["TVR"]), pk.vec(prm["VTX0"]),
+        pk.vec(prm["equivalent_beam_angle"]), pk.vec(prm["Sv_offset"]), stream(),
+    )
+    rows._keep = pk
+    return rows
+
+
+def rows_ek80_complex(C, P, R, cal_type, waveform_bb, n_beam, prm, is_gpt=None):
+    dev = require_cuda()
+    pk = ParamPack(C, P, dev)
+    rows = alloc_rows(C, P, dev)
+    sv = cal_type == "Sv"
+    null = ParamPack.null()
+    gpt = pk.vec(np.asarray(is_gpt, dtype=np.uint8), torch.uint8) if is_gpt is not None else None
+    _lib.call(
+        "epb_rows_ek80_complex", ptr(rows), C, P, R, CAL[cal_type], int(bool(waveform_bb)), int(n_beam),
+        pk.cp(prm["sample_interval"]), pk.cp(prm["sound_speed"]), pk.cp(prm["sound_absorption"]),
+        pk.cp(prm["transmit_duration_nominal"]), pk.cp(prm["transmit_power"]), pk.cp(prm["gain_correction"]),
+        pk.cp(prm["sa_correction"]) if (sv and not waveform_bb) else null,
+        pk.cp(prm["equivalent_beam_angle"]) if sv else null, pk.cp(prm["freq_center"]),
+        pk.cp(prm["tau_effective"]) if sv else null, pk.cp(prm["impedance_transducer"]),
+        pk.cp(prm["impedance_transceiver"]), gpt, stream(),
+    )
+    rows._keep = pk
+    return rows
+
+
+def new_minmax(device=None):
+    mm = torch.empty(4, dtype=torch.float32, device=device or require_cuda())
+    _lib.call("epb_minmax_init", ptr(mm), stream())
+    return mm
+
+
+def sv_power(x, rows, C, P, R, want_range=True, want_minmax=False, out=None, rng=None):
+    out = out if out is not None else empty((C, P, R), device=x.device)
+    rng = rng if rng is not None else (empty((C, P, R), device=x.device) if want_range else None)
+    mm = new_minmax(x.device) if want_minmax else None
+    _lib.call("epb_sv_power", ptr(x), ptr(rows), ptr(out), ptr(rng), ptr(mm), C, P, R, stream())
+    return out, rng, mm
+
+
+def sv_complex(re, im, rows, C, P, R, B, want_range=True, want_minmax=False):
+    out = empty((C, P, R), device=re.device)
+    rng = empty((C, P, R), device=re.device) if want_range else None
+    mm = new_minmax(re.device) if want_minmax else None
+    _lib.call("epb_sv_complex", ptr(re), ptr(im), ptr(rows), ptr(out), ptr(rng), ptr(mm), C, P, R, int(B), stream())
+    return out, rng, mm
+
+
+def pulse_compress_sv(re, im, replicas, rows, C, P, R, B, want_range=True, want_pc=False, want_minmax=False):
+    """replicas: list of per-channel complex transmit replicas (host, complex128)."""
+    dev = re.device
+    offs = np.zeros(C + 1, dtype=np.int32)
+    for c, tx in enumerate(replicas):
+        offs[c + 1] = offs[c] + len(tx)
+    cat = np.concatenate([np.asarray(tx, dtype=np.complex128) for tx in replicas])
+    rep = torch.from_numpy(np.ascontiguousarray(np.stack([cat.real, cat.imag], axis=1).astype(np.float32))).to(dev)
+    inv_norm = torch.from_numpy(np.asarray([1.0 / np.linalg.norm(tx) ** 2 for tx in replicas], dtype=np.float64)).to(dev)
+    out = empty((C, P, R), device=dev)
+    rng = empty((C, P, R), device=dev) if want_range else None
+    pc = empty((C, P, R, 2), device=dev) if want_pc else None
+    mm = new_minmax(dev) if want_minmax else None
+    h_off = (ctypes.c_int * (C + 1))(*offs.tolist())
+    _lib.call(
+        "epb_pulse_compress_sv", ptr(re), ptr(im), ptr(rep), h_off, ptr(inv_norm), ptr(rows), ptr(out), ptr(rng),
+        ptr(pc), ptr(mm), C, P, R, int(B), stream(),
+    )
+    out._keep = (rep, inv_norm)
+    return out, rng, pc, mm
+
+
+def noise_estimate(Sv, echo_range, alpha_cp, pack, C, P, R, ping_num, range_sample_num, noise_max=None):
+    nP = -(-P // ping_num)
+    noise = empty((C, nP), device=Sv.device)
+    nm = float("nan") if noise_max is None else float(noise_max)
+    _lib.call(
+        "epb_noise_estimate", ptr(Sv), ptr(echo_range), alpha_cp, ptr(noise), C, P, R, int(ping_num),
+        int(range_sample_num), ctypes.c_float(nm), stream(),
+    )
+    noise._keep = pack
+    return noise
+
+
+def noise_apply(Sv, echo_range, alpha_cp, pack, noise, C, P, R, ping_num, snr, want_noise=True, want_corr=True, want_minmax=True):
+    sn = empty((C, P, R), device=Sv.device) if want_noise else None
+    sc = empty((C, P, R), device=Sv.device) if want_corr else None
+    mm = new_minmax(Sv.device) if want_minmax else None
+    _lib.call(
+        "epb_noise_apply", ptr(Sv), ptr(echo_range), alpha_cp, ptr(noise), ptr(sn), ptr(sc), ptr(mm), C, P, R,
+        int(ping_num), ctypes.c_float(float(snr)), stream(),
+    )
+    if mm is not None:
+        mm._keep = pack
+    return sn, sc, mm
+
+
+def new_acc(C, nX, nR, device=None):
+    acc = torch.empty((int(C), int(nX), int(nR), 4), dtype=torch.float64, device=device or require_cuda())
+    _lib.call("epb_zero", ptr(acc), acc.numel() * 8, stream())
+    return acc
+
+
+def bin_reduce(Sv, range_var, xbin, r_edges, acc, C, P, R, nX, closed_right=False, with_height=False):
+    nR = int(r_edges.numel()) - 1
+    is64 = 1 if range_var.dtype == torch.float64 else 0
+    _lib.call(
+        "epb_bin_reduce", ptr(Sv), ptr(range_var), is64, ptr(xbin), ptr(r_edges), nR, int(closed_right),
+        int(with_height), ptr(acc), C, P, R, nX, stream(),
+    )
+    return acc
+
+
+def bin_finalize(acc, skipna=True, fill_value=float("nan"), to_db=True, want_height=False):
+    C, nX, nR, _ = acc.shape
+    out = empty((C, nX, nR), device=acc.device)
+    h = torch.empty((C, nX, nR), dtype=torch.float64, device=acc.device) if want_height else None
+    _lib.call(
+        "epb_bin_finalize", ptr(acc), ptr(out), ptr(h), C * nX * nR, int(bool(skipna)), ctypes.c_float(float(fill_value)),
+        int(bool(to_db)), stream(),
+    )
+    return out, h
+
+
+def coarsen(Sv, echo_range, C, P, R, ping_num, range_sample_num):
+    nP, nR = -(-P // ping_num), -(-R // range_sample_num)
+    out = empty((C, nP, nR), device=Sv.device)
+    er = empty((C, nP, nR), device=Sv.device) if echo_range is not None else None
+    _lib.call("epb_coarsen", ptr(Sv), ptr(echo_range), ptr(out), ptr(er), C, P, R, int(ping_num), int(range_sample_num), stream())
+    return out, er
+
+
+def bin_bounds(rows, r_edges, C, P, R, closed_right=False, depth_off=None, depth_scale=None, depth_sign=1.0):
+    nR = int(r_edges.numel()) - 1
+    b = torch.empty((int(C) * int(P), nR + 1), dtype=torch.int32, device=rows.device)
+    _lib.call(
+        "epb_bin_bounds", ptr(rows), ptr(r_edges), nR, int(closed_right), ptr(depth_off), ptr(depth_scale),
+        ctypes.c_double(float(depth_sign)), ptr(b), C, P, R, stream(),
+    )
+    return b
+
+
+def pipeline_power_mvbs(x, rows, bounds, xbin, nR, acc, C, P, R, nX, ping_num, range_sample_num, noise_max=None,
+                        snr=3.0, noise_out=None, Sv=None, echo_range=None, Sv_noise=None, Sv_corrected=None):
+    nm = float("nan") if noise_max is None else float(noise_max)
+    _lib.call(
+        "epb_pipeline_power_mvbs", ptr(x), ptr(rows), ptr(bounds), ptr(xbin), int(nR), ptr(acc), ptr(noise_out),
+        ptr(Sv), ptr(echo_range), ptr(Sv_noise), ptr(Sv_corrected), C, P, R, nX, int(ping_num), int(range_sample_num),
+        ctypes.c_float(nm), ctypes.c_float(float(snr)), stream(),
+    )
+    return acc
+
+
+def synth_fill(shape_cpr, kind, seed, inner=1, ping_offset=0, nan_tail=0.005, scale=1.0, device=None, out=None):
+    C, P, R = (int(s) for s in shape_cpr)
+    dev = device or require_cuda()
+    full = (C, P, R) if inner == 1 else (C, P, R, inner)
+    out = out if out is not None else empty(full, device=dev)
+    q16 = int(round(nan_tail * 65536))
+    _lib.call(
+        "epb_synth_fill", ptr(out), C, P, R, int(inner), int(kind), ctypes.c_ulonglong(int(seed)), int(ping_offset),
+        ctypes.c_uint(q16), ctypes.c_float(float(scale)), stream(),
+    )
+    return out

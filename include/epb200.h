@@ -1,0 +1,193 @@
+/*
+ * epb200.h - C ABI of libepb200.so: the B200 (sm_100a) implementation of echopype's
+ * calibrate -> clean -> commongrid array-compute path.
+ *
+ * echopype (pure Python) has no FFI of its own; each entry point below replaces one internal seam of
+ * the reference where a whole (channel, ping_time, range_sample) array changes hands.  The reference
+ * interface each function stands in for is cited as file:line under /root/reference/echopype.
+ * INTEGRATION.md shows the ctypes stub a maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name starts with h_; the caller owns all memory;
+ *     the library never allocates or frees; scratch sizes are returned by epb_*_workspace_bytes;
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream)
+ *     of the CURRENT device and never synchronise;
+ *   - arrays are C-contiguous in the reference's dimension order (channel, ping_time, range_sample
+ *     [, beam]); C, P, R, B are the sizes of those dimensions;
+ *   - return value 0 = ok, negative = EPB_E_* ; a message is available from epb_last_error()
+ *     (thread-local); no C++ exception crosses the boundary;
+ *   - NaN (quiet) marks invalid samples everywhere, as in the reference.
+ */
+#ifndef EPB200_H
+#define EPB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EPB_VERSION 100 /* 0.1.0 */
+
+#define EPB_OK 0
+#define EPB_E_BADARG (-1)   /* NULL pointer, non-positive size, unsupported option            */
+#define EPB_E_CUDA (-2)     /* kernel launch / runtime error (cudaGetLastError text available) */
+#define EPB_E_UNSUPPORTED (-3)
+
+typedef long long epb_i64;
+
+/* A (channel, ping_time) float64 parameter on the device with element strides; stride 0 broadcasts
+ * (scalar: sc = sp = 0; per-channel: sp = 0). */
+typedef struct epb_cp {
+  const double* ptr;
+  epb_i64 sc;
+  epb_i64 sp;
+} epb_cp;
+
+/* Per-(channel, ping) row record (128 bytes) consumed by every sample kernel.  It carries
+ *   (1) the EXACT float64 range law, evaluated with the reference's operation order, used only for
+ *       index-space decisions (first sample with R' > 0, bin boundaries) so that those decisions are
+ *       bit-identical with the float64 reference:
+ *         law 0 (EK,  calibrate/range.py:138):   R(n) = ((n * p0) * p1) / 2          p0 = sample_interval, p1 = sound_speed
+ *         law 1 (AZFP, calibrate/range.py:81-89): R(n) = (p0 + p1 * (k / p2 + p3)) - p4,  k = (2(n+1)-1)*N - 1
+ *                                                 p0 = c*L/(2f), p1 = c/4, p2 = f, p3 = tau, p4 = TS offset, N = azfp_N
+ *   (2) the affine value form R = r0 + a*n and the folded calibration constants:
+ *         out = front(x) + slog*log10(R') + two_alpha*R' - K,   R' = (R - off1) - off2
+ *         front(x) = x*fscale + foff (power dB / AZFP counts) or 10*log10(fscale*|mean_beam x|^2) (complex)
+ */
+typedef struct epb_row {
+  double p0, p1, p2, p3, p4;
+  double off1, off2;
+  double r0, a;
+  double two_alpha;
+  double K;
+  double fscale, foff;
+  double slog;
+  int n_start; /* first n with R' > 0 under the exact law (R when none); 0 when the variant has no guard */
+  int law;     /* 0 EK, 1 AZFP; bit 8 set: echo_range is NaN where the input sample is NaN (EK) */
+  int azfp_N;
+  int reserved;
+} epb_row;
+
+#define EPB_LAW_EK 0
+#define EPB_LAW_AZFP 1
+#define EPB_LAW_NANRANGE 256
+
+#define EPB_CAL_SV 0
+#define EPB_CAL_TS 1
+#define EPB_SONAR_EX60 0 /* EK60 / ES70: TVG offset = 2 samples (range.py:176-178)                 */
+#define EPB_SONAR_EX80 1 /* EK80 / ES80 / EA640: c*tau/4, GPT channels additionally 2 samples (:180-199) */
+
+const char* epb_last_error(void);
+int epb_version(void);
+
+/* ---- row setup (replaces the (channel,ping) parameter broadcasting in CalibrateEK._cal_power_samples,
+ *      calibrate/calibrate_ek.py:98-183, range_mod_TVG_EK calibrate/range.py:160-201) -------------------- */
+int epb_rows_ek_power(epb_row* rows, epb_i64 C, epb_i64 P, epb_i64 R, int sonar, int cal_type,
+                      epb_cp sample_interval, epb_cp sound_speed, epb_cp absorption,
+                      epb_cp tau_nominal, epb_cp transmit_power, epb_cp gain, epb_cp sa_correction,
+                      epb_cp equivalent_beam_angle, epb_cp frequency_nominal, epb_cp tau_effective,
+                      const unsigned char* is_gpt /* [C] or NULL */, void* stream);
+
+/* calibrate/calibrate_azfp.py:49-111 + compute_range_AZFP calibrate/range.py:11-95.
+ * Per-channel arrays are [C] float64 on the device. */
+int epb_rows_azfp(epb_row* rows, epb_i64 C, epb_i64 P, epb_i64 R, int cal_type, epb_cp sound_speed,
+                  epb_cp absorption, epb_cp tau_nominal, const double* N, const double* f_dig,
+                  const double* L, const double* EL, const double* DS, const double* TVR,
+                  const double* VTX0, const double* psi_linear, const double* Sv_offset, void* stream);
+
+/* CalibrateEK80._cal_complex_samples calibrate/calibrate_ek.py:532-659 (constants of :613-637 and the
+ * received-power scale of :483-490).  `gain` already includes the BB B_theta_phi term, `psi` the BB
+ * frequency scaling; waveform_bb != 0 drops the 2*Sa term. */
+int epb_rows_ek80_complex(epb_row* rows, epb_i64 C, epb_i64 P, epb_i64 R, int cal_type, int waveform_bb,
+                          int n_beam, epb_cp sample_interval, epb_cp sound_speed, epb_cp absorption,
+                          epb_cp tau_nominal, epb_cp transmit_power, epb_cp gain, epb_cp sa_correction,
+                          epb_cp psi, epb_cp freq_center, epb_cp tau_effective, epb_cp z_et, epb_cp z_er,
+                          const unsigned char* is_gpt, void* stream);
+
+/* ---- K1: fused per-sample Sv/TS for power samples (CalibrateEK._cal_power_samples calibrate_ek.py:79,
+ *      CalibrateAZFP._cal_power_samples calibrate_azfp.py:49, compute_range_EK range.py:98) -------------
+ * out, echo_range: [C,P,R] float32 (echo_range may be NULL).  minmax: NULL or 4 floats
+ * {min(out), max(out), min(range), max(range)} updated atomically (initialise with epb_minmax_init). */
+int epb_sv_power(const float* backscatter_r, const epb_row* rows, float* out, float* echo_range,
+                 float* minmax, epb_i64 C, epb_i64 P, epb_i64 R, void* stream);
+
+/* ---- K2: complex CW samples (CalibrateEK80._get_power_from_complex calibrate_ek.py:456-505 without
+ *      pulse compression + _cal_complex_samples).  re/im: [C,P,R,B] float32, B <= 4. ------------------- */
+int epb_sv_complex(const float* re, const float* im, const epb_row* rows, float* out, float* echo_range,
+                   float* minmax, epb_i64 C, epb_i64 P, epb_i64 R, int B, void* stream);
+
+/* ---- K3: broadband pulse compression + Sv/TS epilogue (compress_pulse calibrate/ek80_complex.py:316,
+ *      _convolve_per_channel :285, get_norm_fac :372, then calibrate_ek.py:483-490,:581,:613-637).
+ * replica: per-channel conj-free transmit replicas tx[c][k] as float2, concatenated; replica_off[C+1]
+ * (host array) gives each channel's start; inv_norm[C] = 1/||tx||^2 (device, float64).
+ * pc_out (optional): [C,P,R] float2 beam-averaged normalised pulse-compressed signal. */
+int epb_pulse_compress_sv(const float* re, const float* im, const float* replica /* float2 */,
+                          const int* h_replica_off, const double* inv_norm, const epb_row* rows,
+                          float* out, float* echo_range, float* pc_out, float* minmax, epb_i64 C,
+                          epb_i64 P, epb_i64 R, int B, void* stream);
+
+/* ---- K4/K5: De Robertis & Higginbottom background noise (estimate_background_noise clean/api.py:362,
+ *      remove_background_noise :436) on materialised Sv / echo_range -------------------------------------
+ * noise: [C, ceil(P/ping_num)] float32 (dB).  alpha: (channel,ping) absorption.  noise_max: NaN = no cap. */
+int epb_noise_estimate(const float* Sv, const float* echo_range, epb_cp absorption, float* noise,
+                       epb_i64 C, epb_i64 P, epb_i64 R, int ping_num, int range_sample_num,
+                       float noise_max, void* stream);
+/* Sv_noise and Sv_corrected may each be NULL.  snr_threshold in dB. */
+int epb_noise_apply(const float* Sv, const float* echo_range, epb_cp absorption, const float* noise,
+                    float* Sv_noise, float* Sv_corrected, float* minmax /* 4 floats or NULL */,
+                    epb_i64 C, epb_i64 P, epb_i64 R, int ping_num, float snr_threshold, void* stream);
+
+/* ---- K6: linear-domain bin reduction for MVBS / NASC (_groupby_x_along_channels
+ *      commongrid/utils.py:504-628 = flox xarray_reduce; compute_raw_NASC :97-207) ----------------------
+ * xbin: [P] int32 bin of each ping along ping_time / distance (-1 = outside every bin).
+ * Generic form: range values given per sample (float32 or float64), edges [nR+1] float64.
+ * acc: [C, nX, nR, 4] float64 accumulators {sum of 10^(Sv/10), #non-NaN, #NaN members, sum of height
+ * differences (NASC)}; zero it with epb_zero before the first call; several calls may accumulate. */
+int epb_bin_reduce(const float* Sv, const void* range_var, int range_is_f64, const int* xbin,
+                   const double* r_edges, int nR, int closed_right, int with_height, double* acc,
+                   epb_i64 C, epb_i64 P, epb_i64 R, epb_i64 nX, void* stream);
+/* mean -> dB.  out: [C,nX,nR] float32.  skipna=0 reproduces func="mean".  Bins without members get
+ * fill_value (then 10log10 like the reference).  h_out (NASC, optional): sum of heights per bin. */
+int epb_bin_finalize(const double* acc, float* out, double* h_out, epb_i64 ncell, int skipna,
+                     float fill_value, int to_db, void* stream);
+
+/* ---- K7: index binning (compute_MVBS_index_binning commongrid/api.py:195-266: coarsen mean in the
+ *      linear domain + coarsen min of echo_range).  out/er_out: [C, ceil(P/pn), ceil(R/rn)] float32. ---- */
+int epb_coarsen(const float* Sv, const float* echo_range, float* out, float* er_out, epb_i64 C,
+                epb_i64 P, epb_i64 R, int ping_num, int range_sample_num, void* stream);
+
+/* ---- bin boundaries in sample-index space from the exact range law (so that binning of K1-derived
+ *      ranges is bit-identical with float64 binning of the reference's echo_range / depth) -------------
+ * bounds: [C*P, nR+1] int32, bounds[k] = first n whose range value is >= edge k (closed left) or > edge k
+ * (closed right).  depth (optional, add_depth consolidate/api.py:221): value = off[p] + (sign*R)*scale[p]. */
+int epb_bin_bounds(const epb_row* rows, const double* r_edges, int nR, int closed_right,
+                   const double* depth_off /* [P] or NULL */, const double* depth_scale /* [P] or NULL */,
+                   double depth_sign, int* bounds, epb_i64 C, epb_i64 P, epb_i64 R, void* stream);
+
+/* ---- fused pipeline: power -> Sv -> background-noise removal -> MVBS accumulators in one pass over
+ *      HBM (compute_Sv -> remove_background_noise -> compute_MVBS).
+ * bounds from epb_bin_bounds; acc as in epb_bin_reduce.  Optional full-size outputs (any may be NULL):
+ * Sv, echo_range, Sv_noise, Sv_corrected [C,P,R] float32.  noise_out: [C, ceil(P/ping_num)] or NULL.
+ * ping_num = 0 skips noise removal (Sv -> MVBS). */
+int epb_pipeline_power_mvbs(const float* backscatter_r, const epb_row* rows, const int* bounds,
+                            const int* xbin, int nR, double* acc, float* noise_out, float* Sv,
+                            float* echo_range, float* Sv_noise, float* Sv_corrected, epb_i64 C,
+                            epb_i64 P, epb_i64 R, epb_i64 nX, int ping_num, int range_sample_num,
+                            float noise_max, float snr_threshold, void* stream);
+epb_i64 epb_pipeline_smem_bytes(epb_i64 R, int ping_num);
+
+/* ---- helpers ---------------------------------------------------------------------------------------- */
+int epb_zero(void* ptr, epb_i64 nbytes, void* stream);
+int epb_minmax_init(float* minmax /* 4 floats */, void* stream);
+/* Philox4x32-10 synthetic inputs: counter = element index / 4, key = seed.
+ * kind 0: EK power dB = q * 10log10(2)/256 with q = -24000 + floor(u * 22001 / 2^32) (int16 range)
+ * kind 1: AZFP counts = floor(u / 65536) as float
+ * kind 2: N(0,1)*scale complex plane (Box-Muller)            nan_tail: fraction of pings (x 2^-16)
+ * whose tail beyond a pseudo-random sample index is NaN (pad_shorter_ping). */
+int epb_synth_fill(float* out, epb_i64 C, epb_i64 P, epb_i64 R, epb_i64 inner, int kind,
+                   unsigned long long seed, epb_i64 ping_offset, unsigned nan_tail_q16, float scale,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EPB200_H */
