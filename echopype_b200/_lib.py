@@ -21,10 +21,13 @@ class epb_row(Structure):
     _fields_ = (
         [(n, c_double) for n in ("p0", "p1", "p2", "p3", "p4", "off1", "off2", "r0", "a", "two_alpha", "K", "fscale", "foff", "slog")]
         + [("n_start", c_int), ("law", c_int), ("azfp_N", c_int), ("reserved", c_int)]
+        + [(n, c_float) for n in ("a_h", "a_l", "r0_h", "r0_l", "bp_h", "bp_l", "two_alpha_f", "slog2", "fscale_f", "foffK",
+                                  "c0", "c1", "c2", "spow", "pad0", "pad1")]
     )
 
 
-assert ctypes.sizeof(epb_row) == 128
+ROW_BYTES = ctypes.sizeof(epb_row)
+assert ROW_BYTES == 192
 
 i64, vp = c_longlong, c_void_p
 
@@ -41,16 +44,18 @@ SIGNATURES = {
     "epb_noise_estimate": (c_int, [vp, vp, epb_cp, vp, i64, i64, i64, c_int, c_int, c_float, vp]),
     "epb_noise_apply": (c_int, [vp, vp, epb_cp, vp, vp, vp, vp, i64, i64, i64, c_int, c_float, vp]),
     "epb_bin_reduce": (c_int, [vp, vp, c_int, vp, vp, c_int, c_int, c_int, vp, i64, i64, i64, i64, vp]),
+    "epb_bin_reduce_law": (c_int, [vp, vp, vp, vp, vp, vp, c_int, c_int, vp, i64, i64, i64, i64, vp]),
     "epb_bin_finalize": (c_int, [vp, vp, vp, i64, c_int, c_float, c_int, vp]),
     "epb_coarsen": (c_int, [vp, vp, vp, vp, i64, i64, i64, c_int, c_int, vp]),
-    "epb_bin_bounds": (c_int, [vp, vp, c_int, c_int, vp, vp, c_double, vp, i64, i64, i64, vp]),
     "epb_pipeline_power_mvbs": (
         c_int,
-        [vp, vp, vp, vp, c_int, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, c_int, c_int, c_float, c_float, vp],
+        [vp, vp, vp, vp, c_int, c_int, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, c_int, c_int, c_float, c_float, vp],
     ),
-    "epb_pipeline_smem_bytes": (i64, [i64, c_int]),
+    "epb_pipeline_smem_bytes": (i64, [i64, c_int, c_int, c_int, c_int]),
     "epb_zero": (c_int, [vp, i64, vp]),
     "epb_minmax_init": (c_int, [vp, vp]),
+    "epb_minmax": (c_int, [vp, i64, vp, vp]),
+    "epb_range_max": (c_int, [vp, vp, i64, i64, i64, vp, vp]),
     "epb_synth_fill": (c_int, [vp, i64, i64, i64, i64, c_int, c_ulonglong, i64, c_uint, c_float, vp]),
 }
 

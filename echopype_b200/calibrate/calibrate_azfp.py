@@ -21,9 +21,8 @@ class CalibrateAZFP(CalibrateBase):
             beam=self.echodata["Sonar/Beam_group1"], vend=self.echodata["Vendor_specific"], user_dict=self.cal_params
         )
 
-    def _cal_power_samples(self, cal_type, **kwargs):
-        """Device version of CalibrateAZFP._cal_power_samples (calibrate_azfp.py:49-111) including
-        compute_range_AZFP (calibrate/range.py:11-95)."""
+    def _power_rows(self, cal_type):
+        """Row records + device-resident counts: (rows, x, C, P, R, None)."""
         if cal_type not in ("Sv", "TS"):
             raise ValueError("cal_type not recognized!")
         if "sound_speed" not in self.env_params:
@@ -58,12 +57,19 @@ class CalibrateAZFP(CalibrateBase):
             prm[k] = np.ascontiguousarray(np.broadcast_to(v, (C,)))
         rows = kernels.rows_azfp(C, P, R, cal_type, prm)
         x = to_device_f32(bs.data)
-        out, rng, _ = kernels.sv_power(x, rows, C, P, R, want_range=True)
         self.rows = rows
+        return rows, x, C, P, R, None
+
+    def _cal_power_samples(self, cal_type, **kwargs):
+        """Device version of CalibrateAZFP._cal_power_samples (calibrate_azfp.py:49-111) including
+        compute_range_AZFP (calibrate/range.py:11-95)."""
+        rows, x, C, P, R, _ = self._power_rows(cal_type)
+        beam = self.echodata["Sonar/Beam_group1"]
+        out, rng, mm = kernels.sv_power(x, rows, C, P, R, want_range=True, want_minmax=True)
         ds = Dataset(coords={d: beam[d].values for d in DIMENSION_ORDER})
         ds[cal_type] = DataArray(out, DIMENSION_ORDER, name=cal_type)
         er = DataArray(rng, DIMENSION_ORDER, name="echo_range")
-        er.law = {"rows": rows, "kind": "echo_range"}
+        er.law = {"rows": rows, "kind": "echo_range", "minmax": mm}
         ds["echo_range"] = er
         ds["frequency_nominal"] = beam["frequency_nominal"]
         return self._add_params_to_output(ds)

@@ -183,13 +183,13 @@ class CalibrateEK(CalibrateBase):
         tau_eff = np.where(gpt, tau_nom0, tau_eff)
         return DataArray(tau_eff, dims=["channel"], coords={"channel": chan}, attrs=attrs)
 
-    def _finish(self, cal_type, out_t, rng_t, tau_effective, rows):
+    def _finish(self, cal_type, out_t, rng_t, tau_effective, rows, minmax=None):
         beam = self.beam
         coords = {d: beam[d].values for d in DIMENSION_ORDER}
         ds = Dataset(coords=coords)
         ds[cal_type] = DataArray(out_t, DIMENSION_ORDER, name=cal_type)
         er = DataArray(rng_t, DIMENSION_ORDER, name="echo_range")
-        er.law = {"rows": rows, "kind": "echo_range"}
+        er.law = {"rows": rows, "kind": "echo_range", "minmax": minmax}
         ds["echo_range"] = er
         if cal_type == "Sv" and tau_effective is not None:
             ds["tau_effective"] = tau_effective
@@ -216,8 +216,8 @@ class CalibrateEK(CalibrateBase):
             prm["tau_effective"] = tau_effective.values
         return prm, tau_effective
 
-    def _cal_power_samples(self, cal_type: str) -> Dataset:
-        """Device version of CalibrateEK._cal_power_samples (calibrate_ek.py:79-206)."""
+    def _power_rows(self, cal_type: str):
+        """Row records + device-resident raw samples for the power-sample path: (rows, x, C, P, R, tau_effective)."""
         if cal_type not in ("Sv", "TS"):
             raise ValueError("cal_type must be 'Sv' or 'TS'")
         C, P, R = self._shape()[:3]
@@ -225,9 +225,14 @@ class CalibrateEK(CalibrateBase):
         prm, tau_effective = self._power_params(cal_type)
         rows = kernels.rows_ek_power(C, P, R, self._sonar_code(), cal_type, prm, self._is_gpt())
         x = to_device_f32(self.beam["backscatter_r"].data)
-        out, rng, _ = kernels.sv_power(x, rows, C, P, R, want_range=True)
         self.rows = rows
-        return self._finish(cal_type, out, rng, tau_effective, rows)
+        return rows, x, C, P, R, tau_effective
+
+    def _cal_power_samples(self, cal_type: str) -> Dataset:
+        """Device version of CalibrateEK._cal_power_samples (calibrate_ek.py:79-206)."""
+        rows, x, C, P, R, tau_effective = self._power_rows(cal_type)
+        out, rng, mm = kernels.sv_power(x, rows, C, P, R, want_range=True, want_minmax=True)
+        return self._finish(cal_type, out, rng, tau_effective, rows, mm)
 
 
 class CalibrateEK60(CalibrateEK):
@@ -333,11 +338,11 @@ class CalibrateEK80(CalibrateEK):
         re = to_device_f32(beam["backscatter_r"].data)
         im = to_device_f32(beam["backscatter_i"].data)
         if bb:
-            out, rng, _, _ = kernels.pulse_compress_sv(re, im, [tx[c] for c in chan], rows, C, P, R, B)
+            out, rng, _, mm = kernels.pulse_compress_sv(re, im, [tx[c] for c in chan], rows, C, P, R, B, want_minmax=True)
         else:
-            out, rng, _ = kernels.sv_complex(re, im, rows, C, P, R, B)
+            out, rng, mm = kernels.sv_complex(re, im, rows, C, P, R, B, want_minmax=True)
         self.rows = rows
-        return self._finish(cal_type, out, rng, tau_effective, rows)
+        return self._finish(cal_type, out, rng, tau_effective, rows, mm)
 
     def _compute_cal(self, cal_type) -> Dataset:
         if self.waveform_mode == "BB" or self.encode_mode == "complex":

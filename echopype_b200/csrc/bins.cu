@@ -1,0 +1,311 @@
+// K6: linear-domain bin reduction for MVBS / NASC (commongrid/utils.py:504-628 = flox xarray_reduce with
+// IntervalIndex groups; compute_raw_NASC :97-207) and its finalisation (mean -> dB).
+//
+// One warp per (channel, ping) row; lanes stream float4 (coalesced 512 B per warp instruction).  Each sample
+// gets a key = range-bin index (or -1: outside every bin, NaN range, ping outside the x bins).  Consecutive
+// samples mostly share a key, so the warp performs a SEGMENTED reduction over runs of equal keys with
+// shuffles (head flags -> run ids -> 5-step segmented scan) and only the tail lane of each run issues the
+// float64 atomics: ~2 runs per 128 samples instead of 128 atomics.
+//
+// Two ways to obtain the key:
+//   generic  - the range variable is an array (float32 / float64): position against the float64 edges
+//              with the reference's interval rule (closed left: e[k] <= x < e[k+1]);
+//   law      - the range variable was produced by this library (echo_range / depth of compute_Sv): bin
+//              boundaries are found in SAMPLE-INDEX space by bisection on the exact float64 range law, so
+//              membership is bit-identical with binning the reference's float64 echo_range.
+#include "epb_common.cuh"
+
+namespace {
+using namespace epb;
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kMaxLawBins = 511;  // bounds per warp kept in shared memory
+
+struct Acc3 {
+  float sum;   // sum of 10^(Sv/10) over non-NaN members
+  int cnt;     // low 16 bits: non-NaN members, high 16 bits: NaN members
+  float h;     // NASC: sum of depth differences
+};
+
+// position x against edges[0..nR]; returns bin index or -1
+__device__ __forceinline__ int bin_of(double x, const double* __restrict__ e, int nR, double inv_w, int closed_right) {
+  if (!(x == x)) return -1;
+  const double lo = e[0], hi = e[nR];
+  if (closed_right ? !(x > lo && x <= hi) : !(x >= lo && x < hi)) return -1;
+  int k = (int)((x - lo) * inv_w);  // uniform-edge guess, then exact fix-up against the stored edges
+  k = k < 0 ? 0 : (k > nR - 1 ? nR - 1 : k);
+  if (closed_right) {
+    while (k > 0 && !(x > e[k])) --k;
+    while (k < nR - 1 && x > e[k + 1]) ++k;
+  } else {
+    while (k > 0 && x < e[k]) --k;
+    while (k < nR - 1 && x >= e[k + 1]) ++k;
+  }
+  return k;
+}
+
+__device__ __forceinline__ void flush_run(double* __restrict__ cell, const Acc3& a, bool with_h) {
+  const int good = a.cnt & 0xffff, bad = a.cnt >> 16;
+  if (good) {
+    atomicAdd(cell + 0, (double)a.sum);
+    atomicAdd(cell + 1, (double)good);
+  }
+  if (bad) atomicAdd(cell + 2, (double)bad);
+  if (with_h && a.h != 0.f) atomicAdd(cell + 3, (double)a.h);
+}
+
+// Segmented warp reduction over runs of equal keys; the last lane of each run adds the run total to acc.
+template <bool kHeight>
+__device__ __forceinline__ void warp_runs_to_acc(int key, Acc3 a, double* __restrict__ acc_row /* [nR][4] */) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int prev = __shfl_up_sync(full, key, 1);
+  const bool head = (lane == 0) || (prev != key);
+  const unsigned heads = __ballot_sync(full, head);
+  if (heads == 1u && key < 0) return;  // whole warp outside every bin
+  const int run = __popc(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const float s = __shfl_up_sync(full, a.sum, d);
+    const int c = __shfl_up_sync(full, a.cnt, d);
+    const float h = kHeight ? __shfl_up_sync(full, a.h, d) : 0.f;
+    const int r = __shfl_up_sync(full, run, d);
+    if (lane >= d && r == run) {
+      a.sum += s;
+      a.cnt += c;
+      if (kHeight) a.h += h;
+    }
+  }
+  const int next = __shfl_down_sync(full, run, 1);
+  const bool tail = (lane == 31) || (next != run);
+  if (tail && key >= 0) flush_run(acc_row + 4 * (long long)key, a, kHeight);
+}
+
+__device__ __forceinline__ void add_sample(Acc3& a, float sv) {
+  const float v = fast_exp2(sv * kDb2Log2);  // commongrid/utils.py:592  10^(Sv/10)
+  const bool ok = (v == v);
+  a.sum += ok ? v : 0.f;
+  a.cnt += ok ? 1 : (1 << 16);
+}
+
+// ---- generic: range variable given as an array ----------------------------------------------------------
+template <typename RT, bool kHeight>
+__global__ void __launch_bounds__(32 * kWarpsPerCta) bin_reduce_kernel(const float* __restrict__ Sv,
+                                                                       const RT* __restrict__ rng,
+                                                                       const int* __restrict__ xbin,
+                                                                       const double* __restrict__ edges, int nR,
+                                                                       int closed_right, double* __restrict__ acc,
+                                                                       long long C, long long P, int R, long long nX) {
+  extern __shared__ double s_edges[];
+  for (int k = threadIdx.x; k <= nR; k += blockDim.x) s_edges[k] = edges[k];
+  __syncthreads();
+  const double inv_w = (double)nR / (s_edges[nR] - s_edges[0]);
+  const int lane = threadIdx.x & 31;
+  const long long nrows = C * P;
+  const long long warp0 = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  for (long long row = warp0; row < nrows; row += (long long)gridDim.x * kWarpsPerCta) {
+    const long long c = row / P, p = row % P;
+    const int xb = __ldg(xbin + p);
+    if (xb < 0 || xb >= nX) continue;  // ping outside every x bin: no member
+    double* acc_row = acc + ((c * nX + xb) * (long long)nR) * 4;
+    const float* sv = Sv + row * (long long)R;
+    const RT* rr = rng + row * (long long)R;
+    for (int n0 = 0; n0 < R; n0 += 128) {
+      // lane owns samples n0 + 4*lane .. +3 ; keys per sample, merged per lane when all four agree
+      int keys[4];
+      Acc3 a[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int n = n0 + 4 * lane + k;
+        keys[k] = -1;
+        a[k].sum = 0.f, a[k].cnt = 0, a[k].h = 0.f;
+        if (n < R) {
+          const double x = (double)rr[n];
+          keys[k] = bin_of(x, s_edges, nR, inv_w, closed_right);
+          if (keys[k] >= 0) {
+            add_sample(a[k], ld_stream(sv + n));
+            if (kHeight && n + 1 < R) {
+              const double d = (double)rr[n + 1] - x;  // diff(label="lower") commongrid/utils.py:170-172
+              if (d == d) a[k].h = (float)d;
+            }
+          }
+        }
+      }
+      const bool same = (keys[0] == keys[1]) && (keys[1] == keys[2]) && (keys[2] == keys[3]);
+      int key = -1;
+      Acc3 m;
+      m.sum = 0.f, m.cnt = 0, m.h = 0.f;
+      if (same) {
+        key = keys[0];
+        m.sum = (a[0].sum + a[1].sum) + (a[2].sum + a[3].sum);
+        m.cnt = a[0].cnt + a[1].cnt + a[2].cnt + a[3].cnt;
+        m.h = (a[0].h + a[1].h) + (a[2].h + a[3].h);
+      } else {  // a bin boundary inside this lane's four samples (rare): flush them directly
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (keys[k] >= 0) flush_run(acc_row + 4 * (long long)keys[k], a[k], kHeight);
+      }
+      warp_runs_to_acc<kHeight>(key, m, acc_row);
+    }
+  }
+}
+
+// ---- law: bin boundaries in sample-index space from the exact float64 range law ---------------------------
+// value(n) = depth_off[p] + law_range(row, n) * depth_scale[p]   (echo_range: off = 0, scale = 1)
+__device__ __forceinline__ double law_value(const epb_row& r, int n, double off, double scale, bool is_depth) {
+  const double R = law_range(r, n);
+  return is_depth ? __dadd_rn(off, __dmul_rn(R, scale)) : R;
+}
+
+// smallest n in [0, R] with value(n) >= edge (closed left) / value(n) > edge (closed right); value monotone in n
+__device__ int first_at_or_above(const epb_row& r, int R, double edge, int closed_right, double off, double scale,
+                                 bool is_depth) {
+  int lo = 0, hi = R;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const double v = law_value(r, mid, off, scale, is_depth);
+    const bool pass = closed_right ? (v > edge) : (v >= edge);
+    if (pass)
+      hi = mid;
+    else
+      lo = mid + 1;  // also taken for NaN: a NaN law puts every sample outside
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(32 * kWarpsPerCta) bin_reduce_law_kernel(
+    const float* __restrict__ Sv, const epb_row* __restrict__ rows, const double* __restrict__ depth_off,
+    const double* __restrict__ depth_scale, const int* __restrict__ xbin, const double* __restrict__ edges, int nR,
+    int closed_right, double* __restrict__ acc, long long C, long long P, int R, long long nX) {
+  extern __shared__ double s_edges[];                                        // [nR+1]
+  int* s_bounds = reinterpret_cast<int*>(s_edges + (nR + 1));                // [kWarpsPerCta][nR+1]
+  for (int k = threadIdx.x; k <= nR; k += blockDim.x) s_edges[k] = edges[k];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int* bnd = s_bounds + w * (nR + 1);
+  const bool is_depth = depth_off != nullptr;
+  const long long nrows = C * P;
+  const long long warp0 = (long long)blockIdx.x * kWarpsPerCta + w;
+  for (long long row = warp0; row < nrows; row += (long long)gridDim.x * kWarpsPerCta) {
+    const long long c = row / P, p = row % P;
+    const int xb = __ldg(xbin + p);
+    if (xb < 0 || xb >= nX) continue;
+    const epb_row r = rows[row];
+    const double off = is_depth ? depth_off[p] : 0.0, scale = is_depth ? depth_scale[p] : 1.0;
+    __syncwarp();
+    for (int k = lane; k <= nR; k += 32) bnd[k] = first_at_or_above(r, R, s_edges[k], closed_right, off, scale, is_depth);
+    __syncwarp();
+    double* acc_row = acc + ((c * nX + xb) * (long long)nR) * 4;
+    const float* sv = Sv + row * (long long)R;
+    const int n_lo = bnd[0], n_hi = bnd[nR];  // members are n_lo <= n < n_hi
+    int kcur = 0;
+    for (int n0 = (n_lo / 128) * 128; n0 < n_hi; n0 += 128) {
+      const int nb = n0 + 4 * lane;
+      int keys[4];
+      Acc3 a[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int n = nb + k;
+        keys[k] = -1;
+        a[k].sum = 0.f, a[k].cnt = 0, a[k].h = 0.f;
+        if (n >= n_lo && n < n_hi) {
+          while (bnd[kcur + 1] <= n) ++kcur;  // bnd is non-decreasing; kcur only moves forward
+          keys[k] = kcur;
+          add_sample(a[k], ld_stream(sv + n));
+        }
+      }
+      const bool same = (keys[0] == keys[1]) && (keys[1] == keys[2]) && (keys[2] == keys[3]);
+      int key = -1;
+      Acc3 m;
+      m.sum = 0.f, m.cnt = 0, m.h = 0.f;
+      if (same) {
+        key = keys[0];
+        m.sum = (a[0].sum + a[1].sum) + (a[2].sum + a[3].sum);
+        m.cnt = a[0].cnt + a[1].cnt + a[2].cnt + a[3].cnt;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (keys[k] >= 0) flush_run(acc_row + 4 * (long long)keys[k], a[k], false);
+      }
+      warp_runs_to_acc<false>(key, m, acc_row);
+    }
+  }
+}
+
+// ---- finalise: (sum, n_good, n_nan, h) -> mean [-> dB] -------------------------------------------------------
+__global__ void bin_finalize_kernel(const double* __restrict__ acc, float* __restrict__ out, double* __restrict__ h_out,
+                                    long long ncell, int skipna, float fill_value, int to_db) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= ncell) return;
+  const double s = acc[4 * i], good = acc[4 * i + 1], bad = acc[4 * i + 2];
+  double m;
+  if (good + bad == 0.0)
+    m = (double)fill_value;  // no member: flox fill_value
+  else if (!skipna && bad > 0.0)
+    m = CUDART_NAN;          // func="mean": a NaN member poisons the bin
+  else
+    m = s / good;            // all-NaN members: 0/0 = NaN, as nanmean
+  out[i] = (float)(to_db ? 10.0 * log10(m) : m);  // _lin2log, commongrid/utils.py:92
+  if (h_out) h_out[i] = acc[4 * i + 3];
+}
+
+}  // namespace
+
+extern "C" int epb_bin_reduce(const float* Sv, const void* range_var, int range_is_f64, const int* xbin,
+                              const double* r_edges, int nR, int closed_right, int with_height, double* acc, epb_i64 C,
+                              epb_i64 P, epb_i64 R, epb_i64 nX, void* stream) {
+  EPB_REQUIRE(Sv && range_var && xbin && r_edges && acc, "NULL pointer");
+  EPB_REQUIRE(C > 0 && P > 0 && R > 0 && R < (1LL << 30) && nX > 0, "bad shape");
+  EPB_REQUIRE(nR > 0 && nR <= 20000, "number of range bins must be in 1..20000");
+  const long long nrows = C * P;
+  long long grid = (nrows + kWarpsPerCta - 1) / kWarpsPerCta;
+  const long long cap = (long long)epb_num_sms() * 8;
+  if (grid > cap) grid = cap;
+  const size_t smem = (size_t)(nR + 1) * sizeof(double);
+  cudaStream_t s = (cudaStream_t)stream;
+#define EPB_BR(T, H)                                                                                        \
+  do {                                                                                                      \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(bin_reduce_kernel<T, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    bin_reduce_kernel<T, H><<<(unsigned)grid, 32 * kWarpsPerCta, smem, s>>>(Sv, (const T*)range_var, xbin, r_edges, nR, \
+                                                                            closed_right, acc, C, P, (int)R, nX); \
+  } while (0)
+  if (range_is_f64) {
+    if (with_height)
+      EPB_BR(double, true);
+    else
+      EPB_BR(double, false);
+  } else {
+    if (with_height)
+      EPB_BR(float, true);
+    else
+      EPB_BR(float, false);
+  }
+#undef EPB_BR
+  return epb_check_launch("epb_bin_reduce");
+}
+
+extern "C" int epb_bin_reduce_law(const float* Sv, const epb_row* rows, const double* depth_off,
+                                  const double* depth_scale, const int* xbin, const double* r_edges, int nR,
+                                  int closed_right, double* acc, epb_i64 C, epb_i64 P, epb_i64 R, epb_i64 nX,
+                                  void* stream) {
+  EPB_REQUIRE(Sv && rows && xbin && r_edges && acc, "NULL pointer");
+  EPB_REQUIRE((depth_off == nullptr) == (depth_scale == nullptr), "depth_off and depth_scale go together");
+  EPB_REQUIRE(C > 0 && P > 0 && R > 0 && R < (1LL << 30) && nX > 0, "bad shape");
+  EPB_REQUIRE(nR > 0 && nR <= kMaxLawBins, "law path supports 1..511 range bins (use epb_bin_reduce)");
+  const long long nrows = C * P;
+  long long grid = (nrows + kWarpsPerCta - 1) / kWarpsPerCta;
+  const long long cap = (long long)epb_num_sms() * 8;
+  if (grid > cap) grid = cap;
+  const size_t smem = (size_t)(nR + 1) * sizeof(double) + (size_t)kWarpsPerCta * (nR + 1) * sizeof(int);
+  bin_reduce_law_kernel<<<(unsigned)grid, 32 * kWarpsPerCta, smem, (cudaStream_t)stream>>>(
+      Sv, rows, depth_off, depth_scale, xbin, r_edges, nR, closed_right, acc, C, P, (int)R, nX);
+  return epb_check_launch("epb_bin_reduce_law");
+}
+
+extern "C" int epb_bin_finalize(const double* acc, float* out, double* h_out, epb_i64 ncell, int skipna,
+                                float fill_value, int to_db, void* stream) {
+  EPB_REQUIRE(acc && out && ncell > 0, "bad pointer/size");
+  bin_finalize_kernel<<<(unsigned)((ncell + 255) / 256), 256, 0, (cudaStream_t)stream>>>(acc, out, h_out, ncell, skipna,
+                                                                                         fill_value, to_db);
+  return epb_check_launch("epb_bin_finalize");
+}

@@ -2,12 +2,14 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
+#include <stddef.h>
 #include <stdint.h>
 #include <stdio.h>
 
 #include "../../include/epb200.h"
 
-static_assert(sizeof(epb_row) == 128, "epb_row must be 128 bytes");
+static_assert(sizeof(epb_row) == 192, "epb_row must be 192 bytes");
+static_assert(offsetof(epb_row, a_h) == 128, "float block of epb_row must start at byte 128");
 
 void epb_set_error(const char* fmt, ...);
 int epb_check_launch(const char* what);
@@ -116,6 +118,18 @@ struct MinMax {
     }
   }
 };
+
+// single-MUFU log2 / exp2 (flush-to-zero variants: no denormal pre-scaling code around the MUFU)
+__device__ __forceinline__ float fast_log2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // 10^(x/10) and 10*log10(x) in float32 (accuracy budget: DESIGN.md "numerics")
 __device__ __forceinline__ float db2lin(float x) { return exp2f(x * kDb2Log2); }

@@ -63,6 +63,25 @@ __device__ void finish_row(epb_row& r, int R, bool guard) {
   r.a = (R > 1) ? (law_range(r, R - 1) - r.r0) / (double)(R - 1) : 0.0;
   r.n_start = guard ? first_positive(r, R) : 0;
   r.reserved = 0;
+  // float32 hi/lo block for the FP32-pipe sample kernels (include/epb200.h (3))
+  auto split = [](double d, float& h, float& l) {
+    h = (float)d;
+    l = (float)(d - (double)h);  // NaN / inf propagate into h; l becomes NaN for inf, harmless (h decides)
+    if (!(fabs(d) <= 3.0e38)) l = 0.f;
+  };
+  const double kL = 0.33219280948873623;  // log2(10)/10
+  split(r.a, r.a_h, r.a_l);
+  split(r.r0, r.r0_h, r.r0_l);
+  split((r.r0 - r.off1) - r.off2, r.bp_h, r.bp_l);
+  r.two_alpha_f = (float)r.two_alpha;
+  r.slog2 = (float)(r.slog * 0.3010299956639812);
+  r.fscale_f = (float)r.fscale;
+  r.foffK = (float)(r.foff - r.K);
+  r.c0 = (float)((r.foff - r.K) * kL);
+  r.c1 = (float)(r.fscale * kL);
+  r.c2 = (float)(r.two_alpha * kL);
+  r.spow = (float)(r.slog / 10.0);
+  r.pad0 = r.pad1 = 0.f;
 }
 
 __global__ void rows_ek_power_kernel(epb_row* rows, long long C, long long P, int R, int sonar, int cal_type,

@@ -8,30 +8,15 @@
 // Layout: rows are contiguous R-float runs; a CTA takes whole rows (grid-stride) so the 128-byte row
 // record is read once per row; threads stream float4 (LDG.128 nc / STG.128 cs), 4 independent loads in
 // flight per thread.  HBM-bound: 8 B/sample (12 with echo_range); see DESIGN.md for the roofline.
-#include "epb_common.cuh"
+#include "sample_math.cuh"
 
 namespace {
 using namespace epb;
 
-struct RowC {  // per-row constants hoisted into registers
-  double r0, a, off, two_alpha, K;
-  float fscale, foff, slog;
-  int n_start;
-  bool nanrange;
-  __device__ __forceinline__ explicit RowC(const epb_row& r)
-      : r0(r.r0), a(r.a), off(r.off1 + r.off2), two_alpha(r.two_alpha), K(r.K), fscale((float)r.fscale),
-        foff((float)r.foff), slog((float)r.slog), n_start(r.n_start), nanrange((r.law & EPB_LAW_NANRANGE) != 0) {}
-};
-
-// value of one sample given its dB-domain front end `fr` (NaN-propagating)
-__device__ __forceinline__ float sample_out(const RowC& rc, int n, float fr, float& range_out) {
-  double Rd = fma(rc.a, (double)n, rc.r0);
-  double Rp = Rd - rc.off;
-  float rp = (float)Rp;
-  float lin = (float)fma(rc.two_alpha, Rp, -rc.K);
-  float v = fr + fmaf(rc.slog, log10f(rp), lin);
-  range_out = (float)Rd;
-  return (n >= rc.n_start) ? v : CUDART_NAN_F;
+// value of one sample given front(x) - K (NaN-propagating); also returns echo_range
+__device__ __forceinline__ float sample_out(const RowF& rc, int n, float nf, float frK, float& range_out) {
+  range_out = range_of(rc, nf);
+  return sv_db(rc, n, nf, frK);
 }
 
 template <bool kRange, bool kMinMax>
@@ -41,7 +26,7 @@ __global__ void __launch_bounds__(256) sv_power_vec4(const float* __restrict__ x
   const int R4 = R >> 2;
   MinMax mm_v, mm_r;
   for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
-    const RowC rc(rows[row]);
+    const RowF rc = load_rowf(rows + row);
     const float4* xin = reinterpret_cast<const float4*>(x + row * (long long)R);
     float4* o4 = reinterpret_cast<float4*>(out + row * (long long)R);
     float4* r4 = kRange ? reinterpret_cast<float4*>(rng + row * (long long)R) : nullptr;
@@ -58,10 +43,11 @@ __global__ void __launch_bounds__(256) sv_power_vec4(const float* __restrict__ x
         if (j >= R4) break;
         float in[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
         float o[4], rr[4];
+        const float nf0 = (float)(4 * j);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          float fr = fmaf(in[k], rc.fscale, rc.foff);
-          o[k] = sample_out(rc, 4 * j + k, fr, rr[k]);
+          float fr = fmaf(in[k], rc.fscale, rc.foffK);
+          o[k] = sample_out(rc, 4 * j + k, nf0 + (float)k, fr, rr[k]);
           if (rc.nanrange && in[k] != in[k]) rr[k] = CUDART_NAN_F;  // range.py:143-148
           if (kMinMax) {
             mm_v.add(o[k]);
@@ -86,12 +72,12 @@ __global__ void __launch_bounds__(256) sv_power_scalar(const float* __restrict__
                                                        float* __restrict__ minmax, long long nrows, int R) {
   MinMax mm_v, mm_r;
   for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
-    const RowC rc(rows[row]);
+    const RowF rc = load_rowf(rows + row);
     const long long base = row * (long long)R;
     for (int n = threadIdx.x; n < R; n += blockDim.x) {
       float in = ld_stream(x + base + n);
       float rr;
-      float o = sample_out(rc, n, fmaf(in, rc.fscale, rc.foff), rr);
+      float o = sample_out(rc, n, (float)n, fmaf(in, rc.fscale, rc.foffK), rr);
       if (rc.nanrange && in != in) rr = CUDART_NAN_F;
       out[base + n] = o;
       if (kRange) rng[base + n] = rr;
@@ -116,7 +102,7 @@ __global__ void __launch_bounds__(256) sv_complex_kernel(const float* __restrict
                                                          long long nrows, int R) {
   MinMax mm_v, mm_r;
   for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
-    const RowC rc(rows[row]);
+    const RowF rc = load_rowf(rows + row);
     const long long base = row * (long long)R;
     for (int n = threadIdx.x; n < R; n += blockDim.x) {
       float xr[B], xi[B];
@@ -144,9 +130,9 @@ __global__ void __launch_bounds__(256) sv_complex_kernel(const float* __restrict
       float inv = 1.f / (float)cnt;  // cnt == 0 -> inf*0 = NaN below, as nanmean of an all-NaN slice
       float mr = sr * inv, mi = si * inv;
       float prx = rc.fscale * (mr * mr + mi * mi);
-      float fr = (prx > 0.f) ? 10.f * log10f(prx) : CUDART_NAN_F;
+      float fr = (prx > 0.f) ? fmaf(kLog2ToDb, fast_log2(prx), rc.foffK) : CUDART_NAN_F;
       float rr;
-      float o = sample_out(rc, n, fr, rr);
+      float o = sample_out(rc, n, (float)n, fr, rr);
       if (xr[0] != xr[0]) rr = CUDART_NAN_F;  // range.py:143-145 uses beam 0 of backscatter_r
       out[base + n] = o;
       if (kRange) rng[base + n] = rr;
@@ -239,4 +225,75 @@ extern "C" int epb_sv_complex(const float* re, const float* im, const epb_row* r
   }
 #undef EPB_LAUNCH_B
   return epb_check_launch("epb_sv_complex");
+}
+
+// ---- global reductions used for bin-edge construction and actual_range attributes ----------------------------
+namespace {
+using namespace epb;
+
+// minmax[0..1] = min / max over non-NaN elements, minmax[2] += number of NaN elements (as float, saturating use only)
+__global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ a, long long n, float* __restrict__ minmax) {
+  MinMax mm;
+  int nan = 0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = ld_stream(a + i);
+    mm.add(v);
+    nan |= (v != v);
+  }
+  mm.flush(minmax + 0, minmax + 1);
+  if (__any_sync(0xffffffffu, nan) && (threadIdx.x & 31) == 0) minmax[2] = 1.f;
+}
+
+__device__ __forceinline__ void atomic_max_d(double* addr, double v) {  // v >= 0 or any sign, non-NaN
+  long long iv = __double_as_longlong(v);
+  if (iv >= 0)
+    atomicMax((long long*)addr, iv);
+  else
+    atomicMin((unsigned long long*)addr, (unsigned long long)iv);
+}
+
+// exact float64 nanmax of the echo_range that compute_Sv would produce: per row, the law value at the last
+// sample whose range is not NaN (range.py:143-148: NaN where the input sample is NaN)
+__global__ void range_max_kernel(const float* __restrict__ x, const epb_row* __restrict__ rows, long long nrows, int R,
+                                 double* __restrict__ out) {
+  const long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  double best = -CUDART_INF;
+  if (row < nrows) {
+    const epb_row r = rows[row];
+    int n = R - 1;
+    if (x && (r.law & EPB_LAW_NANRANGE)) {
+      const float* xr = x + row * (long long)R;
+      while (n >= 0 && xr[n] != xr[n]) --n;
+    }
+    if (n >= 0) {  // the law is monotone non-decreasing in n (positive sample interval / sound speed)
+      const double v1 = law_range(r, n);
+      if (v1 == v1) best = v1;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if ((threadIdx.x & 31) == 0 && best != -CUDART_INF) atomic_max_d(out, best);
+}
+
+__global__ void init_range_max_kernel(double* out) { *out = -CUDART_INF; }
+
+}  // namespace
+
+extern "C" int epb_minmax(const float* a, epb_i64 n, float* minmax, void* stream) {
+  EPB_REQUIRE(a && minmax && n > 0, "bad pointer/size");
+  const long long blocks = (n + 255) / 256;
+  const long long cap = (long long)epb_num_sms() * 16;
+  minmax_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(a, n, minmax);
+  return epb_check_launch("epb_minmax");
+}
+
+extern "C" int epb_range_max(const float* backscatter_r, const epb_row* rows, epb_i64 C, epb_i64 P, epb_i64 R,
+                             double* out_max, void* stream) {
+  EPB_REQUIRE(rows && out_max && C > 0 && P > 0 && R > 0 && R < (1LL << 30), "bad pointer/shape");
+  const long long nrows = C * P;
+  init_range_max_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(out_max);
+  range_max_kernel<<<(unsigned)((nrows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(backscatter_r, rows, nrows, (int)R,
+                                                                                    out_max);
+  return epb_check_launch("epb_range_max");
 }

@@ -14,7 +14,7 @@ SONAR_EX60, SONAR_EX80 = 0, 1
 
 
 def alloc_rows(C, P, device=None):
-    return torch.empty(int(C) * int(P) * 128, dtype=torch.uint8, device=device or require_cuda())
+    return torch.empty(int(C) * int(P) * _lib.ROW_BYTES, dtype=torch.uint8, device=device or require_cuda())
 
 
 def rows_ek_power(C, P, R, sonar, cal_type, prm, is_gpt=None):
@@ -156,6 +156,15 @@ def bin_reduce(Sv, range_var, xbin, r_edges, acc, C, P, R, nX, closed_right=Fals
     return acc
 
 
+def bin_reduce_law(Sv, rows, xbin, r_edges, acc, C, P, R, nX, closed_right=False, depth_off=None, depth_scale=None):
+    nR = int(r_edges.numel()) - 1
+    _lib.call(
+        "epb_bin_reduce_law", ptr(Sv), ptr(rows), ptr(depth_off), ptr(depth_scale), ptr(xbin), ptr(r_edges), nR,
+        int(closed_right), ptr(acc), C, P, R, nX, stream(),
+    )
+    return acc
+
+
 def bin_finalize(acc, skipna=True, fill_value=float("nan"), to_db=True, want_height=False):
     C, nX, nR, _ = acc.shape
     out = empty((C, nX, nR), device=acc.device)
@@ -175,23 +184,34 @@ def coarsen(Sv, echo_range, C, P, R, ping_num, range_sample_num):
     return out, er
 
 
-def bin_bounds(rows, r_edges, C, P, R, closed_right=False, depth_off=None, depth_scale=None, depth_sign=1.0):
-    nR = int(r_edges.numel()) - 1
-    b = torch.empty((int(C) * int(P), nR + 1), dtype=torch.int32, device=rows.device)
-    _lib.call(
-        "epb_bin_bounds", ptr(rows), ptr(r_edges), nR, int(closed_right), ptr(depth_off), ptr(depth_scale),
-        ctypes.c_double(float(depth_sign)), ptr(b), C, P, R, stream(),
-    )
-    return b
+def minmax(a):
+    """(min, max, has_nan) over the non-NaN elements of a float32 device tensor (one streaming pass)."""
+    mm = new_minmax(a.device)
+    mm[2:] = 0
+    _lib.call("epb_minmax", ptr(a), a.numel(), ptr(mm), stream())
+    lo, hi, has_nan, _ = mm.tolist()
+    if lo == float("inf"):
+        lo = hi = float("nan")
+    return lo, hi, bool(has_nan)
 
 
-def pipeline_power_mvbs(x, rows, bounds, xbin, nR, acc, C, P, R, nX, ping_num, range_sample_num, noise_max=None,
-                        snr=3.0, noise_out=None, Sv=None, echo_range=None, Sv_noise=None, Sv_corrected=None):
+def range_max(x, rows, C, P, R):
+    """Exact float64 nanmax of the echo_range implied by `rows` (x: raw samples for the NaN rule, or None)."""
+    out = torch.empty(1, dtype=torch.float64, device=rows.device)
+    _lib.call("epb_range_max", ptr(x), ptr(rows), C, P, R, ptr(out), stream())
+    v = float(out.item())
+    return float("nan") if v == float("-inf") else v
+
+
+def pipeline_power_mvbs(x, rows, xbin, r_edges, acc, C, P, R, nX, ping_num, range_sample_num, noise_max=None,
+                        snr=3.0, closed_right=False, noise_out=None, Sv=None, echo_range=None, Sv_noise=None,
+                        Sv_corrected=None):
     nm = float("nan") if noise_max is None else float(noise_max)
+    nR = int(r_edges.numel()) - 1
     _lib.call(
-        "epb_pipeline_power_mvbs", ptr(x), ptr(rows), ptr(bounds), ptr(xbin), int(nR), ptr(acc), ptr(noise_out),
-        ptr(Sv), ptr(echo_range), ptr(Sv_noise), ptr(Sv_corrected), C, P, R, nX, int(ping_num), int(range_sample_num),
-        ctypes.c_float(nm), ctypes.c_float(float(snr)), stream(),
+        "epb_pipeline_power_mvbs", ptr(x), ptr(rows), ptr(xbin), ptr(r_edges), nR, int(closed_right), ptr(acc),
+        ptr(noise_out), ptr(Sv), ptr(echo_range), ptr(Sv_noise), ptr(Sv_corrected), C, P, R, nX, int(ping_num),
+        int(range_sample_num), ctypes.c_float(nm), ctypes.c_float(float(snr)), stream(),
     )
     return acc
 

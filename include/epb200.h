@@ -42,7 +42,7 @@ typedef struct epb_cp {
   epb_i64 sp;
 } epb_cp;
 
-/* Per-(channel, ping) row record (128 bytes) consumed by every sample kernel.  It carries
+/* Per-(channel, ping) row record (192 bytes) consumed by every sample kernel.  It carries
  *   (1) the EXACT float64 range law, evaluated with the reference's operation order, used only for
  *       index-space decisions (first sample with R' > 0, bin boundaries) so that those decisions are
  *       bit-identical with the float64 reference:
@@ -52,6 +52,9 @@ typedef struct epb_cp {
  *   (2) the affine value form R = r0 + a*n and the folded calibration constants:
  *         out = front(x) + slog*log10(R') + two_alpha*R' - K,   R' = (R - off1) - off2
  *         front(x) = x*fscale + foff (power dB / AZFP counts) or 10*log10(fscale*|mean_beam x|^2) (complex)
+ *   (3) the same value form pre-split into float32 hi/lo pairs (written by the epb_rows_* kernels) so the
+ *       per-sample kernels stay on the FP32 pipes: R' = fma(a_h,n,bp_h) + fma(a_l,n,bp_l) is accurate to
+ *       ~1 ulp(R') even where R - off cancels.
  */
 typedef struct epb_row {
   double p0, p1, p2, p3, p4;
@@ -65,6 +68,19 @@ typedef struct epb_row {
   int law;     /* 0 EK, 1 AZFP; bit 8 set: echo_range is NaN where the input sample is NaN (EK) */
   int azfp_N;
   int reserved;
+  /* float32 block (offset 128) */
+  float a_h, a_l;     /* a = a_h + a_l                                   */
+  float r0_h, r0_l;   /* r0                                              */
+  float bp_h, bp_l;   /* r0 - off1 - off2 (intercept of R')              */
+  float two_alpha_f;  /* 2*alpha                                         */
+  float slog2;        /* slog*log10(2): slog*log10(R') = slog2*log2(R')  */
+  float fscale_f;     /* front scale                                     */
+  float foffK;        /* foff - K                                        */
+  float c0;           /* (foff - K) * log2(10)/10  : 10^((front(x)-K)/10) = 2^(x*c1 + c0) */
+  float c1;           /* fscale * log2(10)/10                             */
+  float c2;           /* two_alpha * log2(10)/10                          */
+  float spow;         /* slog/10: R'^spow is the linear-domain spreading  */
+  float pad0, pad1;
 } epb_row;
 
 #define EPB_LAW_EK 0
@@ -139,12 +155,23 @@ int epb_noise_apply(const float* Sv, const float* echo_range, epb_cp absorption,
 /* ---- K6: linear-domain bin reduction for MVBS / NASC (_groupby_x_along_channels
  *      commongrid/utils.py:504-628 = flox xarray_reduce; compute_raw_NASC :97-207) ----------------------
  * xbin: [P] int32 bin of each ping along ping_time / distance (-1 = outside every bin).
- * Generic form: range values given per sample (float32 or float64), edges [nR+1] float64.
- * acc: [C, nX, nR, 4] float64 accumulators {sum of 10^(Sv/10), #non-NaN, #NaN members, sum of height
- * differences (NASC)}; zero it with epb_zero before the first call; several calls may accumulate. */
+ * Generic form: range values given per sample (float32 or float64), edges [nR+1] float64 (ascending).
+ * acc: [C, nX, nR, 4] float64 accumulators {sum of 10^(Sv/10) over non-NaN members, #non-NaN members,
+ * #NaN members, sum of range differences r[n+1]-r[n] of the members (NASC heights, with_height != 0)};
+ * zero it with epb_zero before the first call; several calls (and several ranks) may accumulate. */
 int epb_bin_reduce(const float* Sv, const void* range_var, int range_is_f64, const int* xbin,
                    const double* r_edges, int nR, int closed_right, int with_height, double* acc,
                    epb_i64 C, epb_i64 P, epb_i64 R, epb_i64 nX, void* stream);
+/* Same reduction when the range variable was produced by this library from `rows` (echo_range of
+ * compute_Sv, or depth = depth_off[p] + echo_range*depth_scale[p], consolidate/api.py:221): bin
+ * boundaries are located in sample-index space by bisection on the exact float64 range law, so bin
+ * membership is bit-identical with binning the reference's float64 echo_range.  A NaN input sample is
+ * counted as a NaN member (the reference drops it because its echo_range is NaN): identical results for
+ * skipna=True with a NaN fill_value; use epb_bin_reduce otherwise.  nR <= 511. */
+int epb_bin_reduce_law(const float* Sv, const epb_row* rows, const double* depth_off /* [P] or NULL */,
+                       const double* depth_scale /* [P] or NULL */, const int* xbin, const double* r_edges,
+                       int nR, int closed_right, double* acc, epb_i64 C, epb_i64 P, epb_i64 R, epb_i64 nX,
+                       void* stream);
 /* mean -> dB.  out: [C,nX,nR] float32.  skipna=0 reproduces func="mean".  Bins without members get
  * fill_value (then 10log10 like the reference).  h_out (NASC, optional): sum of heights per bin. */
 int epb_bin_finalize(const double* acc, float* out, double* h_out, epb_i64 ncell, int skipna,
@@ -155,29 +182,31 @@ int epb_bin_finalize(const double* acc, float* out, double* h_out, epb_i64 ncell
 int epb_coarsen(const float* Sv, const float* echo_range, float* out, float* er_out, epb_i64 C,
                 epb_i64 P, epb_i64 R, int ping_num, int range_sample_num, void* stream);
 
-/* ---- bin boundaries in sample-index space from the exact range law (so that binning of K1-derived
- *      ranges is bit-identical with float64 binning of the reference's echo_range / depth) -------------
- * bounds: [C*P, nR+1] int32, bounds[k] = first n whose range value is >= edge k (closed left) or > edge k
- * (closed right).  depth (optional, add_depth consolidate/api.py:221): value = off[p] + (sign*R)*scale[p]. */
-int epb_bin_bounds(const epb_row* rows, const double* r_edges, int nR, int closed_right,
-                   const double* depth_off /* [P] or NULL */, const double* depth_scale /* [P] or NULL */,
-                   double depth_sign, int* bounds, epb_i64 C, epb_i64 P, epb_i64 R, void* stream);
-
 /* ---- fused pipeline: power -> Sv -> background-noise removal -> MVBS accumulators in one pass over
  *      HBM (compute_Sv -> remove_background_noise -> compute_MVBS).
- * bounds from epb_bin_bounds; acc as in epb_bin_reduce.  Optional full-size outputs (any may be NULL):
- * Sv, echo_range, Sv_noise, Sv_corrected [C,P,R] float32.  noise_out: [C, ceil(P/ping_num)] or NULL.
- * ping_num = 0 skips noise removal (Sv -> MVBS). */
-int epb_pipeline_power_mvbs(const float* backscatter_r, const epb_row* rows, const int* bounds,
-                            const int* xbin, int nR, double* acc, float* noise_out, float* Sv,
-                            float* echo_range, float* Sv_noise, float* Sv_corrected, epb_i64 C,
+ * rows: Sv rows from epb_rows_ek_power / epb_rows_azfp.  r_edges [nR+1] float64 (range bins on echo_range),
+ * xbin [P], acc as in epb_bin_reduce.  Optional full-size outputs (any may be NULL): Sv, echo_range, Sv_noise,
+ * Sv_corrected [C,P,R] float32.  noise_out: [C, ceil(P/ping_num)] (dB) or NULL.
+ * ping_num = 0 skips noise removal (Sv -> MVBS).  noise_max: dB, NaN = no cap.  Requires R % 4 == 0,
+ * ping_num <= 256; returns EPB_E_UNSUPPORTED when the per-CTA accumulators exceed shared memory. */
+int epb_pipeline_power_mvbs(const float* backscatter_r, const epb_row* rows, const int* xbin,
+                            const double* r_edges, int nR, int closed_right, double* acc, float* noise_out,
+                            float* Sv, float* echo_range, float* Sv_noise, float* Sv_corrected, epb_i64 C,
                             epb_i64 P, epb_i64 R, epb_i64 nX, int ping_num, int range_sample_num,
                             float noise_max, float snr_threshold, void* stream);
-epb_i64 epb_pipeline_smem_bytes(epb_i64 R, int ping_num);
+epb_i64 epb_pipeline_smem_bytes(epb_i64 R, int nR, int tile, int do_noise, int staged);
 
 /* ---- helpers ---------------------------------------------------------------------------------------- */
 int epb_zero(void* ptr, epb_i64 nbytes, void* stream);
 int epb_minmax_init(float* minmax /* 4 floats */, void* stream);
+/* Global reductions for bin-edge construction (commongrid/api.py:108-114 range_var.max(skipna=True)) and the
+ * actual_range attributes (clean/utils.py:392-395).  epb_minmax: minmax[0..1] = min / max over the non-NaN
+ * elements of a[0..n), minmax[2] = 1 if any element is NaN (initialise with epb_minmax_init).
+ * epb_range_max: exact float64 nanmax of the echo_range that compute_Sv derives from `rows` (NaN where the
+ * input sample is NaN; backscatter_r may be NULL when the variant has no such rule); -inf if all NaN. */
+int epb_minmax(const float* a, epb_i64 n, float* minmax, void* stream);
+int epb_range_max(const float* backscatter_r, const epb_row* rows, epb_i64 C, epb_i64 P, epb_i64 R,
+                  double* out_max, void* stream);
 /* Philox4x32-10 synthetic inputs: counter = element index / 4, key = seed.
  * kind 0: EK power dB = q * 10log10(2)/256 with q = -24000 + floor(u * 22001 / 2^32) (int16 range)
  * kind 1: AZFP counts = floor(u / 65536) as float

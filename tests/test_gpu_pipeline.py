@@ -1,0 +1,163 @@
+"""GPU parity of the fused pipeline (power -> Sv -> remove_background_noise -> MVBS in one kernel) against
+(a) the float64 oracle chain and (b) the three separate API calls.  MVBS bins that contain a sample within 1e-3 dB
+of the SNR threshold may differ by that sample's share of the bin mean (it may fall on either side of the strict
+'>' test, clean/api.py:487); all other bins agree within 1e-4 dB."""
+
+import numpy as np
+import pytest
+
+import oracle_glue as og
+from oracle import clean as oclean
+from oracle import commongrid as ogrid
+
+pytestmark = pytest.mark.gpu
+ATOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def ep():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import echopype_b200 as ep
+
+    return ep
+
+
+def _ns(t):
+    return np.asarray(t).astype("datetime64[ns]").astype(np.int64)
+
+
+def _oracle_chain(ed, kind, pn, rn, nmax, snr, rb, tb, closed="left", skipna=True, env=None):
+    ref = og.ek60(ed, "Sv") if kind == "ek60" else (og.azfp(ed, "Sv", 30.0, 50.0) if kind == "azfp" else og.ek80(ed, "Sv", "CW", "power"))
+    Sv, rng = ref["out"], ref["echo_range"]
+    pt = ed["Sonar/Beam_group1"]["ping_time"].values
+    margin = None
+    if pn:
+        nz = oclean.remove_background_noise(Sv, rng, ref["sound_absorption"], pn, rn, nmax, snr)
+        with np.errstate(all="ignore"):
+            lin = 10 ** (Sv / 10) - 10 ** (nz["Sv_noise"] / 10)
+            c0 = 10 * np.log10(np.where(lin > 0, lin, np.nan))
+            margin = np.fmin(np.nan_to_num(np.abs(c0 - nz["Sv_noise"] - float(snr[:-2])), nan=np.inf),
+                             np.nan_to_num(np.abs(Sv - nz["Sv_noise"]), nan=np.inf))
+        ref.update(nz)
+        Svb = nz["Sv_corrected"]
+    else:
+        Svb = Sv
+    mv = ogrid.compute_MVBS(Svb, rng, _ns(pt), range_bin=rb, ping_time_bin=tb, closed=closed, skipna=skipna)
+    # bins holding a marginal sample
+    marg_bins = np.zeros(mv["Sv"].shape, bool)
+    if margin is not None and (margin < 1e-3).any():
+        xc = ogrid.bin_codes(_ns(pt), mv["p_edges"], closed)
+        rc = ogrid.bin_codes(rng, mv["r_edges"], closed)
+        c, p, n = np.nonzero(margin < 1e-3)
+        ok = (xc[p] >= 0) & (rc[c, p, n] >= 0)
+        marg_bins[c[ok], xc[p][ok], rc[c, p, n][ok]] = True
+    return ref, mv, marg_bins, margin
+
+
+def _check_mvbs(got, want, marg_bins):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    strict = ~marg_bins
+    assert np.array_equal(np.isnan(got[strict]), np.isnan(want[strict])), "MVBS NaN mask differs"
+    ok = strict & ~np.isnan(want)
+    d = np.abs(got[ok] - want[ok])
+    assert d.size == 0 or d.max() <= ATOL, f"max |dMVBS| = {d.max():.3e} dB"
+    okm = marg_bins & ~np.isnan(want) & ~np.isnan(got)
+    assert (np.abs(got[okm] - want[okm]) <= 0.5).all()
+    return float(d.max()) if d.size else 0.0
+
+
+CASES = [
+    # kind, shape, time_varying, ping_num, range_sample_num, noise_max, range_bin, ping_time_bin
+    ("ek60", (4, 103, 1000), False, 5, 30, None, "20m", "20s"),
+    ("ek60", (2, 60, 2048), True, 5, 30, "-125.0dB", "10m", "7s"),
+    ("ek60", (3, 47, 516), False, 10, 20, None, "5m", "1min"),
+    ("ek60", (2, 64, 4096), False, 30, 100, None, "50m", "30s"),
+    ("ek60", (2, 40, 1000), False, None, None, None, "20m", "20s"),
+    ("azfp", (4, 55, 2048), False, None, None, None, "10m", "10s"),
+    ("azfp", (2, 40, 512), False, 4, 16, None, "2m", "10s"),
+    ("ek80", (3, 36, 1024), False, 6, 40, None, "20m", "12s"),
+]
+
+
+@pytest.mark.parametrize("kind,shape,tv,pn,rn,nmax,rb,tb", CASES)
+def test_fused_pipeline_vs_oracle(ep, kind, shape, tv, pn, rn, nmax, rb, tb):
+    from echopype_b200 import synth
+
+    kw = {}
+    if kind == "ek60":
+        ed = synth.make_ek60(*shape, seed=21, nan_tail=0.15, time_varying=tv)
+    elif kind == "azfp":
+        ed = synth.make_azfp(*shape, seed=22)
+        kw = {"env_params": {"salinity": 30.0, "pressure": 50.0}}
+    else:
+        ed = synth.make_ek80(C=shape[0], P=shape[1], R=shape[2], mode="CW", encode="power", gpt_channel=1, nan_tail=0.15, seed=23)
+        kw = {"waveform_mode": "CW", "encode_mode": "power"}
+    ds = ep.pipeline.compute_Sv_clean_MVBS(ed, ping_num=pn, range_sample_num=rn, background_noise_max=nmax, SNR_threshold="3.0dB",
+                                           range_bin=rb, ping_time_bin=tb, keep=("Sv", "echo_range") + (("Sv_noise", "Sv_corrected") if pn else ()), **kw)
+    ref, mv, marg_bins, margin = _oracle_chain(ed, kind, pn, rn, nmax, "3.0dB", rb, tb)
+    _check_mvbs(ds["Sv"].values, mv["Sv"], marg_bins)
+    np.testing.assert_array_equal(_ns(ds["ping_time"].values), mv["ping_time"])
+    np.testing.assert_allclose(ds["echo_range"].values, mv["range"])
+    kept = ds.attrs["kept"]
+    og.compare_db(kept["Sv"].values, ref["out"], ATOL, "Sv")
+    er = kept["echo_range"].values.astype(np.float64)
+    assert np.array_equal(np.isnan(er), np.isnan(ref["echo_range"]))
+    np.testing.assert_allclose(er, ref["echo_range"], rtol=1.3e-7, equal_nan=True)
+    if pn:
+        og.compare_db(kept["Sv_noise"].values, ref["Sv_noise"], ATOL, "Sv_noise")
+        got_c, want_c = kept["Sv_corrected"].values.astype(np.float64), ref["Sv_corrected"]
+        flip = np.isnan(got_c) != np.isnan(want_c)
+        assert (margin[flip] < 1e-3).all()
+        both = ~np.isnan(got_c) & ~np.isnan(want_c)
+        assert np.abs(got_c[both] - want_c[both]).max() <= ATOL
+        # the per-tile noise estimate itself
+        nz = ds.attrs["noise_estimate"].values
+        P = shape[1]
+        want_noise = (ref["Sv_noise"] - oclean.transmission_loss(ref["echo_range"], ref["sound_absorption"]))
+        for i in range(nz.shape[1]):
+            seg = want_noise[:, i * pn:min((i + 1) * pn, P), :]
+            with np.errstate(all="ignore"):
+                w = np.nanmean(seg.reshape(seg.shape[0], -1), axis=1)
+            np.testing.assert_allclose(nz[:, i], w, atol=ATOL, equal_nan=True)
+
+
+def test_fused_equals_three_calls(ep):
+    from echopype_b200 import synth
+
+    ed = synth.make_ek60(3, 80, 1000, seed=5, nan_tail=0.1)
+    fused = ep.pipeline.compute_Sv_clean_MVBS(ed, ping_num=5, range_sample_num=30, range_bin="20m", ping_time_bin="20s")
+    ds = ep.calibrate.compute_Sv(ed)
+    ds = ep.clean.remove_background_noise(ds, ping_num=5, range_sample_num=30)
+    ds["Sv"] = ds["Sv_corrected"]
+    three = ep.commongrid.compute_MVBS(ds, range_bin="20m", ping_time_bin="20s")
+    a, b = fused["Sv"].values, three["Sv"].values
+    assert a.shape == b.shape
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    ok = ~np.isnan(a)
+    assert np.abs(a[ok] - b[ok]).max() < 5e-3  # threshold-marginal samples may flip between the two float32 formulations
+    assert np.median(np.abs(a[ok] - b[ok])) < 1e-5
+
+
+def test_fused_large_property(ep):
+    """Size-independent property at a larger size: constant power => every (ping bin, range bin) of the fused MVBS
+    (no noise removal) equals the closed-form Sv averaged over the bin's samples, identical across ping bins."""
+    import torch
+
+    from echopype_b200 import synth
+
+    C, P, R = 2, 2000, 4096
+    ed = synth.make_ek60(C, P, R, seed=1, nan_tail=0.0)
+    beam = ed["Sonar/Beam_group1"]
+    beam["backscatter_r"] = (("channel", "ping_time", "range_sample"), torch.full((C, P, R), -70.0, device="cuda"))
+    ds = ep.pipeline.compute_Sv_clean_MVBS(ed, range_bin="20m", ping_time_bin="100s")
+    mv = ds["Sv"].values
+    assert np.nanmax(np.abs(mv - mv[:, :1, :])) < 2e-5  # identical pings -> identical ping bins
+    ed_small = synth.make_ek60(C, 3, R, seed=1, nan_tail=0.0)
+    ed_small["Sonar/Beam_group1"]["backscatter_r"] = (("channel", "ping_time", "range_sample"), np.full((C, 3, R), -70.0, np.float32))
+    ref = og.ek60(ed_small, "Sv")
+    want = ogrid.compute_MVBS(ref["out"], ref["echo_range"], _ns(ed_small["Sonar/Beam_group1"]["ping_time"].values), "20m", "100s")
+    og.compare_db(mv[:, 0, :], want["Sv"][:, 0, :], ATOL, "MVBS")

@@ -1,0 +1,128 @@
+"""Per-kernel micro-benchmarks (CUDA events on torch's current stream, which is the stream the library
+launches on).  Usage: python tools/bench_kernels.py [--which sv,svr,...] [--C 4 --P 100000 --R 4096]"""
+
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import ctypes  # noqa: E402
+
+import torch  # noqa: E402
+
+from echopype_b200 import _lib  # noqa: E402
+from echopype_b200.device import ptr, stream  # noqa: E402
+
+from echopype_b200 import kernels, synth  # noqa: E402
+from echopype_b200.calibrate.calibrate_ek import CalibrateEK60  # noqa: E402
+
+PEAK = 6547.8
+if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")):
+    PEAK = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for a, b in ev:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in ev)
+    return ts[len(ts) // 2], ts[0]
+
+
+def report(name, ms, ms_min, nbytes, nsamp):
+    print(json.dumps({"kernel": name, "ms_median": round(ms, 4), "ms_min": round(ms_min, 4), "GBps": round(nbytes / ms / 1e6, 1),
+                      "frac_of_measured_hbm": round(nbytes / ms / 1e6 / PEAK, 3), "Gsamples_s": round(nsamp / ms / 1e6, 2)}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--C", type=int, default=4)
+    ap.add_argument("--P", type=int, default=100000)
+    ap.add_argument("--R", type=int, default=4096)
+    ap.add_argument("--which", default="copy,sv,svr,svrm,noise,bins,pipe")
+    ap.add_argument("--iters", type=int, default=10)
+    a = ap.parse_args()
+    C, P, R = a.C, a.P, a.R
+    which = a.which.split(",")
+    n = C * P * R
+    ed = synth.make_ek60(C, P, R, device=True)
+    cal = CalibrateEK60(ed)
+    prm, _ = cal._power_params("Sv")
+    rows = kernels.rows_ek_power(C, P, R, kernels.SONAR_EX60, "Sv", prm, cal._is_gpt())
+    x = ed["Sonar/Beam_group1"]["backscatter_r"].data
+    out = torch.empty_like(x)
+    rng = torch.empty_like(x)
+    if "copy" in which:
+        ms, mn = timeit(lambda: out.copy_(x), a.iters)
+        report("torch_copy", ms, mn, 8 * n, n)
+    if "sv" in which:
+        ms, mn = timeit(lambda: kernels.sv_power(x, rows, C, P, R, want_range=False, out=out), a.iters)
+        report("sv_power", ms, mn, 8 * n, n)
+    if "svr" in which:
+        ms, mn = timeit(lambda: kernels.sv_power(x, rows, C, P, R, want_range=True, out=out, rng=rng), a.iters)
+        report("sv_power+range", ms, mn, 12 * n, n)
+    if "svrm" in which:
+        ms, mn = timeit(lambda: kernels.sv_power(x, rows, C, P, R, want_range=True, want_minmax=True, out=out, rng=rng), a.iters)
+        report("sv_power+range+minmax", ms, mn, 12 * n, n)
+    if {"noise", "bins", "pipe"} & set(which):
+        extra(a, which, C, P, R, n, x, rows, out, rng, ed)
+
+
+def extra(a, which, C, P, R, n, x, rows, out, rng, ed):
+    import numpy as np
+
+    from echopype_b200.commongrid.utils import assign_bins, ping_time_edges, range_edges
+    from echopype_b200.device import ParamPack
+
+    dev = x.device
+    kernels.sv_power(x, rows, C, P, R, want_range=True, out=out, rng=rng)
+    pack = ParamPack(C, P, dev)
+    alpha = pack.cp(np.array([0.0027, 0.0098, 0.0375, 0.0527, 0.0187, 0.0809][:C]))
+    if "noise" in which:
+        holder = {}
+
+        def est():
+            holder["n"] = kernels.noise_estimate(out, rng, alpha, pack, C, P, R, 5, 30)
+
+        ms, mn = timeit(est, a.iters)
+        report("noise_estimate(5x30)", ms, mn, 8 * n, n)
+        sn, sc = torch.empty_like(x), torch.empty_like(x)
+        nz = holder["n"]
+
+        def app():
+            _lib.call("epb_noise_apply", ptr(out), ptr(rng), alpha, ptr(nz), ptr(sn), ptr(sc), None, C, P, R, 5,
+                      ctypes.c_float(3.0), stream())
+
+        ms, mn = timeit(app, a.iters)
+        report("noise_apply", ms, mn, 16 * n, n)
+        del sn, sc
+    pt = ed["Sonar/Beam_group1"]["ping_time"].values
+    rmax = kernels.range_max(x, rows, C, P, R)
+    r_edges = range_edges(rmax, 20.0)
+    p_edges = ping_time_edges(pt, "20s")
+    xb = torch.from_numpy(assign_bins(pt, p_edges)).to(dev)
+    et = torch.from_numpy(r_edges).to(dev)
+    nX = len(p_edges) - 1
+    acc = kernels.new_acc(C, nX, len(r_edges) - 1, dev)
+    if "bins" in which:
+        ms, mn = timeit(lambda: kernels.bin_reduce_law(out, rows, xb, et, acc, C, P, R, nX), a.iters)
+        report("bin_reduce_law", ms, mn, 4 * n, n)
+        ms, mn = timeit(lambda: kernels.bin_reduce(out, rng, xb, et, acc, C, P, R, nX), a.iters)
+        report("bin_reduce_generic_f32", ms, mn, 8 * n, n)
+    if "pipe" in which:
+        ms, mn = timeit(lambda: kernels.pipeline_power_mvbs(x, rows, xb, et, acc, C, P, R, nX, 5, 30), a.iters)
+        report("pipeline(noise 5x30 + mvbs)", ms, mn, 4 * n, n)
+        ms, mn = timeit(lambda: kernels.pipeline_power_mvbs(x, rows, xb, et, acc, C, P, R, nX, 0, 0), a.iters)
+        report("pipeline(sv->mvbs)", ms, mn, 4 * n, n)
+
+
+if __name__ == "__main__":
+    main()
