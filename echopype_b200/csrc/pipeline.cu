@@ -29,6 +29,8 @@ struct RowS {  // per-row constants in shared memory
   RowF f;
   int slot;    // index of the first tile row with the same ping bin, -1: ping outside every bin
   int xb;
+  int bad;     // NaN calibration constants: every output of the row is NaN, but echo_range / bin membership still
+               // follow the raw sample (the staged tile keeps x instead of e for such rows)
 };
 
 struct ColC {  // range-only terms of one column under one row law
@@ -190,6 +192,7 @@ __global__ void __launch_bounds__(kThreads, 2) pipeline_kernel(const Params pr) 
     rs.xb = __ldg(pr.xbin + p0 + tid);
     if (rs.xb < 0 || rs.xb >= pr.nX) rs.xb = -1;
     rs.slot = -1;
+    rs.bad = !(rs.f.c0 == rs.f.c0 && rs.f.c1 == rs.f.c1);
     s_rows[tid] = rs;
   }
   __syncthreads();
@@ -267,7 +270,8 @@ __global__ void __launch_bounds__(kThreads, 2) pipeline_kernel(const Params pr) 
           s[k] += ok ? q : 0.f;
           cn[k] += ok;
         }
-        if (pr.staged) *reinterpret_cast<float4*>(s_tile + (size_t)t * R + 4 * j) = make_float4(e[0], e[1], e[2], e[3]);
+        if (pr.staged && !s_rows[t].bad)
+          *reinterpret_cast<float4*>(s_tile + (size_t)t * R + 4 * j) = make_float4(e[0], e[1], e[2], e[3]);
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -351,6 +355,7 @@ __global__ void __launch_bounds__(kThreads, 2) pipeline_kernel(const Params pr) 
       if (t == Ta) break;
       if (!live) continue;
       const RowF& rf = s_rows[t].f;
+      const bool rbad = s_rows[t].bad != 0;
       if (!shared_law) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -363,9 +368,10 @@ __global__ void __launch_bounds__(kThreads, 2) pipeline_kernel(const Params pr) 
       float osv[4], orr[4], osn[4], osc[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float e = (pr.staged && pr.do_noise) ? ein[k] : fast_exp2(fmaf(ein[k], rf.c1, rf.c0));
+        const bool raw = !(pr.staged && pr.do_noise) || rbad;  // tile holds the raw sample (else e from phase 1)
+        const float e = raw ? fast_exp2(fmaf(ein[k], rf.c1, rf.c0)) : ein[k];
         const float v = e * cc[k].h;  // 10^(Sv/10)
-        const bool x_nan = !(e == e);
+        const bool x_nan = rbad ? !(ein[k] == ein[k]) : !(e == e);
         const bool member = !(rf.nanrange && x_nan);  // echo_range is NaN where the sample is NaN (range.py:143-148)
         float contrib;
         bool good;
