@@ -21,8 +21,8 @@ class CalibrateAZFP(CalibrateBase):
             beam=self.echodata["Sonar/Beam_group1"], vend=self.echodata["Vendor_specific"], user_dict=self.cal_params
         )
 
-    def _power_rows(self, cal_type):
-        """Row records + device-resident counts: (rows, x, C, P, R, None)."""
+    def _power_row_builder(self, cal_type):
+        """Host assembly of the row-setup launch (parameters uploaded once; .build() launches epb_rows_azfp)."""
         if cal_type not in ("Sv", "TS"):
             raise ValueError("cal_type not recognized!")
         if "sound_speed" not in self.env_params:
@@ -55,8 +55,16 @@ class CalibrateAZFP(CalibrateBase):
             if v.ndim == 2:  # (channel, ping_time) duplicates of a per-channel constant
                 v = v[:, 0]
             prm[k] = np.ascontiguousarray(np.broadcast_to(v, (C,)))
-        rows = kernels.rows_azfp(C, P, R, cal_type, prm)
-        x = to_device_f32(bs.data)
+        rb = kernels.azfp_row_builder(C, P, R, cal_type, prm)
+        rb.tau_effective = None
+        return rb
+
+    def _power_rows(self, cal_type):
+        """Row records + device-resident counts: (rows, x, C, P, R, None)."""
+        rb = self._power_row_builder(cal_type)
+        C, P, R = rb.shape
+        rows = rb.build()
+        x = to_device_f32(self.echodata["Sonar/Beam_group1"]["backscatter_r"].data)
         self.rows = rows
         return rows, x, C, P, R, None
 

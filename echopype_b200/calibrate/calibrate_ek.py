@@ -216,14 +216,23 @@ class CalibrateEK(CalibrateBase):
             prm["tau_effective"] = tau_effective.values
         return prm, tau_effective
 
-    def _power_rows(self, cal_type: str):
-        """Row records + device-resident raw samples for the power-sample path: (rows, x, C, P, R, tau_effective)."""
+    def _power_row_builder(self, cal_type: str):
+        """Host assembly of the row-setup launch (parameters uploaded once; .build() launches epb_rows_ek_power)."""
         if cal_type not in ("Sv", "TS"):
             raise ValueError("cal_type must be 'Sv' or 'TS'")
         C, P, R = self._shape()[:3]
         require_cuda()
         prm, tau_effective = self._power_params(cal_type)
-        rows = kernels.rows_ek_power(C, P, R, self._sonar_code(), cal_type, prm, self._is_gpt())
+        rb = kernels.ek_power_row_builder(C, P, R, self._sonar_code(), cal_type, prm, self._is_gpt())
+        rb.tau_effective = tau_effective
+        return rb
+
+    def _power_rows(self, cal_type: str):
+        """Row records + device-resident raw samples for the power-sample path: (rows, x, C, P, R, tau_effective)."""
+        rb = self._power_row_builder(cal_type)
+        C, P, R = rb.shape
+        tau_effective = rb.tau_effective
+        rows = rb.build()
         x = to_device_f32(self.beam["backscatter_r"].data)
         self.rows = rows
         return rows, x, C, P, R, tau_effective

@@ -17,38 +17,56 @@ def alloc_rows(C, P, device=None):
     return torch.empty(int(C) * int(P) * _lib.ROW_BYTES, dtype=torch.uint8, device=device or require_cuda())
 
 
-def rows_ek_power(C, P, R, sonar, cal_type, prm, is_gpt=None):
+class RowBuilder:
+    """Parameters of one row-setup launch, uploaded once; :meth:`build` (re)launches the epb_rows_* kernel."""
+
+    def __init__(self, name, C, P, R, pack, args):
+        self.name, self.shape, self.pack, self.args = name, (int(C), int(P), int(R)), pack, args
+
+    def build(self, rows=None):
+        C, P, R = self.shape
+        rows = rows if rows is not None else alloc_rows(C, P, self.pack.device)
+        _lib.call(self.name, ptr(rows), C, P, R, *self.args, stream())
+        rows._keep = self.pack  # parameters must outlive the asynchronous launch
+        return rows
+
+
+def ek_power_row_builder(C, P, R, sonar, cal_type, prm, is_gpt=None):
     """prm: dict with sample_interval, sound_speed, sound_absorption, transmit_duration_nominal, transmit_power,
     gain_correction, sa_correction, equivalent_beam_angle, frequency_nominal, tau_effective (host arrays)."""
     dev = require_cuda()
     pk = ParamPack(C, P, dev)
-    rows = alloc_rows(C, P, dev)
     sv = cal_type == "Sv"
     null = ParamPack.null()
     gpt = pk.vec(np.asarray(is_gpt, dtype=np.uint8), torch.uint8) if is_gpt is not None else None
-    _lib.call(
-        "epb_rows_ek_power", ptr(rows), C, P, R, sonar, CAL[cal_type],
+    args = (
+        sonar, CAL[cal_type],
         pk.cp(prm["sample_interval"]), pk.cp(prm["sound_speed"]), pk.cp(prm["sound_absorption"]),
         pk.cp(prm["transmit_duration_nominal"]), pk.cp(prm["transmit_power"]), pk.cp(prm["gain_correction"]),
         pk.cp(prm["sa_correction"]) if sv else null, pk.cp(prm["equivalent_beam_angle"]) if sv else null,
-        pk.cp(prm["frequency_nominal"]), pk.cp(prm["tau_effective"]) if sv else null, gpt, stream(),
+        pk.cp(prm["frequency_nominal"]), pk.cp(prm["tau_effective"]) if sv else null, gpt,
     )
-    rows._keep = pk  # parameters must outlive the asynchronous launch
-    return rows
+    return RowBuilder("epb_rows_ek_power", C, P, R, pk, args)
+
+
+def rows_ek_power(C, P, R, sonar, cal_type, prm, is_gpt=None):
+    return ek_power_row_builder(C, P, R, sonar, cal_type, prm, is_gpt).build()
+
+
+def azfp_row_builder(C, P, R, cal_type, prm):
+    dev = require_cuda()
+    pk = ParamPack(C, P, dev)
+    args = (
+        CAL[cal_type], pk.cp(prm["sound_speed"]), pk.cp(prm["sound_absorption"]),
+        pk.cp(prm["transmit_duration_nominal"]), pk.vec(prm["N"]), pk.vec(prm["f_dig"]), pk.vec(prm["L"]),
+        pk.vec(prm["EL"]), pk.vec(prm["DS"]), pk.vec(prm["TVR"]), pk.vec(prm["VTX0"]),
+        pk.vec(prm["equivalent_beam_angle"]), pk.vec(prm["Sv_offset"]),
+    )
+    return RowBuilder("epb_rows_azfp", C, P, R, pk, args)
 
 
 def rows_azfp(C, P, R, cal_type, prm):
-    dev = require_cuda()
-    pk = ParamPack(C, P, dev)
-    rows = alloc_rows(C, P, dev)
-    _lib.call(
-        "epb_rows_azfp", ptr(rows), C, P, R, CAL[cal_type], pk.cp(prm["sound_speed"]), pk.cp(prm["sound_absorption"]),
-        pk.cp(prm["transmit_duration_nominal"]), pk.vec(prm["N"]), pk.vec(prm["f_dig"]), pk.vec(prm["L"]),
-        pk.vec(prm["EL"]), pk.vec(prm["DS"]), pk.vec(prm["TVR"]), pk.vec(prm["VTX0"]),
-        pk.vec(prm["equivalent_beam_angle"]), pk.vec(prm["Sv_offset"]), stream(),
-    )
-    rows._keep = pk
-    return rows
+    return azfp_row_builder(C, P, R, cal_type, prm).build()
 
 
 def rows_ek80_complex(C, P, R, cal_type, waveform_bb, n_beam, prm, is_gpt=None):
@@ -195,10 +213,16 @@ def minmax(a):
     return lo, hi, bool(has_nan)
 
 
+def range_max_into(x, rows, C, P, R, out):
+    """epb_range_max into a 1-element float64 device tensor (asynchronous; -inf when every range is NaN)."""
+    _lib.call("epb_range_max", ptr(x), ptr(rows), C, P, R, ptr(out), stream())
+    return out
+
+
 def range_max(x, rows, C, P, R):
     """Exact float64 nanmax of the echo_range implied by `rows` (x: raw samples for the NaN rule, or None)."""
     out = torch.empty(1, dtype=torch.float64, device=rows.device)
-    _lib.call("epb_range_max", ptr(x), ptr(rows), C, P, R, ptr(out), stream())
+    range_max_into(x, rows, C, P, R, out)
     v = float(out.item())
     return float("nan") if v == float("-inf") else v
 

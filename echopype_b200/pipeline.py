@@ -6,10 +6,19 @@ The reference runs this chain as three calls that each materialise (channel, pin
 output Dataset as ``compute_MVBS`` applied to ``Sv_corrected``) from the raw power samples with a single
 kernel (epb_pipeline_power_mvbs); the full-size intermediates are produced only on request (``keep=``).
 
-Multi-GPU: the volume shards over ``ping_time`` (one process per GPU, each holding a contiguous ping range
-whose length is a multiple of ``ping_num`` on all but the last rank).  The ping-bin grid is global (derived from
-the first / last ping time over all ranks), every rank accumulates (sum, count) for its own pings and ONE
-all-reduce(sum) over the small accumulator grid merges the bins that straddle shard boundaries.
+:class:`FusedPlan` splits the call into the host-side assembly (argument validation, env / cal parameters,
+ping-bin grid; O(channel x ping_time), done once per dataset) and :meth:`FusedPlan.run`, the device work
+(row setup, exact range maximum, the fused kernel, the straddling-bin reduce, mean -> dB).
+
+Host-resident volumes are STREAMED: contiguous (channel, ping-chunk) slabs are copied to the device on a copy
+stream into a ring of slab buffers while the fused kernel consumes the previous slab on the compute stream
+(the kernel accumulates into the same (sum, count) grid, so the result is identical to the one-shot launch).
+
+Multi-GPU: the volume shards over ``ping_time`` (one process per GPU, each holding a contiguous, time-ordered
+ping range whose length is a multiple of ``ping_num`` on all but the last rank).  The ping-bin grid is global
+(derived from the first / last ping time over all ranks).  Each rank accumulates (sum, count) only for the bins
+its own pings touch; ONE all-reduce(sum) over the first / last local bin of every rank merges the bins that
+straddle shard boundaries (:func:`straddle_reduce`).  Two scalar all-reduces (max) fix the global grid.
 """
 
 from typing import Optional, Sequence
@@ -24,17 +33,22 @@ from .commongrid.api import _set_MVBS_attrs
 from .commongrid.utils import _parse_x_bin, assign_bins, ping_time_bin_parsing_and_conversion, ping_time_edges, range_edges
 from .dataset import DataArray, Dataset, EchoData
 from .device import empty, require_cuda
+
 from .utils.prov import echopype_prov_attrs
 
 DIMS = ("channel", "ping_time", "range_sample")
 _KEEP = ("Sv", "echo_range", "Sv_noise", "Sv_corrected")
 
 
-def _all_reduce(t, op, group):
+def _dist():
     import torch.distributed as dist
 
-    dist.all_reduce(t, op=op, group=group)
-    return t
+    return dist
+
+
+def _comm_device(group):
+    dist = _dist()
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
 
 
 def global_ping_edges(ping_time, ping_time_bin, group=None):
@@ -43,13 +57,306 @@ def global_ping_edges(ping_time, ping_time_bin, group=None):
     pt = np.asarray(ping_time).astype("datetime64[ns]").astype(np.int64)
     lo, hi = int(pt.min()), int(pt.max())
     if group is not None:
-        import torch.distributed as dist
-
-        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
-        t = torch.tensor([-lo, hi], dtype=torch.int64, device=dev)
-        _all_reduce(t, dist.ReduceOp.MAX, group)
+        dist = _dist()
+        t = torch.tensor([-lo, hi], dtype=torch.int64, device=_comm_device(group))
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
         lo, hi = -int(t[0].item()), int(t[1].item())
     return ping_time_edges(np.array([lo, hi], dtype="datetime64[ns]"), ping_time_bin)
+
+
+def straddle_reduce(acc, lo, hi, group):
+    """Merge the ping bins shared between ping-sharded ranks.
+
+    acc : this rank's accumulators [C, hi - lo + 1, nR, 4] for the GLOBAL ping bins lo..hi (inclusive).
+    Shards are contiguous and time-ordered, so only the first and the last local bin of a rank can also
+    receive samples on another rank.  Every rank contributes those two bin slices (C x nR x 4 float64 each) to
+    one all-reduce(sum) of a [world, 2, C, nR, 4] buffer (a few KB); afterwards every rank holds the complete
+    sums of its own edge bins.  Interior bins never leave the rank.  Returns acc (updated in place).
+    """
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if world == 1:
+        return acc
+    C, nXl, nR, _ = acc.shape
+    cdev = _comm_device(group)
+    idx = torch.full((world, 2), -1, dtype=torch.int64, device=cdev)
+    idx[rank, 0], idx[rank, 1] = int(lo), int(hi)
+    buf = torch.zeros((world, 2, C, nR, 4), dtype=torch.float64, device=cdev)
+    if nXl > 0:
+        buf[rank, 0] = acc[:, 0].to(cdev)
+        if hi != lo:
+            buf[rank, 1] = acc[:, nXl - 1].to(cdev)
+    dist.all_reduce(idx, op=dist.ReduceOp.MAX, group=group)  # gather (lo, hi) of every rank
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)  # the data-path collective
+    if nXl == 0:
+        return acc
+    idx = idx.cpu()
+    for slot, b in ((0, int(lo)), (nXl - 1, int(hi))):
+        if slot == nXl - 1 and hi == lo:
+            break
+        tot = torch.zeros((C, nR, 4), dtype=torch.float64, device=cdev)
+        for r in range(world):
+            r_lo, r_hi = int(idx[r, 0]), int(idx[r, 1])
+            if r_lo < 0:
+                continue
+            if r_lo == b:
+                tot += buf[r, 0]
+            elif r_hi == b:  # r_hi != r_lo here
+                tot += buf[r, 1]
+        acc[:, slot] = tot.to(acc.device)
+    return acc
+
+
+class FusedPlan:
+    """Host-side assembly of one fused Sv -> noise -> MVBS job; :meth:`run` launches the device work.
+
+    Arguments as :func:`compute_Sv_clean_MVBS`.  ``chunk_pings``: slab length (pings) for streaming a
+    host-resident volume (rounded to a multiple of ``ping_num``); device-resident volumes run in one launch.
+    """
+
+    def __init__(self, echodata: EchoData, ping_num=None, range_sample_num=None, background_noise_max=None,
+                 SNR_threshold="3.0dB", range_bin="20m", ping_time_bin="20s", skipna=True, fill_value=np.nan,
+                 closed="left", range_var_max=None, keep: Sequence[str] = (), group=None, chunk_pings=8192,
+                 **cal_kwargs):
+        waveform_mode = cal_kwargs.pop("waveform_mode", None)
+        encode_mode = cal_kwargs.pop("encode_mode", None)
+        waveform_mode = "BB" if waveform_mode == "FM" else waveform_mode
+        if echodata.sonar_model in ("EK80", "ES80", "EA640"):
+            if waveform_mode is None or encode_mode is None:
+                raise ValueError("waveform_mode and encode_mode must be specified for EK80 calibration")
+            check_input_args_combination(waveform_mode, encode_mode)
+            if encode_mode != "power":
+                raise ValueError("The fused pipeline handles power samples; use compute_Sv for complex samples")
+        if echodata.sonar_model not in CALIBRATOR:
+            raise ValueError(f"Unsupported sonar_model {echodata.sonar_model!r}")
+        for k in keep:
+            if k not in _KEEP:
+                raise ValueError(f"keep entries must be among {_KEEP}")
+        if not isinstance(range_bin, str):
+            raise TypeError("range_bin must be a string")
+        self.rb = _parse_x_bin(range_bin, "range_bin")
+        if closed not in ["right", "left"]:
+            raise ValueError(f"{closed} is not a valid option. Options are 'left' or 'right'.")
+        if not isinstance(ping_time_bin, str):
+            raise TypeError("ping_time_bin must be a string")
+        self.do_noise = ping_num is not None
+        self.snr = extract_dB(SNR_threshold) if self.do_noise else 0.0
+        self.noise_max = extract_dB(background_noise_max) if (self.do_noise and background_noise_max is not None) else None
+        if self.do_noise and (range_sample_num is None or int(ping_num) <= 0 or int(range_sample_num) <= 0):
+            raise ValueError("ping_num and range_sample_num must be positive integers")
+        self.ping_num = int(ping_num) if self.do_noise else 0
+        self.range_sample_num = int(range_sample_num) if self.do_noise else 0
+        self.range_bin, self.ping_time_bin, self.closed = range_bin, ping_time_bin, closed
+        self.skipna, self.fill_value, self.keep, self.group = skipna, fill_value, tuple(keep), group
+        self.range_var_max = range_var_max
+
+        self.dev = require_cuda()
+        self.cal_obj = CALIBRATOR[echodata.sonar_model](
+            echodata, env_params=cal_kwargs.pop("env_params", None), cal_params=cal_kwargs.pop("cal_params", None),
+            ecs_file=cal_kwargs.pop("ecs_file", None), waveform_mode=waveform_mode, encode_mode=encode_mode,
+            drop_last_hanning_zero=cal_kwargs.pop("drop_last_hanning_zero", False), slice_dict={},
+        )
+        if cal_kwargs:
+            raise TypeError(f"unexpected keyword arguments {sorted(cal_kwargs)}")
+        self.beam = echodata[getattr(self.cal_obj, "ed_beam_group", None) or "Sonar/Beam_group1"]
+        self.row_builder = self.cal_obj._power_row_builder("Sv")  # host params are assembled here, once
+        self.C, self.P, self.R = self.row_builder.shape
+
+        # ping-bin grid (global when sharded) and this rank's window lo..hi of it
+        pt = np.asarray(self.beam["ping_time"].values)
+        self.p_edges = global_ping_edges(pt, ping_time_bin, group)
+        xb = assign_bins(pt, self.p_edges, closed)
+        inside = xb[xb >= 0]
+        self.x_lo = int(inside.min()) if inside.size else 0
+        self.x_hi = int(inside.max()) if inside.size else -1
+        self.nX = self.x_hi - self.x_lo + 1
+        self.sorted_pings = bool(np.all(np.diff(pt.astype("datetime64[ns]").astype(np.int64)) >= 0))
+        if group is not None and not self.sorted_pings:
+            raise ValueError("ping-sharded execution needs time-ordered ping_time on every rank")
+        self.xbin = torch.from_numpy(np.where(xb >= 0, xb - self.x_lo, -1).astype(np.int32)).to(self.dev)
+        self.chunk_pings = max(1, int(chunk_pings))
+        self._ring = None
+        self._streams = None
+        self.launches = 0  # kernels of libepb200 launched by run() so far (bench.py "gpu_launches")
+        self.record_events = False  # bench.py: CUDA events around every fused-kernel launch -> kernel_events
+        self.kernel_events = []
+
+    # ---- device work ------------------------------------------------------------------------------------------
+    def _range_edges(self, x, rows):
+        C, P, R = self.C, self.P, self.R
+        if self.range_var_max is not None:
+            rmax = _parse_x_bin(self.range_var_max) + 1e-8
+        else:
+            rmax = kernels.range_max(x, rows, C, P, R)  # exact float64 nanmax(echo_range), commongrid/api.py:108-114
+            self.launches += 2
+            if self.group is not None:
+                dist = _dist()
+                t = torch.tensor([rmax if rmax == rmax else -np.inf], dtype=torch.float64, device=_comm_device(self.group))
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+                rmax = float(t.item())
+        return range_edges(rmax, self.rb)
+
+    def run(self, x=None, finalize=True):
+        """Launch the device work.  x: raw samples (device tensor or host array, default: the EchoData's own).
+        Returns (mvbs [C, nX, nR] float32 device tensor or None, acc, r_edges, kept dict, noise)."""
+        C, P, R = self.C, self.P, self.R
+        x = self.beam["backscatter_r"].data if x is None else x
+        rows = self.row_builder.build()
+        self.launches += 1
+        on_device = isinstance(x, torch.Tensor) and x.is_cuda
+        outs = {k: (empty((C, P, R), device=self.dev) if k in self.keep else None) for k in _KEEP}
+        noise = empty((C, -(-P // self.ping_num)), device=self.dev) if self.do_noise else None
+        if on_device:
+            r_edges = self._range_edges(x, rows)
+            nR = len(r_edges) - 1
+            edges_t = torch.from_numpy(np.ascontiguousarray(r_edges, dtype=np.float64)).to(self.dev)
+            acc = kernels.new_acc(C, max(self.nX, 1), nR, self.dev)
+            if self.record_events:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
+            kernels.pipeline_power_mvbs(
+                x, rows, self.xbin, edges_t, acc, C, P, R, max(self.nX, 1), self.ping_num, self.range_sample_num,
+                noise_max=self.noise_max, snr=self.snr, closed_right=(self.closed == "right"), noise_out=noise,
+                Sv=outs["Sv"], echo_range=outs["echo_range"], Sv_noise=outs["Sv_noise"], Sv_corrected=outs["Sv_corrected"],
+            )
+            if self.record_events:
+                ev[1].record()
+                self.kernel_events.append(ev)
+            self.launches += 2
+        else:
+            acc, r_edges = self._run_streamed(x, rows, outs, noise)
+            nR = len(r_edges) - 1
+        if self.group is not None:
+            straddle_reduce(acc, self.x_lo, self.x_hi, self.group)
+        mvbs = None
+        if finalize:
+            mvbs, _ = kernels.bin_finalize(acc, skipna=self.skipna, fill_value=self.fill_value, to_db=True)
+            self.launches += 1
+        self.rows = rows
+        return mvbs, acc, r_edges, outs, noise
+
+    def _run_streamed(self, x, rows, outs, noise):
+        """Host-resident volume: slabs of (1 channel, chunk pings) move H2D on a copy stream into a 3-slab ring
+        while the fused kernel runs on the previous slab.  Range bins: the exact range maximum needs the NaN tails
+        of every row (range.py:143-148), which are only known once the data has passed through, so the kernel bins
+        against an upper-bound grid (range law at the last sample of every row, NaN tails ignored) and the grid is
+        cut back to the exact maximum afterwards; bins above the exact maximum cannot have members."""
+        C, P, R = self.C, self.P, self.R
+        xh = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float32)))
+        if xh.dtype != torch.float32:
+            xh = xh.float()
+        xh = xh.contiguous()
+        pn = self.ping_num if self.do_noise else 1
+        chunk = min(P, max(pn, (self.chunk_pings // pn) * pn))
+        if self._ring is None or self._ring[0].numel() < chunk * R:
+            self._ring = [torch.empty(chunk * R, dtype=torch.float32, device=self.dev) for _ in range(3)]
+            self._streams = (torch.cuda.Stream(device=self.dev), [torch.cuda.Event() for _ in range(3)],
+                             [torch.cuda.Event() for _ in range(3)])
+        copy_s, filled, freed = self._streams
+        main = torch.cuda.current_stream()
+        ub = kernels.range_max(None, rows, C, P, R) if self.range_var_max is None else _parse_x_bin(self.range_var_max) + 1e-8
+        self.launches += 2
+        if self.group is not None and self.range_var_max is None:
+            dist = _dist()
+            t = torch.tensor([ub if ub == ub else -np.inf], dtype=torch.float64, device=_comm_device(self.group))
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            ub = float(t.item())
+        e_ub = range_edges(ub, self.rb)
+        nR_ub = len(e_ub) - 1
+        edges_t = torch.from_numpy(np.ascontiguousarray(e_ub, dtype=np.float64)).to(self.dev)
+        nX = max(self.nX, 1)
+        acc = kernels.new_acc(C, nX, nR_ub, self.dev)
+        self.launches += 1
+        rmax_t = torch.full((C * (-(-P // chunk)),), -np.inf, dtype=torch.float64, device=self.dev)
+        copy_s.wait_stream(main)
+        nPt = -(-P // pn)
+        i = 0
+        rows_b = rows.view(C * P, -1)
+        for c in range(C):
+            for p0 in range(0, P, chunk):
+                pc = min(chunk, P - p0)
+                slot = i % 3
+                buf = self._ring[slot][: pc * R]
+                with torch.cuda.stream(copy_s):
+                    if i >= 3:
+                        copy_s.wait_event(freed[slot])
+                    buf.copy_(xh[c, p0 : p0 + pc].reshape(-1), non_blocking=True)
+                    filled[slot].record(copy_s)
+                main.wait_event(filled[slot])
+                rsub = rows_b[c * P + p0 : c * P + p0 + pc]
+                sub = lambda t: None if t is None else t[c, p0 : p0 + pc]  # noqa: E731
+                kernels.pipeline_power_mvbs(
+                    buf, rsub, self.xbin[p0 : p0 + pc], edges_t, acc[c : c + 1], 1, pc, R, nX, self.ping_num,
+                    self.range_sample_num, noise_max=self.noise_max, snr=self.snr, closed_right=(self.closed == "right"),
+                    noise_out=None if noise is None else noise[c, p0 // pn : p0 // pn + -(-pc // pn)],
+                    Sv=sub(outs["Sv"]), echo_range=sub(outs["echo_range"]), Sv_noise=sub(outs["Sv_noise"]),
+                    Sv_corrected=sub(outs["Sv_corrected"]),
+                )
+                if self.range_var_max is None:
+                    kernels.range_max_into(buf, rsub, 1, pc, R, rmax_t[i : i + 1])
+                    self.launches += 2
+                self.launches += 1
+                freed[slot].record(main)
+                i += 1
+        _ = nPt
+        if self.range_var_max is None:
+            rmax = float(rmax_t.max().item())
+            rmax = float("nan") if rmax == float("-inf") else rmax
+            if self.group is not None:
+                dist = _dist()
+                t = torch.tensor([rmax if rmax == rmax else -np.inf], dtype=torch.float64, device=_comm_device(self.group))
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+                rmax = float(t.item())
+            r_edges = range_edges(rmax, self.rb)
+        else:
+            r_edges = e_ub
+        nR = len(r_edges) - 1
+        if nR < nR_ub:
+            acc = acc[:, :, :nR].contiguous()
+        return acc, r_edges
+
+    def wrap(self, mvbs, acc, r_edges, outs, noise):
+        """Dataset with the variables / coords / attrs of compute_MVBS (commongrid/api.py:130-189)."""
+        beam = self.beam
+        pe = self.p_edges[self.x_lo : self.x_hi + 1] if self.nX > 0 else self.p_edges[:0]
+        ds = Dataset(coords={"ping_time": pe, "channel": beam["channel"].values, "echo_range": r_edges[:-1]})
+        if mvbs is not None:
+            v = mvbs.cpu().numpy().astype(np.float64)
+            ds["Sv"] = (("channel", "ping_time", "echo_range"), v[:, : self.nX] if self.nX > 0 else v[:, :0])
+            _set_MVBS_attrs(ds)
+            ds["echo_range"].attrs.update({"long_name": "Range distance", "units": "m"})
+            resvalue, reslabel = ping_time_bin_parsing_and_conversion(self.ping_time_bin)
+            ds["Sv"].attrs.update(
+                {
+                    "cell_methods": (
+                        f"ping_time: mean (interval: {resvalue} {reslabel} "
+                        "comment: ping_time is the interval start) "
+                        f"echo_range: mean (interval: {self.rb} meter "
+                        "comment: echo_range is the interval start)"
+                    ),
+                    "binning_mode": "physical units",
+                    "range_meter_interval": str(self.rb) + "m",
+                    "ping_time_interval": self.ping_time_bin,
+                }
+            )
+        else:
+            ds.attrs["acc"] = acc
+        ds["frequency_nominal"] = beam["frequency_nominal"]
+        prov = echopype_prov_attrs(process_type="processing")
+        prov["processing_function"] = "pipeline.compute_Sv_clean_MVBS"
+        ds.attrs.update(prov)
+        if self.do_noise:
+            ds.attrs["noise_estimate"] = DataArray(noise, ("channel", "ping_tile"), name="noise")
+        if self.keep:
+            kept = Dataset(coords={d: beam[d].values for d in DIMS})
+            for k in self.keep:
+                da = DataArray(outs[k], DIMS, name=k)
+                if k == "echo_range":
+                    da.law = {"rows": self.rows, "kind": "echo_range", "minmax": None}
+                kept[k] = da
+            ds.attrs["kept"] = kept
+        ds.attrs["_rows"] = self.rows  # keeps the row table alive for callers that re-run the kernel
+        return ds
 
 
 def compute_Sv_clean_MVBS(
@@ -67,6 +374,7 @@ def compute_Sv_clean_MVBS(
     keep: Sequence[str] = (),
     group=None,
     finalize: bool = True,
+    chunk_pings: int = 8192,
     **cal_kwargs,
 ):
     """
@@ -79,112 +387,15 @@ def compute_Sv_clean_MVBS(
 
     keep : names among {"Sv", "echo_range", "Sv_noise", "Sv_corrected"} to materialise as device arrays; they
         are returned in ``ds.attrs["kept"]`` as a Dataset.
-    group : torch.distributed process group for ping-sharded execution (each rank passes its own shard).
+    group : torch.distributed process group for ping-sharded execution (each rank passes its own shard and gets
+        the MVBS of the ping bins its shard touches; bins straddling two shards are complete on both ranks).
     finalize : when False the raw accumulators (device tensor [C, nX, nR, 4]) are returned in ``attrs["acc"]``.
+    chunk_pings : slab length for streaming a host-resident volume to the device.
     """
-    waveform_mode = cal_kwargs.pop("waveform_mode", None)
-    encode_mode = cal_kwargs.pop("encode_mode", None)
-    waveform_mode = "BB" if waveform_mode == "FM" else waveform_mode
-    if echodata.sonar_model in ("EK80", "ES80", "EA640"):
-        if waveform_mode is None or encode_mode is None:
-            raise ValueError("waveform_mode and encode_mode must be specified for EK80 calibration")
-        check_input_args_combination(waveform_mode, encode_mode)
-        if encode_mode != "power":
-            raise ValueError("The fused pipeline handles power samples; use compute_Sv for complex samples")
-    if echodata.sonar_model not in CALIBRATOR:
-        raise ValueError(f"Unsupported sonar_model {echodata.sonar_model!r}")
-    for k in keep:
-        if k not in _KEEP:
-            raise ValueError(f"keep entries must be among {_KEEP}")
-    if not isinstance(range_bin, str):
-        raise TypeError("range_bin must be a string")
-    rb = _parse_x_bin(range_bin, "range_bin")
-    if closed not in ["right", "left"]:
-        raise ValueError(f"{closed} is not a valid option. Options are 'left' or 'right'.")
-    if not isinstance(ping_time_bin, str):
-        raise TypeError("ping_time_bin must be a string")
-    do_noise = ping_num is not None
-    snr = extract_dB(SNR_threshold) if do_noise else 0.0
-    noise_max = extract_dB(background_noise_max) if (do_noise and background_noise_max is not None) else None
-    if do_noise and (range_sample_num is None or int(ping_num) <= 0 or int(range_sample_num) <= 0):
-        raise ValueError("ping_num and range_sample_num must be positive integers")
-
-    dev = require_cuda()
-    cal_obj = CALIBRATOR[echodata.sonar_model](
-        echodata, env_params=cal_kwargs.pop("env_params", None), cal_params=cal_kwargs.pop("cal_params", None),
-        ecs_file=cal_kwargs.pop("ecs_file", None), waveform_mode=waveform_mode, encode_mode=encode_mode,
-        drop_last_hanning_zero=cal_kwargs.pop("drop_last_hanning_zero", False), slice_dict={},
+    plan = FusedPlan(
+        echodata, ping_num=ping_num, range_sample_num=range_sample_num, background_noise_max=background_noise_max,
+        SNR_threshold=SNR_threshold, range_bin=range_bin, ping_time_bin=ping_time_bin, skipna=skipna, fill_value=fill_value,
+        closed=closed, range_var_max=range_var_max, keep=keep, group=group, chunk_pings=chunk_pings, **cal_kwargs,
     )
-    if cal_kwargs:
-        raise TypeError(f"unexpected keyword arguments {sorted(cal_kwargs)}")
-    rows, x, C, P, R, tau_effective = cal_obj._power_rows("Sv")
-    beam = echodata[getattr(cal_obj, "ed_beam_group", None) or "Sonar/Beam_group1"]
-
-    # bin edges: range from the exact nanmax of echo_range (commongrid/api.py:108-115), pings from the global grid
-    if range_var_max is None:
-        rmax = kernels.range_max(x, rows, C, P, R)
-        if group is not None:
-            import torch.distributed as dist
-
-            t = torch.tensor([rmax if rmax == rmax else -np.inf], dtype=torch.float64, device=dev)
-            _all_reduce(t, dist.ReduceOp.MAX, group)
-            rmax = float(t.item())
-    else:
-        rmax = _parse_x_bin(range_var_max) + 1e-8
-    r_edges = range_edges(rmax, rb)
-    pt = np.asarray(beam["ping_time"].values)
-    p_edges = global_ping_edges(pt, ping_time_bin, group)
-    xbin_np = assign_bins(pt, p_edges, closed)
-    nX, nR = len(p_edges) - 1, len(r_edges) - 1
-    xbin = torch.from_numpy(xbin_np).to(dev)
-    edges_t = torch.from_numpy(np.ascontiguousarray(r_edges, dtype=np.float64)).to(dev)
-    acc = kernels.new_acc(C, nX, nR, dev)
-    outs = {k: (empty((C, P, R), device=dev) if k in keep else None) for k in _KEEP}
-    noise = empty((C, -(-P // int(ping_num))), device=dev) if do_noise else None
-    kernels.pipeline_power_mvbs(
-        x, rows, xbin, edges_t, acc, C, P, R, nX, int(ping_num) if do_noise else 0, int(range_sample_num) if do_noise else 0,
-        noise_max=noise_max, snr=snr, closed_right=(closed == "right"), noise_out=noise, Sv=outs["Sv"],
-        echo_range=outs["echo_range"], Sv_noise=outs["Sv_noise"], Sv_corrected=outs["Sv_corrected"],
-    )
-    if group is not None:
-        import torch.distributed as dist
-
-        _all_reduce(acc, dist.ReduceOp.SUM, group)  # the single data-path collective: straddling bins merge here
-    ds = Dataset(coords={"ping_time": p_edges[:-1], "channel": beam["channel"].values, "echo_range": r_edges[:-1]})
-    if finalize:
-        mvbs, _ = kernels.bin_finalize(acc, skipna=skipna, fill_value=fill_value, to_db=True)
-        ds["Sv"] = (("channel", "ping_time", "echo_range"), mvbs.cpu().numpy().astype(np.float64))
-        _set_MVBS_attrs(ds)
-        ds["echo_range"].attrs.update({"long_name": "Range distance", "units": "m"})
-        resvalue, reslabel = ping_time_bin_parsing_and_conversion(ping_time_bin)
-        ds["Sv"].attrs.update(
-            {
-                "cell_methods": (
-                    f"ping_time: mean (interval: {resvalue} {reslabel} "
-                    "comment: ping_time is the interval start) "
-                    f"echo_range: mean (interval: {rb} meter "
-                    "comment: echo_range is the interval start)"
-                ),
-                "binning_mode": "physical units",
-                "range_meter_interval": str(rb) + "m",
-                "ping_time_interval": ping_time_bin,
-            }
-        )
-    else:
-        ds.attrs["acc"] = acc
-    ds["frequency_nominal"] = beam["frequency_nominal"]
-    prov = echopype_prov_attrs(process_type="processing")
-    prov["processing_function"] = "pipeline.compute_Sv_clean_MVBS"
-    ds.attrs.update(prov)
-    if do_noise:
-        ds.attrs["noise_estimate"] = DataArray(noise, ("channel", "ping_tile"), name="noise")
-    if keep:
-        kept = Dataset(coords={d: beam[d].values for d in DIMS})
-        for k in keep:
-            da = DataArray(outs[k], DIMS, name=k)
-            if k == "echo_range":
-                da.law = {"rows": rows, "kind": "echo_range", "minmax": None}
-            kept[k] = da
-        ds.attrs["kept"] = kept
-    ds.attrs["_rows"] = rows  # keeps the row table alive for callers that re-run the kernel
-    return ds
+    mvbs, acc, r_edges, outs, noise = plan.run(finalize=finalize)
+    return plan.wrap(mvbs, acc, r_edges, outs, noise)

@@ -36,7 +36,8 @@ def _power_host(rng, C, P, R, nan_tail):
     return x
 
 
-def make_ek60(C=4, P=1000, R=1000, seed=1001, device=False, nan_tail=0.005, ping_interval_s=1.0, time_varying=False, ping_offset=0):
+def make_ek60(C=4, P=1000, R=1000, seed=1001, device=False, nan_tail=0.005, ping_interval_s=1.0, time_varying=False, ping_offset=0,
+              backscatter=None):
     """EK60 CW power volume (cfg1 / cfg2).  ``time_varying`` makes sample_interval / pulse length / env
     parameters change along ping_time to exercise the per-row paths."""
     rng = np.random.default_rng(seed)
@@ -50,7 +51,10 @@ def make_ek60(C=4, P=1000, R=1000, seed=1001, device=False, nan_tail=0.005, ping
         dt[:, P // 2 :] = 1.28e-4
         tau[:, P // 3 :] = 0.512e-3
         tau[0, 1] = np.nan  # a dropped ping (multiplexed systems): NaN parameters -> NaN row
-    if device:
+    if backscatter is not None:  # caller-supplied (C, P, R) float32 volume (host array or device tensor)
+        x = backscatter
+        assert tuple(x.shape) == (C, P, R)
+    elif device:
         from . import kernels
 
         x = kernels.synth_fill((C, P, R), kind=0, seed=seed, nan_tail=nan_tail, ping_offset=ping_offset)

@@ -161,3 +161,42 @@ def test_fused_large_property(ep):
     ref = og.ek60(ed_small, "Sv")
     want = ogrid.compute_MVBS(ref["out"], ref["echo_range"], _ns(ed_small["Sonar/Beam_group1"]["ping_time"].values), "20m", "100s")
     og.compare_db(mv[:, 0, :], want["Sv"][:, 0, :], ATOL, "MVBS")
+
+
+@pytest.mark.parametrize("chunk", [10, 35, 4096])
+def test_streamed_host_volume_equals_resident(ep, chunk):
+    """Host-resident volume streamed in (channel, ping-chunk) slabs == the same volume resident on the device
+    (accumulators are integer-count exact; float sums differ only by atomics order)."""
+    import torch
+
+    from echopype_b200 import synth
+
+    ed = synth.make_ek60(3, 83, 1000, seed=9, nan_tail=0.2)
+    kw = dict(ping_num=5, range_sample_num=30, range_bin="20m", ping_time_bin="20s", keep=("Sv_corrected", "echo_range"))
+    host = ep.pipeline.compute_Sv_clean_MVBS(ed, chunk_pings=chunk, **kw)
+    x = torch.from_numpy(ed["Sonar/Beam_group1"]["backscatter_r"].values).cuda()
+    ed_dev = synth.make_ek60(3, 83, 1000, seed=9, backscatter=x)
+    dev = ep.pipeline.compute_Sv_clean_MVBS(ed_dev, **kw)
+    a, b = host["Sv"].values, dev["Sv"].values
+    assert a.shape == b.shape
+    np.testing.assert_array_equal(host["echo_range"].values, dev["echo_range"].values)
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    np.testing.assert_allclose(a, b, atol=2e-5, equal_nan=True)
+    for k in ("Sv_corrected", "echo_range"):
+        np.testing.assert_array_equal(host.attrs["kept"][k].values, dev.attrs["kept"][k].values)
+    np.testing.assert_array_equal(host.attrs["noise_estimate"].values, dev.attrs["noise_estimate"].values)
+
+
+def test_streamed_short_volume_trims_range_grid(ep):
+    """Every ping NaN-padded beyond sample 300: the exact range maximum (and so the number of range bins) is
+    smaller than the upper bound the streamed kernel bins against; the grid must be cut back to the exact one."""
+    from echopype_b200 import synth
+
+    ed = synth.make_ek60(2, 40, 1000, seed=3, nan_tail=0.0)
+    x = ed["Sonar/Beam_group1"]["backscatter_r"].values.copy()
+    x[:, :, 300:] = np.nan
+    ed = synth.make_ek60(2, 40, 1000, seed=3, backscatter=x)
+    ds = ep.pipeline.compute_Sv_clean_MVBS(ed, range_bin="10m", ping_time_bin="20s", chunk_pings=16)
+    ref, mv, marg_bins, _ = _oracle_chain(ed, "ek60", None, None, None, "3.0dB", "10m", "20s")
+    assert ds["Sv"].values.shape == mv["Sv"].shape
+    _check_mvbs(ds["Sv"].values, mv["Sv"], marg_bins)

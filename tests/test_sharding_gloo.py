@@ -1,0 +1,81 @@
+"""Host logic of ping-sharded execution on CPU with the gloo backend (world_size 2 and 3): the global ping-bin
+grid (pipeline.global_ping_edges) and the straddling-bin reduce (pipeline.straddle_reduce) give every rank the
+same (sum, count) accumulators for the bins it touches as a single-process reduction over the whole volume."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _global_case(seed, P, bounds):
+    """Deterministic 'volume': per ping a [C, nR, 4] contribution; ping times 1 s apart, 7 s bins."""
+    rng = np.random.default_rng(seed)
+    C, nR = 2, 5
+    contrib = rng.integers(0, 1000, size=(P, C, nR, 4)).astype(np.float64)  # integers: sums are order independent
+    t0 = np.datetime64("2018-07-01T00:00:03", "ns")
+    pt = t0 + (np.arange(P) * 1_000_000_000).astype("timedelta64[ns]")
+    return contrib, pt, bounds
+
+
+def _worker(rank, world, port, seed, P, bounds, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from echopype_b200 import pipeline
+        from echopype_b200.commongrid.utils import assign_bins
+
+        contrib, pt, bounds = _global_case(seed, P, bounds)
+        a, b = bounds[rank], bounds[rank + 1]
+        edges = pipeline.global_ping_edges(pt[a:b], "7s", dist.group.WORLD)
+        xb = assign_bins(pt[a:b], edges)
+        lo, hi = int(xb.min()), int(xb.max())
+        acc = torch.zeros((2, hi - lo + 1, 5, 4), dtype=torch.float64)
+        for i, k in enumerate(xb):
+            acc[:, k - lo] += torch.from_numpy(contrib[a + i])
+        pipeline.straddle_reduce(acc, lo, hi, dist.group.WORLD)
+        q.put((rank, lo, hi, acc.numpy(), edges.astype("datetime64[ns]").astype(np.int64)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,P,bounds", [
+    (2, 40, [0, 20, 40]),       # boundary inside a 7 s bin
+    (2, 42, [0, 21, 42]),
+    (3, 30, [0, 10, 12, 30]),   # middle rank lies inside a single bin shared with both neighbours
+    (3, 35, [0, 4, 18, 35]),
+])
+def test_straddle_reduce_matches_single_process(world, P, bounds):
+    from echopype_b200.commongrid.utils import assign_bins, ping_time_edges
+
+    seed = 7
+    contrib, pt, _ = _global_case(seed, P, bounds)
+    edges = ping_time_edges(pt, "7s")
+    xb = assign_bins(pt, edges)
+    want = np.zeros((2, len(edges) - 1, 5, 4))
+    for i, k in enumerate(xb):
+        want[:, k] += contrib[i]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, seed, P, bounds, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, lo, hi, acc, e in got:
+        np.testing.assert_array_equal(e, edges.astype("datetime64[ns]").astype(np.int64))  # same global grid on every rank
+        np.testing.assert_array_equal(acc, want[:, lo : hi + 1])
