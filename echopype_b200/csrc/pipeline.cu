@@ -18,7 +18,7 @@
 // reduction over runs of equal bin index, accumulated per CTA in shared memory and flushed once per touched
 // cell with float64 atomics.  When all rows of a tile share one range law (the normal case: constant
 // sample interval / sound speed / absorption) all range-only terms are computed once per column.
-#include "sample_math.cuh"
+#include "pipeline_common.cuh"
 
 namespace {
 using namespace epb;
@@ -32,30 +32,6 @@ struct RowS {  // per-row constants in shared memory
   int bad;     // NaN calibration constants: every output of the row is NaN, but echo_range / bin membership still
                // follow the raw sample (the staged tile keeps x instead of e for such rows)
 };
-
-struct ColC {  // range-only terms of one column under one row law
-  float g;     // 10^((Sv - TL)/10) / e : phase 1 factor (NaN for n < n_start)
-  float h;     // 10^(Sv/10) / e        : R'^2 * 10^(2 alpha R'/10)
-  float tl;    // 10^(TL/10)            : max(R,1)^2 * 10^(2 alpha R/10)
-  float rr;    // echo_range
-};
-
-__device__ __forceinline__ ColC col_consts(const RowF& r, int n) {
-  const float nf = (float)n;
-  const float rp = tvg_range_of(r, nf);
-  const float rr = range_of(r, nf);
-  const float rm = (rr >= 1.f) ? rr : 1.f;
-  ColC c;
-  float hh = (rp * rp) * fast_exp2(r.c2 * rp);
-  hh = (rp < 0.f) ? CUDART_NAN_F : hh;          // log10 of a negative range is NaN in the reference
-  c.h = (n >= r.n_start) ? hh : CUDART_NAN_F;   // R' <= 0 -> NaN (calibrate_ek.py:107)
-  c.tl = (rm * rm) * fast_exp2(r.c2 * rr);
-  c.g = __fdividef(c.h, c.tl);
-  c.rr = rr;
-  return c;
-}
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 struct Cell {
   float sum;
@@ -90,34 +66,6 @@ __device__ __forceinline__ void warp_runs_to_smem(int key, float s, int cnt, Cel
   if (((lane == 31) || (next != run)) && key >= 0) cell_add(cells + key, s, cnt);
 }
 
-// smallest n in [0, R] with law_range(row, n) >= edge (closed left) / > edge (closed right)
-__device__ int first_at_or_above(const epb_row& r, int R, double edge, int closed_right) {
-  int lo = 0, hi = R;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    const double v = law_range(r, mid);
-    if (closed_right ? (v > edge) : (v >= edge))
-      hi = mid;
-    else
-      lo = mid + 1;
-  }
-  return lo;
-}
-
-__device__ __forceinline__ int key_of(const int* __restrict__ bnd, int nR, int n) {
-  // number of boundaries <= n, minus 1; valid bins are 0..nR-1
-  int lo = 0, hi = nR + 1;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (bnd[mid] <= n)
-      lo = mid + 1;
-    else
-      hi = mid;
-  }
-  const int k = lo - 1;
-  return (k >= 0 && k < nR) ? k : -1;
-}
-
 struct Params {
   const float* x;
   const epb_row* rows;
@@ -133,9 +81,11 @@ struct Params {
   int R, nR, tile, rs_num, closed_right, do_noise, staged;
   float noise_max_lin;  // NaN: no cap
   float snr_fac;        // 1 + 10^(SNR/10)
+  const int* gate;      // NULL, or device flag: run only when *gate != 0 (the fast path declined the launch)
 };
 
 __global__ void __launch_bounds__(kThreads, 2) pipeline_kernel(const Params pr) {
+  if (pr.gate && *pr.gate == 0) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int R = pr.R, nR = pr.nR, T = pr.tile;
   // ---- shared-memory carve-up ------------------------------------------------------------------------------
@@ -440,11 +390,18 @@ extern "C" epb_i64 epb_pipeline_smem_bytes(epb_i64 R, int nR, int tile, int do_n
   return (epb_i64)pipeline_smem(R, nR, tile, do_noise, staged);
 }
 
+int epb_pipeline_fast_try(const float* x, const epb_row* rows, const int* xbin, const double* r_edges, int nR,
+                          int closed_right, double* acc, float* noise_out, long long C, long long P, long long R,
+                          long long nX, int ping_num, int range_sample_num, float noise_max_lin, float snr_lin,
+                          int* irregular, cudaStream_t s);
+
+extern "C" epb_i64 epb_pipeline_workspace_bytes(void) { return 256; }
+
 extern "C" int epb_pipeline_power_mvbs(const float* backscatter_r, const epb_row* rows, const int* xbin,
                                        const double* r_edges, int nR, int closed_right, double* acc, float* noise_out,
                                        float* Sv, float* echo_range, float* Sv_noise, float* Sv_corrected, epb_i64 C,
                                        epb_i64 P, epb_i64 R, epb_i64 nX, int ping_num, int range_sample_num,
-                                       float noise_max, float snr_threshold, void* stream) {
+                                       float noise_max, float snr_threshold, void* workspace, void* stream) {
   EPB_REQUIRE(backscatter_r && rows && xbin && r_edges && acc, "NULL pointer");
   EPB_REQUIRE(C > 0 && P > 0 && R > 0 && R < (1 << 24) && nX > 0, "bad shape");
   EPB_REQUIRE(R % 4 == 0, "fused pipeline needs range_sample % 4 == 0 (use the separate kernels otherwise)");
@@ -464,6 +421,14 @@ extern "C" int epb_pipeline_power_mvbs(const float* backscatter_r, const epb_row
   pr.rs_num = range_sample_num, pr.closed_right = closed_right;
   pr.noise_max_lin = (noise_max == noise_max) ? (float)pow(10.0, (double)noise_max / 10.0) : nanf("");
   pr.snr_fac = (float)(1.0 + pow(10.0, (double)snr_threshold / 10.0));
+  pr.gate = nullptr;
+  // fast path (pipeline_fast.cu): regular volumes without full-size outputs.  A device-side flag written by its
+  // classification kernel decides which of the two kernels does the work; the other returns immediately.
+  if (workspace && !Sv && !echo_range && !Sv_noise && !Sv_corrected && ((uintptr_t)workspace % 4) == 0 &&
+      epb_pipeline_fast_try(backscatter_r, rows, xbin, r_edges, nR, closed_right, acc, noise_out, C, P, R, nX, ping_num,
+                            range_sample_num, pr.noise_max_lin, (float)pow(10.0, (double)snr_threshold / 10.0),
+                            (int*)workspace, (cudaStream_t)stream))
+    pr.gate = (const int*)workspace;
   // stage the tile in shared memory when two CTAs per SM still fit, else when one fits, else stream from global
   pr.staged = 1;
   size_t smem = pipeline_smem(R, nR, pr.tile, pr.do_noise, 1);

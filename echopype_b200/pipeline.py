@@ -117,7 +117,7 @@ class FusedPlan:
     def __init__(self, echodata: EchoData, ping_num=None, range_sample_num=None, background_noise_max=None,
                  SNR_threshold="3.0dB", range_bin="20m", ping_time_bin="20s", skipna=True, fill_value=np.nan,
                  closed="left", range_var_max=None, keep: Sequence[str] = (), group=None, chunk_pings=8192,
-                 **cal_kwargs):
+                 fast=True, **cal_kwargs):
         waveform_mode = cal_kwargs.pop("waveform_mode", None)
         encode_mode = cal_kwargs.pop("encode_mode", None)
         waveform_mode = "BB" if waveform_mode == "FM" else waveform_mode
@@ -149,6 +149,7 @@ class FusedPlan:
         self.range_bin, self.ping_time_bin, self.closed = range_bin, ping_time_bin, closed
         self.skipna, self.fill_value, self.keep, self.group = skipna, fill_value, tuple(keep), group
         self.range_var_max = range_var_max
+        self.fast = bool(fast)  # False: force the general kernel (tests compare the two)
 
         self.dev = require_cuda()
         self.cal_obj = CALIBRATOR[echodata.sonar_model](
@@ -217,7 +218,7 @@ class FusedPlan:
             kernels.pipeline_power_mvbs(
                 x, rows, self.xbin, edges_t, acc, C, P, R, max(self.nX, 1), self.ping_num, self.range_sample_num,
                 noise_max=self.noise_max, snr=self.snr, closed_right=(self.closed == "right"), noise_out=noise,
-                Sv=outs["Sv"], echo_range=outs["echo_range"], Sv_noise=outs["Sv_noise"], Sv_corrected=outs["Sv_corrected"],
+                fast=self.fast, Sv=outs["Sv"], echo_range=outs["echo_range"], Sv_noise=outs["Sv_noise"], Sv_corrected=outs["Sv_corrected"],
             )
             if self.record_events:
                 ev[1].record()
@@ -288,6 +289,7 @@ class FusedPlan:
                 kernels.pipeline_power_mvbs(
                     buf, rsub, self.xbin[p0 : p0 + pc], edges_t, acc[c : c + 1], 1, pc, R, nX, self.ping_num,
                     self.range_sample_num, noise_max=self.noise_max, snr=self.snr, closed_right=(self.closed == "right"),
+                    fast=self.fast,
                     noise_out=None if noise is None else noise[c, p0 // pn : p0 // pn + -(-pc // pn)],
                     Sv=sub(outs["Sv"]), echo_range=sub(outs["echo_range"]), Sv_noise=sub(outs["Sv_noise"]),
                     Sv_corrected=sub(outs["Sv_corrected"]),
@@ -375,6 +377,7 @@ def compute_Sv_clean_MVBS(
     group=None,
     finalize: bool = True,
     chunk_pings: int = 8192,
+    fast: bool = True,
     **cal_kwargs,
 ):
     """
@@ -395,7 +398,7 @@ def compute_Sv_clean_MVBS(
     plan = FusedPlan(
         echodata, ping_num=ping_num, range_sample_num=range_sample_num, background_noise_max=background_noise_max,
         SNR_threshold=SNR_threshold, range_bin=range_bin, ping_time_bin=ping_time_bin, skipna=skipna, fill_value=fill_value,
-        closed=closed, range_var_max=range_var_max, keep=keep, group=group, chunk_pings=chunk_pings, **cal_kwargs,
+        closed=closed, range_var_max=range_var_max, keep=keep, group=group, chunk_pings=chunk_pings, fast=fast, **cal_kwargs,
     )
     mvbs, acc, r_edges, outs, noise = plan.run(finalize=finalize)
     return plan.wrap(mvbs, acc, r_edges, outs, noise)

@@ -200,3 +200,61 @@ def test_streamed_short_volume_trims_range_grid(ep):
     ref, mv, marg_bins, _ = _oracle_chain(ed, "ek60", None, None, None, "3.0dB", "10m", "20s")
     assert ds["Sv"].values.shape == mv["Sv"].shape
     _check_mvbs(ds["Sv"].values, mv["Sv"], marg_bins)
+
+
+FAST_CASES = [
+    # kind, (C, P, R), time_varying, ping_num, range_sample_num, noise_max, range_bin, ping_time_bin, closed
+    ("ek60", (4, 103, 1000), False, 5, 30, None, "20m", "20s", "left"),     # partial last tile, R4 not a warp multiple
+    ("ek60", (2, 200, 4096), False, 5, 30, None, "20m", "20s", "left"),     # the benchmark shape (1024 threads)
+    ("ek60", (2, 97, 2048), False, 5, 30, "-125.0dB", "10m", "7s", "right"),  # ping bins straddle tiles, noise cap
+    ("ek60", (3, 64, 512), False, 8, 16, None, "5m", "1min", "left"),       # largest register tile
+    ("ek60", (3, 50, 516), False, 1, 20, None, "5m", "3s", "left"),         # single-row tiles
+    ("ek60", (2, 61, 2048), True, 5, 30, None, "10m", "7s", "left"),        # irregular (law changes) -> general kernel via gate
+    ("ek60", (2, 45, 1000), False, None, None, None, "20m", "20s", "left"),  # no noise removal
+    ("azfp", (4, 55, 2048), False, None, None, None, "10m", "10s", "left"),
+    ("azfp", (2, 43, 512), False, 4, 16, None, "2m", "10s", "left"),
+    ("ek80", (3, 37, 1024), False, 6, 40, None, "20m", "12s", "left"),      # GPT channel with the double TVG offset
+]
+
+
+@pytest.mark.parametrize("kind,shape,tv,pn,rn,nmax,rb,tb,closed", FAST_CASES)
+def test_fast_kernel_equals_general_kernel(ep, kind, shape, tv, pn, rn, nmax, rb, tb, closed):
+    """The persistent register-resident kernel (pipeline_fast.cu) against the general kernel (pipeline.cu) on the raw
+    accumulators: member / NaN-member counts bit-identical, linear sums within float32 accumulation noise."""
+    from echopype_b200 import synth
+
+    kw = {}
+    if kind == "ek60":
+        ed = synth.make_ek60(*shape, seed=31, nan_tail=0.2, time_varying=tv)
+    elif kind == "azfp":
+        ed = synth.make_azfp(*shape, seed=32)
+        kw = {"env_params": {"salinity": 30.0, "pressure": 50.0}}
+    else:
+        ed = synth.make_ek80(C=shape[0], P=shape[1], R=shape[2], mode="CW", encode="power", gpt_channel=1, nan_tail=0.2, seed=33)
+        kw = {"waveform_mode": "CW", "encode_mode": "power"}
+    args = dict(ping_num=pn, range_sample_num=rn, background_noise_max=nmax, range_bin=rb, ping_time_bin=tb, closed=closed,
+                finalize=False, **kw)
+    a = ep.pipeline.compute_Sv_clean_MVBS(ed, fast=True, **args)
+    b = ep.pipeline.compute_Sv_clean_MVBS(ed, fast=False, **args)
+    fa, fb = a.attrs["acc"].cpu().numpy(), b.attrs["acc"].cpu().numpy()
+    assert fa.shape == fb.shape
+    if pn:
+        np.testing.assert_allclose(a.attrs["noise_estimate"].values, b.attrs["noise_estimate"].values, atol=2e-5, equal_nan=True)
+    total = fa[..., 1] + fa[..., 2]
+    np.testing.assert_array_equal(total, fb[..., 1] + fb[..., 2])  # members per bin: exact
+    # the SNR test may flip for samples within float rounding of the threshold: allow a handful per grid
+    flips = np.abs(fa[..., 1] - fb[..., 1])
+    assert flips.sum() <= max(2, 2e-5 * total.sum()), (flips.sum(), total.sum())
+    ok = (flips == 0) & (fb[..., 1] > 0)
+    np.testing.assert_allclose(fa[..., 0][ok], fb[..., 0][ok], rtol=2e-5)
+    assert ok.sum() > 0.9 * (fb[..., 1] > 0).sum()
+
+
+def test_fast_kernel_vs_oracle_benchmark_shape(ep):
+    """Benchmark-shaped tile geometry (R = 4096, ping_num 5, 20 s bins) through the fast kernel against the oracle."""
+    from echopype_b200 import synth
+
+    ed = synth.make_ek60(2, 120, 4096, seed=77, nan_tail=0.1)
+    ds = ep.pipeline.compute_Sv_clean_MVBS(ed, ping_num=5, range_sample_num=30, range_bin="20m", ping_time_bin="20s")
+    ref, mv, marg_bins, margin = _oracle_chain(ed, "ek60", 5, 30, None, "3.0dB", "20m", "20s")
+    _check_mvbs(ds["Sv"].values, mv["Sv"], marg_bins)
