@@ -155,7 +155,7 @@ __device__ __noinline__ void flush_group(float4 s4, float4 g4, unsigned nanp, in
   }
 }
 
-struct Producer {  // TMA issue cursor, used by thread 0 only (kept in shared memory, not in registers)
+struct Producer {  // TMA issue cursor, used by one thread only (kept in shared memory, not in registers)
   int tile;        // next local tile to issue
   int slot;        // ring slot of its first row
   int rows;        // rows issued so far
@@ -163,21 +163,28 @@ struct Producer {  // TMA issue cursor, used by thread 0 only (kept in shared me
   int c, it;       // channel / ping tile of `tile`
 };
 
+// words of an epb_row (as 48 x 32 bit) that make up the range law: p0..p4, off1, off2, r0, a, two_alpha (0-19),
+// n_start, law, azfp_N (28-30), a_h..bp_l, two_alpha_f, slog2 (32-39), c2, spow (44-45)
+__device__ __forceinline__ bool law_word(int w) {
+  return (w < 20) || (w >= 28 && w <= 30) || (w >= 32 && w <= 39) || w == 44 || w == 45;
+}
+
 // T rows per tile (ping_num), G column groups of four per thread (threads = R / (4 G))
 template <int T, int G, bool kNoise>
 __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams pr) {
   if (*pr.irregular) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long s_full[kMaxTilesInFlight];  // one mbarrier per tile in flight
-  __shared__ TileInfo s_tile[3];  // tile g-1 may still be read while g+1 is written
+  __shared__ TileInfo s_tile[3];  // tile li-1 may still be read while li+2 is written: see describe_store
   __shared__ unsigned int s_min[2];
   __shared__ int s_hasnan[2];   // a thread saw a NaN sample in the tile: range-tile counts come from s_colcnt
-  __shared__ epb_row s_lawrow;  // first row of the current range-law segment
+  __shared__ unsigned s_lawwords[48];  // first row of the current range-law segment (producer warp only)
   __shared__ Producer s_prod;
-  __shared__ int s_desc_c, s_desc_it;  // channel / ping tile of the next tile to describe (warp 0)
   const int R = pr.R, nR = pr.nR, N = pr.nslots;
   const int tid = threadIdx.x;
   const int nth = blockDim.x;
+  const int lane = tid & 31;
+  const bool prod_warp = (tid >> 5) == (nth >> 5) - 1;  // the last warp doubles as descriptor / TMA producer
   const int nRt = kNoise ? (R + pr.rs_num - 1) / pr.rs_num : 0;
   // ---- dynamic shared memory ----------------------------------------------------------------------------------------
   // [h R][ginv R][colsum R][keys R int16][colcnt R bytes][pad to 16][ring N x R][edges nR+1 f64][bounds nR+1][valid nRt]
@@ -198,7 +205,7 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
   const int nPt = pr.nPt;
   const int NB = N / T + 1;  // tile barriers in rotation (>= tiles in flight)
   const uint32_t row_bytes = (uint32_t)R * 4u;
-  // thread 0: issue whole tiles while their rows fit in the ring given `consumed` rows are free again
+  // one thread: issue whole tiles while their rows fit in the ring given `consumed` rows are free again
   // and the tile that last used the tile's mbarrier (tile - NB) has been consumed (last_done = last consumed tile)
   auto issue_tiles = [&](int consumed, int last_done) {
     Producer p = s_prod;
@@ -221,41 +228,61 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
     s_prod = p;
   };
 
-  // tile descriptor: row constants, accumulator-cell runs, law change (warp 0, one tile ahead of its use)
-  auto describe = [&](TileInfo* ti, bool first) {
-    const int lane = tid & 31;
-    const int c = s_desc_c, itile = s_desc_it;
-    const long long p0 = (long long)itile * T;
+  // Tile descriptor (producer warp): row constants, accumulator-cell runs, law change.  Split in two so that the
+  // global loads are in flight while the warp does its share of the tile: describe_load early, describe_store late.
+  struct DescRegs {
+    float c0, c1;
+    int xb;
+    unsigned w0, w1;  // words lane and lane + 32 of the tile's first row record
+    int c, itile;
+  };
+  auto describe_load = [&](int li) {  // local tile li (< ntl)
+    DescRegs d;
+    const long long g = g0 + li;
+    d.c = (int)(g / nPt);
+    d.itile = (int)(g - (long long)d.c * nPt);
+    const long long p0 = (long long)d.itile * T;
     const int Ta = (int)((p0 + T <= pr.P) ? T : (pr.P - p0));
-    const long long row0 = (long long)c * pr.P + p0;
-    int xb = -1;
+    const long long row0 = (long long)d.c * pr.P + p0;
+    d.c0 = 0.f, d.c1 = 0.f, d.xb = -1;
     if (lane < Ta) {
       const epb_row* r = pr.rows + row0 + lane;
-      ti->rc[lane] = make_float2(__ldg(&r->c0), __ldg(&r->c1));
-      xb = __ldg(pr.xbin + p0 + lane);
-      if (xb < 0 || xb >= pr.nX) xb = -1;
+      d.c0 = __ldg(&r->c0);
+      d.c1 = __ldg(&r->c1);
+      d.xb = __ldg(pr.xbin + p0 + lane);
     }
+    const unsigned* w = reinterpret_cast<const unsigned*>(pr.rows + row0);
+    d.w0 = __ldg(w + lane);
+    d.w1 = (lane < 16) ? __ldg(w + 32 + lane) : 0u;
+    return d;
+  };
+  auto describe_store = [&](const DescRegs& d, TileInfo* ti, bool first) {
+    const long long p0 = (long long)d.itile * T;
+    const int Ta = (int)((p0 + T <= pr.P) ? T : (pr.P - p0));
+    int xb = d.xb;
+    if (xb < 0 || xb >= pr.nX) xb = -1;
+    if (lane < Ta) ti->rc[lane] = make_float2(d.c0, d.c1);
     const int prev = __shfl_up_sync(0xffffffffu, xb, 1);
     const bool head = (lane < Ta) && (lane == 0 || prev != xb);
     const unsigned heads = __ballot_sync(0xffffffffu, head);
     if (head) {
       const int r = __popc(heads & ((1u << lane) - 1u));
-      ti->run_cell[r] = (xb >= 0) ? (int)((long long)c * pr.nX + xb) : -1;
+      ti->run_cell[r] = (xb >= 0) ? (int)((long long)d.c * pr.nX + xb) : -1;
       const unsigned later = heads & ~((2u << lane) - 1u);
       ti->run_end[r] = later ? (__ffs(later) - 1) : Ta;
+    }
+    bool diff = law_word(lane) && (d.w0 != s_lawwords[lane]);
+    if (lane < 16) diff = diff || (law_word(lane + 32) && d.w1 != s_lawwords[lane + 32]);
+    const bool chg = first || __any_sync(0xffffffffu, diff);
+    if (chg) {
+      s_lawwords[lane] = d.w0;
+      if (lane < 16) s_lawwords[lane + 32] = d.w1;
     }
     if (lane == 0) {
       ti->nruns = __popc(heads);
       ti->Ta = Ta;
-      ti->row0 = row0;
-      const epb_row& r0 = pr.rows[row0];
-      const bool chg = first || !same_law(s_lawrow, r0);
+      ti->row0 = (long long)d.c * pr.P + p0;
       ti->lawchg = chg;
-      if (chg) s_lawrow = r0;
-      if (itile + 1 == nPt)
-        s_desc_it = 0, s_desc_c = c + 1;
-      else
-        s_desc_it = itile + 1;
     }
     __syncwarp();
   };
@@ -268,12 +295,14 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
     s_hasnan[0] = 0, s_hasnan[1] = 0;
     const int c0 = (int)(g0 / nPt), it0 = (int)(g0 - (long long)c0 * nPt);
     s_prod.tile = 0, s_prod.slot = 0, s_prod.rows = 0, s_prod.bar = 0, s_prod.c = c0, s_prod.it = it0;
-    s_desc_c = c0, s_desc_it = it0;
   }
   for (int k = tid; k <= nR; k += nth) s_edges[k] = pr.edges[k];
   __syncthreads();
-  if (tid == 0) issue_tiles(0, -1);
-  if (tid < 32) describe(&s_tile[0], true);
+  if (prod_warp) {
+    if (lane == 0) issue_tiles(0, -1);
+    describe_store(describe_load(0), &s_tile[0], true);
+    if (ntl > 1) describe_store(describe_load(1), &s_tile[1], false);
+  }
   __syncthreads();
 
   // group g of this thread owns columns n0 + g * 4 * nth .. +3
@@ -303,10 +332,13 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
   for (int li = 0; li < ntl; ++li) {
     const int it = li & 1;
     const TileInfo* ti = &s_tile[tsel];
-    const int tnext = (tsel == 2) ? 0 : tsel + 1;
+    const int tprev = (tsel == 0) ? 2 : tsel - 1;  // slot of tile li+2 (= slot of tile li-1, which is finished)
+    tsel = (tsel == 2) ? 0 : tsel + 1;
     const int Ta = ti->Ta;
-    if (tid < 32 && li + 1 < ntl) describe(&s_tile[tnext], false);  // visible after this tile's barriers
-    tsel = tnext;
+    // producer warp: start the descriptor loads of tile li+2 now, store them after barrier (A)
+    DescRegs dreg;
+    const bool have_desc = prod_warp && (li + 2 < ntl);
+    if (have_desc) dreg = describe_load(li + 2);
 
     // ---- new range-law segment: flush, recompute boundaries, column terms, keys ------------------------------------
     if (ti->lawchg) {
@@ -359,7 +391,7 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
       int slot = slot0;
 #pragma unroll
       for (int t = 0; t < T; ++t) {
-        const float2 rc = ti->rc[t];  // rows beyond Ta: stale constants, stale slot data, never used
+        const float2 rc = ti->rc[t];  // rows beyond Ta: stale constants, stale slot data, zeroed below
 #pragma unroll
         for (int g = 0; g < G; ++g) {
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -394,29 +426,44 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
         for (int t = 1; t < T; ++t) se[g][k] += e[g][t][k];
         chk += se[g][k];
       }
-    const bool clean = (chk * 0.f == 0.f);  // every e of this thread's T x 4 G samples is finite (no NaN sample)
+    // Rare: some sample of this thread is NaN (padded ping) or e overflowed.  Remember where (bit t*4+k per group),
+    // make the column sums NaN-free and replace the sample by -2 (never survives a threshold >= -1).
+    unsigned nanmask[G];
+    int cn[G][4];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      nanmask[g] = 0u;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) cn[g][k] = Ta;
+    }
+    if (!(chk * 0.f == 0.f)) {
+      if (kNoise) s_hasnan[it] = 1;
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          se[g][k] = 0.f;
+          cn[g][k] = 0;
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            const float v = e[g][t][k];
+            const bool ok = (v * 0.f == 0.f);
+            if (t < Ta) {
+              se[g][k] += ok ? v : 0.f;
+              cn[g][k] += ok;
+              if (!ok) nanmask[g] |= 1u << (4 * t + k);
+            }
+            e[g][t][k] = ok ? v : -2.f;
+          }
+        }
+    }
 
     float noise_lin = 0.f;
     if (kNoise) {
       // ---- phase 1: per-column sums of 10^((Sv-TL)/10) -> range-tile means -> min ----------------------------------------
-      if (!clean) s_hasnan[it] = 1;
 #pragma unroll
       for (int g = 0; g < G; ++g) {
         const int ng = n0 + g * 4 * nth;
-        int cn[4] = {Ta, Ta, Ta, Ta};
-        if (!clean) {  // rare: recount with NaN samples skipped (nanmean)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            se[g][k] = 0.f;
-            cn[k] = 0;
-#pragma unroll
-            for (int t = 0; t < T; ++t) {
-              const bool ok = (t < Ta) && (e[g][t][k] == e[g][t][k]);
-              se[g][k] += ok ? e[g][t][k] : 0.f;
-              cn[k] += ok;
-            }
-          }
-        }
         if (ng < R) {
           const float4 g4 = *reinterpret_cast<const float4*>(s_ginv + ng);
           const float gi[4] = {g4.x, g4.y, g4.z, g4.w};
@@ -426,47 +473,64 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
           for (int k = 0; k < 4; ++k) {
             const bool ok = (gi[k] == gi[k]);                   // Sv defined at this column (ginv = inf: Sv = -inf, adds 0)
             cs[k] = ok ? __fdividef(se[g][k], gi[k]) : 0.f;      // sum of 10^((Sv-TL)/10)
-            cc |= (ok ? (unsigned)cn[k] : 0u) << (8 * k);
+            cc |= (ok ? (unsigned)cn[g][k] : 0u) << (8 * k);
           }
           *reinterpret_cast<float4*>(s_colsum + ng) = make_float4(cs[0], cs[1], cs[2], cs[3]);
           *reinterpret_cast<unsigned*>(s_colcnt + ng) = cc;
         }
       }
       __syncthreads();  // (A) the tile's slots are free; column sums visible
-      if (tid == 0) {
-        fence_proxy_async();
-        issue_tiles(consumed + Ta, li);
-        s_min[it ^ 1] = kInfBits;
-        s_hasnan[it ^ 1] = 0;
+      if (prod_warp) {
+        if (lane == 0) {
+          fence_proxy_async();
+          issue_tiles(consumed + Ta, li);
+          s_min[it ^ 1] = kInfBits;
+          s_hasnan[it ^ 1] = 0;
+        }
+        if (have_desc) describe_store(dreg, &s_tile[tprev], false);
       }
-      // four lanes per range tile
-      if ((tid & ~31) < 4 * nRt) {
-        const int q = tid & 3;
+      // one thread per range tile: float4 loads over the tile's column groups, edge groups masked
+      if ((tid & ~31) < nRt) {
         const bool hasnan = s_hasnan[it] != 0;
         unsigned m = kInfBits;
-        for (int rt = tid >> 2; rt < ((nRt + 7) & ~7); rt += nth >> 2) {
-          float s = 0.f;
-          int n = 0;
+        for (int rt = tid; rt < ((nRt + 31) & ~31); rt += nth) {
           if (rt < nRt) {
             const int j0 = rt * pr.rs_num, j1 = (j0 + pr.rs_num < R) ? j0 + pr.rs_num : R;
-            for (int j = j0 + q; j < j1; j += 4) s += s_colsum[j];
-            if (hasnan) {
-              for (int j = j0 + q; j < j1; j += 4) n += s_colcnt[j];
-            } else {
-              n = (q == 0) ? s_valid[rt] * Ta : 0;
+            const int ga = j0 >> 2, gb = (j1 - 1) >> 2;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            for (int gq = ga + 1; gq < gb; ++gq) {  // interior groups
+              const float4 v = *reinterpret_cast<const float4*>(s_colsum + 4 * gq);
+              s0 += v.x, s1 += v.y, s2 += v.z, s3 += v.w;
             }
-          }
-          s += __shfl_xor_sync(0xffffffffu, s, 1);
-          n += __shfl_xor_sync(0xffffffffu, n, 1);
-          s += __shfl_xor_sync(0xffffffffu, s, 2);
-          n += __shfl_xor_sync(0xffffffffu, n, 2);
-          if (n > 0) {
-            const unsigned u = __float_as_uint(__fdividef(s, (float)n));  // >= 0: uint order == float order
-            m = (u < m) ? u : m;
+            {
+              const float4 v = *reinterpret_cast<const float4*>(s_colsum + 4 * ga);
+              const int c = 4 * ga;
+              s0 += (c + 0 >= j0 && c + 0 < j1) ? v.x : 0.f;
+              s1 += (c + 1 >= j0 && c + 1 < j1) ? v.y : 0.f;
+              s2 += (c + 2 >= j0 && c + 2 < j1) ? v.z : 0.f;
+              s3 += (c + 3 < j1) ? v.w : 0.f;
+            }
+            if (gb > ga) {
+              const float4 v = *reinterpret_cast<const float4*>(s_colsum + 4 * gb);
+              const int c = 4 * gb;
+              s0 += v.x;
+              s1 += (c + 1 < j1) ? v.y : 0.f;
+              s2 += (c + 2 < j1) ? v.z : 0.f;
+              s3 += (c + 3 < j1) ? v.w : 0.f;
+            }
+            int n = s_valid[rt] * Ta;
+            if (hasnan) {
+              n = 0;
+              for (int j = j0; j < j1; ++j) n += s_colcnt[j];
+            }
+            if (n > 0) {
+              const unsigned u = __float_as_uint(__fdividef((s0 + s1) + (s2 + s3), (float)n));  // >= 0: uint order == float order
+              m = (u < m) ? u : m;
+            }
           }
         }
         m = __reduce_min_sync(0xffffffffu, m);
-        if ((tid & 31) == 0 && m != kInfBits) atomicMin(&s_min[it], m);
+        if (lane == 0 && m != kInfBits) atomicMin(&s_min[it], m);
       }
       __syncthreads();  // (B)
       {
@@ -478,16 +542,19 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
       }
     } else {
       __syncthreads();  // the tile's slots are free
-      if (tid == 0) {
-        fence_proxy_async();
-        issue_tiles(consumed + Ta, li);
+      if (prod_warp) {
+        if (lane == 0) {
+          fence_proxy_async();
+          issue_tiles(consumed + Ta, li);
+        }
+        if (have_desc) describe_store(dreg, &s_tile[tprev], false);
       }
     }
 
     // ---- phase 2: noise removal + accumulation into the register cells ------------------------------------------------
     // survivors: e > ethr (the SNR test in the e domain);  sum(e h - nl) = h sum(e) - n nl
     const int nruns = ti->nruns;
-    const bool fast_tile = (nruns == 1) && (Ta == T) && clean;
+    const bool simple = (nruns == 1) && (Ta == T);
     int ta = 0;
     for (int r = 0; r < nruns; ++r) {
       const int tb = ti->run_end[r];
@@ -518,7 +585,7 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
               nl = 0.f;
             }
             float sg = 0.f, ng_f = 0.f;
-            if (fast_tile) {  // every e finite: branch-free mask arithmetic (FSET + FFMA + FADD per sample)
+            if (simple) {  // every e finite (or the -2 sentinel): branch-free mask arithmetic, FSET + FFMA + FADD
 #pragma unroll
               for (int t = 0; t < T; ++t) {
                 const float m = (e[g][t][k] > ethr) ? 1.f : 0.f;
@@ -528,26 +595,19 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
             } else {
 #pragma unroll
               for (int t = 0; t < T; ++t) {
-                if (t >= ta && t < tb) {
-                  const bool p = e[g][t][k] > ethr;  // false for NaN e / NaN threshold
-                  sg += p ? e[g][t][k] : 0.f;
-                  ng_f += p ? 1.f : 0.f;
-                }
+                const float m = (t >= ta && t < tb && e[g][t][k] > ethr) ? 1.f : 0.f;
+                sg = fmaf(m, e[g][t][k], sg);
+                ng_f += m;
               }
             }
             const float contrib = fmaf(h[k], sg, -(ng_f * nl));
             acc.s[g][k] += (ng_f > 0.f) ? contrib : 0.f;
             acc.good[g][k] += ng_f;
           }
-          if (!clean && nanrange) {  // echo_range is NaN where the sample is NaN (range.py:143-148): not a member
+          if (nanmask[g] != 0u && nanrange) {  // echo_range is NaN where the sample is NaN (range.py:143-148): not a member
+            const unsigned rows_mask = ((tb >= 8) ? 0xffffffffu : ((1u << (4 * tb)) - 1u)) & ~((1u << (4 * ta)) - 1u);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              int nn = 0;
-#pragma unroll
-              for (int t = 0; t < T; ++t)
-                if (t >= ta && t < tb) nn += (e[g][t][k] != e[g][t][k]);
-              acc.nanm[g] += (unsigned)nn << (8 * k);
-            }
+            for (int k = 0; k < 4; ++k) acc.nanm[g] += (unsigned)__popc(nanmask[g] & rows_mask & (0x11111111u << k)) << (8 * k);
           }
         }
         acc.rows += tb - ta;
