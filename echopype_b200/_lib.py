@@ -49,9 +49,9 @@ SIGNATURES = {
     "epb_coarsen": (c_int, [vp, vp, vp, vp, i64, i64, i64, c_int, c_int, vp]),
     "epb_pipeline_power_mvbs": (
         c_int,
-        [vp, vp, vp, vp, c_int, c_int, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, c_int, c_int, c_float, c_float, vp, vp],
+        [vp, vp, vp, vp, c_int, c_int, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, c_int, c_int, c_float, c_float, vp, i64, vp],
     ),
-    "epb_pipeline_workspace_bytes": (i64, []),
+    "epb_pipeline_workspace_bytes": (i64, [i64, i64, c_int]),
     "epb_pipeline_smem_bytes": (i64, [i64, c_int, c_int, c_int, c_int]),
     "epb_zero": (c_int, [vp, i64, vp]),
     "epb_minmax_init": (c_int, [vp, vp]),

@@ -393,15 +393,20 @@ extern "C" epb_i64 epb_pipeline_smem_bytes(epb_i64 R, int nR, int tile, int do_n
 int epb_pipeline_fast_try(const float* x, const epb_row* rows, const int* xbin, const double* r_edges, int nR,
                           int closed_right, double* acc, float* noise_out, long long C, long long P, long long R,
                           long long nX, int ping_num, int range_sample_num, float noise_max_lin, float snr_lin,
-                          int* irregular, cudaStream_t s);
+                          void* workspace, long long workspace_bytes, cudaStream_t s);
+long long epb_pipeline_fast_workspace(long long C, long long P, int ping_num);
 
-extern "C" epb_i64 epb_pipeline_workspace_bytes(void) { return 256; }
+extern "C" epb_i64 epb_pipeline_workspace_bytes(epb_i64 C, epb_i64 P, int ping_num) {
+  if (C <= 0 || P <= 0 || ping_num < 0) return 256;
+  return epb_pipeline_fast_workspace(C, P, ping_num);
+}
 
 extern "C" int epb_pipeline_power_mvbs(const float* backscatter_r, const epb_row* rows, const int* xbin,
                                        const double* r_edges, int nR, int closed_right, double* acc, float* noise_out,
                                        float* Sv, float* echo_range, float* Sv_noise, float* Sv_corrected, epb_i64 C,
                                        epb_i64 P, epb_i64 R, epb_i64 nX, int ping_num, int range_sample_num,
-                                       float noise_max, float snr_threshold, void* workspace, void* stream) {
+                                       float noise_max, float snr_threshold, void* workspace, epb_i64 workspace_bytes,
+                                       void* stream) {
   EPB_REQUIRE(backscatter_r && rows && xbin && r_edges && acc, "NULL pointer");
   EPB_REQUIRE(C > 0 && P > 0 && R > 0 && R < (1 << 24) && nX > 0, "bad shape");
   EPB_REQUIRE(R % 4 == 0, "fused pipeline needs range_sample % 4 == 0 (use the separate kernels otherwise)");
@@ -424,10 +429,11 @@ extern "C" int epb_pipeline_power_mvbs(const float* backscatter_r, const epb_row
   pr.gate = nullptr;
   // fast path (pipeline_fast.cu): regular volumes without full-size outputs.  A device-side flag written by its
   // classification kernel decides which of the two kernels does the work; the other returns immediately.
-  if (workspace && !Sv && !echo_range && !Sv_noise && !Sv_corrected && ((uintptr_t)workspace % 4) == 0 &&
+  if (workspace && workspace_bytes >= 256 && !Sv && !echo_range && !Sv_noise && !Sv_corrected &&
+      ((uintptr_t)workspace % 16) == 0 &&
       epb_pipeline_fast_try(backscatter_r, rows, xbin, r_edges, nR, closed_right, acc, noise_out, C, P, R, nX, ping_num,
                             range_sample_num, pr.noise_max_lin, (float)pow(10.0, (double)snr_threshold / 10.0),
-                            (int*)workspace, (cudaStream_t)stream))
+                            workspace, workspace_bytes, (cudaStream_t)stream))
     pr.gate = (const int*)workspace;
   // stage the tile in shared memory when two CTAs per SM still fit, else when one fits, else stream from global
   pr.staged = 1;

@@ -233,11 +233,12 @@ def pipeline_power_mvbs(x, rows, xbin, r_edges, acc, C, P, R, nX, ping_num, rang
     """fast=False forces the general kernel (no workspace -> no fast-path dispatch)."""
     nm = float("nan") if noise_max is None else float(noise_max)
     nR = int(r_edges.numel()) - 1
-    ws = torch.empty(int(_lib.load().epb_pipeline_workspace_bytes()), dtype=torch.uint8, device=x.device) if fast else None
+    nws = int(_lib.load().epb_pipeline_workspace_bytes(int(C), int(P), int(ping_num))) if fast else 0
+    ws = torch.empty(nws, dtype=torch.uint8, device=x.device) if fast else None
     _lib.call(
         "epb_pipeline_power_mvbs", ptr(x), ptr(rows), ptr(xbin), ptr(r_edges), nR, int(closed_right), ptr(acc),
         ptr(noise_out), ptr(Sv), ptr(echo_range), ptr(Sv_noise), ptr(Sv_corrected), C, P, R, nX, int(ping_num),
-        int(range_sample_num), ctypes.c_float(nm), ctypes.c_float(float(snr)), ptr(ws), stream(),
+        int(range_sample_num), ctypes.c_float(nm), ctypes.c_float(float(snr)), ptr(ws), nws, stream(),
     )
     return acc
 

@@ -189,16 +189,18 @@ int epb_coarsen(const float* Sv, const float* echo_range, float* out, float* er_
  * Sv_corrected [C,P,R] float32.  noise_out: [C, ceil(P/ping_num)] (dB) or NULL.
  * ping_num = 0 skips noise removal (Sv -> MVBS).  noise_max: dB, NaN = no cap.  Requires R % 4 == 0,
  * ping_num <= 256; returns EPB_E_UNSUPPORTED when the per-CTA accumulators exceed shared memory.
- * workspace: NULL or a device scratch buffer of epb_pipeline_workspace_bytes() bytes owned by the caller and
- * private to this launch; with a workspace, regular volumes (every ping tile shares one range law, finite
+ * workspace: NULL or a 16-byte aligned device scratch buffer of workspace_bytes >=
+ * epb_pipeline_workspace_bytes(C, P, ping_num) bytes owned by the caller and private to this launch (it receives
+ * one 144-byte descriptor per ping tile); with a workspace, regular volumes (every ping tile shares one range law, finite
  * calibration constants, R <= 4096, ping_num <= 8, no full-size outputs) run on the persistent
  * register-resident kernel (pipeline_fast.cu), decided on the device without a host synchronisation. */
 int epb_pipeline_power_mvbs(const float* backscatter_r, const epb_row* rows, const int* xbin,
                             const double* r_edges, int nR, int closed_right, double* acc, float* noise_out,
                             float* Sv, float* echo_range, float* Sv_noise, float* Sv_corrected, epb_i64 C,
                             epb_i64 P, epb_i64 R, epb_i64 nX, int ping_num, int range_sample_num,
-                            float noise_max, float snr_threshold, void* workspace, void* stream);
-epb_i64 epb_pipeline_workspace_bytes(void);
+                            float noise_max, float snr_threshold, void* workspace, epb_i64 workspace_bytes,
+                            void* stream);
+epb_i64 epb_pipeline_workspace_bytes(epb_i64 C, epb_i64 P, int ping_num);
 epb_i64 epb_pipeline_smem_bytes(epb_i64 R, int nR, int tile, int do_noise, int staged);
 
 /* ---- helpers ---------------------------------------------------------------------------------------- */

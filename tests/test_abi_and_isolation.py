@@ -30,7 +30,9 @@ def test_library_exports_every_header_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/epb200.h but not exported by libepb200.so"
     assert lib.epb_version() == 100
-    assert int(ctypes.c_longlong(lib.epb_pipeline_workspace_bytes()).value) >= 4
+    lib.epb_pipeline_workspace_bytes.restype = ctypes.c_longlong
+    lib.epb_pipeline_workspace_bytes.argtypes = [ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int]
+    assert lib.epb_pipeline_workspace_bytes(4, 100, 5) == 256 + 4 * 20 * 144
 
 
 def test_ctypes_table_mirrors_header():
