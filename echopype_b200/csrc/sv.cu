@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) sv_complex_kernel(const float* __restrict
       float fr = (prx > 0.f) ? fmaf(kLog2ToDb, fast_log2(prx), rc.foffK) : CUDART_NAN_F;
       float rr;
       float o = sample_out(rc, n, (float)n, fr, rr);
-      if (xr[0] != xr[0]) rr = CUDART_NAN_F;  // range.py:143-145 uses beam 0 of backscatter_r
+      if (xr[0] != xr[0]) rr = CUDART_NAN_F, o = CUDART_NAN_F;  // range.py:143-145: echo_range (hence R', Sv) is NaN where beam 0 of backscatter_r is
       out[base + n] = o;
       if (kRange) rng[base + n] = rr;
       if (kMinMax) {

@@ -85,11 +85,100 @@ def test_ek80_cw_complex(ep, cal_type, B):
     from echopype_b200 import synth
 
     ed = synth.make_ek80(C=2, P=13, R=500, B=B, mode="CW", encode="complex", gpt_channel=None, nan_tail=0.2, seed=78)
+    beam = ed["Sonar/Beam_group1"]
+    re = beam["backscatter_r"].values.copy()  # single-beam NaNs: nanmean over beams; beam 0 also voids echo_range / Sv
+    rs = np.random.default_rng(11)
+    for _ in range(60):
+        re[rs.integers(2), rs.integers(13), rs.integers(500), rs.integers(B)] = np.nan
+    beam["backscatter_r"] = (("channel", "ping_time", "range_sample", "beam"), re)
     fn = ep.calibrate.compute_Sv if cal_type == "Sv" else ep.calibrate.compute_TS
     ds = fn(ed, waveform_mode="CW", encode_mode="complex")
     want = og.ek80(ed, cal_type, "CW", "complex")
     og.compare_db(ds[cal_type].values, want["out"], SV_ATOL, cal_type)
     _check_range(ds["echo_range"].values, want["echo_range"])
+
+
+BB_ATOL = 2e-4  # float32 accumulation over a few hundred taps; see DESIGN.md numerics
+
+
+@pytest.mark.parametrize("cal_type", ["Sv", "TS"])
+@pytest.mark.parametrize("B,R,beam_nan", [(4, 512, False), (4, 500, False), (4, 301, True), (3, 256, False), (1, 200, True)])
+def test_ek80_bb_pulse_compression(ep, cal_type, B, R, beam_nan):
+    """EK80 broadband: matched filter + Sv/TS epilogue (K3) against scipy's convolution in complex128.  beam_nan pokes NaNs
+    into single beams so that the per-beam fallback (exact nanmean over beams) runs."""
+    from echopype_b200 import synth
+
+    ed = synth.make_ek80(C=2, P=9, R=R, B=B, mode="BB", encode="complex", nan_tail=0.3, seed=91)
+    beam = ed["Sonar/Beam_group1"]
+    if beam_nan:
+        re, im = beam["backscatter_r"].values.copy(), beam["backscatter_i"].values.copy()
+        rng = np.random.default_rng(5)
+        for _ in range(40):
+            c, p, n, b = rng.integers(2), rng.integers(9), rng.integers(R), rng.integers(B)
+            re[c, p, n, b] = np.nan
+            if rng.random() < 0.5:
+                im[c, p, n, b] = np.nan
+        dims = ("channel", "ping_time", "range_sample", "beam")
+        beam["backscatter_r"] = (dims, re)
+        beam["backscatter_i"] = (dims, im)
+    fn = ep.calibrate.compute_Sv if cal_type == "Sv" else ep.calibrate.compute_TS
+    ds = fn(ed, waveform_mode="BB", encode_mode="complex")
+    want = og.ek80(ed, cal_type, "BB", "complex")
+    got = ds[cal_type].values.astype(np.float64)
+    assert np.array_equal(np.isnan(got), np.isnan(want["out"]))
+    # deep nulls of the compressed signal lose relative accuracy in float32: tolerance scales with the distance below the median
+    ok = ~np.isnan(got)
+    prx = want["prx"][ok]
+    weight = np.maximum(1.0, np.sqrt(np.nanmedian(prx) / np.maximum(prx, 1e-300)) * 1e-2)
+    err = np.abs(got[ok] - want["out"][ok])
+    assert (err <= BB_ATOL * weight).all(), float((err / weight).max())
+    assert np.median(err) < 2e-5
+    _check_range(ds["echo_range"].values, want["echo_range"])
+    if cal_type == "Sv":
+        np.testing.assert_allclose(ds["tau_effective"].values, want["tau_effective"], rtol=1e-12)
+    # "FM" is an alias of "BB" (calibrate/api.py:35)
+    ds2 = fn(ed, waveform_mode="FM", encode_mode="complex")
+    np.testing.assert_array_equal(ds2[cal_type].values, ds[cal_type].values)
+
+
+def test_pulse_compress_kernel_vs_scipy(ep):
+    """The compressed, normalised, beam-averaged signal itself (pc_out) against scipy.signal.convolve."""
+    import torch
+    from scipy import signal
+
+    from echopype_b200 import kernels, synth
+
+    C, P, R, B = 2, 5, 777 - 1, 4
+    rng = np.random.default_rng(3)
+    re = rng.standard_normal((C, P, R, B)).astype(np.float32)
+    im = rng.standard_normal((C, P, R, B)).astype(np.float32)
+    re[0, 1, 500:] = np.nan
+    im[0, 1, 500:] = np.nan
+    tx = [rng.standard_normal(37) + 1j * rng.standard_normal(37), rng.standard_normal(150) + 1j * rng.standard_normal(150)]
+    ed = synth.make_ek80(C=C, P=P, R=R, B=B, mode="BB", encode="complex", nan_tail=0.0, seed=1)
+    from echopype_b200.calibrate.calibrate_ek import CalibrateEK80
+
+    cal = CalibrateEK80(ed, waveform_mode="BB", encode_mode="complex")
+    cal._cal_complex_samples("Sv")
+    out, _, pc, _ = kernels.pulse_compress_sv(torch.from_numpy(re).cuda(), torch.from_numpy(im).cuda(), tx, cal.rows, C, P, R, B,
+                                              want_pc=True)
+    pc = pc.cpu().numpy()
+    got = pc[..., 0] + 1j * pc[..., 1]
+    x = re.astype(np.float64) + 1j * im.astype(np.float64)
+    nan = np.isnan(x)
+    xz = np.where(nan, 0, x)
+    for c in range(C):
+        h = np.flipud(np.conj(tx[c]))
+        norm = np.linalg.norm(tx[c]) ** 2
+        for p in range(P):
+            y = np.stack([signal.convolve(xz[c, p, :, b], h, mode="full")[len(h) - 1:] for b in range(B)], axis=-1) / norm
+            y = np.where(nan[c, p], np.nan, y)
+            want = np.nanmean(y, axis=-1) if not nan[c, p].all(axis=-1).any() else np.where(nan[c, p].all(axis=-1), np.nan, np.nanmean(np.where(nan[c, p].all(axis=-1)[:, None], 0, y), axis=-1))
+            g = got[c, p]
+            assert np.array_equal(np.isnan(g), np.isnan(want))
+            ok = ~np.isnan(want)
+            scale = np.abs(want[ok]).max()
+            assert np.abs(g[ok] - want[ok]).max() <= 3e-6 * scale
 
 
 def test_output_contract(ep):
