@@ -318,6 +318,7 @@ class CalibrateEK80(CalibrateEK):
         tx_coeff = get_filter_coeff(self.vend)
         fs = self.cal_params["receiver_sampling_frequency"]
         tx, tx_time = get_transmit_signal(beam, tx_coeff, self.waveform_mode, fs, self.drop_last_hanning_zero)
+        self._tx = tx
         gain = _cp(self.cal_params["gain_correction"], chan)
         if bb:  # transceiver gain compensation, calibrate_ek.py:561-562
             g, Bm = np.asarray(gain, dtype=np.float64), np.asarray(self._get_B_theta_phi_m(), dtype=np.float64)

@@ -64,46 +64,59 @@ def global_ping_edges(ping_time, ping_time_bin, group=None):
     return ping_time_edges(np.array([lo, hi], dtype="datetime64[ns]"), ping_time_bin)
 
 
-def straddle_reduce(acc, lo, hi, group):
+def straddle_plan(lo, hi, group):
+    """Gather the (first, last) global ping bin of every rank once (host ints): the bins a rank shares with its
+    neighbours depend only on the ping times, not on the data."""
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    idx = torch.full((world, 2), -1, dtype=torch.int64, device=_comm_device(group))
+    idx[rank, 0], idx[rank, 1] = int(lo), int(hi)
+    dist.all_reduce(idx, op=dist.ReduceOp.MAX, group=group)
+    idx = idx.cpu().tolist()
+    plan = {"world": world, "rank": rank, "lo": int(lo), "hi": int(hi), "slots": []}
+    if hi < lo:
+        return plan
+    for slot, b in ((0, int(lo)), (int(hi) - int(lo), int(hi))):
+        if slot != 0 and hi == lo:
+            break
+        src = []
+        for r, (r_lo, r_hi) in enumerate(idx):
+            if r_lo < 0:
+                continue
+            if r_lo == b:
+                src.append(2 * r)
+            elif r_hi == b:  # r_hi != r_lo here
+                src.append(2 * r + 1)
+        plan["slots"].append((slot, src))
+    return plan
+
+
+def straddle_reduce(acc, lo, hi, group, plan=None):
     """Merge the ping bins shared between ping-sharded ranks.
 
     acc : this rank's accumulators [C, hi - lo + 1, nR, 4] for the GLOBAL ping bins lo..hi (inclusive).
     Shards are contiguous and time-ordered, so only the first and the last local bin of a rank can also
     receive samples on another rank.  Every rank contributes those two bin slices (C x nR x 4 float64 each) to
-    one all-reduce(sum) of a [world, 2, C, nR, 4] buffer (a few KB); afterwards every rank holds the complete
-    sums of its own edge bins.  Interior bins never leave the rank.  Returns acc (updated in place).
+    ONE all-reduce(sum) of a [world, 2, C, nR, 4] buffer (a few KB); afterwards every rank holds the complete
+    sums of its own edge bins.  Interior bins never leave the rank.  No host synchronisation happens here when a
+    ``plan`` (:func:`straddle_plan`) is supplied.  Returns acc (updated in place).
     """
     dist = _dist()
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    world = dist.get_world_size(group)
     if world == 1:
         return acc
+    plan = plan or straddle_plan(lo, hi, group)
+    rank = plan["rank"]
     C, nXl, nR, _ = acc.shape
     cdev = _comm_device(group)
-    idx = torch.full((world, 2), -1, dtype=torch.int64, device=cdev)
-    idx[rank, 0], idx[rank, 1] = int(lo), int(hi)
-    buf = torch.zeros((world, 2, C, nR, 4), dtype=torch.float64, device=cdev)
-    if nXl > 0:
-        buf[rank, 0] = acc[:, 0].to(cdev)
+    buf = torch.zeros((world * 2, C, nR, 4), dtype=torch.float64, device=cdev)
+    if hi >= lo:
+        buf[2 * rank] = acc[:, 0].to(cdev)
         if hi != lo:
-            buf[rank, 1] = acc[:, nXl - 1].to(cdev)
-    dist.all_reduce(idx, op=dist.ReduceOp.MAX, group=group)  # gather (lo, hi) of every rank
+            buf[2 * rank + 1] = acc[:, hi - lo].to(cdev)
     dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)  # the data-path collective
-    if nXl == 0:
-        return acc
-    idx = idx.cpu()
-    for slot, b in ((0, int(lo)), (nXl - 1, int(hi))):
-        if slot == nXl - 1 and hi == lo:
-            break
-        tot = torch.zeros((C, nR, 4), dtype=torch.float64, device=cdev)
-        for r in range(world):
-            r_lo, r_hi = int(idx[r, 0]), int(idx[r, 1])
-            if r_lo < 0:
-                continue
-            if r_lo == b:
-                tot += buf[r, 0]
-            elif r_hi == b:  # r_hi != r_lo here
-                tot += buf[r, 1]
-        acc[:, slot] = tot.to(acc.device)
+    for slot, src in plan["slots"]:
+        acc[:, slot] = buf[src].sum(dim=0).to(acc.device)
     return acc
 
 
@@ -181,67 +194,87 @@ class FusedPlan:
         self.launches = 0  # kernels of libepb200 launched by run() so far (bench.py "gpu_launches")
         self.record_events = False  # bench.py: CUDA events around every fused-kernel launch -> kernel_events
         self.kernel_events = []
+        self._splan = straddle_plan(self.x_lo, self.x_hi, group) if group is not None else None
+        self._ub = None  # cached upper bound of the range grid (depends on the parameters only, not on the samples)
 
     # ---- device work ------------------------------------------------------------------------------------------
-    def _range_edges(self, x, rows):
-        C, P, R = self.C, self.P, self.R
-        if self.range_var_max is not None:
-            rmax = _parse_x_bin(self.range_var_max) + 1e-8
-        else:
-            rmax = kernels.range_max(x, rows, C, P, R)  # exact float64 nanmax(echo_range), commongrid/api.py:108-114
-            self.launches += 2
-            if self.group is not None:
-                dist = _dist()
-                t = torch.tensor([rmax if rmax == rmax else -np.inf], dtype=torch.float64, device=_comm_device(self.group))
-                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
-                rmax = float(t.item())
-        return range_edges(rmax, self.rb)
+    def _group_max(self, v):
+        if self.group is None:
+            return v
+        dist = _dist()
+        t = torch.tensor([v if v == v else -np.inf], dtype=torch.float64, device=_comm_device(self.group))
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return float(t.item())
+
+    def _upper_edges(self, rows):
+        """Range-bin edges against which the kernel bins.  With ``range_var_max`` they are final.  Otherwise the
+        reference uses nanmax(echo_range) (commongrid/api.py:108-114), which depends on the NaN tails of the samples;
+        the kernel bins against an upper-bound grid (range law at the last sample of every row, from the parameters
+        alone, cached per plan) and the grid is cut back to the exact maximum when the result is read: bins above
+        the exact maximum cannot have members.  This keeps the device sequence free of host synchronisation."""
+        if self._ub is None:
+            C, P, R = self.C, self.P, self.R
+            if self.range_var_max is not None:
+                ub = _parse_x_bin(self.range_var_max) + 1e-8
+            else:
+                ub = self._group_max(kernels.range_max(None, rows, C, P, R))
+            e = range_edges(ub, self.rb)
+            self._ub = (e, torch.from_numpy(np.ascontiguousarray(e, dtype=np.float64)).to(self.dev))
+        return self._ub
 
     def run(self, x=None, finalize=True):
-        """Launch the device work.  x: raw samples (device tensor or host array, default: the EchoData's own).
-        Returns (mvbs [C, nX, nR] float32 device tensor or None, acc, r_edges, kept dict, noise)."""
+        """Launch the device work (no host synchronisation for a device-resident volume after the first call).
+        x: raw samples (device tensor or host array, default: the EchoData's own).
+        Returns (mvbs [C, nX, nR_upper] float32 device tensor or None, acc, rmax, outs, noise); ``rmax`` is a 1-element
+        float64 device tensor holding the exact nanmax(echo_range) of this rank (or None with ``range_var_max``);
+        :meth:`wrap` reads it and trims the range grid."""
         C, P, R = self.C, self.P, self.R
         x = self.beam["backscatter_r"].data if x is None else x
         rows = self.row_builder.build()
         self.launches += 1
+        self.rows = rows
         on_device = isinstance(x, torch.Tensor) and x.is_cuda
         outs = {k: (empty((C, P, R), device=self.dev) if k in self.keep else None) for k in _KEEP}
         noise = empty((C, -(-P // self.ping_num)), device=self.dev) if self.do_noise else None
+        e_ub, edges_t = self._upper_edges(rows)
+        nX = max(self.nX, 1)
+        acc = kernels.new_acc(C, nX, len(e_ub) - 1, self.dev)
+        self.launches += 1
+        rmax = None
         if on_device:
-            r_edges = self._range_edges(x, rows)
-            nR = len(r_edges) - 1
-            edges_t = torch.from_numpy(np.ascontiguousarray(r_edges, dtype=np.float64)).to(self.dev)
-            acc = kernels.new_acc(C, max(self.nX, 1), nR, self.dev)
+            if self.range_var_max is None:
+                rmax = torch.empty(1, dtype=torch.float64, device=self.dev)
+                kernels.range_max_into(x, rows, C, P, R, rmax)
+                self.launches += 2
             if self.record_events:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 ev[0].record()
             kernels.pipeline_power_mvbs(
-                x, rows, self.xbin, edges_t, acc, C, P, R, max(self.nX, 1), self.ping_num, self.range_sample_num,
+                x, rows, self.xbin, edges_t, acc, C, P, R, nX, self.ping_num, self.range_sample_num,
                 noise_max=self.noise_max, snr=self.snr, closed_right=(self.closed == "right"), noise_out=noise,
                 fast=self.fast, Sv=outs["Sv"], echo_range=outs["echo_range"], Sv_noise=outs["Sv_noise"], Sv_corrected=outs["Sv_corrected"],
             )
             if self.record_events:
                 ev[1].record()
                 self.kernel_events.append(ev)
-            self.launches += 2
+            self.launches += 3 if self.fast else 1
         else:
-            acc, r_edges = self._run_streamed(x, rows, outs, noise)
-            nR = len(r_edges) - 1
+            rmax = self._run_streamed(x, rows, outs, noise, acc, edges_t)
         if self.group is not None:
-            straddle_reduce(acc, self.x_lo, self.x_hi, self.group)
+            straddle_reduce(acc, self.x_lo, self.x_hi, self.group, self._splan)
+            if rmax is not None:  # global nanmax(echo_range): a 1-double max all-reduce, read only in wrap()
+                rmax = rmax.max().reshape(1).to(_comm_device(self.group))
+                _dist().all_reduce(rmax, op=_dist().ReduceOp.MAX, group=self.group)
         mvbs = None
         if finalize:
             mvbs, _ = kernels.bin_finalize(acc, skipna=self.skipna, fill_value=self.fill_value, to_db=True)
             self.launches += 1
-        self.rows = rows
-        return mvbs, acc, r_edges, outs, noise
+        return mvbs, acc, rmax, outs, noise
 
-    def _run_streamed(self, x, rows, outs, noise):
+    def _run_streamed(self, x, rows, outs, noise, acc, edges_t):
         """Host-resident volume: slabs of (1 channel, chunk pings) move H2D on a copy stream into a 3-slab ring
-        while the fused kernel runs on the previous slab.  Range bins: the exact range maximum needs the NaN tails
-        of every row (range.py:143-148), which are only known once the data has passed through, so the kernel bins
-        against an upper-bound grid (range law at the last sample of every row, NaN tails ignored) and the grid is
-        cut back to the exact maximum afterwards; bins above the exact maximum cannot have members."""
+        while the fused kernel runs on the previous slab and accumulates into the same grid.  Returns the device
+        tensor of per-slab exact range maxima (or None with ``range_var_max``)."""
         C, P, R = self.C, self.P, self.R
         xh = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float32)))
         if xh.dtype != torch.float32:
@@ -255,22 +288,10 @@ class FusedPlan:
                              [torch.cuda.Event() for _ in range(3)])
         copy_s, filled, freed = self._streams
         main = torch.cuda.current_stream()
-        ub = kernels.range_max(None, rows, C, P, R) if self.range_var_max is None else _parse_x_bin(self.range_var_max) + 1e-8
-        self.launches += 2
-        if self.group is not None and self.range_var_max is None:
-            dist = _dist()
-            t = torch.tensor([ub if ub == ub else -np.inf], dtype=torch.float64, device=_comm_device(self.group))
-            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
-            ub = float(t.item())
-        e_ub = range_edges(ub, self.rb)
-        nR_ub = len(e_ub) - 1
-        edges_t = torch.from_numpy(np.ascontiguousarray(e_ub, dtype=np.float64)).to(self.dev)
         nX = max(self.nX, 1)
-        acc = kernels.new_acc(C, nX, nR_ub, self.dev)
-        self.launches += 1
-        rmax_t = torch.full((C * (-(-P // chunk)),), -np.inf, dtype=torch.float64, device=self.dev)
+        want_rmax = self.range_var_max is None
+        rmax_t = torch.full((C * (-(-P // chunk)),), -np.inf, dtype=torch.float64, device=self.dev) if want_rmax else None
         copy_s.wait_stream(main)
-        nPt = -(-P // pn)
         i = 0
         rows_b = rows.view(C * P, -1)
         for c in range(C):
@@ -294,32 +315,28 @@ class FusedPlan:
                     Sv=sub(outs["Sv"]), echo_range=sub(outs["echo_range"]), Sv_noise=sub(outs["Sv_noise"]),
                     Sv_corrected=sub(outs["Sv_corrected"]),
                 )
-                if self.range_var_max is None:
+                self.launches += 3 if self.fast else 1
+                if want_rmax:
                     kernels.range_max_into(buf, rsub, 1, pc, R, rmax_t[i : i + 1])
                     self.launches += 2
-                self.launches += 1
                 freed[slot].record(main)
                 i += 1
-        _ = nPt
-        if self.range_var_max is None:
-            rmax = float(rmax_t.max().item())
-            rmax = float("nan") if rmax == float("-inf") else rmax
-            if self.group is not None:
-                dist = _dist()
-                t = torch.tensor([rmax if rmax == rmax else -np.inf], dtype=torch.float64, device=_comm_device(self.group))
-                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
-                rmax = float(t.item())
-            r_edges = range_edges(rmax, self.rb)
+        return rmax_t
+
+    def wrap(self, mvbs, acc, rmax, outs, noise):
+        """Dataset with the variables / coords / attrs of compute_MVBS (commongrid/api.py:130-189).  Reads the exact
+        range maximum (one host synchronisation) and cuts the upper-bound range grid back to it."""
+        beam = self.beam
+        e_ub = self._ub[0]
+        if rmax is not None:
+            v = float(rmax.max().item())
+            r_edges = range_edges(float("nan") if v == float("-inf") else v, self.rb)
         else:
             r_edges = e_ub
         nR = len(r_edges) - 1
-        if nR < nR_ub:
-            acc = acc[:, :, :nR].contiguous()
-        return acc, r_edges
-
-    def wrap(self, mvbs, acc, r_edges, outs, noise):
-        """Dataset with the variables / coords / attrs of compute_MVBS (commongrid/api.py:130-189)."""
-        beam = self.beam
+        if nR < len(e_ub) - 1:
+            acc = acc[:, :, :nR]
+            mvbs = None if mvbs is None else mvbs[:, :, :nR]
         pe = self.p_edges[self.x_lo : self.x_hi + 1] if self.nX > 0 else self.p_edges[:0]
         ds = Dataset(coords={"ping_time": pe, "channel": beam["channel"].values, "echo_range": r_edges[:-1]})
         if mvbs is not None:
@@ -342,7 +359,7 @@ class FusedPlan:
                 }
             )
         else:
-            ds.attrs["acc"] = acc
+            ds.attrs["acc"] = acc.contiguous()
         ds["frequency_nominal"] = beam["frequency_nominal"]
         prov = echopype_prov_attrs(process_type="processing")
         prov["processing_function"] = "pipeline.compute_Sv_clean_MVBS"
@@ -400,5 +417,5 @@ def compute_Sv_clean_MVBS(
         SNR_threshold=SNR_threshold, range_bin=range_bin, ping_time_bin=ping_time_bin, skipna=skipna, fill_value=fill_value,
         closed=closed, range_var_max=range_var_max, keep=keep, group=group, chunk_pings=chunk_pings, fast=fast, **cal_kwargs,
     )
-    mvbs, acc, r_edges, outs, noise = plan.run(finalize=finalize)
-    return plan.wrap(mvbs, acc, r_edges, outs, noise)
+    mvbs, acc, rmax, outs, noise = plan.run(finalize=finalize)
+    return plan.wrap(mvbs, acc, rmax, outs, noise)

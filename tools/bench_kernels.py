@@ -49,6 +49,7 @@ def main():
     ap.add_argument("--R", type=int, default=4096)
     ap.add_argument("--which", default="copy,sv,svr,svrm,noise,bins,pipe")
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--bb-pings", type=int, default=2000)
     a = ap.parse_args()
     C, P, R = a.C, a.P, a.R
     which = a.which.split(",")
@@ -74,6 +75,43 @@ def main():
         report("sv_power+range+minmax", ms, mn, 12 * n, n)
     if {"noise", "bins", "pipe"} & set(which):
         extra(a, which, C, P, R, n, x, rows, out, rng, ed)
+    if "pulse" in which:
+        del x, out, rng, ed
+        torch.cuda.empty_cache()
+        pulse(a)
+
+
+def pulse(a):
+    """cfg3-shaped EK80 broadband volume (6 ch x pings x 8192 complex samples x 4 beams), K3 alone."""
+    import numpy as np
+
+    from echopype_b200.calibrate.calibrate_ek import CalibrateEK80
+
+    C, P, R, B = 6, a.bb_pings, 8192, 4
+    ed = synth.make_ek80(C=C, P=P, R=R, B=B, mode="BB", encode="complex", device=True, nan_tail=0.005, seed=3000)
+    cal = CalibrateEK80(ed, waveform_mode="BB", encode_mode="complex")
+    holder = {}
+
+    def run():
+        holder["ds"] = cal._cal_complex_samples("Sv")
+
+    run()  # host-side replica synthesis etc. happen on every call; time the kernel through the C ABI instead
+    beam = ed["Sonar/Beam_group1"]
+    re, im = beam["backscatter_r"].data, beam["backscatter_i"].data
+    chan = np.asarray(beam["channel"].values)
+    tx = [cal._tx[c] for c in chan]
+    M = max(len(t) for t in tx)
+    out = torch.empty((C, P, R), dtype=torch.float32, device=re.device)
+    rng = torch.empty_like(out)
+    ms, mn = timeit(lambda: kernels.pulse_compress_sv(re, im, tx, cal.rows, C, P, R, B, want_range=True), a.iters)
+    n = C * P * R
+    Mpad = (M + 7) // 8 * 8
+    flops = 8.0 * Mpad * n
+    print(json.dumps({"kernel": "pulse_compress_sv (K3)", "taps": M, "ms_median": round(ms, 3), "ms_min": round(mn, 3),
+                      "GBps": round(40 * n / ms / 1e6, 1), "frac_of_measured_hbm": round(40 * n / ms / 1e6 / PEAK, 3),
+                      "TFLOPs_fp32": round(flops / ms / 1e9, 2), "frac_of_fp32_peak_74.4": round(flops / ms / 1e9 / 74.4, 3),
+                      "Gsamples_s": round(n / ms / 1e6, 2)}), flush=True)
+    _ = out, rng
 
 
 def extra(a, which, C, P, R, n, x, rows, out, rng, ed):
