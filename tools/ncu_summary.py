@@ -17,12 +17,14 @@ def f(k):
     except Exception:
         return float("nan")
 print("kernel", d.get("Kernel Name"), "grid", d.get("Grid Size"), "block", d.get("Block Size"))
+units = dict(zip(rows[0], rows[1]))
+SC = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3, "byte": 1e-9, "Kbyte": 1e-6, "Mbyte": 1e-3, "Gbyte": 1.0, "Tbyte": 1e3}
+def scaled(k):
+    return f(k) * SC.get(units.get(k, ""), float("nan"))
 print("duration_ms %.3f  dram_read_GB %.3f dram_write_GB %.4f  dram_pct %.1f  ipc %.2f  regs %s  smem_dyn_KB %s" % (
-    f("gpu__time_duration.sum") / 1e6, f("dram__bytes_read.sum") / 1e9 if d.get("dram__bytes_read.sum") else float("nan"),
-    f("dram__bytes_write.sum") / 1e9 if d.get("dram__bytes_write.sum") else float("nan"),
+    scaled("gpu__time_duration.sum"), scaled("dram__bytes_read.sum"), scaled("dram__bytes_write.sum"),
     f("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"), f("sm__inst_executed.avg.per_cycle_active"),
     d.get("launch__registers_per_thread"), d.get("launch__shared_mem_per_block_dynamic")))
-print("units", {k: rows[1][rows[0].index(k)] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum") if k in rows[0]})
 st = {k[33:]: f(k) for k in d if k.startswith("smsp__pcsamp_warps_issue_stalled_") and not k.endswith("_not_issued")}
 tot = sum(v for v in st.values() if v == v)
 print("stalls% " + " ".join(f"{k}:{100 * v / tot:.0f}" for k, v in sorted(st.items(), key=lambda x: -x[1]) if v / tot > 0.02))
