@@ -22,7 +22,8 @@ class epb_row(Structure):
         [(n, c_double) for n in ("p0", "p1", "p2", "p3", "p4", "off1", "off2", "r0", "a", "two_alpha", "K", "fscale", "foff", "slog")]
         + [("n_start", c_int), ("law", c_int), ("azfp_N", c_int), ("reserved", c_int)]
         + [(n, c_float) for n in ("a_h", "a_l", "r0_h", "r0_l", "bp_h", "bp_l", "two_alpha_f", "slog2", "fscale_f", "foffK",
-                                  "c0", "c1", "c2", "spow", "pad0", "pad1")]
+                                  "c0", "c1", "c2", "spow")]
+        + [("range_last", c_double)]
     )
 
 
@@ -49,7 +50,7 @@ SIGNATURES = {
     "epb_coarsen": (c_int, [vp, vp, vp, vp, i64, i64, i64, c_int, c_int, vp]),
     "epb_pipeline_power_mvbs": (
         c_int,
-        [vp, vp, vp, vp, c_int, c_int, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, c_int, c_int, c_float, c_float, vp, i64, vp],
+        [vp, vp, vp, vp, c_int, c_int, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, c_int, c_int, c_float, c_float, vp, vp, i64, vp],
     ),
     "epb_pipeline_workspace_bytes": (i64, [i64, i64, c_int]),
     "epb_pipeline_smem_bytes": (i64, [i64, c_int, c_int, c_int, c_int]),

@@ -83,6 +83,14 @@ __device__ __forceinline__ void atomic_max_f(float* addr, float v) {
     atomicMin((unsigned int*)addr, __float_as_uint(v));
 }
 
+__device__ __forceinline__ void atomic_max_d(double* addr, double v) {  // v >= 0 or any sign, non-NaN
+  long long iv = __double_as_longlong(v);
+  if (iv >= 0)
+    atomicMax((long long*)addr, iv);
+  else
+    atomicMin((unsigned long long*)addr, (unsigned long long)iv);
+}
+
 __device__ __forceinline__ float warp_min(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));

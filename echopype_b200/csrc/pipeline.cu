@@ -110,8 +110,11 @@ __global__ void __launch_bounds__(kThreads, 2) pipeline_kernel(const Params pr) 
   __shared__ float s_noise_lin;
 
   const int nPt = (int)((pr.P + T - 1) / T);
-  const long long c = blockIdx.x / nPt;
-  const int it = blockIdx.x % nPt;
+  // grid-stride over the (channel, ping tile) tiles: a launch that loses the device-side dispatch against the fast
+  // kernel exits after a few hundred CTAs instead of one per tile
+  for (long long tile = blockIdx.x; tile < pr.C * nPt; tile += gridDim.x) {
+  const long long c = tile / nPt;
+  const int it = (int)(tile % nPt);
   const long long p0 = (long long)it * T;
   const int Ta = (int)((p0 + T <= pr.P) ? T : (pr.P - p0));  // rows actually present in this tile
   const long long row0 = c * pr.P + p0;
@@ -120,6 +123,8 @@ __global__ void __launch_bounds__(kThreads, 2) pipeline_kernel(const Params pr) 
 
   // ---- phase 0: start the TMA bulk copies, meanwhile build row constants / bin boundaries -------------------
   if (pr.staged && tid == 0) {
+    if (tile != blockIdx.x) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&s_bar)) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of the tile vs the new bulk copies
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     const uint32_t row_bytes = (uint32_t)R * 4u;
@@ -369,6 +374,8 @@ __global__ void __launch_bounds__(kThreads, 2) pipeline_kernel(const Params pr) 
     }
     if (bad) atomicAdd(cell + 2, (double)bad);
   }
+  __syncthreads();  // shared memory (tile, accumulators, mbarrier) is reused by the next tile
+  }
 }
 
 size_t pipeline_smem(long long R, int nR, int tile, int do_noise, int staged) {
@@ -393,7 +400,10 @@ extern "C" epb_i64 epb_pipeline_smem_bytes(epb_i64 R, int nR, int tile, int do_n
 int epb_pipeline_fast_try(const float* x, const epb_row* rows, const int* xbin, const double* r_edges, int nR,
                           int closed_right, double* acc, float* noise_out, long long C, long long P, long long R,
                           long long nX, int ping_num, int range_sample_num, float noise_max_lin, float snr_lin,
-                          void* workspace, long long workspace_bytes, cudaStream_t s);
+                          double* range_max_out, void* workspace, long long workspace_bytes, cudaStream_t s);
+void epb_range_max_init_launch(double* out_max, cudaStream_t s);
+void epb_range_max_gated_launch(const float* x, const epb_row* rows, long long nrows, int R, double* out_max, const int* gate,
+                                cudaStream_t s);
 long long epb_pipeline_fast_workspace(long long C, long long P, int ping_num);
 
 extern "C" epb_i64 epb_pipeline_workspace_bytes(epb_i64 C, epb_i64 P, int ping_num) {
@@ -405,8 +415,8 @@ extern "C" int epb_pipeline_power_mvbs(const float* backscatter_r, const epb_row
                                        const double* r_edges, int nR, int closed_right, double* acc, float* noise_out,
                                        float* Sv, float* echo_range, float* Sv_noise, float* Sv_corrected, epb_i64 C,
                                        epb_i64 P, epb_i64 R, epb_i64 nX, int ping_num, int range_sample_num,
-                                       float noise_max, float snr_threshold, void* workspace, epb_i64 workspace_bytes,
-                                       void* stream) {
+                                       float noise_max, float snr_threshold, double* range_max_out, void* workspace,
+                                       epb_i64 workspace_bytes, void* stream) {
   EPB_REQUIRE(backscatter_r && rows && xbin && r_edges && acc, "NULL pointer");
   EPB_REQUIRE(C > 0 && P > 0 && R > 0 && R < (1 << 24) && nX > 0, "bad shape");
   EPB_REQUIRE(R % 4 == 0, "fused pipeline needs range_sample % 4 == 0 (use the separate kernels otherwise)");
@@ -427,13 +437,14 @@ extern "C" int epb_pipeline_power_mvbs(const float* backscatter_r, const epb_row
   pr.noise_max_lin = (noise_max == noise_max) ? (float)pow(10.0, (double)noise_max / 10.0) : nanf("");
   pr.snr_fac = (float)(1.0 + pow(10.0, (double)snr_threshold / 10.0));
   pr.gate = nullptr;
+  if (range_max_out) epb_range_max_init_launch(range_max_out, (cudaStream_t)stream);
   // fast path (pipeline_fast.cu): regular volumes without full-size outputs.  A device-side flag written by its
   // classification kernel decides which of the two kernels does the work; the other returns immediately.
   if (workspace && workspace_bytes >= 256 && !Sv && !echo_range && !Sv_noise && !Sv_corrected &&
       ((uintptr_t)workspace % 16) == 0 &&
       epb_pipeline_fast_try(backscatter_r, rows, xbin, r_edges, nR, closed_right, acc, noise_out, C, P, R, nX, ping_num,
                             range_sample_num, pr.noise_max_lin, (float)pow(10.0, (double)snr_threshold / 10.0),
-                            workspace, workspace_bytes, (cudaStream_t)stream))
+                            range_max_out, workspace, workspace_bytes, (cudaStream_t)stream))
     pr.gate = (const int*)workspace;
   // stage the tile in shared memory when two CTAs per SM still fit, else when one fits, else stream from global
   pr.staged = 1;
@@ -450,6 +461,9 @@ extern "C" int epb_pipeline_power_mvbs(const float* backscatter_r, const epb_row
   EPB_REQUIRE(C * nPt < (1LL << 31), "too many ping tiles");
   if (cudaFuncSetAttribute(pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return epb_check_launch("epb_pipeline_power_mvbs(smem)");
-  pipeline_kernel<<<(unsigned)(C * nPt), kThreads, smem, (cudaStream_t)stream>>>(pr);
+  const long long cap = (long long)epb_num_sms() * 16;
+  pipeline_kernel<<<(unsigned)(C * nPt < cap ? C * nPt : cap), kThreads, smem, (cudaStream_t)stream>>>(pr);
+  // exact nanmax(echo_range): computed by the fast kernel when it runs, by the (gated) range kernel otherwise
+  if (range_max_out) epb_range_max_gated_launch(backscatter_r, rows, C * P, (int)R, range_max_out, pr.gate, (cudaStream_t)stream);
   return epb_check_launch("epb_pipeline_power_mvbs");
 }

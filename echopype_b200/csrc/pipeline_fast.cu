@@ -39,6 +39,7 @@ struct FastParams {
   const double* edges;
   double* acc;
   float* noise_out;
+  double* rmax;  // NULL or exact nanmax(echo_range) (atomic max; initialised by the caller)
   const int* irregular;  // workspace flag from prepare_kernel: != 0 -> this kernel does nothing
   const TileInfo* tiles;  // [ntiles] descriptors from prepare_kernel (workspace)
   long long C, P, nX, ntiles;
@@ -230,6 +231,7 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
   __shared__ unsigned int s_min[2];
   __shared__ int s_hasnan[2];   // a thread saw a NaN sample in the tile: range-tile counts are corrected by s_def
   __shared__ Producer s_prod;
+  __shared__ int s_last[kMaxT];  // last sample with a defined range of the rows whose final sample is NaN (rare)
   const int R = pr.R, nR = pr.nR, NT = pr.nslots;  // NT tile slots of T rows in the ring
   const int tid = threadIdx.x;
   const int nth = blockDim.x;
@@ -282,6 +284,7 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
     mbar_init_fence();
     s_min[0] = kInfBits, s_min[1] = kInfBits;
     s_hasnan[0] = 0, s_hasnan[1] = 0;
+    for (int t = 0; t < kMaxT; ++t) s_last[t] = -1;
     const int c0 = (int)(g0 / nPt), it0 = (int)(g0 - (long long)c0 * nPt);
     s_prod.tile = 0, s_prod.ts = 0, s_prod.ds = 0, s_prod.c = c0, s_prod.it = it0;
   }
@@ -301,6 +304,10 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
     colg[g] = liveg[g] ? n : 0;
   }
   bool nanrange = false;
+  // exact nanmax(echo_range): the thread that owns the last column watches the final sample of every row
+  const int last_group = (R >> 2) - 1;
+  const bool is_last = pr.rmax != nullptr && tid == last_group % nth;
+  double range_last = -CUDART_INF, rmax_local = -CUDART_INF;
   Acc<G> acc;
   acc.clear();
   int cur_cell = -1;
@@ -314,6 +321,34 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
     for (int g = 0; g < G; ++g)
       flush_group(acc.s[g], acc.good[g], acc.nanm[g], acc.rows, s_keys + colg[g], s_ctl[(colg[g] >> 2)], liveg[g], acc_row);
     acc.clear();
+  };
+
+  // rows whose final sample is NaN (need bit t): every thread offers the last column it holds with a valid sample
+  // (e >= 0: the NaN sentinel is -2), thread 0 then evaluates the exact range law there
+  auto offer_last = [&](unsigned need, const float (&e)[G][T][4]) {
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+      if ((need >> t) & 1u) {
+        int best = -1;
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (liveg[g] && e[g][t][k] >= 0.f) best = colg[g] + k;
+        if (best >= 0) atomicMax(&s_last[t], best);
+      }
+  };
+  auto settle_last = [&](unsigned need, long long row0) {  // thread 0
+    for (int t = 0; t < T; ++t)
+      if ((need >> t) & 1u) {
+        const int n = s_last[t];
+        s_last[t] = -1;
+        if (n >= 0) {
+          const epb_row r = pr.rows[row0 + t];
+          const double v = law_range(r, n);
+          if (v == v) atomic_max_d(pr.rmax, v);
+        }
+      }
   };
 
   for (int li = 0; li < ntl; ++li) {
@@ -336,6 +371,7 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
       for (int k = tid; k <= nR; k += nth) s_bounds[k] = first_at_or_above(lr, R, s_edges[k], pr.closed_right);
       const RowF rf = load_rowf(pr.rows + row0);
       nanrange = rf.nanrange;
+      if (is_last) range_last = pr.rows[row0].range_last;
       for (int n = 4 * tid; n < R; n += 4 * nth) {
         float hh[4], gi[4];
 #pragma unroll
@@ -415,7 +451,7 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
 #pragma unroll
     for (int g = 0; g < G; ++g) nanmask[g] = 0u;
     if (!finite_f(chk)) {
-      if (kNoise) s_hasnan[it] = 1;
+      if (kNoise) atomicOr(&s_hasnan[it], 1);
 #pragma unroll
       for (int g = 0; g < G; ++g)
 #pragma unroll
@@ -440,6 +476,22 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
         }
     }
 
+    if (is_last) {  // rows whose final sample is NaN need a search for the last defined range (flags: bits 8.. of s_hasnan)
+      unsigned need = 0u;
+      if (nanrange) {
+        const int gl = last_group / nth;  // the group of this thread that holds the last column
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+          if (g == gl) {
+#pragma unroll
+            for (int t = 0; t < T; ++t)
+              if (t < Ta && ((nanmask[g] >> (4 * t + 3)) & 1u)) need |= 1u << t;
+          }
+      }
+      if (need != ((1u << Ta) - 1u) && range_last == range_last) rmax_local = fmax(rmax_local, range_last);
+      if (need) atomicOr(&s_hasnan[it], (int)(need << 8));
+    }
+
     float noise_lin = 0.f;
     if (kNoise) {
       // ---- phase 1: per-column sums of 10^((Sv-TL)/10) -> range-tile means -> min ----------------------------------------
@@ -461,10 +513,12 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
         s_min[it ^ 1] = kInfBits;
         s_hasnan[it ^ 1] = 0;
       }
+      const unsigned need_last = (unsigned)s_hasnan[it] >> 8;  // CTA-uniform, almost always 0
+      if (need_last) offer_last(need_last, e);
       // four lanes per range tile: lane q takes the column groups ga+q, ga+q+4, ... (one LDS.128 each, edges masked)
       if ((tid & ~31) < 4 * nRt) {
         const int q = tid & 3;
-        const bool hasnan = s_hasnan[it] != 0;
+        const bool hasnan = (s_hasnan[it] & 1) != 0;
         unsigned m = kInfBits;
         for (int rt = tid >> 2; rt < ((nRt + 7) & ~7); rt += nth >> 2) {
           const bool in = rt < nRt;
@@ -507,11 +561,19 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
         noise_lin = v;
         if (tid == 0 && pr.noise_out) pr.noise_out[g0 + li] = kLog2ToDb * fast_log2(v);  // global tile = c * nPt + tile
       }
+      if (need_last && tid == 0) settle_last(need_last, ti->row0);
     } else {
       __syncthreads();  // the tile's slot is free
       if (prod_warp && lane == 0) {
         fence_proxy_async();
         issue_tiles(li);
+        s_hasnan[it ^ 1] = 0;
+      }
+      const unsigned need_last = (unsigned)s_hasnan[it] >> 8;  // CTA-uniform, almost always 0
+      if (need_last) {
+        offer_last(need_last, e);
+        __syncthreads();
+        if (tid == 0) settle_last(need_last, ti->row0);
       }
     }
 
@@ -576,6 +638,7 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
     }
   }
   if (cur_cell >= 0) flush();
+  if (is_last && rmax_local != -CUDART_INF) atomic_max_d(pr.rmax, rmax_local);
 }
 
 size_t fast_smem(long long R, int T, int nR, int ntiles_ring, int nRt) {
@@ -603,7 +666,7 @@ int launch_fast(const FastParams& pr, int threads, size_t smem, cudaStream_t s) 
 int epb_pipeline_fast_try(const float* x, const epb_row* rows, const int* xbin, const double* r_edges, int nR,
                           int closed_right, double* acc, float* noise_out, long long C, long long P, long long R,
                           long long nX, int ping_num, int range_sample_num, float noise_max_lin, float snr_lin,
-                          void* workspace, long long workspace_bytes, cudaStream_t s) {
+                          double* range_max_out, void* workspace, long long workspace_bytes, cudaStream_t s) {
   const bool noise = ping_num > 0;
   const int T = noise ? ping_num : 4;
   if (T > kMaxT || R % 4 != 0 || R > 4096 || R < 128 || C * nX >= (1LL << 31) || nR > 32000) return 0;
@@ -621,6 +684,7 @@ int epb_pipeline_fast_try(const float* x, const epb_row* rows, const int* xbin, 
   const size_t smem = fast_smem(R, T, nR, nslots, nRt);
   FastParams pr;
   pr.x = x, pr.rows = rows, pr.xbin = xbin, pr.edges = r_edges, pr.acc = acc, pr.noise_out = noise_out;
+  pr.rmax = range_max_out;
   int* irregular = (int*)workspace;
   pr.irregular = irregular;
   pr.tiles = reinterpret_cast<const TileInfo*>((char*)workspace + 256);

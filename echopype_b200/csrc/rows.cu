@@ -81,7 +81,7 @@ __device__ void finish_row(epb_row& r, int R, bool guard) {
   r.c1 = (float)(r.fscale * kL);
   r.c2 = (float)(r.two_alpha * kL);
   r.spow = (float)(r.slog / 10.0);
-  r.pad0 = r.pad1 = 0.f;
+  r.range_last = law_range(r, R - 1);
 }
 
 __global__ void rows_ek_power_kernel(epb_row* rows, long long C, long long P, int R, int sonar, int cal_type,

@@ -12,7 +12,7 @@ struct RowF {  // 64-byte float block of epb_row, loaded with four 16-byte loads
   float a_h, a_l, r0_h, r0_l;
   float bp_h, bp_l, two_alpha, slog2;
   float fscale, foffK, c0, c1;
-  float c2, spow, pad0, pad1;
+  float c2, spow;
   int n_start;
   bool nanrange;
 };
@@ -24,7 +24,7 @@ __device__ __forceinline__ RowF load_rowf(const epb_row* __restrict__ r) {
   o.a_h = q0.x, o.a_l = q0.y, o.r0_h = q0.z, o.r0_l = q0.w;
   o.bp_h = q1.x, o.bp_l = q1.y, o.two_alpha = q1.z, o.slog2 = q1.w;
   o.fscale = q2.x, o.foffK = q2.y, o.c0 = q2.z, o.c1 = q2.w;
-  o.c2 = q3.x, o.spow = q3.y, o.pad0 = q3.z, o.pad1 = q3.w;
+  o.c2 = q3.x, o.spow = q3.y;  // q3.z, q3.w: range_last (float64), not used by the sample kernels
   o.n_start = __ldg(&r->n_start);
   o.nanrange = (__ldg(&r->law) & EPB_LAW_NANRANGE) != 0;
   return o;

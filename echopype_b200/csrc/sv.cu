@@ -245,30 +245,28 @@ __global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ a
   if (__any_sync(0xffffffffu, nan) && (threadIdx.x & 31) == 0) minmax[2] = 1.f;
 }
 
-__device__ __forceinline__ void atomic_max_d(double* addr, double v) {  // v >= 0 or any sign, non-NaN
-  long long iv = __double_as_longlong(v);
-  if (iv >= 0)
-    atomicMax((long long*)addr, iv);
-  else
-    atomicMin((unsigned long long*)addr, (unsigned long long)iv);
-}
-
 // exact float64 nanmax of the echo_range that compute_Sv would produce: per row, the law value at the last
-// sample whose range is not NaN (range.py:143-148: NaN where the input sample is NaN)
+// sample whose range is not NaN (range.py:143-148: NaN where the input sample is NaN).  Hot case: the last sample
+// is valid and the answer is the precomputed rows[row].range_last (one 8-byte and one 4-byte read per row).
 __global__ void range_max_kernel(const float* __restrict__ x, const epb_row* __restrict__ rows, long long nrows, int R,
-                                 double* __restrict__ out) {
+                                 double* __restrict__ out, const int* __restrict__ gate) {
+  if (gate && *gate == 0) return;  // the fast fused kernel computed the maximum itself
   const long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   double best = -CUDART_INF;
   if (row < nrows) {
-    const epb_row r = rows[row];
-    int n = R - 1;
-    if (x && (r.law & EPB_LAW_NANRANGE)) {
-      const float* xr = x + row * (long long)R;
-      while (n >= 0 && xr[n] != xr[n]) --n;
-    }
-    if (n >= 0) {  // the law is monotone non-decreasing in n (positive sample interval / sound speed)
-      const double v1 = law_range(r, n);
+    const bool nanrule = x && (__ldg(&rows[row].law) & EPB_LAW_NANRANGE);
+    const float* xr = x + row * (long long)R;
+    if (!nanrule || xr[R - 1] == xr[R - 1]) {
+      const double v1 = __ldg(&rows[row].range_last);  // the law is monotone non-decreasing in n
       if (v1 == v1) best = v1;
+    } else {
+      int n = R - 2;
+      while (n >= 0 && xr[n] != xr[n]) --n;
+      if (n >= 0) {
+        const epb_row r = rows[row];
+        const double v1 = law_range(r, n);
+        if (v1 == v1) best = v1;
+      }
     }
   }
 #pragma unroll
@@ -294,6 +292,13 @@ extern "C" int epb_range_max(const float* backscatter_r, const epb_row* rows, ep
   const long long nrows = C * P;
   init_range_max_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(out_max);
   range_max_kernel<<<(unsigned)((nrows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(backscatter_r, rows, nrows, (int)R,
-                                                                                    out_max);
+                                                                                    out_max, nullptr);
   return epb_check_launch("epb_range_max");
+}
+
+// used by epb_pipeline_power_mvbs: initialise *out_max, and (gated) compute it when the general kernel does the work
+void epb_range_max_init_launch(double* out_max, cudaStream_t s) { init_range_max_kernel<<<1, 1, 0, s>>>(out_max); }
+void epb_range_max_gated_launch(const float* x, const epb_row* rows, long long nrows, int R, double* out_max, const int* gate,
+                                cudaStream_t s) {
+  range_max_kernel<<<(unsigned)((nrows + 127) / 128), 128, 0, s>>>(x, rows, nrows, R, out_max, gate);
 }

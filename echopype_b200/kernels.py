@@ -229,7 +229,7 @@ def range_max(x, rows, C, P, R):
 
 def pipeline_power_mvbs(x, rows, xbin, r_edges, acc, C, P, R, nX, ping_num, range_sample_num, noise_max=None,
                         snr=3.0, closed_right=False, noise_out=None, Sv=None, echo_range=None, Sv_noise=None,
-                        Sv_corrected=None, fast=True):
+                        Sv_corrected=None, fast=True, rmax_out=None):
     """fast=False forces the general kernel (no workspace -> no fast-path dispatch)."""
     nm = float("nan") if noise_max is None else float(noise_max)
     nR = int(r_edges.numel()) - 1
@@ -238,7 +238,7 @@ def pipeline_power_mvbs(x, rows, xbin, r_edges, acc, C, P, R, nX, ping_num, rang
     _lib.call(
         "epb_pipeline_power_mvbs", ptr(x), ptr(rows), ptr(xbin), ptr(r_edges), nR, int(closed_right), ptr(acc),
         ptr(noise_out), ptr(Sv), ptr(echo_range), ptr(Sv_noise), ptr(Sv_corrected), C, P, R, nX, int(ping_num),
-        int(range_sample_num), ctypes.c_float(nm), ctypes.c_float(float(snr)), ptr(ws), nws, stream(),
+        int(range_sample_num), ctypes.c_float(nm), ctypes.c_float(float(snr)), ptr(rmax_out), ptr(ws), nws, stream(),
     )
     return acc
 

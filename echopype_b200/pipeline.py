@@ -243,8 +243,7 @@ class FusedPlan:
         rmax = None
         if on_device:
             if self.range_var_max is None:
-                rmax = torch.empty(1, dtype=torch.float64, device=self.dev)
-                kernels.range_max_into(x, rows, C, P, R, rmax)
+                rmax = torch.empty(1, dtype=torch.float64, device=self.dev)  # filled by the fused launch
                 self.launches += 2
             if self.record_events:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -253,6 +252,7 @@ class FusedPlan:
                 x, rows, self.xbin, edges_t, acc, C, P, R, nX, self.ping_num, self.range_sample_num,
                 noise_max=self.noise_max, snr=self.snr, closed_right=(self.closed == "right"), noise_out=noise,
                 fast=self.fast, Sv=outs["Sv"], echo_range=outs["echo_range"], Sv_noise=outs["Sv_noise"], Sv_corrected=outs["Sv_corrected"],
+                rmax_out=rmax,
             )
             if self.record_events:
                 ev[1].record()
@@ -313,12 +313,9 @@ class FusedPlan:
                     fast=self.fast,
                     noise_out=None if noise is None else noise[c, p0 // pn : p0 // pn + -(-pc // pn)],
                     Sv=sub(outs["Sv"]), echo_range=sub(outs["echo_range"]), Sv_noise=sub(outs["Sv_noise"]),
-                    Sv_corrected=sub(outs["Sv_corrected"]),
+                    Sv_corrected=sub(outs["Sv_corrected"]), rmax_out=rmax_t[i : i + 1] if want_rmax else None,
                 )
-                self.launches += 3 if self.fast else 1
-                if want_rmax:
-                    kernels.range_max_into(buf, rsub, 1, pc, R, rmax_t[i : i + 1])
-                    self.launches += 2
+                self.launches += (3 if self.fast else 1) + (2 if want_rmax else 0)
                 freed[slot].record(main)
                 i += 1
         return rmax_t

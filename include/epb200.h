@@ -80,7 +80,7 @@ typedef struct epb_row {
   float c1;           /* fscale * log2(10)/10                             */
   float c2;           /* two_alpha * log2(10)/10                          */
   float spow;         /* slog/10: R'^spow is the linear-domain spreading  */
-  float pad0, pad1;
+  double range_last;  /* exact range law at the last sample, law_range(R - 1): upper bound of echo_range in the row */
 } epb_row;
 
 #define EPB_LAW_EK 0
@@ -189,6 +189,8 @@ int epb_coarsen(const float* Sv, const float* echo_range, float* out, float* er_
  * Sv_corrected [C,P,R] float32.  noise_out: [C, ceil(P/ping_num)] (dB) or NULL.
  * ping_num = 0 skips noise removal (Sv -> MVBS).  noise_max: dB, NaN = no cap.  Requires R % 4 == 0,
  * ping_num <= 256; returns EPB_E_UNSUPPORTED when the per-CTA accumulators exceed shared memory.
+ * range_max_out: NULL or one float64 that receives the exact nanmax(echo_range) (what epb_range_max computes; -inf if
+ * every range is NaN), for trimming an upper-bound range grid (commongrid/api.py:108-115) without a second pass.
  * workspace: NULL or a 16-byte aligned device scratch buffer of workspace_bytes >=
  * epb_pipeline_workspace_bytes(C, P, ping_num) bytes owned by the caller and private to this launch (it receives
  * one 144-byte descriptor per ping tile); with a workspace, regular volumes (every ping tile shares one range law, finite
@@ -198,8 +200,8 @@ int epb_pipeline_power_mvbs(const float* backscatter_r, const epb_row* rows, con
                             const double* r_edges, int nR, int closed_right, double* acc, float* noise_out,
                             float* Sv, float* echo_range, float* Sv_noise, float* Sv_corrected, epb_i64 C,
                             epb_i64 P, epb_i64 R, epb_i64 nX, int ping_num, int range_sample_num,
-                            float noise_max, float snr_threshold, void* workspace, epb_i64 workspace_bytes,
-                            void* stream);
+                            float noise_max, float snr_threshold, double* range_max_out, void* workspace,
+                            epb_i64 workspace_bytes, void* stream);
 epb_i64 epb_pipeline_workspace_bytes(epb_i64 C, epb_i64 P, int ping_num);
 epb_i64 epb_pipeline_smem_bytes(epb_i64 R, int nR, int tile, int do_noise, int staged);
 
