@@ -417,10 +417,12 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
 #pragma unroll
       for (int g = 0; g < G; ++g) {
         const float4 v = *reinterpret_cast<const float4*>(tbase + t * R + colg[g]);
-        e[g][t][0] = fast_exp2(fmaf(v.x, rc.y, rc.x));
-        e[g][t][1] = fast_exp2(fmaf(v.y, rc.y, rc.x));
-        e[g][t][2] = fast_exp2(fmaf(v.z, rc.y, rc.x));
-        e[g][t][3] = fast_exp2(fmaf(v.w, rc.y, rc.x));
+        const float2 c0p = make_float2(rc.x, rc.x), c1p = make_float2(rc.y, rc.y);
+        const float2 a01 = ffma2(make_float2(v.x, v.y), c1p, c0p), a23 = ffma2(make_float2(v.z, v.w), c1p, c0p);  // FFMA2
+        e[g][t][0] = fast_exp2(a01.x);
+        e[g][t][1] = fast_exp2(a01.y);
+        e[g][t][2] = fast_exp2(a23.x);
+        e[g][t][3] = fast_exp2(a23.y);
       }
     }
     if (Ta < T) {  // partial tile (end of a channel): the missing rows contribute nothing
@@ -438,11 +440,12 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
 #pragma unroll
     for (int g = 0; g < G; ++g)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        se[g][k] = e[g][0][k];
+      for (int k = 0; k < 4; k += 2) {  // column pairs: FADD2
+        float2 acc2 = make_float2(e[g][0][k], e[g][0][k + 1]);
 #pragma unroll
-        for (int t = 1; t < T; ++t) se[g][k] += e[g][t][k];
-        chk += se[g][k];
+        for (int t = 1; t < T; ++t) acc2 = fadd2(acc2, make_float2(e[g][t][k], e[g][t][k + 1]));
+        se[g][k] = acc2.x, se[g][k + 1] = acc2.y;
+        chk += acc2.x + acc2.y;
       }
     // Rare: some sample of this thread is NaN (padded ping) or e overflowed.  Remember where (bit t*4+k per group),
     // make the column sums NaN-free, tell the range-tile reducer how many samples are missing, and replace the
@@ -595,36 +598,39 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
           const float4 h4 = *reinterpret_cast<const float4*>(s_h + colg[g]);
           const float4 g4 = *reinterpret_cast<const float4*>(s_ginv + colg[g]);
           const float h[4] = {h4.x, h4.y, h4.z, h4.w}, gi[4] = {g4.x, g4.y, g4.z, g4.w};
+          float ethr[4], nl[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            float ethr, nl;
             if (kNoise) {
               const float ne = noise_lin * gi[k];  // noise TL / h: the noise floor in the e domain
-              ethr = ne * pr.snr1;                 // Sv_c - Sv_noise > SNR  <=>  e > ne (1 + 10^(SNR/10))
-              nl = ne * h[k];                      // 10^(Sv_noise/10)
+              ethr[k] = ne * pr.snr1;              // Sv_c - Sv_noise > SNR  <=>  e > ne (1 + 10^(SNR/10))
+              nl[k] = ne * h[k];                   // 10^(Sv_noise/10)
             } else {
-              ethr = (h[k] == h[k]) ? -1.f : CUDART_NAN_F;  // every non-NaN e of a column with defined Sv
-              nl = 0.f;
+              ethr[k] = (h[k] == h[k]) ? -1.f : CUDART_NAN_F;  // every non-NaN e of a column with defined Sv
+              nl[k] = 0.f;
             }
-            float sg = 0.f, ng_f = 0.f;
-            if (whole) {  // every e finite (or the -2 sentinel): branch-free mask arithmetic, FSET + FFMA + FADD
+          }
 #pragma unroll
-              for (int t = 0; t < T; ++t) {
-                const float m = (e[g][t][k] > ethr) ? 1.f : 0.f;
-                sg = fmaf(m, e[g][t][k], sg);
-                ng_f += m;
-              }
-            } else {
+          for (int k = 0; k < 4; k += 2) {  // column pairs: mask = (e > ethr) as 1.0 / 0.0, FSET x2 + FFMA2 + FADD2 per row
+            float2 sg = make_float2(0.f, 0.f), ng = make_float2(0.f, 0.f);
 #pragma unroll
-              for (int t = 0; t < T; ++t) {
-                const float m = (t >= ta && t < tb && e[g][t][k] > ethr) ? 1.f : 0.f;
-                sg = fmaf(m, e[g][t][k], sg);
-                ng_f += m;
+            for (int t = 0; t < T; ++t) {
+              float2 m;
+              if (whole) {  // every e finite (or the -2 sentinel)
+                m.x = (e[g][t][k] > ethr[k]) ? 1.f : 0.f;
+                m.y = (e[g][t][k + 1] > ethr[k + 1]) ? 1.f : 0.f;
+              } else {
+                m.x = (t >= ta && t < tb && e[g][t][k] > ethr[k]) ? 1.f : 0.f;
+                m.y = (t >= ta && t < tb && e[g][t][k + 1] > ethr[k + 1]) ? 1.f : 0.f;
               }
+              sg = ffma2(m, make_float2(e[g][t][k], e[g][t][k + 1]), sg);
+              ng = fadd2(ng, m);
             }
-            const float contrib = fmaf(h[k], sg, -(ng_f * nl));
-            acc.s[g][k] += (ng_f > 0.f) ? contrib : 0.f;
-            acc.good[g][k] += ng_f;
+            const float c0 = fmaf(h[k], sg.x, -(ng.x * nl[k])), c1 = fmaf(h[k + 1], sg.y, -(ng.y * nl[k + 1]));
+            acc.s[g][k] += (ng.x > 0.f) ? c0 : 0.f;
+            acc.s[g][k + 1] += (ng.y > 0.f) ? c1 : 0.f;
+            acc.good[g][k] += ng.x;
+            acc.good[g][k + 1] += ng.y;
           }
           if (nanmask[g] != 0u && nanrange) {  // echo_range is NaN where the sample is NaN (range.py:143-148): not a member
             const unsigned rows_mask = ((tb >= 8) ? 0xffffffffu : ((1u << (4 * tb)) - 1u)) & ~((1u << (4 * ta)) - 1u);
