@@ -102,11 +102,13 @@ def _reduce(ds_Sv, range_var, xbin_np, nX, r_edges_np, closed, skipna, fill_valu
     acc = kernels.new_acc(C, nX, nR, dev)
     law = getattr(rda, "law", None)
     use_law = (
-        law is not None and law.get("rows") is not None and law.get("kind") == "echo_range" and skipna
+        law is not None and law.get("rows") is not None and law.get("kind") in ("echo_range", "depth") and skipna
         and np.isnan(fill_value) and nR <= 511 and not with_height and tuple(rda.shape) == (C, P, R)
     )
     if use_law:
-        kernels.bin_reduce_law(Sv_t, law["rows"], xbin, edges, acc, C, P, R, nX, closed_right=(closed == "right"))
+        # depth = off[p] + echo_range * scale[p] (consolidate.add_depth): boundaries on the exact float64 law
+        kernels.bin_reduce_law(Sv_t, law["rows"], xbin, edges, acc, C, P, R, nX, closed_right=(closed == "right"),
+                               depth_off=law.get("off"), depth_scale=law.get("scale"))
     else:
         rng_t = _range_tensor(rda, dev)
         if tuple(rng_t.shape) != (C, P, R):

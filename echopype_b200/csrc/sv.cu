@@ -278,6 +278,42 @@ __global__ void init_range_max_kernel(double* out) { *out = -CUDART_INF; }
 
 }  // namespace
 
+// consolidate.add_depth: depth = off[c,p] + echo_range * scale[c,p] (float64 parameters, float32 samples)
+namespace {
+__global__ void __launch_bounds__(256) add_depth_kernel(const float* __restrict__ rng, epb_cp off, epb_cp scale,
+                                                        float* __restrict__ out, long long nrows, long long P, int R) {
+  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const long long c = row / P, p = row % P;
+    const float o = (float)cp_at(off, c, p), sc = (float)cp_at(scale, c, p);
+    const double od = cp_at(off, c, p), sd = cp_at(scale, c, p);
+    const long long base = row * (long long)R;
+    if ((R & 3) == 0 && ((((uintptr_t)rng) | ((uintptr_t)out)) & 15) == 0) {
+      const float4* r4 = reinterpret_cast<const float4*>(rng + base);
+      float4* o4 = reinterpret_cast<float4*>(out + base);
+      for (int j = threadIdx.x; j < (R >> 2); j += blockDim.x) {
+        const float4 v = ld_stream4(r4 + j);
+        // float64 evaluation of two float32-exact inputs, rounded once: within half an ulp of the reference value
+        st_stream4(o4 + j, make_float4((float)(od + (double)v.x * sd), (float)(od + (double)v.y * sd),
+                                       (float)(od + (double)v.z * sd), (float)(od + (double)v.w * sd)));
+      }
+    } else {
+      for (int n = threadIdx.x; n < R; n += blockDim.x) out[base + n] = (float)(od + (double)rng[base + n] * sd);
+    }
+    (void)o, (void)sc;
+  }
+}
+}  // namespace
+
+extern "C" int epb_add_depth(const float* echo_range, epb_cp depth_offset, epb_cp scale, float* depth, epb_i64 C, epb_i64 P,
+                             epb_i64 R, void* stream) {
+  EPB_REQUIRE(echo_range && depth && depth_offset.ptr && scale.ptr, "NULL pointer");
+  EPB_REQUIRE(C > 0 && P > 0 && R > 0 && R < (1LL << 30), "bad shape");
+  const long long nrows = C * P;
+  const int grid = (int)((nrows < (long long)epb_num_sms() * 8) ? nrows : (long long)epb_num_sms() * 8);
+  add_depth_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(echo_range, depth_offset, scale, depth, nrows, P, (int)R);
+  return epb_check_launch("epb_add_depth");
+}
+
 extern "C" int epb_minmax(const float* a, epb_i64 n, float* minmax, void* stream) {
   EPB_REQUIRE(a && minmax && n > 0, "bad pointer/size");
   const long long blocks = (n + 255) / 256;

@@ -202,6 +202,20 @@ def coarsen(Sv, echo_range, C, P, R, ping_num, range_sample_num):
     return out, er
 
 
+def to_device_f64(a, device=None):
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64))).to(device or require_cuda())
+
+
+def add_depth(echo_range, off_p, scale, C, P, R):
+    """depth = off[p] + echo_range * scale (scale: (P,) per ping or (C, P)); float32 device tensor [C,P,R]."""
+    pk = ParamPack(C, P, echo_range.device)
+    out = empty((C, P, R), device=echo_range.device)
+    _lib.call("epb_add_depth", ptr(echo_range), pk.cp(np.asarray(off_p, dtype=np.float64)), pk.cp(np.asarray(scale, dtype=np.float64)),
+              ptr(out), C, P, R, stream())
+    out._keep = pk
+    return out
+
+
 def minmax(a):
     """(min, max, has_nan) over the non-NaN elements of a float32 device tensor (one streaming pass)."""
     mm = new_minmax(a.device)

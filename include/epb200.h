@@ -205,6 +205,11 @@ int epb_pipeline_power_mvbs(const float* backscatter_r, const epb_row* rows, con
 epb_i64 epb_pipeline_workspace_bytes(epb_i64 C, epb_i64 P, int ping_num);
 epb_i64 epb_pipeline_smem_bytes(epb_i64 R, int nR, int tile, int do_noise, int staged);
 
+/* ---- consolidate.add_depth (consolidate/api.py:221): depth = depth_offset[c,p] + echo_range * scale[c,p], scale =
+ *      orientation * cos(tilt) (or the platform / beam angle scaling).  echo_range, depth: [C,P,R] float32. -------- */
+int epb_add_depth(const float* echo_range, epb_cp depth_offset, epb_cp scale, float* depth, epb_i64 C, epb_i64 P,
+                  epb_i64 R, void* stream);
+
 /* ---- helpers ---------------------------------------------------------------------------------------- */
 int epb_zero(void* ptr, epb_i64 nbytes, void* stream);
 int epb_minmax_init(float* minmax /* 4 floats */, void* stream);
