@@ -55,6 +55,8 @@ SIGNATURES = {
     "epb_pipeline_workspace_bytes": (i64, [i64, i64, c_int]),
     "epb_pipeline_smem_bytes": (i64, [i64, c_int, c_int, c_int, c_int]),
     "epb_add_depth": (c_int, [vp, epb_cp, epb_cp, vp, i64, i64, i64, vp]),
+    "epb_freq_diff_mask": (c_int, [vp, c_int, c_int, c_int, c_float, vp, i64, i64, i64, vp]),
+    "epb_apply_mask": (c_int, [vp, vp, c_int, c_float, vp, i64, i64, i64, vp]),
     "epb_zero": (c_int, [vp, i64, vp]),
     "epb_minmax_init": (c_int, [vp, vp]),
     "epb_minmax": (c_int, [vp, i64, vp, vp]),

@@ -314,6 +314,67 @@ extern "C" int epb_add_depth(const float* echo_range, epb_cp depth_offset, epb_c
   return epb_check_launch("epb_add_depth");
 }
 
+// mask.frequency_differencing / mask.apply_mask (mask/api.py:593-608, :437-438)
+namespace {
+__device__ __forceinline__ bool cmp_op(float lhs, float diff, int op) {
+  switch (op) {
+    case 0: return lhs > diff;
+    case 1: return lhs < diff;
+    case 2: return lhs <= diff;
+    case 3: return lhs >= diff;
+    default: return lhs == diff;
+  }
+}
+__global__ void __launch_bounds__(256) freq_diff_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                        unsigned char* __restrict__ mask, long long n, int op, float diff) {
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 3 < n && (((uintptr_t)a | (uintptr_t)b) & 15) == 0 && (((uintptr_t)mask) & 3) == 0) {
+      const float4 x = ld_stream4(reinterpret_cast<const float4*>(a + i));
+      const float4 y = ld_stream4(reinterpret_cast<const float4*>(b + i));
+      const unsigned m = (cmp_op(x.x - y.x, diff, op) ? 1u : 0u) | (cmp_op(x.y - y.y, diff, op) ? 0x100u : 0u) |
+                         (cmp_op(x.z - y.z, diff, op) ? 0x10000u : 0u) | (cmp_op(x.w - y.w, diff, op) ? 0x1000000u : 0u);
+      *reinterpret_cast<unsigned*>(mask + i) = m;  // NaN differences compare false
+    } else {
+      for (long long j = i; j < n && j < i + 4; ++j) mask[j] = cmp_op(a[j] - b[j], diff, op) ? 1 : 0;
+    }
+  }
+}
+__global__ void __launch_bounds__(256) apply_mask_kernel(const float* __restrict__ src, const unsigned char* __restrict__ mask,
+                                                         float* __restrict__ out, long long n, long long plane,
+                                                         int mask_has_channel, float fill) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+    const long long mi = mask_has_channel ? i : i % plane;
+    out[i] = mask[mi] ? ld_stream(src + i) : fill;
+  }
+}
+}  // namespace
+
+extern "C" int epb_freq_diff_mask(const float* Sv, int chanA, int chanB, int op, float diff, unsigned char* mask, epb_i64 C,
+                                  epb_i64 P, epb_i64 R, void* stream) {
+  EPB_REQUIRE(Sv && mask, "NULL pointer");
+  EPB_REQUIRE(C > 0 && P > 0 && R > 0 && chanA >= 0 && chanA < C && chanB >= 0 && chanB < C && op >= 0 && op <= 4, "bad argument");
+  const long long n = P * R;
+  long long blocks = (n / 4 + 255) / 256;
+  const long long cap = (long long)epb_num_sms() * 16;
+  freq_diff_kernel<<<(unsigned)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap), 256, 0, (cudaStream_t)stream>>>(
+      Sv + chanA * n, Sv + chanB * n, mask, n, op, diff);
+  return epb_check_launch("epb_freq_diff_mask");
+}
+
+extern "C" int epb_apply_mask(const float* src, const unsigned char* mask, int mask_has_channel, float fill_value, float* out,
+                              epb_i64 C, epb_i64 P, epb_i64 R, void* stream) {
+  EPB_REQUIRE(src && mask && out, "NULL pointer");
+  EPB_REQUIRE(C > 0 && P > 0 && R > 0, "bad shape");
+  const long long n = C * P * R;
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)epb_num_sms() * 16;
+  apply_mask_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(src, mask, out, n, P * R,
+                                                                                            mask_has_channel, fill_value);
+  return epb_check_launch("epb_apply_mask");
+}
+
 extern "C" int epb_minmax(const float* a, epb_i64 n, float* minmax, void* stream) {
   EPB_REQUIRE(a && minmax && n > 0, "bad pointer/size");
   const long long blocks = (n + 255) / 256;

@@ -216,6 +216,18 @@ def add_depth(echo_range, off_p, scale, C, P, R):
     return out
 
 
+def freq_diff_mask(Sv, a, b, op, diff, C, P, R):
+    m = torch.empty((int(P), int(R)), dtype=torch.uint8, device=Sv.device)
+    _lib.call("epb_freq_diff_mask", ptr(Sv), int(a), int(b), int(op), ctypes.c_float(float(diff)), ptr(m), C, P, R, stream())
+    return m
+
+
+def apply_mask(src, mask, has_channel, fill, C, P, R):
+    out = empty((C, P, R), device=src.device)
+    _lib.call("epb_apply_mask", ptr(src), ptr(mask), int(bool(has_channel)), ctypes.c_float(float(fill)), ptr(out), C, P, R, stream())
+    return out
+
+
 def minmax(a):
     """(min, max, has_nan) over the non-NaN elements of a float32 device tensor (one streaming pass)."""
     mm = new_minmax(a.device)

@@ -1,0 +1,127 @@
+"""mask.frequency_differencing / mask.apply_mask (echopype/mask/api.py:467-676, :307-464) with the
+O(channel x ping x range) comparisons and selections on the device (epb_freq_diff_mask, epb_apply_mask).  Masks are
+(ping_time, range_sample) or (channel, ping_time, range_sample) boolean arrays; on the device they are uint8 tensors."""
+
+import datetime
+from typing import List, Union
+
+import numpy as np
+import torch
+
+from .. import kernels
+from ..dataset import DataArray, Dataset, as_dataset
+from ..device import require_cuda, to_device_f32
+from ..utils.prov import echopype_prov_attrs, insert_input_processing_level
+from .freq_diff import _check_freq_diff_source_Sv, _parse_freq_diff_eq
+
+_OPS = {">": 0, "<": 1, "<=": 2, ">=": 3, "==": 4}
+
+
+def _history():
+    return f"{datetime.datetime.now(datetime.UTC)}. `depth` calculated using:"
+
+
+def frequency_differencing(source_Sv, storage_options: dict = {}, freqABEq: str = None, chanABEq: str = None) -> DataArray:
+    """Mask where ``Sv[chanA] - Sv[chanB] <operator> diff`` (arguments, errors and attrs as the reference).  Returns a
+    (ping_time, range_sample) boolean DataArray named ``mask`` held on the device as uint8."""
+    freqAB, chanAB, operator, diff = _parse_freq_diff_eq(freqABEq, chanABEq)
+    if isinstance(source_Sv, str):
+        raise NotImplementedError("file inputs are outside the accelerated path; pass a Dataset")
+    source_Sv = as_dataset(source_Sv)
+    _check_freq_diff_source_Sv(source_Sv, freqAB, chanAB)
+    chan = [str(c) for c in np.asarray(source_Sv["channel"].values).tolist()]
+    if freqAB is not None:
+        f = np.asarray(source_Sv["frequency_nominal"].values, dtype=np.float64)
+        chanA = chan[int(np.argwhere(f == freqAB[0]).flatten()[0])]
+        chanB = chan[int(np.argwhere(f == freqAB[1]).flatten()[0])]
+    else:
+        chanA, chanB = chanAB
+    a, b = chan.index(chanA), chan.index(chanB)
+    sv = source_Sv["Sv"]
+    if tuple(sv.dims) != ("channel", "ping_time", "range_sample"):
+        raise ValueError("Sv must have dims ('channel', 'ping_time', 'range_sample')")
+    dev = require_cuda()
+    C, P, R = sv.shape
+    sv_t = to_device_f32(sv.data, dev)
+    m = kernels.freq_diff_mask(sv_t, a, b, _OPS[operator], float(diff), C, P, R)
+    da = DataArray(m, ("ping_time", "range_sample"), name="mask",
+                   coords={k: source_Sv[k].values for k in ("ping_time", "range_sample") if k in source_Sv.coords})
+    da.attrs.update({
+        "mask_type": "frequency differencing",
+        "history": f"{_history()}. Mask created by mask.frequency_differencing. Operation: Sv['{chanA}'] - Sv['{chanB}'] {operator} {diff}",
+    })
+    return da
+
+
+def _mask_tensor(m, dev):
+    """DataArray / ndarray / tensor -> (uint8 device tensor, has_channel).  NaN counts as False (api.py:431-435)."""
+    data = m.data if isinstance(m, DataArray) else m
+    dims = tuple(m.dims) if isinstance(m, DataArray) else None
+    if isinstance(data, torch.Tensor):
+        t = data
+        if t.dtype != torch.uint8:
+            t = (torch.nan_to_num(t.float(), nan=0.0) != 0).to(torch.uint8)
+        t = t.to(dev)
+    else:
+        a = np.asarray(data)
+        if a.dtype.kind == "f":
+            a = np.where(np.isnan(a), 0.0, a)
+        t = torch.from_numpy(np.ascontiguousarray(a.astype(bool).astype(np.uint8))).to(dev)
+    has_channel = (dims is not None and "channel" in dims) or (dims is None and t.ndim == 3)
+    if dims is not None and has_channel and dims[0] != "channel":
+        raise ValueError("masks with a channel dimension must have it first")
+    return t.contiguous(), has_channel
+
+
+def apply_mask(source_ds, mask: Union[DataArray, List[DataArray]], var_name: str = "Sv",
+               fill_value: Union[int, float] = np.nan, storage_options_ds: dict = {}, storage_options_mask=None) -> Dataset:
+    """``source_ds[var_name]`` where the mask(s) hold, ``fill_value`` elsewhere (echopype.mask.apply_mask).  Several
+    masks are combined with logical AND.  Returns a shallow copy of the Dataset with the masked variable (device
+    resident) and the reference's provenance attributes."""
+    source_ds = as_dataset(source_ds)
+    if var_name not in source_ds.variables:
+        raise ValueError("The Dataset source_ds does not contain the variable var_name!")
+    if not isinstance(fill_value, (int, float)):
+        raise NotImplementedError("array-valued fill_value is outside the accelerated path")
+    masks = list(mask) if isinstance(mask, (list, tuple)) else [mask]
+    if not masks:
+        raise ValueError("mask must contain at least one mask")
+    src = source_ds[var_name]
+    if tuple(src.dims) != ("channel", "ping_time", "range_sample"):
+        raise ValueError(f"source_ds[{var_name}] must have dims ('channel', 'ping_time', 'range_sample')")
+    dev = require_cuda()
+    C, P, R = src.shape
+    out = to_device_f32(src.data, dev)
+    for m in masks:
+        mt, has_c = _mask_tensor(m, dev)
+        if tuple(mt.shape[-2:]) != (P, R):
+            raise ValueError(
+                f"The final constructed mask is not of the same shape as source_ds[{var_name}] "
+                "along the ping_time, and range_sample dimensions!"
+            )
+        if has_c and mt.shape[0] != C:
+            raise ValueError(
+                f"If both the final constructed mask and source_ds[{var_name}] "
+                "have the channel dimension, that dimension should match between the two."
+            )
+        out = kernels.apply_mask(out, mt, has_c, float(fill_value), C, P, R)
+    lo, hi, _ = kernels.minmax(out)
+    attrs = dict(src.attrs)
+    attrs.update({
+        "long_name": "Volume backscattering strength, masked (Sv re 1 m-1)",
+        "actual_range": [round(float(lo), 2), round(float(hi), 2)],
+        "history": f"{_history()}. Created masked Sv dataarray.",
+    })
+    m0 = masks[0]
+    if isinstance(m0, DataArray) and len(m0.attrs) > 0:
+        ma = dict(m0.attrs)
+        if "history" in ma:
+            attrs["history"] += f"\n{ma.pop('history')}"
+        attrs.update(ma)
+    output_ds = source_ds.copy()
+    output_ds[var_name] = DataArray(out, src.dims, name=var_name, attrs=attrs)
+    prov = echopype_prov_attrs(process_type="mask")
+    prov["mask_function"] = "mask.apply_mask"
+    output_ds.attrs.update(prov)
+    output_ds = insert_input_processing_level(output_ds, input_ds=source_ds)
+    return output_ds

@@ -210,6 +210,14 @@ epb_i64 epb_pipeline_smem_bytes(epb_i64 R, int nR, int tile, int do_noise, int s
 int epb_add_depth(const float* echo_range, epb_cp depth_offset, epb_cp scale, float* depth, epb_i64 C, epb_i64 P,
                   epb_i64 R, void* stream);
 
+/* ---- mask.frequency_differencing (mask/api.py:593-608): mask[p,n] = (Sv[chanA,p,n] - Sv[chanB,p,n]) op diff with op
+ *      0 ">", 1 "<", 2 "<=", 3 ">=", 4 "==" (NaN -> 0); mask: [P,R] uint8.  mask.apply_mask (:437-438): out = mask ?
+ *      src : fill_value, mask [C,P,R] (mask_has_channel != 0) or [P,R] broadcast over channels. --------------------- */
+int epb_freq_diff_mask(const float* Sv, int chanA, int chanB, int op, float diff, unsigned char* mask, epb_i64 C,
+                       epb_i64 P, epb_i64 R, void* stream);
+int epb_apply_mask(const float* src, const unsigned char* mask, int mask_has_channel, float fill_value, float* out,
+                   epb_i64 C, epb_i64 P, epb_i64 R, void* stream);
+
 /* ---- helpers ---------------------------------------------------------------------------------------- */
 int epb_zero(void* ptr, epb_i64 nbytes, void* stream);
 int epb_minmax_init(float* minmax /* 4 floats */, void* stream);
