@@ -45,7 +45,7 @@ SIGNATURES = {
     "epb_noise_estimate": (c_int, [vp, vp, epb_cp, vp, i64, i64, i64, c_int, c_int, c_float, vp]),
     "epb_noise_apply": (c_int, [vp, vp, epb_cp, vp, vp, vp, vp, i64, i64, i64, c_int, c_float, vp]),
     "epb_bin_reduce": (c_int, [vp, vp, c_int, vp, vp, c_int, c_int, c_int, vp, i64, i64, i64, i64, vp]),
-    "epb_bin_reduce_law": (c_int, [vp, vp, vp, vp, vp, vp, c_int, c_int, vp, i64, i64, i64, i64, vp]),
+    "epb_bin_reduce_law": (c_int, [vp, vp, vp, vp, vp, vp, c_int, c_int, vp, i64, i64, i64, i64, vp, i64, vp]),
     "epb_bin_finalize": (c_int, [vp, vp, vp, i64, c_int, c_float, c_int, vp]),
     "epb_coarsen": (c_int, [vp, vp, vp, vp, i64, i64, i64, c_int, c_int, vp]),
     "epb_pipeline_power_mvbs": (

@@ -176,7 +176,8 @@ __device__ int first_at_or_above(const epb_row& r, int R, double edge, int close
 __global__ void __launch_bounds__(32 * kWarpsPerCta) bin_reduce_law_kernel(
     const float* __restrict__ Sv, const epb_row* __restrict__ rows, const double* __restrict__ depth_off,
     const double* __restrict__ depth_scale, const int* __restrict__ xbin, const double* __restrict__ edges, int nR,
-    int closed_right, double* __restrict__ acc, long long C, long long P, int R, long long nX) {
+    int closed_right, double* __restrict__ acc, long long C, long long P, int R, long long nX, const int* __restrict__ gate) {
+  if (gate && *gate == 0) return;  // the persistent fast kernel did the reduction
   extern __shared__ double s_edges[];                                        // [nR+1]
   int* s_bounds = reinterpret_cast<int*>(s_edges + (nR + 1));                // [kWarpsPerCta][nR+1]
   for (int k = threadIdx.x; k <= nR; k += blockDim.x) s_edges[k] = edges[k];
@@ -284,21 +285,33 @@ extern "C" int epb_bin_reduce(const float* Sv, const void* range_var, int range_
   return epb_check_launch("epb_bin_reduce");
 }
 
+int epb_pipeline_fast_try(const float* x, const epb_row* rows, const int* xbin, const double* r_edges, int nR,
+                          int closed_right, double* acc, float* noise_out, long long C, long long P, long long R,
+                          long long nX, int ping_num, int range_sample_num, float noise_max_lin, float snr_lin,
+                          double* range_max_out, int sv_input, void* workspace, long long workspace_bytes, cudaStream_t s);
+
 extern "C" int epb_bin_reduce_law(const float* Sv, const epb_row* rows, const double* depth_off,
                                   const double* depth_scale, const int* xbin, const double* r_edges, int nR,
                                   int closed_right, double* acc, epb_i64 C, epb_i64 P, epb_i64 R, epb_i64 nX,
-                                  void* stream) {
+                                  void* workspace, epb_i64 workspace_bytes, void* stream) {
   EPB_REQUIRE(Sv && rows && xbin && r_edges && acc, "NULL pointer");
   EPB_REQUIRE((depth_off == nullptr) == (depth_scale == nullptr), "depth_off and depth_scale go together");
   EPB_REQUIRE(C > 0 && P > 0 && R > 0 && R < (1LL << 30) && nX > 0, "bad shape");
   EPB_REQUIRE(nR > 0 && nR <= kMaxLawBins, "law path supports 1..511 range bins (use epb_bin_reduce)");
+  // echo_range binning of a regular volume: the persistent register-accumulating kernel of the fused pipeline, fed
+  // with Sv instead of power (pipeline_fast.cu, sv_input); decided on the device like in epb_pipeline_power_mvbs
+  const int* gate = nullptr;
+  if (workspace && workspace_bytes >= 256 && !depth_off && ((uintptr_t)workspace % 16) == 0 && ((uintptr_t)Sv % 16) == 0 &&
+      epb_pipeline_fast_try(Sv, rows, xbin, r_edges, nR, closed_right, acc, nullptr, C, P, R, nX, 0, 0, nanf(""), 0.f, nullptr, 1,
+                            workspace, workspace_bytes, (cudaStream_t)stream))
+    gate = (const int*)workspace;
   const long long nrows = C * P;
   long long grid = (nrows + kWarpsPerCta - 1) / kWarpsPerCta;
   const long long cap = (long long)epb_num_sms() * 8;
   if (grid > cap) grid = cap;
   const size_t smem = (size_t)(nR + 1) * sizeof(double) + (size_t)kWarpsPerCta * (nR + 1) * sizeof(int);
   bin_reduce_law_kernel<<<(unsigned)grid, 32 * kWarpsPerCta, smem, (cudaStream_t)stream>>>(
-      Sv, rows, depth_off, depth_scale, xbin, r_edges, nR, closed_right, acc, C, P, (int)R, nX);
+      Sv, rows, depth_off, depth_scale, xbin, r_edges, nR, closed_right, acc, C, P, (int)R, nX, gate);
   return epb_check_launch("epb_bin_reduce_law");
 }
 

@@ -400,7 +400,7 @@ extern "C" epb_i64 epb_pipeline_smem_bytes(epb_i64 R, int nR, int tile, int do_n
 int epb_pipeline_fast_try(const float* x, const epb_row* rows, const int* xbin, const double* r_edges, int nR,
                           int closed_right, double* acc, float* noise_out, long long C, long long P, long long R,
                           long long nX, int ping_num, int range_sample_num, float noise_max_lin, float snr_lin,
-                          double* range_max_out, void* workspace, long long workspace_bytes, cudaStream_t s);
+                          double* range_max_out, int sv_input, void* workspace, long long workspace_bytes, cudaStream_t s);
 void epb_range_max_init_launch(double* out_max, cudaStream_t s);
 void epb_range_max_gated_launch(const float* x, const epb_row* rows, long long nrows, int R, double* out_max, const int* gate,
                                 cudaStream_t s);
@@ -444,7 +444,7 @@ extern "C" int epb_pipeline_power_mvbs(const float* backscatter_r, const epb_row
       ((uintptr_t)workspace % 16) == 0 &&
       epb_pipeline_fast_try(backscatter_r, rows, xbin, r_edges, nR, closed_right, acc, noise_out, C, P, R, nX, ping_num,
                             range_sample_num, pr.noise_max_lin, (float)pow(10.0, (double)snr_threshold / 10.0),
-                            range_max_out, workspace, workspace_bytes, (cudaStream_t)stream))
+                            range_max_out, 0, workspace, workspace_bytes, (cudaStream_t)stream))
     pr.gate = (const int*)workspace;
   // stage the tile in shared memory when two CTAs per SM still fit, else when one fits, else stream from global
   pr.staged = 1;

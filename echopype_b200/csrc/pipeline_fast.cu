@@ -46,6 +46,7 @@ struct FastParams {
   int R, nR, rs_num, closed_right, nslots, nPt;
   float noise_max_lin;  // NaN: no cap
   float snr1;           // 1 + 10^(SNR/10)
+  int sv_input;         // the input is Sv in dB (bin reduction of compute_MVBS): e = 10^(Sv/10), h = 1, NaN = NaN member
 };
 
 struct TileInfo {  // 144 bytes; written per tile by prepare_kernel, fetched by TMA together with the tile's rows
@@ -72,7 +73,8 @@ __device__ __forceinline__ bool same_law(const epb_row& a, const epb_row& b) {
 // One thread per tile: build the tile descriptor and flag volumes the fast kernel cannot take (a tile whose rows do
 // not share one range law, or rows with NaN calibration constants).
 __global__ void prepare_kernel(const epb_row* __restrict__ rows, const int* __restrict__ xbin, long long P, long long nX,
-                               int T, int nPt, long long ntiles, TileInfo* __restrict__ tiles, int* __restrict__ irregular) {
+                               int T, int nPt, long long ntiles, int sv_input, TileInfo* __restrict__ tiles,
+                               int* __restrict__ irregular) {
   const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (g >= ntiles) return;
   const long long c = g / nPt;
@@ -90,9 +92,9 @@ __global__ void prepare_kernel(const epb_row* __restrict__ rows, const int* __re
   }
   for (int t = 0; t < Ta; ++t) {
     const epb_row& r = r0[t];
-    if (!(r.c0 == r.c0 && r.c1 == r.c1)) bad = true;
+    if (!sv_input && !(r.c0 == r.c0 && r.c1 == r.c1)) bad = true;
     if (!same_law(r0[0], r)) bad = true;  // NaN laws never compare equal
-    ti.rc[t] = make_float2(r.c0, r.c1);
+    ti.rc[t] = sv_input ? make_float2(0.f, kDb2Log2) : make_float2(r.c0, r.c1);  // Sv input: e = 2^(Sv log2(10)/10)
     int xb = xbin[p0 + t];
     if (xb < 0 || xb >= nX) xb = -1;
     if (t == 0 || xb != prev_xb) {
@@ -370,7 +372,7 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
       const epb_row& lr = pr.rows[row0];
       for (int k = tid; k <= nR; k += nth) s_bounds[k] = first_at_or_above(lr, R, s_edges[k], pr.closed_right);
       const RowF rf = load_rowf(pr.rows + row0);
-      nanrange = rf.nanrange;
+      nanrange = rf.nanrange && !pr.sv_input;
       if (is_last) range_last = pr.rows[row0].range_last;
       for (int n = 4 * tid; n < R; n += 4 * nth) {
         float hh[4], gi[4];
@@ -380,6 +382,7 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
           hh[k] = cc.h;
           gi[k] = __fdividef(cc.tl, cc.h);  // NaN where Sv is undefined; inf where R' = 0
           if (!(cc.h == cc.h)) gi[k] = CUDART_NAN_F;
+          if (pr.sv_input) hh[k] = 1.f, gi[k] = 1.f;
         }
         *reinterpret_cast<float4*>(s_h + n) = make_float4(hh[0], hh[1], hh[2], hh[3]);
         *reinterpret_cast<float4*>(s_ginv + n) = make_float4(gi[0], gi[1], gi[2], gi[3]);
@@ -672,7 +675,7 @@ int launch_fast(const FastParams& pr, int threads, size_t smem, cudaStream_t s) 
 int epb_pipeline_fast_try(const float* x, const epb_row* rows, const int* xbin, const double* r_edges, int nR,
                           int closed_right, double* acc, float* noise_out, long long C, long long P, long long R,
                           long long nX, int ping_num, int range_sample_num, float noise_max_lin, float snr_lin,
-                          double* range_max_out, void* workspace, long long workspace_bytes, cudaStream_t s) {
+                          double* range_max_out, int sv_input, void* workspace, long long workspace_bytes, cudaStream_t s) {
   const bool noise = ping_num > 0;
   const int T = noise ? ping_num : 4;
   if (T > kMaxT || R % 4 != 0 || R > 4096 || R < 128 || C * nX >= (1LL << 31) || nR > 32000) return 0;
@@ -700,9 +703,10 @@ int epb_pipeline_fast_try(const float* x, const epb_row* rows, const int* xbin, 
   pr.R = (int)R, pr.nR = nR, pr.rs_num = range_sample_num, pr.closed_right = closed_right, pr.nslots = nslots;
   pr.noise_max_lin = noise_max_lin;
   pr.snr1 = 1.f + snr_lin;
+  pr.sv_input = sv_input;
   if (workspace_bytes < 256 + pr.ntiles * (long long)sizeof(TileInfo)) return 0;
   if (cudaMemsetAsync(irregular, 0, sizeof(int), s) != cudaSuccess) return 0;
-  prepare_kernel<<<(unsigned)((pr.ntiles + 127) / 128), 128, 0, s>>>(rows, xbin, P, nX, T, pr.nPt, pr.ntiles,
+  prepare_kernel<<<(unsigned)((pr.ntiles + 127) / 128), 128, 0, s>>>(rows, xbin, P, nX, T, pr.nPt, pr.ntiles, sv_input,
                                                                      const_cast<TileInfo*>(pr.tiles), irregular);
   int rc = -1;
 #define EPB_FAST(TT)                                                                                              \

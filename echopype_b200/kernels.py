@@ -174,11 +174,14 @@ def bin_reduce(Sv, range_var, xbin, r_edges, acc, C, P, R, nX, closed_right=Fals
     return acc
 
 
-def bin_reduce_law(Sv, rows, xbin, r_edges, acc, C, P, R, nX, closed_right=False, depth_off=None, depth_scale=None):
+def bin_reduce_law(Sv, rows, xbin, r_edges, acc, C, P, R, nX, closed_right=False, depth_off=None, depth_scale=None, fast=True):
+    """fast=False forces the warp-per-row kernel (no workspace -> no dispatch to the persistent kernel)."""
     nR = int(r_edges.numel()) - 1
+    nws = int(_lib.load().epb_pipeline_workspace_bytes(int(C), int(P), 0)) if fast else 0
+    ws = torch.empty(nws, dtype=torch.uint8, device=Sv.device) if fast else None
     _lib.call(
         "epb_bin_reduce_law", ptr(Sv), ptr(rows), ptr(depth_off), ptr(depth_scale), ptr(xbin), ptr(r_edges), nR,
-        int(closed_right), ptr(acc), C, P, R, nX, stream(),
+        int(closed_right), ptr(acc), C, P, R, nX, ptr(ws), nws, stream(),
     )
     return acc
 

@@ -171,7 +171,9 @@ int epb_bin_reduce(const float* Sv, const void* range_var, int range_is_f64, con
 int epb_bin_reduce_law(const float* Sv, const epb_row* rows, const double* depth_off /* [P] or NULL */,
                        const double* depth_scale /* [P] or NULL */, const int* xbin, const double* r_edges,
                        int nR, int closed_right, double* acc, epb_i64 C, epb_i64 P, epb_i64 R, epb_i64 nX,
-                       void* stream);
+                       void* workspace /* NULL or epb_pipeline_workspace_bytes(C, P, 0) bytes, 16-byte aligned: regular
+                       echo_range volumes then run on the persistent kernel of the fused pipeline */,
+                       epb_i64 workspace_bytes, void* stream);
 /* mean -> dB.  out: [C,nX,nR] float32.  skipna=0 reproduces func="mean".  Bins without members get
  * fill_value (then 10log10 like the reference).  h_out (NASC, optional): sum of heights per bin. */
 int epb_bin_finalize(const double* acc, float* out, double* h_out, epb_i64 ncell, int skipna,

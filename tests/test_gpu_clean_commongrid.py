@@ -217,3 +217,33 @@ def test_compute_NASC(ep):
     np.testing.assert_allclose(got["distance"].values, want["distance"], rtol=1e-9)
     assert got["NASC"].attrs["units"] == "m2 nmi-2"
     assert got.attrs["Conventions"] == "CF-1.7,ACDD-1.3"
+
+
+@pytest.mark.parametrize("shape,rb,tb,closed", [((3, 97, 1000), "20m", "20s", "left"), ((2, 150, 4096), "10m", "7s", "right"), ((2, 40, 516), "5m", "1min", "left")])
+def test_bin_reduce_law_fast_equals_general(ep, shape, rb, tb, closed):
+    """compute_MVBS on library-produced echo_range: the persistent kernel (Sv input) against the warp-per-row kernel on the raw
+    accumulators: counts identical, sums within float32 accumulation noise."""
+    import torch
+
+    from echopype_b200 import kernels, synth
+    from echopype_b200.commongrid.utils import assign_bins, ping_time_edges, range_edges
+
+    C, P, R = shape
+    ed = synth.make_ek60(C, P, R, seed=41, nan_tail=0.2)
+    ds = ep.calibrate.compute_Sv(ed)
+    rows = ds["echo_range"].law["rows"]
+    Sv_t = ds["Sv"].data
+    pt = ds["ping_time"].values
+    rmax = kernels.range_max(ed["Sonar/Beam_group1"]["backscatter_r"].data if False else None, rows, C, P, R)
+    r_edges = range_edges(rmax, float(rb[:-1]))
+    p_edges = ping_time_edges(pt, tb)
+    xb = torch.from_numpy(assign_bins(pt, p_edges, closed)).cuda()
+    et = torch.from_numpy(r_edges).cuda()
+    nX = len(p_edges) - 1
+    a = kernels.bin_reduce_law(Sv_t, rows, xb, et, kernels.new_acc(C, nX, len(r_edges) - 1), C, P, R, nX, closed_right=(closed == "right"), fast=True)
+    b = kernels.bin_reduce_law(Sv_t, rows, xb, et, kernels.new_acc(C, nX, len(r_edges) - 1), C, P, R, nX, closed_right=(closed == "right"), fast=False)
+    fa, fb = a.cpu().numpy(), b.cpu().numpy()
+    np.testing.assert_array_equal(fa[..., 1], fb[..., 1])
+    np.testing.assert_array_equal(fa[..., 2], fb[..., 2])
+    ok = fb[..., 1] > 0
+    np.testing.assert_allclose(fa[..., 0][ok], fb[..., 0][ok], rtol=2e-5)
