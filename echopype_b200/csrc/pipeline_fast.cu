@@ -56,7 +56,7 @@ struct TileInfo {  // 144 bytes; written per tile by prepare_kernel, fetched by 
   int nruns;
   int Ta;      // rows present in the tile
   int lawchg;  // the tile's range law differs from the previous tile's (or first tile of a channel)
-  int pad0;
+  int rcsame;  // every row of the tile has the same (c0, c1)
   long long row0;  // first (channel, ping) row of the tile
   long long pad1, pad2;
 };
@@ -84,7 +84,7 @@ __global__ void prepare_kernel(const epb_row* __restrict__ rows, const int* __re
   const epb_row* r0 = rows + c * P + p0;
   TileInfo ti;
   bool bad = false;
-  int nruns = 0, prev_xb = 0;
+  int nruns = 0, prev_xb = 0, rcsame = 1;
   for (int t = 0; t < kMaxT; ++t) {
     ti.rc[t] = make_float2(0.f, 0.f);
     ti.run_cell[t] = -1;
@@ -95,6 +95,7 @@ __global__ void prepare_kernel(const epb_row* __restrict__ rows, const int* __re
     if (!sv_input && !(r.c0 == r.c0 && r.c1 == r.c1)) bad = true;
     if (!same_law(r0[0], r)) bad = true;  // NaN laws never compare equal
     ti.rc[t] = sv_input ? make_float2(0.f, kDb2Log2) : make_float2(r.c0, r.c1);  // Sv input: e = 2^(Sv log2(10)/10)
+    if (!(ti.rc[t].x == ti.rc[0].x && ti.rc[t].y == ti.rc[0].y)) rcsame = 0;
     int xb = xbin[p0 + t];
     if (xb < 0 || xb >= nX) xb = -1;
     if (t == 0 || xb != prev_xb) {
@@ -107,7 +108,7 @@ __global__ void prepare_kernel(const epb_row* __restrict__ rows, const int* __re
   ti.nruns = nruns;
   ti.Ta = Ta;
   ti.lawchg = (itile == 0) || !same_law(r0[0], *(r0 - T));
-  ti.pad0 = 0;
+  ti.rcsame = rcsame;
   ti.row0 = c * P + p0;
   ti.pad1 = 0, ti.pad2 = 0;
   tiles[g] = ti;
@@ -216,6 +217,24 @@ struct Producer {  // TMA issue cursor, used by one thread only (kept in shared 
   int c, it;       // channel / ping tile of `tile`
 };
 
+// Range-only column terms of the u domain, computed once per range law with the accurate libm variants:
+//   lg = log2(h / TL) = 2 log2(R'/Rm) + c2 (R' - R),  TL = Rm^2 2^(c2 R)   (Rm = max(R, 1), clean/api.py:392-431)
+// Columns where Sv is undefined (n < n_start, R' < 0) get lg = -inf (u = 0) and TL = 0 (the "undefined" marker).
+struct ColT {
+  float lg, tl;
+};
+__device__ __forceinline__ ColT col_tables(const RowF& r, int n) {
+  const float nf = (float)n;
+  const float rp = tvg_range_of(r, nf);
+  const float rr = range_of(r, nf);
+  const float rm = (rr >= 1.f) ? rr : 1.f;
+  ColT c;
+  c.lg = fmaf(2.f, log2f(rp / rm), r.c2 * (rp - rr));
+  c.tl = (rm * rm) * exp2f(r.c2 * rr);
+  if (!(n >= r.n_start) || !(rp >= 0.f)) c.lg = -CUDART_INF_F, c.tl = 0.f;
+  return c;
+}
+
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -241,14 +260,16 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
   const bool prod_warp = (tid >> 5) == (nth >> 5) - 1;  // the last warp doubles as descriptor / TMA producer
   const int nRt = kNoise ? (R + pr.rs_num - 1) / pr.rs_num : 0;
   // ---- dynamic shared memory ----------------------------------------------------------------------------------------
-  // [h R][ginv R][colsum R][keys R int16][ctl R/4 uint16][pad to 16][ring NT x T x R][edges nR+1 f64][bounds nR+1]
+  // [lg R][tl R][ga R/4][gb R/4][keys R int16][ctl R/4 uint16][pad to 16][ring NT x T x R][edges nR+1 f64][bounds nR+1]
   // [valid nRt][def 2 nRt]
-  float* const s_h = reinterpret_cast<float*>(smem_raw);  // 10^(Sv/10) / e
-  float* const s_ginv = s_h + R;                          // 10^(TL/10) / h
-  float* const s_colsum = s_ginv + R;
-  short* const s_keys = reinterpret_cast<short*>(s_colsum + R);
+  float* const s_lg = reinterpret_cast<float*>(smem_raw);  // log2(h / TL): u = 2^(x c1 + c0 + lg) = 10^((Sv - TL)/10);
+                                                           // -inf where Sv is undefined (u = 0: never survives)
+  float* const s_tl = s_lg + R;                            // TL = 10^(TL_dB/10) >= 1;  0 where Sv is undefined
+  float* const s_ga = s_tl + R;                            // per column group: sum of u toward the range tile of its first
+  float* const s_gb = s_ga + (R >> 2);                     // column / toward the following range tile
+  short* const s_keys = reinterpret_cast<short*>(s_gb + (R >> 2));
   unsigned short* const s_ctl = reinterpret_cast<unsigned short*>(s_keys + R);  // per column group: see flush_ctl
-  float* const s_ring = reinterpret_cast<float*>(smem_raw + (((size_t)R * 14 + (size_t)R / 2 + 15) & ~(size_t)15));
+  float* const s_ring = reinterpret_cast<float*>(smem_raw + (((size_t)R * 12 + (size_t)R / 2 + 15) & ~(size_t)15));
   double* const s_edges = reinterpret_cast<double*>(s_ring + (size_t)NT * T * R);
   int* const s_bounds = reinterpret_cast<int*>(s_edges + (nR + 1));
   int* const s_valid = s_bounds + (nR + 1);  // columns of each range tile with a defined Sv (n >= n_start, R' >= 0)
@@ -304,6 +325,13 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
     const int n = 4 * tid + g * 4 * nth;
     liveg[g] = n < R;
     colg[g] = liveg[g] ? n : 0;
+  }
+  int bsplit[G];  // columns k < bsplit[g] of group g lie in the range tile of the group's first column
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const int rs = kNoise ? pr.rs_num : 4;
+    const int b = (colg[g] / rs + 1) * rs - colg[g];
+    bsplit[g] = b < 4 ? b : 4;
   }
   bool nanrange = false;
   // exact nanmax(echo_range): the thread that owns the last column watches the final sample of every row
@@ -375,17 +403,15 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
       nanrange = rf.nanrange && !pr.sv_input;
       if (is_last) range_last = pr.rows[row0].range_last;
       for (int n = 4 * tid; n < R; n += 4 * nth) {
-        float hh[4], gi[4];
+        float lg[4], tl[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const ColC cc = col_consts(rf, n + k);
-          hh[k] = cc.h;
-          gi[k] = __fdividef(cc.tl, cc.h);  // NaN where Sv is undefined; inf where R' = 0
-          if (!(cc.h == cc.h)) gi[k] = CUDART_NAN_F;
-          if (pr.sv_input) hh[k] = 1.f, gi[k] = 1.f;
+          const ColT ct = col_tables(rf, n + k);
+          lg[k] = pr.sv_input ? 0.f : ct.lg;
+          tl[k] = pr.sv_input ? 1.f : ct.tl;
         }
-        *reinterpret_cast<float4*>(s_h + n) = make_float4(hh[0], hh[1], hh[2], hh[3]);
-        *reinterpret_cast<float4*>(s_ginv + n) = make_float4(gi[0], gi[1], gi[2], gi[3]);
+        *reinterpret_cast<float4*>(s_lg + n) = make_float4(lg[0], lg[1], lg[2], lg[3]);
+        *reinterpret_cast<float4*>(s_tl + n) = make_float4(tl[0], tl[1], tl[2], tl[3]);
       }
       __syncthreads();
       for (int nb = 0; nb < R; nb += 4 * nth) {  // warp-uniform trip count: flush_ctl shuffles
@@ -403,29 +429,48 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
       for (int rt = tid; rt < nRt; rt += nth) {
         const int j0 = rt * pr.rs_num, j1 = (j0 + pr.rs_num < R) ? j0 + pr.rs_num : R;
         int nv = 0;
-        for (int j = j0; j < j1; ++j) {
-          const float gi = s_ginv[j];
-          nv += (gi == gi);
-        }
+        for (int j = j0; j < j1; ++j) nv += (s_tl[j] != 0.f);
         s_valid[rt] = nv;
       }
       // no barrier needed here: s_keys is thread-private, s_valid is read after barrier (A)
     }
 
-    // ---- e -> registers ----------------------------------------------------------------------------------------------
+    // ---- u = 10^((Sv - TL)/10) -> registers ---------------------------------------------------------------------------
     float e[G][T][4];
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-      const float2 rc = ti->rc[t];  // rows beyond Ta: stale constants and slot data, zeroed below
+    if (ti->rcsame) {  // the usual case: one (c0, c1) for the tile, the column term folds into the FFMA2 addend
+      const float2 rc = ti->rc[0];
+      const float2 c1p = make_float2(rc.y, rc.y);
 #pragma unroll
       for (int g = 0; g < G; ++g) {
-        const float4 v = *reinterpret_cast<const float4*>(tbase + t * R + colg[g]);
-        const float2 c0p = make_float2(rc.x, rc.x), c1p = make_float2(rc.y, rc.y);
-        const float2 a01 = ffma2(make_float2(v.x, v.y), c1p, c0p), a23 = ffma2(make_float2(v.z, v.w), c1p, c0p);  // FFMA2
-        e[g][t][0] = fast_exp2(a01.x);
-        e[g][t][1] = fast_exp2(a01.y);
-        e[g][t][2] = fast_exp2(a23.x);
-        e[g][t][3] = fast_exp2(a23.y);
+        const float4 l4 = *reinterpret_cast<const float4*>(s_lg + colg[g]);
+        const float2 b01 = make_float2(l4.x + rc.x, l4.y + rc.x), b23 = make_float2(l4.z + rc.x, l4.w + rc.x);
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const float4 v = *reinterpret_cast<const float4*>(tbase + t * R + colg[g]);
+          const float2 a01 = ffma2(make_float2(v.x, v.y), c1p, b01), a23 = ffma2(make_float2(v.z, v.w), c1p, b23);
+          e[g][t][0] = fast_exp2(a01.x);
+          e[g][t][1] = fast_exp2(a01.y);
+          e[g][t][2] = fast_exp2(a23.x);
+          e[g][t][3] = fast_exp2(a23.y);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const float4 l4 = *reinterpret_cast<const float4*>(s_lg + colg[g]);
+        const float2 l01 = make_float2(l4.x, l4.y), l23 = make_float2(l4.z, l4.w);
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const float2 rc = ti->rc[t];  // rows beyond Ta: stale constants and slot data, zeroed below
+          const float4 v = *reinterpret_cast<const float4*>(tbase + t * R + colg[g]);
+          const float2 c0p = make_float2(rc.x, rc.x), c1p = make_float2(rc.y, rc.y);
+          const float2 a01 = fadd2(ffma2(make_float2(v.x, v.y), c1p, c0p), l01);
+          const float2 a23 = fadd2(ffma2(make_float2(v.z, v.w), c1p, c0p), l23);
+          e[g][t][0] = fast_exp2(a01.x);
+          e[g][t][1] = fast_exp2(a01.y);
+          e[g][t][2] = fast_exp2(a23.x);
+          e[g][t][3] = fast_exp2(a23.y);
+        }
       }
     }
     if (Ta < T) {  // partial tile (end of a channel): the missing rows contribute nothing
@@ -475,10 +520,8 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
             }
             e[g][t][k] = ok ? v : -2.f;
           }
-          if (kNoise && missing && liveg[g]) {
-            const float gi = s_ginv[colg[g] + k];
-            if (gi == gi) atomicAdd(&s_def[it * nRt + (colg[g] + k) / pr.rs_num], missing);
-          }
+          if (kNoise && missing && liveg[g] && s_tl[colg[g] + k] != 0.f)
+            atomicAdd(&s_def[it * nRt + (colg[g] + k) / pr.rs_num], missing);
         }
     }
 
@@ -500,17 +543,15 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
 
     float noise_lin = 0.f;
     if (kNoise) {
-      // ---- phase 1: per-column sums of 10^((Sv-TL)/10) -> range-tile means -> min ----------------------------------------
+      // ---- phase 1: column sums of u -> column-group sums -> range-tile means -> min ---------------------------------
+      // a group of four columns touches at most two range tiles (range_sample_num >= 4): columns k < bsplit[g] belong
+      // to the tile of the first column (sum A), the rest to the next tile (sum B)
 #pragma unroll
       for (int g = 0; g < G; ++g) {
-        const float4 g4 = *reinterpret_cast<const float4*>(s_ginv + colg[g]);
-        // sum of 10^((Sv-TL)/10) = sum(e) h / TL; undefined Sv (ginv NaN) -> 0 through fmaxf; ginv = inf -> 0
-        float4 cs;
-        cs.x = fmaxf(se[g][0] * rcp_approx(g4.x), 0.f);
-        cs.y = fmaxf(se[g][1] * rcp_approx(g4.y), 0.f);
-        cs.z = fmaxf(se[g][2] * rcp_approx(g4.z), 0.f);
-        cs.w = fmaxf(se[g][3] * rcp_approx(g4.w), 0.f);
-        if (liveg[g]) *reinterpret_cast<float4*>(s_colsum + colg[g]) = cs;
+        const int b = bsplit[g];
+        const float A = se[g][0] + ((b > 1) ? se[g][1] : 0.f) + (((b > 2) ? se[g][2] : 0.f) + ((b > 3) ? se[g][3] : 0.f));
+        const float B = ((b > 1) ? 0.f : se[g][1]) + (((b > 2) ? 0.f : se[g][2]) + ((b > 3) ? 0.f : se[g][3]));
+        if (liveg[g]) s_ga[colg[g] >> 2] = A, s_gb[colg[g] >> 2] = B;
       }
       __syncthreads();  // (A) the tile's slot is free; column sums visible
       if (prod_warp && lane == 0) {
@@ -521,32 +562,27 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
       }
       const unsigned need_last = (unsigned)s_hasnan[it] >> 8;  // CTA-uniform, almost always 0
       if (need_last) offer_last(need_last, e);
-      // four lanes per range tile: lane q takes the column groups ga+q, ga+q+4, ... (one LDS.128 each, edges masked)
-      if ((tid & ~31) < 4 * nRt) {
-        const int q = tid & 3;
+      // two lanes per range tile: the groups whose first column lies in the tile (A sums, alternating between the
+      // lanes) plus the B sum of the group that straddles into it
+      if ((tid & ~31) < 2 * nRt) {
+        const int q = tid & 1;
         const bool hasnan = (s_hasnan[it] & 1) != 0;
         unsigned m = kInfBits;
-        for (int rt = tid >> 2; rt < ((nRt + 7) & ~7); rt += nth >> 2) {
+        for (int rt = tid >> 1; rt < ((nRt + 15) & ~15); rt += nth >> 1) {
           const bool in = rt < nRt;
           const int j0 = in ? rt * pr.rs_num : 0;
           const int j1 = in ? ((j0 + pr.rs_num < R) ? j0 + pr.rs_num : R) : 0;
-          const unsigned span = (unsigned)(j1 - j0);
-          float s = 0.f;
-          for (int gq = (j0 >> 2) + q; 4 * gq < j1; gq += 4) {
-            const float4 v = *reinterpret_cast<const float4*>(s_colsum + 4 * gq);
-            const unsigned o = (unsigned)(4 * gq - j0);  // column offset into the tile (wraps below zero before j0)
-            s += ((o < span) ? v.x : 0.f) + ((o + 1u < span) ? v.y : 0.f);
-            s += ((o + 2u < span) ? v.z : 0.f) + ((o + 3u < span) ? v.w : 0.f);
-          }
+          const int ga = (j0 + 3) >> 2, gb = (j1 + 3) >> 2;
+          float s = (q == 0 && ga > 0 && in) ? s_gb[ga - 1] : 0.f;
+          for (int gq = ga + q; gq < gb; gq += 2) s += s_ga[gq];
           s += __shfl_xor_sync(0xffffffffu, s, 1);
-          s += __shfl_xor_sync(0xffffffffu, s, 2);
           int def = 0;
           if (hasnan) {  // CTA-uniform
             if (in && q == 0) {
               def = s_def[it * nRt + rt];
               s_def[it * nRt + rt] = 0;
             }
-            def = __shfl_sync(0xffffffffu, def, lane & ~3);
+            def = __shfl_sync(0xffffffffu, def, lane & ~1);
           }
           if (in) {
             const int n = s_valid[rt] * Ta - def;
@@ -584,7 +620,9 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
     }
 
     // ---- phase 2: noise removal + accumulation into the register cells ------------------------------------------------
-    // survivors: e > ethr (the SNR test in the e domain);  sum(e h - nl) = h sum(e) - n nl
+    // survivors: u > thr (one tile-wide threshold);  sum(TL u - TL noise) = TL (sum(u) - n noise)
+    const float thr = kNoise ? noise_lin * pr.snr1 : -1.f;    // Sv_c - Sv_noise > SNR  <=>  u > noise (1 + 10^(SNR/10))
+    const float nz = (noise_lin == noise_lin) ? noise_lin : 0.f;  // NaN noise: nothing survives, keep the sums clean
     const int nruns = ti->nruns;
     int ta = 0;
     for (int r = 0; r < nruns; ++r) {
@@ -598,40 +636,31 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
         const bool whole = (tb - ta == T);
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-          const float4 h4 = *reinterpret_cast<const float4*>(s_h + colg[g]);
-          const float4 g4 = *reinterpret_cast<const float4*>(s_ginv + colg[g]);
-          const float h[4] = {h4.x, h4.y, h4.z, h4.w}, gi[4] = {g4.x, g4.y, g4.z, g4.w};
-          float ethr[4], nl[4];
+          const float4 t4 = *reinterpret_cast<const float4*>(s_tl + colg[g]);
+          const float tl[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (kNoise) {
-              const float ne = noise_lin * gi[k];  // noise TL / h: the noise floor in the e domain
-              ethr[k] = ne * pr.snr1;              // Sv_c - Sv_noise > SNR  <=>  e > ne (1 + 10^(SNR/10))
-              nl[k] = ne * h[k];                   // 10^(Sv_noise/10)
-            } else {
-              ethr[k] = (h[k] == h[k]) ? -1.f : CUDART_NAN_F;  // every non-NaN e of a column with defined Sv
-              nl[k] = 0.f;
-            }
-          }
-#pragma unroll
-          for (int k = 0; k < 4; k += 2) {  // column pairs: mask = (e > ethr) as 1.0 / 0.0, FSET x2 + FFMA2 + FADD2 per row
+          for (int k = 0; k < 4; k += 2) {  // column pairs: mask = (u > thr) as 1.0 / 0.0, FSET x2 + FFMA2 + FADD2 per row
             float2 sg = make_float2(0.f, 0.f), ng = make_float2(0.f, 0.f);
 #pragma unroll
             for (int t = 0; t < T; ++t) {
               float2 m;
-              if (whole) {  // every e finite (or the -2 sentinel)
-                m.x = (e[g][t][k] > ethr[k]) ? 1.f : 0.f;
-                m.y = (e[g][t][k + 1] > ethr[k + 1]) ? 1.f : 0.f;
+              if (whole) {  // every u finite (or the -2 sentinel)
+                m.x = (e[g][t][k] > thr) ? 1.f : 0.f;
+                m.y = (e[g][t][k + 1] > thr) ? 1.f : 0.f;
               } else {
-                m.x = (t >= ta && t < tb && e[g][t][k] > ethr[k]) ? 1.f : 0.f;
-                m.y = (t >= ta && t < tb && e[g][t][k + 1] > ethr[k + 1]) ? 1.f : 0.f;
+                m.x = (t >= ta && t < tb && e[g][t][k] > thr) ? 1.f : 0.f;
+                m.y = (t >= ta && t < tb && e[g][t][k + 1] > thr) ? 1.f : 0.f;
               }
               sg = ffma2(m, make_float2(e[g][t][k], e[g][t][k + 1]), sg);
               ng = fadd2(ng, m);
             }
-            const float c0 = fmaf(h[k], sg.x, -(ng.x * nl[k])), c1 = fmaf(h[k + 1], sg.y, -(ng.y * nl[k + 1]));
-            acc.s[g][k] += (ng.x > 0.f) ? c0 : 0.f;
-            acc.s[g][k + 1] += (ng.y > 0.f) ? c1 : 0.f;
+            if (!kNoise) {  // thr = -1 lets the u = 0 of an undefined column through: not a survivor
+              ng.x = (tl[k] != 0.f) ? ng.x : 0.f;
+              ng.y = (tl[k + 1] != 0.f) ? ng.y : 0.f;
+            }
+            // sum over the survivors of 10^(Sv_corrected/10) = TL (u - noise)
+            acc.s[g][k] = fmaf(tl[k], fmaf(-ng.x, nz, sg.x), acc.s[g][k]);
+            acc.s[g][k + 1] = fmaf(tl[k + 1], fmaf(-ng.y, nz, sg.y), acc.s[g][k + 1]);
             acc.good[g][k] += ng.x;
             acc.good[g][k + 1] += ng.y;
           }
@@ -651,7 +680,7 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
 }
 
 size_t fast_smem(long long R, int T, int nR, int ntiles_ring, int nRt) {
-  return (((size_t)R * 14 + (size_t)R / 2 + 15) & ~(size_t)15) + (size_t)ntiles_ring * T * R * 4 + (size_t)(nR + 1) * 12 + (size_t)nRt * 12 + 16;
+  return (((size_t)R * 12 + (size_t)R / 2 + 15) & ~(size_t)15) + (size_t)ntiles_ring * T * R * 4 + (size_t)(nR + 1) * 12 + (size_t)nRt * 12 + 16;
 }
 
 constexpr size_t kSmemMax = 227 * 1024 - 2048;  // static shared memory of the kernel comes on top
@@ -679,6 +708,7 @@ int epb_pipeline_fast_try(const float* x, const epb_row* rows, const int* xbin, 
   const bool noise = ping_num > 0;
   const int T = noise ? ping_num : 4;
   if (T > kMaxT || R % 4 != 0 || R > 4096 || R < 128 || C * nX >= (1LL << 31) || nR > 32000) return 0;
+  if (noise && range_sample_num < 4) return 0;  // a column group of four may touch at most two range tiles
   const int G = (R / 4 > 512) ? 2 : 1;  // column groups per thread
   const int threads = (int)(((R / 4 + G - 1) / G + 31) / 32 * 32);
   const int nRt = noise ? (int)((R + range_sample_num - 1) / range_sample_num) : 0;
