@@ -140,74 +140,11 @@ __device__ __forceinline__ void atomic_cell(double* cell, float s, int good, int
   if (bad) atomicAdd(cell + 2, (double)bad);
 }
 
-// Control word of one column group for the segmented warp reduction at flush time; it depends only on the keys,
-// so it is computed once per range law (flush_ctl) and parked in shared memory:
-//   bits 0-4  lane - 2^i belongs to the same run of equal keys (scan step i)
-//   bit  5    last lane of its run        bit 6  the four columns share one key
-//   bits 8-13 lanes in the run up to and including this one
-// Every lane of the warp must call flush_ctl; key = the group's common key, or -1.
-__device__ __forceinline__ unsigned flush_ctl(int kk, bool same) {
-  const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const int prev = __shfl_up_sync(full, kk, 1);
-  const unsigned heads = __ballot_sync(full, (lane == 0) || (prev != kk));
-  unsigned ctl = 0;
-#pragma unroll
-  for (int i = 0; i < 5; ++i) {
-    const int d = 1 << i;
-    const bool take = (lane >= d) && (((heads >> (lane - d + 1)) & ((1u << d) - 1u)) == 0u);
-    ctl |= take ? (1u << i) : 0u;
-  }
-  const bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u);
-  const int head_lane = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
-  ctl |= (tail ? 32u : 0u) | (same ? 64u : 0u) | ((unsigned)(lane - head_lane + 1) << 8);
-  return ctl;
-}
-
-// Reduce one group of per-thread accumulators of a warp (128 adjacent columns) over runs of equal range-bin keys
-// and add each run to the float64 accumulator grid; every lane of the warp must call this.  keys: the thread's
-// four range-bin indices (int16, -1 = outside every bin); ctl: see flush_ctl.
-__device__ __forceinline__ void flush_group(const float (&sv)[4], const float (&gv)[4], unsigned nanp, int rows,
-                                            const short* __restrict__ keys, unsigned ctl, bool live,
-                                            double* __restrict__ acc_row) {
-  const unsigned full = 0xffffffffu;
-  short4 k4 = make_short4(-1, -1, -1, -1);
-  if (live) k4 = *reinterpret_cast<const short4*>(keys);
-  int kk = -1;
-  float ms = 0.f, mg = 0.f;  // sum, survivors of the thread's four columns
-  if (ctl & 64u) {
-    kk = k4.x;
-    ms = (sv[0] + sv[1]) + (sv[2] + sv[3]);
-    mg = (gv[0] + gv[1]) + (gv[2] + gv[3]);
-  } else {  // a bin boundary inside the thread's four columns
-    const int key[4] = {k4.x, k4.y, k4.z, k4.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (key[k] >= 0) {
-        const int good = (int)gv[k];
-        atomic_cell(acc_row + 4 * (long long)key[k], sv[k], good, rows - (int)((nanp >> (8 * k)) & 0xffu) - good);
-      }
-  }
-  float md = 0.f;  // non-member rows (NaN echo_range) of the run: rare
-  const bool any_nan = __any_sync(full, nanp != 0u);
-  if (any_nan && (ctl & 64u)) md = (float)((nanp & 0xffu) + ((nanp >> 8) & 0xffu) + ((nanp >> 16) & 0xffu) + (nanp >> 24));
-#pragma unroll
-  for (int i = 0; i < 5; ++i) {
-    const float s2 = __shfl_up_sync(full, ms, 1 << i);
-    const float g2 = __shfl_up_sync(full, mg, 1 << i);
-    const bool take = (ctl >> i) & 1u;
-    ms += take ? s2 : 0.f;
-    mg += take ? g2 : 0.f;
-    if (any_nan) {
-      const float d2 = __shfl_up_sync(full, md, 1 << i);
-      md += take ? d2 : 0.f;
-    }
-  }
-  if ((ctl & 32u) && kk >= 0) {
-    const int members = rows * 4 * (int)((ctl >> 8) & 63u) - (int)md;
-    const int good = (int)mg;
-    atomic_cell(acc_row + 4 * (long long)kk, ms, good, members - good);
-  }
+// A + (columns k >= b), B = (columns k < b ? 0 : v): split of a group's four column values at position b (1..4)
+__device__ __forceinline__ float2 split_sum(const float (&v)[4], int b) {
+  const float A = v[0] + ((b > 1) ? v[1] : 0.f) + (((b > 2) ? v[2] : 0.f) + ((b > 3) ? v[3] : 0.f));
+  const float B = ((b > 1) ? 0.f : v[1]) + (((b > 2) ? 0.f : v[2]) + ((b > 3) ? 0.f : v[3]));
+  return make_float2(A, B);
 }
 
 struct Producer {  // TMA issue cursor, used by one thread only (kept in shared memory, not in registers)
@@ -252,6 +189,7 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
   __shared__ unsigned int s_min[2];
   __shared__ int s_hasnan[2];   // a thread saw a NaN sample in the tile: range-tile counts are corrected by s_def
   __shared__ Producer s_prod;
+  __shared__ int s_multi;  // the current law has a column group of four in more than two range bins
   __shared__ int s_last[kMaxT];  // last sample with a defined range of the rows whose final sample is NaN (rare)
   const int R = pr.R, nR = pr.nR, NT = pr.nslots;  // NT tile slots of T rows in the ring
   const int tid = threadIdx.x;
@@ -267,9 +205,13 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
   float* const s_tl = s_lg + R;                            // TL = 10^(TL_dB/10) >= 1;  0 where Sv is undefined
   float* const s_ga = s_tl + R;                            // per column group: sum of u toward the range tile of its first
   float* const s_gb = s_ga + (R >> 2);                     // column / toward the following range tile
-  short* const s_keys = reinterpret_cast<short*>(s_gb + (R >> 2));
-  unsigned short* const s_ctl = reinterpret_cast<unsigned short*>(s_keys + R);  // per column group: see flush_ctl
-  float* const s_ring = reinterpret_cast<float*>(smem_raw + (((size_t)R * 12 + (size_t)R / 2 + 15) & ~(size_t)15));
+  float2* const s_fs = reinterpret_cast<float2*>(s_ga);    // flush (aliases ga/gb): per column group, cell sums toward the
+                                                           // range bin of its first column (.x) / of its last column (.y)
+  uint2* const s_fc = reinterpret_cast<uint2*>(s_gb + (R >> 2));  // flush: survivor counts (.x) and non-member counts
+                                                                  // (.y), first-bin part | last-bin part << 16
+  unsigned char* const s_bsp = reinterpret_cast<unsigned char*>(s_fc + (R >> 2));  // leading columns of a group that
+                                                                                   // share the range bin of the first one
+  float* const s_ring = reinterpret_cast<float*>(smem_raw + (((size_t)R * 12 + (size_t)R / 4 + 15) & ~(size_t)15));
   double* const s_edges = reinterpret_cast<double*>(s_ring + (size_t)NT * T * R);
   int* const s_bounds = reinterpret_cast<int*>(s_edges + (nR + 1));
   int* const s_valid = s_bounds + (nR + 1);  // columns of each range tile with a defined Sv (n >= n_start, R' >= 0)
@@ -345,11 +287,80 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
   unsigned par = 0;
   int tsel = 0;      // li % (NT + 1): descriptor slot
 
+  // Add the register cell (per-column sums / survivor counts of acc.rows rows) to the accumulator grid.  Called by
+  // the whole CTA (the conditions are tile properties).  Column-group partial sums go through shared memory, eight
+  // lanes per range bin add the groups of the bin and one of them issues the float64 atomics: one triple per
+  // (CTA, range bin).  Laws with a group of four columns in more than two bins take per-column atomics instead.
   auto flush = [&]() {
     double* acc_row = pr.acc + (long long)cur_cell * nR * 4;
+    if (s_multi) {
 #pragma unroll
-    for (int g = 0; g < G; ++g)
-      flush_group(acc.s[g], acc.good[g], acc.nanm[g], acc.rows, s_keys + colg[g], s_ctl[(colg[g] >> 2)], liveg[g], acc_row);
+      for (int g = 0; g < G; ++g)
+        if (liveg[g]) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int key = key_of(s_bounds, nR, colg[g] + k);
+            if (key >= 0) {
+              const int good = (int)acc.good[g][k];
+              atomic_cell(acc_row + 4 * (long long)key, acc.s[g][k], good,
+                          acc.rows - (int)((acc.nanm[g] >> (8 * k)) & 0xffu) - good);
+            }
+          }
+        }
+      acc.clear();
+      __syncthreads();  // s_multi is rewritten at the next law change
+      return;
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int grp = colg[g] >> 2;
+      const int b = s_bsp[grp];
+      const float2 fs = split_sum(acc.s[g], b), fg = split_sum(acc.good[g], b);
+      unsigned nn = 0u;
+      if (acc.nanm[g] != 0u) {  // rare: samples that are no members of any bin (NaN echo_range)
+        const unsigned m = acc.nanm[g];
+        const unsigned lo = (b > 3) ? m : (m & ((1u << (8 * b)) - 1u)), hi = m ^ lo;
+        nn = ((lo & 0xffu) + ((lo >> 8) & 0xffu) + ((lo >> 16) & 0xffu) + (lo >> 24)) |
+             (((hi & 0xffu) + ((hi >> 8) & 0xffu) + ((hi >> 16) & 0xffu) + (hi >> 24)) << 16);
+      }
+      if (liveg[g]) {
+        s_fs[grp] = fs;
+        s_fc[grp] = make_uint2((unsigned)fg.x | ((unsigned)fg.y << 16), nn);
+      }
+    }
+    __syncthreads();
+    {
+      const int q = tid & 7;
+      const int rows = acc.rows;
+      for (int k = tid >> 3; k < ((nR + 3) & ~3); k += nth >> 3) {  // warp-uniform trip count
+        const bool in = k < nR;
+        const int c0 = in ? s_bounds[k] : 0, c1 = in ? s_bounds[k + 1] : 0;
+        const int ga = (c0 + 3) >> 2, gb = (c1 + 3) >> 2;
+        float sum = 0.f;
+        unsigned cg = 0u, cn = 0u;
+        if (q == 0 && (c0 & 3) && c1 > c0) {  // the group that straddles into the bin
+          sum = s_fs[ga - 1].y;
+          const uint2 c = s_fc[ga - 1];
+          cg = c.x >> 16, cn = c.y >> 16;
+        }
+        for (int gq = ga + q; gq < gb; gq += 8) {
+          sum += s_fs[gq].x;
+          const uint2 c = s_fc[gq];
+          cg += c.x & 0xffffu, cn += c.y & 0xffffu;
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          cg += __shfl_xor_sync(0xffffffffu, cg, o);
+          cn += __shfl_xor_sync(0xffffffffu, cn, o);
+        }
+        if (q == 0 && c1 > c0) {
+          const int members = rows * (c1 - c0) - (int)cn;
+          atomic_cell(acc_row + 4 * (long long)k, sum, (int)cg, members - (int)cg);
+        }
+      }
+    }
+    __syncthreads();  // s_fs aliases the column-group sums of the next tile's noise estimate
     acc.clear();
   };
 
@@ -395,7 +406,8 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
     if (ti->lawchg || li == 0) {
       if (cur_cell >= 0) flush();
       cur_cell = -1;
-      __syncthreads();  // every warp has used the old keys
+      if (tid == 0) s_multi = 0;
+      __syncthreads();  // every warp has used the old tables
       const long long row0 = ti->row0;
       const epb_row& lr = pr.rows[row0];
       for (int k = tid; k <= nR; k += nth) s_bounds[k] = first_at_or_above(lr, R, s_edges[k], pr.closed_right);
@@ -414,17 +426,14 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
         *reinterpret_cast<float4*>(s_tl + n) = make_float4(tl[0], tl[1], tl[2], tl[3]);
       }
       __syncthreads();
-      for (int nb = 0; nb < R; nb += 4 * nth) {  // warp-uniform trip count: flush_ctl shuffles
-        const int n = nb + 4 * tid;
-        short kk[4] = {-1, -1, -1, -1};
-        if (n < R) {
+      for (int n = 4 * tid; n < R; n += 4 * nth) {
+        int kk[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) kk[k] = (short)key_of(s_bounds, nR, n + k);
-          *reinterpret_cast<short4*>(s_keys + n) = make_short4(kk[0], kk[1], kk[2], kk[3]);
-        }
-        const bool same = (kk[0] == kk[1]) && (kk[1] == kk[2]) && (kk[2] == kk[3]);
-        const unsigned ctl = flush_ctl(same ? (int)kk[0] : -1, same);
-        if (n < R) s_ctl[n >> 2] = (unsigned short)ctl;
+        for (int k = 0; k < 4; ++k) kk[k] = key_of(s_bounds, nR, n + k);
+        const int b = (kk[1] != kk[0]) ? 1 : (kk[2] != kk[0]) ? 2 : (kk[3] != kk[0]) ? 3 : 4;
+        const int changes = (kk[1] != kk[0]) + (kk[2] != kk[1]) + (kk[3] != kk[2]);
+        s_bsp[n >> 2] = (unsigned char)b;
+        if (changes > 1) s_multi = 1;  // bins narrower than the group: per-column flush for this law
       }
       for (int rt = tid; rt < nRt; rt += nth) {
         const int j0 = rt * pr.rs_num, j1 = (j0 + pr.rs_num < R) ? j0 + pr.rs_num : R;
@@ -432,7 +441,7 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
         for (int j = j0; j < j1; ++j) nv += (s_tl[j] != 0.f);
         s_valid[rt] = nv;
       }
-      // no barrier needed here: s_keys is thread-private, s_valid is read after barrier (A)
+      // no barrier needed here: s_bsp is thread-private, s_valid / s_multi are read after barrier (A)
     }
 
     // ---- u = 10^((Sv - TL)/10) -> registers ---------------------------------------------------------------------------
@@ -680,7 +689,7 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
 }
 
 size_t fast_smem(long long R, int T, int nR, int ntiles_ring, int nRt) {
-  return (((size_t)R * 12 + (size_t)R / 2 + 15) & ~(size_t)15) + (size_t)ntiles_ring * T * R * 4 + (size_t)(nR + 1) * 12 + (size_t)nRt * 12 + 16;
+  return (((size_t)R * 12 + (size_t)R / 4 + 15) & ~(size_t)15) + (size_t)ntiles_ring * T * R * 4 + (size_t)(nR + 1) * 12 + (size_t)nRt * 12 + 16;
 }
 
 constexpr size_t kSmemMax = 227 * 1024 - 2048;  // static shared memory of the kernel comes on top

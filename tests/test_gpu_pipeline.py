@@ -214,6 +214,9 @@ FAST_CASES = [
     ("azfp", (4, 55, 2048), False, None, None, None, "10m", "10s", "left"),
     ("azfp", (2, 43, 512), False, 4, 16, None, "2m", "10s", "left"),
     ("ek80", (3, 37, 1024), False, 6, 40, None, "20m", "12s", "left"),      # GPT channel with the double TVG offset
+    ("ek60", (2, 83, 1024), False, 5, 30, None, "0.3m", "9s", "left"),      # bins narrower than a column group: per-column flush
+    ("ek60", (2, 83, 1024), False, 3, 4, None, "1m", "9s", "right"),        # smallest range tile of the fast path; 5-sample bins
+    ("ek60", (2, 300, 640), False, 5, 7, None, "50m", "10min", "left"),     # cells longer than the packed counters (flush by rows)
 ]
 
 
