@@ -6,7 +6,8 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_longlong, c_ubyte, c_uint, c_ulonglong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libepb200.so")
+# EPB200_LIB: developer knob for A/B builds of the same library (tools/ab_build.py); never a different backend
+LIB_PATH = os.environ.get("EPB200_LIB") or os.path.join(_HERE, "libepb200.so")
 
 
 class EpbError(RuntimeError):

@@ -44,6 +44,7 @@ struct FastParams {
   const TileInfo* tiles;  // [ntiles] descriptors from prepare_kernel (workspace)
   long long C, P, nX, ntiles;
   int R, nR, rs_num, closed_right, nslots, nPt;
+  int rt_lanes, rt_tpw, rt_recip;  // noise estimate: lanes per range tile, range tiles per warp, ceil(2^16 / lanes)
   float noise_max_lin;  // NaN: no cap
   float snr1;           // 1 + 10^(SNR/10)
   int sv_input;         // the input is Sv in dB (bin reduction of compute_MVBS): e = 10^(Sv/10), h = 1, NaN = NaN member
@@ -180,13 +181,16 @@ __device__ __forceinline__ float rcp_approx(float x) {
 __device__ __forceinline__ bool finite_f(float x) { return x * 0.f == 0.f; }
 
 // T rows per tile (ping_num), G column groups of four per thread (threads = R / (4 G))
+#ifndef EPB_G1_BLOCKS
+#define EPB_G1_BLOCKS 2  // resident CTAs per SM of the one-group variant (R <= 2048): 64 registers per thread
+#endif
 template <int T, int G, bool kNoise>
-__global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams pr) {
+__global__ void __launch_bounds__(512, G == 1 ? EPB_G1_BLOCKS : 1) pipeline_fast_kernel(const FastParams pr) {
   if (*pr.irregular) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long s_full[kMaxTilesInFlight];  // one mbarrier per tile slot
   __shared__ __align__(16) TileInfo s_tile[kMaxTilesInFlight + 1];  // NT + 1 in rotation: a descriptor outlives its ring slot
-  __shared__ unsigned int s_min[2];
+  __shared__ __align__(16) unsigned int s_wmin[16];  // per warp: minimum range-tile mean of the current tile (float bits)
   __shared__ int s_hasnan[2];   // a thread saw a NaN sample in the tile: range-tile counts are corrected by s_def
   __shared__ Producer s_prod;
   __shared__ int s_multi;  // the current law has a column group of four in more than two range bins
@@ -234,7 +238,7 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
       float* dst = s_ring + (size_t)p.ts * T * R;
       mbar_expect_tx(bar, row_bytes * (uint32_t)Ta + (uint32_t)sizeof(TileInfo));
       bulk_g2s(&s_tile[p.ds], pr.tiles + g0 + p.tile, (uint32_t)sizeof(TileInfo), bar);
-      for (int t = 0; t < Ta; ++t) bulk_g2s(dst + (size_t)t * R, src + (size_t)t * R, row_bytes, bar);
+      bulk_g2s(dst, src, row_bytes * (uint32_t)Ta, bar);  // the rows of a tile are contiguous on both sides
       ++p.tile;
       if (++p.ts == NT) p.ts = 0;
       if (++p.ds == NT + 1) p.ds = 0;
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
   if (tid == 0) {
     for (int i = 0; i < kMaxTilesInFlight; ++i) mbar_init(&s_full[i], 1);
     mbar_init_fence();
-    s_min[0] = kInfBits, s_min[1] = kInfBits;
+    for (int i = 0; i < 16; ++i) s_wmin[i] = kInfBits;
     s_hasnan[0] = 0, s_hasnan[1] = 0;
     for (int t = 0; t < kMaxT; ++t) s_last[t] = -1;
     const int c0 = (int)(g0 / nPt), it0 = (int)(g0 - (long long)c0 * nPt);
@@ -563,37 +567,46 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
         if (liveg[g]) s_ga[colg[g] >> 2] = A, s_gb[colg[g] >> 2] = B;
       }
       __syncthreads();  // (A) the tile's slot is free; column sums visible
-      if (prod_warp && lane == 0) {
+      if (prod_warp && lane == 0) {  // refill at once: a later issue (after (B)) measured slower, the lead time matters
         fence_proxy_async();
         issue_tiles(li);
-        s_min[it ^ 1] = kInfBits;
         s_hasnan[it ^ 1] = 0;
       }
       const unsigned need_last = (unsigned)s_hasnan[it] >> 8;  // CTA-uniform, almost always 0
       if (need_last) offer_last(need_last, e);
-      // two lanes per range tile: the groups whose first column lies in the tile (A sums, alternating between the
-      // lanes) plus the B sum of the group that straddles into it
-      if ((tid & ~31) < 2 * nRt) {
-        const int q = tid & 1;
+      // L lanes per range tile (L = pr.rt_lanes, 32 / L tiles per warp so that one pass over the warps covers the
+      // row): the A sums of the groups whose first column lies in the tile, interleaved over the lanes, plus the B sum
+      // of the group that straddles into it; per-warp minima are combined by every thread after barrier (B)
+      {
+        const int L = pr.rt_lanes, tpw = pr.rt_tpw;
+        const int slot = (lane * pr.rt_recip) >> 16;  // lane / L
+        const int q = lane - slot * L;
         const bool hasnan = (s_hasnan[it] & 1) != 0;
         unsigned m = kInfBits;
-        for (int rt = tid >> 1; rt < ((nRt + 15) & ~15); rt += nth >> 1) {
-          const bool in = rt < nRt;
+        for (int rb = (tid >> 5) * tpw; rb < nRt; rb += (nth >> 5) * tpw) {  // warp-uniform
+          const int rt = rb + slot;
+          const bool in = slot < tpw && rt < nRt;
           const int j0 = in ? rt * pr.rs_num : 0;
           const int j1 = in ? ((j0 + pr.rs_num < R) ? j0 + pr.rs_num : R) : 0;
           const int ga = (j0 + 3) >> 2, gb = (j1 + 3) >> 2;
           float s = (q == 0 && ga > 0 && in) ? s_gb[ga - 1] : 0.f;
-          for (int gq = ga + q; gq < gb; gq += 2) s += s_ga[gq];
-          s += __shfl_xor_sync(0xffffffffu, s, 1);
-          int def = 0;
-          if (hasnan) {  // CTA-uniform
-            if (in && q == 0) {
+          for (int gq = ga + q; gq < gb; gq += 3 * L) {  // three loads in flight
+            const float a0 = s_ga[gq];
+            const float a1 = (gq + L < gb) ? s_ga[gq + L] : 0.f;
+            const float a2 = (gq + 2 * L < gb) ? s_ga[gq + 2 * L] : 0.f;
+            s += (a0 + a1) + a2;
+          }
+#pragma unroll
+          for (int d = 1; d < 8; d <<= 1) {
+            const float o = __shfl_down_sync(0xffffffffu, s, d);
+            s += (q + d < L) ? o : 0.f;
+          }
+          if (in && q == 0) {
+            int def = 0;
+            if (hasnan) {  // CTA-uniform
               def = s_def[it * nRt + rt];
               s_def[it * nRt + rt] = 0;
             }
-            def = __shfl_sync(0xffffffffu, def, lane & ~1);
-          }
-          if (in) {
             const int n = s_valid[rt] * Ta - def;
             if (n > 0) {
               const unsigned u = __float_as_uint(s * rcp_approx((float)n));  // >= 0: uint order == float order
@@ -602,11 +615,14 @@ __global__ void __launch_bounds__(512, 1) pipeline_fast_kernel(const FastParams 
           }
         }
         m = __reduce_min_sync(0xffffffffu, m);
-        if (lane == 0 && m != kInfBits) atomicMin(&s_min[it], m);
+        if (lane == 0) s_wmin[tid >> 5] = m;
       }
       __syncthreads();  // (B)
       {
-        const unsigned u = s_min[it];
+        const uint4 w0 = *reinterpret_cast<const uint4*>(s_wmin), w1 = *reinterpret_cast<const uint4*>(s_wmin + 4);
+        const uint4 w2 = *reinterpret_cast<const uint4*>(s_wmin + 8), w3 = *reinterpret_cast<const uint4*>(s_wmin + 12);
+        const unsigned u = min(min(min(min(w0.x, w0.y), min(w0.z, w0.w)), min(min(w1.x, w1.y), min(w1.z, w1.w))),
+                               min(min(min(w2.x, w2.y), min(w2.z, w2.w)), min(min(w3.x, w3.y), min(w3.z, w3.w))));
         float v = (u == kInfBits) ? CUDART_NAN_F : __uint_as_float(u);
         if (pr.noise_max_lin == pr.noise_max_lin) v = (v < pr.noise_max_lin) ? v : pr.noise_max_lin;  // NaN -> max
         noise_lin = v;
@@ -722,9 +738,11 @@ int epb_pipeline_fast_try(const float* x, const epb_row* rows, const int* xbin, 
   const int threads = (int)(((R / 4 + G - 1) / G + 31) / 32 * 32);
   const int nRt = noise ? (int)((R + range_sample_num - 1) / range_sample_num) : 0;
   // ring: as many tile slots as fit (at least one, at most kMaxTilesInFlight; more than 4 buys nothing)
+  // one-group variant: leave room for EPB_G1_BLOCKS resident CTAs per SM (1 KB per CTA is reserved by the driver)
+  const size_t smem_cap = (G == 1 && EPB_G1_BLOCKS > 1) ? (size_t)(227 * 1024) / EPB_G1_BLOCKS - 3072 : kSmemMax;
   int nslots = 0;
   for (int n = 4; n >= 1; --n)
-    if (fast_smem(R, T, nR, n, nRt) <= kSmemMax) {
+    if (fast_smem(R, T, nR, n, nRt) <= smem_cap || (n == 1 && fast_smem(R, T, nR, n, nRt) <= kSmemMax)) {
       nslots = n;
       break;
     }
@@ -740,6 +758,14 @@ int epb_pipeline_fast_try(const float* x, const epb_row* rows, const int* xbin, 
   pr.nPt = (int)((P + T - 1) / T);
   pr.ntiles = C * (long long)pr.nPt;
   pr.R = (int)R, pr.nR = nR, pr.rs_num = range_sample_num, pr.closed_right = closed_right, pr.nslots = nslots;
+  pr.rt_lanes = 1;
+  for (int L : {8, 4, 3, 2})  // the most lanes per range tile with which one pass of the warps covers the row
+    if (noise && (long long)(32 / L) * (threads / 32) >= nRt && L <= (range_sample_num + 3) / 4 + 1) {
+      pr.rt_lanes = L;
+      break;
+    }
+  pr.rt_tpw = 32 / pr.rt_lanes;
+  pr.rt_recip = (65536 + pr.rt_lanes - 1) / pr.rt_lanes;
   pr.noise_max_lin = noise_max_lin;
   pr.snr1 = 1.f + snr_lin;
   pr.sv_input = sv_input;
