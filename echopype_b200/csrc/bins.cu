@@ -285,7 +285,7 @@ extern "C" int epb_bin_reduce(const float* Sv, const void* range_var, int range_
   return epb_check_launch("epb_bin_reduce");
 }
 
-int epb_pipeline_fast_try(const float* x, const epb_row* rows, const int* xbin, const double* r_edges, int nR,
+int epb_pipeline_fast_try(const void* x, int x_i16, const epb_row* rows, const int* xbin, const double* r_edges, int nR,
                           int closed_right, double* acc, float* noise_out, long long C, long long P, long long R,
                           long long nX, int ping_num, int range_sample_num, float noise_max_lin, float snr_lin,
                           double* range_max_out, int sv_input, void* workspace, long long workspace_bytes, cudaStream_t s);
@@ -302,7 +302,7 @@ extern "C" int epb_bin_reduce_law(const float* Sv, const epb_row* rows, const do
   // with Sv instead of power (pipeline_fast.cu, sv_input); decided on the device like in epb_pipeline_power_mvbs
   const int* gate = nullptr;
   if (workspace && workspace_bytes >= 256 && !depth_off && ((uintptr_t)workspace % 16) == 0 && ((uintptr_t)Sv % 16) == 0 &&
-      epb_pipeline_fast_try(Sv, rows, xbin, r_edges, nR, closed_right, acc, nullptr, C, P, R, nX, 0, 0, nanf(""), 0.f, nullptr, 1,
+      epb_pipeline_fast_try(Sv, 0, rows, xbin, r_edges, nR, closed_right, acc, nullptr, C, P, R, nX, 0, 0, nanf(""), 0.f, nullptr, 1,
                             workspace, workspace_bytes, (cudaStream_t)stream))
     gate = (const int*)workspace;
   const long long nrows = C * P;

@@ -27,6 +27,11 @@ namespace epb {
 
 constexpr float kLog2_10 = 3.321928094887362f;      // log2(10)
 constexpr float kDb2Log2 = 0.3321928094887362f;     // log2(10)/10 : 10^(x/10) = 2^(x*kDb2Log2)
+// INDEX2POWER = 10 log10(2) / 256 (convert/parse_base.py:24) as a float32 hi/lo pair: fmaf(count, hi, count * lo) is the
+// float32 nearest to the reference's float64 product count * INDEX2POWER for every int16 count (tests/test_ingest.py)
+constexpr float kIndex2PowerHi = 0.011758984066545963f;
+constexpr float kIndex2PowerLo = 1.3907830442860813e-10f;
+__device__ __forceinline__ float count_to_db_f(float q) { return fmaf(q, kIndex2PowerHi, __fmul_rn(q, kIndex2PowerLo)); }
 constexpr float kLog2ToDb = 3.0102999566398120f;    // 10*log10(2) : 10*log10(x) = log2(x)*kLog2ToDb
 
 __device__ __forceinline__ double cp_at(const epb_cp& a, long long c, long long p) {
@@ -146,6 +151,15 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
   asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
   float2 d;
   asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
   return d;

@@ -397,7 +397,7 @@ extern "C" epb_i64 epb_pipeline_smem_bytes(epb_i64 R, int nR, int tile, int do_n
   return (epb_i64)pipeline_smem(R, nR, tile, do_noise, staged);
 }
 
-int epb_pipeline_fast_try(const float* x, const epb_row* rows, const int* xbin, const double* r_edges, int nR,
+int epb_pipeline_fast_try(const void* x, int x_i16, const epb_row* rows, const int* xbin, const double* r_edges, int nR,
                           int closed_right, double* acc, float* noise_out, long long C, long long P, long long R,
                           long long nX, int ping_num, int range_sample_num, float noise_max_lin, float snr_lin,
                           double* range_max_out, int sv_input, void* workspace, long long workspace_bytes, cudaStream_t s);
@@ -405,18 +405,21 @@ void epb_range_max_init_launch(double* out_max, cudaStream_t s);
 void epb_range_max_gated_launch(const float* x, const epb_row* rows, long long nrows, int R, double* out_max, const int* gate,
                                 cudaStream_t s);
 long long epb_pipeline_fast_workspace(long long C, long long P, int ping_num);
+void epb_ingest_gated_launch(const short* counts, float* out, long long n, const int* gate, cudaStream_t s);
 
 extern "C" epb_i64 epb_pipeline_workspace_bytes(epb_i64 C, epb_i64 P, int ping_num) {
   if (C <= 0 || P <= 0 || ping_num < 0) return 256;
   return epb_pipeline_fast_workspace(C, P, ping_num);
 }
 
-extern "C" int epb_pipeline_power_mvbs(const float* backscatter_r, const epb_row* rows, const int* xbin,
-                                       const double* r_edges, int nR, int closed_right, double* acc, float* noise_out,
-                                       float* Sv, float* echo_range, float* Sv_noise, float* Sv_corrected, epb_i64 C,
-                                       epb_i64 P, epb_i64 R, epb_i64 nX, int ping_num, int range_sample_num,
-                                       float noise_max, float snr_threshold, double* range_max_out, void* workspace,
-                                       epb_i64 workspace_bytes, void* stream) {
+// counts: NULL, or the int16 raw power counts of which backscatter_r (then a scratch buffer) is the float32 image that
+// the ingest kernel writes only when the general kernel has to run.
+static int pipeline_power_mvbs_impl(const short* counts, float* backscatter_r, const epb_row* rows, const int* xbin,
+                                    const double* r_edges, int nR, int closed_right, double* acc, float* noise_out,
+                                    float* Sv, float* echo_range, float* Sv_noise, float* Sv_corrected, epb_i64 C,
+                                    epb_i64 P, epb_i64 R, epb_i64 nX, int ping_num, int range_sample_num,
+                                    float noise_max, float snr_threshold, double* range_max_out, void* workspace,
+                                    epb_i64 workspace_bytes, void* stream) {
   EPB_REQUIRE(backscatter_r && rows && xbin && r_edges && acc, "NULL pointer");
   EPB_REQUIRE(C > 0 && P > 0 && R > 0 && R < (1 << 24) && nX > 0, "bad shape");
   EPB_REQUIRE(R % 4 == 0, "fused pipeline needs range_sample % 4 == 0 (use the separate kernels otherwise)");
@@ -442,10 +445,11 @@ extern "C" int epb_pipeline_power_mvbs(const float* backscatter_r, const epb_row
   // classification kernel decides which of the two kernels does the work; the other returns immediately.
   if (workspace && workspace_bytes >= 256 && !Sv && !echo_range && !Sv_noise && !Sv_corrected &&
       ((uintptr_t)workspace % 16) == 0 &&
-      epb_pipeline_fast_try(backscatter_r, rows, xbin, r_edges, nR, closed_right, acc, noise_out, C, P, R, nX, ping_num,
+      epb_pipeline_fast_try(counts ? (const void*)counts : (const void*)backscatter_r, counts != nullptr, rows, xbin, r_edges, nR, closed_right, acc, noise_out, C, P, R, nX, ping_num,
                             range_sample_num, pr.noise_max_lin, (float)pow(10.0, (double)snr_threshold / 10.0),
                             range_max_out, 0, workspace, workspace_bytes, (cudaStream_t)stream))
     pr.gate = (const int*)workspace;
+  if (counts) epb_ingest_gated_launch(counts, backscatter_r, C * P * R, pr.gate, (cudaStream_t)stream);
   // stage the tile in shared memory when two CTAs per SM still fit, else when one fits, else stream from global
   pr.staged = 1;
   size_t smem = pipeline_smem(R, nR, pr.tile, pr.do_noise, 1);
@@ -466,4 +470,27 @@ extern "C" int epb_pipeline_power_mvbs(const float* backscatter_r, const epb_row
   // exact nanmax(echo_range): computed by the fast kernel when it runs, by the (gated) range kernel otherwise
   if (range_max_out) epb_range_max_gated_launch(backscatter_r, rows, C * P, (int)R, range_max_out, pr.gate, (cudaStream_t)stream);
   return epb_check_launch("epb_pipeline_power_mvbs");
+}
+
+extern "C" int epb_pipeline_power_mvbs(const float* backscatter_r, const epb_row* rows, const int* xbin,
+                                       const double* r_edges, int nR, int closed_right, double* acc, float* noise_out,
+                                       float* Sv, float* echo_range, float* Sv_noise, float* Sv_corrected, epb_i64 C,
+                                       epb_i64 P, epb_i64 R, epb_i64 nX, int ping_num, int range_sample_num,
+                                       float noise_max, float snr_threshold, double* range_max_out, void* workspace,
+                                       epb_i64 workspace_bytes, void* stream) {
+  return pipeline_power_mvbs_impl(nullptr, const_cast<float*>(backscatter_r), rows, xbin, r_edges, nR, closed_right, acc,
+                                  noise_out, Sv, echo_range, Sv_noise, Sv_corrected, C, P, R, nX, ping_num,
+                                  range_sample_num, noise_max, snr_threshold, range_max_out, workspace, workspace_bytes, stream);
+}
+
+extern "C" int epb_pipeline_power_mvbs_i16(const short* counts, float* scratch, const epb_row* rows, const int* xbin,
+                                           const double* r_edges, int nR, int closed_right, double* acc, float* noise_out,
+                                           epb_i64 C, epb_i64 P, epb_i64 R, epb_i64 nX, int ping_num, int range_sample_num,
+                                           float noise_max, float snr_threshold, double* range_max_out, void* workspace,
+                                           epb_i64 workspace_bytes, void* stream) {
+  EPB_REQUIRE(counts && scratch, "NULL pointer");
+  EPB_REQUIRE(((uintptr_t)counts % 16) == 0, "arrays must be 16-byte aligned");
+  return pipeline_power_mvbs_impl(counts, scratch, rows, xbin, r_edges, nR, closed_right, acc, noise_out, nullptr, nullptr,
+                                  nullptr, nullptr, C, P, R, nX, ping_num, range_sample_num, noise_max, snr_threshold,
+                                  range_max_out, workspace, workspace_bytes, stream);
 }

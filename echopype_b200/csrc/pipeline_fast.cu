@@ -33,7 +33,7 @@ constexpr unsigned kInfBits = 0x7f800000u;
 struct TileInfo;
 
 struct FastParams {
-  const float* x;
+  const void* x;  // float32 samples, or int16 raw power counts (kI16; -32768 marks padding)
   const epb_row* rows;
   const int* xbin;
   const double* edges;
@@ -184,7 +184,22 @@ __device__ __forceinline__ bool finite_f(float x) { return x * 0.f == 0.f; }
 #ifndef EPB_G1_BLOCKS
 #define EPB_G1_BLOCKS 2  // resident CTAs per SM of the one-group variant (R <= 2048): 64 registers per thread
 #endif
-template <int T, int G, bool kNoise>
+// raw power counts (int16) -> dB as float32, exactly as the ingest kernel / convert/parse_base.py:24,302 do it:
+// the float32 nearest to count * 10 log10(2) / 256 (count_to_db_f).  The 16-bit payloads are spliced into the mantissa of 2^23 (PRMT), so the
+// conversion runs on the integer / FMA pipes and leaves the MUFU (where I2F lives) to the ex2 of phase 0.
+__device__ __forceinline__ float4 counts_to_db(uint2 w) {
+  const unsigned a = w.x ^ 0x80008000u, b = w.y ^ 0x80008000u;  // offset binary: payload = count + 32768
+  const float kMagic = 8388608.f + 32768.f;
+  float2 f01 = make_float2(__uint_as_float(__byte_perm(a, 0x4B000000u, 0x7610)), __uint_as_float(__byte_perm(a, 0x4B000000u, 0x7632)));
+  float2 f23 = make_float2(__uint_as_float(__byte_perm(b, 0x4B000000u, 0x7610)), __uint_as_float(__byte_perm(b, 0x4B000000u, 0x7632)));
+  const float2 mm = make_float2(-kMagic, -kMagic), hi = make_float2(kIndex2PowerHi, kIndex2PowerHi), lo = make_float2(kIndex2PowerLo, kIndex2PowerLo);
+  f01 = fadd2(f01, mm), f23 = fadd2(f23, mm);
+  f01 = ffma2(f01, hi, fmul2(f01, lo));  // count_to_db_f on pairs
+  f23 = ffma2(f23, hi, fmul2(f23, lo));
+  return make_float4(f01.x, f01.y, f23.x, f23.y);
+}
+
+template <int T, int G, bool kNoise, bool kI16>
 __global__ void __launch_bounds__(512, G == 1 ? EPB_G1_BLOCKS : 1) pipeline_fast_kernel(const FastParams pr) {
   if (*pr.irregular) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -215,8 +230,9 @@ __global__ void __launch_bounds__(512, G == 1 ? EPB_G1_BLOCKS : 1) pipeline_fast
                                                                   // (.y), first-bin part | last-bin part << 16
   unsigned char* const s_bsp = reinterpret_cast<unsigned char*>(s_fc + (R >> 2));  // leading columns of a group that
                                                                                    // share the range bin of the first one
-  float* const s_ring = reinterpret_cast<float*>(smem_raw + (((size_t)R * 12 + (size_t)R / 4 + 15) & ~(size_t)15));
-  double* const s_edges = reinterpret_cast<double*>(s_ring + (size_t)NT * T * R);
+  constexpr int kXB = kI16 ? 2 : 4;  // bytes per input sample
+  unsigned char* const s_ring = smem_raw + (((size_t)R * 12 + (size_t)R / 4 + 15) & ~(size_t)15);
+  double* const s_edges = reinterpret_cast<double*>(s_ring + (((size_t)NT * T * R * kXB + 15) & ~(size_t)15));
   int* const s_bounds = reinterpret_cast<int*>(s_edges + (nR + 1));
   int* const s_valid = s_bounds + (nR + 1);  // columns of each range tile with a defined Sv (n >= n_start, R' >= 0)
   int* const s_def = s_valid + nRt;          // [2][nRt] samples missing (NaN) from each range tile, by tile parity
@@ -226,16 +242,16 @@ __global__ void __launch_bounds__(512, G == 1 ? EPB_G1_BLOCKS : 1) pipeline_fast
   const int ntl = (int)(pr.ntiles * (long long)(blockIdx.x + 1) / gridDim.x - g0);  // local tiles 0..ntl-1
   if (ntl <= 0) return;
   const int nPt = pr.nPt;
-  const uint32_t row_bytes = (uint32_t)R * 4u;
+  const uint32_t row_bytes = (uint32_t)R * (uint32_t)kXB;
   // one thread: issue every tile whose slot is free (the tile NT before it has been consumed)
   auto issue_tiles = [&](int last_done) {
     Producer p = s_prod;
     while (p.tile < ntl && p.tile - NT <= last_done) {
       const long long p0 = (long long)p.it * T;
       const int Ta = (int)((p0 + T <= pr.P) ? T : (pr.P - p0));
-      const float* src = pr.x + ((long long)p.c * pr.P + p0) * (long long)R;
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(pr.x) + ((long long)p.c * pr.P + p0) * (long long)row_bytes;
       unsigned long long* bar = &s_full[p.ts];
-      float* dst = s_ring + (size_t)p.ts * T * R;
+      unsigned char* dst = s_ring + (size_t)p.ts * T * row_bytes;
       mbar_expect_tx(bar, row_bytes * (uint32_t)Ta + (uint32_t)sizeof(TileInfo));
       bulk_g2s(&s_tile[p.ds], pr.tiles + g0 + p.tile, (uint32_t)sizeof(TileInfo), bar);
       bulk_g2s(dst, src, row_bytes * (uint32_t)Ta, bar);  // the rows of a tile are contiguous on both sides
@@ -400,7 +416,14 @@ __global__ void __launch_bounds__(512, G == 1 ? EPB_G1_BLOCKS : 1) pipeline_fast
     const int it = li & 1;
     // ---- wait for the tile (rows + descriptor) ---------------------------------------------------------------------
     mbar_wait(&s_full[ts], par);
-    const float* tbase = s_ring + (size_t)ts * T * R;
+    const unsigned char* tbase = s_ring + (size_t)ts * T * row_bytes;
+    unsigned mn16 = 0x7fff7fffu;  // kI16: packed minimum of the thread's counts (finds the padding marker)
+    auto ld4 = [&](int t, int g) -> float4 {
+      if (!kI16) return *reinterpret_cast<const float4*>(tbase + ((size_t)t * R + colg[g]) * 4);
+      const uint2 w = *reinterpret_cast<const uint2*>(tbase + ((size_t)t * R + colg[g]) * 2);
+      mn16 = __vimin3_s16x2(mn16, w.x, w.y);  // VIMNMX3.S16x2
+      return counts_to_db(w);
+    };
     if (++ts == NT) ts = 0, par ^= 1u;
     const TileInfo* ti = &s_tile[tsel];
     if (++tsel == NT + 1) tsel = 0;
@@ -459,7 +482,7 @@ __global__ void __launch_bounds__(512, G == 1 ? EPB_G1_BLOCKS : 1) pipeline_fast
         const float2 b01 = make_float2(l4.x + rc.x, l4.y + rc.x), b23 = make_float2(l4.z + rc.x, l4.w + rc.x);
 #pragma unroll
         for (int t = 0; t < T; ++t) {
-          const float4 v = *reinterpret_cast<const float4*>(tbase + t * R + colg[g]);
+          const float4 v = ld4(t, g);
           const float2 a01 = ffma2(make_float2(v.x, v.y), c1p, b01), a23 = ffma2(make_float2(v.z, v.w), c1p, b23);
           e[g][t][0] = fast_exp2(a01.x);
           e[g][t][1] = fast_exp2(a01.y);
@@ -475,7 +498,7 @@ __global__ void __launch_bounds__(512, G == 1 ? EPB_G1_BLOCKS : 1) pipeline_fast
 #pragma unroll
         for (int t = 0; t < T; ++t) {
           const float2 rc = ti->rc[t];  // rows beyond Ta: stale constants and slot data, zeroed below
-          const float4 v = *reinterpret_cast<const float4*>(tbase + t * R + colg[g]);
+          const float4 v = ld4(t, g);
           const float2 c0p = make_float2(rc.x, rc.x), c1p = make_float2(rc.y, rc.y);
           const float2 a01 = fadd2(ffma2(make_float2(v.x, v.y), c1p, c0p), l01);
           const float2 a23 = fadd2(ffma2(make_float2(v.z, v.w), c1p, c0p), l23);
@@ -514,6 +537,19 @@ __global__ void __launch_bounds__(512, G == 1 ? EPB_G1_BLOCKS : 1) pipeline_fast
     unsigned nanmask[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) nanmask[g] = 0u;
+    if (kI16 && ((mn16 & 0xffffu) == 0x8000u || (mn16 >> 16) == 0x8000u)) {  // padding marker seen: those samples are NaN
+#pragma unroll
+      for (int t = 0; t < T; ++t)
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const uint2 w = *reinterpret_cast<const uint2*>(tbase + ((size_t)t * R + colg[g]) * 2);
+          if ((w.x & 0xffffu) == 0x8000u) e[g][t][0] = CUDART_NAN_F;
+          if ((w.x >> 16) == 0x8000u) e[g][t][1] = CUDART_NAN_F;
+          if ((w.y & 0xffffu) == 0x8000u) e[g][t][2] = CUDART_NAN_F;
+          if ((w.y >> 16) == 0x8000u) e[g][t][3] = CUDART_NAN_F;
+        }
+      chk = CUDART_NAN_F;
+    }
     if (!finite_f(chk)) {
       if (kNoise) atomicOr(&s_hasnan[it], 1);
 #pragma unroll
@@ -704,15 +740,16 @@ __global__ void __launch_bounds__(512, G == 1 ? EPB_G1_BLOCKS : 1) pipeline_fast
   if (is_last && rmax_local != -CUDART_INF) atomic_max_d(pr.rmax, rmax_local);
 }
 
-size_t fast_smem(long long R, int T, int nR, int ntiles_ring, int nRt) {
-  return (((size_t)R * 12 + (size_t)R / 4 + 15) & ~(size_t)15) + (size_t)ntiles_ring * T * R * 4 + (size_t)(nR + 1) * 12 + (size_t)nRt * 12 + 16;
+size_t fast_smem(long long R, int T, int nR, int ntiles_ring, int nRt, int xbytes) {
+  return (((size_t)R * 12 + (size_t)R / 4 + 15) & ~(size_t)15) + (((size_t)ntiles_ring * T * R * xbytes + 15) & ~(size_t)15) +
+         (size_t)(nR + 1) * 12 + (size_t)nRt * 12 + 16;
 }
 
 constexpr size_t kSmemMax = 227 * 1024 - 2048;  // static shared memory of the kernel comes on top
 
-template <int T, int G, bool kNoise>
+template <int T, int G, bool kNoise, bool kI16>
 int launch_fast(const FastParams& pr, int threads, size_t smem, cudaStream_t s) {
-  auto kern = pipeline_fast_kernel<T, G, kNoise>;
+  auto kern = pipeline_fast_kernel<T, G, kNoise, kI16>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) return -1;
@@ -726,13 +763,16 @@ int launch_fast(const FastParams& pr, int threads, size_t smem, cudaStream_t s) 
 
 // Tries to launch the fast path.  Returns 1 when launched (the general kernel must then be launched with the same
 // `irregular` flag so that exactly one of the two does the work), 0 when the static conditions do not hold.
-int epb_pipeline_fast_try(const float* x, const epb_row* rows, const int* xbin, const double* r_edges, int nR,
+// x_i16: x holds int16 raw power counts (-32768 = padding) instead of float32 dB samples.
+int epb_pipeline_fast_try(const void* x, int x_i16, const epb_row* rows, const int* xbin, const double* r_edges, int nR,
                           int closed_right, double* acc, float* noise_out, long long C, long long P, long long R,
                           long long nX, int ping_num, int range_sample_num, float noise_max_lin, float snr_lin,
                           double* range_max_out, int sv_input, void* workspace, long long workspace_bytes, cudaStream_t s) {
   const bool noise = ping_num > 0;
   const int T = noise ? ping_num : 4;
   if (T > kMaxT || R % 4 != 0 || R > 4096 || R < 128 || C * nX >= (1LL << 31) || nR > 32000) return 0;
+  if (x_i16 && (R % 8 != 0 || sv_input)) return 0;  // 16-byte rows for the bulk copies
+  const int xb = x_i16 ? 2 : 4;
   if (noise && range_sample_num < 4) return 0;  // a column group of four may touch at most two range tiles
   const int G = (R / 4 > 512) ? 2 : 1;  // column groups per thread
   const int threads = (int)(((R / 4 + G - 1) / G + 31) / 32 * 32);
@@ -742,12 +782,12 @@ int epb_pipeline_fast_try(const float* x, const epb_row* rows, const int* xbin, 
   const size_t smem_cap = (G == 1 && EPB_G1_BLOCKS > 1) ? (size_t)(227 * 1024) / EPB_G1_BLOCKS - 3072 : kSmemMax;
   int nslots = 0;
   for (int n = 4; n >= 1; --n)
-    if (fast_smem(R, T, nR, n, nRt) <= smem_cap || (n == 1 && fast_smem(R, T, nR, n, nRt) <= kSmemMax)) {
+    if (fast_smem(R, T, nR, n, nRt, xb) <= smem_cap || (n == 1 && fast_smem(R, T, nR, n, nRt, xb) <= kSmemMax)) {
       nslots = n;
       break;
     }
   if (nslots == 0) return 0;
-  const size_t smem = fast_smem(R, T, nR, nslots, nRt);
+  const size_t smem = fast_smem(R, T, nR, nslots, nRt, xb);
   FastParams pr;
   pr.x = x, pr.rows = rows, pr.xbin = xbin, pr.edges = r_edges, pr.acc = acc, pr.noise_out = noise_out;
   pr.rmax = range_max_out;
@@ -774,12 +814,13 @@ int epb_pipeline_fast_try(const float* x, const epb_row* rows, const int* xbin, 
   prepare_kernel<<<(unsigned)((pr.ntiles + 127) / 128), 128, 0, s>>>(rows, xbin, P, nX, T, pr.nPt, pr.ntiles, sv_input,
                                                                      const_cast<TileInfo*>(pr.tiles), irregular);
   int rc = -1;
-#define EPB_FAST(TT)                                                                                              \
-  case TT:                                                                                                        \
-    rc = (G == 2) ? launch_fast<TT, 2, true>(pr, threads, smem, s) : launch_fast<TT, 1, true>(pr, threads, smem, s); \
+#define EPB_FAST_G(TT, NZ, I16) ((G == 2) ? launch_fast<TT, 2, NZ, I16>(pr, threads, smem, s) : launch_fast<TT, 1, NZ, I16>(pr, threads, smem, s))
+#define EPB_FAST(TT)                                                            \
+  case TT:                                                                      \
+    rc = x_i16 ? EPB_FAST_G(TT, true, true) : EPB_FAST_G(TT, true, false);      \
     break;
   if (!noise)
-    rc = (G == 2) ? launch_fast<4, 2, false>(pr, threads, smem, s) : launch_fast<4, 1, false>(pr, threads, smem, s);
+    rc = x_i16 ? EPB_FAST_G(4, false, true) : EPB_FAST_G(4, false, false);
   else
     switch (T) {
       EPB_FAST(1)
@@ -791,6 +832,7 @@ int epb_pipeline_fast_try(const float* x, const epb_row* rows, const int* xbin, 
       EPB_FAST(7)
       EPB_FAST(8)
     }
+#undef EPB_FAST_G
 #undef EPB_FAST
   if (rc != 0) cudaMemsetAsync(irregular, 1, sizeof(int), s);  // could not launch: the general kernel does the work
   return 1;

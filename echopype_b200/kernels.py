@@ -272,6 +272,55 @@ def pipeline_power_mvbs(x, rows, xbin, r_edges, acc, C, P, R, nX, ping_num, rang
     return acc
 
 
+def pipeline_power_mvbs_i16(counts, scratch, rows, xbin, r_edges, acc, C, P, R, nX, ping_num, range_sample_num,
+                            noise_max=None, snr=3.0, closed_right=False, noise_out=None, rmax_out=None):
+    """Fused pipeline on int16 raw power counts (-32768 = padding); scratch: float32 buffer of C*P*R elements."""
+    nm = float("nan") if noise_max is None else float(noise_max)
+    nR = int(r_edges.numel()) - 1
+    nws = int(_lib.load().epb_pipeline_workspace_bytes(int(C), int(P), int(ping_num)))
+    ws = torch.empty(nws, dtype=torch.uint8, device=counts.device)
+    assert counts.dtype == torch.int16 and scratch.dtype == torch.float32 and scratch.numel() >= C * P * R
+    _lib.call(
+        "epb_pipeline_power_mvbs_i16", ptr(counts), ptr(scratch), ptr(rows), ptr(xbin), ptr(r_edges), nR, int(closed_right),
+        ptr(acc), ptr(noise_out), C, P, R, nX, int(ping_num), int(range_sample_num), ctypes.c_float(nm),
+        ctypes.c_float(float(snr)), ptr(rmax_out), ptr(ws), nws, stream(),
+    )
+    return acc
+
+
+def ingest_power_i16(counts, out=None):
+    """int16 raw power counts -> float32 backscatter_r (dB), -32768 -> NaN (convert/parse_base.py:24,302,686-730)."""
+    assert counts.dtype == torch.int16 and counts.is_cuda and counts.is_contiguous()
+    out = out if out is not None else torch.empty(counts.shape, dtype=torch.float32, device=counts.device)
+    _lib.call("epb_ingest_power_i16", ptr(counts), ptr(out), int(counts.numel()), stream())
+    return out
+
+
+def is_raw_counts(x):
+    """True for int16 raw power counts (the ingest format: -32768 = padding), host array or tensor."""
+    return getattr(x, "dtype", None) in (torch.int16, np.dtype("int16"))
+
+
+def power_to_device_f32(x):
+    """Power samples -> float32 CUDA tensor.  int16 raw counts cross PCIe as they are (2 bytes per sample) and are
+    converted on the device (epb_ingest_power_i16); float data goes through :func:`device.to_device_f32`."""
+    from .device import to_device_f32
+
+    data = getattr(x, "data", x)
+    if not is_raw_counts(data):
+        return to_device_f32(data)
+    t = data if isinstance(data, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(data))
+    return ingest_power_i16(t.to(require_cuda(), non_blocking=True).contiguous())
+
+
+def synth_fill_i16(shape_cpr, seed, ping_offset=0, nan_tail=0.005, device=None):
+    C, P, R = (int(s) for s in shape_cpr)
+    out = torch.empty((C, P, R), dtype=torch.int16, device=device or require_cuda())
+    _lib.call("epb_synth_fill_i16", ptr(out), C, P, R, ctypes.c_ulonglong(int(seed)), int(ping_offset),
+              ctypes.c_uint(int(round(nan_tail * 65536))), stream())
+    return out
+
+
 def synth_fill(shape_cpr, kind, seed, inner=1, ping_offset=0, nan_tail=0.005, scale=1.0, device=None, out=None):
     C, P, R = (int(s) for s in shape_cpr)
     dev = device or require_cuda()

@@ -190,6 +190,7 @@ class FusedPlan:
         self.xbin = torch.from_numpy(np.where(xb >= 0, xb - self.x_lo, -1).astype(np.int32)).to(self.dev)
         self.chunk_pings = max(1, int(chunk_pings))
         self._ring = None
+        self._scratch = None  # float32 image of an int16 volume / slab, written only when the general kernel runs
         self._streams = None
         self.launches = 0  # kernels of libepb200 launched by run() so far (bench.py "gpu_launches")
         self.record_events = False  # bench.py: CUDA events around every fused-kernel launch -> kernel_events
@@ -233,6 +234,10 @@ class FusedPlan:
         rows = self.row_builder.build()
         self.launches += 1
         self.rows = rows
+        raw = kernels.is_raw_counts(x)  # int16 raw power counts (ingest format, -32768 = padding)
+        if raw and (self.keep or not self.fast):  # full-size outputs / forced general kernel: float image first
+            x, raw = kernels.power_to_device_f32(x), False
+            self.launches += 1
         on_device = isinstance(x, torch.Tensor) and x.is_cuda
         outs = {k: (empty((C, P, R), device=self.dev) if k in self.keep else None) for k in _KEEP}
         noise = empty((C, -(-P // self.ping_num)), device=self.dev) if self.do_noise else None
@@ -248,12 +253,21 @@ class FusedPlan:
             if self.record_events:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 ev[0].record()
-            kernels.pipeline_power_mvbs(
-                x, rows, self.xbin, edges_t, acc, C, P, R, nX, self.ping_num, self.range_sample_num,
-                noise_max=self.noise_max, snr=self.snr, closed_right=(self.closed == "right"), noise_out=noise,
-                fast=self.fast, Sv=outs["Sv"], echo_range=outs["echo_range"], Sv_noise=outs["Sv_noise"], Sv_corrected=outs["Sv_corrected"],
-                rmax_out=rmax,
-            )
+            if raw:
+                if self._scratch is None or self._scratch.numel() < C * P * R:
+                    self._scratch = torch.empty(C * P * R, dtype=torch.float32, device=self.dev)
+                kernels.pipeline_power_mvbs_i16(
+                    x, self._scratch, rows, self.xbin, edges_t, acc, C, P, R, nX, self.ping_num, self.range_sample_num,
+                    noise_max=self.noise_max, snr=self.snr, closed_right=(self.closed == "right"), noise_out=noise, rmax_out=rmax,
+                )
+                self.launches += 1  # the (gated) ingest kernel
+            else:
+                kernels.pipeline_power_mvbs(
+                    x, rows, self.xbin, edges_t, acc, C, P, R, nX, self.ping_num, self.range_sample_num,
+                    noise_max=self.noise_max, snr=self.snr, closed_right=(self.closed == "right"), noise_out=noise,
+                    fast=self.fast, Sv=outs["Sv"], echo_range=outs["echo_range"], Sv_noise=outs["Sv_noise"], Sv_corrected=outs["Sv_corrected"],
+                    rmax_out=rmax,
+                )
             if self.record_events:
                 ev[1].record()
                 self.kernel_events.append(ev)
@@ -276,14 +290,19 @@ class FusedPlan:
         while the fused kernel runs on the previous slab and accumulates into the same grid.  Returns the device
         tensor of per-slab exact range maxima (or None with ``range_var_max``)."""
         C, P, R = self.C, self.P, self.R
-        xh = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float32)))
-        if xh.dtype != torch.float32:
-            xh = xh.float()
+        raw = kernels.is_raw_counts(x)
+        if raw:
+            xh = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+        else:
+            xh = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float32)))
+            if xh.dtype != torch.float32:
+                xh = xh.float()
         xh = xh.contiguous()
         pn = self.ping_num if self.do_noise else 1
         chunk = min(P, max(pn, (self.chunk_pings // pn) * pn))
-        if self._ring is None or self._ring[0].numel() < chunk * R:
-            self._ring = [torch.empty(chunk * R, dtype=torch.float32, device=self.dev) for _ in range(3)]
+        if self._ring is None or self._ring[0].numel() < chunk * R or self._ring[0].dtype != xh.dtype:
+            self._ring = [torch.empty(chunk * R, dtype=xh.dtype, device=self.dev) for _ in range(3)]
+            self._scratch = torch.empty(chunk * R, dtype=torch.float32, device=self.dev) if raw else None
             self._streams = (torch.cuda.Stream(device=self.dev), [torch.cuda.Event() for _ in range(3)],
                              [torch.cuda.Event() for _ in range(3)])
         copy_s, filled, freed = self._streams
@@ -307,14 +326,22 @@ class FusedPlan:
                 main.wait_event(filled[slot])
                 rsub = rows_b[c * P + p0 : c * P + p0 + pc]
                 sub = lambda t: None if t is None else t[c, p0 : p0 + pc]  # noqa: E731
-                kernels.pipeline_power_mvbs(
-                    buf, rsub, self.xbin[p0 : p0 + pc], edges_t, acc[c : c + 1], 1, pc, R, nX, self.ping_num,
-                    self.range_sample_num, noise_max=self.noise_max, snr=self.snr, closed_right=(self.closed == "right"),
-                    fast=self.fast,
-                    noise_out=None if noise is None else noise[c, p0 // pn : p0 // pn + -(-pc // pn)],
-                    Sv=sub(outs["Sv"]), echo_range=sub(outs["echo_range"]), Sv_noise=sub(outs["Sv_noise"]),
-                    Sv_corrected=sub(outs["Sv_corrected"]), rmax_out=rmax_t[i : i + 1] if want_rmax else None,
-                )
+                nz = None if noise is None else noise[c, p0 // pn : p0 // pn + -(-pc // pn)]
+                if raw:
+                    kernels.pipeline_power_mvbs_i16(
+                        buf, self._scratch, rsub, self.xbin[p0 : p0 + pc], edges_t, acc[c : c + 1], 1, pc, R, nX, self.ping_num,
+                        self.range_sample_num, noise_max=self.noise_max, snr=self.snr, closed_right=(self.closed == "right"),
+                        noise_out=nz, rmax_out=rmax_t[i : i + 1] if want_rmax else None,
+                    )
+                    self.launches += 1
+                else:
+                    kernels.pipeline_power_mvbs(
+                        buf, rsub, self.xbin[p0 : p0 + pc], edges_t, acc[c : c + 1], 1, pc, R, nX, self.ping_num,
+                        self.range_sample_num, noise_max=self.noise_max, snr=self.snr, closed_right=(self.closed == "right"),
+                        fast=self.fast, noise_out=nz,
+                        Sv=sub(outs["Sv"]), echo_range=sub(outs["echo_range"]), Sv_noise=sub(outs["Sv_noise"]),
+                        Sv_corrected=sub(outs["Sv_corrected"]), rmax_out=rmax_t[i : i + 1] if want_rmax else None,
+                    )
                 self.launches += (3 if self.fast else 1) + (2 if want_rmax else 0)
                 freed[slot].record(main)
                 i += 1

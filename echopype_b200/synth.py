@@ -11,7 +11,7 @@ import numpy as np
 from .dataset import DataArray, Dataset, EchoData
 
 _T0 = np.datetime64("2018-07-01T00:00:00", "ns")
-_DB_PER_COUNT = np.float32(10.0 * np.log10(2.0) / 256.0)  # convert/parse_base.py:24
+_DB_PER_COUNT = 10.0 * np.log10(2.0) / 256.0  # INDEX2POWER, convert/parse_base.py:24
 
 
 def ping_times(P, interval_s=1.0, jitter_ms=0, rng=None, offset=0):
@@ -25,19 +25,21 @@ def _chan_names(prefix, freqs):
     return np.array([f"{prefix} {int(f / 1000)} kHz" for f in freqs], dtype=object)
 
 
-def _power_host(rng, C, P, R, nan_tail):
-    q = rng.integers(-24000, -2000, size=(C, P, R), endpoint=True).astype(np.float32)
-    x = q * _DB_PER_COUNT
+def _power_host(rng, C, P, R, nan_tail, raw_counts=False):
+    qi = rng.integers(-24000, -2000, size=(C, P, R), endpoint=True).astype(np.int16)
+    x = (qi.astype(np.float64) * _DB_PER_COUNT).astype(np.float32)  # parse_base.py:302 computes this product in float64
     if nan_tail:
         short = rng.random((C, P)) < nan_tail
         cut = rng.integers(R // 4, R, size=(C, P))
         n = np.arange(R)[None, None, :]
-        x[short[:, :, None] & (n >= cut[:, :, None])] = np.nan
-    return x
+        pad = short[:, :, None] & (n >= cut[:, :, None])
+        x[pad] = np.nan
+        qi[pad] = -32768  # the padding marker of the raw-count ingest format
+    return qi if raw_counts else x
 
 
 def make_ek60(C=4, P=1000, R=1000, seed=1001, device=False, nan_tail=0.005, ping_interval_s=1.0, time_varying=False, ping_offset=0,
-              backscatter=None):
+              backscatter=None, raw_counts=False):
     """EK60 CW power volume (cfg1 / cfg2).  ``time_varying`` makes sample_interval / pulse length / env
     parameters change along ping_time to exercise the per-row paths."""
     rng = np.random.default_rng(seed)
@@ -57,9 +59,12 @@ def make_ek60(C=4, P=1000, R=1000, seed=1001, device=False, nan_tail=0.005, ping
     elif device:
         from . import kernels
 
-        x = kernels.synth_fill((C, P, R), kind=0, seed=seed, nan_tail=nan_tail, ping_offset=ping_offset)
+        if raw_counts:  # the same volume as int16 raw power counts (ingest format)
+            x = kernels.synth_fill_i16((C, P, R), seed=seed, nan_tail=nan_tail, ping_offset=ping_offset)
+        else:
+            x = kernels.synth_fill((C, P, R), kind=0, seed=seed, nan_tail=nan_tail, ping_offset=ping_offset)
     else:
-        x = _power_host(rng, C, P, R, nan_tail)
+        x = _power_host(rng, C, P, R, nan_tail, raw_counts)
     beam = Dataset(
         {
             "backscatter_r": (("channel", "ping_time", "range_sample"), x),

@@ -204,8 +204,23 @@ int epb_pipeline_power_mvbs(const float* backscatter_r, const epb_row* rows, con
                             epb_i64 P, epb_i64 R, epb_i64 nX, int ping_num, int range_sample_num,
                             float noise_max, float snr_threshold, double* range_max_out, void* workspace,
                             epb_i64 workspace_bytes, void* stream);
+/* The same pipeline on RAW POWER COUNTS: counts [C,P,R] int16 as read from the power datagrams,
+ * -32768 marking the NaN padding of shorter pings (convert/parse_base.py:686-730); the samples enter the kernel at
+ * 2 bytes each and are scaled by INDEX2POWER (parse_base.py:24,302) in registers, bit-identical with
+ * epb_ingest_power_i16 followed by epb_pipeline_power_mvbs.  scratch: [C,P,R] float32 owned by the caller; it is
+ * written (by the ingest kernel) only when the volume is irregular and the general kernel has to run.
+ * Needs R % 8 == 0 for the direct path; no full-size outputs (ingest + epb_pipeline_power_mvbs serve those). */
+int epb_pipeline_power_mvbs_i16(const short* counts, float* scratch, const epb_row* rows, const int* xbin,
+                                const double* r_edges, int nR, int closed_right, double* acc, float* noise_out,
+                                epb_i64 C, epb_i64 P, epb_i64 R, epb_i64 nX, int ping_num, int range_sample_num,
+                                float noise_max, float snr_threshold, double* range_max_out, void* workspace,
+                                epb_i64 workspace_bytes, void* stream);
 epb_i64 epb_pipeline_workspace_bytes(epb_i64 C, epb_i64 P, int ping_num);
 epb_i64 epb_pipeline_smem_bytes(epb_i64 R, int nR, int tile, int do_noise, int staged);
+
+/* ---- raw power ingest (convert/parse_base.py:24,302 `power = counts.astype(float32) * INDEX2POWER`, :686-730
+ *      pad_shorter_ping): n int16 counts -> float32 dB, -32768 (padding marker) -> NaN. -------------------------- */
+int epb_ingest_power_i16(const short* counts, float* backscatter_r, epb_i64 n, void* stream);
 
 /* ---- consolidate.add_depth (consolidate/api.py:221): depth = depth_offset[c,p] + echo_range * scale[c,p], scale =
  *      orientation * cos(tilt) (or the platform / beam angle scaling).  echo_range, depth: [C,P,R] float32. -------- */
@@ -239,6 +254,11 @@ int epb_range_max(const float* backscatter_r, const epb_row* rows, epb_i64 C, ep
 int epb_synth_fill(float* out, epb_i64 C, epb_i64 P, epb_i64 R, epb_i64 inner, int kind,
                    unsigned long long seed, epb_i64 ping_offset, unsigned nan_tail_q16, float scale,
                    void* stream);
+
+/* kind 0 of epb_synth_fill as raw int16 counts q (-32768 past the NaN cut): epb_ingest_power_i16 of it equals
+ * epb_synth_fill(kind 0) bit for bit. */
+int epb_synth_fill_i16(short* out, epb_i64 C, epb_i64 P, epb_i64 R, unsigned long long seed, epb_i64 ping_offset,
+                       unsigned nan_tail_q16, void* stream);
 
 #ifdef __cplusplus
 }

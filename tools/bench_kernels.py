@@ -73,7 +73,7 @@ def main():
     if "svrm" in which:
         ms, mn = timeit(lambda: kernels.sv_power(x, rows, C, P, R, want_range=True, want_minmax=True, out=out, rng=rng), a.iters)
         report("sv_power+range+minmax", ms, mn, 12 * n, n)
-    if {"noise", "bins", "pipe"} & set(which):
+    if {"noise", "bins", "pipe", "pipe16"} & set(which):
         extra(a, which, C, P, R, n, x, rows, out, rng, ed)
     if "pulse" in which:
         del x, out, rng, ed
@@ -160,6 +160,14 @@ def extra(a, which, C, P, R, n, x, rows, out, rng, ed):
         report("pipeline(noise 5x30 + mvbs)", ms, mn, 4 * n, n)
         ms, mn = timeit(lambda: kernels.pipeline_power_mvbs(x, rows, xb, et, acc, C, P, R, nX, 0, 0), a.iters)
         report("pipeline(sv->mvbs)", ms, mn, 4 * n, n)
+    if "pipe16" in which:  # the same chain on int16 raw power counts (2 algorithmic bytes per sample)
+        q = kernels.synth_fill_i16((C, P, R), seed=1001)
+        ms, mn = timeit(lambda: kernels.pipeline_power_mvbs_i16(q, out.view(-1), rows, xb, et, acc, C, P, R, nX, 5, 30), a.iters)
+        report("pipeline_i16(noise 5x30 + mvbs)", ms, mn, 2 * n, n)
+        ms, mn = timeit(lambda: kernels.pipeline_power_mvbs_i16(q, out.view(-1), rows, xb, et, acc, C, P, R, nX, 0, 0), a.iters)
+        report("pipeline_i16(sv->mvbs)", ms, mn, 2 * n, n)
+        ms, mn = timeit(lambda: kernels.ingest_power_i16(q, out=out), a.iters)
+        report("ingest_power_i16", ms, mn, 6 * n, n)
 
 
 if __name__ == "__main__":
