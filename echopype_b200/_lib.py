@@ -64,6 +64,10 @@ SIGNATURES = {
     "epb_add_depth": (c_int, [vp, epb_cp, epb_cp, vp, i64, i64, i64, vp]),
     "epb_freq_diff_mask": (c_int, [vp, c_int, c_int, c_int, c_float, vp, i64, i64, i64, vp]),
     "epb_apply_mask": (c_int, [vp, vp, c_int, c_float, vp, i64, i64, i64, vp]),
+    "epb_range_diff_mean": (c_int, [vp, vp, vp, i64, i64, i64, vp]),
+    "epb_first_not_le": (c_int, [vp, i64, c_float, vp, vp]),
+    "epb_impulse_noise_mask": (c_int, [vp, vp, vp, vp, i64, i64, i64, c_int, c_int, c_float, vp]),
+    "epb_transient_noise_mask": (c_int, [vp, vp, vp, vp, vp, i64, i64, i64, c_int, c_int, c_int, c_float, vp]),
     "epb_zero": (c_int, [vp, i64, vp]),
     "epb_minmax_init": (c_int, [vp, vp]),
     "epb_minmax": (c_int, [vp, i64, vp, vp]),

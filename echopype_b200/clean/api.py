@@ -9,6 +9,7 @@ from .. import kernels
 from ..dataset import DataArray, Dataset, as_dataset
 from ..device import ParamPack, require_cuda, to_device_f32
 from ..utils.prov import add_processing_level, echopype_prov_attrs, insert_input_processing_level
+from ..commongrid.utils import _parse_x_bin
 from .utils import extract_dB, noise_attrs
 
 DIMS = ("channel", "ping_time", "range_sample")
@@ -87,3 +88,102 @@ def remove_background_noise(ds_Sv, ping_num: int, range_sample_num: int, backgro
     out = out.assign_attrs(prov_dict)
     out = insert_input_processing_level(out, input_ds=ds_Sv)
     return out
+
+
+# ---- impulse / transient noise masks with index binning ---------------------------------------
+def _index_binning_inputs(ds_Sv, range_var, what):
+    """Sv and the range variable as device arrays plus the number of range samples per depth bin of each channel
+    (clean/utils.py:131-133, 280-282: ceil(depth_bin / nanmean(diff(range_var, axis=range_sample))))."""
+    if range_var not in ["echo_range", "depth"]:
+        raise ValueError("`range_var` must be either `echo_range` or `depth`.")
+    if range_var not in ds_Sv:
+        raise ValueError(f"Masking {what} noise requires `{range_var}` data variable in `ds_Sv`.")
+    sv = ds_Sv["Sv"]
+    if tuple(sv.dims) != DIMS:
+        raise ValueError(f"Sv must have dims {DIMS}, got {tuple(sv.dims)}")
+    dev = require_cuda()
+    C, P, R = sv.shape
+    Sv = to_device_f32(sv.data, dev)
+    rng = to_device_f32(ds_Sv[range_var].data, dev)
+    if tuple(rng.shape) != (C, P, R):
+        raise ValueError(f"{range_var} must have the shape of Sv")
+    return Sv, rng, C, P, R
+
+
+def _samples_per_bin(rng, depth_bin, C, P, R):
+    mean_diff = kernels.range_diff_mean(rng, C, P, R)
+    if not np.all(np.isfinite(mean_diff)) or np.any(mean_diff <= 0):
+        raise ValueError("the range variable has no valid, increasing sample spacing in some channel")
+    return np.ceil(depth_bin / mean_diff).astype(int)
+
+
+def _mask_coords(ds_Sv):
+    return {d: ds_Sv[d].values for d in DIMS if d in ds_Sv}
+
+
+def mask_impulse_noise(ds_Sv, depth_bin: str = "5m", num_side_pings: int = 2, impulse_noise_threshold: str = "10.0dB",
+                       range_var: str = "depth", use_index_binning: bool = False) -> DataArray:
+    """
+    Locate and create a mask for impulse noise using a ping-wise two-sided comparison (Ryan et al. 2015; arguments
+    as echopype.clean.mask_impulse_noise, clean/api.py:169-266).
+
+    The accelerated path is ``use_index_binning=True``: Sv is averaged (linear domain) over blocks of
+    ``ceil(depth_bin / mean sample spacing)`` range samples per channel, forward filled back to every sample and compared
+    with the pings ``num_side_pings`` before and after.  Returns a boolean (uint8 on the device) DataArray with dims
+    (channel, ping_time, range_sample); the reference's ``apply_ufunc`` hands the same values back with the last two
+    dims swapped.
+    """
+    ds_Sv = as_dataset(ds_Sv)
+    if range_var not in ["echo_range", "depth"]:
+        raise ValueError("`range_var` must be either `echo_range` or `depth`.")
+    if range_var not in ds_Sv and not use_index_binning:
+        raise ValueError(f"Masking impulse noise requires `{range_var}` data variable in `ds_Sv`.")
+    thr = extract_dB(impulse_noise_threshold)
+    depth_bin = _parse_x_bin(depth_bin, "range_bin")
+    if not use_index_binning:
+        raise NotImplementedError("only use_index_binning=True runs on the device (SURVEY.md 8f rank 3); the per-ping "
+                                  "depth-value binning of the reference's default is outside the accelerated path")
+    if not (isinstance(num_side_pings, (int, np.integer)) and num_side_pings >= 1):
+        raise ValueError("num_side_pings must be a positive integer")
+    Sv, rng, C, P, R = _index_binning_inputs(ds_Sv, range_var, "impulse")
+    nsamp = _samples_per_bin(rng, depth_bin, C, P, R)
+    mask, _ = kernels.impulse_noise_mask(Sv, nsamp, C, P, R, int(num_side_pings), thr)
+    return DataArray(mask, DIMS, coords=_mask_coords(ds_Sv), name="Sv")
+
+
+def mask_transient_noise(ds_Sv, func: str = "nanmean", depth_bin: str = "10m", num_side_pings: int = 25,
+                         exclude_above: str = "250.0m", transient_noise_threshold: str = "12.0dB", range_var: str = "depth",
+                         use_index_binning: bool = False, chunk_dict: dict = {}) -> DataArray:
+    """
+    Locate and create a mask for transient noise using a pooling comparison (Ryan et al. 2015; arguments as
+    echopype.clean.mask_transient_noise, clean/api.py:30-166).
+
+    The accelerated path is ``use_index_binning=True`` with ``func="nanmean"``: pooled Sv is the mean (linear domain)
+    over ``2 num_side_pings + 1`` pings x ``2 ceil(depth_bin / mean sample spacing) + 1`` range samples with reflected
+    borders, computed below the first sample deeper than ``exclude_above``; the mask is
+    ``Sv - pooled_Sv > transient_noise_threshold``.  ``chunk_dict`` (dask chunking of the reference) is ignored.
+    """
+    ds_Sv = as_dataset(ds_Sv)
+    if range_var not in ["echo_range", "depth"]:
+        raise ValueError("`range_var` must be either `echo_range` or `depth`.")
+    if range_var not in ds_Sv and not use_index_binning:
+        raise ValueError(f"Masking transient noise requires `{range_var}` data variable in `ds_Sv`.")
+    if func != "nanmean" and func != "nanmedian":
+        raise ValueError(f"Input `func` is `{func}`. `func` must be `nanmean` or `nanmedian`.")
+    thr = extract_dB(transient_noise_threshold)
+    depth_bin = _parse_x_bin(depth_bin, "range_bin")
+    exclude_above = _parse_x_bin(exclude_above, "range_bin")
+    if not use_index_binning or func != "nanmean":
+        raise NotImplementedError("only use_index_binning=True with func='nanmean' runs on the device (SURVEY.md 8f rank 3)")
+    if not (isinstance(num_side_pings, (int, np.integer)) and num_side_pings >= 0):
+        raise ValueError("num_side_pings must be a non-negative integer")
+    Sv, rng, C, P, R = _index_binning_inputs(ds_Sv, range_var, "transient")
+    nsamp = _samples_per_bin(rng, depth_bin, C, P, R)
+    # clean/utils.py:141: np.argmin over the WHOLE (channel, ping_time, range_sample) <= mask, i.e. the first flat index
+    # that is deeper than exclude_above (0 when every sample is shallower: argmin of an all-True array)
+    m0 = kernels.first_not_le(rng, exclude_above)
+    m0 = 0 if m0 is None else m0
+    if m0 >= R:  # slice(min_range_sample, None) is empty: nothing is pooled, nothing is masked
+        m0 = R
+    mask, _ = kernels.transient_noise_mask(Sv, nsamp, C, P, R, m0, int(num_side_pings), thr)
+    return DataArray(mask, DIMS, coords=_mask_coords(ds_Sv), name="Sv")

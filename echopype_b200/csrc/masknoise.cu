@@ -1,0 +1,262 @@
+// clean.mask_impulse_noise / clean.mask_transient_noise with use_index_binning=True.
+// Reference: echopype/clean/api.py:30-266 and clean/utils.py:109-189 (index_binning_pool_Sv), :263-317
+// (index_binning_downsample_upsample_along_depth), :320-337 (echopy_impulse_noise_mask).  Both masks are window means
+// of 10^(Sv/10) over range_sample INDEX windows whose length comes from the mean sample spacing of the range variable
+// of each channel: the tile-mean machinery of the noise estimate with disjoint blocks (impulse) or sliding windows
+// with reflected borders (transient).  HBM-bound passes; window sums are accumulated in float64.
+#include "epb_common.cuh"
+
+namespace {
+using namespace epb;
+
+// ---- per-channel sum / count of the forward differences of a range variable (clean/utils.py:131-133, 280-282:
+//      np.nanmean(np.diff(range_var, axis=2), axis=(1, 2))).  float32 neighbours subtract exactly (Sterbenz), the sum
+//      telescopes in float64.  One CTA per (channel, ping) row, grid-stride. ----------------------------------------
+__global__ void __launch_bounds__(256) range_diff_kernel(const float* __restrict__ rng, long long nrows, long long P, int R,
+                                                         double* __restrict__ sum, unsigned long long* __restrict__ cnt) {
+  __shared__ double s_s[8];
+  __shared__ unsigned s_n[8];
+  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const float* r = rng + row * (long long)R;
+    double s = 0.0;
+    unsigned n = 0;
+    for (int j = threadIdx.x; j + 1 < R; j += blockDim.x) {
+      const float d = r[j + 1] - r[j];
+      if (d == d) s += (double)d, ++n;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      n += __shfl_xor_sync(0xffffffffu, n, o);
+    }
+    if ((threadIdx.x & 31) == 0) s_s[threadIdx.x >> 5] = s, s_n[threadIdx.x >> 5] = n;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double ts = 0.0;
+      unsigned long long tn = 0;
+      for (int w = 0; w < 8; ++w) ts += s_s[w], tn += s_n[w];
+      if (tn) {
+        atomicAdd(sum + row / P, ts);
+        atomicAdd(cnt + row / P, tn);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- first flat index i with !(a[i] <= thr)  (clean/utils.py:141: np.argmin((range_var <= exclude_above).data)) ----
+__global__ void __launch_bounds__(256) first_not_le_kernel(const float* __restrict__ a, long long n, float thr,
+                                                           unsigned long long* __restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+    if ((unsigned long long)i >= *reinterpret_cast<volatile unsigned long long*>(out)) return;  // an earlier hit exists
+    if (!(a[i] <= thr)) {
+      atomicMin(out, (unsigned long long)i);
+      return;
+    }
+  }
+}
+
+// ---- impulse noise, step 1: U[c,p,b] = 10 log10(nanmean of 10^(Sv/10) over the block b of nsamp[c] range samples)
+//      (coarsen(range_sample=n, boundary="pad").mean(skipna=True), clean/utils.py:292-302).  CTA per row. -------------
+__global__ void __launch_bounds__(256) block_mean_kernel(const float* __restrict__ Sv, const int* __restrict__ nsamp,
+                                                         float* __restrict__ U, long long nrows, long long P, int R,
+                                                         int nbmax) {
+  extern __shared__ float s_row[];
+  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int n = nsamp[row / P];
+    const int nb = (R + n - 1) / n;
+    const float* sv = Sv + row * (long long)R;
+    for (int j = threadIdx.x; j < R; j += blockDim.x) s_row[j] = fast_exp2(ld_stream(sv + j) * kDb2Log2);
+    __syncthreads();
+    for (int b = threadIdx.x; b < nbmax; b += blockDim.x) {
+      float u = CUDART_NAN_F;
+      if (b < nb) {
+        const int j0 = b * n, j1 = (j0 + n < R) ? j0 + n : R;
+        double s = 0.0;
+        int m = 0;
+        for (int j = j0; j < j1; ++j) {
+          const float q = s_row[j];
+          if (q == q) s += (double)q, ++m;
+        }
+        if (m > 0) u = 10.f * log10f((float)(s / (double)m));
+      }
+      U[row * nbmax + b] = u;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- impulse noise, step 2: the two-sided ping comparison on the block means, upsampled by forward fill
+//      (clean/utils.py:305-312 reindex ffill, :320-337 echopy_impulse_noise_mask): NaN differences count as +inf. ----
+__global__ void __launch_bounds__(256) impulse_mask_kernel(const float* __restrict__ U, const int* __restrict__ nsamp,
+                                                           unsigned char* __restrict__ mask, long long nrows, long long P,
+                                                           int R, int nbmax, int k, float thr) {
+  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const long long c = row / P, p = row - c * P;
+    const int n = nsamp[c];
+    const float* u0 = U + row * nbmax;
+    const float* uf = (p + k < P) ? U + (row + k) * nbmax : nullptr;
+    const float* ub = (p - k >= 0) ? U + (row - k) * nbmax : nullptr;
+    unsigned char* m = mask + row * (long long)R;
+    for (int j = threadIdx.x; j < R; j += blockDim.x) {
+      const int b = j / n;
+      const float v = u0[b];
+      float f = v - (uf ? uf[b] : CUDART_NAN_F), w = v - (ub ? ub[b] : CUDART_NAN_F);
+      f = (f == f) ? f : CUDART_INF_F;
+      w = (w == w) ? w : CUDART_INF_F;
+      m[j] = (f > thr && w > thr) ? 1 : 0;
+    }
+  }
+}
+
+// ---- transient noise, step 1: per (channel, ping) row, sum and count of the valid 10^(Sv/10) over the range window
+//      [n - w, n + w] of the array sliced at m0, borders reflected (d c b a | a b c d | d c b a: scipy.ndimage
+//      mode="reflect", clean/utils.py:158-170).  Float64 prefix sums in shared memory.  CTA per row. ------------------
+__global__ void __launch_bounds__(256) pool_rows_kernel(const float* __restrict__ Sv, const int* __restrict__ nsamp,
+                                                        float2* __restrict__ S1, long long nrows, long long P, int R, int m0) {
+  extern __shared__ double s_pre[];             // [L + 1] prefix sums of the valid linear values
+  const int L = R - m0;
+  int* s_cpre = reinterpret_cast<int*>(s_pre + (L + 1));  // [L + 1] prefix counts
+  __shared__ double s_ps[256];
+  __shared__ int s_pc[256];
+  const int per = (L + blockDim.x - 1) / blockDim.x;
+  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int w = nsamp[row / P];
+    const float* sv = Sv + row * (long long)R + m0;
+    // chunk-local inclusive prefix, then the offsets of the chunks
+    const int a = threadIdx.x * per, b = (a + per < L) ? a + per : L;
+    double s = 0.0;
+    int m = 0;
+    for (int j = a; j < b; ++j) {
+      const float q = fast_exp2(sv[j] * kDb2Log2);
+      if (q == q) s += (double)q, ++m;
+      s_pre[j + 1] = s;
+      s_cpre[j + 1] = m;
+    }
+    s_ps[threadIdx.x] = s, s_pc[threadIdx.x] = m;
+    __syncthreads();
+    double off = 0.0;
+    int coff = 0;
+    for (int t = 0; t < (int)threadIdx.x; ++t) off += s_ps[t], coff += s_pc[t];
+    for (int j = a; j < b; ++j) s_pre[j + 1] += off, s_cpre[j + 1] += coff;
+    if (threadIdx.x == 0) s_pre[0] = 0.0, s_cpre[0] = 0;
+    __syncthreads();
+    float2* o = S1 + row * (long long)R + m0;
+    for (int j = threadIdx.x; j < L; j += blockDim.x) {
+      const int lo = j - w, hi = j + w;
+      const int ca = lo < 0 ? 0 : lo, cb = hi >= L ? L - 1 : hi;
+      double ws = s_pre[cb + 1] - s_pre[ca];
+      int wc = s_cpre[cb + 1] - s_cpre[ca];
+      if (lo < 0) ws += s_pre[-lo] - s_pre[0], wc += s_cpre[-lo] - s_cpre[0];                           // [0, -lo - 1]
+      if (hi >= L) ws += s_pre[L] - s_pre[2 * L - hi - 1], wc += s_cpre[L] - s_cpre[2 * L - hi - 1];    // [2L-hi-1, L-1]
+      o[j] = make_float2((float)ws, (float)wc);
+    }
+    __syncthreads();
+  }
+}
+
+// ---- transient noise, step 2: sliding sum of the row windows over pings [p - k, p + k] (reflected), pooled Sv =
+//      10 log10(sum / count), mask = Sv - pooled > threshold (clean/api.py:163-166); samples above m0 are never
+//      masked (pooled NaN, clean/utils.py:174-176).  Thread per column and chunk of pings, float64 running sums. -----
+__global__ void __launch_bounds__(128) pool_pings_mask_kernel(const float2* __restrict__ S1, const float* __restrict__ Sv,
+                                                              unsigned char* __restrict__ mask, float* __restrict__ pooled,
+                                                              long long P, int R, int m0, int k, float thr, int chunk) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= R) return;
+  const long long c = blockIdx.z;
+  const long long p0 = (long long)blockIdx.y * chunk, p1 = (p0 + chunk < P) ? p0 + chunk : P;
+  const long long base = c * P * (long long)R + n;
+  if (n < m0) {
+    for (long long p = p0; p < p1; ++p) {
+      mask[base + p * R] = 0;
+      if (pooled) pooled[base + p * R] = CUDART_NAN_F;
+    }
+    return;
+  }
+  auto refl = [&](long long q) { return q < 0 ? -q - 1 : (q >= P ? 2 * P - q - 1 : q); };
+  double s = 0.0, m = 0.0;
+  for (long long q = p0 - k; q <= p0 + k; ++q) {
+    const float2 v = S1[base + refl(q) * R];
+    s += (double)v.x, m += (double)v.y;
+  }
+  for (long long p = p0; p < p1; ++p) {
+    const float pv = (m > 0.0) ? 10.f * log10f((float)(s / m)) : CUDART_NAN_F;
+    const float sv = Sv[base + p * R];
+    mask[base + p * R] = (sv - pv > thr) ? 1 : 0;
+    if (pooled) pooled[base + p * R] = pv;
+    const float2 in = S1[base + refl(p + k + 1) * R], out = S1[base + refl(p - k) * R];
+    s += (double)in.x - (double)out.x;
+    m += (double)in.y - (double)out.y;
+  }
+}
+
+}  // namespace
+
+extern "C" int epb_range_diff_mean(const float* range_var, double* sum, unsigned long long* count, epb_i64 C, epb_i64 P,
+                                   epb_i64 R, void* stream) {
+  EPB_REQUIRE(range_var && sum && count && C > 0 && P > 0 && R > 1, "bad pointer/shape");
+  if (cudaMemsetAsync(sum, 0, C * sizeof(double), (cudaStream_t)stream) != cudaSuccess ||
+      cudaMemsetAsync(count, 0, C * sizeof(unsigned long long), (cudaStream_t)stream) != cudaSuccess)
+    return epb_check_launch("epb_range_diff_mean(memset)");
+  const long long nrows = C * P, cap = (long long)epb_num_sms() * 8;
+  range_diff_kernel<<<(unsigned)(nrows < cap ? nrows : cap), 256, 0, (cudaStream_t)stream>>>(range_var, nrows, P, (int)R, sum,
+                                                                                             count);
+  return epb_check_launch("epb_range_diff_mean");
+}
+
+extern "C" int epb_first_not_le(const float* a, epb_i64 n, float threshold, unsigned long long* out, void* stream) {
+  EPB_REQUIRE(a && out && n > 0, "bad pointer/size");
+  if (cudaMemsetAsync(out, 0xff, sizeof(unsigned long long), (cudaStream_t)stream) != cudaSuccess)
+    return epb_check_launch("epb_first_not_le(memset)");
+  const long long blocks = (n + 255) / 256, cap = (long long)epb_num_sms() * 8;
+  first_not_le_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(a, n, threshold, out);
+  return epb_check_launch("epb_first_not_le");
+}
+
+extern "C" int epb_impulse_noise_mask(const float* Sv, const int* nsamp, float* block_means, unsigned char* mask, epb_i64 C,
+                                      epb_i64 P, epb_i64 R, int nbmax, int num_side_pings, float threshold, void* stream) {
+  EPB_REQUIRE(Sv && nsamp && block_means && mask, "NULL pointer");
+  EPB_REQUIRE(C > 0 && P > 0 && R > 0 && R <= 49152 && nbmax > 0 && num_side_pings >= 1, "bad shape / num_side_pings");
+  const long long nrows = C * P, cap = (long long)epb_num_sms() * 8;
+  const unsigned grid = (unsigned)(nrows < cap ? nrows : cap);
+  const size_t smem = (size_t)R * 4;
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(block_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return epb_check_launch("epb_impulse_noise_mask(smem)");
+  block_mean_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(Sv, nsamp, block_means, nrows, P, (int)R, nbmax);
+  impulse_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(block_means, nsamp, mask, nrows, P, (int)R, nbmax,
+                                                              num_side_pings, threshold);
+  return epb_check_launch("epb_impulse_noise_mask");
+}
+
+extern "C" int epb_transient_noise_mask(const float* Sv, const int* nsamp, float* window_sums /* float2 [C,P,R] */,
+                                        unsigned char* mask, float* pooled_Sv, epb_i64 C, epb_i64 P, epb_i64 R,
+                                        int min_range_sample, int max_nsamp, int num_side_pings, float threshold,
+                                        void* stream) {
+  EPB_REQUIRE(Sv && nsamp && window_sums && mask, "NULL pointer");
+  EPB_REQUIRE(max_nsamp >= 1 && (max_nsamp <= R - min_range_sample || min_range_sample == R),
+              "range window longer than the sliced range axis (single reflection)");
+  EPB_REQUIRE(C > 0 && C < 65536 && P > 0 && R > 0 && num_side_pings >= 0, "bad shape");
+  EPB_REQUIRE(min_range_sample >= 0 && min_range_sample <= R, "min_range_sample outside the range axis");
+  EPB_REQUIRE(num_side_pings <= P, "num_side_pings must not exceed the number of pings (single reflection)");
+  EPB_REQUIRE(((uintptr_t)window_sums % 8) == 0, "window_sums must be 8-byte aligned");
+  const int L = (int)R - min_range_sample;
+  const size_t smem = (size_t)(L + 1) * 12 + 8;
+  EPB_REQUIRE(smem <= 200 * 1024, "range_sample dimension too long for the shared-memory prefix sums");
+  const long long nrows = C * P, cap = (long long)epb_num_sms() * 8;
+  if (L > 0) {
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(pool_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return epb_check_launch("epb_transient_noise_mask(smem)");
+    pool_rows_kernel<<<(unsigned)(nrows < cap ? nrows : cap), 256, smem, (cudaStream_t)stream>>>(
+        Sv, nsamp, reinterpret_cast<float2*>(window_sums), nrows, P, (int)R, min_range_sample);
+  }
+  const int chunk = 256;
+  dim3 grid((unsigned)((R + 127) / 128), (unsigned)((P + chunk - 1) / chunk), (unsigned)C);
+  EPB_REQUIRE(grid.y < 65536, "too many ping chunks");
+  pool_pings_mask_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(window_sums), Sv, mask,
+                                                                 pooled_Sv, P, (int)R, min_range_sample, num_side_pings,
+                                                                 threshold, chunk);
+  return epb_check_launch("epb_transient_noise_mask");
+}

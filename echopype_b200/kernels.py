@@ -296,6 +296,44 @@ def ingest_power_i16(counts, out=None):
     return out
 
 
+def range_diff_mean(rng, C, P, R):
+    """Per-channel nanmean of the forward differences of a [C,P,R] float32 range variable (host float64 array [C])."""
+    s = torch.empty(C, dtype=torch.float64, device=rng.device)
+    n = torch.empty(C, dtype=torch.int64, device=rng.device)
+    _lib.call("epb_range_diff_mean", ptr(rng), ptr(s), ptr(n), C, P, R, stream())
+    s, n = s.cpu().numpy(), n.cpu().numpy()
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return np.where(n > 0, s / np.maximum(n, 1), np.nan)
+
+
+def first_not_le(a, threshold):
+    """First flat index of ``a`` where ``a <= threshold`` is False (np.argmin of the <= mask); None if there is none."""
+    out = torch.empty(1, dtype=torch.int64, device=a.device)
+    _lib.call("epb_first_not_le", ptr(a), int(a.numel()), ctypes.c_float(float(threshold)), ptr(out), stream())
+    v = int(out.item())
+    return None if v < 0 else v  # UINT64_MAX reads back as -1
+
+
+def impulse_noise_mask(Sv, nsamp, C, P, R, num_side_pings, threshold):
+    ns = torch.from_numpy(np.ascontiguousarray(nsamp, dtype=np.int32)).to(Sv.device)
+    nbmax = int(max(-(-R // int(n)) for n in nsamp))
+    blocks = torch.empty((C, P, nbmax), dtype=torch.float32, device=Sv.device)
+    mask = torch.empty((C, P, R), dtype=torch.uint8, device=Sv.device)
+    _lib.call("epb_impulse_noise_mask", ptr(Sv), ptr(ns), ptr(blocks), ptr(mask), C, P, R, nbmax, int(num_side_pings),
+              ctypes.c_float(float(threshold)), stream())
+    return mask, blocks
+
+
+def transient_noise_mask(Sv, nsamp, C, P, R, min_range_sample, num_side_pings, threshold, want_pooled=False):
+    ns = torch.from_numpy(np.ascontiguousarray(nsamp, dtype=np.int32)).to(Sv.device)
+    sums = torch.empty((C, P, R, 2), dtype=torch.float32, device=Sv.device)
+    mask = torch.empty((C, P, R), dtype=torch.uint8, device=Sv.device)
+    pooled = torch.empty((C, P, R), dtype=torch.float32, device=Sv.device) if want_pooled else None
+    _lib.call("epb_transient_noise_mask", ptr(Sv), ptr(ns), ptr(sums), ptr(mask), ptr(pooled), C, P, R, int(min_range_sample),
+              int(max(nsamp)), int(num_side_pings), ctypes.c_float(float(threshold)), stream())
+    return mask, pooled
+
+
 def is_raw_counts(x):
     """True for int16 raw power counts (the ingest format: -32768 = padding), host array or tensor."""
     return getattr(x, "dtype", None) in (torch.int16, np.dtype("int16"))
@@ -306,7 +344,7 @@ def power_to_device_f32(x):
     converted on the device (epb_ingest_power_i16); float data goes through :func:`device.to_device_f32`."""
     from .device import to_device_f32
 
-    data = getattr(x, "data", x)
+    data = x.data if hasattr(x, "dims") else x  # DataArray -> its array (ndarray.data would be a raw buffer)
     if not is_raw_counts(data):
         return to_device_f32(data)
     t = data if isinstance(data, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(data))

@@ -218,6 +218,29 @@ int epb_pipeline_power_mvbs_i16(const short* counts, float* scratch, const epb_r
 epb_i64 epb_pipeline_workspace_bytes(epb_i64 C, epb_i64 P, int ping_num);
 epb_i64 epb_pipeline_smem_bytes(epb_i64 R, int nR, int tile, int do_noise, int staged);
 
+/* ---- clean.mask_impulse_noise / mask_transient_noise with use_index_binning=True (clean/api.py:30-266; SURVEY.md 8f
+ *      rank 3).  nsamp [C] int32: range samples per depth bin of each channel,
+ *      ceil(depth_bin / nanmean(diff(range_var))) (clean/utils.py:131-133, 280-282); epb_range_diff_mean returns the
+ *      per-channel sum [C] float64 and count [C] uint64 of the valid forward differences of a [C,P,R] float32 range
+ *      variable.  epb_first_not_le: first flat index with !(a[i] <= threshold) (np.argmin of the <= mask,
+ *      clean/utils.py:141), UINT64_MAX if none. */
+int epb_range_diff_mean(const float* range_var, double* sum, unsigned long long* count, epb_i64 C, epb_i64 P, epb_i64 R,
+                        void* stream);
+int epb_first_not_le(const float* a, epb_i64 n, float threshold, unsigned long long* out, void* stream);
+/* Impulse noise (clean/utils.py:263-337): block_means [C,P,nbmax] float32 scratch/output (dB mean of every block of
+ * nsamp[c] range samples, NaN-aware, linear domain), mask [C,P,R] uint8 = both ping-wise differences of the forward
+ * filled block means (p vs p + k and p vs p - k, NaN difference = +inf) exceed threshold. */
+int epb_impulse_noise_mask(const float* Sv, const int* nsamp, float* block_means, unsigned char* mask, epb_i64 C, epb_i64 P,
+                           epb_i64 R, int nbmax, int num_side_pings, float threshold, void* stream);
+/* Transient noise (clean/utils.py:109-189 with func = nanmean, clean/api.py:163-166): pooled Sv = dB of the nanmean of
+ * 10^(Sv/10) over (2 k + 1) pings x (2 nsamp[c] + 1) range samples of the volume sliced at min_range_sample, borders
+ * reflected (scipy.ndimage "reflect"); mask [C,P,R] uint8 = Sv - pooled > threshold, 0 above min_range_sample.
+ * window_sums: [C,P,R] float2 scratch; pooled_Sv: NULL or [C,P,R] float32 (NaN above min_range_sample).
+ * max_nsamp = max(nsamp) (validated against the sliced axis length: one reflection per border). */
+int epb_transient_noise_mask(const float* Sv, const int* nsamp, float* window_sums, unsigned char* mask, float* pooled_Sv,
+                             epb_i64 C, epb_i64 P, epb_i64 R, int min_range_sample, int max_nsamp, int num_side_pings,
+                             float threshold, void* stream);
+
 /* ---- raw power ingest (convert/parse_base.py:24,302 `power = counts.astype(float32) * INDEX2POWER`, :686-730
  *      pad_shorter_ping): n int16 counts -> float32 dB, -32768 (padding marker) -> NaN. -------------------------- */
 int epb_ingest_power_i16(const short* counts, float* backscatter_r, epb_i64 n, void* stream);

@@ -133,3 +133,73 @@ def remove_background_noise(
         "attrs_noise": _attrs(Sv_noise, "noise"),
         "attrs_corrected": _attrs(corr, "corrected"),
     }
+
+
+# ---- impulse / transient noise masks with index binning ---------------------------------------
+def samples_per_depth_bin(range_var, depth_bin):
+    """clean/utils.py:131-133 / 280-282: range samples per depth bin of each channel; range_var (C, P, R)."""
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        return np.ceil(depth_bin / np.nanmean(np.diff(range_var, axis=2), axis=(1, 2))).astype(int)
+
+
+def index_binning_downsample_upsample(Sv, range_var, depth_bin):
+    """clean/utils.py:263-317: per channel coarsen(range_sample=n, boundary="pad").mean(skipna=True) of 10^(Sv/10),
+    back to dB, block b re-labelled with range_sample n*b and reindexed onto every range_sample with ffill."""
+    C, P, R = Sv.shape
+    out = np.empty((C, P, R))
+    for c, n in enumerate(samples_per_depth_bin(range_var, depth_bin)):
+        nb = -(-R // n)
+        lin = np.full((P, nb * n), np.nan)
+        lin[:, :R] = log2lin(Sv[c])
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            coarse = lin2log(np.nanmean(lin.reshape(P, nb, n), axis=2))
+        out[c] = np.repeat(coarse, n, axis=1)[:, :R]
+    return out
+
+
+def echopy_impulse_noise_mask(Sv, num_side_pings, impulse_noise_threshold):
+    """clean/utils.py:320-337; Sv is one channel laid out (range_sample, ping_time)."""
+    k = num_side_pings
+    dummy = np.zeros((Sv.shape[0], k)) * np.nan
+    fwd = Sv - np.c_[Sv[:, k:], dummy]
+    bwd = Sv - np.c_[dummy, Sv[:, 0:-k]]
+    fwd[np.isnan(fwd)] = np.inf
+    bwd[np.isnan(bwd)] = np.inf
+    return (fwd > impulse_noise_threshold) & (bwd > impulse_noise_threshold)
+
+
+def mask_impulse_noise_index_binning(Sv, range_var, depth_bin, num_side_pings, impulse_noise_threshold):
+    """clean/api.py:169-266 with use_index_binning=True.  Returns (mask, upsampled_Sv), both (C, P, R); the reference's
+    apply_ufunc output carries the same values with dims (channel, range_sample, ping_time)."""
+    up = index_binning_downsample_upsample(Sv, range_var, depth_bin)
+    mask = np.stack([echopy_impulse_noise_mask(up[c].T, num_side_pings, impulse_noise_threshold).T for c in range(Sv.shape[0])])
+    return mask, up
+
+
+def index_binning_pool_Sv(Sv, range_var, depth_bin, num_side_pings, exclude_above):
+    """clean/utils.py:109-189 with func = np.nanmean: per channel scipy.ndimage.generic_filter (what
+    dask_image.ndfilters.generic_filter evaluates) of 10^(Sv/10) over [(2 k + 1) pings, (2 n + 1) range samples],
+    mode="reflect", on the volume sliced at the first flat index deeper than exclude_above (:141)."""
+    from scipy import ndimage
+
+    C, P, R = Sv.shape
+    pooled = np.full((C, P, R), np.nan)
+    m0 = int(np.argmin(range_var <= exclude_above))
+    if m0 >= R:
+        return pooled, m0
+    for c, n in enumerate(samples_per_depth_bin(range_var, depth_bin)):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            filt = ndimage.generic_filter(log2lin(Sv[c][:, m0:]), function=np.nanmean,
+                                          size=[2 * num_side_pings + 1, 2 * n + 1], mode="reflect")
+            pooled[c][:, m0:] = lin2log(filt)
+    return pooled, m0
+
+
+def mask_transient_noise_index_binning(Sv, range_var, depth_bin, num_side_pings, exclude_above, transient_noise_threshold):
+    """clean/api.py:30-166 with use_index_binning=True, func="nanmean".  Returns (mask, pooled_Sv)."""
+    pooled, _ = index_binning_pool_Sv(Sv, range_var, depth_bin, num_side_pings, exclude_above)
+    with np.errstate(invalid="ignore"):
+        return (Sv - pooled) > transient_noise_threshold, pooled

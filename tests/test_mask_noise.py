@@ -1,0 +1,176 @@
+"""clean.mask_impulse_noise / clean.mask_transient_noise with use_index_binning=True.
+
+CPU part: the oracle against the properties the reference's own tests check (tests/clean/test_noise.py:342-447
+reflection == symmetric padding; :616-682 block means; :696-768 the negated impulse condition), on mock data.
+GPU part: the device masks against the oracle; samples whose comparison sits within float32 rounding of the threshold
+are identified from the oracle's margin and excluded.
+"""
+
+import numpy as np
+import pytest
+
+from oracle import clean as oclean
+
+
+def _mock(C=2, P=40, R=200, seed=3, nan_frac=0.02, spacing=(0.19, 0.25)):
+    rng = np.random.default_rng(seed)
+    Sv = rng.normal(-70.0, 6.0, size=(C, P, R))
+    Sv[:, rng.integers(0, P, 6), :] += 18.0 * (rng.random((C, 6, R)) < 0.5)  # loud pings: impulse / transient candidates
+    Sv[rng.random(Sv.shape) < nan_frac] = np.nan
+    Sv[0, 5, R // 2 :] = np.nan  # a short ping
+    depth = np.stack([np.broadcast_to(2.0 + s * np.arange(R), (P, R)) for s in np.resize(spacing, C)]).copy()
+    return Sv, depth
+
+
+def test_oracle_block_means_property():
+    """tests/clean/test_noise.py:616-682: every upsampled value equals the manual linear-domain mean of its block."""
+    Sv, depth = _mock()
+    up = oclean.index_binning_downsample_upsample(Sv, depth, 2.0)
+    for c, n in enumerate(oclean.samples_per_depth_bin(depth, 2.0)):
+        assert n == int(np.ceil(2.0 / (depth[c, 0, 1] - depth[c, 0, 0])))
+        for p in range(0, Sv.shape[1], 7):
+            for b in range(-(-Sv.shape[2] // n)):
+                blk = Sv[c, p, n * b : n * (b + 1)]
+                want = np.nan if np.all(np.isnan(blk)) else oclean.lin2log(np.nanmean(oclean.log2lin(blk)))
+                got = np.unique(up[c, p, n * b : n * (b + 1)])
+                assert got.size == 1 and (np.isnan(want) and np.isnan(got[0]) or np.isclose(got[0], want, atol=1e-10, rtol=1e-10))
+
+
+def test_oracle_impulse_condition_negation():
+    """tests/clean/test_noise.py:696-768: where the mask is False and all three values exist, one side is <= threshold."""
+    Sv, depth = _mock()
+    k, thr = 2, 10.0
+    mask, up = oclean.mask_impulse_noise_index_binning(Sv, depth, 2.0, k, thr)
+    assert mask.any() and not mask.all()
+    clean = np.where(mask, np.nan, up)
+    for p in range(k, Sv.shape[1] - k):
+        left, right = clean[:, p] - clean[:, p - k], clean[:, p] - clean[:, p + k]
+        ok = ~(np.isnan(clean[:, p]) | np.isnan(left) | np.isnan(right))
+        assert np.all((left[ok] <= thr) | (right[ok] <= thr))
+    # edges: the missing side counts as +inf (np.c_ with the NaN dummy), so only the existing side decides
+    assert np.array_equal(mask[:, 0], np.where(np.isnan(up[:, 0] - up[:, k]), True, up[:, 0] - up[:, k] > thr))
+
+
+def test_oracle_pooled_Sv_is_symmetric_padding():
+    """tests/clean/test_noise.py:342-447: generic_filter(mode="reflect") == windows over np.pad(mode="symmetric")."""
+    Sv, depth = _mock(P=24, R=90)
+    k, depth_bin, excl = 2, 1.0, 4.0
+    pooled, m0 = oclean.index_binning_pool_Sv(Sv, depth, depth_bin, k, excl)
+    assert m0 == int(np.argmin(depth[0, 0] <= excl)) and np.all(np.isnan(pooled[:, :, :m0]))
+    for c, n in enumerate(oclean.samples_per_depth_bin(depth, depth_bin)):
+        pad = np.pad(Sv[c][:, m0:], ((k, k), (n, n)), mode="symmetric")
+        for p in range(0, Sv.shape[1], 5):
+            for j in range(0, Sv.shape[2] - m0, 11):
+                win = oclean.log2lin(pad[p : p + 2 * k + 1, j : j + 2 * n + 1])
+                want = oclean.lin2log(np.nanmean(win))
+                assert np.isclose(pooled[c, p, m0 + j], want, rtol=1e-10, atol=1e-10)
+
+
+# ---- GPU --------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def ep():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import echopype_b200 as ep
+
+    return ep
+
+
+def _ds(ep, Sv, depth, range_var="depth"):
+    from echopype_b200.dataset import Dataset
+
+    C, P, R = Sv.shape
+    dims = ("channel", "ping_time", "range_sample")
+    return Dataset({"Sv": (dims, Sv.astype(np.float32)), range_var: (dims, depth.astype(np.float32))},
+                   coords={"channel": np.array([f"ch{i}" for i in range(C)], dtype=object),
+                           "ping_time": np.datetime64("2024-01-01") + np.arange(P) * np.timedelta64(1, "s"), "range_sample": np.arange(R)})
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,depth_bin,k", [((2, 40, 200), "2m", 2), ((3, 33, 1001), "5m", 3), ((1, 7, 64), "1m", 1)])
+def test_mask_impulse_noise_vs_oracle(ep, shape, depth_bin, k):
+    Sv, depth = _mock(*shape)
+    Sv32 = Sv.astype(np.float32).astype(np.float64)
+    thr = 10.0
+    want, up = oclean.mask_impulse_noise_index_binning(Sv32, depth, float(depth_bin[:-1]), k, thr)
+    got = ep.clean.mask_impulse_noise(_ds(ep, Sv, depth), depth_bin, k, "10.0dB", "depth", use_index_binning=True)
+    assert tuple(got.dims) == ("channel", "ping_time", "range_sample")
+    g = got.values.astype(bool)
+    # margin of the two comparisons (NaN difference = +inf)
+    P = shape[1]
+    fwd = np.full(Sv.shape, np.inf)
+    bwd = np.full(Sv.shape, np.inf)
+    fwd[:, : P - k] = up[:, : P - k] - up[:, k:]
+    bwd[:, k:] = up[:, k:] - up[:, : P - k]
+    fwd[np.isnan(fwd)] = np.inf
+    bwd[np.isnan(bwd)] = np.inf
+    sure = (np.abs(fwd - thr) > 1e-3) & (np.abs(bwd - thr) > 1e-3)
+    assert sure.mean() > 0.99 and want.any()
+    np.testing.assert_array_equal(g[sure], want[sure])
+
+
+@pytest.mark.gpu
+def test_impulse_block_means_within_tolerance(ep):
+    import torch
+
+    from echopype_b200 import kernels
+
+    Sv, depth = _mock(2, 25, 333)
+    Sv32 = Sv.astype(np.float32)
+    up = oclean.index_binning_downsample_upsample(Sv32.astype(np.float64), depth, 2.0)
+    nsamp = oclean.samples_per_depth_bin(depth, 2.0)
+    _, blocks = kernels.impulse_noise_mask(torch.from_numpy(Sv32).cuda(), nsamp, 2, 25, 333, 2, 10.0)
+    blocks = blocks.cpu().numpy()
+    for c, n in enumerate(nsamp):
+        ref = up[c][:, ::n]
+        got = blocks[c][:, : ref.shape[1]]
+        np.testing.assert_array_equal(np.isnan(got), np.isnan(ref))
+        assert np.nanmax(np.abs(got - ref)) < 1e-4  # dB, the tolerance of the path
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,depth_bin,k,excl", [((2, 40, 200), "2m", 3, "6m"), ((2, 30, 150), "1m", 25, "0m"),
+                                                  ((1, 12, 90), "1m", 2, "4.0m"), ((2, 9, 64), "1m", 1, "500m")])
+def test_mask_transient_noise_vs_oracle(ep, shape, depth_bin, k, excl):
+    import torch
+
+    from echopype_b200 import kernels
+
+    Sv, depth = _mock(*shape)
+    Sv32 = Sv.astype(np.float32).astype(np.float64)
+    thr = 6.0
+    want, pooled = oclean.mask_transient_noise_index_binning(Sv32, depth, float(depth_bin[:-1]), k, float(excl[:-1]), thr)
+    got = ep.clean.mask_transient_noise(_ds(ep, Sv, depth), "nanmean", depth_bin, k, excl, "6.0dB", "depth", use_index_binning=True)
+    g = got.values.astype(bool)
+    with np.errstate(invalid="ignore"):
+        margin = np.abs((Sv32 - pooled) - thr)
+    sure = np.isnan(margin) | (margin > 1e-3)
+    assert sure.mean() > 0.99
+    np.testing.assert_array_equal(g[sure], want[sure])
+    if float(excl[:-1]) < 100:
+        assert want.any()
+    # pooled Sv itself: within the tolerance of the path, identical NaN pattern
+    C, P, R = shape
+    nsamp = oclean.samples_per_depth_bin(depth, float(depth_bin[:-1]))
+    m0 = int(np.argmin(depth <= float(excl[:-1])))
+    _, pl = kernels.transient_noise_mask(torch.from_numpy(Sv.astype(np.float32)).cuda(), nsamp, C, P, R, min(m0, R), k, thr, want_pooled=True)
+    pl = pl.cpu().numpy()
+    np.testing.assert_array_equal(np.isnan(pl), np.isnan(pooled))
+    if not np.all(np.isnan(pooled)):
+        assert np.nanmax(np.abs(pl - pooled)) < 1e-4
+
+
+@pytest.mark.gpu
+def test_mask_noise_argument_errors(ep):
+    Sv, depth = _mock(1, 8, 40)
+    ds = _ds(ep, Sv, depth)
+    with pytest.raises(ValueError, match="`range_var` must be either `echo_range` or `depth`."):
+        ep.clean.mask_impulse_noise(ds, range_var="range", use_index_binning=True)
+    with pytest.raises(ValueError, match="must be `nanmean` or `nanmedian`"):
+        ep.clean.mask_transient_noise(ds, func="mean", use_index_binning=True)
+    with pytest.raises(ValueError, match="requires `echo_range` data variable"):
+        ep.clean.mask_transient_noise(ds, range_var="echo_range", use_index_binning=True)
+    with pytest.raises(NotImplementedError):
+        ep.clean.mask_impulse_noise(ds, use_index_binning=False)
