@@ -314,20 +314,22 @@ def first_not_le(a, threshold):
     return None if v < 0 else v  # UINT64_MAX reads back as -1
 
 
-def impulse_noise_mask(Sv, nsamp, C, P, R, num_side_pings, threshold):
+def impulse_noise_mask(Sv, nsamp, C, P, R, num_side_pings, threshold, out=None):
+    """out: optional (mask, block_means) buffers to reuse."""
     ns = torch.from_numpy(np.ascontiguousarray(nsamp, dtype=np.int32)).to(Sv.device)
     nbmax = int(max(-(-R // int(n)) for n in nsamp))
-    blocks = torch.empty((C, P, nbmax), dtype=torch.float32, device=Sv.device)
-    mask = torch.empty((C, P, R), dtype=torch.uint8, device=Sv.device)
+    mask, blocks = out if out is not None else (torch.empty((C, P, R), dtype=torch.uint8, device=Sv.device),
+                                                torch.empty((C, P, nbmax), dtype=torch.float32, device=Sv.device))
     _lib.call("epb_impulse_noise_mask", ptr(Sv), ptr(ns), ptr(blocks), ptr(mask), C, P, R, nbmax, int(num_side_pings),
               ctypes.c_float(float(threshold)), stream())
     return mask, blocks
 
 
-def transient_noise_mask(Sv, nsamp, C, P, R, min_range_sample, num_side_pings, threshold, want_pooled=False):
+def transient_noise_mask(Sv, nsamp, C, P, R, min_range_sample, num_side_pings, threshold, want_pooled=False, out=None):
+    """out: optional (mask, window_sums) buffers to reuse."""
     ns = torch.from_numpy(np.ascontiguousarray(nsamp, dtype=np.int32)).to(Sv.device)
-    sums = torch.empty((C, P, R, 2), dtype=torch.float32, device=Sv.device)
-    mask = torch.empty((C, P, R), dtype=torch.uint8, device=Sv.device)
+    mask, sums = out if out is not None else (torch.empty((C, P, R), dtype=torch.uint8, device=Sv.device),
+                                              torch.empty((C, P, R, 2), dtype=torch.float32, device=Sv.device))
     pooled = torch.empty((C, P, R), dtype=torch.float32, device=Sv.device) if want_pooled else None
     _lib.call("epb_transient_noise_mask", ptr(Sv), ptr(ns), ptr(sums), ptr(mask), ptr(pooled), C, P, R, int(min_range_sample),
               int(max(nsamp)), int(num_side_pings), ctypes.c_float(float(threshold)), stream())
