@@ -181,6 +181,9 @@ __device__ __forceinline__ float rcp_approx(float x) {
 __device__ __forceinline__ bool finite_f(float x) { return x * 0.f == 0.f; }
 
 // T rows per tile (ping_num), G column groups of four per thread (threads = R / (4 G))
+#ifndef EPB_G1_THREADS
+#define EPB_G1_THREADS 512  // the one-group variant runs up to this many threads per CTA; 1024 (64 registers, R = 4096 in one group) measured 2.02 ms vs 1.67 ms on cfg2
+#endif
 #ifndef EPB_G1_BLOCKS
 #define EPB_G1_BLOCKS 2  // resident CTAs per SM of the one-group variant (R <= 2048): 64 registers per thread
 #endif
@@ -200,12 +203,13 @@ __device__ __forceinline__ float4 counts_to_db(uint2 w) {
 }
 
 template <int T, int G, bool kNoise, bool kI16>
-__global__ void __launch_bounds__(512, G == 1 ? EPB_G1_BLOCKS : 1) pipeline_fast_kernel(const FastParams pr) {
+__global__ void __launch_bounds__(G == 1 ? EPB_G1_THREADS : 512, (G == 1 && EPB_G1_THREADS == 512) ? EPB_G1_BLOCKS : 1)
+    pipeline_fast_kernel(const FastParams pr) {
   if (*pr.irregular) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long s_full[kMaxTilesInFlight];  // one mbarrier per tile slot
   __shared__ __align__(16) TileInfo s_tile[kMaxTilesInFlight + 1];  // NT + 1 in rotation: a descriptor outlives its ring slot
-  __shared__ __align__(16) unsigned int s_wmin[16];  // per warp: minimum range-tile mean of the current tile (float bits)
+  __shared__ __align__(16) unsigned int s_wmin[32];  // per warp: minimum range-tile mean of the current tile (float bits)
   __shared__ int s_hasnan[2];   // a thread saw a NaN sample in the tile: range-tile counts are corrected by s_def
   __shared__ Producer s_prod;
   __shared__ int s_multi;  // the current law has a column group of four in more than two range bins
@@ -267,7 +271,7 @@ __global__ void __launch_bounds__(512, G == 1 ? EPB_G1_BLOCKS : 1) pipeline_fast
   if (tid == 0) {
     for (int i = 0; i < kMaxTilesInFlight; ++i) mbar_init(&s_full[i], 1);
     mbar_init_fence();
-    for (int i = 0; i < 16; ++i) s_wmin[i] = kInfBits;
+    for (int i = 0; i < 32; ++i) s_wmin[i] = kInfBits;
     s_hasnan[0] = 0, s_hasnan[1] = 0;
     for (int t = 0; t < kMaxT; ++t) s_last[t] = -1;
     const int c0 = (int)(g0 / nPt), it0 = (int)(g0 - (long long)c0 * nPt);
@@ -655,10 +659,11 @@ __global__ void __launch_bounds__(512, G == 1 ? EPB_G1_BLOCKS : 1) pipeline_fast
       }
       __syncthreads();  // (B)
       {
-        const uint4 w0 = *reinterpret_cast<const uint4*>(s_wmin), w1 = *reinterpret_cast<const uint4*>(s_wmin + 4);
-        const uint4 w2 = *reinterpret_cast<const uint4*>(s_wmin + 8), w3 = *reinterpret_cast<const uint4*>(s_wmin + 12);
-        const unsigned u = min(min(min(min(w0.x, w0.y), min(w0.z, w0.w)), min(min(w1.x, w1.y), min(w1.z, w1.w))),
-                               min(min(min(w2.x, w2.y), min(w2.z, w2.w)), min(min(w3.x, w3.y), min(w3.z, w3.w))));
+        unsigned u = kInfBits;
+        for (int i = 0; i < (nth >> 5); i += 4) {  // CTA-uniform; entries of absent warps stay +inf
+          const uint4 w4 = *reinterpret_cast<const uint4*>(s_wmin + i);
+          u = min(u, min(min(w4.x, w4.y), min(w4.z, w4.w)));
+        }
         float v = (u == kInfBits) ? CUDART_NAN_F : __uint_as_float(u);
         if (pr.noise_max_lin == pr.noise_max_lin) v = (v < pr.noise_max_lin) ? v : pr.noise_max_lin;  // NaN -> max
         noise_lin = v;
@@ -774,12 +779,12 @@ int epb_pipeline_fast_try(const void* x, int x_i16, const epb_row* rows, const i
   if (x_i16 && (R % 8 != 0 || sv_input)) return 0;  // 16-byte rows for the bulk copies
   const int xb = x_i16 ? 2 : 4;
   if (noise && range_sample_num < 4) return 0;  // a column group of four may touch at most two range tiles
-  const int G = (R / 4 > 512) ? 2 : 1;  // column groups per thread
+  const int G = (R / 4 > EPB_G1_THREADS) ? 2 : 1;  // column groups per thread
   const int threads = (int)(((R / 4 + G - 1) / G + 31) / 32 * 32);
   const int nRt = noise ? (int)((R + range_sample_num - 1) / range_sample_num) : 0;
   // ring: as many tile slots as fit (at least one, at most kMaxTilesInFlight; more than 4 buys nothing)
   // one-group variant: leave room for EPB_G1_BLOCKS resident CTAs per SM (1 KB per CTA is reserved by the driver)
-  const size_t smem_cap = (G == 1 && EPB_G1_BLOCKS > 1) ? (size_t)(227 * 1024) / EPB_G1_BLOCKS - 3072 : kSmemMax;
+  const size_t smem_cap = (G == 1 && threads <= 512 && EPB_G1_BLOCKS > 1) ? (size_t)(227 * 1024) / EPB_G1_BLOCKS - 3072 : kSmemMax;
   int nslots = 0;
   for (int n = 4; n >= 1; --n)
     if (fast_smem(R, T, nR, n, nRt, xb) <= smem_cap || (n == 1 && fast_smem(R, T, nR, n, nRt, xb) <= kSmemMax)) {
