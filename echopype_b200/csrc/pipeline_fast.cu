@@ -184,6 +184,9 @@ __device__ __forceinline__ bool finite_f(float x) { return x * 0.f == 0.f; }
 #ifndef EPB_G1_THREADS
 #define EPB_G1_THREADS 512  // the one-group variant runs up to this many threads per CTA; 1024 (64 registers, R = 4096 in one group) measured 2.02 ms vs 1.67 ms on cfg2
 #endif
+#ifndef EPB_GBIG
+#define EPB_GBIG 2  // column groups per thread of the wide variant (R > 4 * EPB_G1_THREADS): 2 -> 512 threads, 4 -> 256
+#endif
 #ifndef EPB_G1_BLOCKS
 #define EPB_G1_BLOCKS 2  // resident CTAs per SM of the one-group variant (R <= 2048): 64 registers per thread
 #endif
@@ -203,7 +206,7 @@ __device__ __forceinline__ float4 counts_to_db(uint2 w) {
 }
 
 template <int T, int G, bool kNoise, bool kI16>
-__global__ void __launch_bounds__(G == 1 ? EPB_G1_THREADS : 512, (G == 1 && EPB_G1_THREADS == 512) ? EPB_G1_BLOCKS : 1)
+__global__ void __launch_bounds__(G == 1 ? EPB_G1_THREADS : 512 / (EPB_GBIG / 2), (G == 1 && EPB_G1_THREADS == 512) ? EPB_G1_BLOCKS : 1)
     pipeline_fast_kernel(const FastParams pr) {
   if (*pr.irregular) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -779,7 +782,7 @@ int epb_pipeline_fast_try(const void* x, int x_i16, const epb_row* rows, const i
   if (x_i16 && (R % 8 != 0 || sv_input)) return 0;  // 16-byte rows for the bulk copies
   const int xb = x_i16 ? 2 : 4;
   if (noise && range_sample_num < 4) return 0;  // a column group of four may touch at most two range tiles
-  const int G = (R / 4 > EPB_G1_THREADS) ? 2 : 1;  // column groups per thread
+  const int G = (R / 4 > EPB_G1_THREADS) ? EPB_GBIG : 1;  // column groups per thread
   const int threads = (int)(((R / 4 + G - 1) / G + 31) / 32 * 32);
   const int nRt = noise ? (int)((R + range_sample_num - 1) / range_sample_num) : 0;
   // ring: as many tile slots as fit (at least one, at most kMaxTilesInFlight; more than 4 buys nothing)
@@ -819,7 +822,7 @@ int epb_pipeline_fast_try(const void* x, int x_i16, const epb_row* rows, const i
   prepare_kernel<<<(unsigned)((pr.ntiles + 127) / 128), 128, 0, s>>>(rows, xbin, P, nX, T, pr.nPt, pr.ntiles, sv_input,
                                                                      const_cast<TileInfo*>(pr.tiles), irregular);
   int rc = -1;
-#define EPB_FAST_G(TT, NZ, I16) ((G == 2) ? launch_fast<TT, 2, NZ, I16>(pr, threads, smem, s) : launch_fast<TT, 1, NZ, I16>(pr, threads, smem, s))
+#define EPB_FAST_G(TT, NZ, I16) ((G != 1) ? launch_fast<TT, EPB_GBIG, NZ, I16>(pr, threads, smem, s) : launch_fast<TT, 1, NZ, I16>(pr, threads, smem, s))
 #define EPB_FAST(TT)                                                            \
   case TT:                                                                      \
     rc = x_i16 ? EPB_FAST_G(TT, true, true) : EPB_FAST_G(TT, true, false);      \
