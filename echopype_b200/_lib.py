@@ -90,6 +90,8 @@ def load():
         )
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
+        if os.environ.get("EPB200_LIB") and not hasattr(lib, name):
+            continue  # A/B build of an older revision (developer knob only)
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args

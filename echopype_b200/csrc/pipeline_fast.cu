@@ -212,7 +212,8 @@ __global__ void __launch_bounds__(G == 1 ? EPB_G1_THREADS : 512 / (EPB_GBIG / 2)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long s_full[kMaxTilesInFlight];  // one mbarrier per tile slot
   __shared__ __align__(16) TileInfo s_tile[kMaxTilesInFlight + 1];  // NT + 1 in rotation: a descriptor outlives its ring slot
-  __shared__ __align__(16) unsigned int s_wmin[32];  // per warp: minimum range-tile mean of the current tile (float bits)
+  constexpr int kMaxWarps = (EPB_G1_THREADS > 512 ? EPB_G1_THREADS : 512) / 32;
+  __shared__ __align__(16) unsigned int s_wmin[kMaxWarps];  // per warp: minimum range-tile mean of the current tile (float bits)
   __shared__ int s_hasnan[2];   // a thread saw a NaN sample in the tile: range-tile counts are corrected by s_def
   __shared__ Producer s_prod;
   __shared__ int s_multi;  // the current law has a column group of four in more than two range bins
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(G == 1 ? EPB_G1_THREADS : 512 / (EPB_GBIG / 2)
   if (tid == 0) {
     for (int i = 0; i < kMaxTilesInFlight; ++i) mbar_init(&s_full[i], 1);
     mbar_init_fence();
-    for (int i = 0; i < 32; ++i) s_wmin[i] = kInfBits;
+    for (int i = 0; i < kMaxWarps; ++i) s_wmin[i] = kInfBits;
     s_hasnan[0] = 0, s_hasnan[1] = 0;
     for (int t = 0; t < kMaxT; ++t) s_last[t] = -1;
     const int c0 = (int)(g0 / nPt), it0 = (int)(g0 - (long long)c0 * nPt);
@@ -426,8 +427,8 @@ __global__ void __launch_bounds__(G == 1 ? EPB_G1_THREADS : 512 / (EPB_GBIG / 2)
     const unsigned char* tbase = s_ring + (size_t)ts * T * row_bytes;
     unsigned mn16 = 0x7fff7fffu;  // kI16: packed minimum of the thread's counts (finds the padding marker)
     auto ld4 = [&](int t, int g) -> float4 {
-      if (!kI16) return *reinterpret_cast<const float4*>(tbase + ((size_t)t * R + colg[g]) * 4);
-      const uint2 w = *reinterpret_cast<const uint2*>(tbase + ((size_t)t * R + colg[g]) * 2);
+      if (!kI16) return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(tbase) + t * R + colg[g]);
+      const uint2 w = *reinterpret_cast<const uint2*>(reinterpret_cast<const short*>(tbase) + t * R + colg[g]);
       mn16 = __vimin3_s16x2(mn16, w.x, w.y);  // VIMNMX3.S16x2
       return counts_to_db(w);
     };
@@ -549,7 +550,7 @@ __global__ void __launch_bounds__(G == 1 ? EPB_G1_THREADS : 512 / (EPB_GBIG / 2)
       for (int t = 0; t < T; ++t)
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-          const uint2 w = *reinterpret_cast<const uint2*>(tbase + ((size_t)t * R + colg[g]) * 2);
+          const uint2 w = *reinterpret_cast<const uint2*>(reinterpret_cast<const short*>(tbase) + t * R + colg[g]);
           if ((w.x & 0xffffu) == 0x8000u) e[g][t][0] = CUDART_NAN_F;
           if ((w.x >> 16) == 0x8000u) e[g][t][1] = CUDART_NAN_F;
           if ((w.y & 0xffffu) == 0x8000u) e[g][t][2] = CUDART_NAN_F;
@@ -663,7 +664,8 @@ __global__ void __launch_bounds__(G == 1 ? EPB_G1_THREADS : 512 / (EPB_GBIG / 2)
       __syncthreads();  // (B)
       {
         unsigned u = kInfBits;
-        for (int i = 0; i < (nth >> 5); i += 4) {  // CTA-uniform; entries of absent warps stay +inf
+#pragma unroll
+        for (int i = 0; i < kMaxWarps; i += 4) {  // entries of absent warps stay +inf
           const uint4 w4 = *reinterpret_cast<const uint4*>(s_wmin + i);
           u = min(u, min(min(w4.x, w4.y), min(w4.z, w4.w)));
         }
