@@ -72,17 +72,38 @@ __device__ __forceinline__ bool same_law(const epb_row& a, const epb_row& b) {
 }
 
 // One thread per tile: build the tile descriptor and flag volumes the fast kernel cannot take (a tile whose rows do
-// not share one range law, or rows with NaN calibration constants).
-__global__ void prepare_kernel(const epb_row* __restrict__ rows, const int* __restrict__ xbin, long long P, long long nX,
-                               int T, int nPt, long long ntiles, int sv_input, TileInfo* __restrict__ tiles,
-                               int* __restrict__ irregular) {
-  const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (g >= ntiles) return;
+// not share one range law, or rows with NaN calibration constants).  A block handles tpb consecutive tiles; their
+// row records (contiguous: tile g + 1 starts where tile g ends, plus the T rows before the first tile for its
+// "law changed" test) are staged in shared memory with coalesced 16-byte loads (192-byte records read by one thread
+// each ran at 1.2 TB/s: 64 us of the 1.8 ms cfg2 step).
+__global__ void __launch_bounds__(128) prepare_kernel(const epb_row* __restrict__ rows, const int* __restrict__ xbin,
+                                                      long long P, long long nX, int T, int nPt, long long ntiles,
+                                                      long long nrows, int tpb, int sv_input, TileInfo* __restrict__ tiles,
+                                                      int* __restrict__ irregular) {
+  extern __shared__ __align__(16) unsigned char s_prep[];
+  const long long gb = blockIdx.x * (long long)tpb;
+  const long long ge = (gb + tpb < ntiles) ? gb + tpb : ntiles;
+  auto row0_of = [&](long long gg) {
+    const long long cc = gg / nPt;
+    return cc * P + (gg - cc * nPt) * (long long)T;
+  };
+  const long long rfirst = row0_of(gb);
+  const long long rb = (rfirst >= T) ? rfirst - T : 0;
+  const long long re = (ge == ntiles) ? nrows : row0_of(ge);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(rows + rb);
+    uint4* dst = reinterpret_cast<uint4*>(s_prep);
+    const int n16 = (int)(re - rb) * (int)(sizeof(epb_row) / 16);
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const long long g = gb + threadIdx.x;
+  if ((int)threadIdx.x >= tpb || g >= ntiles) return;
   const long long c = g / nPt;
   const int itile = (int)(g - c * nPt);
   const long long p0 = (long long)itile * T;
   const int Ta = (int)((p0 + T <= P) ? T : (P - p0));
-  const epb_row* r0 = rows + c * P + p0;
+  const epb_row* r0 = reinterpret_cast<const epb_row*>(s_prep) + (c * P + p0 - rb);
   TileInfo ti;
   bool bad = false;
   int nruns = 0, prev_xb = 0, rcsame = 1;
@@ -182,7 +203,7 @@ __device__ __forceinline__ bool finite_f(float x) { return x * 0.f == 0.f; }
 
 // T rows per tile (ping_num), G column groups of four per thread (threads = R / (4 G))
 #ifndef EPB_G1_THREADS
-#define EPB_G1_THREADS 512  // the one-group variant runs up to this many threads per CTA; 1024 (64 registers, R = 4096 in one group) measured 2.02 ms vs 1.67 ms on cfg2
+#define EPB_G1_THREADS 256  // one column group per thread up to this many threads (R <= 1024); wider rows take two groups: R = 2048 as 2 x 256 threads x 128 registers with two resident CTAs per SM measured 1.58 ms vs 1.97 ms for 1 x 512 x 64 registers (4x200000x2048)
 #endif
 #ifndef EPB_GBIG
 #define EPB_GBIG 2  // column groups per thread of the wide variant (R > 4 * EPB_G1_THREADS): 2 -> 512 threads, 4 -> 256
@@ -663,12 +684,9 @@ __global__ void __launch_bounds__(G == 1 ? EPB_G1_THREADS : 512 / (EPB_GBIG / 2)
       }
       __syncthreads();  // (B)
       {
-        unsigned u = kInfBits;
-#pragma unroll
-        for (int i = 0; i < kMaxWarps; i += 4) {  // entries of absent warps stay +inf
-          const uint4 w4 = *reinterpret_cast<const uint4*>(s_wmin + i);
-          u = min(u, min(min(w4.x, w4.y), min(w4.z, w4.w)));
-        }
+        // minimum of the per-warp minima: one entry per lane and a warp reduction (entries of absent warps stay +inf)
+        static_assert(kMaxWarps <= 32, "one s_wmin entry per lane");
+        const unsigned u = __reduce_min_sync(0xffffffffu, lane < kMaxWarps ? s_wmin[lane] : kInfBits);
         float v = (u == kInfBits) ? CUDART_NAN_F : __uint_as_float(u);
         if (pr.noise_max_lin == pr.noise_max_lin) v = (v < pr.noise_max_lin) ? v : pr.noise_max_lin;  // NaN -> max
         noise_lin = v;
@@ -789,7 +807,10 @@ int epb_pipeline_fast_try(const void* x, int x_i16, const epb_row* rows, const i
   const int nRt = noise ? (int)((R + range_sample_num - 1) / range_sample_num) : 0;
   // ring: as many tile slots as fit (at least one, at most kMaxTilesInFlight; more than 4 buys nothing)
   // one-group variant: leave room for EPB_G1_BLOCKS resident CTAs per SM (1 KB per CTA is reserved by the driver)
-  const size_t smem_cap = (G == 1 && threads <= 512 && EPB_G1_BLOCKS > 1) ? (size_t)(227 * 1024) / EPB_G1_BLOCKS - 3072 : kSmemMax;
+  // leave room for two resident CTAs per SM whenever the register file allows them: one group x <= 512 threads at 64
+  // registers, or two groups x <= 256 threads at 128 registers (1 KB per CTA is reserved by the driver)
+  const bool two_ctas = (G == 1 && threads <= 512 && EPB_G1_BLOCKS > 1) || (G == 2 && threads <= 256);
+  const size_t smem_cap = two_ctas ? (size_t)(227 * 1024) / 2 - 3072 : kSmemMax;
   int nslots = 0;
   for (int n = 4; n >= 1; --n)
     if (fast_smem(R, T, nR, n, nRt, xb) <= smem_cap || (n == 1 && fast_smem(R, T, nR, n, nRt, xb) <= kSmemMax)) {
@@ -821,8 +842,13 @@ int epb_pipeline_fast_try(const void* x, int x_i16, const epb_row* rows, const i
   pr.sv_input = sv_input;
   if (workspace_bytes < 256 + pr.ntiles * (long long)sizeof(TileInfo)) return 0;
   if (cudaMemsetAsync(irregular, 0, sizeof(int), s) != cudaSuccess) return 0;
-  prepare_kernel<<<(unsigned)((pr.ntiles + 127) / 128), 128, 0, s>>>(rows, xbin, P, nX, T, pr.nPt, pr.ntiles, sv_input,
-                                                                     const_cast<TileInfo*>(pr.tiles), irregular);
+  {
+    const int max_rows = 48 * 1024 / (int)sizeof(epb_row);  // 256 row records of shared memory
+    int tpb = max_rows / T - 1;
+    tpb = tpb > 128 ? 128 : tpb;
+    prepare_kernel<<<(unsigned)((pr.ntiles + tpb - 1) / tpb), 128, (size_t)(tpb + 1) * T * sizeof(epb_row), s>>>(
+        rows, xbin, P, nX, T, pr.nPt, pr.ntiles, C * P, tpb, sv_input, const_cast<TileInfo*>(pr.tiles), irregular);
+  }
   int rc = -1;
 #define EPB_FAST_G(TT, NZ, I16) ((G != 1) ? launch_fast<TT, EPB_GBIG, NZ, I16>(pr, threads, smem, s) : launch_fast<TT, 1, NZ, I16>(pr, threads, smem, s))
 #define EPB_FAST(TT)                                                            \
