@@ -235,6 +235,7 @@ def run_b200(args):
         plan.run()
     sync_all()
     plan.kernel_events.clear()
+    plan.comm_events.clear()
     l0 = plan.launches
     clocks = ClockSampler(local)
     clocks.start()
@@ -249,10 +250,12 @@ def run_b200(args):
     launches = plan.launches - l0
     k_ms = [a.elapsed_time(b) for a, b in plan.kernel_events]
     k_avg = sum(k_ms) / len(k_ms)
-    t = torch.tensor([ms_total, k_avg], dtype=torch.float64, device="cuda")
+    c_ms = [a.elapsed_time(b) for a, b in plan.comm_events]
+    c_avg = sum(c_ms) / len(c_ms) if c_ms else 0.0
+    t = torch.tensor([ms_total, k_avg, c_avg], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, k_avg = float(t[0]), float(t[1])
+    ms_total, k_avg, c_avg = float(t[0]), float(t[1]), float(t[2])
     value = n_local * world * args.steps / (ms_total * 1e-3)
     nan_frac = float(torch.isnan(mvbs).float().mean())
     plan.record_events = False
@@ -320,6 +323,7 @@ def run_b200(args):
             "config": {
                 "workload": workload_name(P), "l2": "inputs (6.55 GB/GPU) far exceed the 126 MB L2; no flush needed",
                 "parallelism": f"ping_time sharded over {world} GPU(s); straddling-bin all-reduce only",
+                "collectives_ms_per_step": round(c_avg, 4),
                 "mvbs_grid": list(mvbs.shape), "mvbs_nan_frac": round(nan_frac, 4), "e2e_matches_resident_nan_mask": same,
             },
             "roofline": {

@@ -322,3 +322,77 @@ extern "C" int epb_bin_finalize(const double* acc, float* out, double* h_out, ep
                                                                                          fill_value, to_db);
   return epb_check_launch("epb_bin_finalize");
 }
+
+// ---- ping-sharded execution: the straddling-bin exchange (pipeline.straddle_reduce) in two launches around ONE
+//      all-reduce(sum).  buf: [world][2 S + 1] float64 with S = C * nR * 4: rank r fills its own slot with the first and
+//      the last local ping bin of its accumulators (the only bins another rank can also hold) and its exact range
+//      maximum, zeros everywhere else; after the sum every rank sees every slot.  unpack adds, for its own first / last
+//      bin, the slots of the ranks that share that global bin (src lists from the host plan) and takes the maximum of
+//      the range maxima. -------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) straddle_pack_kernel(const double* __restrict__ acc, long long C, long long nXl, long long SC,
+                                                            const double* __restrict__ rmax, int nrmax, double* __restrict__ buf,
+                                                            int rank, int world, int has_last) {
+  const long long S = C * SC, W = 2 * S + 1;
+  const long long n = W * world;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long w = i / W, j = i - w * W;
+    double v = 0.0;
+    if (w == rank) {
+      if (j < 2 * S) {
+        const long long part = j / S, k = j - part * S, c = k / SC, q = k - c * SC;
+        if (part == 0)
+          v = acc[(c * nXl) * SC + q];
+        else if (has_last)
+          v = acc[(c * nXl + (nXl - 1)) * SC + q];
+      } else {
+        v = -CUDART_INF;
+        for (int t = 0; t < nrmax; ++t) v = fmax(v, rmax[t]);
+      }
+    }
+    buf[i] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) straddle_unpack_kernel(const double* __restrict__ buf, const int* __restrict__ src,
+                                                              int nsrc0, int nsrc1, long long C, long long nXl, long long SC,
+                                                              int world, double* __restrict__ acc, double* __restrict__ rmax_out) {
+  const long long S = C * SC, W = 2 * S + 1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < 2 * S; i += (long long)gridDim.x * blockDim.x) {
+    const long long slot = i / S, k = i - slot * S, c = k / SC, q = k - c * SC;
+    const int ns = slot == 0 ? nsrc0 : nsrc1;
+    if (ns == 0) continue;  // this slot is not shared (or hi == lo and the slot is the same bin as slot 0)
+    double v = 0.0;
+    for (int t = 0; t < ns; ++t) {
+      const int e = src[slot * world + t];  // 2 r: first bin of rank r, 2 r + 1: its last bin
+      v += buf[(long long)(e >> 1) * W + (long long)(e & 1) * S + k];
+    }
+    acc[(c * nXl + (slot == 0 ? 0 : nXl - 1)) * SC + q] = v;
+  }
+  if (rmax_out && blockIdx.x == 0 && threadIdx.x == 0) {
+    double m = -CUDART_INF;
+    for (int w = 0; w < world; ++w) m = fmax(m, buf[(long long)w * W + 2 * S]);
+    *rmax_out = m;
+  }
+}
+}  // namespace
+
+extern "C" int epb_straddle_pack(const double* acc, epb_i64 C, epb_i64 nXl, epb_i64 nR, const double* rmax, int nrmax,
+                                 double* buf, int rank, int world, int has_last, void* stream) {
+  EPB_REQUIRE(acc && buf && C > 0 && nXl > 0 && nR > 0 && world > 0 && rank >= 0 && rank < world, "bad pointer/shape");
+  EPB_REQUIRE(rmax || nrmax == 0, "rmax pointer missing");
+  const long long n = (2 * C * nR * 4 + 1) * (long long)world;
+  straddle_pack_kernel<<<(unsigned)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184), 256, 0, (cudaStream_t)stream>>>(
+      acc, C, nXl, nR * 4, rmax, nrmax, buf, rank, world, has_last);
+  return epb_check_launch("epb_straddle_pack");
+}
+
+extern "C" int epb_straddle_unpack(const double* buf, const int* src, int nsrc0, int nsrc1, epb_i64 C, epb_i64 nXl, epb_i64 nR,
+                                   int world, double* acc, double* rmax_out, void* stream) {
+  EPB_REQUIRE(buf && src && acc && C > 0 && nXl > 0 && nR > 0 && world > 0, "bad pointer/shape");
+  EPB_REQUIRE(nsrc0 >= 0 && nsrc0 <= world && nsrc1 >= 0 && nsrc1 <= world, "bad source counts");
+  const long long n = 2 * C * nR * 4;
+  straddle_unpack_kernel<<<(unsigned)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184), 256, 0, (cudaStream_t)stream>>>(
+      buf, src, nsrc0, nsrc1, C, nXl, nR * 4, world, acc, rmax_out);
+  return epb_check_launch("epb_straddle_unpack");
+}

@@ -72,10 +72,15 @@ def straddle_plan(lo, hi, group):
     idx = torch.full((world, 2), -1, dtype=torch.int64, device=_comm_device(group))
     idx[rank, 0], idx[rank, 1] = int(lo), int(hi)
     dist.all_reduce(idx, op=dist.ReduceOp.MAX, group=group)
-    idx = idx.cpu().tolist()
-    plan = {"world": world, "rank": rank, "lo": int(lo), "hi": int(hi), "slots": []}
+    return {"world": world, "rank": rank, "lo": int(lo), "hi": int(hi), "slots": straddle_slots(idx.cpu().tolist(), lo, hi)}
+
+
+def straddle_slots(idx, lo, hi):
+    """For the first (slot 0) and the last (slot hi - lo) local ping bin: which slices of the exchange buffer hold the
+    same global bin (entry 2 r: first bin of rank r, 2 r + 1: its last bin).  idx: [(lo, hi)] of every rank, -1 = none."""
+    slots = []
     if hi < lo:
-        return plan
+        return slots
     for slot, b in ((0, int(lo)), (int(hi) - int(lo), int(hi))):
         if slot != 0 and hi == lo:
             break
@@ -87,8 +92,8 @@ def straddle_plan(lo, hi, group):
                 src.append(2 * r)
             elif r_hi == b:  # r_hi != r_lo here
                 src.append(2 * r + 1)
-        plan["slots"].append((slot, src))
-    return plan
+        slots.append((slot, src))
+    return slots
 
 
 def straddle_reduce(acc, lo, hi, group, plan=None):
@@ -118,6 +123,40 @@ def straddle_reduce(acc, lo, hi, group, plan=None):
     for slot, src in plan["slots"]:
         acc[:, slot] = buf[src].sum(dim=0).to(acc.device)
     return acc
+
+
+def straddle_exchange_cuda(acc, rmax, plan, group):
+    """NCCL path of :func:`straddle_reduce` plus the global range maximum in THREE launches: epb_straddle_pack (own
+    first / last ping bin and max(rmax) into this rank's slot of a [world, 2 S + 1] buffer, zeros elsewhere), ONE
+    all-reduce(sum) of that buffer (the data-path collective), epb_straddle_unpack (sums of the shared slices into the
+    own edge bins, maximum of the range maxima).  ``rmax``: device float64 tensor of local maxima or None.
+    Returns the 1-element global range maximum (or None).  No host synchronisation."""
+    from . import _lib
+    from .device import ptr, stream
+
+    dist = _dist()
+    world, rank = plan["world"], plan["rank"]
+    C, nXl, nR, _ = acc.shape
+    W = 2 * C * nR * 4 + 1
+    st = plan.setdefault("_cuda", {})
+    if st.get("W") != W:
+        src = np.zeros((2, world), dtype=np.int32)
+        n0 = n1 = 0
+        for slot, lst in plan["slots"]:
+            if slot == 0:
+                src[0, : len(lst)], n0 = lst, len(lst)
+            else:
+                src[1, : len(lst)], n1 = lst, len(lst)
+        st.update(W=W, buf=torch.empty(world * W, dtype=torch.float64, device=acc.device),
+                  src=torch.from_numpy(src).to(acc.device), n0=n0, n1=n1)
+    buf = st["buf"]
+    has_last = int(plan["hi"] > plan["lo"])
+    _lib.call("epb_straddle_pack", ptr(acc), C, nXl, nR, ptr(rmax), 0 if rmax is None else int(rmax.numel()), ptr(buf),
+              rank, world, has_last, stream())
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)  # the data-path collective
+    out = torch.empty(1, dtype=torch.float64, device=acc.device) if rmax is not None else None
+    _lib.call("epb_straddle_unpack", ptr(buf), ptr(st["src"]), st["n0"], st["n1"], C, nXl, nR, world, ptr(acc), ptr(out), stream())
+    return out
 
 
 class FusedPlan:
@@ -195,6 +234,7 @@ class FusedPlan:
         self.launches = 0  # kernels of libepb200 launched by run() so far (bench.py "gpu_launches")
         self.record_events = False  # bench.py: CUDA events around every fused-kernel launch -> kernel_events
         self.kernel_events = []
+        self.comm_events = []  # bench.py: events around the straddling-bin / range-maximum collectives of a step
         self._splan = straddle_plan(self.x_lo, self.x_hi, group) if group is not None else None
         self._ub = None  # cached upper bound of the range grid (depends on the parameters only, not on the samples)
 
@@ -275,10 +315,20 @@ class FusedPlan:
         else:
             rmax = self._run_streamed(x, rows, outs, noise, acc, edges_t)
         if self.group is not None:
-            straddle_reduce(acc, self.x_lo, self.x_hi, self.group, self._splan)
-            if rmax is not None:  # global nanmax(echo_range): a 1-double max all-reduce, read only in wrap()
-                rmax = rmax.max().reshape(1).to(_comm_device(self.group))
-                _dist().all_reduce(rmax, op=_dist().ReduceOp.MAX, group=self.group)
+            if self.record_events:
+                cev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                cev[0].record()
+            if acc.is_cuda and _dist().get_backend(self.group) == "nccl":
+                rmax = straddle_exchange_cuda(acc, rmax, self._splan, self.group)
+                self.launches += 2
+            else:
+                straddle_reduce(acc, self.x_lo, self.x_hi, self.group, self._splan)
+                if rmax is not None:  # global nanmax(echo_range): a 1-double max all-reduce, read only in wrap()
+                    rmax = rmax.max().reshape(1).to(_comm_device(self.group))
+                    _dist().all_reduce(rmax, op=_dist().ReduceOp.MAX, group=self.group)
+            if self.record_events:
+                cev[1].record()
+                self.comm_events.append(cev)
         mvbs = None
         if finalize:
             mvbs, _ = kernels.bin_finalize(acc, skipna=self.skipna, fill_value=self.fill_value, to_db=True)

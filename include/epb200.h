@@ -218,6 +218,17 @@ int epb_pipeline_power_mvbs_i16(const short* counts, float* scratch, const epb_r
 epb_i64 epb_pipeline_workspace_bytes(epb_i64 C, epb_i64 P, int ping_num);
 epb_i64 epb_pipeline_smem_bytes(epb_i64 R, int nR, int tile, int do_noise, int staged);
 
+/* ---- ping-sharded execution: pack / unpack around the ONE all-reduce(sum) that merges the ping bins two
+ *      ranks share.  acc [C,nXl,nR,4] float64 (this rank's window of the global ping bins); buf [world][2*C*nR*4 + 1]
+ *      float64: own slot = first bin, last bin (zeros when has_last == 0, i.e. nXl == 1) and max(rmax[0..nrmax)), other
+ *      slots zero.  After the caller's all-reduce, unpack writes into the first / last local bin the sum of the slices
+ *      listed in src [2][world] (entry 2 r = first bin of rank r, 2 r + 1 = its last bin; nsrc0 / nsrc1 entries) and
+ *      the maximum of the range maxima into rmax_out (nullable). */
+int epb_straddle_pack(const double* acc, epb_i64 C, epb_i64 nXl, epb_i64 nR, const double* rmax, int nrmax, double* buf,
+                      int rank, int world, int has_last, void* stream);
+int epb_straddle_unpack(const double* buf, const int* src, int nsrc0, int nsrc1, epb_i64 C, epb_i64 nXl, epb_i64 nR,
+                        int world, double* acc, double* rmax_out, void* stream);
+
 /* ---- clean.mask_impulse_noise / mask_transient_noise with use_index_binning=True (clean/api.py:30-266; SURVEY.md 8f
  *      rank 3).  nsamp [C] int32: range samples per depth bin of each channel,
  *      ceil(depth_bin / nanmean(diff(range_var))) (clean/utils.py:131-133, 280-282); epb_range_diff_mean returns the

@@ -261,3 +261,50 @@ def test_fast_kernel_vs_oracle_benchmark_shape(ep):
     ds = ep.pipeline.compute_Sv_clean_MVBS(ed, ping_num=5, range_sample_num=30, range_bin="20m", ping_time_bin="20s")
     ref, mv, marg_bins, margin = _oracle_chain(ed, "ek60", 5, 30, None, "3.0dB", "20m", "20s")
     _check_mvbs(ds["Sv"].values, mv["Sv"], marg_bins)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("windows", [[(0, 4), (4, 7), (7, 9)], [(0, 3), (3, 3), (3, 6)], [(2, 5), (-1, -2), (6, 8)]])
+def test_straddle_pack_unpack_kernels_equal_global_sums(ep, windows):
+    """The NCCL path of the straddling-bin exchange (epb_straddle_pack -> all-reduce(sum) -> epb_straddle_unpack) on one
+    GPU: the all-reduce is emulated by adding the packed buffers of three fake ranks; every rank must end up with the
+    global sums in its first / last ping bin and with the global range maximum."""
+    import torch
+
+    from echopype_b200 import _lib
+    from echopype_b200.device import ptr, stream
+    from echopype_b200.pipeline import straddle_slots
+
+    rng = np.random.default_rng(7)
+    C, nR, world = 2, 5, len(windows)
+    accs, rmaxs, bufs = [], [], []
+    W = 2 * C * nR * 4 + 1
+    for r, (lo, hi) in enumerate(windows):
+        nXl = max(hi - lo + 1, 1)
+        a = rng.random((C, nXl, nR, 4)) if hi >= lo else np.zeros((C, 1, nR, 4))
+        accs.append(torch.from_numpy(a).cuda())
+        rmaxs.append(torch.tensor([10.0 * r + 1.0, 5.0 - r], dtype=torch.float64, device="cuda"))
+        buf = torch.full((world * W,), 7.0, dtype=torch.float64, device="cuda")  # stale contents must be overwritten
+        _lib.call("epb_straddle_pack", ptr(accs[r]), C, nXl, nR, ptr(rmaxs[r]), 2, ptr(buf), r, world, int(hi > lo), stream())
+        bufs.append(buf)
+    total = torch.stack(bufs).sum(0)
+    glob = {}  # global bin -> sum over the ranks that hold it
+    for r, (lo, hi) in enumerate(windows):
+        for b in range(lo, hi + 1):
+            glob[b] = glob.get(b, 0) + accs[r][:, b - lo].cpu().numpy()
+    idx = [w if w[1] >= w[0] else (-1, -1) for w in windows]
+    for r, (lo, hi) in enumerate(windows):
+        slots = straddle_slots(idx, lo, hi)
+        src = np.zeros((2, world), dtype=np.int32)
+        n = [0, 0]
+        for slot, lst in slots:
+            k = 0 if slot == 0 else 1
+            src[k, : len(lst)], n[k] = lst, len(lst)
+        acc = accs[r].clone()
+        out = torch.empty(1, dtype=torch.float64, device="cuda")
+        _lib.call("epb_straddle_unpack", ptr(total), ptr(torch.from_numpy(src).cuda()), n[0], n[1], C, acc.shape[1], nR, world,
+                  ptr(acc), ptr(out), stream())
+        assert float(out) == 10.0 * (world - 1) + 1.0
+        got = acc.cpu().numpy()
+        for b in range(lo, hi + 1):
+            np.testing.assert_allclose(got[:, b - lo], glob[b], rtol=1e-15)
