@@ -328,7 +328,10 @@ __global__ void __launch_bounds__(G == 1 ? EPB_G1_THREADS : 512 / (EPB_GBIG / 2)
   // exact nanmax(echo_range): the thread that owns the last column watches the final sample of every row
   const int last_group = (R >> 2) - 1;
   const bool is_last = pr.rmax != nullptr && tid == last_group % nth;
-  double range_last = -CUDART_INF, rmax_local = -CUDART_INF;
+  // watcher state lives in shared memory (one thread uses it; as registers it would cost every thread four)
+  __shared__ double s_range_last, s_rmax_local;  // range of the final sample under the current law; running maximum
+  __shared__ int s_seen_full;                     // some row under the current law had a defined final sample
+  if (is_last) s_range_last = -CUDART_INF, s_rmax_local = -CUDART_INF, s_seen_full = 0;
   Acc<G> acc;
   acc.clear();
   int cur_cell = -1;
@@ -469,7 +472,11 @@ __global__ void __launch_bounds__(G == 1 ? EPB_G1_THREADS : 512 / (EPB_GBIG / 2)
       for (int k = tid; k <= nR; k += nth) s_bounds[k] = first_at_or_above(lr, R, s_edges[k], pr.closed_right);
       const RowF rf = load_rowf(pr.rows + row0);
       nanrange = rf.nanrange && !pr.sv_input;
-      if (is_last) range_last = pr.rows[row0].range_last;
+      if (is_last) {
+        if (s_seen_full && s_range_last == s_range_last) s_rmax_local = fmax(s_rmax_local, s_range_last);
+        s_range_last = pr.rows[row0].range_last;
+        s_seen_full = 0;
+      }
       for (int n = 4 * tid; n < R; n += 4 * nth) {
         float lg[4], tl[4];
 #pragma unroll
@@ -604,19 +611,21 @@ __global__ void __launch_bounds__(G == 1 ? EPB_G1_THREADS : 512 / (EPB_GBIG / 2)
     }
 
     if (is_last) {  // rows whose final sample is NaN need a search for the last defined range (flags: bits 8.. of s_hasnan)
-      unsigned need = 0u;
-      if (nanrange) {
-        const int gl = last_group / nth;  // the group of this thread that holds the last column
+      const int gl = last_group / nth;  // the group of this thread that holds the last column
+      unsigned nm = 0u;
 #pragma unroll
-        for (int g = 0; g < G; ++g)
-          if (g == gl) {
+      for (int g = 0; g < G; ++g)
+        if (g == gl) nm = nanmask[g];
+      if (nm == 0u || !nanrange) {  // the usual tile: every final sample is defined
+        s_seen_full = 1;
+      } else {
+        unsigned need = 0u;
 #pragma unroll
-            for (int t = 0; t < T; ++t)
-              if (t < Ta && ((nanmask[g] >> (4 * t + 3)) & 1u)) need |= 1u << t;
-          }
+        for (int t = 0; t < T; ++t)
+          if (t < Ta && ((nm >> (4 * t + 3)) & 1u)) need |= 1u << t;
+        if (need != ((1u << Ta) - 1u)) s_seen_full = 1;
+        if (need) atomicOr(&s_hasnan[it], (int)(need << 8));
       }
-      if (need != ((1u << Ta) - 1u) && range_last == range_last) rmax_local = fmax(rmax_local, range_last);
-      if (need) atomicOr(&s_hasnan[it], (int)(need << 8));
     }
 
     float noise_lin = 0.f;
@@ -765,7 +774,10 @@ __global__ void __launch_bounds__(G == 1 ? EPB_G1_THREADS : 512 / (EPB_GBIG / 2)
     }
   }
   if (cur_cell >= 0) flush();
-  if (is_last && rmax_local != -CUDART_INF) atomic_max_d(pr.rmax, rmax_local);
+  if (is_last) {
+    if (s_seen_full && s_range_last == s_range_last) s_rmax_local = fmax(s_rmax_local, s_range_last);
+    if (s_rmax_local != -CUDART_INF) atomic_max_d(pr.rmax, s_rmax_local);
+  }
 }
 
 size_t fast_smem(long long R, int T, int nR, int ntiles_ring, int nRt, int xbytes) {

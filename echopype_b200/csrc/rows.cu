@@ -84,11 +84,30 @@ __device__ void finish_row(epb_row& r, int R, bool guard) {
   r.range_last = law_range(r, R - 1);
 }
 
+// A thread builds one 192-byte row record; a plain struct store would scatter 192-byte pieces.  The records of a warp
+// (32 consecutive rows = 6 KB contiguous) go through shared memory and leave as coalesced 16-byte stores.  Every thread
+// of the block must call this (blockDim.x == 128).
+__device__ __forceinline__ void store_row_coalesced(epb_row* __restrict__ rows, long long nrows, long long i, const epb_row& r) {
+  __shared__ __align__(16) epb_row s_rows[128];
+  s_rows[threadIdx.x] = r;
+  __syncwarp();
+  const int lane = threadIdx.x & 31, w0 = threadIdx.x & ~31;
+  const long long first = i - lane;  // row of lane 0
+  const long long left = nrows - first;
+  const int nvalid = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
+  const uint4* src = reinterpret_cast<const uint4*>(s_rows + w0);
+  uint4* dst = reinterpret_cast<uint4*>(rows + first);
+  const int n16 = nvalid * (int)(sizeof(epb_row) / 16);
+  for (int k = lane; k < n16; k += 32) dst[k] = src[k];
+  __syncwarp();
+}
+
 __global__ void rows_ek_power_kernel(epb_row* rows, long long C, long long P, int R, int sonar, int cal_type,
                                      epb_cp dt_, epb_cp c_, epb_cp al_, epb_cp tau_, epb_cp pt_, epb_cp g_,
                                      epb_cp sa_, epb_cp psi_, epb_cp f_, epb_cp te_, const unsigned char* is_gpt) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= C * P) return;
+  const long long i_store = i;  // rows past the end are computed from the last row and not stored
+  if (i >= C * P) i = C * P - 1;
   long long c = i / P, p = i % P;
   double dt = cp_at(dt_, c, p), cw = cp_at(c_, c, p), alpha = cp_at(al_, c, p);
   double tau = cp_at(tau_, c, p), pt = cp_at(pt_, c, p), G = cp_at(g_, c, p);
@@ -123,7 +142,7 @@ __global__ void rows_ek_power_kernel(epb_row* rows, long long C, long long P, in
   r.fscale = 1.0;
   r.foff = 0.0;
   finish_row(r, R, true);
-  rows[i] = r;
+  store_row_coalesced(rows, C * P, i_store, r);
 }
 
 __global__ void rows_azfp_kernel(epb_row* rows, long long C, long long P, int R, int cal_type, epb_cp c_,
@@ -131,7 +150,8 @@ __global__ void rows_azfp_kernel(epb_row* rows, long long C, long long P, int R,
                                  const double* EL, const double* DS, const double* TVR, const double* VTX0,
                                  const double* psi_lin, const double* Sv_offset) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= C * P) return;
+  const long long i_store = i;  // rows past the end are computed from the last row and not stored
+  if (i >= C * P) i = C * P - 1;
   long long c = i / P, p = i % P;
   double cw = cp_at(c_, c, p), alpha = cp_at(al_, c, p), tau = cp_at(tau_, c, p);
   epb_row r;
@@ -156,7 +176,7 @@ __global__ void rows_azfp_kernel(epb_row* rows, long long C, long long P, int R,
     r.slog = 40.0;
   }
   finish_row(r, R, false);  // no R' > 0 guard for AZFP (calibrate_azfp.py:64)
-  rows[i] = r;
+  store_row_coalesced(rows, C * P, i_store, r);
 }
 
 __global__ void rows_ek80_complex_kernel(epb_row* rows, long long C, long long P, int R, int cal_type, int bb,
@@ -164,7 +184,8 @@ __global__ void rows_ek80_complex_kernel(epb_row* rows, long long C, long long P
                                          epb_cp g_, epb_cp sa_, epb_cp psi_, epb_cp f_, epb_cp te_, epb_cp zet_,
                                          epb_cp zer_, const unsigned char* is_gpt) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= C * P) return;
+  const long long i_store = i;  // rows past the end are computed from the last row and not stored
+  if (i >= C * P) i = C * P - 1;
   long long c = i / P, p = i % P;
   double dt = cp_at(dt_, c, p), cw = cp_at(c_, c, p), alpha = cp_at(al_, c, p);
   double tau = cp_at(tau_, c, p), pt = cp_at(pt_, c, p), G = cp_at(g_, c, p), f = cp_at(f_, c, p);
@@ -196,7 +217,7 @@ __global__ void rows_ek80_complex_kernel(epb_row* rows, long long C, long long P
   r.fscale = (double)n_beam / 8.0 * zr * zr / zet;
   r.foff = 0.0;
   finish_row(r, R, true);
-  rows[i] = r;
+  store_row_coalesced(rows, C * P, i_store, r);
 }
 
 int grid_for(long long n, int block) { return (int)((n + block - 1) / block); }

@@ -73,7 +73,7 @@ def main():
     if "svrm" in which:
         ms, mn = timeit(lambda: kernels.sv_power(x, rows, C, P, R, want_range=True, want_minmax=True, out=out, rng=rng), a.iters)
         report("sv_power+range+minmax", ms, mn, 12 * n, n)
-    if {"noise", "bins", "pipe", "pipe16", "masks"} & set(which):
+    if {"noise", "bins", "pipe", "pipe16", "masks", "pipex"} & set(which):
         extra(a, which, C, P, R, n, x, rows, out, rng, ed)
     if "pulse" in which:
         del x, out, rng, ed
@@ -169,6 +169,12 @@ def extra(a, which, C, P, R, n, x, rows, out, rng, ed):
         tbuf = (mbuf[0], torch.empty((C, P, R, 2), dtype=torch.float32, device=dev))
         ms, mn = timeit(lambda: kernels.transient_noise_mask(out, nsamp, C, P, R, 1300, 25, 12.0, out=tbuf), max(3, a.iters // 2))
         report("mask_transient_noise(10m, 25 pings)", ms, mn, 5 * n, n)
+    if "pipex" in which:  # cost of the optional outputs of the fused launch
+        nz = torch.empty((C, -(-P // 5)), dtype=torch.float32, device=dev)
+        rm = torch.empty(1, dtype=torch.float64, device=dev)
+        for name, kw in (("none", {}), ("noise_out", {"noise_out": nz}), ("rmax_out", {"rmax_out": rm}), ("both", {"noise_out": nz, "rmax_out": rm})):
+            ms, mn = timeit(lambda: kernels.pipeline_power_mvbs(x, rows, xb, et, acc, C, P, R, nX, 5, 30, **kw), a.iters)
+            report(f"pipeline(noise 5x30 + mvbs) [{name}]", ms, mn, 4 * n, n)
     if "pipe16" in which:  # the same chain on int16 raw power counts (2 algorithmic bytes per sample)
         q = kernels.synth_fill_i16((C, P, R), seed=1001)
         ms, mn = timeit(lambda: kernels.pipeline_power_mvbs_i16(q, out.view(-1), rows, xb, et, acc, C, P, R, nX, 5, 30), a.iters)
