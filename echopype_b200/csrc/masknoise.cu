@@ -319,12 +319,8 @@ extern "C" int epb_transient_noise_mask(const float* Sv, const int* nsamp, float
   const int chunk = 256;
   dim3 grid((unsigned)((R + 127) / 128), (unsigned)((P + chunk - 1) / chunk), (unsigned)C);
   EPB_REQUIRE(grid.y < 65536, "too many ping chunks");
-#ifndef EPB_POOL_PAD_SMEM
-#define EPB_POOL_PAD_SMEM 0
-#endif
-  // EPB_POOL_PAD_SMEM > 0: unused dynamic shared memory that caps the resident CTAs, so that the rows a CTA reads a
-  // second time (2 k + 1 pings later) are still in L2
-  pool_pings_mask_kernel<<<grid, 128, EPB_POOL_PAD_SMEM, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(window_sums), Sv, mask,
+  // (capping the resident CTAs so that the second read of a row hits L2 measured slower: 12.1 -> 14.7 ms)
+  pool_pings_mask_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(window_sums), Sv, mask,
                                                                  pooled_Sv, P, (int)R, min_range_sample, num_side_pings,
                                                                  threshold, chunk);
   return epb_check_launch("epb_transient_noise_mask");
