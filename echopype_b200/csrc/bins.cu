@@ -44,6 +44,25 @@ __device__ __forceinline__ int bin_of(double x, const double* __restrict__ e, in
   return k;
 }
 
+// float32 range variables: x >= e (float64 edge) <=> x >= ceil32(e) and x > e <=> x > floor32(e) for every float32 x, so
+// the interval rule of the reference can be decided with float32 compares against thresholds rounded toward the side
+// of the rule (t[k] = ceil32(e[k]) for closed left, floor32(e[k]) for closed right): same keys, no float64 per sample.
+__device__ __forceinline__ int bin_of_f32(float x, const float* __restrict__ t, int nR, float inv_w, int closed_right) {
+  if (!(x == x)) return -1;
+  const float lo = t[0], hi = t[nR];
+  if (closed_right ? !(x > lo && x <= hi) : !(x >= lo && x < hi)) return -1;
+  int k = (int)((x - lo) * inv_w);
+  k = k < 0 ? 0 : (k > nR - 1 ? nR - 1 : k);
+  if (closed_right) {
+    while (k > 0 && !(x > t[k])) --k;
+    while (k < nR - 1 && x > t[k + 1]) ++k;
+  } else {
+    while (k > 0 && x < t[k]) --k;
+    while (k < nR - 1 && x >= t[k + 1]) ++k;
+  }
+  return k;
+}
+
 __device__ __forceinline__ void flush_run(double* __restrict__ cell, const Acc3& a, bool with_h) {
   const int good = a.cnt & 0xffff, bad = a.cnt >> 16;
   if (good) {
@@ -97,12 +116,19 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) bin_reduce_kernel(const flo
                                                                        int closed_right, double* __restrict__ acc,
                                                                        long long C, long long P, int R, long long nX) {
   extern __shared__ double s_edges[];
-  for (int k = threadIdx.x; k <= nR; k += blockDim.x) s_edges[k] = edges[k];
+  constexpr bool kF32 = sizeof(RT) == 4;
+  float* s_t32 = reinterpret_cast<float*>(s_edges + (nR + 1));  // [nR+1] float32 thresholds (kF32)
+  for (int k = threadIdx.x; k <= nR; k += blockDim.x) {
+    s_edges[k] = edges[k];
+    if (kF32) s_t32[k] = closed_right ? __double2float_rd(edges[k]) : __double2float_ru(edges[k]);
+  }
   __syncthreads();
   const double inv_w = (double)nR / (s_edges[nR] - s_edges[0]);
+  const float inv_w32 = (float)inv_w;
   const int lane = threadIdx.x & 31;
   const long long nrows = C * P;
   const long long warp0 = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  const bool vec = kF32 && (R & 3) == 0;  // rows start 16-byte aligned: one float4 of Sv and of range per lane
   for (long long row = warp0; row < nrows; row += (long long)gridDim.x * kWarpsPerCta) {
     const long long c = row / P, p = row % P;
     const int xb = __ldg(xbin + p);
@@ -114,16 +140,24 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) bin_reduce_kernel(const flo
       // lane owns samples n0 + 4*lane .. +3 ; keys per sample, merged per lane when all four agree
       int keys[4];
       Acc3 a[4];
+      float xv[4] = {0.f, 0.f, 0.f, 0.f}, sv4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (vec && n0 + 4 * lane < R) {
+        const float4 q = ld_stream4(reinterpret_cast<const float4*>(rr + n0 + 4 * lane));
+        const float4 w = ld_stream4(reinterpret_cast<const float4*>(sv + n0 + 4 * lane));
+        xv[0] = q.x, xv[1] = q.y, xv[2] = q.z, xv[3] = q.w;
+        sv4[0] = w.x, sv4[1] = w.y, sv4[2] = w.z, sv4[3] = w.w;
+      }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int n = n0 + 4 * lane + k;
         keys[k] = -1;
         a[k].sum = 0.f, a[k].cnt = 0, a[k].h = 0.f;
         if (n < R) {
-          const double x = (double)rr[n];
-          keys[k] = bin_of(x, s_edges, nR, inv_w, closed_right);
+          const double x = vec ? (double)xv[k] : (double)rr[n];
+          keys[k] = kF32 ? bin_of_f32(vec ? xv[k] : (float)rr[n], s_t32, nR, inv_w32, closed_right)
+                         : bin_of(x, s_edges, nR, inv_w, closed_right);
           if (keys[k] >= 0) {
-            add_sample(a[k], ld_stream(sv + n));
+            add_sample(a[k], vec ? sv4[k] : ld_stream(sv + n));
             if (kHeight && n + 1 < R) {
               const double d = (double)rr[n + 1] - x;  // diff(label="lower") commongrid/utils.py:170-172
               if (d == d) a[k].h = (float)d;
@@ -262,7 +296,7 @@ extern "C" int epb_bin_reduce(const float* Sv, const void* range_var, int range_
   long long grid = (nrows + kWarpsPerCta - 1) / kWarpsPerCta;
   const long long cap = (long long)epb_num_sms() * 8;
   if (grid > cap) grid = cap;
-  const size_t smem = (size_t)(nR + 1) * sizeof(double);
+  const size_t smem = (size_t)(nR + 1) * (sizeof(double) + sizeof(float));  // edges + float32 thresholds
   cudaStream_t s = (cudaStream_t)stream;
 #define EPB_BR(T, H)                                                                                        \
   do {                                                                                                      \
