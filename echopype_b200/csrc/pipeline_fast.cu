@@ -72,38 +72,18 @@ __device__ __forceinline__ bool same_law(const epb_row& a, const epb_row& b) {
 }
 
 // One thread per tile: build the tile descriptor and flag volumes the fast kernel cannot take (a tile whose rows do
-// not share one range law, or rows with NaN calibration constants).  A block handles tpb consecutive tiles; their
-// row records (contiguous: tile g + 1 starts where tile g ends, plus the T rows before the first tile for its
-// "law changed" test) are staged in shared memory with coalesced 16-byte loads (192-byte records read by one thread
-// each ran at 1.2 TB/s: 64 us of the 1.8 ms cfg2 step).
-__global__ void __launch_bounds__(128) prepare_kernel(const epb_row* __restrict__ rows, const int* __restrict__ xbin,
-                                                      long long P, long long nX, int T, int nPt, long long ntiles,
-                                                      long long nrows, int tpb, int sv_input, TileInfo* __restrict__ tiles,
-                                                      int* __restrict__ irregular) {
-  extern __shared__ __align__(16) unsigned char s_prep[];
-  const long long gb = blockIdx.x * (long long)tpb;
-  const long long ge = (gb + tpb < ntiles) ? gb + tpb : ntiles;
-  auto row0_of = [&](long long gg) {
-    const long long cc = gg / nPt;
-    return cc * P + (gg - cc * nPt) * (long long)T;
-  };
-  const long long rfirst = row0_of(gb);
-  const long long rb = (rfirst >= T) ? rfirst - T : 0;
-  const long long re = (ge == ntiles) ? nrows : row0_of(ge);
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(rows + rb);
-    uint4* dst = reinterpret_cast<uint4*>(s_prep);
-    const int n16 = (int)(re - rb) * (int)(sizeof(epb_row) / 16);
-    for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
-  }
-  __syncthreads();
-  const long long g = gb + threadIdx.x;
-  if ((int)threadIdx.x >= tpb || g >= ntiles) return;
+// not share one range law, or rows with NaN calibration constants).  64 us on cfg2 (3.7 % of the step); staging the
+// 192-byte row records through shared memory for coalesced loads measured slower (81 us: too few loads in flight).
+__global__ void prepare_kernel(const epb_row* __restrict__ rows, const int* __restrict__ xbin, long long P, long long nX,
+                               int T, int nPt, long long ntiles, int sv_input, TileInfo* __restrict__ tiles,
+                               int* __restrict__ irregular) {
+  const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (g >= ntiles) return;
   const long long c = g / nPt;
   const int itile = (int)(g - c * nPt);
   const long long p0 = (long long)itile * T;
   const int Ta = (int)((p0 + T <= P) ? T : (P - p0));
-  const epb_row* r0 = reinterpret_cast<const epb_row*>(s_prep) + (c * P + p0 - rb);
+  const epb_row* r0 = rows + c * P + p0;
   TileInfo ti;
   bool bad = false;
   int nruns = 0, prev_xb = 0, rcsame = 1;
@@ -854,13 +834,8 @@ int epb_pipeline_fast_try(const void* x, int x_i16, const epb_row* rows, const i
   pr.sv_input = sv_input;
   if (workspace_bytes < 256 + pr.ntiles * (long long)sizeof(TileInfo)) return 0;
   if (cudaMemsetAsync(irregular, 0, sizeof(int), s) != cudaSuccess) return 0;
-  {
-    const int max_rows = 48 * 1024 / (int)sizeof(epb_row);  // 256 row records of shared memory
-    int tpb = max_rows / T - 1;
-    tpb = tpb > 128 ? 128 : tpb;
-    prepare_kernel<<<(unsigned)((pr.ntiles + tpb - 1) / tpb), 128, (size_t)(tpb + 1) * T * sizeof(epb_row), s>>>(
-        rows, xbin, P, nX, T, pr.nPt, pr.ntiles, C * P, tpb, sv_input, const_cast<TileInfo*>(pr.tiles), irregular);
-  }
+  prepare_kernel<<<(unsigned)((pr.ntiles + 127) / 128), 128, 0, s>>>(rows, xbin, P, nX, T, pr.nPt, pr.ntiles, sv_input,
+                                                                     const_cast<TileInfo*>(pr.tiles), irregular);
   int rc = -1;
 #define EPB_FAST_G(TT, NZ, I16) ((G != 1) ? launch_fast<TT, EPB_GBIG, NZ, I16>(pr, threads, smem, s) : launch_fast<TT, 1, NZ, I16>(pr, threads, smem, s))
 #define EPB_FAST(TT)                                                            \
