@@ -115,32 +115,37 @@ __global__ void __launch_bounds__(256) block_mean_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) impulse_mask_kernel(const float* __restrict__ U, const int* __restrict__ nsamp,
                                                            unsigned char* __restrict__ mask, long long nrows, long long P,
                                                            int R, int nbmax, int k, float thr) {
+  extern __shared__ unsigned char s_flag[];  // [nbmax] mask value of every block of the row
   for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
     const long long c = row / P, p = row - c * P;
     const int n = nsamp[c];
+    const int nb = (R + n - 1) / n;
     const float* u0 = U + row * nbmax;
     const float* uf = (p + k < P) ? U + (row + k) * nbmax : nullptr;
     const float* ub = (p - k >= 0) ? U + (row - k) * nbmax : nullptr;
-    unsigned char* m = mask + row * (long long)R;
-    auto flag = [&](int b) -> unsigned {
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
       const float v = u0[b];
       float f = v - (uf ? uf[b] : CUDART_NAN_F), w = v - (ub ? ub[b] : CUDART_NAN_F);
       f = (f == f) ? f : CUDART_INF_F;
       w = (w == w) ? w : CUDART_INF_F;
-      return (f > thr && w > thr) ? 1u : 0u;
-    };
-    // 16 consecutive samples per thread and step (one 16-byte store when the row allows it); the block index advances
-    // with a counter instead of a division per sample
+      s_flag[b] = (f > thr && w > thr) ? 1 : 0;
+    }
+    __syncthreads();
+    // forward fill: 16 consecutive samples per thread and step (one 16-byte store when the row allows it); the block
+    // index advances with a counter instead of a division per sample
+    unsigned char* m = mask + row * (long long)R;
     const bool vec = ((R & 15) == 0);
     for (int j0 = threadIdx.x * 16; j0 < R; j0 += blockDim.x * 16) {
       int b = j0 / n, rem = j0 - b * n;
-      unsigned fl = flag(b);
+      unsigned fl = s_flag[b];
       unsigned wv[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        if (j0 + i < R) {
-          wv[i >> 2] |= fl << (8 * (i & 3));
-          if (++rem == n && j0 + i + 1 < R) rem = 0, fl = flag(++b);
+        wv[i >> 2] |= fl << (8 * (i & 3));
+        if (++rem == n) {
+          rem = 0;
+          ++b;
+          fl = (b < nb) ? s_flag[b] : 0u;
         }
       }
       if (vec) {
@@ -149,6 +154,7 @@ __global__ void __launch_bounds__(256) impulse_mask_kernel(const float* __restri
         for (int i = 0; i < 16 && j0 + i < R; ++i) m[j0 + i] = (unsigned char)((wv[i >> 2] >> (8 * (i & 3))) & 0xffu);
       }
     }
+    __syncthreads();
   }
 }
 
@@ -289,7 +295,7 @@ extern "C" int epb_impulse_noise_mask(const float* Sv, const int* nsamp, float* 
       cudaFuncSetAttribute(block_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return epb_check_launch("epb_impulse_noise_mask(smem)");
   block_mean_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(Sv, nsamp, block_means, nrows, P, (int)R, nbmax);
-  impulse_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(block_means, nsamp, mask, nrows, P, (int)R, nbmax,
+  impulse_mask_kernel<<<grid, 256, (size_t)((nbmax + 15) & ~15), (cudaStream_t)stream>>>(block_means, nsamp, mask, nrows, P, (int)R, nbmax,
                                                               num_side_pings, threshold);
   return epb_check_launch("epb_impulse_noise_mask");
 }
