@@ -1,0 +1,4 @@
+// Instantiations of the persistent fused kernel (pipeline_fast_impl.cuh): int16 raw counts, ping_num in {1, 2, 3, 4} and the variant without noise removal.
+#include "pipeline_fast_impl.cuh"
+
+EPB_DEFINE_FAST_LAUNCHER(epb_fast_launch_i16a, true, 1, 2, 3, 4, true)
