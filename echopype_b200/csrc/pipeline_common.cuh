@@ -1,4 +1,4 @@
-// Helpers shared by the fused pipeline kernels (pipeline.cu: general kernel, pipeline_fast.cu: register-resident
+// Helpers shared by the fused pipeline kernels (pipeline.cu: general kernel, pipeline_fast_impl.cuh: register-resident
 // persistent kernel): range-only column terms, exact bin-boundary search, TMA / mbarrier wrappers.
 #pragma once
 #include "sample_math.cuh"

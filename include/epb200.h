@@ -197,7 +197,7 @@ int epb_coarsen(const float* Sv, const float* echo_range, float* out, float* er_
  * epb_pipeline_workspace_bytes(C, P, ping_num) bytes owned by the caller and private to this launch (it receives
  * one 144-byte descriptor per ping tile); with a workspace, regular volumes (every ping tile shares one range law, finite
  * calibration constants, R <= 4096, ping_num <= 8, no full-size outputs) run on the persistent
- * register-resident kernel (pipeline_fast.cu), decided on the device without a host synchronisation. */
+ * register-resident kernel (pipeline_fast_impl.cuh), decided on the device without a host synchronisation. */
 int epb_pipeline_power_mvbs(const float* backscatter_r, const epb_row* rows, const int* xbin,
                             const double* r_edges, int nR, int closed_right, double* acc, float* noise_out,
                             float* Sv, float* echo_range, float* Sv_noise, float* Sv_corrected, epb_i64 C,

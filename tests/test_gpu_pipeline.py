@@ -222,7 +222,7 @@ FAST_CASES = [
 
 @pytest.mark.parametrize("kind,shape,tv,pn,rn,nmax,rb,tb,closed", FAST_CASES)
 def test_fast_kernel_equals_general_kernel(ep, kind, shape, tv, pn, rn, nmax, rb, tb, closed):
-    """The persistent register-resident kernel (pipeline_fast.cu) against the general kernel (pipeline.cu) on the raw
+    """The persistent register-resident kernel (pipeline_fast_impl.cuh) against the general kernel (pipeline.cu) on the raw
     accumulators: member / NaN-member counts bit-identical, linear sums within float32 accumulation noise."""
     from echopype_b200 import synth
 
