@@ -41,6 +41,7 @@ SIGNATURES = {
     "epb_rows_azfp": (c_int, [vp, i64, i64, i64, c_int, epb_cp, epb_cp, epb_cp] + [vp] * 9 + [vp]),
     "epb_rows_ek80_complex": (c_int, [vp, i64, i64, i64, c_int, c_int, c_int] + [epb_cp] * 12 + [vp, vp]),
     "epb_sv_power": (c_int, [vp, vp, vp, vp, vp, i64, i64, i64, vp]),
+    "epb_sv_power_i16": (c_int, [vp, vp, vp, vp, vp, i64, i64, i64, vp]),
     "epb_sv_complex": (c_int, [vp, vp, vp, vp, vp, vp, i64, i64, i64, c_int, vp]),
     "epb_pulse_compress_sv": (c_int, [vp, vp, vp, POINTER(c_int), vp, vp, vp, vp, vp, vp, i64, i64, i64, c_int, vp]),
     "epb_noise_estimate": (c_int, [vp, vp, epb_cp, vp, i64, i64, i64, c_int, c_int, c_float, vp]),

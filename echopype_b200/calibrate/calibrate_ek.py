@@ -233,7 +233,7 @@ class CalibrateEK(CalibrateBase):
         C, P, R = rb.shape
         tau_effective = rb.tau_effective
         rows = rb.build()
-        x = kernels.power_to_device_f32(self.beam["backscatter_r"].data)  # float32 dB, or int16 raw counts (ingest)
+        x = kernels.power_to_device_f32(self.beam["backscatter_r"].data, keep_counts=True)  # float32 dB, or int16 raw counts
         self.rows = rows
         return rows, x, C, P, R, tau_effective
 

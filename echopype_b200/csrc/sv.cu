@@ -19,15 +19,28 @@ __device__ __forceinline__ float sample_out(const RowF& rc, int n, float nf, flo
   return sv_db(rc, n, nf, frK);
 }
 
-template <bool kRange, bool kMinMax>
-__global__ void __launch_bounds__(256) sv_power_vec4(const float* __restrict__ x, const epb_row* __restrict__ rows,
+// four consecutive input samples as float32 dB: float32 input as stored, or int16 raw power counts (SURVEY.md 8f rank 4:
+// K1 reads 2 bytes per sample; count_to_db_f, -32768 = NaN padding, the values epb_ingest_power_i16 would write)
+__device__ __forceinline__ float4 load_quad(const float* row, int j) { return ld_stream4(reinterpret_cast<const float4*>(row) + j); }
+__device__ __forceinline__ float4 load_quad(const short* row, int j) {
+  unsigned lo, hi;
+  asm volatile("ld.global.cs.v2.u32 {%0,%1}, [%2];" : "=r"(lo), "=r"(hi) : "l"(reinterpret_cast<const uint2*>(row) + j));
+  const short q[4] = {(short)(lo & 0xffffu), (short)(lo >> 16), (short)(hi & 0xffffu), (short)(hi >> 16)};
+  float v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = (q[k] == (short)-32768) ? CUDART_NAN_F : count_to_db_f((float)q[k]);
+  return make_float4(v[0], v[1], v[2], v[3]);
+}
+
+template <bool kRange, bool kMinMax, typename XT>
+__global__ void __launch_bounds__(256) sv_power_vec4(const XT* __restrict__ x, const epb_row* __restrict__ rows,
                                                      float* __restrict__ out, float* __restrict__ rng,
                                                      float* __restrict__ minmax, long long nrows, int R) {
   const int R4 = R >> 2;
   MinMax mm_v, mm_r;
   for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
     const RowF rc = load_rowf(rows + row);
-    const float4* xin = reinterpret_cast<const float4*>(x + row * (long long)R);
+    const XT* xin = x + row * (long long)R;
     float4* o4 = reinterpret_cast<float4*>(out + row * (long long)R);
     float4* r4 = kRange ? reinterpret_cast<float4*>(rng + row * (long long)R) : nullptr;
     for (int j0 = threadIdx.x; j0 < R4; j0 += 4 * blockDim.x) {
@@ -35,7 +48,7 @@ __global__ void __launch_bounds__(256) sv_power_vec4(const float* __restrict__ x
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         int j = j0 + u * blockDim.x;
-        if (j < R4) v[u] = ld_stream4(xin + j);
+        if (j < R4) v[u] = load_quad(xin, j);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -66,7 +79,7 @@ __global__ void __launch_bounds__(256) sv_power_vec4(const float* __restrict__ x
 }
 
 // scalar fallback for R % 4 != 0 or unaligned bases (ragged last dimension)
-template <bool kRange, bool kMinMax>
+template <bool kRange, bool kMinMax, typename XT = float>
 __global__ void __launch_bounds__(256) sv_power_scalar(const float* __restrict__ x, const epb_row* __restrict__ rows,
                                                        float* __restrict__ out, float* __restrict__ rng,
                                                        float* __restrict__ minmax, long long nrows, int R) {
@@ -178,23 +191,39 @@ extern "C" int epb_sv_power(const float* x, const epb_row* rows, float* out, flo
   const long long nrows = C * P;
   const int grid = (int)((nrows < (long long)epb_num_sms() * 8) ? nrows : (long long)epb_num_sms() * 8);
   const bool vec = (R % 4 == 0) && (((uintptr_t)x | (uintptr_t)out | (uintptr_t)echo_range) % 16 == 0);
+  using XT = float;
 #define EPB_LAUNCH(K)                                                                              \
   do {                                                                                             \
     if (echo_range && minmax)                                                                      \
-      K<true, true><<<grid, 256, 0, s>>>(x, rows, out, echo_range, minmax, nrows, (int)R);         \
+      K<true, true, XT><<<grid, 256, 0, s>>>(x, rows, out, echo_range, minmax, nrows, (int)R);         \
     else if (echo_range)                                                                           \
-      K<true, false><<<grid, 256, 0, s>>>(x, rows, out, echo_range, minmax, nrows, (int)R);        \
+      K<true, false, XT><<<grid, 256, 0, s>>>(x, rows, out, echo_range, minmax, nrows, (int)R);        \
     else if (minmax)                                                                               \
-      K<false, true><<<grid, 256, 0, s>>>(x, rows, out, echo_range, minmax, nrows, (int)R);        \
+      K<false, true, XT><<<grid, 256, 0, s>>>(x, rows, out, echo_range, minmax, nrows, (int)R);        \
     else                                                                                           \
-      K<false, false><<<grid, 256, 0, s>>>(x, rows, out, echo_range, minmax, nrows, (int)R);       \
+      K<false, false, XT><<<grid, 256, 0, s>>>(x, rows, out, echo_range, minmax, nrows, (int)R);       \
   } while (0)
   if (vec)
     EPB_LAUNCH(sv_power_vec4);
   else
     EPB_LAUNCH(sv_power_scalar);
-#undef EPB_LAUNCH
   return epb_check_launch("epb_sv_power");
+}
+
+extern "C" int epb_sv_power_i16(const short* counts, const epb_row* rows, float* out, float* echo_range, float* minmax,
+                                epb_i64 C, epb_i64 P, epb_i64 R, void* stream) {
+  EPB_REQUIRE(counts && rows && out, "NULL pointer");
+  EPB_REQUIRE(C > 0 && P > 0 && R > 0 && R < (1LL << 30), "bad shape");
+  EPB_REQUIRE(R % 4 == 0 && ((uintptr_t)counts % 8) == 0 && (((uintptr_t)out | (uintptr_t)echo_range) % 16) == 0,
+              "the int16 kernel needs range_sample % 4 == 0 and aligned arrays (epb_ingest_power_i16 + epb_sv_power otherwise)");
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long nrows = C * P;
+  const int grid = (int)((nrows < (long long)epb_num_sms() * 8) ? nrows : (long long)epb_num_sms() * 8);
+  const short* x = counts;
+  using XT = short;
+  EPB_LAUNCH(sv_power_vec4);
+#undef EPB_LAUNCH
+  return epb_check_launch("epb_sv_power_i16");
 }
 
 extern "C" int epb_sv_complex(const float* re, const float* im, const epb_row* rows, float* out, float* echo_range,

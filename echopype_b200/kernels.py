@@ -99,7 +99,9 @@ def sv_power(x, rows, C, P, R, want_range=True, want_minmax=False, out=None, rng
     out = out if out is not None else empty((C, P, R), device=x.device)
     rng = rng if rng is not None else (empty((C, P, R), device=x.device) if want_range else None)
     mm = new_minmax(x.device) if want_minmax else None
-    _lib.call("epb_sv_power", ptr(x), ptr(rows), ptr(out), ptr(rng), ptr(mm), C, P, R, stream())
+    # int16 raw power counts (ingest format) are read directly, 2 bytes per sample, when the row length allows it
+    name = "epb_sv_power_i16" if x.dtype == torch.int16 else "epb_sv_power"
+    _lib.call(name, ptr(x), ptr(rows), ptr(out), ptr(rng), ptr(mm), C, P, R, stream())
     return out, rng, mm
 
 
@@ -341,7 +343,7 @@ def is_raw_counts(x):
     return getattr(x, "dtype", None) in (torch.int16, np.dtype("int16"))
 
 
-def power_to_device_f32(x):
+def power_to_device_f32(x, keep_counts=False):
     """Power samples -> float32 CUDA tensor.  int16 raw counts cross PCIe as they are (2 bytes per sample) and are
     converted on the device (epb_ingest_power_i16); float data goes through :func:`device.to_device_f32`."""
     from .device import to_device_f32
@@ -350,7 +352,10 @@ def power_to_device_f32(x):
     if not is_raw_counts(data):
         return to_device_f32(data)
     t = data if isinstance(data, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(data))
-    return ingest_power_i16(t.to(require_cuda(), non_blocking=True).contiguous())
+    t = t.to(require_cuda(), non_blocking=True).contiguous()
+    if keep_counts and t.shape[-1] % 4 == 0:
+        return t  # K1 (epb_sv_power_i16) reads the counts itself
+    return ingest_power_i16(t)
 
 
 def synth_fill_i16(shape_cpr, seed, ping_offset=0, nan_tail=0.005, device=None):

@@ -126,6 +126,11 @@ int epb_rows_ek80_complex(epb_row* rows, epb_i64 C, epb_i64 P, epb_i64 R, int ca
 int epb_sv_power(const float* backscatter_r, const epb_row* rows, float* out, float* echo_range,
                  float* minmax, epb_i64 C, epb_i64 P, epb_i64 R, void* stream);
 
+/* K1 on RAW POWER COUNTS: counts [C,P,R] int16 (-32768 = NaN padding) are scaled by INDEX2POWER in
+ * registers (the values epb_ingest_power_i16 writes), so the kernel reads 2 bytes per sample.  Needs R % 4 == 0. */
+int epb_sv_power_i16(const short* counts, const epb_row* rows, float* out, float* echo_range, float* minmax, epb_i64 C,
+                     epb_i64 P, epb_i64 R, void* stream);
+
 /* ---- K2: complex CW samples (CalibrateEK80._get_power_from_complex calibrate_ek.py:456-505 without
  *      pulse compression + _cal_complex_samples).  re/im: [C,P,R,B] float32, B <= 4. ------------------- */
 int epb_sv_complex(const float* re, const float* im, const epb_row* rows, float* out, float* echo_range,

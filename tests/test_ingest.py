@@ -141,11 +141,15 @@ def test_fused_pipeline_on_counts_equals_float_path(ep, shape, tv, pn, rn, rb, t
 
 
 @pytest.mark.gpu
-def test_compute_Sv_accepts_raw_counts(ep):
+@pytest.mark.parametrize("R", [500, 502])  # K1 reads the counts itself (R % 4 == 0) / ingest kernel first
+def test_compute_Sv_accepts_raw_counts(ep, R):
     from echopype_b200 import synth
 
     rng = np.random.default_rng(9)
-    q = synth._power_host(rng, 2, 30, 500, 0.2, raw_counts=True)
-    ds_q = ep.calibrate.compute_Sv(synth.make_ek60(2, 30, 500, seed=9, backscatter=q))
-    ds_f = ep.calibrate.compute_Sv(synth.make_ek60(2, 30, 500, seed=9, backscatter=oconv.ingest_power_i16(q)))
-    np.testing.assert_array_equal(ds_q["Sv"].values.view(np.uint32), ds_f["Sv"].values.view(np.uint32))
+    q = synth._power_host(rng, 2, 30, R, 0.2, raw_counts=True)
+    for fn in (ep.calibrate.compute_Sv, ep.calibrate.compute_TS):
+        ds_q = fn(synth.make_ek60(2, 30, R, seed=9, backscatter=q))
+        ds_f = fn(synth.make_ek60(2, 30, R, seed=9, backscatter=oconv.ingest_power_i16(q)))
+        name = "Sv" if "Sv" in ds_q else "TS"
+        np.testing.assert_array_equal(ds_q[name].values.view(np.uint32), ds_f[name].values.view(np.uint32))
+        np.testing.assert_array_equal(ds_q["echo_range"].values.view(np.uint32), ds_f["echo_range"].values.view(np.uint32))

@@ -183,6 +183,8 @@ def extra(a, which, C, P, R, n, x, rows, out, rng, ed):
         report("pipeline_i16(sv->mvbs)", ms, mn, 2 * n, n)
         ms, mn = timeit(lambda: kernels.ingest_power_i16(q, out=out), a.iters)
         report("ingest_power_i16", ms, mn, 6 * n, n)
+        ms, mn = timeit(lambda: kernels.sv_power(q, rows, C, P, R, want_range=False, out=out), a.iters)
+        report("sv_power_i16 (K1 on raw counts)", ms, mn, 6 * n, n)
 
 
 if __name__ == "__main__":
