@@ -78,6 +78,59 @@ __global__ void __launch_bounds__(256) sv_power_vec4(const XT* __restrict__ x, c
   }
 }
 
+// K1 on raw counts with rows of R % 8 == 0: one 16-byte load (eight int16 counts) per thread and step, four in flight
+template <bool kRange, bool kMinMax>
+__global__ void __launch_bounds__(256) sv_power_i16_vec8(const short* __restrict__ x, const epb_row* __restrict__ rows,
+                                                         float* __restrict__ out, float* __restrict__ rng,
+                                                         float* __restrict__ minmax, long long nrows, int R) {
+  const int R8 = R >> 3;
+  MinMax mm_v, mm_r;
+  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const RowF rc = load_rowf(rows + row);
+    const int4* xin = reinterpret_cast<const int4*>(x + row * (long long)R);
+    float4* o4 = reinterpret_cast<float4*>(out + row * (long long)R);
+    float4* r4 = kRange ? reinterpret_cast<float4*>(rng + row * (long long)R) : nullptr;
+    for (int j0 = threadIdx.x; j0 < R8; j0 += 4 * blockDim.x) {
+      int4 w[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * blockDim.x;
+        if (j < R8) asm volatile("ld.global.cs.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(w[u].x), "=r"(w[u].y), "=r"(w[u].z), "=r"(w[u].w) : "l"(xin + j));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * blockDim.x;
+        if (j >= R8) break;
+        const int ws[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+        float o[8], rr[8];
+        const float nf0 = (float)(8 * j);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const short q = (short)((k & 1) ? (ws[k >> 1] >> 16) : (ws[k >> 1] & 0xffff));
+          const float in = (q == (short)-32768) ? CUDART_NAN_F : count_to_db_f((float)q);
+          const float fr = fmaf(in, rc.fscale, rc.foffK);
+          o[k] = sample_out(rc, 8 * j + k, nf0 + (float)k, fr, rr[k]);
+          if (rc.nanrange && in != in) rr[k] = CUDART_NAN_F;  // range.py:143-148
+          if (kMinMax) {
+            mm_v.add(o[k]);
+            mm_r.add(rr[k]);
+          }
+        }
+        st_stream4(o4 + 2 * j, make_float4(o[0], o[1], o[2], o[3]));
+        st_stream4(o4 + 2 * j + 1, make_float4(o[4], o[5], o[6], o[7]));
+        if (kRange) {
+          st_stream4(r4 + 2 * j, make_float4(rr[0], rr[1], rr[2], rr[3]));
+          st_stream4(r4 + 2 * j + 1, make_float4(rr[4], rr[5], rr[6], rr[7]));
+        }
+      }
+    }
+  }
+  if (kMinMax) {
+    mm_v.flush(minmax + 0, minmax + 1);
+    mm_r.flush(minmax + 2, minmax + 3);
+  }
+}
+
 // scalar fallback for R % 4 != 0 or unaligned bases (ragged last dimension)
 template <bool kRange, bool kMinMax, typename XT = float>
 __global__ void __launch_bounds__(256) sv_power_scalar(const float* __restrict__ x, const epb_row* __restrict__ rows,
@@ -221,7 +274,18 @@ extern "C" int epb_sv_power_i16(const short* counts, const epb_row* rows, float*
   const int grid = (int)((nrows < (long long)epb_num_sms() * 8) ? nrows : (long long)epb_num_sms() * 8);
   const short* x = counts;
   using XT = short;
-  EPB_LAUNCH(sv_power_vec4);
+  if (R % 8 == 0 && ((uintptr_t)counts % 16) == 0) {
+    if (echo_range && minmax)
+      sv_power_i16_vec8<true, true><<<grid, 256, 0, s>>>(x, rows, out, echo_range, minmax, nrows, (int)R);
+    else if (echo_range)
+      sv_power_i16_vec8<true, false><<<grid, 256, 0, s>>>(x, rows, out, echo_range, minmax, nrows, (int)R);
+    else if (minmax)
+      sv_power_i16_vec8<false, true><<<grid, 256, 0, s>>>(x, rows, out, echo_range, minmax, nrows, (int)R);
+    else
+      sv_power_i16_vec8<false, false><<<grid, 256, 0, s>>>(x, rows, out, echo_range, minmax, nrows, (int)R);
+  } else {
+    EPB_LAUNCH(sv_power_vec4);
+  }
 #undef EPB_LAUNCH
   return epb_check_launch("epb_sv_power_i16");
 }

@@ -141,7 +141,7 @@ def test_fused_pipeline_on_counts_equals_float_path(ep, shape, tv, pn, rn, rb, t
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("R", [500, 502])  # K1 reads the counts itself (R % 4 == 0) / ingest kernel first
+@pytest.mark.parametrize("R", [504, 500, 502])  # K1 reads the counts itself (R % 8 == 0, R % 4 == 0) / ingest kernel first
 def test_compute_Sv_accepts_raw_counts(ep, R):
     from echopype_b200 import synth
 
