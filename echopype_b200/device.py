@@ -76,7 +76,7 @@ class ParamPack:
                 a2, sc, sp = np.ascontiguousarray(a), P, 1
         else:
             raise ValueError(f"parameter of shape {a.shape} does not broadcast to (channel={C}, ping_time={P})")
-        t = torch.from_numpy(np.ascontiguousarray(a2)).to(self.device)
+        t = torch.from_numpy(np.array(a2, dtype=np.float64, order="C", copy=True)).to(self.device)  # (C,)/(C,P) parameters: tiny; copy makes read-only views writable for torch
         self._keep.append(t)
         return epb_cp(t.data_ptr(), sc, sp)
 
