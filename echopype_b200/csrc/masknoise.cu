@@ -229,6 +229,8 @@ __global__ void __launch_bounds__(256) pool_rows_kernel(const float* __restrict_
 // ---- transient noise, step 2: sliding sum of the row windows over pings [p - k, p + k] (reflected), pooled Sv =
 //      10 log10(sum / count), mask = Sv - pooled > threshold (clean/api.py:163-166); samples above m0 are never
 //      masked (pooled NaN, clean/utils.py:174-176).  Thread per column and chunk of pings, float64 running sums. -----
+// (a row of the (sum, count) intermediate is read twice, 2 k + 1 pings apart; L2 evict_last / evict_first cache-hint
+// policies on the two reads measured slower: 11.3 -> 12.2 ms, as did capping the resident CTAs)
 __global__ void __launch_bounds__(128) pool_pings_mask_kernel(const float2* __restrict__ S1, const float* __restrict__ Sv,
                                                               unsigned char* __restrict__ mask, float* __restrict__ pooled,
                                                               long long P, int R, int m0, int k, float thr, int chunk) {
@@ -252,7 +254,7 @@ __global__ void __launch_bounds__(128) pool_pings_mask_kernel(const float2* __re
   }
   for (long long p = p0; p < p1; ++p) {
     const float pv = (m > 0.0) ? 10.f * log10f((float)(s / m)) : CUDART_NAN_F;
-    const float sv = Sv[base + p * R];
+    const float sv = ld_stream(Sv + base + p * R);
     mask[base + p * R] = (sv - pv > thr) ? 1 : 0;
     if (pooled) pooled[base + p * R] = pv;
     const float2 in = S1[base + refl(p + k + 1) * R], out = S1[base + refl(p - k) * R];
