@@ -52,21 +52,34 @@ def _compute_cal(cal_type, echodata: EchoData, env_params=None, cal_params=None,
     if echodata.sonar_model not in CALIBRATOR:
         raise ValueError(f"Unsupported sonar_model {echodata.sonar_model!r}")
 
-    if echodata.sonar_model in ["EK80", "ES80", "EA640"]:
-        vend = echodata["Vendor_specific"]
-        if "filter_time" in vend.sizes and vend.sizes["filter_time"] > 1 and not assume_single_filter_time:
-            # calibrate/api.py:128-197 splits per (channel, filter_time) and outer-joins the pieces; that
-            # control-plane path is not on the accelerated array path (SURVEY.md 8a #a1)
-            raise NotImplementedError(
-                "Multiple filter_time entries: pass assume_single_filter_time=True (first filter set is used)."
-            )
+    def _compute_cal_ds(ed, slice_dict):
+        cal_obj = CALIBRATOR[ed.sonar_model](
+            ed, env_params=env_params, cal_params=cal_params, ecs_file=ecs_file, waveform_mode=waveform_mode,
+            encode_mode=encode_mode, drop_last_hanning_zero=drop_last_hanning_zero, slice_dict=slice_dict,
+        )
+        cal_obj._check_echodata_backscatter_size()
+        return cal_obj.compute_Sv() if cal_type == "Sv" else cal_obj.compute_TS()
 
-    cal_obj = CALIBRATOR[echodata.sonar_model](
-        echodata, env_params=env_params, cal_params=cal_params, ecs_file=ecs_file, waveform_mode=waveform_mode,
-        encode_mode=encode_mode, drop_last_hanning_zero=drop_last_hanning_zero, slice_dict={},
-    )
-    cal_obj._check_echodata_backscatter_size()
-    cal_ds = cal_obj.compute_Sv() if cal_type == "Sv" else cal_obj.compute_TS()
+    vend = echodata["Vendor_specific"] if echodata.sonar_model in ["EK80", "ES80", "EA640"] else None
+    if vend is None or "filter_time" not in vend.sizes or vend.sizes["filter_time"] == 1:
+        cal_ds = _compute_cal_ds(echodata, {})
+    else:  # several filter sets, calibrate/api.py:101-197
+        from . import filter_time as ft
+        from .calibrate_ek import retrieve_correct_beam_group
+
+        beam_group = retrieve_correct_beam_group(echodata, waveform_mode, encode_mode)
+        beam = echodata[beam_group]
+        if assume_single_filter_time:
+            first_valid = ft.first_valid_filter_time_per_channel(beam)
+            ed = ft._with_groups(echodata)
+            ed["Vendor_specific"] = ft.collapse_vend(vend, first_valid)
+            cal_ds = _compute_cal_ds(ed, {"first_valid_filter_time_per_channel": first_valid})
+        else:
+            pieces = [
+                _compute_cal_ds(ft.piece_echodata(echodata, beam_group, ci, p_idx, fi), {"channel": ci, "filter_time": fi})
+                for ci, p_idx, fi in ft.filter_pieces(beam, vend)
+            ]
+            cal_ds = ft.merge_pieces(pieces)
 
     # attributes, calibrate/api.py:200-219
     cal_ds["range_sample"].attrs.update({"long_name": "Along-range sample number, base 0"})

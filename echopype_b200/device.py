@@ -81,7 +81,7 @@ class ParamPack:
         return epb_cp(t.data_ptr(), sc, sp)
 
     def vec(self, x, dtype=torch.float64):
-        a = np.ascontiguousarray(np.asarray(getattr(x, "values", x)))
+        a = np.array(np.asarray(getattr(x, "values", x)), order="C", copy=True)  # small; read-only views become writable
         t = torch.from_numpy(a).to(self.device).to(dtype)
         self._keep.append(t)
         return ctypes.c_void_p(t.data_ptr())

@@ -210,3 +210,70 @@ def test_argument_errors(ep):
         ep.calibrate.compute_Sv(ed60, assume_single_filter_time=True)
     with pytest.raises(ReferenceError):
         ep.calibrate.compute_Sv(synth.make_azfp(1, 2, 16))
+
+
+# ---- EK80 with several filter_time entries (calibrate/api.py:95-197) --------------------------------------------------
+def _multi_filter_ed(second_same=True, mux=False):
+    """EK80 BB volume whose Vendor_specific carries two filter sets: at the first ping and at ping 7."""
+    from echopype_b200 import synth
+    from echopype_b200.dataset import Dataset
+
+    ed = synth.make_ek80(C=2, P=12, R=256, B=4, mode="BB", encode="complex", nan_tail=0.2, seed=17)
+    vend, beam = ed["Vendor_specific"], ed["Sonar/Beam_group1"]
+    pt = np.asarray(beam["ping_time"].values)
+    new = {}
+    for name in vend:
+        v = vend[name]
+        a = np.asarray(v.values)
+        if "filter_time" in v.dims:
+            ax = list(v.dims).index("filter_time")
+            b = a.copy()
+            if not second_same and name.startswith("PC_coeffs"):
+                b = b * 0.5 + 0.01
+            a = np.concatenate([a, b], axis=ax)
+        new[name] = (tuple(v.dims), a)
+    coords = {k: np.asarray(c.values) for k, c in vend.coords.items() if k != "filter_time"}
+    coords["filter_time"] = pt[[1 if mux else 0, 7]]
+    ed["Vendor_specific"] = Dataset(new, coords=coords)
+    if mux:  # channel-dependent first valid ping (multiplexed transceivers)
+        tau = np.asarray(beam["transmit_duration_nominal"].values, dtype=np.float64).copy()
+        tau[:, 0] = np.nan
+        beam["transmit_duration_nominal"] = (("channel", "ping_time"), tau)
+    return ed
+
+
+def test_ek80_multiple_filter_times_equal_single_when_filters_repeat(ep):
+    """The same filter set re-sent mid-file (what combining files produces): the piecewise calibration merged back
+    together equals the one-shot calibration, channels in sorted order."""
+    from echopype_b200 import synth
+
+    ed1 = synth.make_ek80(C=2, P=12, R=256, B=4, mode="BB", encode="complex", nan_tail=0.2, seed=17)
+    want = ep.calibrate.compute_Sv(ed1, waveform_mode="BB", encode_mode="complex")
+    got = ep.calibrate.compute_Sv(_multi_filter_ed(), waveform_mode="BB", encode_mode="complex")
+    order = np.argsort([str(c) for c in want["channel"].values])
+    assert list(got["channel"].values) == [want["channel"].values[i] for i in order]
+    np.testing.assert_array_equal(got["ping_time"].values, want["ping_time"].values)
+    for name in ("Sv", "echo_range"):
+        a, b = got[name].values, want[name].values[order]
+        np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
+    np.testing.assert_allclose(got["tau_effective"].values, want["tau_effective"].values[order], rtol=0)
+    # assume_single_filter_time: one pass with the collapsed filter table, same numbers
+    one = ep.calibrate.compute_Sv(_multi_filter_ed(), waveform_mode="BB", encode_mode="complex", assume_single_filter_time=True)
+    np.testing.assert_array_equal(one["Sv"].values.view(np.uint32), want["Sv"].values[order].view(np.uint32))
+
+
+def test_ek80_multiple_filter_times_conflict_and_missing(ep):
+    # differing filter sets give per-channel tau_effective values that xr.merge(compat="no_conflicts") refuses
+    with pytest.raises(ValueError, match="conflicting values for variable 'tau_effective'"):
+        ep.calibrate.compute_Sv(_multi_filter_ed(second_same=False), waveform_mode="BB", encode_mode="complex")
+    # assume_single_filter_time picks the filter set AT each channel's first valid ping (ping 1 here)
+    ed = _multi_filter_ed(second_same=False, mux=True)
+    one = ep.calibrate.compute_Sv(ed, waveform_mode="BB", encode_mode="complex", assume_single_filter_time=True)
+    assert np.isnan(one["Sv"].values[:, 0]).all() and not np.isnan(one["Sv"].values[:, 1]).all()
+    # ... and fails like Dataset.sel when no filter set was recorded at that ping
+    bad = _multi_filter_ed(mux=True)
+    bad["Vendor_specific"]._set_coord("filter_time", np.asarray(bad["Sonar/Beam_group1"]["ping_time"].values)[[0, 7]])
+    with pytest.raises(KeyError):
+        ep.calibrate.compute_Sv(bad, waveform_mode="BB", encode_mode="complex", assume_single_filter_time=True)
+    with pytest.raises(ValueError, match="assume_single_filter_time can only be used on complex EK80 data."):
+        ep.calibrate.compute_Sv(_multi_filter_ed(), waveform_mode="CW", encode_mode="power", assume_single_filter_time=True)
