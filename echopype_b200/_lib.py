@@ -65,6 +65,7 @@ SIGNATURES = {
     "epb_add_depth": (c_int, [vp, epb_cp, epb_cp, vp, i64, i64, i64, vp]),
     "epb_freq_diff_mask": (c_int, [vp, c_int, c_int, c_int, c_float, vp, i64, i64, i64, vp]),
     "epb_apply_mask": (c_int, [vp, vp, c_int, c_float, vp, i64, i64, i64, vp]),
+    "epb_apply_mask_fill_array": (c_int, [vp, vp, c_int, vp, vp, i64, i64, i64, vp]),
     "epb_straddle_pack": (c_int, [vp, i64, i64, i64, vp, c_int, vp, c_int, c_int, c_int, vp]),
     "epb_straddle_unpack": (c_int, [vp, vp, c_int, c_int, i64, i64, i64, c_int, vp, vp, vp]),
     "epb_range_diff_mean": (c_int, [vp, vp, vp, i64, i64, i64, vp]),

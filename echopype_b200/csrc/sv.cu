@@ -435,11 +435,12 @@ __global__ void __launch_bounds__(256) freq_diff_kernel(const float* __restrict_
 }
 __global__ void __launch_bounds__(256) apply_mask_kernel(const float* __restrict__ src, const unsigned char* __restrict__ mask,
                                                          float* __restrict__ out, long long n, long long plane,
-                                                         int mask_has_channel, float fill) {
+                                                         int mask_has_channel, float fill, const float* __restrict__ fill_plane) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
-    const long long mi = mask_has_channel ? i : i % plane;
-    out[i] = mask[mi] ? ld_stream(src + i) : fill;
+    const long long pi = i % plane;
+    const long long mi = mask_has_channel ? i : pi;
+    out[i] = mask[mi] ? ld_stream(src + i) : (fill_plane ? fill_plane[pi] : fill);
   }
 }
 }  // namespace
@@ -456,16 +457,27 @@ extern "C" int epb_freq_diff_mask(const float* Sv, int chanA, int chanB, int op,
   return epb_check_launch("epb_freq_diff_mask");
 }
 
-extern "C" int epb_apply_mask(const float* src, const unsigned char* mask, int mask_has_channel, float fill_value, float* out,
-                              epb_i64 C, epb_i64 P, epb_i64 R, void* stream) {
+static int apply_mask_impl(const float* src, const unsigned char* mask, int mask_has_channel, float fill_value,
+                           const float* fill_plane, float* out, epb_i64 C, epb_i64 P, epb_i64 R, void* stream) {
   EPB_REQUIRE(src && mask && out, "NULL pointer");
   EPB_REQUIRE(C > 0 && P > 0 && R > 0, "bad shape");
   const long long n = C * P * R;
   long long blocks = (n + 255) / 256;
   const long long cap = (long long)epb_num_sms() * 16;
   apply_mask_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(src, mask, out, n, P * R,
-                                                                                            mask_has_channel, fill_value);
+                                                                                            mask_has_channel, fill_value, fill_plane);
   return epb_check_launch("epb_apply_mask");
+}
+
+extern "C" int epb_apply_mask(const float* src, const unsigned char* mask, int mask_has_channel, float fill_value, float* out,
+                              epb_i64 C, epb_i64 P, epb_i64 R, void* stream) {
+  return apply_mask_impl(src, mask, mask_has_channel, fill_value, nullptr, out, C, P, R, stream);
+}
+
+extern "C" int epb_apply_mask_fill_array(const float* src, const unsigned char* mask, int mask_has_channel,
+                                         const float* fill_plane, float* out, epb_i64 C, epb_i64 P, epb_i64 R, void* stream) {
+  EPB_REQUIRE(fill_plane, "NULL fill array");
+  return apply_mask_impl(src, mask, mask_has_channel, 0.f, fill_plane, out, C, P, R, stream);
 }
 
 extern "C" int epb_minmax(const float* a, epb_i64 n, float* minmax, void* stream) {

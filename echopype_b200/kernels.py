@@ -228,8 +228,12 @@ def freq_diff_mask(Sv, a, b, op, diff, C, P, R):
 
 
 def apply_mask(src, mask, has_channel, fill, C, P, R):
+    """fill: a number, or a float32 device tensor of shape (P, R) broadcast over channel."""
     out = empty((C, P, R), device=src.device)
-    _lib.call("epb_apply_mask", ptr(src), ptr(mask), int(bool(has_channel)), ctypes.c_float(float(fill)), ptr(out), C, P, R, stream())
+    if isinstance(fill, torch.Tensor):
+        _lib.call("epb_apply_mask_fill_array", ptr(src), ptr(mask), int(bool(has_channel)), ptr(fill), ptr(out), C, P, R, stream())
+    else:
+        _lib.call("epb_apply_mask", ptr(src), ptr(mask), int(bool(has_channel)), ctypes.c_float(float(fill)), ptr(out), C, P, R, stream())
     return out
 
 

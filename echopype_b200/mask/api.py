@@ -81,8 +81,8 @@ def apply_mask(source_ds, mask: Union[DataArray, List[DataArray]], var_name: str
     source_ds = as_dataset(source_ds)
     if var_name not in source_ds.variables:
         raise ValueError("The Dataset source_ds does not contain the variable var_name!")
-    if not isinstance(fill_value, (int, float)):
-        raise NotImplementedError("array-valued fill_value is outside the accelerated path")
+    if not isinstance(fill_value, (int, float, DataArray)):
+        raise TypeError("The input fill_value must be of type int, float, or xr.DataArray!")
     masks = list(mask) if isinstance(mask, (list, tuple)) else [mask]
     if not masks:
         raise ValueError("mask must contain at least one mask")
@@ -91,6 +91,14 @@ def apply_mask(source_ds, mask: Union[DataArray, List[DataArray]], var_name: str
         raise ValueError(f"source_ds[{var_name}] must have dims ('channel', 'ping_time', 'range_sample')")
     dev = require_cuda()
     C, P, R = src.shape
+    if isinstance(fill_value, DataArray):  # mask/api.py:233-246: squeeze a length-1 channel, shape of one channel of var_name
+        fdata = fill_value.data
+        fshape = tuple(int(n) for n in fdata.shape if int(n) != 1) if fdata.ndim > 2 else tuple(fdata.shape)
+        if fshape != (P, R):
+            raise ValueError(f"If fill_value is an array it must be of the same shape as {var_name}!")
+        fill = to_device_f32(fdata, dev).reshape(P, R).contiguous()
+    else:
+        fill = float(fill_value)
     out = to_device_f32(src.data, dev)
     for m in masks:
         mt, has_c = _mask_tensor(m, dev)
@@ -104,7 +112,7 @@ def apply_mask(source_ds, mask: Union[DataArray, List[DataArray]], var_name: str
                 f"If both the final constructed mask and source_ds[{var_name}] "
                 "have the channel dimension, that dimension should match between the two."
             )
-        out = kernels.apply_mask(out, mt, has_c, float(fill_value), C, P, R)
+        out = kernels.apply_mask(out, mt, has_c, fill, C, P, R)
     lo, hi, _ = kernels.minmax(out)
     attrs = dict(src.attrs)
     attrs.update({

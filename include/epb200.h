@@ -273,6 +273,9 @@ int epb_freq_diff_mask(const float* Sv, int chanA, int chanB, int op, float diff
                        epb_i64 P, epb_i64 R, void* stream);
 int epb_apply_mask(const float* src, const unsigned char* mask, int mask_has_channel, float fill_value, float* out,
                    epb_i64 C, epb_i64 P, epb_i64 R, void* stream);
+/* fill_value given as a (ping_time, range_sample) array, broadcast over channel (mask/api.py:233-246, xr.where :438) */
+int epb_apply_mask_fill_array(const float* src, const unsigned char* mask, int mask_has_channel, const float* fill_plane,
+                              float* out, epb_i64 C, epb_i64 P, epb_i64 R, void* stream);
 
 /* ---- helpers ---------------------------------------------------------------------------------------- */
 int epb_zero(void* ptr, epb_i64 nbytes, void* stream);

@@ -105,3 +105,13 @@ def test_apply_mask_gpu():
     assert ar == [round(float(np.nanmin(w2)), 2), round(float(np.nanmax(w2)), 2)]
     with pytest.raises(ValueError, match="is not of the same shape"):
         ep.mask.apply_mask(ds, ep.DataArray(m2[:, :-1], ("ping_time", "range_sample")))
+    # fill_value given as an array of the shape of one channel (mask/api.py:233-246), broadcast over channel
+    fill = rs.normal(-90.0, 1.0, size=Sv.shape[1:]).astype(np.float32)
+    got3 = ep.mask.apply_mask(ds, masks[:2], fill_value=ep.DataArray(fill[None], ("channel", "ping_time", "range_sample")))["Sv"].values
+    want3 = omask.apply_mask(Sv, [omask.frequency_differencing(Sv, 0, 1, ">", 1.0), m2], fill.astype(np.float64))
+    assert np.array_equal(np.isnan(got3), np.isnan(want3))
+    np.testing.assert_array_equal(np.nan_to_num(got3.astype(np.float64), nan=1.0), np.nan_to_num(want3, nan=1.0))
+    with pytest.raises(ValueError, match="If fill_value is an array it must be of the same shape as Sv!"):
+        ep.mask.apply_mask(ds, mfd, fill_value=ep.DataArray(fill[:, :-1], ("ping_time", "range_sample")))
+    with pytest.raises(TypeError, match="The input fill_value must be of type int, float, or xr.DataArray!"):
+        ep.mask.apply_mask(ds, mfd, fill_value="nan")
