@@ -127,9 +127,9 @@ def mask_impulse_noise(ds_Sv, depth_bin: str = "5m", num_side_pings: int = 2, im
     Locate and create a mask for impulse noise using a ping-wise two-sided comparison (Ryan et al. 2015; arguments
     as echopype.clean.mask_impulse_noise, clean/api.py:169-266).
 
-    The accelerated path is ``use_index_binning=True``: Sv is averaged (linear domain) over blocks of
-    ``ceil(depth_bin / mean sample spacing)`` range samples per channel, forward filled back to every sample and compared
-    with the pings ``num_side_pings`` before and after.  Returns a boolean (uint8 on the device) DataArray with dims
+    Sv is averaged in the linear domain over depth bins - intervals of ``range_var`` VALUES per ping (the default), or
+    with ``use_index_binning=True`` blocks of ``ceil(depth_bin / mean sample spacing)`` range samples per channel -
+    forward filled back to every sample and compared with the pings ``num_side_pings`` before and after.  Returns a boolean (uint8 on the device) DataArray with dims
     (channel, ping_time, range_sample); the reference's ``apply_ufunc`` hands the same values back with the last two
     dims swapped.
     """
@@ -140,12 +140,17 @@ def mask_impulse_noise(ds_Sv, depth_bin: str = "5m", num_side_pings: int = 2, im
         raise ValueError(f"Masking impulse noise requires `{range_var}` data variable in `ds_Sv`.")
     thr = extract_dB(impulse_noise_threshold)
     depth_bin = _parse_x_bin(depth_bin, "range_bin")
-    if not use_index_binning:
-        raise NotImplementedError("only use_index_binning=True runs on the device (SURVEY.md 8f rank 3); the per-ping "
-                                  "depth-value binning of the reference's default is outside the accelerated path")
     if not (isinstance(num_side_pings, (int, np.integer)) and num_side_pings >= 1):
         raise ValueError("num_side_pings must be a positive integer")
     Sv, rng, C, P, R = _index_binning_inputs(ds_Sv, range_var, "impulse")
+    if not use_index_binning:
+        # clean/utils.py:192-260: intervals of depth VALUES, np.arange(min, max + depth_bin, depth_bin), per ping
+        lo, hi, _ = kernels.minmax(rng)
+        if not (np.isfinite(lo) and np.isfinite(hi)):
+            raise ValueError(f"`{range_var}` has no valid values")
+        edges = np.arange(float(lo), float(hi) + depth_bin, depth_bin)
+        mask, _, _ = kernels.impulse_noise_mask_depth(Sv, rng, edges, C, P, R, int(num_side_pings), thr)
+        return DataArray(mask, DIMS, coords=_mask_coords(ds_Sv), name="Sv")
     nsamp = _samples_per_bin(rng, depth_bin, C, P, R)
     mask, _ = kernels.impulse_noise_mask(Sv, nsamp, C, P, R, int(num_side_pings), thr)
     return DataArray(mask, DIMS, coords=_mask_coords(ds_Sv), name="Sv")

@@ -158,6 +158,108 @@ __global__ void __launch_bounds__(256) impulse_mask_kernel(const float* __restri
   }
 }
 
+// ---- impulse noise with depth-VALUE binning (use_index_binning=False, clean/utils.py:192-260): per (channel, ping) row
+//      the samples are grouped by the interval [e_b, e_b+1) their depth falls into (depth increases along the row, NaN
+//      depths of padded pings count as beyond every edge), U[c,p,b] = dB of the nanmean of 10^(Sv/10) over the interval
+//      and F[c,p,b] = first sample with depth >= e_b (what np.digitize + np.unique(return_index) give).  Thread per
+//      interval: two bisections on the row in shared memory, then a serial sum.  t32: float32 thresholds ceil32(e_b)
+//      (x >= e_b <=> x >= ceil32(e_b) for float32 x). ----------------------------------------------------------------
+__global__ void __launch_bounds__(256) depth_bin_mean_kernel(const float* __restrict__ Sv, const float* __restrict__ depth,
+                                                             const float* __restrict__ t32, int nb, float* __restrict__ U,
+                                                             int* __restrict__ F, long long nrows, int R) {
+  extern __shared__ float s_buf[];  // [R] depth (NaN -> +inf), [R] linear Sv
+  float* s_d = s_buf;
+  float* s_l = s_buf + R;
+  auto first_ge = [&](float t) {
+    int lo = 0, hi = R;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (s_d[mid] >= t)
+        hi = mid;
+      else
+        lo = mid + 1;
+    }
+    return lo;
+  };
+  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const float* sv = Sv + row * (long long)R;
+    const float* dp = depth + row * (long long)R;
+    for (int j = threadIdx.x; j < R; j += blockDim.x) {
+      const float d = ld_stream(dp + j);
+      s_d[j] = (d == d) ? d : CUDART_INF_F;
+      s_l[j] = fast_exp2(ld_stream(sv + j) * kDb2Log2);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+      const int j0 = first_ge(t32[b]), j1 = first_ge(t32[b + 1]);
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+      int m = 0;
+      for (int j = j0; j < j1; j += 4) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float q = (j + i < j1) ? s_l[j + i] : CUDART_NAN_F;
+          const bool ok = (q == q);
+          s4[i] += ok ? q : 0.f;
+          m += ok;
+        }
+      }
+      U[row * nb + b] = (m > 0) ? kLog2ToDb * log2f(((s4[0] + s4[1]) + (s4[2] + s4[3])) / (float)m) : CUDART_NAN_F;
+      F[row * nb + b] = j0;
+    }
+    __syncthreads();
+  }
+}
+
+// two-sided ping comparison on the interval means, every sample taking the value of ITS interval in each of the three
+// pings (the intervals of ping p and p +- k start at different samples when the transducer depth changes)
+__global__ void __launch_bounds__(256) impulse_mask_depth_kernel(const float* __restrict__ U, const int* __restrict__ F,
+                                                                 unsigned char* __restrict__ mask, long long nrows, long long P,
+                                                                 int R, int nb, int k, float thr) {
+  extern __shared__ int s_tab[];  // [3][nb] first samples, [3][nb] values (float bits) of pings p, p + k, p - k
+  int* s_f = s_tab;
+  float* s_u = reinterpret_cast<float*>(s_tab + 3 * nb);
+  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const long long c = row / P, p = row - c * P;
+    const long long rws[3] = {row, (p + k < P) ? row + k : -1, (p - k >= 0) ? row - k : -1};
+    for (int i = threadIdx.x; i < 3 * nb; i += blockDim.x) {
+      const int w = i / nb, b = i - w * nb;
+      s_f[i] = rws[w] >= 0 ? F[rws[w] * nb + b] : 0;
+      s_u[i] = rws[w] >= 0 ? U[rws[w] * nb + b] : CUDART_NAN_F;
+    }
+    __syncthreads();
+    unsigned char* m = mask + row * (long long)R;
+    for (int j0 = threadIdx.x * 16; j0 < R; j0 += blockDim.x * 16) {
+      int b[3];
+#pragma unroll
+      for (int w = 0; w < 3; ++w) {  // interval of sample j0: number of first-sample labels <= j0, minus 1 (ffill)
+        int lo = 0, hi = nb;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (s_f[w * nb + mid] <= j0)
+            lo = mid + 1;
+          else
+            hi = mid;
+        }
+        b[w] = lo - 1;
+      }
+      for (int i = 0; i < 16 && j0 + i < R; ++i) {
+        const int j = j0 + i;
+        float v[3];
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+          while (b[w] + 1 < nb && s_f[w * nb + b[w] + 1] <= j) ++b[w];
+          v[w] = b[w] >= 0 ? s_u[w * nb + b[w]] : CUDART_NAN_F;
+        }
+        float f = v[0] - v[1], q = v[0] - v[2];
+        f = (f == f) ? f : CUDART_INF_F;
+        q = (q == q) ? q : CUDART_INF_F;
+        m[j] = (f > thr && q > thr) ? 1 : 0;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // ---- transient noise, step 1: per (channel, ping) row, sum and count of the valid 10^(Sv/10) over the range window
 //      [n - w, n + w] of the array sliced at m0, borders reflected (d c b a | a b c d | d c b a: scipy.ndimage
 //      mode="reflect", clean/utils.py:158-170).  Float64 prefix sums in shared memory.  CTA per row. ------------------
@@ -332,4 +434,34 @@ extern "C" int epb_transient_noise_mask(const float* Sv, const int* nsamp, float
                                                                  pooled_Sv, P, (int)R, min_range_sample, num_side_pings,
                                                                  threshold, chunk);
   return epb_check_launch("epb_transient_noise_mask");
+}
+
+namespace {
+__global__ void edges_ceil32_kernel(const double* __restrict__ e, float* __restrict__ t, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) t[i] = __double2float_ru(e[i]);
+}
+}  // namespace
+
+extern "C" int epb_impulse_noise_mask_depth(const float* Sv, const float* depth, const double* edges, int nbins,
+                                            float* bin_means, int* bin_first, unsigned char* mask, epb_i64 C, epb_i64 P, epb_i64 R,
+                                            int num_side_pings, float threshold, float* thresholds_scratch, void* stream) {
+  EPB_REQUIRE(Sv && depth && edges && bin_means && bin_first && mask && thresholds_scratch, "NULL pointer");
+  EPB_REQUIRE(C > 0 && P > 0 && R > 0 && R <= 24576 && nbins > 0 && nbins <= 8192 && num_side_pings >= 1, "bad shape / argument");
+  // float32 thresholds of the float64 edges (closed-left intervals): computed on the device by a tiny kernel
+  edges_ceil32_kernel<<<(nbins + 1 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(edges, thresholds_scratch, nbins + 1);
+  const long long nrows = C * P, cap = (long long)epb_num_sms() * 8;
+  const unsigned grid = (unsigned)(nrows < cap ? nrows : cap);
+  const size_t smem_a = (size_t)R * 8, smem_b = (size_t)nbins * 24;
+  if (smem_a > 48 * 1024 &&
+      cudaFuncSetAttribute(depth_bin_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a) != cudaSuccess)
+    return epb_check_launch("epb_impulse_noise_mask_depth(smem)");
+  if (smem_b > 48 * 1024 &&
+      cudaFuncSetAttribute(impulse_mask_depth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b) != cudaSuccess)
+    return epb_check_launch("epb_impulse_noise_mask_depth(smem)");
+  depth_bin_mean_kernel<<<grid, 256, smem_a, (cudaStream_t)stream>>>(Sv, depth, thresholds_scratch, nbins, bin_means, bin_first,
+                                                                     nrows, (int)R);
+  impulse_mask_depth_kernel<<<grid, 256, smem_b, (cudaStream_t)stream>>>(bin_means, bin_first, mask, nrows, P, (int)R, nbins,
+                                                                         num_side_pings, threshold);
+  return epb_check_launch("epb_impulse_noise_mask_depth");
 }

@@ -331,6 +331,19 @@ def impulse_noise_mask(Sv, nsamp, C, P, R, num_side_pings, threshold, out=None):
     return mask, blocks
 
 
+def impulse_noise_mask_depth(Sv, depth, edges, C, P, R, num_side_pings, threshold):
+    """Depth-value binning variant (use_index_binning=False); edges: host float64 array of interval edges."""
+    nb = len(edges) - 1
+    e = torch.from_numpy(np.ascontiguousarray(edges, dtype=np.float64)).to(Sv.device)
+    means = torch.empty((C, P, nb), dtype=torch.float32, device=Sv.device)
+    first = torch.empty((C, P, nb), dtype=torch.int32, device=Sv.device)
+    mask = torch.empty((C, P, R), dtype=torch.uint8, device=Sv.device)
+    scratch = torch.empty(nb + 1, dtype=torch.float32, device=Sv.device)
+    _lib.call("epb_impulse_noise_mask_depth", ptr(Sv), ptr(depth), ptr(e), nb, ptr(means), ptr(first), ptr(mask), C, P, R,
+              int(num_side_pings), ctypes.c_float(float(threshold)), ptr(scratch), stream())
+    return mask, means, first
+
+
 def transient_noise_mask(Sv, nsamp, C, P, R, min_range_sample, num_side_pings, threshold, want_pooled=False, out=None):
     """out: optional (mask, window_sums) buffers to reuse."""
     ns = torch.from_numpy(np.ascontiguousarray(nsamp, dtype=np.int32)).to(Sv.device)

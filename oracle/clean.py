@@ -203,3 +203,39 @@ def mask_transient_noise_index_binning(Sv, range_var, depth_bin, num_side_pings,
     pooled, _ = index_binning_pool_Sv(Sv, range_var, depth_bin, num_side_pings, exclude_above)
     with np.errstate(invalid="ignore"):
         return (Sv - pooled) > transient_noise_threshold, pooled
+
+
+def downsample_upsample_along_depth(Sv, range_var, depth_bin):
+    """clean/utils.py:192-260 (use_index_binning=False): depth intervals [e_k, e_k+1) from np.arange(min, max + bin, bin);
+    per (channel, ping) nanmean of 10^(Sv/10) over the samples whose depth falls into the interval (flox nanmean, NaN depths
+    dropped, empty interval -> NaN); every sample is then given the value of the interval np.digitize assigns it to
+    (first sample of each interval as the new range_sample label, reindex with ffill).  Returns (downsampled, upsampled).
+    Like the reference it needs depth to increase along range_sample and every interval to occur in every ping."""
+    C, P, R = Sv.shape
+    edges = np.arange(np.nanmin(range_var), np.nanmax(range_var) + depth_bin, depth_bin)
+    lefts = edges[:-1]
+    nb = len(lefts)
+    lin = log2lin(Sv)
+    down = np.full((C, P, nb), np.nan)
+    up = np.full((C, P, R), np.nan)
+    assign = np.digitize(range_var, lefts)
+    for c in range(C):
+        for p in range(P):
+            d = range_var[c, p]
+            for b in range(nb):
+                m = (d >= edges[b]) & (d < edges[b + 1]) & ~np.isnan(lin[c, p])
+                if m.any():
+                    down[c, p, b] = lin2log(lin[c, p][m].mean())
+            uniq, first = np.unique(assign[c, p], return_index=True)
+            if len(uniq) != nb:
+                raise ValueError("conflicting sizes for dimension 'depth_bins'")  # assign_coords in the reference
+            j = np.searchsorted(first, np.arange(R), side="right") - 1  # reindex(..., method="ffill")
+            up[c, p] = np.where(j >= 0, down[c, p][np.maximum(j, 0)], np.nan)
+    return down, up
+
+
+def mask_impulse_noise_depth_binning(Sv, range_var, depth_bin, num_side_pings, impulse_noise_threshold):
+    """clean/api.py:169-266 with use_index_binning=False.  Returns (mask, upsampled_Sv), both (C, P, R)."""
+    _, up = downsample_upsample_along_depth(Sv, range_var, depth_bin)
+    mask = np.stack([echopy_impulse_noise_mask(up[c].T, num_side_pings, impulse_noise_threshold).T for c in range(Sv.shape[0])])
+    return mask, up

@@ -173,4 +173,72 @@ def test_mask_noise_argument_errors(ep):
     with pytest.raises(ValueError, match="requires `echo_range` data variable"):
         ep.clean.mask_transient_noise(ds, range_var="echo_range", use_index_binning=True)
     with pytest.raises(NotImplementedError):
-        ep.clean.mask_impulse_noise(ds, use_index_binning=False)
+        ep.clean.mask_transient_noise(ds, use_index_binning=False)
+
+
+# ---- use_index_binning=False: intervals of depth VALUES (clean/utils.py:192-260) --------------------------------------
+def _mock_depth_varying(C=2, P=30, R=220, seed=11, depth_bin=2.0):
+    """Mock volume whose transducer depth changes from ping to ping (so the intervals start at different samples in
+    neighbouring pings), sized so that every ping still reaches every depth interval as the reference requires."""
+    Sv, _ = _mock(C, P, R, seed=seed)
+    rng = np.random.default_rng(seed)
+    off = rng.choice([0.0, 0.07, 0.13], size=(C, P))
+    for Rr in range(R, R + 40):
+        depth = (3.0 + off[:, :, None] + 0.19 * np.arange(Rr)[None, None, :]).astype(np.float32).astype(np.float64)
+        edges = np.arange(depth.min(), depth.max() + depth_bin, depth_bin)
+        if depth.max(axis=2).min() - edges[-2] > 0.3:  # every ping has samples in the last interval
+            Sv2, _ = _mock(C, P, Rr, seed=seed)
+            return Sv2, depth
+    raise AssertionError("no suitable size")
+
+
+def test_oracle_depth_binning_property():
+    """tests/clean/test_noise.py:550-612 in spirit: every upsampled value is the linear mean of the samples of its own
+    depth interval in its own ping."""
+    Sv, depth = _mock_depth_varying()
+    down, up = oclean.downsample_upsample_along_depth(Sv, depth, 2.0)
+    edges = np.arange(depth.min(), depth.max() + 2.0, 2.0)
+    for c in range(Sv.shape[0]):
+        for p in range(0, Sv.shape[1], 4):
+            b = np.digitize(depth[c, p], edges[:-1]) - 1
+            for n in range(0, Sv.shape[2], 9):
+                m = (depth[c, p] >= edges[b[n]]) & (depth[c, p] < edges[b[n] + 1]) & ~np.isnan(Sv[c, p])
+                want = oclean.lin2log(oclean.log2lin(Sv[c, p][m]).mean()) if m.any() else np.nan
+                assert (np.isnan(want) and np.isnan(up[c, p, n])) or np.isclose(up[c, p, n], want, rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,depth_bin", [(2, "2m"), (1, "5m")])
+def test_mask_impulse_noise_depth_binning_vs_oracle(ep, k, depth_bin):
+    import torch
+
+    from echopype_b200 import kernels
+
+    db = float(depth_bin[:-1])
+    Sv, depth = _mock_depth_varying(depth_bin=db)
+    Sv32 = Sv.astype(np.float32).astype(np.float64)
+    thr = 10.0
+    want, up = oclean.mask_impulse_noise_depth_binning(Sv32, depth, db, k, thr)
+    got = ep.clean.mask_impulse_noise(_ds(ep, Sv, depth), depth_bin, k, "10.0dB", "depth")  # the reference's default path
+    g = got.values.astype(bool)
+    P = Sv.shape[1]
+    fwd = np.full(Sv.shape, np.inf)
+    bwd = np.full(Sv.shape, np.inf)
+    fwd[:, : P - k] = up[:, : P - k] - up[:, k:]
+    bwd[:, k:] = up[:, k:] - up[:, : P - k]
+    fwd[np.isnan(fwd)] = np.inf
+    bwd[np.isnan(bwd)] = np.inf
+    sure = (np.abs(fwd - thr) > 1e-3) & (np.abs(bwd - thr) > 1e-3)
+    assert sure.mean() > 0.99 and want.any() and not want.all()
+    np.testing.assert_array_equal(g[sure], want[sure])
+    # the interval means and first samples themselves
+    C, P, R = Sv.shape
+    edges = np.arange(depth.min(), depth.max() + db, db)
+    _, means, first = kernels.impulse_noise_mask_depth(torch.from_numpy(Sv.astype(np.float32)).cuda(),
+                                                       torch.from_numpy(depth.astype(np.float32)).cuda(), edges, C, P, R, k, thr)
+    down, _ = oclean.downsample_upsample_along_depth(Sv32, depth, db)
+    means = means.cpu().numpy()
+    np.testing.assert_array_equal(np.isnan(means), np.isnan(down))
+    assert np.nanmax(np.abs(means - down)) < 1e-4
+    want_first = np.stack([[np.searchsorted(depth[c, p], edges[:-1], side="left") for p in range(P)] for c in range(C)])
+    np.testing.assert_array_equal(first.cpu().numpy(), want_first)
