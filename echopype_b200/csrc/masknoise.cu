@@ -167,9 +167,10 @@ __global__ void __launch_bounds__(256) impulse_mask_kernel(const float* __restri
 __global__ void __launch_bounds__(256) depth_bin_mean_kernel(const float* __restrict__ Sv, const float* __restrict__ depth,
                                                              const float* __restrict__ t32, int nb, float* __restrict__ U,
                                                              int* __restrict__ F, long long nrows, int R) {
-  extern __shared__ float s_buf[];  // [R] depth (NaN -> +inf), [R] linear Sv
+  extern __shared__ __align__(16) float s_buf[];  // [R] depth (NaN -> +inf), [R] linear Sv, [nb + 1] interval starts
   float* s_d = s_buf;
   float* s_l = s_buf + R;
+  int* s_j0 = reinterpret_cast<int*>(s_buf + 2 * R);  // [nb + 1] first sample at or beyond every edge
   auto first_ge = [&](float t) {
     int lo = 0, hi = R;
     while (lo < hi) {
@@ -184,14 +185,27 @@ __global__ void __launch_bounds__(256) depth_bin_mean_kernel(const float* __rest
   for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
     const float* sv = Sv + row * (long long)R;
     const float* dp = depth + row * (long long)R;
-    for (int j = threadIdx.x; j < R; j += blockDim.x) {
-      const float d = ld_stream(dp + j);
-      s_d[j] = (d == d) ? d : CUDART_INF_F;
-      s_l[j] = fast_exp2(ld_stream(sv + j) * kDb2Log2);
+    if ((R & 3) == 0) {  // 16-byte loads, both arrays in flight
+      for (int j = threadIdx.x; j < (R >> 2); j += blockDim.x) {
+        const float4 d4 = ld_stream4(reinterpret_cast<const float4*>(dp) + j);
+        const float4 v4 = ld_stream4(reinterpret_cast<const float4*>(sv) + j);
+        *reinterpret_cast<float4*>(s_d + 4 * j) = make_float4((d4.x == d4.x) ? d4.x : CUDART_INF_F, (d4.y == d4.y) ? d4.y : CUDART_INF_F,
+                                                              (d4.z == d4.z) ? d4.z : CUDART_INF_F, (d4.w == d4.w) ? d4.w : CUDART_INF_F);
+        *reinterpret_cast<float4*>(s_l + 4 * j) = make_float4(fast_exp2(v4.x * kDb2Log2), fast_exp2(v4.y * kDb2Log2),
+                                                              fast_exp2(v4.z * kDb2Log2), fast_exp2(v4.w * kDb2Log2));
+      }
+    } else {
+      for (int j = threadIdx.x; j < R; j += blockDim.x) {
+        const float d = ld_stream(dp + j);
+        s_d[j] = (d == d) ? d : CUDART_INF_F;
+        s_l[j] = fast_exp2(ld_stream(sv + j) * kDb2Log2);
+      }
     }
     __syncthreads();
+    for (int b = threadIdx.x; b <= nb; b += blockDim.x) s_j0[b] = first_ge(t32[b]);  // one bisection per edge
+    __syncthreads();
     for (int b = threadIdx.x; b < nb; b += blockDim.x) {
-      const int j0 = first_ge(t32[b]), j1 = first_ge(t32[b + 1]);
+      const int j0 = s_j0[b], j1 = s_j0[b + 1];
       float s4[4] = {0.f, 0.f, 0.f, 0.f};
       int m = 0;
       for (int j = j0; j < j1; j += 4) {
@@ -242,18 +256,39 @@ __global__ void __launch_bounds__(256) impulse_mask_depth_kernel(const float* __
         }
         b[w] = lo - 1;
       }
-      for (int i = 0; i < 16 && j0 + i < R; ++i) {
-        const int j = j0 + i;
+      // the flag changes only when one of the three interval indices advances; next[w] = first sample of the following
+      // interval (R when there is none) keeps the per-sample work at three compares
+      int next[3];
+      unsigned fl = 0u;
+      auto refresh = [&]() {
         float v[3];
 #pragma unroll
         for (int w = 0; w < 3; ++w) {
-          while (b[w] + 1 < nb && s_f[w * nb + b[w] + 1] <= j) ++b[w];
           v[w] = b[w] >= 0 ? s_u[w * nb + b[w]] : CUDART_NAN_F;
+          next[w] = (b[w] + 1 < nb) ? s_f[w * nb + b[w] + 1] : R;
         }
         float f = v[0] - v[1], q = v[0] - v[2];
         f = (f == f) ? f : CUDART_INF_F;
         q = (q == q) ? q : CUDART_INF_F;
-        m[j] = (f > thr && q > thr) ? 1 : 0;
+        fl = (f > thr && q > thr) ? 1u : 0u;
+      };
+      refresh();
+      unsigned wv[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int j = j0 + i;
+        if (j >= next[0] || j >= next[1] || j >= next[2]) {
+#pragma unroll
+          for (int w = 0; w < 3; ++w)
+            while (b[w] + 1 < nb && s_f[w * nb + b[w] + 1] <= j) ++b[w];
+          refresh();
+        }
+        wv[i >> 2] |= fl << (8 * (i & 3));
+      }
+      if ((R & 15) == 0) {
+        *reinterpret_cast<uint4*>(m + j0) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+      } else {
+        for (int i = 0; i < 16 && j0 + i < R; ++i) m[j0 + i] = (unsigned char)((wv[i >> 2] >> (8 * (i & 3))) & 0xffu);
       }
     }
     __syncthreads();
@@ -452,7 +487,7 @@ extern "C" int epb_impulse_noise_mask_depth(const float* Sv, const float* depth,
   edges_ceil32_kernel<<<(nbins + 1 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(edges, thresholds_scratch, nbins + 1);
   const long long nrows = C * P, cap = (long long)epb_num_sms() * 8;
   const unsigned grid = (unsigned)(nrows < cap ? nrows : cap);
-  const size_t smem_a = (size_t)R * 8, smem_b = (size_t)nbins * 24;
+  const size_t smem_a = (size_t)R * 8 + (size_t)(nbins + 1) * 4, smem_b = (size_t)nbins * 24;
   if (smem_a > 48 * 1024 &&
       cudaFuncSetAttribute(depth_bin_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a) != cudaSuccess)
     return epb_check_launch("epb_impulse_noise_mask_depth(smem)");
