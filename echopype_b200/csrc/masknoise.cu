@@ -166,7 +166,8 @@ __global__ void __launch_bounds__(256) impulse_mask_kernel(const float* __restri
 //      (x >= e_b <=> x >= ceil32(e_b) for float32 x). ----------------------------------------------------------------
 __global__ void __launch_bounds__(256) depth_bin_mean_kernel(const float* __restrict__ Sv, const float* __restrict__ depth,
                                                              const float* __restrict__ t32, int nb, float* __restrict__ U,
-                                                             int* __restrict__ F, long long nrows, int R) {
+                                                             int* __restrict__ F, float* __restrict__ up, long long nrows,
+                                                             int R) {
   extern __shared__ __align__(16) float s_buf[];  // [R] depth (NaN -> +inf), [R] linear Sv, [nb + 1] interval starts
   float* s_d = s_buf;
   float* s_l = s_buf + R;
@@ -217,81 +218,80 @@ __global__ void __launch_bounds__(256) depth_bin_mean_kernel(const float* __rest
           m += ok;
         }
       }
-      U[row * nb + b] = (m > 0) ? kLog2ToDb * log2f(((s4[0] + s4[1]) + (s4[2] + s4[3])) / (float)m) : CUDART_NAN_F;
+      const float u = (m > 0) ? kLog2ToDb * log2f(((s4[0] + s4[1]) + (s4[2] + s4[3])) / (float)m) : CUDART_NAN_F;
+      U[row * nb + b] = u;
       F[row * nb + b] = j0;
+      s_d[b] = u;  // the depths are no longer needed: interval means for the forward fill below
+    }
+    __syncthreads();
+    // forward fill (np.digitize on the left edges + reindex ffill): sample j takes the mean of the last interval that
+    // starts at or before it; four samples per thread and step, one 16-byte store
+    float* urow = up + row * (long long)R;
+    for (int j0 = 4 * threadIdx.x; j0 < R; j0 += 4 * blockDim.x) {
+      int lo = 0, hi = nb;  // number of interval starts <= j0
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (s_j0[mid] <= j0)
+          lo = mid + 1;
+        else
+          hi = mid;
+      }
+      int b = lo - 1;
+      float v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        while (b + 1 < nb && s_j0[b + 1] <= j0 + i) ++b;
+        v[i] = b >= 0 ? s_d[b] : CUDART_NAN_F;
+      }
+      if ((R & 3) == 0) {
+        *reinterpret_cast<float4*>(urow + j0) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+        for (int i = 0; i < 4 && j0 + i < R; ++i) urow[j0 + i] = v[i];
+      }
     }
     __syncthreads();
   }
 }
 
-// two-sided ping comparison on the interval means, every sample taking the value of ITS interval in each of the three
-// pings (the intervals of ping p and p +- k start at different samples when the transducer depth changes)
-__global__ void __launch_bounds__(256) impulse_mask_depth_kernel(const float* __restrict__ U, const int* __restrict__ F,
-                                                                 unsigned char* __restrict__ mask, long long nrows, long long P,
-                                                                 int R, int nb, int k, float thr) {
-  extern __shared__ int s_tab[];  // [3][nb] first samples, [3][nb] values (float bits) of pings p, p + k, p - k
-  int* s_f = s_tab;
-  float* s_u = reinterpret_cast<float*>(s_tab + 3 * nb);
+// echopy_impulse_noise_mask (clean/utils.py:320-337) on a materialised (channel, ping, range_sample) array of
+// downsampled-upsampled Sv: elementwise on the rows p, p + k, p - k; 16 samples per thread, one 16-byte store
+__global__ void __launch_bounds__(256) impulse_mask_rows_kernel(const float* __restrict__ up, unsigned char* __restrict__ mask,
+                                                                long long nrows, long long P, int R, int k, float thr) {
   for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
     const long long c = row / P, p = row - c * P;
-    const long long rws[3] = {row, (p + k < P) ? row + k : -1, (p - k >= 0) ? row - k : -1};
-    for (int i = threadIdx.x; i < 3 * nb; i += blockDim.x) {
-      const int w = i / nb, b = i - w * nb;
-      s_f[i] = rws[w] >= 0 ? F[rws[w] * nb + b] : 0;
-      s_u[i] = rws[w] >= 0 ? U[rws[w] * nb + b] : CUDART_NAN_F;
-    }
-    __syncthreads();
+    const float* u0 = up + row * (long long)R;
+    const float* uf = (p + k < P) ? up + (row + k) * (long long)R : nullptr;
+    const float* ub = (p - k >= 0) ? up + (row - k) * (long long)R : nullptr;
     unsigned char* m = mask + row * (long long)R;
+    const bool vec = (R & 15) == 0;
     for (int j0 = threadIdx.x * 16; j0 < R; j0 += blockDim.x * 16) {
-      int b[3];
-#pragma unroll
-      for (int w = 0; w < 3; ++w) {  // interval of sample j0: number of first-sample labels <= j0, minus 1 (ffill)
-        int lo = 0, hi = nb;
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (s_f[w * nb + mid] <= j0)
-            lo = mid + 1;
-          else
-            hi = mid;
-        }
-        b[w] = lo - 1;
-      }
-      // the flag changes only when one of the three interval indices advances; next[w] = first sample of the following
-      // interval (R when there is none) keeps the per-sample work at three compares
-      int next[3];
-      unsigned fl = 0u;
-      auto refresh = [&]() {
-        float v[3];
-#pragma unroll
-        for (int w = 0; w < 3; ++w) {
-          v[w] = b[w] >= 0 ? s_u[w * nb + b[w]] : CUDART_NAN_F;
-          next[w] = (b[w] + 1 < nb) ? s_f[w * nb + b[w] + 1] : R;
-        }
-        float f = v[0] - v[1], q = v[0] - v[2];
-        f = (f == f) ? f : CUDART_INF_F;
-        q = (q == q) ? q : CUDART_INF_F;
-        fl = (f > thr && q > thr) ? 1u : 0u;
-      };
-      refresh();
       unsigned wv[4] = {0u, 0u, 0u, 0u};
+      if (vec) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int j = j0 + i;
-        if (j >= next[0] || j >= next[1] || j >= next[2]) {
+        for (int q = 0; q < 4; ++q) {
+          const float4 a = *reinterpret_cast<const float4*>(u0 + j0 + 4 * q);
+          const float4 f4 = uf ? *reinterpret_cast<const float4*>(uf + j0 + 4 * q) : make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
+          const float4 b4 = ub ? *reinterpret_cast<const float4*>(ub + j0 + 4 * q) : make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
+          const float av[4] = {a.x, a.y, a.z, a.w}, fv[4] = {f4.x, f4.y, f4.z, f4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-          for (int w = 0; w < 3; ++w)
-            while (b[w] + 1 < nb && s_f[w * nb + b[w] + 1] <= j) ++b[w];
-          refresh();
+          for (int i = 0; i < 4; ++i) {
+            float f = av[i] - fv[i], w = av[i] - bv[i];
+            f = (f == f) ? f : CUDART_INF_F;
+            w = (w == w) ? w : CUDART_INF_F;
+            wv[q] |= ((f > thr && w > thr) ? 1u : 0u) << (8 * i);
+          }
         }
-        wv[i >> 2] |= fl << (8 * (i & 3));
-      }
-      if ((R & 15) == 0) {
         *reinterpret_cast<uint4*>(m + j0) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
       } else {
-        for (int i = 0; i < 16 && j0 + i < R; ++i) m[j0 + i] = (unsigned char)((wv[i >> 2] >> (8 * (i & 3))) & 0xffu);
+        for (int i = 0; i < 16 && j0 + i < R; ++i) {
+          const float v = u0[j0 + i];
+          float f = v - (uf ? uf[j0 + i] : CUDART_NAN_F), w = v - (ub ? ub[j0 + i] : CUDART_NAN_F);
+          f = (f == f) ? f : CUDART_INF_F;
+          w = (w == w) ? w : CUDART_INF_F;
+          m[j0 + i] = (f > thr && w > thr) ? 1 : 0;
+        }
       }
     }
-    __syncthreads();
   }
 }
 
@@ -479,24 +479,22 @@ __global__ void edges_ceil32_kernel(const double* __restrict__ e, float* __restr
 }  // namespace
 
 extern "C" int epb_impulse_noise_mask_depth(const float* Sv, const float* depth, const double* edges, int nbins,
-                                            float* bin_means, int* bin_first, unsigned char* mask, epb_i64 C, epb_i64 P, epb_i64 R,
-                                            int num_side_pings, float threshold, float* thresholds_scratch, void* stream) {
-  EPB_REQUIRE(Sv && depth && edges && bin_means && bin_first && mask && thresholds_scratch, "NULL pointer");
+                                            float* bin_means, int* bin_first, float* upsampled, unsigned char* mask, epb_i64 C,
+                                            epb_i64 P, epb_i64 R, int num_side_pings, float threshold, float* thresholds_scratch,
+                                            void* stream) {
+  EPB_REQUIRE(Sv && depth && edges && bin_means && bin_first && upsampled && mask && thresholds_scratch, "NULL pointer");
   EPB_REQUIRE(C > 0 && P > 0 && R > 0 && R <= 24576 && nbins > 0 && nbins <= 8192 && num_side_pings >= 1, "bad shape / argument");
   // float32 thresholds of the float64 edges (closed-left intervals): computed on the device by a tiny kernel
   edges_ceil32_kernel<<<(nbins + 1 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(edges, thresholds_scratch, nbins + 1);
   const long long nrows = C * P, cap = (long long)epb_num_sms() * 8;
   const unsigned grid = (unsigned)(nrows < cap ? nrows : cap);
-  const size_t smem_a = (size_t)R * 8 + (size_t)(nbins + 1) * 4, smem_b = (size_t)nbins * 24;
+  const size_t smem_a = (size_t)R * 8 + (size_t)(nbins + 1) * 4;
+  EPB_REQUIRE(nbins <= R, "more depth intervals than range samples");
   if (smem_a > 48 * 1024 &&
       cudaFuncSetAttribute(depth_bin_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a) != cudaSuccess)
     return epb_check_launch("epb_impulse_noise_mask_depth(smem)");
-  if (smem_b > 48 * 1024 &&
-      cudaFuncSetAttribute(impulse_mask_depth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b) != cudaSuccess)
-    return epb_check_launch("epb_impulse_noise_mask_depth(smem)");
   depth_bin_mean_kernel<<<grid, 256, smem_a, (cudaStream_t)stream>>>(Sv, depth, thresholds_scratch, nbins, bin_means, bin_first,
-                                                                     nrows, (int)R);
-  impulse_mask_depth_kernel<<<grid, 256, smem_b, (cudaStream_t)stream>>>(bin_means, bin_first, mask, nrows, P, (int)R, nbins,
-                                                                         num_side_pings, threshold);
+                                                                     upsampled, nrows, (int)R);
+  impulse_mask_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(upsampled, mask, nrows, P, (int)R, num_side_pings, threshold);
   return epb_check_launch("epb_impulse_noise_mask_depth");
 }

@@ -338,10 +338,11 @@ def impulse_noise_mask_depth(Sv, depth, edges, C, P, R, num_side_pings, threshol
     means = torch.empty((C, P, nb), dtype=torch.float32, device=Sv.device)
     first = torch.empty((C, P, nb), dtype=torch.int32, device=Sv.device)
     mask = torch.empty((C, P, R), dtype=torch.uint8, device=Sv.device)
+    up = torch.empty((C, P, R), dtype=torch.float32, device=Sv.device)  # the reference's upsampled_Sv
     scratch = torch.empty(nb + 1, dtype=torch.float32, device=Sv.device)
-    _lib.call("epb_impulse_noise_mask_depth", ptr(Sv), ptr(depth), ptr(e), nb, ptr(means), ptr(first), ptr(mask), C, P, R,
-              int(num_side_pings), ctypes.c_float(float(threshold)), ptr(scratch), stream())
-    return mask, means, first
+    _lib.call("epb_impulse_noise_mask_depth", ptr(Sv), ptr(depth), ptr(e), nb, ptr(means), ptr(first), ptr(up), ptr(mask),
+              C, P, R, int(num_side_pings), ctypes.c_float(float(threshold)), ptr(scratch), stream())
+    return mask, means, first, up
 
 
 def transient_noise_mask(Sv, nsamp, C, P, R, min_range_sample, num_side_pings, threshold, want_pooled=False, out=None):

@@ -251,12 +251,12 @@ int epb_impulse_noise_mask(const float* Sv, const int* nsamp, float* block_means
 /* Impulse noise with depth-VALUE binning (use_index_binning=False, clean/utils.py:192-260): edges [nbins+1] float64 =
  * np.arange(min, max + depth_bin, depth_bin) of the range variable; per (channel, ping) the NaN-aware linear mean of Sv
  * over the samples of each interval [e_b, e_b+1) (bin_means [C,P,nbins] float32, dB) and the first sample at or below
- * e_b (bin_first [C,P,nbins] int32); every sample takes the mean of its interval (np.digitize + forward fill) and the mask
- * is the two-sided ping comparison of those values.  depth must increase along range_sample (NaN tails allowed).
- * thresholds_scratch: [nbins+1] float32. */
+ * e_b (bin_first [C,P,nbins] int32); every sample takes the mean of its interval (np.digitize + forward fill: upsampled
+ * [C,P,R] float32, the reference's upsampled_Sv) and the mask is the two-sided ping comparison of those values.  depth
+ * must increase along range_sample (NaN tails allowed).  thresholds_scratch: [nbins+1] float32. */
 int epb_impulse_noise_mask_depth(const float* Sv, const float* depth, const double* edges, int nbins, float* bin_means,
-                                 int* bin_first, unsigned char* mask, epb_i64 C, epb_i64 P, epb_i64 R, int num_side_pings,
-                                 float threshold, float* thresholds_scratch, void* stream);
+                                 int* bin_first, float* upsampled, unsigned char* mask, epb_i64 C, epb_i64 P, epb_i64 R,
+                                 int num_side_pings, float threshold, float* thresholds_scratch, void* stream);
 /* Transient noise (clean/utils.py:109-189 with func = nanmean, clean/api.py:163-166): pooled Sv = dB of the nanmean of
  * 10^(Sv/10) over (2 k + 1) pings x (2 nsamp[c] + 1) range samples of the volume sliced at min_range_sample, borders
  * reflected (scipy.ndimage "reflect"); mask [C,P,R] uint8 = Sv - pooled > threshold, 0 above min_range_sample.

@@ -234,7 +234,7 @@ def test_mask_impulse_noise_depth_binning_vs_oracle(ep, k, depth_bin):
     # the interval means and first samples themselves
     C, P, R = Sv.shape
     edges = np.arange(depth.min(), depth.max() + db, db)
-    _, means, first = kernels.impulse_noise_mask_depth(torch.from_numpy(Sv.astype(np.float32)).cuda(),
+    _, means, first, upd = kernels.impulse_noise_mask_depth(torch.from_numpy(Sv.astype(np.float32)).cuda(),
                                                        torch.from_numpy(depth.astype(np.float32)).cuda(), edges, C, P, R, k, thr)
     down, _ = oclean.downsample_upsample_along_depth(Sv32, depth, db)
     means = means.cpu().numpy()
@@ -242,3 +242,6 @@ def test_mask_impulse_noise_depth_binning_vs_oracle(ep, k, depth_bin):
     assert np.nanmax(np.abs(means - down)) < 1e-4
     want_first = np.stack([[np.searchsorted(depth[c, p], edges[:-1], side="left") for p in range(P)] for c in range(C)])
     np.testing.assert_array_equal(first.cpu().numpy(), want_first)
+    upd = upd.cpu().numpy()
+    np.testing.assert_array_equal(np.isnan(upd), np.isnan(up))
+    assert np.nanmax(np.abs(upd - up)) < 1e-4  # upsampled_Sv of the reference, per sample
