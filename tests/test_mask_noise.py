@@ -131,7 +131,7 @@ def test_impulse_block_means_within_tolerance(ep):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape,depth_bin,k,excl", [((2, 40, 200), "2m", 3, "6m"), ((2, 30, 150), "1m", 25, "0m"),
+@pytest.mark.parametrize("shape,depth_bin,k,excl", [((2, 40, 200), "2m", 3, "6m"), ((2, 30, 150), "1m", 25, "0m"), ((2, 300, 301), "2m", 25, "5m"),
                                                   ((1, 12, 90), "1m", 2, "4.0m"), ((2, 9, 64), "1m", 1, "500m")])
 def test_mask_transient_noise_vs_oracle(ep, shape, depth_bin, k, excl):
     import torch
