@@ -1,25 +1,27 @@
 // Fused pipeline, fast path: raw power -> Sv -> background-noise removal -> MVBS accumulators, one pass over HBM
-// at 4 algorithmic bytes per sample (same semantics as pipeline.cu).
+// at 4 algorithmic bytes per sample, 2 on int16 raw counts (same semantics as pipeline.cu).
 //
-// PERSISTENT kernel, one CTA per SM (grid = SM count x resident CTAs), each CTA owns a contiguous run of
-// (channel, ping-tile) tiles.  Design points (DESIGN.md "fused pipeline, fast path"):
-//   * a ring of row slots in shared memory is filled by TMA bulk copies (cp.async.bulk, one per ping row, the rows
-//     of a tile completing on the tile's mbarrier; SASS UBLKCP / SYNCS) issued tiles ahead of the consumer, so HBM
-//     latency and the per-tile reductions of the consumer overlap;
-//   * one thread owns four adjacent range samples (one LDS.128 per row).  e = 10^((front(x)-K)/10) of the
-//     whole tile (ping_num <= 8 rows) lives in REGISTERS between the noise estimate (phase 1) and the noise
-//     removal / binning (phase 2): one FFMA + one MUFU.EX2 per sample, shared memory is read once per sample;
-//   * all range-only terms (h = R'^2 10^(2aR'/10) and TL/h) and the range-bin index of every column are computed
-//     once per range law (normally once per channel) and parked in shared memory, the exact float64 bin
-//     boundaries likewise;
-//   * noise removal in the e domain: the sample survives iff e > noise (1 + 10^(SNR/10)) TL / h (one compare), the
-//     surviving e are summed per column and scaled once per tile: sum(e h - noise TL) = h sum(e) - n noise TL;
-//   * (sum, count) of a thread's four columns accumulate in registers ACROSS tiles while the ping bin does not
-//     change; on a bin change a segmented warp-shuffle reduction over runs of equal range-bin index issues one
-//     float64 atomic triple per (warp, range bin).
+// PERSISTENT kernel (grid = SM count x resident CTAs: one CTA per SM at R = 4096, two at R <= 2048), each CTA owns a
+// contiguous run of (channel, ping-tile) tiles.  Design points (DESIGN.md "fused pipeline, fast path"):
+//   * a ring of tile slots in shared memory is filled by TMA bulk copies (cp.async.bulk: one copy for the rows of a
+//     tile and one for its 144-byte descriptor from prepare_kernel, completing on the tile's mbarrier; SASS UBLKCP /
+//     SYNCS), issued as soon as a slot is free, so HBM latency and the per-tile reductions overlap;
+//   * a thread owns G x 4 adjacent range samples (one LDS.128 per row and group).  u = 10^((Sv - TL)/10) =
+//     2^(x c1 + c0 + lg[column]) of the whole tile (ping_num <= 8 rows) lives in REGISTERS between the noise estimate
+//     (phase 1) and the noise removal / binning (phase 2): FFMA2 + one MUFU.EX2 per sample, shared memory is read
+//     once per sample;
+//   * the range-only terms (lg = log2(h / TL), TL) and the range-bin boundaries are computed once per range law
+//     (normally once per channel) and parked in shared memory;
+//   * noise estimate: column sums of u -> two partial sums per column group (toward the range tile of its first
+//     column and toward the next one) -> L lanes per range tile -> per-warp minima -> warp reduction;
+//   * noise removal in the u domain: the sample survives iff u > noise (1 + 10^(SNR/10)) (one tile-wide compare), the
+//     surviving u are summed per column and scaled once per tile: sum(Sv_corrected_lin) = TL (sum(u) - n noise);
+//   * (sum, count) of a thread's columns accumulate in registers ACROSS tiles while the ping bin does not change; on
+//     a bin change the column-group partial sums go through shared memory and eight lanes per range bin issue ONE
+//     float64 atomic triple per (CTA, range bin).
 // Handles the regular case: every tile's rows share one range law and have finite calibration constants (checked
-// on the device by classify_kernel; otherwise the general kernel of pipeline.cu runs instead), R % 4 == 0,
-// R <= 4096, ping_num <= 8, no full-size outputs.
+// on the device by prepare_kernel; otherwise the general kernel of pipeline.cu runs instead), R % 4 == 0 (8 for int16
+// input), R <= 4096, ping_num <= 8, range_sample_num >= 4, no full-size outputs.
 #pragma once
 #include "pipeline_common.cuh"
 
