@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(G == 1 ? EPB_G1_THREADS : 512 / (EPB_GBIG / 2)
   if (prod_warp && lane == 0) issue_tiles(-1);
 
   // group g of this thread owns columns n0 + g * 4 * nth .. +3; threads past the row end work on column 0 (their
-  // results are never stored: no colsum store, key -1 at flush), so the hot loads carry no predicates
+  // results are never stored: no partial-sum store, not stored at flush), so the hot loads carry no predicates
   int colg[G];
   bool liveg[G];
 #pragma unroll
