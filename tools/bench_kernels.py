@@ -75,10 +75,14 @@ def main():
         report("sv_power+range+minmax", ms, mn, 12 * n, n)
     if {"noise", "bins", "pipe", "pipe16", "masks", "pipex"} & set(which):
         extra(a, which, C, P, R, n, x, rows, out, rng, ed)
-    if "pulse" in which:
+    if "pulse" in which or "k2" in which:
         del x, out, rng, ed
         torch.cuda.empty_cache()
-        pulse(a)
+        if "k2" in which:
+            complex_cw(a)
+            torch.cuda.empty_cache()
+        if "pulse" in which:
+            pulse(a)
 
 
 def pulse(a):
@@ -112,6 +116,23 @@ def pulse(a):
                       "TFLOPs_fp32": round(flops / ms / 1e9, 2), "frac_of_fp32_peak_74.4": round(flops / ms / 1e9 / 74.4, 3),
                       "Gsamples_s": round(n / ms / 1e6, 2)}), flush=True)
     _ = out, rng
+
+
+def complex_cw(a):
+    """EK80 CW complex samples (K2): 6 ch x pings x 4096 samples x 4 beams, 36 algorithmic bytes per sample (40 with range)."""
+    from echopype_b200.calibrate.calibrate_ek import CalibrateEK80
+
+    C, P, R, B = 6, 8 * a.bb_pings, 4096, 4
+    ed = synth.make_ek80(C=C, P=P, R=R, B=B, mode="CW", encode="complex", device=True, nan_tail=0.005, seed=3100)
+    cal = CalibrateEK80(ed, waveform_mode="CW", encode_mode="complex")
+    cal._cal_complex_samples("Sv")
+    beam = ed["Sonar/Beam_group1"]
+    re, im = beam["backscatter_r"].data, beam["backscatter_i"].data
+    n = C * P * R
+    ms, mn = timeit(lambda: kernels.sv_complex(re, im, cal.rows, C, P, R, B, want_range=True), a.iters)
+    report("sv_complex (K2, 4 beams, + range)", ms, mn, 40 * n, n)
+    ms, mn = timeit(lambda: kernels.sv_complex(re, im, cal.rows, C, P, R, B, want_range=False), a.iters)
+    report("sv_complex (K2, 4 beams)", ms, mn, 36 * n, n)
 
 
 def extra(a, which, C, P, R, n, x, rows, out, rng, ed):
