@@ -345,6 +345,18 @@ def impulse_noise_mask_depth(Sv, depth, edges, C, P, R, num_side_pings, threshol
     return mask, means, first, up
 
 
+def transient_noise_mask_depth(Sv, depth, C, P, R, dmin, dmax, depth_bin, exclude_above, num_side_pings, threshold, want_pooled=False):
+    """Depth-value window variant (use_index_binning=False)."""
+    pre = torch.empty((C, P, R + 1), dtype=torch.float64, device=Sv.device)
+    cnt = torch.empty((C, P, R + 1), dtype=torch.int32, device=Sv.device)
+    mask = torch.empty((C, P, R), dtype=torch.uint8, device=Sv.device)
+    pooled = torch.empty((C, P, R), dtype=torch.float32, device=Sv.device) if want_pooled else None
+    _lib.call("epb_transient_noise_mask_depth", ptr(Sv), ptr(depth), ptr(pre), ptr(cnt), ptr(mask), ptr(pooled), C, P, R,
+              ctypes.c_double(float(dmin)), ctypes.c_double(float(dmax)), ctypes.c_double(float(depth_bin)),
+              ctypes.c_double(float(exclude_above)), int(num_side_pings), ctypes.c_float(float(threshold)), stream())
+    return mask, pooled
+
+
 def transient_noise_mask(Sv, nsamp, C, P, R, min_range_sample, num_side_pings, threshold, want_pooled=False, out=None):
     """out: optional (mask, window_sums) buffers to reuse."""
     ns = torch.from_numpy(np.ascontiguousarray(nsamp, dtype=np.int32)).to(Sv.device)

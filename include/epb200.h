@@ -266,6 +266,17 @@ int epb_transient_noise_mask(const float* Sv, const int* nsamp, float* window_su
                              epb_i64 C, epb_i64 P, epb_i64 R, int min_range_sample, int max_nsamp, int num_side_pings,
                              float threshold, void* stream);
 
+/* Transient noise with depth-VALUE windows (use_index_binning=False, clean/utils.py:28-105 pool_Sv, func = nanmean): for
+ * every sample whose depth d keeps [d - depth_bin, d + depth_bin] inside [depth_min, depth_max] (the extent of the range
+ * variable) and below exclude_above, and whose ping keeps p - k >= 0 and p + k <= P: pooled Sv = dB of the nanmean of
+ * 10^(Sv/10) over the samples of the channel with |depth - d| <= depth_bin in pings p - k .. p + k; NaN elsewhere;
+ * mask = Sv - pooled > threshold.  depth must increase along range_sample (NaN tails allowed).
+ * prefix_sums [C,P,R+1] float64 and prefix_counts [C,P,R+1] int32 are scratch; pooled_Sv NULL or [C,P,R] float32. */
+int epb_transient_noise_mask_depth(const float* Sv, const float* depth, double* prefix_sums, int* prefix_counts,
+                                   unsigned char* mask, float* pooled_Sv, epb_i64 C, epb_i64 P, epb_i64 R, double depth_min,
+                                   double depth_max, double depth_bin, double exclude_above, int num_side_pings, float threshold,
+                                   void* stream);
+
 /* ---- raw power ingest (convert/parse_base.py:24,302 `power = counts.astype(float32) * INDEX2POWER`, :686-730
  *      pad_shorter_ping): n int16 counts -> float32 dB, -32768 (padding marker) -> NaN. -------------------------- */
 int epb_ingest_power_i16(const short* counts, float* backscatter_r, epb_i64 n, void* stream);

@@ -239,3 +239,38 @@ def mask_impulse_noise_depth_binning(Sv, range_var, depth_bin, num_side_pings, i
     _, up = downsample_upsample_along_depth(Sv, range_var, depth_bin)
     mask = np.stack([echopy_impulse_noise_mask(up[c].T, num_side_pings, impulse_noise_threshold).T for c in range(Sv.shape[0])])
     return mask, up
+
+
+def pool_Sv(Sv, range_var, depth_bin, num_side_pings, exclude_above):
+    """clean/utils.py:28-105 with func = np.nanmean (the use_index_binning=False path of mask_transient_noise): for every
+    sample whose depth d keeps d +- depth_bin inside the depth extent of the dataset and below exclude_above and whose
+    ping keeps p - k >= 0 and p + k <= n_ping, the nanmean of 10^(Sv/10) over the samples of the same channel with
+    d - depth_bin <= depth <= d + depth_bin in the pings p - k .. p + k, in dB; NaN elsewhere."""
+    C, P, R = Sv.shape
+    dmin, dmax = np.nanmin(range_var), np.nanmax(range_var)
+    lin = log2lin(Sv)
+    pooled = np.full((C, P, R), np.nan)
+    k = num_side_pings
+    for c in range(C):
+        for p in range(P):
+            if not (p - k >= 0 and p + k <= P):
+                continue
+            q0, q1 = p - k, min(p + k, P - 1)
+            dep = range_var[c, q0 : q1 + 1]
+            win = lin[c, q0 : q1 + 1]
+            for n in range(R):
+                d = range_var[c, p, n]
+                if not ((d - depth_bin >= dmin) and (d + depth_bin <= dmax) and (d - depth_bin >= exclude_above)):
+                    continue
+                with np.errstate(invalid="ignore"):
+                    m = (d - depth_bin <= dep) & (dep <= d + depth_bin) & ~np.isnan(win)
+                if m.any():
+                    pooled[c, p, n] = lin2log(win[m].mean())
+    return pooled
+
+
+def mask_transient_noise_depth_binning(Sv, range_var, depth_bin, num_side_pings, exclude_above, transient_noise_threshold):
+    """clean/api.py:30-166 with use_index_binning=False, func="nanmean".  Returns (mask, pooled_Sv)."""
+    pooled = pool_Sv(Sv, range_var, depth_bin, num_side_pings, exclude_above)
+    with np.errstate(invalid="ignore"):
+        return (Sv - pooled) > transient_noise_threshold, pooled

@@ -173,7 +173,7 @@ def test_mask_noise_argument_errors(ep):
     with pytest.raises(ValueError, match="requires `echo_range` data variable"):
         ep.clean.mask_transient_noise(ds, range_var="echo_range", use_index_binning=True)
     with pytest.raises(NotImplementedError):
-        ep.clean.mask_transient_noise(ds, use_index_binning=False)
+        ep.clean.mask_transient_noise(ds, func="nanmedian")
 
 
 # ---- use_index_binning=False: intervals of depth VALUES (clean/utils.py:192-260) --------------------------------------
@@ -245,3 +245,35 @@ def test_mask_impulse_noise_depth_binning_vs_oracle(ep, k, depth_bin):
     upd = upd.cpu().numpy()
     np.testing.assert_array_equal(np.isnan(upd), np.isnan(up))
     assert np.nanmax(np.abs(upd - up)) < 1e-4  # upsampled_Sv of the reference, per sample
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,depth_bin,excl", [(2, "2m", "4m"), (3, "1m", "0m")])
+def test_mask_transient_noise_depth_windows_vs_oracle(ep, k, depth_bin, excl):
+    """The reference's default path (use_index_binning=False): windows of depth values, clean/utils.py:28-105."""
+    import torch
+
+    from echopype_b200 import kernels
+
+    db, ex = float(depth_bin[:-1]), float(excl[:-1])
+    Sv, _ = _mock(2, 14, 70, seed=21)
+    rng = np.random.default_rng(21)
+    off = rng.choice([0.0, 0.07, 0.13], size=(2, 14))
+    depth = (3.0 + off[:, :, None] + 0.19 * np.arange(70)[None, None, :]).astype(np.float32).astype(np.float64)
+    depth[0, 5, 35:] = np.nan  # the short ping of the mock: NaN range where the samples are padding
+    Sv32 = Sv.astype(np.float32).astype(np.float64)
+    thr = 3.0
+    want, pooled = oclean.mask_transient_noise_depth_binning(Sv32, depth, db, k, ex, thr)
+    got = ep.clean.mask_transient_noise(_ds(ep, Sv, depth), "nanmean", depth_bin, k, excl, "3.0dB", "depth")  # defaults otherwise
+    g = got.values.astype(bool)
+    with np.errstate(invalid="ignore"):
+        margin = np.abs((Sv32 - pooled) - thr)
+    sure = np.isnan(margin) | (margin > 1e-3)
+    assert sure.mean() > 0.99 and want.any() and (~np.isnan(pooled)).any() and np.isnan(pooled[:, :k]).all()
+    np.testing.assert_array_equal(g[sure], want[sure])
+    C, P, R = Sv.shape
+    _, pl = kernels.transient_noise_mask_depth(torch.from_numpy(Sv.astype(np.float32)).cuda(), torch.from_numpy(depth.astype(np.float32)).cuda(),
+                                               C, P, R, np.nanmin(depth), np.nanmax(depth), db, ex, k, thr, want_pooled=True)
+    pl = pl.cpu().numpy()
+    np.testing.assert_array_equal(np.isnan(pl), np.isnan(pooled))
+    assert np.nanmax(np.abs(pl - pooled)) < 1e-4
