@@ -73,6 +73,14 @@ def make_ek60(C=4, P=1000, R=1000, seed=1001, device=False, nan_tail=0.005, ping
             "transmit_power": (("channel", "ping_time"), np.repeat(cyc([2000, 2000, 250, 120, 750, 60])[:, None], P, 1)),
             "frequency_nominal": (("channel",), freqs),
             "equivalent_beam_angle": (("channel",), cyc([-17.0, -20.6, -20.7, -20.5, -20.7, -20.1])),
+            # split-beam angle parameters: not used by the power calibration, but the reference's
+            # get_cal_params_EK pulls them from the beam group for every EK60 file (cal_params.py:455-460)
+            "angle_offset_alongship": (("channel",), cyc([0.05, -0.08, 0.0, 0.02])),
+            "angle_offset_athwartship": (("channel",), cyc([-0.03, 0.06, 0.01, 0.0])),
+            "angle_sensitivity_alongship": (("channel",), cyc([15.5, 18.0, 23.0, 23.0])),
+            "angle_sensitivity_athwartship": (("channel",), cyc([15.5, 18.0, 23.0, 23.0])),
+            "beamwidth_twoway_alongship": (("channel",), cyc([10.9, 7.0, 6.8, 6.5])),
+            "beamwidth_twoway_athwartship": (("channel",), cyc([10.8, 7.1, 6.7, 6.6])),
         },
         coords={"channel": chan, "ping_time": pt, "range_sample": np.arange(R)},
     )
@@ -96,13 +104,16 @@ def make_ek60(C=4, P=1000, R=1000, seed=1001, device=False, nan_tail=0.005, ping
     return EchoData("EK60", {"Sonar/Beam_group1": beam, "Environment": env, "Vendor_specific": vend, "Platform": plat}, source_file="synthetic_ek60.raw")
 
 
-def make_azfp(C=4, P=1000, R=1000, seed=4001, device=False, ping_interval_s=1.0, ping_offset=0):
+def make_azfp(C=4, P=1000, R=1000, seed=4001, device=False, ping_interval_s=1.0, ping_offset=0, backscatter=None):
     """AZFP counts volume (cfg4)."""
     rng = np.random.default_rng(seed)
     freqs = np.resize(np.array([38e3, 125e3, 200e3, 455e3]), C)
     chan = np.array([f"55030-{int(f / 1000)}-{i + 1}" for i, f in enumerate(freqs)], dtype=object)
     pt = ping_times(P, ping_interval_s, offset=ping_offset)
-    if device:
+    if backscatter is not None:
+        x = backscatter
+        assert tuple(x.shape) == (C, P, R)
+    elif device:
         from . import kernels
 
         x = kernels.synth_fill((C, P, R), kind=1, seed=seed, nan_tail=0.0, ping_offset=ping_offset)
@@ -146,7 +157,8 @@ def _ek80_filters(C, rng):
     return wbt, pc
 
 
-def make_ek80(C=2, P=50, R=512, B=4, seed=3001, mode="BB", encode="complex", device=False, gpt_channel=None, nan_tail=0.02, ping_offset=0):
+def make_ek80(C=2, P=50, R=512, B=4, seed=3001, mode="BB", encode="complex", device=False, gpt_channel=None, nan_tail=0.02, ping_offset=0,
+              backscatter=None):
     """EK80 volume: mode "BB" (complex, pulse compression), "CW" with encode "complex" or "power" (cfg3 / cfg5)."""
     rng = np.random.default_rng(seed)
     freqs = np.resize(np.array([18e3, 38e3, 70e3, 120e3, 200e3, 333e3]), C)
@@ -176,7 +188,10 @@ def make_ek80(C=2, P=50, R=512, B=4, seed=3001, mode="BB", encode="complex", dev
     }
     if encode == "complex":
         coords["beam"] = np.arange(1, B + 1).astype(str)
-        if device:
+        if backscatter is not None:  # caller-supplied (re, im) pair of (C, P, R, B) float32 volumes
+            re, im = backscatter
+            assert tuple(re.shape) == tuple(im.shape) == (C, P, R, B)
+        elif device:
             from . import kernels
 
             re = kernels.synth_fill((C, P, R), kind=2, seed=seed, inner=B, nan_tail=nan_tail, scale=1e-3, ping_offset=ping_offset)
@@ -193,7 +208,10 @@ def make_ek80(C=2, P=50, R=512, B=4, seed=3001, mode="BB", encode="complex", dev
         dv["backscatter_i"] = (("channel", "ping_time", "range_sample", "beam"), im)
         descr = "complex_FM" if mode == "BB" else "complex_CW"
     else:
-        if device:
+        if backscatter is not None:
+            x = backscatter
+            assert tuple(x.shape) == (C, P, R)
+        elif device:
             from . import kernels
 
             x = kernels.synth_fill((C, P, R), kind=0, seed=seed, nan_tail=nan_tail, ping_offset=ping_offset)

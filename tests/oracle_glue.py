@@ -70,7 +70,7 @@ def azfp(ed, cal_type, salinity, pressure):
     return res
 
 
-def _ek80_replicas(beam, vend, waveform_mode):
+def _ek80_replicas(beam, vend, waveform_mode, drop_last_hanning_zero=False):
     C = len(_v(beam, "channel"))
     fs = _v(vend, "receiver_sampling_frequency").astype(np.float64)
     txs, fs_deci = [], []
@@ -86,14 +86,14 @@ def _ek80_replicas(beam, vend, waveform_mode):
         tx, t = ek80_signal.transmit_signal(
             waveform_mode, fs[c], float(_v(beam, "transmit_duration_nominal")[c, 0]), float(_v(beam, "slope")[c, 0]),
             float(_v(beam, "transmit_frequency_start")[c, 0]), float(_v(beam, "transmit_frequency_stop")[c, 0]),
-            float(_v(beam, "frequency_nominal")[c]), filt,
+            float(_v(beam, "frequency_nominal")[c]), filt, drop_last_hanning_zero,
         )
         txs.append(tx)
         fs_deci.append(1.0 / (t[1] - t[0]))
     return txs, np.asarray(fs_deci)
 
 
-def ek80(ed, cal_type, waveform_mode, encode_mode):
+def ek80(ed, cal_type, waveform_mode, encode_mode, drop_last_hanning_zero=False):
     beam, env, vend = ed["Sonar/Beam_group1"], ed["Environment"], ed["Vendor_specific"]
     C = len(_v(beam, "channel"))
     tau = _v(beam, "transmit_duration_nominal")
@@ -124,7 +124,7 @@ def ek80(ed, cal_type, waveform_mode, encode_mode):
         res["params"] = {"sound_speed": c, "sound_absorption": alpha, "gain_correction": gain, "sa_correction": sa,
                          "tau_effective": te}
         return res
-    txs, fs_deci = _ek80_replicas(beam, vend, waveform_mode)
+    txs, fs_deci = _ek80_replicas(beam, vend, waveform_mode, drop_last_hanning_zero)
     te = np.array([ek80_signal.tau_effective(txs[i], fs_deci[i], waveform_mode) for i in range(C)])
     te = np.where(is_gpt, tau[:, 0], te)
     if waveform_mode == "BB":
