@@ -64,15 +64,64 @@ def global_ping_edges(ping_time, ping_time_bin, group=None):
     return ping_time_edges(np.array([lo, hi], dtype="datetime64[ns]"), ping_time_bin)
 
 
-def straddle_plan(lo, hi, group):
+def straddle_plan(lo, hi, group, shard=None):
     """Gather the (first, last) global ping bin of every rank once (host ints): the bins a rank shares with its
-    neighbours depend only on the ping times, not on the data."""
+    neighbours depend only on the ping times, not on the data.
+
+    ``shard`` = (n_pings, first_ping_ns, last_ping_ns, ping_num) of this rank: the same collective carries it so
+    that the preconditions of ping-sharded execution are CHECKED instead of assumed - every rank but the last must
+    hold a multiple of ``ping_num`` pings (otherwise the coarsen(ping_time=ping_num, boundary="pad") noise tiles of
+    clean/api.py:403-407 would differ from the single-process tiling near every shard boundary) and the shards must
+    be time-ordered across ranks.  Violations raise ValueError on every rank."""
     dist = _dist()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    idx = torch.full((world, 2), -1, dtype=torch.int64, device=_comm_device(group))
+    idx = torch.full((world, 5), -1, dtype=torch.int64, device=_comm_device(group))
     idx[rank, 0], idx[rank, 1] = int(lo), int(hi)
+    if shard is not None:
+        idx[rank, 2], idx[rank, 3], idx[rank, 4] = int(shard[0]), int(shard[1]), int(shard[2])
+    # values are >= -1 except timestamps before 1970, which ping-sharded execution does not support
     dist.all_reduce(idx, op=dist.ReduceOp.MAX, group=group)
-    return {"world": world, "rank": rank, "lo": int(lo), "hi": int(hi), "slots": straddle_slots(idx.cpu().tolist(), lo, hi)}
+    tab = idx.cpu().tolist()
+    if shard is not None:
+        ping_num = int(shard[3])
+        held = [r for r in range(world) if tab[r][2] > 0]
+        for a, b in zip(held[:-1], held[1:]):
+            if ping_num > 1 and tab[a][2] % ping_num != 0:
+                raise ValueError(
+                    f"ping-sharded noise removal: rank {a} holds {tab[a][2]} pings, not a multiple of ping_num={ping_num}; "
+                    "only the last shard may be short (its last tile is padded like coarsen(boundary='pad'))"
+                )
+            if tab[a][4] > tab[b][3]:
+                raise ValueError(f"ping-sharded execution needs time-ordered shards: rank {a} ends after rank {b} starts")
+    windows = [t[:2] for t in tab]
+    plan = {"world": world, "rank": rank, "lo": int(lo), "hi": int(hi), "slots": straddle_slots(windows, lo, hi)}
+    plan.update(straddle_neighbours(windows, rank))
+    return plan
+
+
+def straddle_neighbours(windows, rank):
+    """Who shares this rank's first / last ping bin.  When every shared bin is held by exactly two (adjacent) ranks the
+    exchange is PAIRWISE: ``left`` / ``right`` are the ranks to swap one bin slice with (None: that edge is not shared)
+    and ``pairwise`` is True on every rank.  A bin held by three or more ranks (a shard that lies inside one ping bin)
+    makes ``pairwise`` False everywhere and the all-reduce path is used."""
+    holders = {}
+    for r, (lo, hi) in enumerate(windows):
+        if lo < 0 or hi < lo:
+            continue
+        for b in {int(lo), int(hi)}:
+            holders.setdefault(b, []).append(r)
+    pairwise = all(len(v) <= 2 for v in holders.values())
+    lo, hi = windows[rank]
+    left = right = None
+    if pairwise and lo >= 0 and hi >= lo:
+        for b, v in holders.items():
+            if len(v) == 2 and rank in v:
+                other = v[0] if v[1] == rank else v[1]
+                if b == int(lo) and other < rank:
+                    left = other
+                if b == int(hi) and other > rank:
+                    right = other
+    return {"pairwise": pairwise, "left": left, "right": right}
 
 
 def straddle_slots(idx, lo, hi):
@@ -159,6 +208,48 @@ def straddle_exchange_cuda(acc, rmax, plan, group):
     return out
 
 
+def straddle_exchange_p2p(acc, plan, group):
+    """Pairwise form of the straddling-bin exchange over NCCL point-to-point (ONE grouped send/recv launch): the own
+    first / last ping-bin slices are packed (epb_straddle_pack), the first goes to ``left``, the last to ``right``, the
+    neighbours' slices land in the inbox half of the same buffer and epb_straddle_unpack adds them to the own edge bins.
+    Only neighbours synchronise - an N-rank all-reduce would expose the skew of the slowest rank to every rank."""
+    from . import _lib
+    from .device import ptr, stream
+
+    dist = _dist()
+    C, nXl, nR, _ = acc.shape
+    S = C * nR * 4
+    W = 2 * S + 1
+    st = plan.setdefault("_p2p", {})
+    left, right = plan["left"], plan["right"]
+    single = plan["hi"] == plan["lo"]
+    if st.get("W") != W:
+        src = np.zeros((2, 2), dtype=np.int32)  # entries: 0 own first, 1 own last, 2 inbox from left, 3 inbox from right
+        n0 = n1 = 0
+        first = [0] + ([2] if left is not None else []) + ([3] if (single and right is not None) else [])
+        if len(first) > 1:
+            src[0, : len(first)], n0 = first[:2], min(len(first), 2)
+        if not single and right is not None:
+            src[1, :2], n1 = [1, 3], 2
+        if len(first) > 2:  # a one-bin shard shared with both neighbours would need three sources: not pairwise by construction
+            raise RuntimeError("internal: pairwise straddle plan with a three-way bin")
+        st.update(W=W, buf=torch.empty(2 * W, dtype=torch.float64, device=acc.device), src=torch.from_numpy(src).to(acc.device), n0=n0, n1=n1)
+    buf = st["buf"]
+    _lib.call("epb_straddle_pack", ptr(acc), C, nXl, nR, None, 0, ptr(buf), 0, 2, int(not single), stream())
+    ops = []
+    if left is not None:
+        ops.append(dist.P2POp(dist.isend, buf[0:S], left, group))
+        ops.append(dist.P2POp(dist.irecv, buf[W : W + S], left, group))
+    if right is not None:
+        ops.append(dist.P2POp(dist.isend, buf[0:S] if single else buf[S : 2 * S], right, group))
+        ops.append(dist.P2POp(dist.irecv, buf[W + S : W + 2 * S], right, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        _lib.call("epb_straddle_unpack", ptr(buf), ptr(st["src"]), st["n0"], st["n1"], C, nXl, nR, 2, ptr(acc), None, stream())
+    return 2 if ops else 1
+
+
 class FusedPlan:
     """Host-side assembly of one fused Sv -> noise -> MVBS job; :meth:`run` launches the device work.
 
@@ -202,6 +293,7 @@ class FusedPlan:
         self.skipna, self.fill_value, self.keep, self.group = skipna, fill_value, tuple(keep), group
         self.range_var_max = range_var_max
         self.fast = bool(fast)  # False: force the general kernel (tests compare the two)
+        self.p2p = True  # ping-sharded: pairwise neighbour exchange when the plan allows it (False: always all-reduce)
 
         self.dev = require_cuda()
         self.cal_obj = CALIBRATOR[echodata.sonar_model](
@@ -235,7 +327,12 @@ class FusedPlan:
         self.record_events = False  # bench.py: CUDA events around every fused-kernel launch -> kernel_events
         self.kernel_events = []
         self.comm_events = []  # bench.py: events around the straddling-bin / range-maximum collectives of a step
-        self._splan = straddle_plan(self.x_lo, self.x_hi, group) if group is not None else None
+        if group is not None:
+            pt_ns = pt.astype("datetime64[ns]").astype(np.int64)
+            shard = (self.P, int(pt_ns[0]) if self.P else -1, int(pt_ns[-1]) if self.P else -1, self.ping_num if self.do_noise else 1)
+            self._splan = straddle_plan(self.x_lo, self.x_hi, group, shard)
+        else:
+            self._splan = None
         self._ub = None  # cached upper bound of the range grid (depends on the parameters only, not on the samples)
 
     # ---- device work ------------------------------------------------------------------------------------------
@@ -318,7 +415,14 @@ class FusedPlan:
             if self.record_events:
                 cev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 cev[0].record()
-            if acc.is_cuda and _dist().get_backend(self.group) == "nccl":
+            if acc.is_cuda and _dist().get_backend(self.group) == "nccl" and self._splan["pairwise"] and self.p2p:
+                self.launches += straddle_exchange_p2p(acc, self._splan, self.group)
+                if rmax is not None:  # global nanmax(echo_range): needed when the grid is read (wrap), not by the bins;
+                    # the 1-double max all-reduce runs asynchronously on NCCL's stream, off the critical path
+                    if rmax.numel() > 1:
+                        rmax = rmax.max().reshape(1)
+                    rmax._work = _dist().all_reduce(rmax, op=_dist().ReduceOp.MAX, group=self.group, async_op=True)
+            elif acc.is_cuda and _dist().get_backend(self.group) == "nccl":
                 rmax = straddle_exchange_cuda(acc, rmax, self._splan, self.group)
                 self.launches += 2
             else:
@@ -397,12 +501,21 @@ class FusedPlan:
                 i += 1
         return rmax_t
 
+    @staticmethod
+    def wait_rmax(rmax):
+        """make the asynchronous global range maximum of a ping-sharded run visible to the current stream"""
+        work = getattr(rmax, "_work", None)
+        if work is not None:
+            work.wait()
+            rmax._work = None
+
     def wrap(self, mvbs, acc, rmax, outs, noise):
         """Dataset with the variables / coords / attrs of compute_MVBS (commongrid/api.py:130-189).  Reads the exact
         range maximum (one host synchronisation) and cuts the upper-bound range grid back to it."""
         beam = self.beam
         e_ub = self._ub[0]
         if rmax is not None:
+            self.wait_rmax(rmax)
             v = float(rmax.max().item())
             r_edges = range_edges(float("nan") if v == float("-inf") else v, self.rb)
         else:
