@@ -25,8 +25,8 @@ One "step" = one pass of the chain over the whole volume (inputs far exceed the 
 * N > 1 (torchrun, one rank per GPU): by default WEAK scaling (every rank holds its own 100 000-ping shard of one
   global, time-ordered volume).  The ping axis starts 10 s after a 20 s bin edge, so EVERY shard boundary falls inside
   a ping bin: the straddling-bin exchange merges real partial sums.  `config.verified`: on a reduced volume the
-  N-rank grid is compared on rank 0 with the single-GPU grid of the concatenated volume (counts bit-equal,
-  sums to 1e-12 relative, MVBS to 1e-6 dB).
+  N-rank grid is compared on rank 0 with the single-GPU grid of the concatenated volume (member counts bit-equal,
+  linear sums to a few float32 ulp, MVBS within 2 float32 ulp of the dB value).
 * `cpu_baseline` (rank 0, N = 1) and `--impl reference`: the numpy float64 oracle (a port of the reference's operation
   sequence, pinned to outputs of the reference's own code by tests/test_reference_pinned.py; echopype itself cannot
   be imported in this image) on one core / ping-sharded over all host cores, bounded samples.
@@ -459,7 +459,7 @@ def verify_sharded(ctx, name, P_v):
         plan1 = pipeline.FusedPlan(ed1, group=None, **kw)
         _, acc1, rmax1, _, _ = plan1.run(finalize=False)
         mv1, _ = kernels.bin_finalize(acc1, to_db=True)
-        ok_counts, ok_sums, max_db, shared, nan_same = True, True, 0.0, 0, True
+        ok_counts, max_rel, max_db, shared, nan_same = True, 0.0, 0.0, 0, True
         owners = torch.zeros(nX_g, dtype=torch.int64, device="cuda")
         nR = min(acc1.shape[2], accs[0].shape[2])
         for r in range(ctx.world):
@@ -469,7 +469,8 @@ def verify_sharded(ctx, name, P_v):
             owners[lo : hi + 1] += 1
             a, b = accs[r][:, lo : hi + 1, :nR], acc1[:, lo : hi + 1, :nR]
             ok_counts &= bool(torch.equal(a[..., 1], b[..., 1]) and torch.equal(a[..., 2], b[..., 2]))
-            ok_sums &= bool(torch.allclose(a[..., 0], b[..., 0], rtol=1e-12, atol=0.0))
+            rel = ((a[..., 0] - b[..., 0]).abs() / b[..., 0].abs().clamp_min(1e-300))[b[..., 1] > 0]
+            max_rel = max(max_rel, float(rel.max()) if rel.numel() else 0.0)
             g, w = mvs[r][:, lo : hi + 1, :nR], mv1[:, lo : hi + 1, :nR]
             nan_same &= bool(torch.equal(torch.isnan(g), torch.isnan(w)))
             d = (g - w).abs()
@@ -477,8 +478,12 @@ def verify_sharded(ctx, name, P_v):
             max_db = max(max_db, float(d.max()) if d.numel() else 0.0)
         shared = int((owners > 1).sum())
         rmax_ok = bool(rmax is None or abs(float(rm) - float(rmax1.max())) == 0.0)
-        result = {"ok": bool(ok_counts and ok_sums and nan_same and max_db <= 1e-6 and shared >= ctx.world - 1 and rmax_ok),
-                  "counts_bit_equal": ok_counts, "sums_rtol_1e-12": ok_sums, "nan_masks_equal": nan_same, "max_abs_dB": max_db,
+        # member counts are integers: bit-equal.  Linear sums: float32 partial sums per CTA (their grouping depends on the
+        # tile -> CTA assignment, which differs between the two runs) added into float64 cells: equal to a few float32 ulp.
+        # The MVBS itself is a float32 dB value: 1 ulp at -70 dB is 7.6e-6 dB.
+        result = {"ok": bool(ok_counts and max_rel <= 4e-6 and nan_same and max_db <= 1.6e-5 and shared >= ctx.world - 1 and rmax_ok),
+                  "counts_bit_equal": ok_counts, "max_rel_diff_of_linear_sums": max_rel, "nan_masks_equal": nan_same, "max_abs_dB": max_db,
+                  "tolerance": "counts bit-equal; sums 4e-6 relative (float32 partials); MVBS 1.6e-5 dB (2 float32 ulp of the dB value)",
                   "ping_bins_shared_by_two_ranks": shared, "range_max_equal": rmax_ok,
                   "volume": f"{ctx.world} ranks x ({C}ch x {P_v} ping x {R} range) vs one GPU on the concatenated {P_v * ctx.world} pings"}
         del xcat, ed1, plan1, acc1, mv1
