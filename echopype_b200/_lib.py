@@ -44,6 +44,9 @@ SIGNATURES = {
     "epb_sv_power_i16": (c_int, [vp, vp, vp, vp, vp, i64, i64, i64, vp]),
     "epb_sv_complex": (c_int, [vp, vp, vp, vp, vp, vp, i64, i64, i64, c_int, vp]),
     "epb_pulse_compress_sv": (c_int, [vp, vp, vp, POINTER(c_int), vp, vp, vp, vp, vp, vp, i64, i64, i64, c_int, vp]),
+    "epb_pulse_fft_workspace_bytes": (i64, [i64]),
+    "epb_pulse_fft_max_taps": (c_int, []),
+    "epb_pulse_compress_sv_fft": (c_int, [vp, vp, vp, POINTER(c_int), vp, vp, vp, vp, vp, vp, i64, i64, i64, c_int, vp, i64, vp]),
     "epb_noise_estimate": (c_int, [vp, vp, epb_cp, vp, i64, i64, i64, c_int, c_int, c_float, vp]),
     "epb_noise_apply": (c_int, [vp, vp, epb_cp, vp, vp, vp, vp, i64, i64, i64, c_int, c_float, vp]),
     "epb_bin_reduce": (c_int, [vp, vp, c_int, vp, vp, c_int, c_int, c_int, vp, i64, i64, i64, i64, vp]),

@@ -1,0 +1,470 @@
+// K3, FFT form: EK80 broadband pulse compression (matched filter) by overlap-save FFT in shared memory, fused with the
+// Sv / TS epilogue.  Same contract as pulse.cu (the direct form, kept for replicas longer than 2049 taps).
+//
+// Reference: compress_pulse + _convolve_per_channel (calibrate/ek80_complex.py:285-369): per (ping, beam) and channel
+//   y[n] = sum_{k<M} x[n+k] conj(tx[k])   (scipy.signal.convolve with the flipped conjugate replica, "full"[M-1:])
+// NaN samples zeroed before and restored after, normalised by ||tx||^2 (get_norm_fac :372-391), then
+// _get_power_from_complex (calibrate_ek.py:483-490) and the Sv / TS chain of _cal_complex_samples (:564-637).
+// scipy is free to evaluate that convolution by FFT; so is this kernel:
+//
+//   * a ping is cut into segments of L = 4096 - M + 1 outputs; each segment is one 4096-point circular correlation
+//     IFFT(FFT(x) * conj(FFT(tx))) whose first L outputs are exact (overlap-save).  8 M flop per sample become
+//     ~ 2 * 5 N log2 N / L: 17x less arithmetic at M = 277, which moves K3 from the FP32 pipes to the HBM roofline.
+//   * 256 threads, 16 points per thread, radix 16 x 16 x 16.  Forward = decimation in frequency (digit-reversed
+//     spectrum), inverse = decimation in time from the digit-reversed spectrum: no reordering pass, every pass is in
+//     place on the same 16 positions {i + m j}.  The last forward pass, the spectrum product and the first inverse
+//     pass touch the same 16 consecutive points and stay in registers.  The first forward pass reads its points
+//     straight from global memory (coalesced: position t + 256 j), the last inverse pass leaves the outputs of the same
+//     positions in registers for the epilogue: 4 shared-memory round trips per segment.
+//   * shared-memory index p -> p + (p >> 4) (one pad per 16 points): every pass is bank-conflict free.
+//   * twiddles come from tables computed in float64 (sincospi) by the setup kernel, laid out k-major so a warp reads
+//     consecutive entries; the replica spectrum H = conj(FFT(tx)) / (N ||tx||^2) is computed by the same setup kernel
+//     (direct float64 DFT of the M taps) in the register order of the fused pass.
+//   * the four beams are summed on the way in (the correlation is linear and NaN padding is normally identical across
+//     beams); a segment whose beams carry different NaN masks runs the transform once per beam and forms the exact
+//     nanmean (xarray mean(dim="beam") skips NaN, calibrate_ek.py:484).
+// Precision: float32 transforms with exact twiddles give ~1.6e-7 of the ping's RMS output per sample (the direct
+// float32 sum over 277 taps: 3.7e-7); the reference itself stores the compressed samples as complex64.
+#include "sample_math.cuh"
+
+namespace {
+using namespace epb;
+
+constexpr int kN = 4096;
+constexpr int kT = 256;
+constexpr int kPadN = kN + kN / 16;
+constexpr int kMaxChan = 32;
+
+struct FftParams {
+  const float* re;
+  const float* im;
+  const float2* H;    // [C][16][256]
+  const float2* tw1;  // [16][256]  w_4096^(i k), k major
+  const float2* tw2;  // [16][16]   w_256^(i k), k major
+  const int* lead0;   // [C] number of leading taps that are exactly zero
+  const epb_row* rows;
+  float* out;
+  float* rng;
+  float2* pc_out;
+  float* minmax;
+  long long nrows, P;
+  int R, L, nseg;
+};
+
+__device__ __forceinline__ int pad(int p) { return p + (p >> 4); }
+// TMA prefetch of a contiguous global range into L2 (one instruction, no registers held): the next segment's samples
+// are already on chip when its loads are issued
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x)); }
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {  // a * conj(b)
+  return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+template <bool kInv>
+__device__ __forceinline__ void dft4(float2& x0, float2& x1, float2& x2, float2& x3) {
+  const float2 t0 = cadd(x0, x2), t1 = csub(x0, x2), t2 = cadd(x1, x3), t3 = csub(x1, x3);
+  x0 = cadd(t0, t2);
+  x2 = csub(t0, t2);
+  if (!kInv) {  // forward: w4 = -i
+    x1 = make_float2(t1.x + t3.y, t1.y - t3.x);
+    x3 = make_float2(t1.x - t3.y, t1.y + t3.x);
+  } else {
+    x1 = make_float2(t1.x - t3.y, t1.y + t3.x);
+    x3 = make_float2(t1.x + t3.y, t1.y - t3.x);
+  }
+}
+
+// 16-point DFT of v[0..15] (natural order in, natural order out); kInv: conjugate kernel, no scaling
+template <bool kInv>
+__device__ __forceinline__ void dft16(float2 (&v)[16]) {
+  constexpr float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, h = 0.70710678118654752f;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) dft4<kInv>(v[a], v[a + 4], v[a + 8], v[a + 12]);  // v[a + 4 d] = S_a[d]
+  // twiddle w16^(a d), forward (cos, -sin); inverse conjugate
+  const float sg = kInv ? 1.f : -1.f;
+  // exponents: (a,d) -> a*d : 1:(1,1) 2:(1,2),(2,1) 3:(1,3),(3,1) 4:(2,2) 6:(2,3),(3,2) 9:(3,3)
+  auto tw = [&](float2& z, float cr, float ci) { z = make_float2(z.x * cr - z.y * (sg * ci), z.x * (sg * ci) + z.y * cr); };
+  tw(v[1 + 4 * 1], c1, s1);
+  tw(v[1 + 4 * 2], h, h);
+  tw(v[2 + 4 * 1], h, h);
+  tw(v[1 + 4 * 3], s1, c1);
+  tw(v[3 + 4 * 1], s1, c1);
+  {  // exponent 4: multiply by -i (forward) / +i (inverse)
+    float2& z = v[2 + 4 * 2];
+    z = kInv ? make_float2(-z.y, z.x) : make_float2(z.y, -z.x);
+  }
+  tw(v[2 + 4 * 3], -h, h);
+  tw(v[3 + 4 * 2], -h, h);
+  tw(v[3 + 4 * 3], -c1, -s1);
+#pragma unroll
+  for (int d = 0; d < 4; ++d) dft4<kInv>(v[4 * d], v[4 * d + 1], v[4 * d + 2], v[4 * d + 3]);  // v[4 d + c] = X[d + 4 c]
+  float2 o[16];
+#pragma unroll
+  for (int d = 0; d < 4; ++d)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) o[d + 4 * c] = v[4 * d + c];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = o[k];
+}
+
+// one 4096-point circular correlation with the replica spectrum: v[j] = x[t + 256 j] in, y[t + 256 j] out
+__device__ __forceinline__ void correlate(float2 (&v)[16], float2* __restrict__ s, const float2* __restrict__ s_tw1,
+                                          const float2* __restrict__ s_tw2, const float2* __restrict__ Hc, int t) {
+  // ---- forward pass 1 (n = 4096, m = 256): registers -> shared ---------------------------------------------------
+  dft16<false>(v);
+  s[pad(t)] = v[0];
+#pragma unroll
+  for (int k = 1; k < 16; ++k) s[pad(t + 256 * k)] = cmul(v[k], s_tw1[k * 256 + t]);
+  __syncthreads();
+  // ---- forward pass 2 (n = 256, m = 16) ------------------------------------------------------------------------------
+  const int blk = t >> 4, i2 = t & 15;
+  const int b2 = blk * 256 + i2;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = s[pad(b2 + 16 * j)];
+  dft16<false>(v);
+  s[pad(b2)] = v[0];
+#pragma unroll
+  for (int k = 1; k < 16; ++k) s[pad(b2 + 16 * k)] = cmul(v[k], s_tw2[k * 16 + i2]);
+  __syncthreads();
+  // ---- forward pass 3 (n = 16) * H, inverse pass 1 (n = 16): registers only -------------------------------------------
+  const int b3 = 17 * t;  // pad(16 t + j) = 17 t + j
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = s[b3 + j];
+  dft16<false>(v);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = cmul(v[k], __ldg(Hc + k * 256 + t));
+  dft16<true>(v);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) s[b3 + j] = v[j];
+  __syncthreads();
+  // ---- inverse pass 2 (n = 256, m = 16) -------------------------------------------------------------------------------
+  v[0] = s[pad(b2)];
+#pragma unroll
+  for (int k = 1; k < 16; ++k) v[k] = cmulc(s[pad(b2 + 16 * k)], s_tw2[k * 16 + i2]);
+  dft16<true>(v);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) s[pad(b2 + 16 * j)] = v[j];
+  __syncthreads();
+  // ---- inverse pass 3 (n = 4096, m = 256): shared -> registers ------------------------------------------------------------
+  v[0] = s[pad(t)];
+#pragma unroll
+  for (int k = 1; k < 16; ++k) v[k] = cmulc(s[pad(t + 256 * k)], s_tw1[k * 256 + t]);
+  dft16<true>(v);
+  __syncthreads();  // the next transform overwrites the work buffer
+}
+
+// y[t + 256 j] of one segment -> Sv / TS, echo_range, optional compressed samples and min / max.
+// cnt4: 4 bits per point = number of beams whose sample is valid (the nanmean divisor); nanre0: bit j = beam-0 real part NaN.
+template <int B, bool kUniform>
+__device__ __forceinline__ void epilogue(const FftParams& pr, const float2 (&v)[16], long long row, long long base, int n0, int nout, int t,
+                                         unsigned long long cnt4, unsigned okmask, unsigned nanre0, int zero_from, MinMax& mm_v,
+                                         MinMax& mm_r) {
+  const RowF rc = load_rowf(pr.rows + row);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int q = t + 256 * j;
+    if (q < nout) {
+      const int n = n0 + q;
+      float sc;
+      bool any;
+      if (kUniform) {  // every beam valid or none
+        sc = 1.f / (float)B;
+        any = (okmask >> j) & 1u;
+      } else {
+        const int cnt = (int)((cnt4 >> (4 * j)) & 15ull);
+        sc = 1.f;  // 1 / cnt as selects
+        sc = (cnt == 2) ? 0.5f : sc;
+        sc = (cnt == 3) ? (1.f / 3.f) : sc;
+        sc = (cnt == 4) ? 0.25f : sc;
+        any = cnt > 0;
+      }
+      // outputs whose every product is exactly zero (the replica starts with zero taps - the Hann taper does - and only
+      // zero samples follow) are exactly zero in the reference's sum, hence NaN after prx.where(prx > 0)
+      // (calibrate_ek.py:581); a transform would leave rounding noise there
+      const bool exact0 = q >= zero_from;
+      const float mr = exact0 ? 0.f : v[j].x * sc, mi = exact0 ? 0.f : v[j].y * sc;
+      const float prx = rc.fscale * fmaf(mr, mr, mi * mi);
+      const float fr = (any && prx > 0.f) ? fmaf(kLog2ToDb, fast_log2(prx), rc.foffK) : CUDART_NAN_F;  // calibrate_ek.py:581
+      const float nf = (float)n;
+      float rr = range_of(rc, nf);
+      float o = sv_db(rc, n, nf, fr);
+      if ((nanre0 >> j) & 1u) rr = CUDART_NAN_F, o = CUDART_NAN_F;  // range.py:143-145: NaN where beam 0 of backscatter_r is
+      st_stream(pr.out + base + n, o);
+      if (pr.rng) st_stream(pr.rng + base + n, rr);
+      if (pr.pc_out) pr.pc_out[base + n] = any ? make_float2(mr, mi) : make_float2(CUDART_NAN_F, CUDART_NAN_F);
+      if (pr.minmax) {
+        mm_v.add(o);
+        mm_r.add(rr);
+      }
+    }
+  }
+}
+
+// cold path: the beams of this segment carry different NaN masks.  One transform per beam; beam b's output counts only
+// where beam b's input sample is valid (the exact nanmean over beams of calibrate_ek.py:484).  Everything is passed by
+// value: a reference to the kernel parameters or to the caller's running min / max would force them into local memory
+// on the hot path as well.
+template <int B>
+__device__ __noinline__ void per_beam_segment(const FftParams pr, float2* __restrict__ s, const float2* __restrict__ s_tw1,
+                                              const float2* __restrict__ s_tw2, const float2* __restrict__ Hc, long long row,
+                                              long long base, int n0, int nout, int t, unsigned nanre0, int zero_from) {
+  MinMax mm_v, mm_r;
+  float2 acc[16], v[16];
+  unsigned long long valid = 0ull, cnt4 = 0ull;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    acc[j] = make_float2(0.f, 0.f);
+    const int n = n0 + t + 256 * j;
+    unsigned fl = 0u;
+    if (n < pr.R)
+      for (int b = 0; b < B; ++b) {
+        const float xr = pr.re[(base + n) * B + b], xi = pr.im[(base + n) * B + b];
+        fl |= (xr == xr && xi == xi) ? (1u << b) : 0u;  // a complex sample is NaN if either part is
+      }
+    valid |= (unsigned long long)fl << (4 * j);
+    cnt4 |= (unsigned long long)__popc(fl) << (4 * j);
+  }
+  for (int b = 0; b < B; ++b) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int n = n0 + t + 256 * j;
+      const bool ok = (valid >> (4 * j + b)) & 1ull;
+      v[j] = ok ? make_float2(pr.re[(base + n) * B + b], pr.im[(base + n) * B + b]) : make_float2(0.f, 0.f);
+    }
+    correlate(v, s, s_tw1, s_tw2, Hc, t);
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if ((valid >> (4 * j + b)) & 1ull) acc[j] = cadd(acc[j], v[j]);
+  }
+  epilogue<B, false>(pr, acc, row, base, n0, nout, t, cnt4, 0u, nanre0, zero_from, mm_v, mm_r);
+  if (pr.minmax) {
+    mm_v.flush(pr.minmax + 0, pr.minmax + 1);
+    mm_r.flush(pr.minmax + 2, pr.minmax + 3);
+  }
+}
+
+template <int B>
+__global__ void __launch_bounds__(kT, 2) pulse_fft_kernel(const FftParams pr) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* s = reinterpret_cast<float2*>(smem_raw);  // [kPadN]
+  float2* s_tw1 = s + kPadN;                         // [4096]
+  float2* s_tw2 = s_tw1 + 4096;                      // [256]
+  int* s_wmax = reinterpret_cast<int*>(s_tw2 + 256);  // [8] per-warp last nonzero input position of the segment
+  const int t = threadIdx.x;
+  for (int k = t; k < 4096; k += kT) s_tw1[k] = pr.tw1[k];
+  s_tw2[t] = pr.tw2[t];
+  __syncthreads();
+  const int R = pr.R, L = pr.L;
+  MinMax mm_v, mm_r;
+
+  for (long long row = blockIdx.x; row < pr.nrows; row += gridDim.x) {
+    const int c = (int)(row / pr.P);
+    const float2* Hc = pr.H + (size_t)c * kN;
+    const int lead0 = __ldg(pr.lead0 + c);
+    const long long base = row * (long long)R;
+    for (int seg = 0; seg < pr.nseg; ++seg) {
+      const int n0 = seg * L;
+      const int nout = min(L, R - n0);  // outputs of this segment
+      // ---- load: x[n0 + t + 256 j], beams summed; four points (8 x 16 bytes) in flight.  A NaN anywhere in the point
+      //      makes the plain sum NaN: only then the per-beam validity is worked out (NaN -> 0). ---------------------------------
+      float2 v[16];
+      unsigned okmask = 0u;   // bit j: every beam of point j is valid
+      unsigned nanre0 = 0u;   // bit j: beam-0 real part is NaN (range.py:143-145)
+      int nonuniform = 0;     // some point has valid and invalid beams: the per-beam path
+      int last_nz = -1;       // last position of this thread holding a nonzero (summed) sample
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float xr[4][B], xi[4][B];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int n = n0 + t + 256 * (4 * g + u);
+          const long long e = (base + (n < R ? n : 0)) * B;  // clamped address; the value is discarded below
+          if (B == 4) {
+            const float4 a4 = ld_stream4(reinterpret_cast<const float4*>(pr.re + e));
+            const float4 b4 = ld_stream4(reinterpret_cast<const float4*>(pr.im + e));
+            xr[u][0] = a4.x, xr[u][1 % B] = a4.y, xr[u][2 % B] = a4.z, xr[u][3 % B] = a4.w;
+            xi[u][0] = b4.x, xi[u][1 % B] = b4.y, xi[u][2 % B] = b4.z, xi[u][3 % B] = b4.w;
+          } else {
+#pragma unroll
+            for (int bb = 0; bb < B; ++bb) {
+              xr[u][bb] = ld_stream(pr.re + e + bb);
+              xi[u][bb] = ld_stream(pr.im + e + bb);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = 4 * g + u;
+          const bool inside = (n0 + t + 256 * j) < R;
+          float sr = xr[u][0], si = xi[u][0];
+#pragma unroll
+          for (int bb = 1; bb < B; ++bb) sr += xr[u][bb], si += xi[u][bb];
+          const bool clean = (sr == sr) && (si == si);  // finite inputs: the sum is NaN iff some part is NaN
+          if (inside && !clean) {                        // rare: NaN padding / missing sectors
+            unsigned fl = 0u;
+            sr = 0.f, si = 0.f;
+#pragma unroll
+            for (int bb = 0; bb < B; ++bb) {
+              const bool ok = (xr[u][bb] == xr[u][bb]) && (xi[u][bb] == xi[u][bb]);
+              sr += ok ? xr[u][bb] : 0.f;
+              si += ok ? xi[u][bb] : 0.f;
+              fl |= ok ? (1u << bb) : 0u;
+            }
+            nanre0 |= (xr[u][0] != xr[u][0]) ? (1u << j) : 0u;
+            nonuniform |= (fl != 0u);  // fl != all here
+          }
+          okmask |= (inside && clean) ? (1u << j) : 0u;
+          v[j] = inside ? make_float2(sr, si) : make_float2(0.f, 0.f);
+          last_nz = (inside && (sr != 0.f || si != 0.f)) ? (t + 256 * j) : last_nz;
+        }
+      }
+      if (B == 4 && t == 0) {  // while this segment is transformed, the next one streams from HBM into L2
+        long long nrow = row;
+        int nn0 = n0 + L;
+        if (seg + 1 >= pr.nseg) nrow = row + gridDim.x, nn0 = 0;
+        if (nrow < pr.nrows) {
+          const unsigned bytes = (unsigned)min(kN, R - nn0) * 16u;
+          prefetch_l2_bulk(pr.re + (nrow * (long long)R + nn0) * 4, bytes);
+          prefetch_l2_bulk(pr.im + (nrow * (long long)R + nn0) * 4, bytes);
+        }
+      }
+      last_nz = __reduce_max_sync(0xffffffffu, last_nz);
+      if ((t & 31) == 0) s_wmax[t >> 5] = last_nz;
+      nonuniform = __syncthreads_or(nonuniform);
+#pragma unroll
+      for (int w = 0; w < kT / 32; ++w) last_nz = max(last_nz, s_wmax[w]);
+      const int zero_from = last_nz - lead0 + 1;  // outputs q >= zero_from see only zero taps or zero samples
+      if (!nonuniform) {
+        correlate(v, s, s_tw1, s_tw2, Hc, t);
+        epilogue<B, true>(pr, v, row, base, n0, nout, t, 0ull, okmask, nanre0, zero_from, mm_v, mm_r);
+      } else {
+        per_beam_segment<B>(pr, s, s_tw1, s_tw2, Hc, row, base, n0, nout, t, nanre0, zero_from);
+      }
+    }
+  }
+  if (pr.minmax) {
+    mm_v.flush(pr.minmax + 0, pr.minmax + 1);
+    mm_r.flush(pr.minmax + 2, pr.minmax + 3);
+  }
+}
+
+// twiddle tables and the replica spectra, float64 arithmetic (exact to float32 rounding)
+__global__ void __launch_bounds__(256) pulse_fft_setup_kernel(const float2* __restrict__ replica, const double* __restrict__ inv_norm,
+                                                              int C, const int* __restrict__ off, float2* __restrict__ H,
+                                                              float2* __restrict__ tw1, float2* __restrict__ tw2, int* __restrict__ lead0) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.y == 0) {  // tables
+    if (g < C) {
+      int z = 0;
+      const int M = off[g + 1] - off[g];
+      while (z < M && replica[off[g] + z].x == 0.f && replica[off[g] + z].y == 0.f) ++z;
+      lead0[g] = z;
+    }
+    if (g < 4096) {
+      const int k = g >> 8, i = g & 255;
+      double sn, cs;
+      sincospi(-2.0 * (double)(i * k) / 4096.0, &sn, &cs);
+      tw1[g] = make_float2((float)cs, (float)sn);
+    }
+    if (g < 256) {
+      const int k = g >> 4, i = g & 15;
+      double sn, cs;
+      sincospi(-2.0 * (double)(i * k) / 256.0, &sn, &cs);
+      tw2[g] = make_float2((float)cs, (float)sn);
+    }
+    return;
+  }
+  const int c = blockIdx.y - 1;
+  if (c >= C || g >= kN) return;
+  // entry g = k * 256 + t of channel c: spectrum at the natural frequency f of work position 16 t + k (digit reversed)
+  const int k = g >> 8, t = g & 255;
+  const int f = (t >> 4) + 16 * (t & 15) + 256 * k;
+  const int M = off[c + 1] - off[c];
+  const float2* tx = replica + off[c];
+  double ar = 0.0, ai = 0.0;
+  for (int m = 0; m < M; ++m) {  // T[f] = sum_m tx[m] exp(-2 pi i f m / N)
+    double sn, cs;
+    sincospi(-2.0 * (double)(((long long)f * m) % kN) / (double)kN, &sn, &cs);
+    const double xr = tx[m].x, xi = tx[m].y;
+    ar += xr * cs - xi * sn;
+    ai += xr * sn + xi * cs;
+  }
+  const double scale = inv_norm[c] / (double)kN;
+  H[(size_t)c * kN + g] = make_float2((float)(ar * scale), (float)(-ai * scale));  // conj(T) / (N ||tx||^2)
+}
+
+constexpr size_t kSmemBytes = (size_t)(kPadN + 4096 + 256) * sizeof(float2) + 8 * sizeof(int);
+
+}  // namespace
+
+extern "C" epb_i64 epb_pulse_fft_workspace_bytes(epb_i64 C) {
+  if (C <= 0 || C > kMaxChan) return 0;
+  return (epb_i64)((size_t)C * kN + 4096 + 256) * (epb_i64)sizeof(float2) + (epb_i64)(2 * kMaxChan + 1) * (epb_i64)sizeof(int) + 64;
+}
+
+extern "C" int epb_pulse_fft_max_taps(void) { return kN / 2 + 1; }
+
+extern "C" int epb_pulse_compress_sv_fft(const float* re, const float* im, const float* replica, const int* h_replica_off,
+                                         const double* inv_norm, const epb_row* rows, float* out, float* echo_range,
+                                         float* pc_out, float* minmax, epb_i64 C, epb_i64 P, epb_i64 R, int B,
+                                         void* workspace, epb_i64 workspace_bytes, void* stream) {
+  EPB_REQUIRE(re && im && replica && h_replica_off && inv_norm && rows && out && workspace, "NULL pointer");
+  EPB_REQUIRE(C > 0 && C <= kMaxChan && P > 0 && R > 0 && R < (1LL << 24), "bad shape (channel <= 32)");
+  EPB_REQUIRE(B >= 1 && B <= 4, "B must be 1..4");
+  EPB_REQUIRE(B != 4 || (((uintptr_t)re | (uintptr_t)im) % 16 == 0), "4-beam planes must be 16-byte aligned");
+  EPB_REQUIRE(((uintptr_t)replica % 8) == 0 && ((uintptr_t)pc_out % 8) == 0, "replica / pc_out must be 8-byte aligned");
+  EPB_REQUIRE(workspace_bytes >= epb_pulse_fft_workspace_bytes(C) && ((uintptr_t)workspace % 16) == 0, "workspace too small / misaligned");
+  int Mmax = 0;
+  int h_off[kMaxChan + 1];
+  for (int c = 0; c <= C; ++c) h_off[c] = h_replica_off[c];
+  for (int c = 0; c < C; ++c) {
+    const int M = h_off[c + 1] - h_off[c];
+    EPB_REQUIRE(M > 0, "empty replica");
+    Mmax = M > Mmax ? M : Mmax;
+  }
+  if (Mmax > epb_pulse_fft_max_taps()) {
+    epb_set_error("epb_pulse_compress_sv_fft: %d-tap replica exceeds %d (use epb_pulse_compress_sv)", Mmax, epb_pulse_fft_max_taps());
+    return EPB_E_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  float2* H = reinterpret_cast<float2*>(workspace);
+  float2* tw1 = H + (size_t)C * kN;
+  float2* tw2 = tw1 + 4096;
+  int* d_off = reinterpret_cast<int*>(tw2 + 256);
+  int* d_lead0 = d_off + kMaxChan + 1;
+  if (cudaMemcpyAsync(d_off, h_off, sizeof(int) * (C + 1), cudaMemcpyHostToDevice, st) != cudaSuccess)
+    return epb_check_launch("epb_pulse_compress_sv_fft(offsets)");
+  pulse_fft_setup_kernel<<<dim3(kN / 256, (unsigned)C + 1), 256, 0, st>>>(reinterpret_cast<const float2*>(replica), inv_norm, (int)C, d_off, H,
+                                                                          tw1, tw2, d_lead0);
+  int rc0 = epb_check_launch("epb_pulse_compress_sv_fft(setup)");
+  if (rc0 != 0) return rc0;
+  FftParams pr;
+  pr.re = re, pr.im = im, pr.H = H, pr.tw1 = tw1, pr.tw2 = tw2, pr.lead0 = d_lead0, pr.rows = rows;
+  pr.out = out, pr.rng = echo_range, pr.pc_out = reinterpret_cast<float2*>(pc_out), pr.minmax = minmax;
+  pr.nrows = C * P, pr.P = P, pr.R = (int)R;
+  int L = kN - Mmax + 1;
+  if (L > 64) L &= ~31;  // warp-aligned segment starts keep the stores of a segment 128-byte aligned
+  pr.L = L;
+  pr.nseg = (int)((R + L - 1) / L);
+  const long long cap = (long long)epb_num_sms() * 2;
+  const int grid = (int)(pr.nrows < cap ? pr.nrows : cap);
+#define EPB_FFT(BB)                                                                                                          \
+  do {                                                                                                                       \
+    auto kern = pulse_fft_kernel<BB>;                                                                                        \
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)             \
+      return epb_check_launch("epb_pulse_compress_sv_fft(smem)");                                                            \
+    kern<<<grid, kT, kSmemBytes, st>>>(pr);                                                                                  \
+  } while (0)
+  switch (B) {
+    case 1: EPB_FFT(1); break;
+    case 2: EPB_FFT(2); break;
+    case 3: EPB_FFT(3); break;
+    default: EPB_FFT(4); break;
+  }
+#undef EPB_FFT
+  return epb_check_launch("epb_pulse_compress_sv_fft");
+}

@@ -113,8 +113,9 @@ def sv_complex(re, im, rows, C, P, R, B, want_range=True, want_minmax=False):
     return out, rng, mm
 
 
-def pulse_compress_sv(re, im, replicas, rows, C, P, R, B, want_range=True, want_pc=False, want_minmax=False):
-    """replicas: list of per-channel complex transmit replicas (host, complex128)."""
+def pulse_compress_sv(re, im, replicas, rows, C, P, R, B, want_range=True, want_pc=False, want_minmax=False, method="auto"):
+    """replicas: list of per-channel complex transmit replicas (host, complex128).
+    method: "fft" (overlap-save FFT kernel), "direct" (tap loop) or "auto" (FFT whenever the replicas fit)."""
     dev = re.device
     offs = np.zeros(C + 1, dtype=np.int32)
     for c, tx in enumerate(replicas):
@@ -127,11 +128,24 @@ def pulse_compress_sv(re, im, replicas, rows, C, P, R, B, want_range=True, want_
     pc = empty((C, P, R, 2), device=dev) if want_pc else None
     mm = new_minmax(dev) if want_minmax else None
     h_off = (ctypes.c_int * (C + 1))(*offs.tolist())
-    _lib.call(
-        "epb_pulse_compress_sv", ptr(re), ptr(im), ptr(rep), h_off, ptr(inv_norm), ptr(rows), ptr(out), ptr(rng),
-        ptr(pc), ptr(mm), C, P, R, int(B), stream(),
-    )
-    out._keep = (rep, inv_norm)
+    lib = _lib.load()
+    fits = max(len(tx) for tx in replicas) <= int(lib.epb_pulse_fft_max_taps())
+    if method == "fft" and not fits:
+        raise ValueError("replica too long for the FFT form")
+    ws = None
+    if method == "fft" or (method == "auto" and fits):
+        nws = int(lib.epb_pulse_fft_workspace_bytes(int(C)))
+        ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+        _lib.call(
+            "epb_pulse_compress_sv_fft", ptr(re), ptr(im), ptr(rep), h_off, ptr(inv_norm), ptr(rows), ptr(out), ptr(rng),
+            ptr(pc), ptr(mm), C, P, R, int(B), ptr(ws), nws, stream(),
+        )
+    else:
+        _lib.call(
+            "epb_pulse_compress_sv", ptr(re), ptr(im), ptr(rep), h_off, ptr(inv_norm), ptr(rows), ptr(out), ptr(rng),
+            ptr(pc), ptr(mm), C, P, R, int(B), stream(),
+        )
+    out._keep = (rep, inv_norm, ws)
     return out, rng, pc, mm
 
 

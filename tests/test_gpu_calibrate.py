@@ -98,7 +98,7 @@ def test_ek80_cw_complex(ep, cal_type, B):
     _check_range(ds["echo_range"].values, want["echo_range"])
 
 
-BB_ATOL = 2e-4  # float32 accumulation over a few hundred taps; see DESIGN.md numerics
+BB_ATOL = 1e-4  # north-star tolerance outside nulls of the matched-filter output (oracle_glue.compare_bb_db)
 
 
 @pytest.mark.parametrize("cal_type", ["Sv", "TS"])
@@ -125,14 +125,9 @@ def test_ek80_bb_pulse_compression(ep, cal_type, B, R, beam_nan):
     ds = fn(ed, waveform_mode="BB", encode_mode="complex")
     want = og.ek80(ed, cal_type, "BB", "complex")
     got = ds[cal_type].values.astype(np.float64)
-    assert np.array_equal(np.isnan(got), np.isnan(want["out"]))
-    # deep nulls of the compressed signal lose relative accuracy in float32: tolerance scales with the distance below the median
+    og.compare_bb_db(got, want["out"], want["prx"], BB_ATOL, cal_type)
     ok = ~np.isnan(got)
-    prx = want["prx"][ok]
-    weight = np.maximum(1.0, np.sqrt(np.nanmedian(prx) / np.maximum(prx, 1e-300)) * 1e-2)
-    err = np.abs(got[ok] - want["out"][ok])
-    assert (err <= BB_ATOL * weight).all(), float((err / weight).max())
-    assert np.median(err) < 2e-5
+    assert np.median(np.abs(got[ok] - want["out"][ok])) < 2e-5
     _check_range(ds["echo_range"].values, want["echo_range"])
     if cal_type == "Sv":
         np.testing.assert_allclose(ds["tau_effective"].values, want["tau_effective"], rtol=1e-12)
@@ -141,14 +136,16 @@ def test_ek80_bb_pulse_compression(ep, cal_type, B, R, beam_nan):
     np.testing.assert_array_equal(ds2[cal_type].values, ds[cal_type].values)
 
 
-def test_pulse_compress_kernel_vs_scipy(ep):
-    """The compressed, normalised, beam-averaged signal itself (pc_out) against scipy.signal.convolve."""
+@pytest.mark.parametrize("method", ["fft", "direct"])
+def test_pulse_compress_kernel_vs_scipy(ep, method):
+    """The compressed, normalised, beam-averaged signal itself (pc_out) against scipy.signal.convolve: the overlap-save
+    FFT kernel and the direct tap-loop kernel."""
     import torch
     from scipy import signal
 
     from echopype_b200 import kernels, synth
 
-    C, P, R, B = 2, 5, 777 - 1, 4
+    C, P, R, B = 2, 5, (777 - 1 if method == "direct" else 9001), 4  # 9001: three FFT segments, the last one short
     rng = np.random.default_rng(3)
     re = rng.standard_normal((C, P, R, B)).astype(np.float32)
     im = rng.standard_normal((C, P, R, B)).astype(np.float32)
@@ -160,8 +157,9 @@ def test_pulse_compress_kernel_vs_scipy(ep):
 
     cal = CalibrateEK80(ed, waveform_mode="BB", encode_mode="complex")
     cal._cal_complex_samples("Sv")
+    re[1, 2, 100:140, 2] = np.nan  # one beam missing on a stretch: the per-beam path (exact nanmean over beams)
     out, _, pc, _ = kernels.pulse_compress_sv(torch.from_numpy(re).cuda(), torch.from_numpy(im).cuda(), tx, cal.rows, C, P, R, B,
-                                              want_pc=True)
+                                              want_pc=True, method=method)
     pc = pc.cpu().numpy()
     got = pc[..., 0] + 1j * pc[..., 1]
     x = re.astype(np.float64) + 1j * im.astype(np.float64)
@@ -178,7 +176,9 @@ def test_pulse_compress_kernel_vs_scipy(ep):
             assert np.array_equal(np.isnan(g), np.isnan(want))
             ok = ~np.isnan(want)
             scale = np.abs(want[ok]).max()
-            assert np.abs(g[ok] - want[ok]).max() <= 3e-6 * scale
+            rms = np.sqrt(np.mean(np.abs(want[ok]) ** 2))
+            tol = (1.0e-6 if method == "fft" else 3e-6) * rms * (1 if method == "fft" else scale / rms)
+            assert np.abs(g[ok] - want[ok]).max() <= tol, (method, c, p, np.abs(g[ok] - want[ok]).max() / rms)
 
 
 def test_output_contract(ep):

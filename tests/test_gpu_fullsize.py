@@ -173,16 +173,11 @@ def test_cfg3_ek80_bb_full_size(ep):
         e["Sonar/Beam_group1"]["backscatter_i"] = (dims, beam["backscatter_i"].data[:, p0:p1].cpu().numpy())
         want = og.ek80(e, "Sv", "BB", "complex")
         got = sv[:, p0:p1].cpu().numpy().astype(np.float64)
-        assert np.array_equal(np.isnan(got), np.isnan(want["out"]))
+        # the north-star tolerance (1e-4 dB) outside nulls of the matched-filter output; RMS-relative amplitude inside
+        m, frac_null, worst = og.compare_bb_db(got, want["out"], want["prx"], ATOL, "cfg3 Sv")
+        assert frac_null < 0.02, frac_null
         ok = ~np.isnan(got)
-        prx = want["prx"][ok]
-        weight = np.maximum(1.0, np.sqrt(np.nanmedian(prx) / np.maximum(prx, 1e-300)) * 1e-2)
-        err = np.abs(got[ok] - want["out"][ok])
-        # float32 matched filter over ~280 taps: the tolerance of tests/test_gpu_calibrate.py (2e-4 dB, scaled in deep
-        # nulls of the compressed signal) holds for all but the extreme tail of the 145 000 samples of a slice
-        assert (err <= 1e-3 * weight).all(), float((err / weight).max())
-        assert (err <= 2e-4 * weight).mean() > 0.999
-        assert np.median(err) < 2e-5
+        assert np.median(np.abs(got[ok] - want["out"][ok])) < 1e-5
     # size-independent property: the NaN tail of a padded ping is NaN in Sv, everything before it is defined beyond
     # the TVG guard (R' > 0)
     nan_rows = torch.isnan(beam["backscatter_r"].data[..., 0]).any(dim=2)
