@@ -157,193 +157,283 @@ __device__ __forceinline__ void correlate(float2 (&v)[16], float2* __restrict__ 
   __syncthreads();  // the next transform overwrites the work buffer
 }
 
-// y[t + 256 j] of one segment -> Sv / TS, echo_range, optional compressed samples and min / max.
+// One 4096-point transform ("item").  Normally it holds one segment of one ping.  The LAST segment of a ping is usually
+// short (cfg3: 576 of 3808 outputs), so the tails of up to four consecutive pings of a channel are packed into one
+// transform, each in its own sub-block of 1024 (or 2048) positions: a sub-block's correlation window (outputs + M - 1
+// samples) fits inside it and everything else is zero, so the circular correlation never mixes pings.
+struct Item {
+  long long row0;  // sub-block b holds row0 + b (b < nsub)
+  int nsub;        // sub-blocks that hold a ping
+  int shift;       // point j lies in sub-block j >> shift (4: one block of 4096, 3: two of 2048, 2: four of 1024)
+  int n0;          // first sample of every sub-block
+  int nout;        // outputs per sub-block
+};
+
+struct Plan {  // launch-wide constants of the item enumeration
+  int L, nfull, pack, tail_n0, tail_nout, groups_per_chan, nchan;
+};
+
+// group g (32-bit: C * ceil(P / pack) groups) -> channel, first row, rows in the group
+struct Group {
+  int c, rows;
+  long long first;
+};
+__device__ __forceinline__ Group make_group(const Plan& pl, int P, int g) {
+  Group gr;
+  gr.c = g / pl.groups_per_chan;
+  const int gi = g - gr.c * pl.groups_per_chan;
+  gr.first = (long long)gr.c * P + (long long)gi * pl.pack;
+  gr.rows = min(pl.pack, P - gi * pl.pack);
+  return gr;
+}
+__device__ __forceinline__ int items_in_group(const Plan& pl, const Group& gr) { return gr.rows * pl.nfull + (pl.tail_nout > 0 ? 1 : 0); }
+// item k of a group: the full segments of its rows (row-major), then the packed tails
+__device__ __forceinline__ Item make_item(const Plan& pl, const Group& gr, int k) {
+  Item it;
+  if (k < gr.rows * pl.nfull) {
+    const int r = k / pl.nfull;
+    it.row0 = gr.first + r, it.nsub = 1, it.shift = 4, it.n0 = (k - r * pl.nfull) * pl.L, it.nout = pl.L;
+  } else {
+    it.row0 = gr.first, it.nsub = gr.rows, it.shift = pl.pack == 4 ? 2 : (pl.pack == 2 ? 3 : 4), it.n0 = pl.tail_n0, it.nout = pl.tail_nout;
+  }
+  return it;
+}
+
+// y -> Sv / TS, echo_range, optional compressed samples and min / max.  SHIFT: sub-block of point j = j >> SHIFT
+// (4: the whole transform is one segment).
 // cnt4: 4 bits per point = number of beams whose sample is valid (the nanmean divisor); nanre0: bit j = beam-0 real part NaN.
-template <int B, bool kUniform>
-__device__ __forceinline__ void epilogue(const FftParams& pr, const float2 (&v)[16], long long row, long long base, int n0, int nout, int t,
-                                         unsigned long long cnt4, unsigned okmask, unsigned nanre0, int zero_from, MinMax& mm_v,
-                                         MinMax& mm_r) {
-  const RowF rc = load_rowf(pr.rows + row);
+template <int B, int SHIFT, bool kUniform>
+__device__ __forceinline__ void epilogue(const FftParams& pr, const float2 (&v)[16], const Item& it, int t, unsigned long long cnt4,
+                                         unsigned okmask, unsigned nanre0, const int* __restrict__ s_zf, MinMax& mm_v, MinMax& mm_r) {
+  constexpr int kPer = 1 << SHIFT, kSmask = (256 << SHIFT) - 1;
+  const int R = pr.R;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const int q = t + 256 * j;
-    if (q < nout) {
-      const int n = n0 + q;
-      float sc;
-      bool any;
-      if (kUniform) {  // every beam valid or none
-        sc = 1.f / (float)B;
-        any = (okmask >> j) & 1u;
-      } else {
-        const int cnt = (int)((cnt4 >> (4 * j)) & 15ull);
-        sc = 1.f;  // 1 / cnt as selects
-        sc = (cnt == 2) ? 0.5f : sc;
-        sc = (cnt == 3) ? (1.f / 3.f) : sc;
-        sc = (cnt == 4) ? 0.25f : sc;
-        any = cnt > 0;
-      }
-      // outputs whose every product is exactly zero (the replica starts with zero taps - the Hann taper does - and only
-      // zero samples follow) are exactly zero in the reference's sum, hence NaN after prx.where(prx > 0)
-      // (calibrate_ek.py:581); a transform would leave rounding noise there
-      const bool exact0 = q >= zero_from;
-      const float mr = exact0 ? 0.f : v[j].x * sc, mi = exact0 ? 0.f : v[j].y * sc;
-      const float prx = rc.fscale * fmaf(mr, mr, mi * mi);
-      const float fr = (any && prx > 0.f) ? fmaf(kLog2ToDb, fast_log2(prx), rc.foffK) : CUDART_NAN_F;  // calibrate_ek.py:581
-      const float nf = (float)n;
-      float rr = range_of(rc, nf);
-      float o = sv_db(rc, n, nf, fr);
-      if ((nanre0 >> j) & 1u) rr = CUDART_NAN_F, o = CUDART_NAN_F;  // range.py:143-145: NaN where beam 0 of backscatter_r is
-      st_stream(pr.out + base + n, o);
-      if (pr.rng) st_stream(pr.rng + base + n, rr);
-      if (pr.pc_out) pr.pc_out[base + n] = any ? make_float2(mr, mi) : make_float2(CUDART_NAN_F, CUDART_NAN_F);
-      if (pr.minmax) {
-        mm_v.add(o);
-        mm_r.add(rr);
+  for (int sb = 0; sb < 16 / kPer; ++sb) {
+    if (SHIFT != 4 && sb >= it.nsub) break;
+    const RowF rc = load_rowf(pr.rows + it.row0 + sb);
+    const long long base = (it.row0 + sb) * (long long)R + it.n0;
+    const int zero_from = s_zf[sb];
+    const int nout = min(it.nout, R - it.n0);
+#pragma unroll
+    for (int jj = 0; jj < kPer; ++jj) {
+      const int j = sb * kPer + jj;
+      const int q = (t + 256 * j) & kSmask;
+      if (q < nout) {
+        const int n = it.n0 + q;
+        float sc;
+        bool any;
+        if (kUniform) {  // every beam valid or none
+          sc = 1.f / (float)B;
+          any = (okmask >> j) & 1u;
+        } else {
+          const int cnt = (int)((cnt4 >> (4 * j)) & 15ull);
+          sc = 1.f;  // 1 / cnt as selects
+          sc = (cnt == 2) ? 0.5f : sc;
+          sc = (cnt == 3) ? (1.f / 3.f) : sc;
+          sc = (cnt == 4) ? 0.25f : sc;
+          any = cnt > 0;
+        }
+        // outputs whose every product is exactly zero (the replica starts with zero taps - the Hann taper does - and only
+        // zero samples follow) are exactly zero in the reference's sum, hence NaN after prx.where(prx > 0)
+        // (calibrate_ek.py:581); a transform would leave rounding noise there
+        const bool exact0 = q >= zero_from;
+        const float mr = exact0 ? 0.f : v[j].x * sc, mi = exact0 ? 0.f : v[j].y * sc;
+        float prx = rc.fscale * fmaf(mr, mr, mi * mi);
+        // deep in a null the transform's rounding noise is quantised and can be exactly (0, 0) where the true sum is tiny
+        // but not zero: keep such samples finite (the smallest normal power) so that NaN marks only what is NaN in the
+        // reference - structurally zero sums (exact0) and invalid samples
+        prx = (!exact0 && prx == 0.f) ? 1.17549435e-38f : prx;
+        const float fr = (any && prx > 0.f) ? fmaf(kLog2ToDb, fast_log2(prx), rc.foffK) : CUDART_NAN_F;  // calibrate_ek.py:581
+        const float nf = (float)n;
+        float rr = range_of(rc, nf);
+        float o = sv_db(rc, n, nf, fr);
+        if ((nanre0 >> j) & 1u) rr = CUDART_NAN_F, o = CUDART_NAN_F;  // range.py:143-145: NaN where beam 0 of backscatter_r is
+        st_stream(pr.out + base + q, o);
+        if (pr.rng) st_stream(pr.rng + base + q, rr);
+        if (pr.pc_out) pr.pc_out[base + q] = any ? make_float2(mr, mi) : make_float2(CUDART_NAN_F, CUDART_NAN_F);
+        if (pr.minmax) {
+          mm_v.add(o);
+          mm_r.add(rr);
+        }
       }
     }
   }
 }
 
-// cold path: the beams of this segment carry different NaN masks.  One transform per beam; beam b's output counts only
+// cold path: the beams of this item carry different NaN masks.  One transform per beam; beam b's output counts only
 // where beam b's input sample is valid (the exact nanmean over beams of calibrate_ek.py:484).  Everything is passed by
 // value: a reference to the kernel parameters or to the caller's running min / max would force them into local memory
 // on the hot path as well.
-template <int B>
-__device__ __noinline__ void per_beam_segment(const FftParams pr, float2* __restrict__ s, const float2* __restrict__ s_tw1,
-                                              const float2* __restrict__ s_tw2, const float2* __restrict__ Hc, long long row,
-                                              long long base, int n0, int nout, int t, unsigned nanre0, int zero_from) {
+template <int B, int SHIFT>
+__device__ __noinline__ void per_beam_item(const FftParams pr, float2* __restrict__ s, const float2* __restrict__ s_tw1,
+                                           const float2* __restrict__ s_tw2, const int* __restrict__ s_zf, const float2* __restrict__ Hc,
+                                           const Item it, int t, unsigned nanre0) {
+  constexpr int kSmask = (256 << SHIFT) - 1;
   MinMax mm_v, mm_r;
   float2 acc[16], v[16];
   unsigned long long valid = 0ull, cnt4 = 0ull;
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     acc[j] = make_float2(0.f, 0.f);
-    const int n = n0 + t + 256 * j;
+    const int sb = j >> SHIFT, n = it.n0 + ((t + 256 * j) & kSmask);
     unsigned fl = 0u;
-    if (n < pr.R)
+    if (sb < it.nsub && n < pr.R) {
+      const long long e = ((it.row0 + sb) * (long long)pr.R + n) * B;
       for (int b = 0; b < B; ++b) {
-        const float xr = pr.re[(base + n) * B + b], xi = pr.im[(base + n) * B + b];
+        const float xr = pr.re[e + b], xi = pr.im[e + b];
         fl |= (xr == xr && xi == xi) ? (1u << b) : 0u;  // a complex sample is NaN if either part is
       }
+    }
     valid |= (unsigned long long)fl << (4 * j);
     cnt4 |= (unsigned long long)__popc(fl) << (4 * j);
   }
   for (int b = 0; b < B; ++b) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const int n = n0 + t + 256 * j;
+      const int sb = j >> SHIFT, n = it.n0 + ((t + 256 * j) & kSmask);
+      const long long e = ((it.row0 + sb) * (long long)pr.R + n) * B + b;
       const bool ok = (valid >> (4 * j + b)) & 1ull;
-      v[j] = ok ? make_float2(pr.re[(base + n) * B + b], pr.im[(base + n) * B + b]) : make_float2(0.f, 0.f);
+      v[j] = ok ? make_float2(pr.re[e], pr.im[e]) : make_float2(0.f, 0.f);
     }
     correlate(v, s, s_tw1, s_tw2, Hc, t);
 #pragma unroll
     for (int j = 0; j < 16; ++j)
       if ((valid >> (4 * j + b)) & 1ull) acc[j] = cadd(acc[j], v[j]);
   }
-  epilogue<B, false>(pr, acc, row, base, n0, nout, t, cnt4, 0u, nanre0, zero_from, mm_v, mm_r);
+  epilogue<B, SHIFT, false>(pr, acc, it, t, cnt4, 0u, nanre0, s_zf, mm_v, mm_r);
   if (pr.minmax) {
     mm_v.flush(pr.minmax + 0, pr.minmax + 1);
     mm_r.flush(pr.minmax + 2, pr.minmax + 3);
   }
 }
 
-template <int B>
-__global__ void __launch_bounds__(kT, 2) pulse_fft_kernel(const FftParams pr) {
+// load + transform + epilogue of one item
+template <int B, int SHIFT>
+__device__ __forceinline__ void process_item(const FftParams& pr, const Item& it, float2* __restrict__ s, const float2* __restrict__ s_tw1,
+                                             const float2* __restrict__ s_tw2, int* __restrict__ s_wmax, int* __restrict__ s_zf,
+                                             const float2* __restrict__ Hc, int lead0, int t, MinMax& mm_v, MinMax& mm_r) {
+  constexpr int kPer = 1 << SHIFT, kSmask = (256 << SHIFT) - 1;
+  const int R = pr.R;
+  // ---- load: beams summed; four points (8 x 16 bytes) in flight.  A NaN anywhere in the point makes the plain sum NaN:
+  //      only then the per-beam validity is worked out (NaN -> 0). -------------------------------------------------------------
+  float2 v[16];
+  unsigned okmask = 0u;   // bit j: every beam of point j is valid
+  unsigned nanre0 = 0u;   // bit j: beam-0 real part is NaN (range.py:143-145)
+  unsigned nzmask = 0u;   // bit j: the (summed) sample is nonzero
+  int nonuniform = 0;     // some point has valid and invalid beams: the per-beam path
+#pragma unroll
+  for (int gq = 0; gq < 4; ++gq) {
+    float xr[4][B], xi[4][B];
+    bool inside[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = 4 * gq + u;
+      const int sb = j >> SHIFT, n = it.n0 + ((t + 256 * j) & kSmask);
+      inside[u] = (SHIFT == 4 || sb < it.nsub) && (n < R);
+      const long long e = inside[u] ? ((it.row0 + sb) * (long long)R + n) * B : 0;  // clamped address; value discarded
+      if (B == 4) {
+        const float4 a4 = ld_stream4(reinterpret_cast<const float4*>(pr.re + e));
+        const float4 b4 = ld_stream4(reinterpret_cast<const float4*>(pr.im + e));
+        xr[u][0] = a4.x, xr[u][1 % B] = a4.y, xr[u][2 % B] = a4.z, xr[u][3 % B] = a4.w;
+        xi[u][0] = b4.x, xi[u][1 % B] = b4.y, xi[u][2 % B] = b4.z, xi[u][3 % B] = b4.w;
+      } else {
+#pragma unroll
+        for (int bb = 0; bb < B; ++bb) {
+          xr[u][bb] = ld_stream(pr.re + e + bb);
+          xi[u][bb] = ld_stream(pr.im + e + bb);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = 4 * gq + u;
+      float sr = xr[u][0], si = xi[u][0];
+#pragma unroll
+      for (int bb = 1; bb < B; ++bb) sr += xr[u][bb], si += xi[u][bb];
+      const bool clean = (sr == sr) && (si == si);  // finite inputs: the sum is NaN iff some part is NaN
+      if (inside[u] && !clean) {                     // rare: NaN padding / missing sectors
+        unsigned fl = 0u;
+        sr = 0.f, si = 0.f;
+#pragma unroll
+        for (int bb = 0; bb < B; ++bb) {
+          const bool ok = (xr[u][bb] == xr[u][bb]) && (xi[u][bb] == xi[u][bb]);
+          sr += ok ? xr[u][bb] : 0.f;
+          si += ok ? xi[u][bb] : 0.f;
+          fl |= ok ? (1u << bb) : 0u;
+        }
+        nanre0 |= (xr[u][0] != xr[u][0]) ? (1u << j) : 0u;
+        nonuniform |= (fl != 0u);  // fl != all here
+      }
+      okmask |= (inside[u] && clean) ? (1u << j) : 0u;
+      v[j] = inside[u] ? make_float2(sr, si) : make_float2(0.f, 0.f);
+      nzmask |= (inside[u] && (sr != 0.f || si != 0.f)) ? (1u << j) : 0u;
+    }
+  }
+  // last nonzero input position per sub-block (this thread: highest set bit of its points in the sub-block)
+#pragma unroll
+  for (int sb = 0; sb < 16 / kPer; ++sb) {
+    const unsigned bits = (nzmask >> (sb * kPer)) & ((1u << kPer) - 1u);
+    int last = bits ? ((t + 256 * (sb * kPer + 31 - __clz((int)bits))) & kSmask) : -1;
+    last = __reduce_max_sync(0xffffffffu, last);
+    if ((t & 31) == 0) s_wmax[(t >> 5) * 4 + sb] = last;
+  }
+  nonuniform = __syncthreads_or(nonuniform);
+  if (t < 16 / kPer) {
+    int last = -1;
+#pragma unroll
+    for (int w = 0; w < kT / 32; ++w) last = max(last, s_wmax[w * 4 + t]);
+    s_zf[t] = last - lead0 + 1;  // outputs q >= this see only zero taps or zero samples (read after correlate's barriers)
+  }
+  if (!nonuniform) {
+    correlate(v, s, s_tw1, s_tw2, Hc, t);
+    epilogue<B, SHIFT, true>(pr, v, it, t, 0ull, okmask, nanre0, s_zf, mm_v, mm_r);
+  } else {
+    per_beam_item<B, SHIFT>(pr, s, s_tw1, s_tw2, s_zf, Hc, it, t, nanre0);
+  }
+}
+
+// PSHIFT: sub-block shift of the packed tail items (4: tails are not packed)
+template <int B, int PSHIFT>
+__global__ void __launch_bounds__(kT, 2) pulse_fft_kernel(const FftParams pr, const Plan pl) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* s = reinterpret_cast<float2*>(smem_raw);  // [kPadN]
   float2* s_tw1 = s + kPadN;                         // [4096]
   float2* s_tw2 = s_tw1 + 4096;                      // [256]
-  int* s_wmax = reinterpret_cast<int*>(s_tw2 + 256);  // [8] per-warp last nonzero input position of the segment
+  int* s_wmax = reinterpret_cast<int*>(s_tw2 + 256);  // [8][4] per warp and sub-block: last nonzero input position
+  int* s_zf = s_wmax + 32;                            // [4] per sub-block: first structurally-zero output
   const int t = threadIdx.x;
   for (int k = t; k < 4096; k += kT) s_tw1[k] = pr.tw1[k];
   s_tw2[t] = pr.tw2[t];
   __syncthreads();
-  const int R = pr.R, L = pr.L;
+  const int R = pr.R;
+  const int P = (int)pr.P;
+  const int ngroups = pl.nchan * pl.groups_per_chan;
   MinMax mm_v, mm_r;
 
-  for (long long row = blockIdx.x; row < pr.nrows; row += gridDim.x) {
-    const int c = (int)(row / pr.P);
-    const float2* Hc = pr.H + (size_t)c * kN;
-    const int lead0 = __ldg(pr.lead0 + c);
-    const long long base = row * (long long)R;
-    for (int seg = 0; seg < pr.nseg; ++seg) {
-      const int n0 = seg * L;
-      const int nout = min(L, R - n0);  // outputs of this segment
-      // ---- load: x[n0 + t + 256 j], beams summed; four points (8 x 16 bytes) in flight.  A NaN anywhere in the point
-      //      makes the plain sum NaN: only then the per-beam validity is worked out (NaN -> 0). ---------------------------------
-      float2 v[16];
-      unsigned okmask = 0u;   // bit j: every beam of point j is valid
-      unsigned nanre0 = 0u;   // bit j: beam-0 real part is NaN (range.py:143-145)
-      int nonuniform = 0;     // some point has valid and invalid beams: the per-beam path
-      int last_nz = -1;       // last position of this thread holding a nonzero (summed) sample
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        float xr[4][B], xi[4][B];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int n = n0 + t + 256 * (4 * g + u);
-          const long long e = (base + (n < R ? n : 0)) * B;  // clamped address; the value is discarded below
-          if (B == 4) {
-            const float4 a4 = ld_stream4(reinterpret_cast<const float4*>(pr.re + e));
-            const float4 b4 = ld_stream4(reinterpret_cast<const float4*>(pr.im + e));
-            xr[u][0] = a4.x, xr[u][1 % B] = a4.y, xr[u][2 % B] = a4.z, xr[u][3 % B] = a4.w;
-            xi[u][0] = b4.x, xi[u][1 % B] = b4.y, xi[u][2 % B] = b4.z, xi[u][3 % B] = b4.w;
-          } else {
-#pragma unroll
-            for (int bb = 0; bb < B; ++bb) {
-              xr[u][bb] = ld_stream(pr.re + e + bb);
-              xi[u][bb] = ld_stream(pr.im + e + bb);
-            }
+  for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const Group gr = make_group(pl, P, g);
+    const float2* Hc = pr.H + (size_t)gr.c * kN;
+    const int lead0 = __ldg(pr.lead0 + gr.c);
+    const int nitems = items_in_group(pl, gr);
+    for (int k = 0; k < nitems; ++k) {
+      const Item it = make_item(pl, gr, k);
+      if (B == 4 && t == 0) {  // while this item is loaded and transformed, the next one streams from HBM into L2
+        int ng = g, nk = k + 1;
+        if (nk >= nitems) ng = g + gridDim.x, nk = 0;
+        if (ng < ngroups) {
+          const Item nx = make_item(pl, make_group(pl, P, ng), nk);
+          const int len = min(256 << nx.shift, R - nx.n0);
+          for (int sb = 0; sb < nx.nsub; ++sb) {
+            const long long e = ((nx.row0 + sb) * (long long)R + nx.n0) * 4;
+            prefetch_l2_bulk(pr.re + e, (unsigned)len * 16u);
+            prefetch_l2_bulk(pr.im + e, (unsigned)len * 16u);
           }
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = 4 * g + u;
-          const bool inside = (n0 + t + 256 * j) < R;
-          float sr = xr[u][0], si = xi[u][0];
-#pragma unroll
-          for (int bb = 1; bb < B; ++bb) sr += xr[u][bb], si += xi[u][bb];
-          const bool clean = (sr == sr) && (si == si);  // finite inputs: the sum is NaN iff some part is NaN
-          if (inside && !clean) {                        // rare: NaN padding / missing sectors
-            unsigned fl = 0u;
-            sr = 0.f, si = 0.f;
-#pragma unroll
-            for (int bb = 0; bb < B; ++bb) {
-              const bool ok = (xr[u][bb] == xr[u][bb]) && (xi[u][bb] == xi[u][bb]);
-              sr += ok ? xr[u][bb] : 0.f;
-              si += ok ? xi[u][bb] : 0.f;
-              fl |= ok ? (1u << bb) : 0u;
-            }
-            nanre0 |= (xr[u][0] != xr[u][0]) ? (1u << j) : 0u;
-            nonuniform |= (fl != 0u);  // fl != all here
-          }
-          okmask |= (inside && clean) ? (1u << j) : 0u;
-          v[j] = inside ? make_float2(sr, si) : make_float2(0.f, 0.f);
-          last_nz = (inside && (sr != 0.f || si != 0.f)) ? (t + 256 * j) : last_nz;
-        }
       }
-      if (B == 4 && t == 0) {  // while this segment is transformed, the next one streams from HBM into L2
-        long long nrow = row;
-        int nn0 = n0 + L;
-        if (seg + 1 >= pr.nseg) nrow = row + gridDim.x, nn0 = 0;
-        if (nrow < pr.nrows) {
-          const unsigned bytes = (unsigned)min(kN, R - nn0) * 16u;
-          prefetch_l2_bulk(pr.re + (nrow * (long long)R + nn0) * 4, bytes);
-          prefetch_l2_bulk(pr.im + (nrow * (long long)R + nn0) * 4, bytes);
-        }
-      }
-      last_nz = __reduce_max_sync(0xffffffffu, last_nz);
-      if ((t & 31) == 0) s_wmax[t >> 5] = last_nz;
-      nonuniform = __syncthreads_or(nonuniform);
-#pragma unroll
-      for (int w = 0; w < kT / 32; ++w) last_nz = max(last_nz, s_wmax[w]);
-      const int zero_from = last_nz - lead0 + 1;  // outputs q >= zero_from see only zero taps or zero samples
-      if (!nonuniform) {
-        correlate(v, s, s_tw1, s_tw2, Hc, t);
-        epilogue<B, true>(pr, v, row, base, n0, nout, t, 0ull, okmask, nanre0, zero_from, mm_v, mm_r);
-      } else {
-        per_beam_segment<B>(pr, s, s_tw1, s_tw2, Hc, row, base, n0, nout, t, nanre0, zero_from);
-      }
+      if (PSHIFT == 4 || it.shift == 4)
+        process_item<B, 4>(pr, it, s, s_tw1, s_tw2, s_wmax, s_zf, Hc, lead0, t, mm_v, mm_r);
+      else
+        process_item<B, PSHIFT>(pr, it, s, s_tw1, s_tw2, s_wmax, s_zf, Hc, lead0, t, mm_v, mm_r);
     }
   }
   if (pr.minmax) {
@@ -397,7 +487,7 @@ __global__ void __launch_bounds__(256) pulse_fft_setup_kernel(const float2* __re
   H[(size_t)c * kN + g] = make_float2((float)(ar * scale), (float)(-ai * scale));  // conj(T) / (N ||tx||^2)
 }
 
-constexpr size_t kSmemBytes = (size_t)(kPadN + 4096 + 256) * sizeof(float2) + 8 * sizeof(int);
+constexpr size_t kSmemBytes = (size_t)(kPadN + 4096 + 256) * sizeof(float2) + 40 * sizeof(int);
 
 }  // namespace
 
@@ -450,20 +540,40 @@ extern "C" int epb_pulse_compress_sv_fft(const float* re, const float* im, const
   if (L > 64) L &= ~31;  // warp-aligned segment starts keep the stores of a segment 128-byte aligned
   pr.L = L;
   pr.nseg = (int)((R + L - 1) / L);
+  Plan pl;
+  const int nlast = (int)(R - (long long)(pr.nseg - 1) * L);  // outputs of a ping's last segment
+  pl.L = L;
+  pl.pack = (B != 4) ? 1 : (nlast + Mmax - 1 <= 1024) ? 4 : (nlast + Mmax - 1 <= 2048 ? 2 : 1);
+  if (pl.pack > 1) {
+    pl.nfull = pr.nseg - 1, pl.tail_n0 = (pr.nseg - 1) * L, pl.tail_nout = nlast;
+  } else {
+    pl.nfull = pr.nseg, pl.tail_n0 = 0, pl.tail_nout = 0;
+  }
+  EPB_REQUIRE(P < (1LL << 30), "ping_time too long for one launch");
+  pl.groups_per_chan = (int)((P + pl.pack - 1) / pl.pack);
+  pl.nchan = (int)C;
+  const long long ngroups = C * (long long)pl.groups_per_chan;
   const long long cap = (long long)epb_num_sms() * 2;
-  const int grid = (int)(pr.nrows < cap ? pr.nrows : cap);
-#define EPB_FFT(BB)                                                                                                          \
+  const int grid = (int)(ngroups < cap ? ngroups : cap);
+#define EPB_FFT(BB, PS)                                                                                                      \
   do {                                                                                                                       \
-    auto kern = pulse_fft_kernel<BB>;                                                                                        \
+    auto kern = pulse_fft_kernel<BB, PS>;                                                                                    \
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)             \
       return epb_check_launch("epb_pulse_compress_sv_fft(smem)");                                                            \
-    kern<<<grid, kT, kSmemBytes, st>>>(pr);                                                                                  \
+    kern<<<grid, kT, kSmemBytes, st>>>(pr, pl);                                                                              \
   } while (0)
   switch (B) {
-    case 1: EPB_FFT(1); break;
-    case 2: EPB_FFT(2); break;
-    case 3: EPB_FFT(3); break;
-    default: EPB_FFT(4); break;
+    case 1: EPB_FFT(1, 4); break;
+    case 2: EPB_FFT(2, 4); break;
+    case 3: EPB_FFT(3, 4); break;
+    default:
+      if (pl.pack == 4)
+        EPB_FFT(4, 2);
+      else if (pl.pack == 2)
+        EPB_FFT(4, 3);
+      else
+        EPB_FFT(4, 4);
+      break;
   }
 #undef EPB_FFT
   return epb_check_launch("epb_pulse_compress_sv_fft");

@@ -164,7 +164,7 @@ def compare_db(got, want, atol, what="Sv"):
 
 
 BB_NULL_DB = 26.0  # a "null" of the matched-filter output: received power more than 26 dB below the ping's mean power
-BB_NULL_REL = 1.5e-6  # amplitude error allowed inside nulls, relative to the ping's RMS matched-filter amplitude
+BB_NULL_REL = 5e-6  # amplitude error allowed inside nulls, relative to the ping's RMS matched-filter amplitude (-106 dB)
 
 
 def compare_bb_db(got, want, prx, atol, what="Sv"):

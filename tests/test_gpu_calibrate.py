@@ -253,13 +253,23 @@ def test_ek80_multiple_filter_times_equal_single_when_filters_repeat(ep):
     order = np.argsort([str(c) for c in want["channel"].values])
     assert list(got["channel"].values) == [want["channel"].values[i] for i in order]
     np.testing.assert_array_equal(got["ping_time"].values, want["ping_time"].values)
-    for name in ("Sv", "echo_range"):
-        a, b = got[name].values, want[name].values[order]
-        np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
+    a, b = got["echo_range"].values, want["echo_range"].values[order]
+    np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
+
+    def same_sv(a, b):
+        # the FFT matched filter packs the short last segments of up to four pings into one transform, so a ping's
+        # rounding noise (~1e-7 of its RMS output) depends on which pings share the transform: equal outside nulls only
+        # (these pings are shorter than the replica, R = 256 < M = 277: every output is a partial window)
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        d = np.abs(a - b)[~np.isnan(a)]
+        # a wrong merge (pings or channels swapped) would show up as dB-scale differences
+        assert np.median(d) <= 1e-3 and np.quantile(d, 0.9) <= 1e-2, (float(np.median(d)), float(np.quantile(d, 0.9)))
+
+    same_sv(got["Sv"].values, want["Sv"].values[order])
     np.testing.assert_allclose(got["tau_effective"].values, want["tau_effective"].values[order], rtol=0)
     # assume_single_filter_time: one pass with the collapsed filter table, same numbers
     one = ep.calibrate.compute_Sv(_multi_filter_ed(), waveform_mode="BB", encode_mode="complex", assume_single_filter_time=True)
-    np.testing.assert_array_equal(one["Sv"].values.view(np.uint32), want["Sv"].values[order].view(np.uint32))
+    same_sv(one["Sv"].values, want["Sv"].values[order])
 
 
 def test_ek80_multiple_filter_times_conflict_and_missing(ep):
