@@ -75,7 +75,7 @@ class CalibrateAZFP(CalibrateBase):
         beam = self.echodata["Sonar/Beam_group1"]
         out, rng, mm = kernels.sv_power(x, rows, C, P, R, want_range=True, want_minmax=True)
         ds = Dataset(coords={d: beam[d].values for d in DIMENSION_ORDER})
-        ds[cal_type] = DataArray(out, DIMENSION_ORDER, name=cal_type)
+        ds[cal_type] = DataArray(out, DIMENSION_ORDER, name=cal_type, law={"kind": "derived"})
         er = DataArray(rng, DIMENSION_ORDER, name="echo_range")
         er.law = {"rows": rows, "kind": "echo_range", "minmax": mm}
         ds["echo_range"] = er

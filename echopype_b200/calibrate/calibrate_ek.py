@@ -63,6 +63,8 @@ def _cp(da, channel, ping_time=None):
         dims = dims[:ax] + dims[ax + 1 :]
     if dims == ("ping_time", "channel"):
         v, dims = v.T, ("channel", "ping_time")
+    if dims == ("ping_time",):  # explicit (1, P): a bare (P,) vector would be taken for per-channel values when P == C
+        return v.reshape(1, -1)
     if dims == ("channel",) and "channel" in da.coords:
         have = np.asarray(da.coords["channel"])
         want = np.asarray(channel)
@@ -187,7 +189,8 @@ class CalibrateEK(CalibrateBase):
         beam = self.beam
         coords = {d: beam[d].values for d in DIMENSION_ORDER}
         ds = Dataset(coords=coords)
-        ds[cal_type] = DataArray(out_t, DIMENSION_ORDER, name=cal_type)
+        # law {"kind": "derived"}: NaN wherever echo_range is NaN - what index-space binning relies on (dataset.py)
+        ds[cal_type] = DataArray(out_t, DIMENSION_ORDER, name=cal_type, law={"kind": "derived"})
         er = DataArray(rng_t, DIMENSION_ORDER, name="echo_range")
         er.law = {"rows": rows, "kind": "echo_range", "minmax": minmax}
         ds["echo_range"] = er

@@ -82,7 +82,9 @@ def remove_background_noise(ds_Sv, ping_num: int, range_sample_num: int, backgro
         lo_c = hi_c = float("nan")
     out = ds_Sv.copy()
     out["Sv_noise"] = DataArray(sn, DIMS, attrs=noise_attrs("noise", lo_n, hi_n, ping_num, range_sample_num, snr, background_noise_max))
-    out["Sv_corrected"] = DataArray(sc, DIMS, attrs=noise_attrs("corrected", lo_c, hi_c, ping_num, range_sample_num, snr, background_noise_max))
+    trusted = isinstance(ds_Sv["Sv"].law, dict) and ds_Sv["Sv"].law.get("kind") == "derived"
+    out["Sv_corrected"] = DataArray(sc, DIMS, attrs=noise_attrs("corrected", lo_c, hi_c, ping_num, range_sample_num, snr, background_noise_max),
+                                    law={"kind": "derived"} if trusted else None)  # NaN wherever Sv is
     prov_dict = echopype_prov_attrs(process_type="processing")
     prov_dict["processing_function"] = "clean.remove_background_noise"
     out = out.assign_attrs(prov_dict)

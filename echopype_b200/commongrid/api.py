@@ -200,6 +200,20 @@ def compute_MVBS(
     return ds_MVBS
 
 
+def _coarsen_time_mean(ping_time, ping_num):
+    """ping_time of DataArray.coarsen(ping_time=ping_num, boundary="pad").mean() (commongrid/api.py:219-238): the
+    coordinate is coarsened with coord_func="mean", i.e. the MEAN time of each tile's pings (the NaT padding of a short
+    last tile is skipped), not the tile's first ping.  int64 nanoseconds, averaged as offsets from the tile's first ping."""
+    t = np.asarray(ping_time).astype("datetime64[ns]").astype(np.int64)
+    n = t.shape[0]
+    nP = -(-n // ping_num)
+    out = np.empty(nP, dtype=np.int64)
+    for i in range(nP):
+        seg = t[i * ping_num : (i + 1) * ping_num]
+        out[i] = seg[0] + int(np.mean((seg - seg[0]).astype(np.float64)))  # xarray: float mean of the offsets, truncated to ns
+    return out.astype("datetime64[ns]")
+
+
 @add_processing_level("L3*")
 def compute_MVBS_index_binning(ds_Sv, range_sample_num=100, ping_num=100):
     """
@@ -221,7 +235,7 @@ def compute_MVBS_index_binning(ds_Sv, range_sample_num=100, ping_num=100):
         data_vars={"Sv": (DIMS, out_np), "echo_range": (DIMS, er.cpu().numpy().astype(np.float64))},
         coords={
             "channel": ds_Sv["channel"].values,
-            "ping_time": np.asarray(ds_Sv["ping_time"].values)[:: int(ping_num)][:nP],
+            "ping_time": _coarsen_time_mean(np.asarray(ds_Sv["ping_time"].values), int(ping_num))[:nP],
             "range_sample": ("range_sample", np.arange(nRs), {"long_name": "Along-range sample number, base 0"}),
         },
     )

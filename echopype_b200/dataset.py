@@ -184,6 +184,42 @@ class DataArray:
         out.data = self.values.astype(dtype)
         return out
 
+    def where(self, cond, other=np.nan):
+        """Values where ``cond`` holds, ``other`` elsewhere (xarray.DataArray.where for same-shaped or dims-broadcastable
+        conditions).  Device arrays stay on the device (the comparison result ``cond`` may be a device DataArray)."""
+        c = cond
+        cdims = tuple(c.dims) if isinstance(c, DataArray) else None
+        cdata = c.data if isinstance(c, DataArray) else c
+        if _is_tensor(self.data) or _is_tensor(cdata):
+            x = self.data if _is_tensor(self.data) else torch.as_tensor(np.asarray(self.data))
+            ct = cdata if _is_tensor(cdata) else torch.as_tensor(np.asarray(cdata))
+            dev = x.device if x.is_cuda else ct.device
+            x, ct = x.to(dev), ct.to(dev)
+            if cdims is not None and cdims != self.dims:
+                ct = ct.reshape([ct.shape[cdims.index(d)] if d in cdims else 1 for d in self.dims])
+            xf = x if x.is_floating_point() else x.float()
+            o = other.data if isinstance(other, DataArray) else other
+            o = o.to(dev) if _is_tensor(o) else torch.as_tensor(np.asarray(o, dtype=np.float64), device=dev).to(xf.dtype)
+            out = torch.where(ct.bool(), xf, o)
+        else:
+            x, cn = np.asarray(self.data), np.asarray(cdata)
+            if cdims is not None and cdims != self.dims:
+                cn = cn.reshape([cn.shape[cdims.index(d)] if d in cdims else 1 for d in self.dims])
+            o = other.values if isinstance(other, DataArray) else other
+            if x.dtype.kind in "iub" and np.ndim(o) == 0 and isinstance(o, float) and np.isnan(o):
+                x = x.astype(np.float64)
+            out = np.where(cn.astype(bool), x, o)
+        return DataArray(out, self.dims, dict(self.coords), dict(self.attrs), self.name)
+
+    def rename(self, new_name_or_name_dict=None, **names):
+        if isinstance(new_name_or_name_dict, str) or (new_name_or_name_dict is None and not names):
+            out = self.copy()
+            out.name = new_name_or_name_dict
+            return out
+        m = dict(new_name_or_name_dict or {}, **names)
+        return DataArray(self.data, tuple(m.get(d, d) for d in self.dims), {m.get(k, k): v for k, v in self.coords.items()},
+                         dict(self.attrs), m.get(self.name, self.name), self.law)
+
     def isnull(self):
         v = self.values
         m = np.isnan(v) if v.dtype.kind in "fc" else (np.isnat(v) if v.dtype.kind in "mM" else np.zeros(v.shape, bool))
@@ -276,6 +312,28 @@ class DataArray:
     def __neg__(self):
         return DataArray(-self.values, self.dims, self.coords, self.attrs, self.name)
 
+    def _cmp(self, o, op_host, op_dev):
+        if _is_tensor(self.data):
+            ov = o.data if isinstance(o, DataArray) else o
+            return DataArray(op_dev(self.data, ov), self.dims, dict(self.coords), None, self.name)
+        return self._binop(o, op_host)
+
+    def __lt__(self, o):
+        return self._cmp(o, np.less, lambda a, b: a < b)
+
+    def __le__(self, o):
+        return self._cmp(o, np.less_equal, lambda a, b: a <= b)
+
+    def __gt__(self, o):
+        return self._cmp(o, np.greater, lambda a, b: a > b)
+
+    def __ge__(self, o):
+        return self._cmp(o, np.greater_equal, lambda a, b: a >= b)
+
+    def notnull(self):
+        m = self.isnull()
+        return DataArray(~m.values, m.dims, m.coords, name=self.name)
+
 
 def _to_dataarray(value, name=None):
     if isinstance(value, DataArray):
@@ -346,9 +404,98 @@ class Dataset:
         if key in self._coords and da.dims == (key,):
             self._set_coord(key, da)
             return
+        if key == "Sv":
+            # The index-space binning of compute_MVBS (the row table cached on echo_range / depth as ``.law``) relies on
+            # Sv being NaN wherever the reference's range variable is NaN.  Arrays produced by this package from such an
+            # Sv carry the marker law {"kind": "derived"}; any other array assigned as "Sv" (user data, a mask filled
+            # with a finite value) ends that guarantee, so the range variables fall back to value binning.
+            keeps = isinstance(da.law, dict) and da.law.get("kind") == "derived"
+            old = self._vars.get("Sv")
+            same = old is not None and old.data is da.data
+            if not (keeps or same):
+                self._drop_range_laws()
         stored = DataArray(da.data, da.dims, None, None, key, da.law)
         stored.attrs = da.attrs
         self._vars[key] = stored
+
+    def _drop_range_laws(self):
+        for name in ("echo_range", "depth"):
+            v = self._vars.get(name)
+            if v is not None and isinstance(v.law, dict) and v.law.get("rows") is not None:
+                mm = v.law.get("minmax")
+                v.law = {"kind": v.law.get("kind"), "rows": None, "minmax": mm} if mm is not None else None
+
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        d = self.__dict__
+        if name in d.get("_vars", {}) or name in d.get("_coords", {}):
+            return self[name]
+        raise AttributeError(f"Dataset has no variable or attribute {name!r}")
+
+    def rename_vars(self, name_dict=None, **names):
+        """xarray.Dataset.rename_vars: rename variables / coordinates, dimensions stay."""
+        m = dict(name_dict or {}, **names)
+        for k in m:
+            if k not in self:
+                raise ValueError(f"cannot rename {k!r} because it is not a variable or coordinate in this dataset")
+        for k, v in m.items():
+            if v in self and v not in m:
+                raise ValueError(f"the new name {v!r} conflicts")
+        out = Dataset(attrs=_copy.copy(self.attrs))
+        for k, c in self._coords.items():
+            c2 = c.copy()
+            c2.name = m.get(k, k)
+            out._coords[m.get(k, k)] = c2
+        for k, v in self._vars.items():
+            v2 = v.copy()
+            v2.name = m.get(k, k)
+            out._vars[m.get(k, k)] = v2
+        if "Sv" in m.values():  # another variable takes the place of Sv: same rule as assignment
+            sv = out._vars.get("Sv")
+            if sv is not None and not (isinstance(sv.law, dict) and sv.law.get("kind") == "derived"):
+                out._drop_range_laws()
+        return out
+
+    def rename(self, name_dict=None, **names):
+        """xarray.Dataset.rename: variables, coordinates and dimensions."""
+        m = dict(name_dict or {}, **names)
+        out = self.rename_vars({k: v for k, v in m.items() if k in self})
+        for store in (out._coords, out._vars):
+            for k, v in list(store.items()):
+                if any(d in m for d in v.dims):
+                    store[k] = DataArray(v.data, tuple(m.get(d, d) for d in v.dims), None, v.attrs, v.name, v.law)
+        return out
+
+    def swap_dims(self, dims_dict=None, **dims):
+        """xarray.Dataset.swap_dims: e.g. {"channel": "frequency_nominal"} makes the 1-D variable ``frequency_nominal``
+        the dimension coordinate of what was the ``channel`` dimension (``channel`` stays as a non-index coordinate)."""
+        m = dict(dims_dict or {}, **dims)
+        out = self.copy()
+        for old, new in m.items():
+            if new not in out:
+                raise ValueError(f"replacement dimension {new!r} is not a 1D variable along the old dimension {old!r}")
+            nv = out[new]
+            if nv.dims != (old,):
+                raise ValueError(f"replacement dimension {new!r} is not a 1D variable along the old dimension {old!r}")
+            out._vars.pop(new, None)
+            out._coords[new] = DataArray(nv.values, (new,), None, nv.attrs, new)
+            for store in (out._coords, out._vars):
+                for k, v in list(store.items()):
+                    if k != new and old in v.dims:
+                        store[k] = DataArray(v.data, tuple(new if d == old else d for d in v.dims), None, v.attrs, v.name, v.law)
+        return out
+
+    def where(self, cond, other=np.nan):
+        """xarray.Dataset.where over the data variables that contain every dimension of ``cond``."""
+        out = self.copy()
+        cdims = set(cond.dims) if isinstance(cond, DataArray) else None
+        for k, v in self._vars.items():
+            if cdims is None or cdims <= set(v.dims):
+                out._vars[k] = DataArray(self[k].where(cond, other).data, v.dims, None, v.attrs, k)
+        if "Sv" in out._vars and not (isinstance(other, float) and np.isnan(other)):
+            out._drop_range_laws()
+        return out
 
     def __contains__(self, key):
         return key in self._vars or key in self._coords

@@ -56,7 +56,10 @@ class ParamPack:
         self._keep = []
 
     def cp(self, x):
-        """scalar | (C,) | (C,1) | (C,P) | (P,) array -> epb_cp on the device (stride 0 = broadcast)."""
+        """scalar | (C,) | (C,1) | (1,P) | (C,P) | (P,) array -> epb_cp on the device (stride 0 = broadcast).
+        A 1-D array of length C is per-channel (also when C == P); per-ping parameters should be passed as (1,P)
+        (calibrate_ek._cp and consolidate.add_depth do, from the dimension names); a bare (P,) vector is accepted only
+        when P != C."""
         C, P = self.C, self.P
         a = np.asarray(getattr(x, "values", x), dtype=np.float64)
         if a.ndim == 0:
@@ -65,6 +68,8 @@ class ParamPack:
             a2, sc, sp = a, 1, 0
         elif a.ndim == 1 and a.shape[0] == P:
             a2, sc, sp = a, 0, 1
+        elif a.ndim == 2 and a.shape == (1, P) and not (C == 1):
+            a2, sc, sp = a.reshape(P), 0, 1
         elif a.ndim == 2 and a.shape == (C, 1):
             a2, sc, sp = a.reshape(C), 1, 0
         elif a.ndim == 2 and a.shape == (C, P):

@@ -229,7 +229,11 @@ def add_depth(echo_range, off_p, scale, C, P, R):
     """depth = off[p] + echo_range * scale (scale: (P,) per ping or (C, P)); float32 device tensor [C,P,R]."""
     pk = ParamPack(C, P, echo_range.device)
     out = empty((C, P, R), device=echo_range.device)
-    _lib.call("epb_add_depth", ptr(echo_range), pk.cp(np.asarray(off_p, dtype=np.float64)), pk.cp(np.asarray(scale, dtype=np.float64)),
+    off_p = np.asarray(off_p, dtype=np.float64)
+    scale = np.asarray(scale, dtype=np.float64)
+    off_p = off_p.reshape(1, -1) if off_p.ndim == 1 else off_p  # per ping: explicit (1, P), unambiguous when C == P
+    scale = scale.reshape(1, -1) if scale.ndim == 1 else scale
+    _lib.call("epb_add_depth", ptr(echo_range), pk.cp(off_p), pk.cp(scale),
               ptr(out), C, P, R, stream())
     out._keep = pk
     return out

@@ -55,6 +55,14 @@ def frequency_differencing(source_Sv, storage_options: dict = {}, freqABEq: str 
 
 def _mask_tensor(m, dev):
     """DataArray / ndarray / tensor -> (uint8 device tensor, has_channel).  NaN counts as False (api.py:431-435)."""
+    if isinstance(m, DataArray):  # align by dimension NAME like the reference (its own maskers return
+        # (channel, range_sample, ping_time)): transpose to ([channel,] ping_time, range_sample)
+        unknown = [d for d in m.dims if d not in ("channel", "ping_time", "range_sample")]
+        if unknown:
+            raise ValueError(f"mask has dimensions {unknown} that the source variable does not have")
+        want = tuple(d for d in ("channel", "ping_time", "range_sample") if d in m.dims)
+        if tuple(m.dims) != want and set(want) >= {"ping_time", "range_sample"}:
+            m = m.transpose(*want)
     data = m.data if isinstance(m, DataArray) else m
     dims = tuple(m.dims) if isinstance(m, DataArray) else None
     if isinstance(data, torch.Tensor):
@@ -127,7 +135,11 @@ def apply_mask(source_ds, mask: Union[DataArray, List[DataArray]], var_name: str
             attrs["history"] += f"\n{ma.pop('history')}"
         attrs.update(ma)
     output_ds = source_ds.copy()
-    output_ds[var_name] = DataArray(out, src.dims, name=var_name, attrs=attrs)
+    # a NaN fill keeps "NaN wherever the range variable is NaN"; a finite fill (or a fill array) does not, and the
+    # index-space binning of compute_MVBS must not be used on the result (Dataset.__setitem__ drops the range laws)
+    nan_fill = isinstance(fill, float) and fill != fill
+    trusted = isinstance(src.law, dict) and src.law.get("kind") == "derived"
+    output_ds[var_name] = DataArray(out, src.dims, name=var_name, attrs=attrs, law={"kind": "derived"} if (nan_fill and trusted) else None)
     prov = echopype_prov_attrs(process_type="mask")
     prov["mask_function"] = "mask.apply_mask"
     output_ds.attrs.update(prov)

@@ -556,7 +556,7 @@ class FusedPlan:
         if self.keep:
             kept = Dataset(coords={d: beam[d].values for d in DIMS})
             for k in self.keep:
-                da = DataArray(outs[k], DIMS, name=k)
+                da = DataArray(outs[k], DIMS, name=k, law={"kind": "derived"} if k in ("Sv", "Sv_corrected") else None)
                 if k == "echo_range":
                     da.law = {"rows": self.rows, "kind": "echo_range", "minmax": None}
                 kept[k] = da

@@ -1,0 +1,61 @@
+"""The documented processing chain of the reference (tests/utils/test_processinglevels_integration.py:103-141) through
+the public API: compute_Sv -> remove_background_noise(ping_num=10, range_sample_num=20) -> rename Sv_corrected to Sv ->
+frequency_differencing -> apply_mask -> compute_MVBS("30m", "1min"), against the same chain of the float64 oracle."""
+
+import numpy as np
+import pytest
+
+import oracle_glue as og
+from oracle import clean as oclean
+from oracle import commongrid as ogrid
+from oracle import mask as omask
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ep():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import echopype_b200 as ep
+
+    return ep
+
+
+@pytest.mark.parametrize("fill", [np.nan, -999.0])
+def test_documented_processing_chain(ep, fill):
+    from echopype_b200 import synth
+
+    ed = synth.make_ek60(C=3, P=200, R=600, seed=5, nan_tail=0.1)
+    ds = ep.calibrate.compute_Sv(ed)
+    den = ep.clean.remove_background_noise(ds, ping_num=10, range_sample_num=20)
+    assert den.attrs["processing_level"] == "Level 2B" if "processing_level" in den.attrs else True
+    out = den.rename_vars(name_dict={"Sv": "Sv_raw", "Sv_corrected": "Sv"})
+    f = list(out.frequency_nominal.values[:2])
+    eq = str(f[0]) + "Hz" + "-" + str(f[1]) + "Hz" + ">" + str(5) + "dB"
+    m = ep.mask.frequency_differencing(source_Sv=out, freqABEq=eq)
+    masked = ep.mask.apply_mask(source_ds=out, var_name="Sv", mask=m, fill_value=fill)
+    law = masked["echo_range"].law
+    if fill == fill:  # a finite fill puts values where echo_range is NaN: value binning, not the cached row table
+        assert law is None or law.get("rows") is None
+    else:
+        assert law is not None and law.get("rows") is not None
+    mv = ep.commongrid.compute_MVBS(masked, range_bin="30m", ping_time_bin="1min")
+
+    ref = og.ek60(ed, "Sv")
+    nz = oclean.remove_background_noise(ref["out"], ref["echo_range"], ref["sound_absorption"], 10, 20, None, "3.0dB")
+    svc = nz["Sv_corrected"]
+    mk = omask.frequency_differencing(svc, 0, 1, ">", 5.0)
+    want_masked = omask.apply_mask(svc, [mk], fill)
+    pt = np.asarray(ed["Sonar/Beam_group1"]["ping_time"].values).astype("datetime64[ns]").astype(np.int64)
+    want = ogrid.compute_MVBS(want_masked, ref["echo_range"], pt, range_bin="30m", ping_time_bin="1min")["Sv"]
+    got = mv["Sv"].values
+    assert got.shape == want.shape
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    # a sample within 1e-3 dB of the SNR threshold or of the 5 dB difference may fall on either side in float32; one such
+    # sample moves a 9000-member bin mean by < 1e-3 dB
+    assert np.abs(got[ok] - want[ok]).max() < 2e-3, float(np.abs(got[ok] - want[ok]).max())
+    assert np.median(np.abs(got[ok] - want[ok])) < 1e-4
