@@ -6,6 +6,17 @@ int epb_fast_launch_f32a(const void* pr, int T, int G, int noise, int threads, s
 int epb_fast_launch_f32b(const void* pr, int T, int G, int noise, int threads, size_t smem, cudaStream_t s);
 int epb_fast_launch_i16a(const void* pr, int T, int G, int noise, int threads, size_t smem, cudaStream_t s);
 int epb_fast_launch_i16b(const void* pr, int T, int G, int noise, int threads, size_t smem, cudaStream_t s);
+int epb_fast_launch_f32c(const void* pr, int T, int G, int noise, int threads, size_t smem, cudaStream_t s);
+int epb_fast_launch_i16c(const void* pr, int T, int G, int noise, int threads, size_t smem, cudaStream_t s);
+
+namespace {
+constexpr int kMaxPingNum = 64;  // two-sweep mode: up to 8 sub-tiles of 8 rows
+// sub-tiles per noise tile and rows per sub-tile
+inline void sweep_shape(int ping_num, int* S, int* T) {
+  *S = (ping_num + kMaxT - 1) / kMaxT;
+  *T = (ping_num + *S - 1) / *S;
+}
+}  // namespace
 
 // Tries to launch the fast path.  Returns 1 when launched (the general kernel must then be launched with the same
 // `irregular` flag so that exactly one of the two does the work), 0 when the static conditions do not hold.
@@ -15,8 +26,10 @@ int epb_pipeline_fast_try(const void* x, int x_i16, const epb_row* rows, const i
                           long long nX, int ping_num, int range_sample_num, float noise_max_lin, float snr_lin,
                           double* range_max_out, int sv_input, void* workspace, long long workspace_bytes, cudaStream_t s) {
   const bool noise = ping_num > 0;
-  const int T = noise ? ping_num : 4;
-  if (T > kMaxT || R % 4 != 0 || R > 4096 || R < 128 || C * nX >= (1LL << 31) || nR > 32000) return 0;
+  const bool sweep = noise && ping_num > kMaxT;  // the noise tile streams through the ring twice in sub-tiles
+  int S = 1, T = noise ? ping_num : 4;
+  if (sweep) sweep_shape(ping_num, &S, &T);
+  if (ping_num > kMaxPingNum || R % 4 != 0 || R > 4096 || R < 128 || C * nX >= (1LL << 31) || nR > 32000) return 0;
   if (x_i16 && (R % 8 != 0 || sv_input)) return 0;  // 16-byte rows for the bulk copies
   const int xb = x_i16 ? 2 : 4;
   if (noise && range_sample_num < 4) return 0;  // a column group of four may touch at most two range tiles
@@ -44,7 +57,8 @@ int epb_pipeline_fast_try(const void* x, int x_i16, const epb_row* rows, const i
   pr.irregular = irregular;
   pr.tiles = reinterpret_cast<const TileInfo*>((char*)workspace + 256);
   pr.C = C, pr.P = P, pr.nX = nX;
-  pr.nPt = (int)((P + T - 1) / T);
+  pr.PN = noise ? ping_num : T, pr.S = S;
+  pr.nPt = (int)((P + pr.PN - 1) / pr.PN);
   pr.ntiles = C * (long long)pr.nPt;
   pr.R = (int)R, pr.nR = nR, pr.rs_num = range_sample_num, pr.closed_right = closed_right, pr.nslots = nslots;
   pr.rt_lanes = 1;
@@ -58,20 +72,27 @@ int epb_pipeline_fast_try(const void* x, int x_i16, const epb_row* rows, const i
   pr.noise_max_lin = noise_max_lin;
   pr.snr1 = 1.f + snr_lin;
   pr.sv_input = sv_input;
-  if (workspace_bytes < 256 + pr.ntiles * (long long)sizeof(TileInfo)) return 0;
+  const long long ndesc = pr.ntiles * S;
+  if (workspace_bytes < 256 + ndesc * (long long)sizeof(TileInfo)) return 0;
   if (cudaMemsetAsync(irregular, 0, sizeof(int), s) != cudaSuccess) return 0;
-  prepare_kernel<<<(unsigned)((pr.ntiles + 127) / 128), 128, 0, s>>>(rows, xbin, P, nX, T, pr.nPt, pr.ntiles, sv_input,
-                                                                     const_cast<TileInfo*>(pr.tiles), irregular);
+  prepare_kernel<<<(unsigned)((ndesc + 127) / 128), 128, 0, s>>>(rows, xbin, P, nX, T, pr.PN, S, pr.nPt, ndesc, sv_input,
+                                                                 const_cast<TileInfo*>(pr.tiles), irregular);
   int rc = -2;
-  for (auto launcher : {x_i16 ? epb_fast_launch_i16a : epb_fast_launch_f32a, x_i16 ? epb_fast_launch_i16b : epb_fast_launch_f32b}) {
-    rc = launcher(&pr, T, G, noise ? 1 : 0, threads, smem, s);
-    if (rc != -2) break;
+  if (sweep) {
+    rc = (x_i16 ? epb_fast_launch_i16c : epb_fast_launch_f32c)(&pr, T, G, 1, threads, smem, s);
+  } else {
+    for (auto launcher : {x_i16 ? epb_fast_launch_i16a : epb_fast_launch_f32a, x_i16 ? epb_fast_launch_i16b : epb_fast_launch_f32b}) {
+      rc = launcher(&pr, T, G, noise ? 1 : 0, threads, smem, s);
+      if (rc != -2) break;
+    }
   }
   if (rc != 0) cudaMemsetAsync(irregular, 1, sizeof(int), s);  // could not launch: the general kernel does the work
   return 1;
 }
 
 long long epb_pipeline_fast_workspace(long long C, long long P, int ping_num) {
-  const int T = ping_num > 0 ? ping_num : 4;
-  return 256 + C * ((P + T - 1) / T) * (long long)sizeof(TileInfo);
+  const int PN = ping_num > 0 ? ping_num : 4;
+  int S = 1, T = PN;
+  if (ping_num > kMaxT && ping_num <= kMaxPingNum) sweep_shape(ping_num, &S, &T);
+  return 256 + C * ((P + PN - 1) / PN) * S * (long long)sizeof(TileInfo);
 }

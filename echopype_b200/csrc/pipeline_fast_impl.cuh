@@ -21,7 +21,14 @@
 //     float64 atomic triple per (CTA, range bin).
 // Handles the regular case: every tile's rows share one range law and have finite calibration constants (checked
 // on the device by prepare_kernel; otherwise the general kernel of pipeline.cu runs instead), R % 4 == 0 (8 for int16
-// input), R <= 4096, ping_num <= 8, range_sample_num >= 4, no full-size outputs.
+// input), R <= 4096, range_sample_num >= 4, no full-size outputs.
+//
+// ping_num > 8 (kSweep; the reference's own test setting is remove_background_noise(ping_num=10, range_sample_num=20),
+// tests/utils/test_processinglevels_integration.py:111): u of a whole noise tile no longer fits the registers and the tile
+// no longer fits the ring (10 x 4096 x 4 B = 160 KB).  The noise tile is cut into S = ceil(ping_num / 8) sub-tiles of T
+// rows that stream through the same ring TWICE: sweep 1 adds up the column sums of u (the noise estimate needs nothing
+// else), sweep 2 fetches the same rows again - from L2, where sweep 1 left them a few microseconds earlier, so HBM is
+// still read once - recomputes u and does the noise removal / binning with the now known noise.
 #pragma once
 #include "pipeline_common.cuh"
 
@@ -47,6 +54,7 @@ struct FastParams {
   const TileInfo* tiles;  // [ntiles] descriptors from prepare_kernel (workspace)
   long long C, P, nX, ntiles;
   int R, nR, rs_num, closed_right, nslots, nPt;
+  int PN, S;  // rows of a noise tile (ping_num) and sub-tiles per noise tile (1 unless kSweep); descriptors: [ntiles][S]
   int rt_lanes, rt_tpw, rt_recip;  // noise estimate: lanes per range tile, range tiles per warp, ceil(2^16 / lanes)
   float noise_max_lin;  // NaN: no cap
   float snr1;           // 1 + 10^(SNR/10)
@@ -78,15 +86,21 @@ __device__ __forceinline__ bool same_law(const epb_row& a, const epb_row& b) {
 // not share one range law, or rows with NaN calibration constants).  64 us on cfg2 (3.7 % of the step); staging the
 // 192-byte row records through shared memory for coalesced loads measured slower (81 us: too few loads in flight).
 __global__ void prepare_kernel(const epb_row* __restrict__ rows, const int* __restrict__ xbin, long long P, long long nX,
-                               int T, int nPt, long long ntiles, int sv_input, TileInfo* __restrict__ tiles,
+                               int T, int PN, int S, int nPt, long long ndesc, int sv_input, TileInfo* __restrict__ tiles,
                                int* __restrict__ irregular) {
-  const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (g >= ntiles) return;
+  const long long d = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (d >= ndesc) return;
+  const long long g = d / S;  // noise tile
+  const int ksub = (int)(d - g * S);
   const long long c = g / nPt;
   const int itile = (int)(g - c * nPt);
-  const long long p0 = (long long)itile * T;
-  const int Ta = (int)((p0 + T <= P) ? T : (P - p0));
+  const long long pt0 = (long long)itile * PN;  // first row of the noise tile
+  const long long p0 = pt0 + (long long)ksub * T;
+  long long pend = pt0 + ((ksub + 1) * T < PN ? (ksub + 1) * T : PN);
+  pend = pend < P ? pend : P;
+  const int Ta = (int)(pend > p0 ? pend - p0 : 0);
   const epb_row* r0 = rows + c * P + p0;
+  const epb_row* rt0 = rows + c * P + pt0;  // every row of a noise tile must share the law of its first row
   TileInfo ti;
   bool bad = false;
   int nruns = 0, prev_xb = 0, rcsame = 1;
@@ -98,7 +112,7 @@ __global__ void prepare_kernel(const epb_row* __restrict__ rows, const int* __re
   for (int t = 0; t < Ta; ++t) {
     const epb_row& r = r0[t];
     if (!sv_input && !(r.c0 == r.c0 && r.c1 == r.c1)) bad = true;
-    if (!same_law(r0[0], r)) bad = true;  // NaN laws never compare equal
+    if (!same_law(rt0[0], r)) bad = true;  // NaN laws never compare equal
     ti.rc[t] = sv_input ? make_float2(0.f, kDb2Log2) : make_float2(r.c0, r.c1);  // Sv input: e = 2^(Sv log2(10)/10)
     if (!(ti.rc[t].x == ti.rc[0].x && ti.rc[t].y == ti.rc[0].y)) rcsame = 0;
     int xb = xbin[p0 + t];
@@ -112,11 +126,11 @@ __global__ void prepare_kernel(const epb_row* __restrict__ rows, const int* __re
   }
   ti.nruns = nruns;
   ti.Ta = Ta;
-  ti.lawchg = (itile == 0) || !same_law(r0[0], *(r0 - T));
+  ti.lawchg = (ksub == 0) && ((itile == 0) || !same_law(rt0[0], *(rt0 - PN)));
   ti.rcsame = rcsame;
   ti.row0 = c * P + p0;
   ti.pad1 = 0, ti.pad2 = 0;
-  tiles[g] = ti;
+  tiles[d] = ti;
   if (bad) *irregular = 1;
 }
 
@@ -157,6 +171,8 @@ struct Producer {  // TMA issue cursor, used by one thread only (kept in shared 
   int ts;          // its tile slot (tile % NT)
   int ds;          // its descriptor slot (tile % (NT + 1))
   int c, it;       // channel / ping tile of `tile`
+  int k, ph;       // kSweep: sub-tile and sweep (0 / 1) of the next item; `tile` then counts items
+  int li;          // kSweep: local noise tile of the next item
 };
 
 // Range-only column terms of the u domain, computed once per range law with the accurate libm variants:
@@ -209,9 +225,10 @@ __device__ __forceinline__ float4 counts_to_db(uint2 w) {
   return make_float4(f01.x, f01.y, f23.x, f23.y);
 }
 
-template <int T, int G, bool kNoise, bool kI16>
+template <int T, int G, bool kNoise, bool kI16, bool kSweep = false>
 __global__ void __launch_bounds__(G == 1 ? EPB_G1_THREADS : 512 / (EPB_GBIG / 2), (G == 1 && EPB_G1_THREADS == 512) ? EPB_G1_BLOCKS : 1)
     pipeline_fast_kernel(const FastParams pr) {
+  static_assert(!kSweep || kNoise, "two sweeps only make sense with the noise estimate");
   if (*pr.irregular) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long s_full[kMaxTilesInFlight];  // one mbarrier per tile slot
@@ -256,21 +273,44 @@ __global__ void __launch_bounds__(G == 1 ? EPB_G1_THREADS : 512 / (EPB_GBIG / 2)
   const int nPt = pr.nPt;
   const uint32_t row_bytes = (uint32_t)R * (uint32_t)kXB;
   // one thread: issue every tile whose slot is free (the tile NT before it has been consumed)
+  const int S = kSweep ? pr.S : 1;
+  const int nitems = kSweep ? ntl * 2 * S : ntl;  // ring items: tiles, or (noise tile, sweep, sub-tile)
   auto issue_tiles = [&](int last_done) {
     Producer p = s_prod;
-    while (p.tile < ntl && p.tile - NT <= last_done) {
-      const long long p0 = (long long)p.it * T;
-      const int Ta = (int)((p0 + T <= pr.P) ? T : (pr.P - p0));
+    while (p.tile < nitems && p.tile - NT <= last_done) {
+      long long p0;
+      int Ta;
+      const TileInfo* desc;
+      if (!kSweep) {
+        p0 = (long long)p.it * T;
+        Ta = (int)((p0 + T <= pr.P) ? T : (pr.P - p0));
+        desc = pr.tiles + g0 + p.tile;
+      } else {
+        const long long pt0 = (long long)p.it * pr.PN;
+        p0 = pt0 + (long long)p.k * T;
+        long long pend = pt0 + ((p.k + 1) * T < pr.PN ? (p.k + 1) * T : pr.PN);
+        pend = pend < pr.P ? pend : pr.P;
+        Ta = (int)(pend > p0 ? pend - p0 : 0);
+        desc = pr.tiles + (g0 + p.li) * S + p.k;
+      }
       const unsigned char* src = reinterpret_cast<const unsigned char*>(pr.x) + ((long long)p.c * pr.P + p0) * (long long)row_bytes;
       unsigned long long* bar = &s_full[p.ts];
       unsigned char* dst = s_ring + (size_t)p.ts * T * row_bytes;
       mbar_expect_tx(bar, row_bytes * (uint32_t)Ta + (uint32_t)sizeof(TileInfo));
-      bulk_g2s(&s_tile[p.ds], pr.tiles + g0 + p.tile, (uint32_t)sizeof(TileInfo), bar);
-      bulk_g2s(dst, src, row_bytes * (uint32_t)Ta, bar);  // the rows of a tile are contiguous on both sides
+      bulk_g2s(&s_tile[p.ds], desc, (uint32_t)sizeof(TileInfo), bar);
+      if (Ta > 0) bulk_g2s(dst, src, row_bytes * (uint32_t)Ta, bar);  // the rows of a tile are contiguous on both sides
       ++p.tile;
       if (++p.ts == NT) p.ts = 0;
       if (++p.ds == NT + 1) p.ds = 0;
-      if (++p.it == nPt) p.it = 0, ++p.c;
+      if (!kSweep) {
+        if (++p.it == nPt) p.it = 0, ++p.c;
+      } else if (++p.k == S) {
+        p.k = 0;
+        if (++p.ph == 2) {
+          p.ph = 0, ++p.li;
+          if (++p.it == nPt) p.it = 0, ++p.c;
+        }
+      }
     }
     s_prod = p;
   };
@@ -284,6 +324,7 @@ __global__ void __launch_bounds__(G == 1 ? EPB_G1_THREADS : 512 / (EPB_GBIG / 2)
     for (int t = 0; t < kMaxT; ++t) s_last[t] = -1;
     const int c0 = (int)(g0 / nPt), it0 = (int)(g0 - (long long)c0 * nPt);
     s_prod.tile = 0, s_prod.ts = 0, s_prod.ds = 0, s_prod.c = c0, s_prod.it = it0;
+    s_prod.k = 0, s_prod.ph = 0, s_prod.li = 0;
   }
   for (int k = tid; k <= nR; k += nth) s_edges[k] = pr.edges[k];
   for (int k = tid; k < 2 * nRt; k += nth) s_def[k] = 0;
@@ -427,7 +468,17 @@ __global__ void __launch_bounds__(G == 1 ? EPB_G1_THREADS : 512 / (EPB_GBIG / 2)
       }
   };
 
-  for (int li = 0; li < ntl; ++li) {
+  float se_acc[kSweep ? G : 1][4];  // kSweep: column sums of u over the sub-tiles of the current noise tile (sweep 1)
+#pragma unroll
+  for (int g = 0; g < (kSweep ? G : 1); ++g)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) se_acc[g][k] = 0.f;
+  int rows_acc = 0;        // kSweep: rows of the current noise tile seen in sweep 1
+  float noise_keep = 0.f;  // kSweep: the noise of the current noise tile (linear), known after sweep 1
+  int swli = 0, swk = 0, swph = 0;  // kSweep: noise tile, sub-tile, sweep of the current item
+  for (int qi = 0; qi < nitems; ++qi) {
+    const int li = kSweep ? swli : qi;
+    const bool first_of_tile = !kSweep || (swph == 0 && swk == 0);
     const int it = li & 1;
     // ---- wait for the tile (rows + descriptor) ---------------------------------------------------------------------
     mbar_wait(&s_full[ts], par);
@@ -445,7 +496,7 @@ __global__ void __launch_bounds__(G == 1 ? EPB_G1_THREADS : 512 / (EPB_GBIG / 2)
     const int Ta = ti->Ta;
 
     // ---- new range-law segment: flush, recompute boundaries, column terms, keys ------------------------------------
-    if (ti->lawchg || li == 0) {
+    if (first_of_tile && (ti->lawchg || qi == 0)) {
       if (cur_cell >= 0) flush();
       cur_cell = -1;
       if (tid == 0) s_multi = 0;
@@ -588,12 +639,12 @@ __global__ void __launch_bounds__(G == 1 ? EPB_G1_THREADS : 512 / (EPB_GBIG / 2)
             }
             e[g][t][k] = ok ? v : -2.f;
           }
-          if (kNoise && missing && liveg[g] && s_tl[colg[g] + k] != 0.f)
+          if (kNoise && (!kSweep || swph == 0) && missing && liveg[g] && s_tl[colg[g] + k] != 0.f)
             atomicAdd(&s_def[it * nRt + (colg[g] + k) / pr.rs_num], missing);
         }
     }
 
-    if (is_last) {  // rows whose final sample is NaN need a search for the last defined range (flags: bits 8.. of s_hasnan)
+    if (is_last && (!kSweep || swph == 1)) {  // rows whose final sample is NaN need a search for the last defined range (flags: bits 8.. of s_hasnan)
       const int gl = last_group / nth;  // the group of this thread that holds the last column
       unsigned nm = 0u;
 #pragma unroll
@@ -612,7 +663,100 @@ __global__ void __launch_bounds__(G == 1 ? EPB_G1_THREADS : 512 / (EPB_GBIG / 2)
     }
 
     float noise_lin = 0.f;
-    if (kNoise) {
+    if (kSweep) {
+      const bool lastk = swk == S - 1;
+      if (swph == 0) {
+        // ---- sweep 1: only the column sums of u are kept; the last sub-tile runs the range-tile reduction ----------------
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) se_acc[kSweep ? g : 0][k] += se[g][k];
+        rows_acc += Ta;
+        if (lastk) {
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            const int b = bsplit[g];
+            const float(&cs)[4] = se_acc[kSweep ? g : 0];
+            const float A = cs[0] + ((b > 1) ? cs[1] : 0.f) + (((b > 2) ? cs[2] : 0.f) + ((b > 3) ? cs[3] : 0.f));
+            const float B = ((b > 1) ? 0.f : cs[1]) + (((b > 2) ? 0.f : cs[2]) + ((b > 3) ? 0.f : cs[3]));
+            if (liveg[g]) s_ga[colg[g] >> 2] = A, s_gb[colg[g] >> 2] = B;
+          }
+        }
+        __syncthreads();  // the sub-tile's slot is free; (last sub-tile) column sums visible
+        if (prod_warp && lane == 0) {
+          fence_proxy_async();
+          issue_tiles(qi);
+          if (lastk) s_hasnan[it ^ 1] = 0;
+        }
+        if (lastk) {
+          const int L = pr.rt_lanes, tpw = pr.rt_tpw;
+          const int slot = (lane * pr.rt_recip) >> 16;  // lane / L
+          const int q = lane - slot * L;
+          const bool hasnan = (s_hasnan[it] & 1) != 0;
+          unsigned m = kInfBits;
+          for (int rb = (tid >> 5) * tpw; rb < nRt; rb += (nth >> 5) * tpw) {  // warp-uniform
+            const int rt = rb + slot;
+            const bool in = slot < tpw && rt < nRt;
+            const int j0 = in ? rt * pr.rs_num : 0;
+            const int j1 = in ? ((j0 + pr.rs_num < R) ? j0 + pr.rs_num : R) : 0;
+            const int ga = (j0 + 3) >> 2, gb = (j1 + 3) >> 2;
+            float sm = (q == 0 && ga > 0 && in) ? s_gb[ga - 1] : 0.f;
+            for (int gq = ga + q; gq < gb; gq += L) sm += s_ga[gq];
+#pragma unroll
+            for (int d = 1; d < 8; d <<= 1) {
+              const float o = __shfl_down_sync(0xffffffffu, sm, d);
+              sm += (q + d < L) ? o : 0.f;
+            }
+            if (in && q == 0) {
+              int def = 0;
+              if (hasnan) {  // CTA-uniform
+                def = s_def[it * nRt + rt];
+                s_def[it * nRt + rt] = 0;
+              }
+              const int n = s_valid[rt] * rows_acc - def;
+              if (n > 0) {
+                const unsigned u = __float_as_uint(sm * rcp_approx((float)n));  // >= 0: uint order == float order
+                m = (u < m) ? u : m;
+              }
+            }
+          }
+          m = __reduce_min_sync(0xffffffffu, m);
+          if (lane == 0) s_wmin[tid >> 5] = m;
+          __syncthreads();
+          const unsigned u = __reduce_min_sync(0xffffffffu, lane < kMaxWarps ? s_wmin[lane] : kInfBits);
+          float v = (u == kInfBits) ? CUDART_NAN_F : __uint_as_float(u);
+          if (pr.noise_max_lin == pr.noise_max_lin) v = (v < pr.noise_max_lin) ? v : pr.noise_max_lin;  // NaN -> max
+          noise_keep = v;
+          if (tid == 0 && pr.noise_out) pr.noise_out[g0 + li] = kLog2ToDb * fast_log2(v);
+          __syncthreads();  // s_wmin / s_ga are rewritten by the next noise tile; s_fs (flush) aliases s_ga
+#pragma unroll
+          for (int g = 0; g < (kSweep ? G : 1); ++g)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) se_acc[g][k] = 0.f;
+          rows_acc = 0;
+        }
+        if (++swk == S) swk = 0, swph = 1;
+        continue;  // no binning in sweep 1
+      }
+      // ---- sweep 2: the noise is known; free the slot, then remove the noise and bin --------------------------------------
+      __syncthreads();
+      if (prod_warp && lane == 0) {
+        fence_proxy_async();
+        issue_tiles(qi);
+      }
+      const unsigned need_last = (unsigned)s_hasnan[it] >> 8;  // CTA-uniform, almost always 0
+      if (need_last) {
+        offer_last(need_last, e);
+        __syncthreads();
+        if (tid == 0) {
+          settle_last(need_last, ti->row0);
+          s_hasnan[it] &= 0xff;  // the flags belong to this sub-tile only
+        }
+        __syncthreads();
+      }
+      noise_lin = noise_keep;
+      if (++swk == S) swk = 0, swph = 0, ++swli;
+    } else if (kNoise) {
       // ---- phase 1: column sums of u -> column-group sums -> range-tile means -> min ---------------------------------
       // a group of four columns touches at most two range tiles (range_sample_num >= 4): columns k < bsplit[g] belong
       // to the tile of the first column (sum A), the rest to the next tile (sum B)
@@ -770,9 +914,9 @@ size_t fast_smem(long long R, int T, int nR, int ntiles_ring, int nRt, int xbyte
 
 constexpr size_t kSmemMax = 227 * 1024 - 2048;  // static shared memory of the kernel comes on top
 
-template <int T, int G, bool kNoise, bool kI16>
+template <int T, int G, bool kNoise, bool kI16, bool kSweep = false>
 int launch_fast(const FastParams& pr, int threads, size_t smem, cudaStream_t s) {
-  auto kern = pipeline_fast_kernel<T, G, kNoise, kI16>;
+  auto kern = pipeline_fast_kernel<T, G, kNoise, kI16, kSweep>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) return -1;
@@ -799,6 +943,22 @@ int launch_fast(const FastParams& pr, int threads, size_t smem, cudaStream_t s) 
       case TB: return EPB_FAST_LAUNCH_CASE(TB, true, I16);                                                            \
       case TC: return EPB_FAST_LAUNCH_CASE(TC, true, I16);                                                            \
       case TD: return EPB_FAST_LAUNCH_CASE(TD, true, I16);                                                            \
+    }                                                                                                                 \
+    return -2;                                                                                                        \
+  }
+
+// kSweep instantiations (ping_num > 8: sub-tiles of TA..TD rows, two sweeps)
+#define EPB_FAST_SWEEP_CASE(TT, I16) \
+  ((G != 1) ? launch_fast<TT, EPB_GBIG, true, I16, true>(pr, threads, smem, s) : launch_fast<TT, 1, true, I16, true>(pr, threads, smem, s))
+#define EPB_DEFINE_FAST_SWEEP_LAUNCHER(NAME, I16, TA, TB, TC, TD)                                                     \
+  int NAME(const void* prv, int T, int G, int noise, int threads, size_t smem, cudaStream_t s) {                      \
+    const FastParams& pr = *static_cast<const FastParams*>(prv);                                                       \
+    if (!noise) return -2;                                                                                            \
+    switch (T) {                                                                                                      \
+      case TA: return EPB_FAST_SWEEP_CASE(TA, I16);                                                                   \
+      case TB: return EPB_FAST_SWEEP_CASE(TB, I16);                                                                   \
+      case TC: return EPB_FAST_SWEEP_CASE(TC, I16);                                                                   \
+      case TD: return EPB_FAST_SWEEP_CASE(TD, I16);                                                                   \
     }                                                                                                                 \
     return -2;                                                                                                        \
   }

@@ -217,6 +217,13 @@ FAST_CASES = [
     ("ek60", (2, 83, 1024), False, 5, 30, None, "0.3m", "9s", "left"),      # bins narrower than a column group: per-column flush
     ("ek60", (2, 83, 1024), False, 3, 4, None, "1m", "9s", "right"),        # smallest range tile of the fast path; 5-sample bins
     ("ek60", (2, 300, 640), False, 5, 7, None, "50m", "10min", "left"),     # cells longer than the packed counters (flush by rows)
+    # ping_num > 8: two sweeps over sub-tiles (the reference's own test setting is ping_num=10, range_sample_num=20)
+    ("ek60", (3, 205, 4096), False, 10, 20, None, "20m", "20s", "left"),    # 2 sub-tiles of 5; P % 10 != 0: short last noise tile
+    ("ek60", (2, 97, 1024), False, 9, 30, "-125.0dB", "10m", "7s", "left"),  # 5 + 4 rows
+    ("ek60", (2, 140, 2048), False, 17, 25, None, "5m", "13s", "right"),    # 3 sub-tiles of 6 (6 + 6 + 5)
+    ("ek80", (3, 131, 1024), False, 32, 40, None, "20m", "12s", "left"),    # 4 sub-tiles of 8; P ends inside a sub-tile
+    ("ek60", (2, 61, 2048), True, 12, 30, None, "10m", "7s", "left"),       # law changes inside noise tiles -> general kernel via gate
+    ("azfp", (2, 143, 512), False, 20, 16, None, "2m", "10s", "left"),      # 3 sub-tiles of 7 (7 + 7 + 6)
 ]
 
 
@@ -253,13 +260,15 @@ def test_fast_kernel_equals_general_kernel(ep, kind, shape, tv, pn, rn, nmax, rb
     assert ok.sum() > 0.9 * (fb[..., 1] > 0).sum()
 
 
-def test_fast_kernel_vs_oracle_benchmark_shape(ep):
-    """Benchmark-shaped tile geometry (R = 4096, ping_num 5, 20 s bins) through the fast kernel against the oracle."""
+@pytest.mark.parametrize("pn,rn", [(5, 30), (10, 20)])
+def test_fast_kernel_vs_oracle_benchmark_shape(ep, pn, rn):
+    """Benchmark-shaped tile geometry (R = 4096, 20 s bins) through the fast kernel against the oracle: ping_num 5 (u in
+    registers) and the reference's own test setting ping_num=10, range_sample_num=20 (two sweeps over sub-tiles)."""
     from echopype_b200 import synth
 
     ed = synth.make_ek60(2, 120, 4096, seed=77, nan_tail=0.1)
-    ds = ep.pipeline.compute_Sv_clean_MVBS(ed, ping_num=5, range_sample_num=30, range_bin="20m", ping_time_bin="20s")
-    ref, mv, marg_bins, margin = _oracle_chain(ed, "ek60", 5, 30, None, "3.0dB", "20m", "20s")
+    ds = ep.pipeline.compute_Sv_clean_MVBS(ed, ping_num=pn, range_sample_num=rn, range_bin="20m", ping_time_bin="20s")
+    ref, mv, marg_bins, margin = _oracle_chain(ed, "ek60", pn, rn, None, "3.0dB", "20m", "20s")
     _check_mvbs(ds["Sv"].values, mv["Sv"], marg_bins)
 
 

@@ -105,6 +105,8 @@ I16_CASES = [
     ((2, 45, 1000), False, None, None, "20m", "20s"),  # Sv -> MVBS without noise removal
     ((2, 61, 2048), True, 5, 30, "10m", "7s"),      # irregular volume: ingest + general kernel through the scratch
     ((2, 50, 1004), False, 5, 30, "10m", "7s"),     # R % 8 != 0: no direct path, ingest + float pipeline
+    ((2, 123, 4096), False, 10, 20, "20m", "20s"),  # ping_num > 8: two sweeps over sub-tiles, counts read twice
+    ((2, 90, 1024), False, 17, 30, "10m", "7s"),    # three sub-tiles of 6
 ]
 
 
