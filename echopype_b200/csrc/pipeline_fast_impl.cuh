@@ -849,6 +849,47 @@ __global__ void __launch_bounds__(G == 1 ? EPB_G1_THREADS : 512 / (EPB_GBIG / 2)
     const float thr = kNoise ? noise_lin * pr.snr1 : -1.f;    // Sv_c - Sv_noise > SNR  <=>  u > noise (1 + 10^(SNR/10))
     const float nz = (noise_lin == noise_lin) ? noise_lin : 0.f;  // NaN noise: nothing survives, keep the sums clean
     const int nruns = ti->nruns;
+    // The usual tile: all T rows fall into ONE ping bin (one run, no row predicates, no run loop).  Straight-line code:
+    // per column pair and row FSET x2 + FFMA2 + FADD2.
+    if (nruns == 1 && Ta == T && ti->run_cell[0] >= 0) {
+      const int cell = ti->run_cell[0];
+      if (cell != cur_cell || acc.rows + T > kFlushRows) {
+        if (cur_cell >= 0) flush();
+        cur_cell = cell;
+      }
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const float4 t4 = *reinterpret_cast<const float4*>(s_tl + colg[g]);
+        const float tl[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+        for (int k = 0; k < 4; k += 2) {
+          float2 sg = make_float2(0.f, 0.f), ng = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            float2 m;
+            m.x = (e[g][t][k] > thr) ? 1.f : 0.f;
+            m.y = (e[g][t][k + 1] > thr) ? 1.f : 0.f;
+            sg = ffma2(m, make_float2(e[g][t][k], e[g][t][k + 1]), sg);
+            ng = fadd2(ng, m);
+          }
+          if (!kNoise) {  // thr = -1 lets the u = 0 of an undefined column through: not a survivor
+            ng.x = (tl[k] != 0.f) ? ng.x : 0.f;
+            ng.y = (tl[k + 1] != 0.f) ? ng.y : 0.f;
+          }
+          acc.s[g][k] = fmaf(tl[k], fmaf(-ng.x, nz, sg.x), acc.s[g][k]);
+          acc.s[g][k + 1] = fmaf(tl[k + 1], fmaf(-ng.y, nz, sg.y), acc.s[g][k + 1]);
+          acc.good[g][k] += ng.x;
+          acc.good[g][k + 1] += ng.y;
+        }
+        if (nanmask[g] != 0u && nanrange) {  // echo_range is NaN where the sample is NaN (range.py:143-148): not a member
+          const unsigned rows_mask = (T >= 8) ? 0xffffffffu : ((1u << (4 * T)) - 1u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc.nanm[g] += (unsigned)__popc(nanmask[g] & rows_mask & (0x11111111u << k)) << (8 * k);
+        }
+      }
+      acc.rows += T;
+      continue;
+    }
     int ta = 0;
     for (int r = 0; r < nruns; ++r) {
       const int tb = ti->run_end[r];
@@ -858,7 +899,6 @@ __global__ void __launch_bounds__(G == 1 ? EPB_G1_THREADS : 512 / (EPB_GBIG / 2)
         cur_cell = cell;
       }
       if (cell >= 0) {
-        const bool whole = (tb - ta == T);
 #pragma unroll
         for (int g = 0; g < G; ++g) {
           const float4 t4 = *reinterpret_cast<const float4*>(s_tl + colg[g]);
@@ -869,13 +909,8 @@ __global__ void __launch_bounds__(G == 1 ? EPB_G1_THREADS : 512 / (EPB_GBIG / 2)
 #pragma unroll
             for (int t = 0; t < T; ++t) {
               float2 m;
-              if (whole) {  // every u finite (or the -2 sentinel)
-                m.x = (e[g][t][k] > thr) ? 1.f : 0.f;
-                m.y = (e[g][t][k + 1] > thr) ? 1.f : 0.f;
-              } else {
-                m.x = (t >= ta && t < tb && e[g][t][k] > thr) ? 1.f : 0.f;
-                m.y = (t >= ta && t < tb && e[g][t][k + 1] > thr) ? 1.f : 0.f;
-              }
+              m.x = (t >= ta && t < tb && e[g][t][k] > thr) ? 1.f : 0.f;
+              m.y = (t >= ta && t < tb && e[g][t][k + 1] > thr) ? 1.f : 0.f;
               sg = ffma2(m, make_float2(e[g][t][k], e[g][t][k + 1]), sg);
               ng = fadd2(ng, m);
             }
