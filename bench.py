@@ -258,8 +258,42 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------------
 # own arm
 # ---------------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa(local_rank):
+    """Pin this process (and therefore its pinned host allocations: first touch) to the CPUs of the NUMA node the GPU
+    hangs off.  With 4-8 ranks streaming from pinned memory, host buffers on the wrong socket push every H2D copy over
+    the inter-socket link.  Returns a short description for the bench line."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        idx = local_rank
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis and all(v.strip().isdigit() for v in vis.split(",")):
+            idx = int(vis.split(",")[local_rank])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:  # nvml pads the domain to 8 hex digits, sysfs uses 4
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return {"numa_node": None, "note": "no NUMA information for the GPU"}
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed)}
+    except Exception as e:  # noqa: BLE001
+        return {"numa_node": None, "note": repr(e)[:120]}
+
+
 class Ctx:
     def __init__(self):
+        self.numa = bind_to_gpu_numa(int(os.environ.get("LOCAL_RANK", "0")))
         import torch
         import torch.distributed as dist
 
@@ -512,6 +546,18 @@ def e2e_legs(ctx, name, P_local, ping_offset, steps, seed):
     torch.cuda.synchronize()
     del x_dev
     ctx.free()
+    # the copies alone (same slabs, no kernels): what the host side of this rank can deliver while all ranks copy
+    slab = torch.empty((8192, R), dtype=torch.float32, device="cuda")
+    ctx.sync_all()
+    t0 = time.perf_counter()
+    for c_ in range(C):
+        for p0 in range(0, P_local, 8192):
+            pc = min(8192, P_local - p0)
+            slab[:pc].copy_(x_pin[c_, p0 : p0 + pc], non_blocking=True)
+    torch.cuda.synchronize()
+    (dt_copy,) = ctx.max_over_ranks([time.perf_counter() - t0])
+    out["h2d_only"] = {"GBps_per_rank": n_local * 4 / dt_copy / 1e9, "GBps_all_ranks": n_local * 4 * ctx.world / dt_copy / 1e9, "numa": ctx.numa}
+    del slab
     ed_host = make_echodata(name, P_local, ping_offset, device=False, backscatter=x_pin.numpy(), seed=seed)
     for _ in range(2):
         ds = pipeline.compute_Sv_clean_MVBS(ed_host, group=ctx.group, **kw)
@@ -675,6 +721,7 @@ def run_b200(args):
         e2e_P = P_local if name != "cfg5" else min(P_local, 100_000)
         legs = e2e_legs(ctx, name, e2e_P, ping_offset, max(1, min(steps, args.e2e_steps)), seed)
         line["e2e"] = legs["e2e"]
+        line["e2e"]["h2d_only"] = legs["h2d_only"]
         if e2e_P != P_local:
             line["e2e"]["sample"] = f"first {e2e_P} pings of the rank's shard (pinned host memory for the full 98 GB volume is not assumed)"
         if "e2e_raw_counts" in legs:
@@ -781,7 +828,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-sample-pings", type=int, default=4000)
     ap.add_argument("--ref-pings-per-core", type=int, default=1000)
-    ap.add_argument("--verify-pings", type=int, default=5005, help="pings per rank of the N-rank vs 1-rank verification volume")
+    ap.add_argument("--verify-pings", type=int, default=5000, help="pings per rank of the N-rank vs 1-rank verification volume")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip extra.kernels / extra.configs / extra.sustained")
     ap.add_argument("--no-verify", action="store_true", help="skip the N-rank vs 1-rank verification (N > 1)")
