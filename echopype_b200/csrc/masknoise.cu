@@ -514,6 +514,160 @@ __global__ void __launch_bounds__(256) pool_depth_mask_kernel(const float* __res
   }
 }
 
+// ---- transient noise as ONE strip kernel (rows of up to 4096 samples): no (sum, count) intermediate -------------------
+// A CTA walks a (channel, ping-chunk) strip ping by ping.  Each of its 512 threads owns 8 adjacent columns and keeps,
+// in float64 registers, the running sum over the 2 k + 1 pings of the window (reflected at the ends of the ping axis)
+// of the valid 10^(Sv/10) of its columns, plus the count: per output ping one row enters and one row leaves.  The
+// range window [n - w, n + w] of the array sliced at m0 (reflected at its ends) is then a difference of an inclusive
+// prefix sum ACROSS the columns, rebuilt per ping in shared memory (thread-local prefix over the 8 columns, warp scan,
+// 16 warp totals).  Reading the entering, the leaving and the centre row is all the traffic there is: the two-pass
+// form wrote a float2 per sample and read it twice (ncu: 39 GB of DRAM traffic for 8.2 GB algorithmic).
+constexpr int kStripThreads = 512, kStripCols = 8;
+
+__global__ void __launch_bounds__(kStripThreads, 1)
+    transient_strip_kernel(const float* __restrict__ Sv, const int* __restrict__ nsamp, unsigned char* __restrict__ mask,
+                           float* __restrict__ pooled, long long P, int R, int m0, int k, float thr, int chunk, int nchunks,
+                           long long nstrips) {
+  // one pad element per 8: a thread's 8 adjacent columns and its neighbours' fall into different banks (pidx)
+  extern __shared__ double s_pre[];                        // [pidx(L) + 1] inclusive prefix of the running column sums (sliced axis)
+  const int L = R - m0;
+  auto pidx = [](int e) { return e + (e >> 3); };
+  int* s_cpre = reinterpret_cast<int*>(s_pre + (pidx(L) + 2));   // [pidx(L) + 1]
+  __shared__ double s_ws[kStripThreads / 32];
+  __shared__ int s_wc[kStripThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n0 = tid * kStripCols;  // first absolute column of this thread
+  for (long long strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
+    const long long c = strip / nchunks;
+    const long long p0 = (strip - c * nchunks) * chunk, p1 = (p0 + chunk < P) ? p0 + chunk : P;
+    const int w = nsamp[c];
+    const float* base = Sv + c * P * (long long)R;
+    auto refl = [&](long long q) { return q < 0 ? -q - 1 : (q >= P ? 2 * P - q - 1 : q); };
+    // the thread's 8 columns of a row as linear values; columns outside [m0, R) count as invalid
+    auto load8 = [&](long long q, float (&v)[kStripCols]) {
+      if (n0 < R) {
+        const float4* r4 = reinterpret_cast<const float4*>(base + q * (long long)R + n0);
+        const float4 a = __ldg(r4), b = __ldg(r4 + 1);
+        v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < kStripCols; ++j) v[j] = CUDART_NAN_F;
+      }
+    };
+    double cs[kStripCols];
+    int cc[kStripCols];
+#pragma unroll
+    for (int j = 0; j < kStripCols; ++j) cs[j] = 0.0, cc[j] = 0;
+    auto add_row = [&](const float (&v)[kStripCols], int sign) {
+#pragma unroll
+      for (int j = 0; j < kStripCols; ++j) {
+        const float q = fast_exp2(v[j] * kDb2Log2);
+        const bool ok = (q == q) && (n0 + j >= m0);
+        cs[j] += ok ? (sign > 0 ? (double)q : -(double)q) : 0.0;
+        cc[j] += ok ? sign : 0;
+      }
+    };
+    // window of the first output ping, minus the row that enters in the first step
+    for (long long q = p0 - k; q < p0 + k; ++q) {
+      float v[kStripCols];
+      load8(refl(q), v);
+      add_row(v, +1);
+    }
+    // software pipeline: the three rows of the NEXT ping are requested before this ping's scan and barriers
+    float nin[kStripCols], nout[kStripCols], nc[kStripCols];
+    load8(refl(p0 + k), nin);
+    load8(p0, nc);
+#pragma unroll
+    for (int j = 0; j < kStripCols; ++j) nout[j] = CUDART_NAN_F;  // nothing leaves in the first step
+    for (long long p = p0; p < p1; ++p) {
+      float vin[kStripCols], vout[kStripCols], vc[kStripCols];
+#pragma unroll
+      for (int j = 0; j < kStripCols; ++j) vin[j] = nin[j], vout[j] = nout[j], vc[j] = nc[j];
+      if (p + 1 < p1) {
+        load8(refl(p + 1 + k), nin);
+        load8(p + 1, nc);
+        load8(refl(p - k), nout);
+      }
+      add_row(vin, +1);
+      add_row(vout, -1);  // NaN (first step) adds nothing
+      // inclusive prefix across the columns: thread-local, warp scan, warp totals
+      double lp[kStripCols];
+      int lc[kStripCols];
+      double run = 0.0;
+      int crun = 0;
+#pragma unroll
+      for (int j = 0; j < kStripCols; ++j) {
+        run += cs[j], crun += cc[j];
+        lp[j] = run, lc[j] = crun;
+      }
+      double inc = run;
+      int cinc = crun;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, inc, o);
+        const int tc = __shfl_up_sync(0xffffffffu, cinc, o);
+        if (lane >= o) inc += t, cinc += tc;
+      }
+      if (lane == 31) s_ws[wid] = inc, s_wc[wid] = cinc;
+      __syncthreads();  // also: the previous ping's window reads of s_pre are done
+      // exclusive offset of this warp: lanes 0..15 scan the 16 warp totals with shuffles (a serial walk over shared
+      // memory put ~15 dependent loads on the critical path of every ping)
+      double wt = (lane < kStripThreads / 32) ? s_ws[lane] : 0.0;
+      int wtc = (lane < kStripThreads / 32) ? s_wc[lane] : 0;
+      double wi = wt;
+      int wic = wtc;
+#pragma unroll
+      for (int o = 1; o < kStripThreads / 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, wi, o);
+        const int tc = __shfl_up_sync(0xffffffffu, wic, o);
+        if (lane >= o) wi += t, wic += tc;
+      }
+      const double off = (inc - run) + __shfl_sync(0xffffffffu, wi - wt, wid);
+      const int coff = (cinc - crun) + __shfl_sync(0xffffffffu, wic - wtc, wid);
+#pragma unroll
+      for (int j = 0; j < kStripCols; ++j) {
+        const int jj = n0 + j - m0;  // index on the sliced axis
+        if (jj >= 0 && jj < L) s_pre[pidx(jj + 1)] = off + lp[j], s_cpre[pidx(jj + 1)] = coff + lc[j];
+      }
+      if (tid == 0) s_pre[0] = 0.0, s_cpre[0] = 0;
+      __syncthreads();
+      // range windows, pooled Sv, mask: 8 outputs per thread
+      if (n0 < R) {
+        unsigned mlo = 0u, mhi = 0u;
+        float pv[kStripCols];
+#pragma unroll
+        for (int j = 0; j < kStripCols; ++j) {
+          const int jj = n0 + j - m0;
+          float pooled_db = CUDART_NAN_F;
+          if (jj >= 0) {
+            const int lo = jj - w, hi = jj + w;
+            const int ca = lo < 0 ? 0 : lo, cb = hi >= L ? L - 1 : hi;
+            double ws = s_pre[pidx(cb + 1)] - s_pre[pidx(ca)];
+            int wc = s_cpre[pidx(cb + 1)] - s_cpre[pidx(ca)];
+            if (lo < 0) ws += s_pre[pidx(-lo)] - s_pre[0], wc += s_cpre[pidx(-lo)] - s_cpre[0];               // [0, -lo - 1]
+            if (hi >= L)                                                                                       // [2L-hi-1, L-1]
+              ws += s_pre[pidx(L)] - s_pre[pidx(2 * L - hi - 1)], wc += s_cpre[pidx(L)] - s_cpre[pidx(2 * L - hi - 1)];
+            if (wc > 0) pooled_db = kLog2ToDb * fast_log2(__fdividef((float)ws, (float)wc));
+          }
+          pv[j] = pooled_db;
+          const unsigned bit = (jj >= 0 && vc[j] - pooled_db > thr) ? 1u : 0u;
+          if (j < 4)
+            mlo |= bit << (8 * j);
+          else
+            mhi |= bit << (8 * (j - 4));
+        }
+        *reinterpret_cast<uint2*>(mask + (c * P + p) * (long long)R + n0) = make_uint2(mlo, mhi);
+        if (pooled) {
+          float4* o4 = reinterpret_cast<float4*>(pooled + (c * P + p) * (long long)R + n0);
+          o4[0] = make_float4(pv[0], pv[1], pv[2], pv[3]);
+          o4[1] = make_float4(pv[4], pv[5], pv[6], pv[7]);
+        }
+      }
+    }
+    __syncthreads();  // next strip rewrites s_ws / s_pre
+  }
+}
+
 }  // namespace
 
 extern "C" int epb_range_diff_mean(const float* range_var, double* sum, unsigned long long* count, epb_i64 C, epb_i64 P,
@@ -557,7 +711,7 @@ extern "C" int epb_transient_noise_mask(const float* Sv, const int* nsamp, float
                                         unsigned char* mask, float* pooled_Sv, epb_i64 C, epb_i64 P, epb_i64 R,
                                         int min_range_sample, int max_nsamp, int num_side_pings, float threshold,
                                         void* stream) {
-  EPB_REQUIRE(Sv && nsamp && window_sums && mask, "NULL pointer");
+  EPB_REQUIRE(Sv && nsamp && mask, "NULL pointer");
   EPB_REQUIRE(max_nsamp >= 1 && (max_nsamp <= R - min_range_sample || min_range_sample == R),
               "range window longer than the sliced range axis (single reflection)");
   EPB_REQUIRE(C > 0 && C < 65536 && P > 0 && R > 0 && num_side_pings >= 0, "bad shape");
@@ -567,6 +721,26 @@ extern "C" int epb_transient_noise_mask(const float* Sv, const int* nsamp, float
   const int L = (int)R - min_range_sample;
   const size_t smem = (size_t)(L + 1) * 12 + 8;
   EPB_REQUIRE(smem <= 200 * 1024, "range_sample dimension too long for the shared-memory prefix sums");
+  // rows of up to 4096 samples (8 columns x 512 threads), 16-byte aligned: the single-pass strip kernel
+  if (R % 8 == 0 && R <= kStripThreads * kStripCols && L > 0 && ((uintptr_t)Sv % 16) == 0 && ((uintptr_t)mask % 8) == 0 &&
+      ((uintptr_t)pooled_Sv % 16) == 0) {
+    // strips: at least ~3 per SM, chunks not shorter than 8 windows (the 2 k pings of warm-up are read twice)
+    const long long want = ((long long)epb_num_sms() * 3 + C - 1) / C;
+    long long chunk = (P + want - 1) / want;
+    const long long min_chunk = 8LL * (2 * num_side_pings + 1);
+    if (chunk < min_chunk) chunk = min_chunk;
+    if (chunk > P) chunk = P;
+    const long long nchunks = (P + chunk - 1) / chunk;
+    const size_t sm = (size_t)(L + L / 8 + 4) * 12 + 32;
+    if (sm > 48 * 1024 &&
+        cudaFuncSetAttribute(transient_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess)
+      return epb_check_launch("epb_transient_noise_mask(smem)");
+    const long long nstrips = nchunks * C, capg = (long long)epb_num_sms();
+    transient_strip_kernel<<<(unsigned)(nstrips < capg ? nstrips : capg), kStripThreads, sm, (cudaStream_t)stream>>>(
+        Sv, nsamp, mask, pooled_Sv, P, (int)R, min_range_sample, num_side_pings, threshold, (int)chunk, (int)nchunks, nstrips);
+    return epb_check_launch("epb_transient_noise_mask(strip)");
+  }
+  EPB_REQUIRE(window_sums, "window_sums scratch is needed for rows longer than 4096 samples");
   const long long nrows = C * P, cap = (long long)epb_num_sms() * 8;
   if (L > 0) {
     if (smem > 48 * 1024 &&

@@ -378,8 +378,12 @@ def transient_noise_mask_depth(Sv, depth, C, P, R, dmin, dmax, depth_bin, exclud
 def transient_noise_mask(Sv, nsamp, C, P, R, min_range_sample, num_side_pings, threshold, want_pooled=False, out=None):
     """out: optional (mask, window_sums) buffers to reuse."""
     ns = torch.from_numpy(np.ascontiguousarray(nsamp, dtype=np.int32)).to(Sv.device)
-    mask, sums = out if out is not None else (torch.empty((C, P, R), dtype=torch.uint8, device=Sv.device),
-                                              torch.empty((C, P, R, 2), dtype=torch.float32, device=Sv.device))
+    strip = R % 8 == 0 and R <= 4096  # the single-pass strip kernel needs no (sum, count) scratch (8 bytes per sample)
+    if out is not None:
+        mask, sums = out
+    else:
+        mask = torch.empty((C, P, R), dtype=torch.uint8, device=Sv.device)
+        sums = None if strip else torch.empty((C, P, R, 2), dtype=torch.float32, device=Sv.device)
     pooled = torch.empty((C, P, R), dtype=torch.float32, device=Sv.device) if want_pooled else None
     _lib.call("epb_transient_noise_mask", ptr(Sv), ptr(ns), ptr(sums), ptr(mask), ptr(pooled), C, P, R, int(min_range_sample),
               int(max(nsamp)), int(num_side_pings), ctypes.c_float(float(threshold)), stream())

@@ -271,7 +271,8 @@ int epb_impulse_noise_mask_depth(const float* Sv, const float* depth, const doub
 /* Transient noise (clean/utils.py:109-189 with func = nanmean, clean/api.py:163-166): pooled Sv = dB of the nanmean of
  * 10^(Sv/10) over (2 k + 1) pings x (2 nsamp[c] + 1) range samples of the volume sliced at min_range_sample, borders
  * reflected (scipy.ndimage "reflect"); mask [C,P,R] uint8 = Sv - pooled > threshold, 0 above min_range_sample.
- * window_sums: [C,P,R] float2 scratch; pooled_Sv: NULL or [C,P,R] float32 (NaN above min_range_sample).
+ * window_sums: [C,P,R] float2 scratch, needed only for rows longer than 4096 samples or R % 8 != 0 (may be NULL
+ * otherwise: such rows take a single-pass strip kernel); pooled_Sv: NULL or [C,P,R] float32 (NaN above min_range_sample).
  * max_nsamp = max(nsamp) (validated against the sliced axis length: one reflection per border). */
 int epb_transient_noise_mask(const float* Sv, const int* nsamp, float* window_sums, unsigned char* mask, float* pooled_Sv,
                              epb_i64 C, epb_i64 P, epb_i64 R, int min_range_sample, int max_nsamp, int num_side_pings,

@@ -162,6 +162,43 @@ def test_compute_MVBS_generic_path(ep, skipna, f64):
     og.compare_db(got["Sv"].values, want["Sv"], ATOL, "MVBS")
 
 
+@pytest.mark.parametrize("case", ["narrow_bins", "non_monotone", "closed_right_wide", "gaps_and_outside"])
+def test_compute_MVBS_generic_path_stress(ep, case):
+    """The staged generic kernel keeps two adjacent bins per thread in registers and falls back to an exact per-sample path
+    when a thread's chunk of samples holds a third bin: bins narrower than the chunk, a range variable that is not
+    monotone, samples outside the grid, rows wider than one pass."""
+    from echopype_b200.dataset import Dataset
+
+    g = np.random.default_rng({"narrow_bins": 1, "non_monotone": 2, "closed_right_wide": 3, "gaps_and_outside": 4}[case])
+    C, P, R = (2, 45, 4096) if case != "closed_right_wide" else (1, 30, 8192)
+    Sv = g.uniform(-90, -40, (C, P, R)).astype(np.float32)
+    Sv[g.random((C, P, R)) < 0.03] = np.nan
+    rng = np.cumsum(g.uniform(0.01, 0.05, (C, P, R)), axis=2).astype(np.float32)  # ~120 m
+    kw = dict(range_bin="20m", ping_time_bin="10s")
+    if case == "narrow_bins":
+        kw["range_bin"] = "0.2m"  # ~7 samples per bin: every 16-sample chunk holds three or more bins
+    elif case == "non_monotone":
+        rng = g.permuted(rng, axis=2).astype(np.float32)
+        kw["range_bin"] = "7m"
+    elif case == "closed_right_wide":
+        kw.update(range_bin="3m", closed="right")
+        rng[0, :, ::97] = np.round(rng[0, :, ::97] / 3.0) * 3.0  # samples exactly on bin edges
+    else:
+        rng[:, ::3, 1000:1500] = np.nan          # NaN coordinates in the middle of rows
+        rng[1, :, :300] -= 5.0                     # negative ranges: below the first edge
+        kw["range_var_max"] = "63m"                # samples beyond the grid
+    pt = np.datetime64("2020-01-01T00:00:03", "ns") + (np.arange(P) * 1_300_000_000).astype("timedelta64[ns]")
+    ds = Dataset(
+        {"Sv": (("channel", "ping_time", "range_sample"), Sv), "echo_range": (("channel", "ping_time", "range_sample"), rng),
+         "frequency_nominal": (("channel",), np.array([38e3, 120e3][:C]))},
+        coords={"channel": np.array(["a", "b"][:C], dtype=object), "ping_time": pt, "range_sample": np.arange(R)},
+    )
+    got = ep.commongrid.compute_MVBS(ds, **kw)
+    want = _mvbs_oracle(Sv, rng, pt, **kw)
+    assert got["Sv"].shape == want["Sv"].shape
+    og.compare_db(got["Sv"].values, want["Sv"], ATOL, "MVBS " + case)
+
+
 def test_compute_MVBS_validation(ep):
     ed, ds = _sv_dataset(ep, (1, 10, 64))
     with pytest.raises(ValueError, match="range_var must be one of 'echo_range' or 'depth'."):
