@@ -165,7 +165,7 @@ def mask_transient_noise(ds_Sv, func: str = "nanmean", depth_bin: str = "10m", n
     Locate and create a mask for transient noise using a pooling comparison (Ryan et al. 2015; arguments as
     echopype.clean.mask_transient_noise, clean/api.py:30-166).
 
-    Pooled Sv is the mean (linear domain, ``func="nanmean"``) over ``2 num_side_pings + 1`` pings and, by default, the
+    Pooled Sv is the mean or the median (linear domain, ``func="nanmean"`` / ``"nanmedian"``) over ``2 num_side_pings + 1`` pings and, by default, the
     samples within ``depth_bin`` of the sample's own depth (windows of ``range_var`` VALUES, valid where the window stays
     inside the data and below ``exclude_above``); with ``use_index_binning=True`` over ``2 ceil(depth_bin / mean sample
     spacing) + 1`` range samples with reflected borders, below the first sample deeper than ``exclude_above``.  The mask is
@@ -181,15 +181,15 @@ def mask_transient_noise(ds_Sv, func: str = "nanmean", depth_bin: str = "10m", n
     thr = extract_dB(transient_noise_threshold)
     depth_bin = _parse_x_bin(depth_bin, "range_bin")
     exclude_above = _parse_x_bin(exclude_above, "range_bin")
-    if func != "nanmean":
-        raise NotImplementedError("func='nanmedian' (a sort per window) is outside the accelerated path; use func='nanmean'")
+    median = func == "nanmedian"  # a selection per sample (radix select over the window) instead of window sums
     if not (isinstance(num_side_pings, (int, np.integer)) and num_side_pings >= 0):
         raise ValueError("num_side_pings must be a non-negative integer")
     Sv, rng, C, P, R = _index_binning_inputs(ds_Sv, range_var, "transient")
     if not use_index_binning:
         # clean/utils.py:28-105 pool_Sv: windows of depth VALUES (d +- depth_bin) over pings p - k .. p + k
         lo, hi, _ = kernels.minmax(rng)
-        mask, _ = kernels.transient_noise_mask_depth(Sv, rng, C, P, R, lo, hi, depth_bin, exclude_above, int(num_side_pings), thr)
+        pool = kernels.transient_noise_mask_depth_median if median else kernels.transient_noise_mask_depth
+        mask, _ = pool(Sv, rng, C, P, R, lo, hi, depth_bin, exclude_above, int(num_side_pings), thr)
         return DataArray(mask, DIMS, coords=_mask_coords(ds_Sv), name="Sv")
     nsamp = _samples_per_bin(rng, depth_bin, C, P, R)
     # clean/utils.py:141: np.argmin over the WHOLE (channel, ping_time, range_sample) <= mask, i.e. the first flat index
@@ -198,5 +198,6 @@ def mask_transient_noise(ds_Sv, func: str = "nanmean", depth_bin: str = "10m", n
     m0 = 0 if m0 is None else m0
     if m0 >= R:  # slice(min_range_sample, None) is empty: nothing is pooled, nothing is masked
         m0 = R
-    mask, _ = kernels.transient_noise_mask(Sv, nsamp, C, P, R, m0, int(num_side_pings), thr)
+    pool = kernels.transient_noise_mask_median if median else kernels.transient_noise_mask
+    mask, _ = pool(Sv, nsamp, C, P, R, m0, int(num_side_pings), thr)
     return DataArray(mask, DIMS, coords=_mask_coords(ds_Sv), name="Sv")

@@ -514,6 +514,112 @@ __global__ void __launch_bounds__(256) pool_depth_mask_kernel(const float* __res
   }
 }
 
+// ---- transient noise with func = nanmedian (clean/api.py:132-145: generic_filter(np.nanmedian) / pool_Sv(func)) --------
+// The median of the valid 10^(Sv/10) of a window is a selection, not a sum: no prefix trick.  One thread per output
+// sample walks its window once per bit of a radix select over the float32 bit patterns (positive floats order like
+// their bit patterns): 32 passes for the lower middle element, 32 more for the upper one when the count is even
+// (np.nanmedian averages the two).  O(64 x window) per sample - the reference's own cost class (it evaluates
+// np.nanmedian per sample in Python / dask) - meant for the volumes this option is used on, not for cfg2.
+template <typename ForEach>
+__device__ float window_nanmedian(ForEach for_each) {
+  int m = 0;
+  for_each([&](float v) { m += (v == v) ? 1 : 0; });
+  if (m == 0) return CUDART_NAN_F;
+  auto select = [&](int kth) {  // kth smallest (0-based) of the valid values
+    unsigned prefix = 0u;
+    for (int bit = 31; bit >= 0; --bit) {
+      const unsigned hi_mask = (bit == 31) ? 0u : (0xffffffffu << (bit + 1));
+      int zeros = 0;
+      for_each([&](float v) {
+        const unsigned u = __float_as_uint(v);
+        zeros += ((v == v) && ((u & hi_mask) == prefix) && !((u >> bit) & 1u)) ? 1 : 0;
+      });
+      if (kth >= zeros) {
+        prefix |= 1u << bit;
+        kth -= zeros;
+      }
+    }
+    return __uint_as_float(prefix);
+  };
+  const float a = select((m - 1) / 2);
+  if (m & 1) return a;
+  const float b = select(m / 2);
+  return 0.5f * (a + b);
+}
+
+// index windows: (2 k + 1) pings x (2 w + 1) range samples of the array sliced at m0, both reflected (scipy "reflect")
+__global__ void __launch_bounds__(128) transient_median_kernel(const float* __restrict__ Sv, const int* __restrict__ nsamp,
+                                                               unsigned char* __restrict__ mask, float* __restrict__ pooled,
+                                                               long long P, int R, int m0, int k, float thr, long long total) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int L = R - m0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long row = i / R;
+    const int n = (int)(i - row * R);
+    const long long c = row / P, p = row - c * P;
+    float pv = CUDART_NAN_F;
+    if (n >= m0) {
+      const int w = nsamp[c], j = n - m0;
+      const float* base = Sv + c * P * (long long)R + m0;
+      pv = window_nanmedian([&](auto&& f) {
+        for (long long q = p - k; q <= p + k; ++q) {
+          const long long qq = q < 0 ? -q - 1 : (q >= P ? 2 * P - q - 1 : q);
+          const float* r = base + qq * (long long)R;
+          for (int jj = j - w; jj <= j + w; ++jj) {
+            const int jr = jj < 0 ? -jj - 1 : (jj >= L ? 2 * L - jj - 1 : jj);
+            f(fast_exp2(r[jr] * kDb2Log2));
+          }
+        }
+      });
+      pv = kLog2ToDb * log2f(pv);
+    }
+    mask[i] = (Sv[i] - pv > thr) ? 1 : 0;
+    if (pooled) pooled[i] = pv;
+  }
+}
+
+// depth-value windows (pool_Sv, clean/utils.py:28-105): the samples of pings p - k .. p + k whose depth lies within
+// depth_bin of the sample's own depth; valid windows only (same conditions as pool_depth_mask_kernel)
+__global__ void __launch_bounds__(128) transient_median_depth_kernel(const float* __restrict__ Sv, const float* __restrict__ depth,
+                                                                     unsigned char* __restrict__ mask, float* __restrict__ pooled,
+                                                                     long long P, int R, double dmin, double dmax, double bin,
+                                                                     double exclude_above, int k, float thr, long long total) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long row = i / R;
+    const long long c = row / P, p = row - c * P;
+    const double d = (double)depth[i];
+    float pv = CUDART_NAN_F;
+    if ((d - bin >= dmin) && (d + bin <= dmax) && (d - bin >= exclude_above) && (p - k >= 0) && (p + k <= P)) {
+      const double lo_v = d - bin, hi_v = d + bin;
+      const long long q1 = (p + k < P) ? p + k : P - 1;
+      pv = window_nanmedian([&](auto&& f) {
+        for (long long q = p - k; q <= q1; ++q) {
+          const float* dr = depth + (c * P + q) * (long long)R;
+          const float* sr = Sv + (c * P + q) * (long long)R;
+          int lo = 0, hi = R;  // first sample with depth >= lo_v (NaN counts as +inf)
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            const float v = dr[mid];
+            if (!(v == v) || (double)v >= lo_v)
+              hi = mid;
+            else
+              lo = mid + 1;
+          }
+          for (int n = lo; n < R; ++n) {
+            const float v = dr[n];
+            if (!(v == v) || (double)v > hi_v) break;
+            f(fast_exp2(sr[n] * kDb2Log2));
+          }
+        }
+      });
+      pv = kLog2ToDb * log2f(pv);
+    }
+    mask[i] = (Sv[i] - pv > thr) ? 1 : 0;
+    if (pooled) pooled[i] = pv;
+  }
+}
+
 // ---- transient noise as ONE strip kernel (rows of up to 4096 samples): no (sum, count) intermediate -------------------
 // A CTA walks a (channel, ping-chunk) strip ping by ping.  Each of its 512 threads owns 8 adjacent columns and keeps,
 // in float64 registers, the running sum over the 2 k + 1 pings of the window (reflected at the ends of the ping axis)
@@ -802,4 +908,31 @@ extern "C" int epb_transient_noise_mask_depth(const float* Sv, const float* dept
       Sv, depth, prefix_sums, prefix_counts, mask, pooled_Sv, P, (int)R, depth_min, depth_max, depth_bin, exclude_above,
       num_side_pings, threshold, total);
   return epb_check_launch("epb_transient_noise_mask_depth");
+}
+
+extern "C" int epb_transient_noise_mask_median(const float* Sv, const int* nsamp, unsigned char* mask, float* pooled_Sv, epb_i64 C,
+                                               epb_i64 P, epb_i64 R, int min_range_sample, int max_nsamp, int num_side_pings,
+                                               float threshold, void* stream) {
+  EPB_REQUIRE(Sv && nsamp && mask, "NULL pointer");
+  EPB_REQUIRE(C > 0 && P > 0 && R > 0 && num_side_pings >= 0, "bad shape");
+  EPB_REQUIRE(min_range_sample >= 0 && min_range_sample <= R, "min_range_sample outside the range axis");
+  EPB_REQUIRE(max_nsamp >= 1 && (max_nsamp <= R - min_range_sample || min_range_sample == R),
+              "range window longer than the sliced range axis (single reflection)");
+  EPB_REQUIRE(num_side_pings <= P, "num_side_pings must not exceed the number of pings (single reflection)");
+  const long long total = C * P * R, cap = (long long)epb_num_sms() * 16, gb = (total + 127) / 128;
+  transient_median_kernel<<<(unsigned)(gb < cap ? gb : cap), 128, 0, (cudaStream_t)stream>>>(
+      Sv, nsamp, mask, pooled_Sv, P, (int)R, min_range_sample, num_side_pings, threshold, total);
+  return epb_check_launch("epb_transient_noise_mask_median");
+}
+
+extern "C" int epb_transient_noise_mask_depth_median(const float* Sv, const float* depth, unsigned char* mask, float* pooled_Sv,
+                                                     epb_i64 C, epb_i64 P, epb_i64 R, double depth_min, double depth_max,
+                                                     double depth_bin, double exclude_above, int num_side_pings, float threshold,
+                                                     void* stream) {
+  EPB_REQUIRE(Sv && depth && mask, "NULL pointer");
+  EPB_REQUIRE(C > 0 && P > 0 && R > 0 && num_side_pings >= 0, "bad shape");
+  const long long total = C * P * R, cap = (long long)epb_num_sms() * 16, gb = (total + 127) / 128;
+  transient_median_depth_kernel<<<(unsigned)(gb < cap ? gb : cap), 128, 0, (cudaStream_t)stream>>>(
+      Sv, depth, mask, pooled_Sv, P, (int)R, depth_min, depth_max, depth_bin, exclude_above, num_side_pings, threshold, total);
+  return epb_check_launch("epb_transient_noise_mask_depth_median");
 }

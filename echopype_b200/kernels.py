@@ -390,6 +390,26 @@ def transient_noise_mask(Sv, nsamp, C, P, R, min_range_sample, num_side_pings, t
     return mask, pooled
 
 
+def transient_noise_mask_median(Sv, nsamp, C, P, R, min_range_sample, num_side_pings, threshold, want_pooled=False):
+    """func="nanmedian", index windows."""
+    ns = torch.from_numpy(np.ascontiguousarray(nsamp, dtype=np.int32)).to(Sv.device)
+    mask = torch.empty((C, P, R), dtype=torch.uint8, device=Sv.device)
+    pooled = torch.empty((C, P, R), dtype=torch.float32, device=Sv.device) if want_pooled else None
+    _lib.call("epb_transient_noise_mask_median", ptr(Sv), ptr(ns), ptr(mask), ptr(pooled), C, P, R, int(min_range_sample),
+              int(max(nsamp)), int(num_side_pings), ctypes.c_float(float(threshold)), stream())
+    return mask, pooled
+
+
+def transient_noise_mask_depth_median(Sv, depth, C, P, R, dmin, dmax, depth_bin, exclude_above, num_side_pings, threshold, want_pooled=False):
+    """func="nanmedian", depth-value windows."""
+    mask = torch.empty((C, P, R), dtype=torch.uint8, device=Sv.device)
+    pooled = torch.empty((C, P, R), dtype=torch.float32, device=Sv.device) if want_pooled else None
+    _lib.call("epb_transient_noise_mask_depth_median", ptr(Sv), ptr(depth), ptr(mask), ptr(pooled), C, P, R,
+              ctypes.c_double(float(dmin)), ctypes.c_double(float(dmax)), ctypes.c_double(float(depth_bin)),
+              ctypes.c_double(float(exclude_above)), int(num_side_pings), ctypes.c_float(float(threshold)), stream())
+    return mask, pooled
+
+
 def is_raw_counts(x):
     """True for int16 raw power counts (the ingest format: -32768 = padding), host array or tensor."""
     return getattr(x, "dtype", None) in (torch.int16, np.dtype("int16"))

@@ -277,6 +277,15 @@ int epb_impulse_noise_mask_depth(const float* Sv, const float* depth, const doub
 int epb_transient_noise_mask(const float* Sv, const int* nsamp, float* window_sums, unsigned char* mask, float* pooled_Sv,
                              epb_i64 C, epb_i64 P, epb_i64 R, int min_range_sample, int max_nsamp, int num_side_pings,
                              float threshold, void* stream);
+/* func = "nanmedian" (clean/api.py:132-145): pooled Sv = dB of np.nanmedian of 10^(Sv/10) over the same windows.  A
+ * selection per sample (radix select over the window, O(64 x window)), no scratch. */
+int epb_transient_noise_mask_median(const float* Sv, const int* nsamp, unsigned char* mask, float* pooled_Sv, epb_i64 C,
+                                    epb_i64 P, epb_i64 R, int min_range_sample, int max_nsamp, int num_side_pings,
+                                    float threshold, void* stream);
+int epb_transient_noise_mask_depth_median(const float* Sv, const float* depth, unsigned char* mask, float* pooled_Sv,
+                                          epb_i64 C, epb_i64 P, epb_i64 R, double depth_min, double depth_max,
+                                          double depth_bin, double exclude_above, int num_side_pings, float threshold,
+                                          void* stream);
 
 /* Transient noise with depth-VALUE windows (use_index_binning=False, clean/utils.py:28-105 pool_Sv, func = nanmean): for
  * every sample whose depth d keeps [d - depth_bin, d + depth_bin] inside [depth_min, depth_max] (the extent of the range

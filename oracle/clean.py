@@ -178,8 +178,8 @@ def mask_impulse_noise_index_binning(Sv, range_var, depth_bin, num_side_pings, i
     return mask, up
 
 
-def index_binning_pool_Sv(Sv, range_var, depth_bin, num_side_pings, exclude_above):
-    """clean/utils.py:109-189 with func = np.nanmean: per channel scipy.ndimage.generic_filter (what
+def index_binning_pool_Sv(Sv, range_var, depth_bin, num_side_pings, exclude_above, func=np.nanmean):
+    """clean/utils.py:109-189 with func = np.nanmean / np.nanmedian (clean/api.py:132-145): per channel scipy.ndimage.generic_filter (what
     dask_image.ndfilters.generic_filter evaluates) of 10^(Sv/10) over [(2 k + 1) pings, (2 n + 1) range samples],
     mode="reflect", on the volume sliced at the first flat index deeper than exclude_above (:141)."""
     from scipy import ndimage
@@ -192,15 +192,16 @@ def index_binning_pool_Sv(Sv, range_var, depth_bin, num_side_pings, exclude_abov
     for c, n in enumerate(samples_per_depth_bin(range_var, depth_bin)):
         with warnings.catch_warnings():
             warnings.simplefilter("ignore", RuntimeWarning)
-            filt = ndimage.generic_filter(log2lin(Sv[c][:, m0:]), function=np.nanmean,
+            filt = ndimage.generic_filter(log2lin(Sv[c][:, m0:]), function=func,
                                           size=[2 * num_side_pings + 1, 2 * n + 1], mode="reflect")
             pooled[c][:, m0:] = lin2log(filt)
     return pooled, m0
 
 
-def mask_transient_noise_index_binning(Sv, range_var, depth_bin, num_side_pings, exclude_above, transient_noise_threshold):
-    """clean/api.py:30-166 with use_index_binning=True, func="nanmean".  Returns (mask, pooled_Sv)."""
-    pooled, _ = index_binning_pool_Sv(Sv, range_var, depth_bin, num_side_pings, exclude_above)
+def mask_transient_noise_index_binning(Sv, range_var, depth_bin, num_side_pings, exclude_above, transient_noise_threshold,
+                                       func=np.nanmean):
+    """clean/api.py:30-166 with use_index_binning=True.  Returns (mask, pooled_Sv)."""
+    pooled, _ = index_binning_pool_Sv(Sv, range_var, depth_bin, num_side_pings, exclude_above, func)
     with np.errstate(invalid="ignore"):
         return (Sv - pooled) > transient_noise_threshold, pooled
 
@@ -241,8 +242,8 @@ def mask_impulse_noise_depth_binning(Sv, range_var, depth_bin, num_side_pings, i
     return mask, up
 
 
-def pool_Sv(Sv, range_var, depth_bin, num_side_pings, exclude_above):
-    """clean/utils.py:28-105 with func = np.nanmean (the use_index_binning=False path of mask_transient_noise): for every
+def pool_Sv(Sv, range_var, depth_bin, num_side_pings, exclude_above, func=np.nanmean):
+    """clean/utils.py:28-105 with func = np.nanmean / np.nanmedian (the use_index_binning=False path of mask_transient_noise): for every
     sample whose depth d keeps d +- depth_bin inside the depth extent of the dataset and below exclude_above and whose
     ping keeps p - k >= 0 and p + k <= n_ping, the nanmean of 10^(Sv/10) over the samples of the same channel with
     d - depth_bin <= depth <= d + depth_bin in the pings p - k .. p + k, in dB; NaN elsewhere."""
@@ -265,12 +266,13 @@ def pool_Sv(Sv, range_var, depth_bin, num_side_pings, exclude_above):
                 with np.errstate(invalid="ignore"):
                     m = (d - depth_bin <= dep) & (dep <= d + depth_bin) & ~np.isnan(win)
                 if m.any():
-                    pooled[c, p, n] = lin2log(win[m].mean())
+                    pooled[c, p, n] = lin2log(func(win[m]))
     return pooled
 
 
-def mask_transient_noise_depth_binning(Sv, range_var, depth_bin, num_side_pings, exclude_above, transient_noise_threshold):
-    """clean/api.py:30-166 with use_index_binning=False, func="nanmean".  Returns (mask, pooled_Sv)."""
-    pooled = pool_Sv(Sv, range_var, depth_bin, num_side_pings, exclude_above)
+def mask_transient_noise_depth_binning(Sv, range_var, depth_bin, num_side_pings, exclude_above, transient_noise_threshold,
+                                       func=np.nanmean):
+    """clean/api.py:30-166 with use_index_binning=False.  Returns (mask, pooled_Sv)."""
+    pooled = pool_Sv(Sv, range_var, depth_bin, num_side_pings, exclude_above, func)
     with np.errstate(invalid="ignore"):
         return (Sv - pooled) > transient_noise_threshold, pooled

@@ -172,8 +172,51 @@ def test_mask_noise_argument_errors(ep):
         ep.clean.mask_transient_noise(ds, func="mean", use_index_binning=True)
     with pytest.raises(ValueError, match="requires `echo_range` data variable"):
         ep.clean.mask_transient_noise(ds, range_var="echo_range", use_index_binning=True)
-    with pytest.raises(NotImplementedError):
-        ep.clean.mask_transient_noise(ds, func="nanmedian")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("index_binning", [True, False])
+def test_mask_transient_noise_nanmedian_vs_oracle(ep, index_binning):
+    """func="nanmedian" (clean/api.py:132-145): the pooled value is np.nanmedian of the window's linear values - a radix
+    select per sample on the device - for index windows (generic_filter, reflected) and for depth-value windows."""
+    import torch
+
+    from echopype_b200 import kernels
+
+    thr = 4.0
+    if index_binning:
+        Sv, depth = _mock(2, 21, 96, seed=5)
+        k, depth_bin, excl = 3, "1m", "4m"
+        Sv32 = Sv.astype(np.float32).astype(np.float64)
+        want, pooled = oclean.mask_transient_noise_index_binning(Sv32, depth, 1.0, k, 4.0, thr, func=np.nanmedian)
+    else:
+        Sv, _ = _mock(2, 14, 70, seed=21)
+        rng = np.random.default_rng(21)
+        off = rng.choice([0.0, 0.07, 0.13], size=(2, 14))
+        depth = (3.0 + off[:, :, None] + 0.19 * np.arange(70)[None, None, :]).astype(np.float32).astype(np.float64)
+        depth[0, 5, 35:] = np.nan
+        k, depth_bin, excl = 2, "2m", "4m"
+        Sv32 = Sv.astype(np.float32).astype(np.float64)
+        want, pooled = oclean.mask_transient_noise_depth_binning(Sv32, depth, 2.0, k, 4.0, thr, func=np.nanmedian)
+    got = ep.clean.mask_transient_noise(_ds(ep, Sv, depth), "nanmedian", depth_bin, k, excl, "4.0dB", "depth", use_index_binning=index_binning)
+    g = got.values.astype(bool)
+    with np.errstate(invalid="ignore"):
+        margin = np.abs((Sv32 - pooled) - thr)
+    sure = np.isnan(margin) | (margin > 1e-3)
+    assert sure.mean() > 0.99 and (~np.isnan(pooled)).any()
+    np.testing.assert_array_equal(g[sure], want[sure])
+    C, P, R = Sv.shape
+    Svt = torch.from_numpy(Sv.astype(np.float32)).cuda()
+    if index_binning:
+        nsamp = oclean.samples_per_depth_bin(depth, 1.0)
+        m0 = int(np.argmin(depth <= 4.0))
+        _, pl = kernels.transient_noise_mask_median(Svt, nsamp, C, P, R, min(m0, R), k, thr, want_pooled=True)
+    else:
+        _, pl = kernels.transient_noise_mask_depth_median(Svt, torch.from_numpy(depth.astype(np.float32)).cuda(), C, P, R, np.nanmin(depth),
+                                                          np.nanmax(depth), 2.0, 4.0, k, thr, want_pooled=True)
+    pl = pl.cpu().numpy()
+    np.testing.assert_array_equal(np.isnan(pl), np.isnan(pooled))
+    assert np.nanmax(np.abs(pl - pooled)) < 1e-4
 
 
 # ---- use_index_binning=False: intervals of depth VALUES (clean/utils.py:192-260) --------------------------------------
