@@ -361,6 +361,7 @@ def time_pipeline(ctx, name, P_local, ping_offset, steps, warmup, seed=None, sus
     e0.record()
     for _ in range(steps):
         mvbs = plan.run()[0]
+    plan.sync_pending()  # N > 1: the side-stream exchange of the last step belongs to the timed region
     e1.record()
     ctx.sync_all()
     clk = clocks.stop()
@@ -379,6 +380,7 @@ def time_pipeline(ctx, name, P_local, ping_offset, steps, warmup, seed=None, sus
         e0.record()
         for _ in range(n):
             plan.run()
+        plan.sync_pending()
         e1.record()
         ctx.sync_all()
         clk2 = clocks.stop()
@@ -465,6 +467,17 @@ def verify_sharded(ctx, name, P_v):
     plan = pipeline.FusedPlan(ed, group=ctx.group, **kw)
     _, acc, rmax, _, _ = plan.run(finalize=False)
     mv, _ = kernels.bin_finalize(acc, to_db=True)
+    # the optional side-stream form of a step (exchange + edge-bin finalisation off the main stream) must give the same grid
+    plan.async_exchange = True
+    mv_async = plan.run()[0]
+    plan.sync_pending()
+    plan.async_exchange = False
+    torch.cuda.synchronize()
+    same = torch.tensor([int(torch.equal(torch.nan_to_num(mv_async, nan=1.0), torch.nan_to_num(mv, nan=1.0))
+                             and torch.equal(torch.isnan(mv_async), torch.isnan(mv)))], dtype=torch.int64, device="cuda")
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    async_equal = bool(int(same.item()))
+    del mv_async
     x = ed["Sonar/Beam_group1"]["backscatter_r"].data
     parts = [torch.empty_like(x) for _ in range(ctx.world)] if ctx.rank == 0 else None
     dist.gather(x, parts, dst=0)
@@ -515,7 +528,8 @@ def verify_sharded(ctx, name, P_v):
         # member counts are integers: bit-equal.  Linear sums: float32 partial sums per CTA (their grouping depends on the
         # tile -> CTA assignment, which differs between the two runs) added into float64 cells: equal to a few float32 ulp.
         # The MVBS itself is a float32 dB value: 1 ulp at -70 dB is 7.6e-6 dB.
-        result = {"ok": bool(ok_counts and max_rel <= 4e-6 and nan_same and max_db <= 1.6e-5 and shared >= ctx.world - 1 and rmax_ok),
+        result = {"ok": bool(ok_counts and max_rel <= 4e-6 and nan_same and max_db <= 1.6e-5 and shared >= ctx.world - 1 and rmax_ok and async_equal),
+                  "async_side_stream_step_equals_synchronous_step": async_equal,
                   "counts_bit_equal": ok_counts, "max_rel_diff_of_linear_sums": max_rel, "nan_masks_equal": nan_same, "max_abs_dB": max_db,
                   "tolerance": "counts bit-equal; sums 4e-6 relative (float32 partials); MVBS 1.6e-5 dB (2 float32 ulp of the dB value)",
                   "ping_bins_shared_by_two_ranks": shared, "range_max_equal": rmax_ok,

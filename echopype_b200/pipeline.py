@@ -21,6 +21,7 @@ its own pings touch; ONE all-reduce(sum) over the first / last local bin of ever
 straddle shard boundaries (:func:`straddle_reduce`).  Two scalar all-reduces (max) fix the global grid.
 """
 
+import ctypes
 from typing import Optional, Sequence
 
 import numpy as np
@@ -294,6 +295,14 @@ class FusedPlan:
         self.range_var_max = range_var_max
         self.fast = bool(fast)  # False: force the general kernel (tests compare the two)
         self.p2p = True  # ping-sharded: pairwise neighbour exchange when the plan allows it (False: always all-reduce)
+        # Optional: pairwise exchange + re-finalisation of the two edge ping bins on a side stream, so that the main stream
+        # never waits for a neighbour.  Measured SLOWER on B200 (N = 2: 2.24 ms per step against 1.70 ms): the fused kernel
+        # is persistent and holds every SM (one 216 KB CTA each), so the NCCL send/recv kernels of step s cannot start
+        # before the fused kernel of step s + 1 retires its CTAs, and the small kernels of both streams interleave.  Off by
+        # default; the result is identical either way (bench.py verification, N > 1).
+        self.async_exchange = False
+        self._comm_stream = None
+        self._pending = None  # event: the side-stream work of the last run() is complete
 
         self.dev = require_cuda()
         self.cal_obj = CALIBRATOR[echodata.sonar_model](
@@ -411,6 +420,10 @@ class FusedPlan:
             self.launches += 3 if self.fast else 1
         else:
             rmax = self._run_streamed(x, rows, outs, noise, acc, edges_t)
+        if (self.group is not None and finalize and self.async_exchange and self.p2p and acc.is_cuda and self._splan["pairwise"]
+                and _dist().get_backend(self.group) == "nccl"):
+            mvbs, rmax = self._exchange_async(acc, rmax)
+            return mvbs, acc, rmax, outs, noise
         if self.group is not None:
             if self.record_events:
                 cev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -438,6 +451,58 @@ class FusedPlan:
             mvbs, _ = kernels.bin_finalize(acc, skipna=self.skipna, fill_value=self.fill_value, to_db=True)
             self.launches += 1
         return mvbs, acc, rmax, outs, noise
+
+    def _exchange_async(self, acc, rmax):
+        """Finalise every bin on the main stream (the edge ping bins provisionally), then, on the side stream: swap the
+        edge slices with the neighbours, add them, finalise the two edge ping bins again.  The main stream does not
+        wait; :meth:`sync_pending` (called by :meth:`wrap`) makes the side-stream results visible."""
+        from . import _lib
+        from .device import ptr, stream
+
+        main = torch.cuda.current_stream()
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=self.dev)
+        comm = self._comm_stream
+        mvbs, _ = kernels.bin_finalize(acc, skipna=self.skipna, fill_value=self.fill_value, to_db=True)
+        self.launches += 1
+        ready = torch.cuda.Event()
+        ready.record(main)
+        for t in (acc, mvbs, rmax):
+            if t is not None:
+                t.record_stream(comm)
+        C, nXl, nR, _ = acc.shape
+        with torch.cuda.stream(comm):
+            comm.wait_event(ready)
+            if self.record_events:
+                cev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                cev[0].record(comm)
+            self.launches += straddle_exchange_p2p(acc, self._splan, self.group)
+            slots = ([0] if self._splan["left"] is not None or (nXl == 1 and self._splan["right"] is not None) else [])
+            if nXl > 1 and self._splan["right"] is not None:
+                slots.append(nXl - 1)
+            for slot in slots:  # the merged edge ping bins: mean -> dB again (one tiny launch per channel)
+                for c in range(C):
+                    _lib.call("epb_bin_finalize", ptr(acc[c, slot]), ptr(mvbs[c, slot]), None, nR, int(bool(self.skipna)),
+                              ctypes.c_float(float(self.fill_value)), 1, stream())
+                    self.launches += 1
+            if rmax is not None:
+                if rmax.numel() > 1:
+                    rmax = rmax.max().reshape(1)
+                    rmax.record_stream(comm)
+                rmax._work = _dist().all_reduce(rmax, op=_dist().ReduceOp.MAX, group=self.group, async_op=True)
+            if self.record_events:
+                cev[1].record(comm)
+                self.comm_events.append(cev)
+            done = torch.cuda.Event()
+            done.record(comm)
+        self._pending = done
+        return mvbs, rmax
+
+    def sync_pending(self):
+        """make the side-stream part of the last :meth:`run` (edge-bin exchange) visible to the current stream"""
+        if self._pending is not None:
+            torch.cuda.current_stream().wait_event(self._pending)
+            self._pending = None
 
     def _run_streamed(self, x, rows, outs, noise, acc, edges_t):
         """Host-resident volume: slabs of (1 channel, chunk pings) move H2D on a copy stream into a 3-slab ring
@@ -514,6 +579,7 @@ class FusedPlan:
         range maximum (one host synchronisation) and cuts the upper-bound range grid back to it."""
         beam = self.beam
         e_ub = self._ub[0]
+        self.sync_pending()
         if rmax is not None:
             self.wait_rmax(rmax)
             v = float(rmax.max().item())
