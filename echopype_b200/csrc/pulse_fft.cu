@@ -61,8 +61,10 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(
 __device__ __forceinline__ float2 cmulc(float2 a, float2 b) {  // a * conj(b)
   return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
 }
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// complex add / subtract as ONE packed FP32 instruction each (Blackwell FADD2 / FFMA2: two lanes per instruction): the
+// butterflies are ~60 % of the transform's instructions
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return fadd2(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return ffma2(b, make_float2(-1.f, -1.f), a); }
 
 template <bool kInv>
 __device__ __forceinline__ void dft4(float2& x0, float2& x1, float2& x2, float2& x3) {
@@ -186,19 +188,6 @@ __device__ __forceinline__ Group make_group(const Plan& pl, int P, int g) {
   gr.rows = min(pl.pack, P - gi * pl.pack);
   return gr;
 }
-__device__ __forceinline__ int items_in_group(const Plan& pl, const Group& gr) { return gr.rows * pl.nfull + (pl.tail_nout > 0 ? 1 : 0); }
-// item k of a group: the full segments of its rows (row-major), then the packed tails
-__device__ __forceinline__ Item make_item(const Plan& pl, const Group& gr, int k) {
-  Item it;
-  if (k < gr.rows * pl.nfull) {
-    const int r = k / pl.nfull;
-    it.row0 = gr.first + r, it.nsub = 1, it.shift = 4, it.n0 = (k - r * pl.nfull) * pl.L, it.nout = pl.L;
-  } else {
-    it.row0 = gr.first, it.nsub = gr.rows, it.shift = pl.pack == 4 ? 2 : (pl.pack == 2 ? 3 : 4), it.n0 = pl.tail_n0, it.nout = pl.tail_nout;
-  }
-  return it;
-}
-
 // y -> Sv / TS, echo_range, optional compressed samples and min / max.  SHIFT: sub-block of point j = j >> SHIFT
 // (4: the whole transform is one segment).
 // cnt4: 4 bits per point = number of beams whose sample is valid (the nanmean divisor); nanre0: bit j = beam-0 real part NaN.
@@ -392,8 +381,11 @@ __device__ __forceinline__ void process_item(const FftParams& pr, const Item& it
   }
 }
 
-// PSHIFT: sub-block shift of the packed tail items (4: tails are not packed)
-template <int B, int PSHIFT>
+// One launch per item kind, so that each kernel carries ONE inlined copy of the transform (with both kinds in one kernel
+// 12 % of the issue slots were lost to instruction fetch): SHIFT == 4 walks the full segments (row, seg < nfull) of all
+// rows, SHIFT in {2, 3} the packed tails of the row groups.  A CTA owns a contiguous range of items, so the next item
+// (prefetched into L2 by TMA while this one is transformed) follows in memory.
+template <int B, int SHIFT>
 __global__ void __launch_bounds__(kT, 2) pulse_fft_kernel(const FftParams pr, const Plan pl) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* s = reinterpret_cast<float2*>(smem_raw);  // [kPadN]
@@ -407,34 +399,39 @@ __global__ void __launch_bounds__(kT, 2) pulse_fft_kernel(const FftParams pr, co
   __syncthreads();
   const int R = pr.R;
   const int P = (int)pr.P;
-  const int ngroups = pl.nchan * pl.groups_per_chan;
-  MinMax mm_v, mm_r;
-
-  for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
-    const Group gr = make_group(pl, P, g);
-    const float2* Hc = pr.H + (size_t)gr.c * kN;
-    const int lead0 = __ldg(pr.lead0 + gr.c);
-    const int nitems = items_in_group(pl, gr);
-    for (int k = 0; k < nitems; ++k) {
-      const Item it = make_item(pl, gr, k);
-      if (B == 4 && t == 0) {  // while this item is loaded and transformed, the next one streams from HBM into L2
-        int ng = g, nk = k + 1;
-        if (nk >= nitems) ng = g + gridDim.x, nk = 0;
-        if (ng < ngroups) {
-          const Item nx = make_item(pl, make_group(pl, P, ng), nk);
-          const int len = min(256 << nx.shift, R - nx.n0);
-          for (int sb = 0; sb < nx.nsub; ++sb) {
-            const long long e = ((nx.row0 + sb) * (long long)R + nx.n0) * 4;
-            prefetch_l2_bulk(pr.re + e, (unsigned)len * 16u);
-            prefetch_l2_bulk(pr.im + e, (unsigned)len * 16u);
-          }
-        }
-      }
-      if (PSHIFT == 4 || it.shift == 4)
-        process_item<B, 4>(pr, it, s, s_tw1, s_tw2, s_wmax, s_zf, Hc, lead0, t, mm_v, mm_r);
-      else
-        process_item<B, PSHIFT>(pr, it, s, s_tw1, s_tw2, s_wmax, s_zf, Hc, lead0, t, mm_v, mm_r);
+  // items of this launch and this CTA's contiguous share of them
+  const long long nitems = (SHIFT == 4) ? pr.nrows * (long long)pl.nfull : (long long)pl.nchan * pl.groups_per_chan;
+  const long long i0 = nitems * (long long)blockIdx.x / gridDim.x, i1 = nitems * (long long)(blockIdx.x + 1) / gridDim.x;
+  auto item_of = [&](long long i, int* chan) {
+    Item it;
+    if (SHIFT == 4) {
+      const long long row = i / pl.nfull;
+      it.row0 = row, it.nsub = 1, it.shift = 4, it.n0 = (int)(i - row * pl.nfull) * pl.L, it.nout = pl.L;
+      *chan = (int)(row / P);
+    } else {
+      const Group gr = make_group(pl, P, (int)i);
+      it.row0 = gr.first, it.nsub = gr.rows, it.shift = SHIFT, it.n0 = pl.tail_n0, it.nout = pl.tail_nout;
+      *chan = gr.c;
     }
+    return it;
+  };
+  MinMax mm_v, mm_r;
+  for (long long i = i0; i < i1; ++i) {
+    int c;
+    const Item it = item_of(i, &c);
+    const float2* Hc = pr.H + (size_t)c * kN;
+    const int lead0 = __ldg(pr.lead0 + c);
+    if (B == 4 && t == 0 && i + 1 < i1) {  // while this item is loaded and transformed, the next one streams from HBM into L2
+      int cn;
+      const Item nx = item_of(i + 1, &cn);
+      const int len = min(256 << nx.shift, R - nx.n0);
+      for (int sb = 0; sb < nx.nsub; ++sb) {
+        const long long e = ((nx.row0 + sb) * (long long)R + nx.n0) * 4;
+        prefetch_l2_bulk(pr.re + e, (unsigned)len * 16u);
+        prefetch_l2_bulk(pr.im + e, (unsigned)len * 16u);
+      }
+    }
+    process_item<B, SHIFT>(pr, it, s, s_tw1, s_tw2, s_wmax, s_zf, Hc, lead0, t, mm_v, mm_r);
   }
   if (pr.minmax) {
     mm_v.flush(pr.minmax + 0, pr.minmax + 1);
@@ -554,25 +551,25 @@ extern "C" int epb_pulse_compress_sv_fft(const float* re, const float* im, const
   pl.nchan = (int)C;
   const long long ngroups = C * (long long)pl.groups_per_chan;
   const long long cap = (long long)epb_num_sms() * 2;
-  const int grid = (int)(ngroups < cap ? ngroups : cap);
-#define EPB_FFT(BB, PS)                                                                                                      \
+#define EPB_FFT(BB, SH, NITEMS)                                                                                              \
   do {                                                                                                                       \
-    auto kern = pulse_fft_kernel<BB, PS>;                                                                                    \
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)             \
-      return epb_check_launch("epb_pulse_compress_sv_fft(smem)");                                                            \
-    kern<<<grid, kT, kSmemBytes, st>>>(pr, pl);                                                                              \
+    const long long n_ = (NITEMS);                                                                                           \
+    if (n_ > 0) {                                                                                                            \
+      auto kern = pulse_fft_kernel<BB, SH>;                                                                                  \
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)           \
+        return epb_check_launch("epb_pulse_compress_sv_fft(smem)");                                                          \
+      kern<<<(unsigned)(n_ < cap ? n_ : cap), kT, kSmemBytes, st>>>(pr, pl);                                                 \
+    }                                                                                                                        \
   } while (0)
+  const long long nseg_items = pr.nrows * (long long)pl.nfull;
   switch (B) {
-    case 1: EPB_FFT(1, 4); break;
-    case 2: EPB_FFT(2, 4); break;
-    case 3: EPB_FFT(3, 4); break;
+    case 1: EPB_FFT(1, 4, nseg_items); break;
+    case 2: EPB_FFT(2, 4, nseg_items); break;
+    case 3: EPB_FFT(3, 4, nseg_items); break;
     default:
-      if (pl.pack == 4)
-        EPB_FFT(4, 2);
-      else if (pl.pack == 2)
-        EPB_FFT(4, 3);
-      else
-        EPB_FFT(4, 4);
+      EPB_FFT(4, 4, nseg_items);                     // the full segments of every row
+      if (pl.pack == 4) EPB_FFT(4, 2, ngroups);      // then the short last segments, four pings per transform
+      if (pl.pack == 2) EPB_FFT(4, 3, ngroups);      // ... or two
       break;
   }
 #undef EPB_FFT
