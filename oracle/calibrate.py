@@ -8,9 +8,9 @@ float64 numpy restatement of
   echopype/calibrate/cal_params.py:261-324    (pulse-length table lookup)
   echopype/calibrate/env_params.py:24-71      (time1 -> ping_time harmonisation)
 All arrays are plain numpy with the reference dimension order (channel, ping_time, range_sample
-[, beam]).  PARITY UNPINNED offline for the numeric Sv/TS values (no raw files / external goldens
-in this environment); the sub-steps with offline known-answer tests are pinned in
-tests/test_oracle_golden.py.
+[, beam]).  PINNED: tests/test_reference_pinned.py checks every function here against outputs of the
+reference's own calibration classes executed from /root/reference (tests/golden/make_golden_calibrate.py,
+tests/golden/calibrate_vectors.npz) to 1e-9 dB.
 """
 
 import numpy as np
