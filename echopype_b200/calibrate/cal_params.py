@@ -96,14 +96,17 @@ def _get_interp_da(da_param, freq_center: DataArray, alternative, BB_factor=1) -
             cf = np.asarray(da_param.coords["cal_frequency"], dtype=np.float64)
             cf = cf[k] if cf.ndim == 2 else cf
             ok = ~np.isnan(tbl)
-            v = np.interp(fc, cf[ok], tbl[ok], left=np.nan, right=np.nan)  # xarray interp: NaN outside
+            if fc.size > 1 and np.all(fc == fc[0]):  # one transmit setting for the whole file: interpolate once
+                v = np.full(fc.size, np.interp(fc[:1], cf[ok], tbl[ok], left=np.nan, right=np.nan)[0])
+            else:
+                v = np.interp(fc, cf[ok], tbl[ok], left=np.nan, right=np.nan)  # xarray interp: NaN outside
             rows.append(v if has_ping else v.reshape(()))
         else:
             bb = BB_factor.values[ci] if isinstance(BB_factor, DataArray) else BB_factor
             if isinstance(alternative, DataArray):
                 alt = np.asarray(alternative.sel(channel=ch_id).values * bb, dtype=np.float64).squeeze()
             elif isinstance(alternative, (int, float)):
-                alt = np.asarray([alternative] * fc.size, dtype=np.float64).squeeze() * bb
+                alt = np.full(fc.size, alternative, dtype=np.float64).squeeze() * bb
             else:
                 raise ValueError("'alternative' has to be of the type int, float, or xr.DataArray")
             alt = np.asarray(alt, dtype=np.float64)

@@ -70,6 +70,8 @@ def _cp(da, channel, ping_time=None):
         want = np.asarray(channel)
         if have.shape == want.shape and not np.array_equal(have, want) and set(have.tolist()) == set(want.tolist()):
             v = v[[int(np.flatnonzero(have == c)[0]) for c in want]]
+    if dims == ("channel", "ping_time") and v.shape[1] > 1 and bool(np.all(v == v[:, :1])):
+        v = np.ascontiguousarray(v[:, :1])  # constant along ping_time: (C,1) broadcasts the same way and ships C values
     return v
 
 
@@ -152,6 +154,15 @@ class CalibrateEK(CalibrateBase):
             return kernels.SONAR_EX80
         raise ValueError("The specified sonar_model is not supported!")
 
+    def _transmit_signal(self, tx_coeff, fs):
+        """One replica build per calibration object: tau_effective and the matched filter use the same signal."""
+        memo = getattr(self, "_tx_memo", None)
+        if memo is None:
+            memo = get_transmit_signal(self.beam, tx_coeff, self.waveform_mode, fs, getattr(self, "drop_last_hanning_zero", False))
+            self._tx_memo = memo
+            self._tx = memo[0]
+        return memo
+
     def _tau_effective(self, what):
         """calibrate_ek.py:112-151 / :586-607: transmit-signal tau_eff with GPT channels (all of EK60)
         overwritten by transmit_duration_nominal of ping 0."""
@@ -169,7 +180,7 @@ class CalibrateEK(CalibrateBase):
         try:
             tx_coeff = get_filter_coeff(vend)
             fs = self.cal_params["receiver_sampling_frequency"]
-            tx, tx_time = get_transmit_signal(beam, tx_coeff, self.waveform_mode, fs, getattr(self, "drop_last_hanning_zero", False))
+            tx, tx_time = self._transmit_signal(tx_coeff, fs)
             tau_eff = get_tau_effective(
                 tx, {k: 1 / np.diff(v[:2]) for k, v in tx_time.items()}, self.waveform_mode, chan, beam["ping_time"]
             ).values.astype(np.float64)
@@ -320,8 +331,7 @@ class CalibrateEK80(CalibrateEK):
         bb = self.waveform_mode == "BB"
         tx_coeff = get_filter_coeff(self.vend)
         fs = self.cal_params["receiver_sampling_frequency"]
-        tx, tx_time = get_transmit_signal(beam, tx_coeff, self.waveform_mode, fs, self.drop_last_hanning_zero)
-        self._tx = tx
+        tx, tx_time = self._transmit_signal(tx_coeff, fs)
         gain = _cp(self.cal_params["gain_correction"], chan)
         if bb:  # transceiver gain compensation, calibrate_ek.py:561-562
             g, Bm = np.asarray(gain, dtype=np.float64), np.asarray(self._get_B_theta_phi_m(), dtype=np.float64)

@@ -89,21 +89,34 @@ def get_tau_effective(ytx_dict, fs_deci_dict, waveform_mode, channel, ping_time=
     return DataArray(np.asarray(vals), dims=["channel"], coords={"channel": np.asarray(getattr(channel, "values", channel))})
 
 
+def _unique_non_nan(row):
+    """np.unique(row) without NaN; rows that hold one value (the normal case) skip the sort."""
+    if row.size and row[0] == row[0] and bool(np.all(row == row[0])):
+        return row[:1].copy()
+    v = np.unique(row)
+    return v[~np.isnan(v)]
+
+
 def get_transmit_signal(beam: Dataset, coeff: Dict, waveform_mode: str, fs, drop_last_hanning_zero: bool = False):
-    if waveform_mode == "BB" and np.all(np.asarray(beam["transmit_type"].values) == "CW"):
-        raise TypeError("File does not contain BB mode complex samples!")
+    if waveform_mode == "BB":
+        ttype = np.asarray(beam["transmit_type"].values)
+        if ttype.size and ttype.flat[0] == "CW" and np.all(ttype == "CW"):
+            raise TypeError("File does not contain BB mode complex samples!")
     y_all, y_time_all = {}, {}
     names = ["transmit_duration_nominal", "slope", "transmit_frequency_start", "transmit_frequency_stop"]
     chans = np.asarray(beam["channel"].values)
+    tables = {}
+    for p in names:
+        if waveform_mode == "CW" and p in ("transmit_frequency_start", "transmit_frequency_stop"):
+            tables[p] = np.asarray(beam["frequency_nominal"].values, dtype=np.float64).reshape(len(chans), -1)
+        else:
+            tables[p] = np.asarray(beam[p].transpose("channel", "ping_time").values, dtype=np.float64)
     for ci, ch in enumerate(chans):
         fs_chan = _scalar(fs.sel(channel=ch).values) if isinstance(fs, DataArray) else fs
         tx = {}
         for p in names:
-            if waveform_mode == "CW" and p in ("transmit_frequency_start", "transmit_frequency_stop"):
-                tx[p] = np.unique(np.asarray(beam["frequency_nominal"].values)[ci])
-            else:
-                v = np.unique(np.asarray(beam[p].transpose("channel", "ping_time").values, dtype=np.float64)[ci])
-                tx[p] = v[~np.isnan(v)]
+            cw_freq = waveform_mode == "CW" and p in ("transmit_frequency_start", "transmit_frequency_stop")
+            tx[p] = np.unique(tables[p][ci]) if cw_freq else _unique_non_nan(tables[p][ci])
             if tx[p].size != 1:
                 raise TypeError("File contains changing %s!" % p)
         y_ch, _ = tapered_chirp(fs=fs_chan, drop_last_hanning_zero=drop_last_hanning_zero, **tx)

@@ -141,6 +141,19 @@ def _calc_absorption(frequency, T, S, P, pH=None, c=None, formula="FG"):
         kw["pH"] = ph
     if cc is not None:
         kw["sound_speed"] = cc
+    # The formulae are elementwise: inputs that do not vary along ping_time (the usual case -- one transmit setting
+    # and one environment record per file) are evaluated on a single ping and the result repeated, instead of on
+    # the full (channel, ping_time) grid.
+    nP = 0
+    ins = [x for x in (f, t, s, p, ph, cc) if x is not None and "ping_time" in x.dims]
+    if ins and all(x.sizes["ping_time"] == ins[0].sizes["ping_time"] for x in ins) and ins[0].sizes["ping_time"] > 1:
+        def const(x):
+            v = np.moveaxis(x.values, x.dims.index("ping_time"), -1)
+            return bool(np.all(v == v[..., :1]))
+        if all(const(x) for x in ins):
+            nP, pt = ins[0].sizes["ping_time"], ins[0].coords.get("ping_time")
+            f, t, s, p, ph, cc = (x.isel(ping_time=slice(0, 1)) if x is not None and "ping_time" in x.dims else x
+                                  for x in (f, t, s, p, ph, cc))
     # DataArray arithmetic broadcasts by dim name; np.sqrt / np.exp / np.all inside need plain arrays
     ref = f
     for other in (t, s, p, ph, cc):
@@ -156,6 +169,12 @@ def _calc_absorption(frequency, T, S, P, pH=None, c=None, formula="FG"):
         **({"pH": b(ph)} if ph is not None else {}), **({"sound_speed": b(cc)} if cc is not None else {}),
         formula_source=formula,
     )
+    if nP:
+        ax = dims.index("ping_time")
+        out = np.repeat(out, nP, axis=ax)
+        coords = dict(coords)
+        if pt is not None:
+            coords["ping_time"] = pt
     return DataArray(out, dims, coords)
 
 
