@@ -660,22 +660,28 @@ def extra_kernels(ctx, ed, steps):
     # ping_num = 10 > 8 takes the two-sweep form of the fused kernel (sub-tiles of 5 rows, second read from L2)
     from echopype_b200 import pipeline
 
-    plan = pipeline.FusedPlan(ed, ping_num=10, range_sample_num=20, SNR_threshold=SNR, range_bin=RANGE_BIN, ping_time_bin=PING_BIN)
-    plan.record_events = True
-    for _ in range(3):
-        plan.run()
-    torch.cuda.synchronize()
-    plan.kernel_events.clear()
-    for _ in range(max(5, steps)):
-        plan.run()
-    torch.cuda.synchronize()
-    ms = sorted(a.elapsed_time(b) for a, b in plan.kernel_events)
-    avg = sum(ms) / len(ms)
-    res["fused pipeline, remove_background_noise(ping_num=10, range_sample_num=20) (4 B/sample)"] = {
-        "ms": avg, "ms_min": ms[0], "GBps": 4 * n / avg / 1e6, "frac_of_measured_hbm": 4 * n / avg / 1e6 / peak, "Gsamples_s": n / avg / 1e6,
-        "launches_timed": len(ms)}
-    del plan
-    ctx.free()
+    def fused(label, nbytes, **kw):
+        plan = pipeline.FusedPlan(ed, SNR_threshold=SNR, range_bin=RANGE_BIN, ping_time_bin=PING_BIN, **kw)
+        plan.record_events = True
+        for _ in range(3):
+            plan.run()
+        torch.cuda.synchronize()
+        plan.kernel_events.clear()
+        for _ in range(max(5, steps)):
+            plan.run()
+        torch.cuda.synchronize()
+        ms = sorted(a.elapsed_time(b) for a, b in plan.kernel_events)
+        avg = sum(ms) / len(ms)
+        res[label] = {"ms": avg, "ms_min": ms[0], "GBps": nbytes * n / avg / 1e6, "frac_of_measured_hbm": nbytes * n / avg / 1e6 / peak,
+                      "Gsamples_s": n / avg / 1e6, "launches_timed": len(ms)}
+        del plan
+        ctx.free()
+
+    fused("fused pipeline, remove_background_noise(ping_num=10, range_sample_num=20) (4 B/sample)", 4, ping_num=10, range_sample_num=20)
+    # full-size outputs streamed out of the same kernel (keep=): 4 B in + 4 B out per kept array
+    fused("fused pipeline, keep=('Sv_corrected',) (8 B/sample)", 8, ping_num=PING_NUM, range_sample_num=RS_NUM, keep=("Sv_corrected",))
+    fused("fused pipeline, keep=('Sv','echo_range','Sv_noise','Sv_corrected') (20 B/sample)", 20, ping_num=PING_NUM,
+          range_sample_num=RS_NUM, keep=("Sv", "echo_range", "Sv_noise", "Sv_corrected"))
     return res
 
 

@@ -613,7 +613,8 @@ extern "C" int epb_bin_reduce(const float* Sv, const void* range_var, int range_
 int epb_pipeline_fast_try(const void* x, int x_i16, const epb_row* rows, const int* xbin, const double* r_edges, int nR,
                           int closed_right, double* acc, float* noise_out, long long C, long long P, long long R,
                           long long nX, int ping_num, int range_sample_num, float noise_max_lin, float snr_lin,
-                          double* range_max_out, int sv_input, void* workspace, long long workspace_bytes, cudaStream_t s);
+                          double* range_max_out, int sv_input, void* workspace, long long workspace_bytes, cudaStream_t s,
+                          float* o_sv = nullptr, float* o_rng = nullptr, float* o_svn = nullptr, float* o_svc = nullptr);
 
 extern "C" int epb_bin_reduce_law(const float* Sv, const epb_row* rows, const double* depth_off,
                                   const double* depth_scale, const int* xbin, const double* r_edges, int nR,

@@ -400,7 +400,8 @@ extern "C" epb_i64 epb_pipeline_smem_bytes(epb_i64 R, int nR, int tile, int do_n
 int epb_pipeline_fast_try(const void* x, int x_i16, const epb_row* rows, const int* xbin, const double* r_edges, int nR,
                           int closed_right, double* acc, float* noise_out, long long C, long long P, long long R,
                           long long nX, int ping_num, int range_sample_num, float noise_max_lin, float snr_lin,
-                          double* range_max_out, int sv_input, void* workspace, long long workspace_bytes, cudaStream_t s);
+                          double* range_max_out, int sv_input, void* workspace, long long workspace_bytes, cudaStream_t s,
+                          float* o_sv = nullptr, float* o_rng = nullptr, float* o_svn = nullptr, float* o_svc = nullptr);
 void epb_range_max_init_launch(double* out_max, cudaStream_t s);
 void epb_range_max_gated_launch(const float* x, const epb_row* rows, long long nrows, int R, double* out_max, const int* gate,
                                 cudaStream_t s);
@@ -443,11 +444,11 @@ static int pipeline_power_mvbs_impl(const short* counts, float* backscatter_r, c
   if (range_max_out) epb_range_max_init_launch(range_max_out, (cudaStream_t)stream);
   // fast path (pipeline_fast.cu): regular volumes without full-size outputs.  A device-side flag written by its
   // classification kernel decides which of the two kernels does the work; the other returns immediately.
-  if (workspace && workspace_bytes >= 256 && !Sv && !echo_range && !Sv_noise && !Sv_corrected &&
-      ((uintptr_t)workspace % 16) == 0 &&
+  if (workspace && workspace_bytes >= 256 && ((uintptr_t)workspace % 16) == 0 &&
       epb_pipeline_fast_try(counts ? (const void*)counts : (const void*)backscatter_r, counts != nullptr, rows, xbin, r_edges, nR, closed_right, acc, noise_out, C, P, R, nX, ping_num,
                             range_sample_num, pr.noise_max_lin, (float)pow(10.0, (double)snr_threshold / 10.0),
-                            range_max_out, 0, workspace, workspace_bytes, (cudaStream_t)stream))
+                            range_max_out, 0, workspace, workspace_bytes, (cudaStream_t)stream, Sv, echo_range, Sv_noise,
+                            Sv_corrected))
     pr.gate = (const int*)workspace;
   if (counts) epb_ingest_gated_launch(counts, backscatter_r, C * P * R, pr.gate, (cudaStream_t)stream);
   // stage the tile in shared memory when two CTAs per SM still fit, else when one fits, else stream from global

@@ -8,6 +8,9 @@ int epb_fast_launch_i16a(const void* pr, int T, int G, int noise, int threads, s
 int epb_fast_launch_i16b(const void* pr, int T, int G, int noise, int threads, size_t smem, cudaStream_t s);
 int epb_fast_launch_f32c(const void* pr, int T, int G, int noise, int threads, size_t smem, cudaStream_t s);
 int epb_fast_launch_i16c(const void* pr, int T, int G, int noise, int threads, size_t smem, cudaStream_t s);
+int epb_fast_launch_f32ka(const void* pr, int T, int G, int noise, int threads, size_t smem, cudaStream_t s);
+int epb_fast_launch_f32kb(const void* pr, int T, int G, int noise, int threads, size_t smem, cudaStream_t s);
+int epb_fast_launch_f32kc(const void* pr, int T, int G, int noise, int threads, size_t smem, cudaStream_t s);
 
 namespace {
 constexpr int kMaxPingNum = 64;  // two-sweep mode: up to 8 sub-tiles of 8 rows
@@ -24,8 +27,11 @@ inline void sweep_shape(int ping_num, int* S, int* T) {
 int epb_pipeline_fast_try(const void* x, int x_i16, const epb_row* rows, const int* xbin, const double* r_edges, int nR,
                           int closed_right, double* acc, float* noise_out, long long C, long long P, long long R,
                           long long nX, int ping_num, int range_sample_num, float noise_max_lin, float snr_lin,
-                          double* range_max_out, int sv_input, void* workspace, long long workspace_bytes, cudaStream_t s) {
+                          double* range_max_out, int sv_input, void* workspace, long long workspace_bytes, cudaStream_t s,
+                          float* o_sv, float* o_rng, float* o_svn, float* o_svc) {
   const bool noise = ping_num > 0;
+  const bool keep = o_sv || o_rng || o_svn || o_svc;  // full-size outputs: the kKeep instantiations (float32 input only)
+  if (keep && (x_i16 || sv_input)) return 0;
   const bool sweep = noise && ping_num > kMaxT;  // the noise tile streams through the ring twice in sub-tiles
   int S = 1, T = noise ? ping_num : 4;
   if (sweep) sweep_shape(ping_num, &S, &T);
@@ -44,15 +50,16 @@ int epb_pipeline_fast_try(const void* x, int x_i16, const epb_row* rows, const i
   const size_t smem_cap = two_ctas ? (size_t)(227 * 1024) / 2 - 3072 : kSmemMax;
   int nslots = 0;
   for (int n = 4; n >= 1; --n)
-    if (fast_smem(R, T, nR, n, nRt, xb) <= smem_cap || (n == 1 && fast_smem(R, T, nR, n, nRt, xb) <= kSmemMax)) {
+    if (fast_smem(R, T, nR, n, nRt, xb, keep) <= smem_cap || (n == 1 && fast_smem(R, T, nR, n, nRt, xb, keep) <= kSmemMax)) {
       nslots = n;
       break;
     }
   if (nslots == 0) return 0;
-  const size_t smem = fast_smem(R, T, nR, nslots, nRt, xb);
+  const size_t smem = fast_smem(R, T, nR, nslots, nRt, xb, keep);
   FastParams pr;
   pr.x = x, pr.rows = rows, pr.xbin = xbin, pr.edges = r_edges, pr.acc = acc, pr.noise_out = noise_out;
   pr.rmax = range_max_out;
+  pr.o_sv = o_sv, pr.o_rng = o_rng, pr.o_svn = o_svn, pr.o_svc = o_svc;
   int* irregular = (int*)workspace;
   pr.irregular = irregular;
   pr.tiles = reinterpret_cast<const TileInfo*>((char*)workspace + 256);
@@ -78,7 +85,16 @@ int epb_pipeline_fast_try(const void* x, int x_i16, const epb_row* rows, const i
   prepare_kernel<<<(unsigned)((ndesc + 127) / 128), 128, 0, s>>>(rows, xbin, P, nX, T, pr.PN, S, pr.nPt, ndesc, sv_input,
                                                                  const_cast<TileInfo*>(pr.tiles), irregular);
   int rc = -2;
-  if (sweep) {
+  if (keep) {
+    if (sweep) {
+      rc = epb_fast_launch_f32kc(&pr, T, G, 1, threads, smem, s);
+    } else {
+      for (auto launcher : {epb_fast_launch_f32ka, epb_fast_launch_f32kb}) {
+        rc = launcher(&pr, T, G, noise ? 1 : 0, threads, smem, s);
+        if (rc != -2) break;
+      }
+    }
+  } else if (sweep) {
     rc = (x_i16 ? epb_fast_launch_i16c : epb_fast_launch_f32c)(&pr, T, G, 1, threads, smem, s);
   } else {
     for (auto launcher : {x_i16 ? epb_fast_launch_i16a : epb_fast_launch_f32a, x_i16 ? epb_fast_launch_i16b : epb_fast_launch_f32b}) {

@@ -1,0 +1,5 @@
+// Instantiations of the persistent fused kernel (pipeline_fast_impl.cuh) with full-size outputs (keep=): float32 samples,
+// ping_num > 8 (two sweeps over sub-tiles of 5..8 rows).
+#include "pipeline_fast_impl.cuh"
+
+EPB_DEFINE_FAST_KEEP_LAUNCHER(epb_fast_launch_f32kc, true, 5, 6, 7, 8, false)

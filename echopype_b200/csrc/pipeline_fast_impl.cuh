@@ -21,7 +21,8 @@
 //     float64 atomic triple per (CTA, range bin).
 // Handles the regular case: every tile's rows share one range law and have finite calibration constants (checked
 // on the device by prepare_kernel; otherwise the general kernel of pipeline.cu runs instead), R % 4 == 0 (8 for int16
-// input), R <= 4096, range_sample_num >= 4, no full-size outputs.
+// input), R <= 4096, range_sample_num >= 4.  Full-size outputs (keep=: Sv, echo_range, Sv_noise, Sv_corrected) come from
+// the kKeep instantiations, which stream them out of the register tile between the noise estimate and the binning.
 //
 // ping_num > 8 (kSweep; the reference's own test setting is remove_background_noise(ping_num=10, range_sample_num=20),
 // tests/utils/test_processinglevels_integration.py:111): u of a whole noise tile no longer fits the registers and the tile
@@ -50,6 +51,7 @@ struct FastParams {
   double* acc;
   float* noise_out;
   double* rmax;  // NULL or exact nanmax(echo_range) (atomic max; initialised by the caller)
+  float *o_sv, *o_rng, *o_svn, *o_svc;  // kKeep: optional full-size outputs Sv / echo_range / Sv_noise / Sv_corrected [C,P,R]
   const int* irregular;  // workspace flag from prepare_kernel: != 0 -> this kernel does nothing
   const TileInfo* tiles;  // [ntiles] descriptors from prepare_kernel (workspace)
   long long C, P, nX, ntiles;
@@ -225,10 +227,11 @@ __device__ __forceinline__ float4 counts_to_db(uint2 w) {
   return make_float4(f01.x, f01.y, f23.x, f23.y);
 }
 
-template <int T, int G, bool kNoise, bool kI16, bool kSweep = false>
+template <int T, int G, bool kNoise, bool kI16, bool kSweep = false, bool kKeep = false>
 __global__ void __launch_bounds__(G == 1 ? EPB_G1_THREADS : 512 / (EPB_GBIG / 2), (G == 1 && EPB_G1_THREADS == 512) ? EPB_G1_BLOCKS : 1)
     pipeline_fast_kernel(const FastParams pr) {
   static_assert(!kSweep || kNoise, "two sweeps only make sense with the noise estimate");
+  static_assert(!kKeep || !kI16, "full-size outputs are produced from the float32 image");
   if (*pr.irregular) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long s_full[kMaxTilesInFlight];  // one mbarrier per tile slot
@@ -265,6 +268,9 @@ __global__ void __launch_bounds__(G == 1 ? EPB_G1_THREADS : 512 / (EPB_GBIG / 2)
   int* const s_bounds = reinterpret_cast<int*>(s_edges + (nR + 1));
   int* const s_valid = s_bounds + (nR + 1);  // columns of each range tile with a defined Sv (n >= n_start, R' >= 0)
   int* const s_def = s_valid + nRt;          // [2][nRt] samples missing (NaN) from each range tile, by tile parity
+  // kKeep: log2(TL) (also where Sv is undefined) and echo_range of every column under the current law
+  float* const s_ltl = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_def + 2 * nRt) + 15) & ~(uintptr_t)15);
+  float* const s_rr = s_ltl + R;
 
   // ---- tile range of this CTA -----------------------------------------------------------------------------------
   const long long g0 = pr.ntiles * (long long)blockIdx.x / gridDim.x;
@@ -521,6 +527,17 @@ __global__ void __launch_bounds__(G == 1 ? EPB_G1_THREADS : 512 / (EPB_GBIG / 2)
         }
         *reinterpret_cast<float4*>(s_lg + n) = make_float4(lg[0], lg[1], lg[2], lg[3]);
         *reinterpret_cast<float4*>(s_tl + n) = make_float4(tl[0], tl[1], tl[2], tl[3]);
+        if (kKeep) {
+          float lt[4], rr[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            rr[k] = range_of(rf, (float)(n + k));
+            const float rm = (rr[k] >= 1.f) ? rr[k] : 1.f;
+            lt[k] = fmaf(2.f, log2f(rm), rf.c2 * rr[k]);
+          }
+          *reinterpret_cast<float4*>(s_ltl + n) = make_float4(lt[0], lt[1], lt[2], lt[3]);
+          *reinterpret_cast<float4*>(s_rr + n) = make_float4(rr[0], rr[1], rr[2], rr[3]);
+        }
       }
       __syncthreads();
       for (int n = 4 * tid; n < R; n += 4 * nth) {
@@ -848,6 +865,49 @@ __global__ void __launch_bounds__(G == 1 ? EPB_G1_THREADS : 512 / (EPB_GBIG / 2)
     // survivors: u > thr (one tile-wide threshold);  sum(TL u - TL noise) = TL (sum(u) - n noise)
     const float thr = kNoise ? noise_lin * pr.snr1 : -1.f;    // Sv_c - Sv_noise > SNR  <=>  u > noise (1 + 10^(SNR/10))
     const float nz = (noise_lin == noise_lin) ? noise_lin : 0.f;  // NaN noise: nothing survives, keep the sums clean
+    if (kKeep) {
+      // Full-size outputs straight from the register tile (u domain): Sv = dB(u TL), Sv_noise = dB(noise TL),
+      // Sv_corrected = dB((u - noise) TL) where it survives; a NaN sample (u = -2 sentinel) gives NaN, and with it a
+      // NaN echo_range / Sv_noise when the law ties the range to the sample (range.py:143-148).  Streaming stores.
+      const float lnz = fast_log2(noise_lin);
+      const long long row0 = ti->row0;
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+        if (liveg[g]) {
+          const float4 t4 = *reinterpret_cast<const float4*>(s_tl + colg[g]);
+          const float4 l4 = *reinterpret_cast<const float4*>(s_ltl + colg[g]);
+          const float4 r4 = *reinterpret_cast<const float4*>(s_rr + colg[g]);
+          const float tl[4] = {t4.x, t4.y, t4.z, t4.w}, ltl[4] = {l4.x, l4.y, l4.z, l4.w}, rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+          for (int t = 0; t < T; ++t)
+            if (t < Ta) {
+              const size_t o = (size_t)(row0 + t) * R + colg[g];
+              float osv[4], orr[4], osn[4], osc[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float u = e[g][t][k];
+                const bool member = !(nanrange && u < 0.f);
+                orr[k] = member ? rr[k] : CUDART_NAN_F;
+                if (kNoise) osn[k] = member ? kLog2ToDb * (lnz + ltl[k]) : CUDART_NAN_F;
+              }
+              if (pr.o_sv) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) osv[k] = (tl[k] != 0.f) ? kLog2ToDb * (fast_log2(e[g][t][k]) + ltl[k]) : CUDART_NAN_F;
+                st_stream4(reinterpret_cast<float4*>(pr.o_sv + o), make_float4(osv[0], osv[1], osv[2], osv[3]));
+              }
+              if (pr.o_rng) st_stream4(reinterpret_cast<float4*>(pr.o_rng + o), make_float4(orr[0], orr[1], orr[2], orr[3]));
+              if (kNoise && pr.o_svn) st_stream4(reinterpret_cast<float4*>(pr.o_svn + o), make_float4(osn[0], osn[1], osn[2], osn[3]));
+              if (kNoise && pr.o_svc) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float u = e[g][t][k];
+                  osc[k] = (u > thr) ? kLog2ToDb * (fast_log2(u - noise_lin) + ltl[k]) : CUDART_NAN_F;
+                }
+                st_stream4(reinterpret_cast<float4*>(pr.o_svc + o), make_float4(osc[0], osc[1], osc[2], osc[3]));
+              }
+            }
+        }
+    }
     const int nruns = ti->nruns;
     // The usual tile: all T rows fall into ONE ping bin (one run, no row predicates, no run loop).  Straight-line code:
     // per column pair and row FSET x2 + FFMA2 + FADD2.
@@ -942,16 +1002,16 @@ __global__ void __launch_bounds__(G == 1 ? EPB_G1_THREADS : 512 / (EPB_GBIG / 2)
   }
 }
 
-size_t fast_smem(long long R, int T, int nR, int ntiles_ring, int nRt, int xbytes) {
+size_t fast_smem(long long R, int T, int nR, int ntiles_ring, int nRt, int xbytes, bool keep = false) {
   return (((size_t)R * 12 + (size_t)R / 4 + 15) & ~(size_t)15) + (((size_t)ntiles_ring * T * R * xbytes + 15) & ~(size_t)15) +
-         (size_t)(nR + 1) * 12 + (size_t)nRt * 12 + 16;
+         (size_t)(nR + 1) * 12 + (size_t)nRt * 12 + 16 + (keep ? (size_t)R * 8 + 16 : 0);
 }
 
 constexpr size_t kSmemMax = 227 * 1024 - 2048;  // static shared memory of the kernel comes on top
 
-template <int T, int G, bool kNoise, bool kI16, bool kSweep = false>
+template <int T, int G, bool kNoise, bool kI16, bool kSweep = false, bool kKeep = false>
 int launch_fast(const FastParams& pr, int threads, size_t smem, cudaStream_t s) {
-  auto kern = pipeline_fast_kernel<T, G, kNoise, kI16, kSweep>;
+  auto kern = pipeline_fast_kernel<T, G, kNoise, kI16, kSweep, kKeep>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) return -1;
@@ -994,6 +1054,22 @@ int launch_fast(const FastParams& pr, int threads, size_t smem, cudaStream_t s) 
       case TB: return EPB_FAST_SWEEP_CASE(TB, I16);                                                                   \
       case TC: return EPB_FAST_SWEEP_CASE(TC, I16);                                                                   \
       case TD: return EPB_FAST_SWEEP_CASE(TD, I16);                                                                   \
+    }                                                                                                                 \
+    return -2;                                                                                                        \
+  }
+
+// kKeep instantiations (float32 input, full-size outputs streamed out of the register tile)
+#define EPB_FAST_KEEP_CASE(TT, NZ, SW) \
+  ((G != 1) ? launch_fast<TT, EPB_GBIG, NZ, false, SW, true>(pr, threads, smem, s) : launch_fast<TT, 1, NZ, false, SW, true>(pr, threads, smem, s))
+#define EPB_DEFINE_FAST_KEEP_LAUNCHER(NAME, SW, TA, TB, TC, TD, WITH_NONOISE)                                         \
+  int NAME(const void* prv, int T, int G, int noise, int threads, size_t smem, cudaStream_t s) {                      \
+    const FastParams& pr = *static_cast<const FastParams*>(prv);                                                       \
+    if (!noise) return WITH_NONOISE ? EPB_FAST_KEEP_CASE(4, false, false) : -2;                                       \
+    switch (T) {                                                                                                      \
+      case TA: return EPB_FAST_KEEP_CASE(TA, true, SW);                                                               \
+      case TB: return EPB_FAST_KEEP_CASE(TB, true, SW);                                                               \
+      case TC: return EPB_FAST_KEEP_CASE(TC, true, SW);                                                               \
+      case TD: return EPB_FAST_KEEP_CASE(TD, true, SW);                                                               \
     }                                                                                                                 \
     return -2;                                                                                                        \
   }

@@ -260,6 +260,55 @@ def test_fast_kernel_equals_general_kernel(ep, kind, shape, tv, pn, rn, nmax, rb
     assert ok.sum() > 0.9 * (fb[..., 1] > 0).sum()
 
 
+KEEP_CASES = [
+    # kind, (C, P, R), time_varying, ping_num, range_sample_num
+    ("ek60", (2, 103, 4096), False, 5, 30),    # benchmark geometry: two column groups per thread
+    ("ek60", (3, 47, 1000), False, 8, 16),     # one group, R / 4 not a warp multiple, partial last tile
+    ("ek60", (2, 205, 2048), False, 10, 20),   # two sweeps (the reference's own setting)
+    ("ek60", (2, 45, 1000), False, None, None),  # no noise removal: Sv / echo_range only
+    ("azfp", (2, 43, 512), False, 4, 16),
+    ("ek80", (3, 37, 1024), False, 6, 40),     # GPT channel
+    ("ek60", (2, 61, 2048), True, 5, 30),      # law changes inside tiles: the gate hands the volume to the general kernel
+]
+
+
+@pytest.mark.parametrize("kind,shape,tv,pn,rn", KEEP_CASES)
+def test_fast_kernel_keep_outputs_equal_general_kernel(ep, kind, shape, tv, pn, rn):
+    """keep= through the persistent kernel (kKeep instantiations stream Sv / echo_range / Sv_noise / Sv_corrected out of
+    the register tile) against the general kernel: echo_range bit-identical, dB arrays within float32 rounding, NaN
+    masks identical except for samples within rounding of the SNR threshold."""
+    from echopype_b200 import synth
+
+    kw = {}
+    if kind == "ek60":
+        ed = synth.make_ek60(*shape, seed=41, nan_tail=0.2, time_varying=tv)
+    elif kind == "azfp":
+        ed = synth.make_azfp(*shape, seed=42)
+        kw = {"env_params": {"salinity": 30.0, "pressure": 50.0}}
+    else:
+        ed = synth.make_ek80(C=shape[0], P=shape[1], R=shape[2], mode="CW", encode="power", gpt_channel=1, nan_tail=0.2, seed=43)
+        kw = {"waveform_mode": "CW", "encode_mode": "power"}
+    keep = ("Sv", "echo_range") + (("Sv_noise", "Sv_corrected") if pn else ())
+    args = dict(ping_num=pn, range_sample_num=rn, range_bin="20m", ping_time_bin="20s", keep=keep, **kw)
+    a = ep.pipeline.compute_Sv_clean_MVBS(ed, fast=True, **args)
+    b = ep.pipeline.compute_Sv_clean_MVBS(ed, fast=False, **args)
+    ka, kb = a.attrs["kept"], b.attrs["kept"]
+    np.testing.assert_array_equal(ka["echo_range"].values, kb["echo_range"].values)
+    for k in ("Sv",) + (("Sv_noise",) if pn else ()):
+        x, y = ka[k].values, kb[k].values
+        assert np.array_equal(np.isnan(x), np.isnan(y)), k
+        np.testing.assert_allclose(x, y, atol=1e-4, equal_nan=True, err_msg=k)  # a few float32 ulps at |dB| ~ 200
+    if pn:
+        x, y = ka["Sv_corrected"].values, kb["Sv_corrected"].values
+        flip = np.isnan(x) != np.isnan(y)
+        assert flip.sum() <= max(2, 2e-5 * x.size), flip.sum()
+        both = ~np.isnan(x) & ~np.isnan(y)
+        # Sv_corrected = dB(v - noise): cancellation amplifies the float32 rounding of v and noise near the threshold
+        # (v / (v - noise) <= 1 / (1 - 10^-0.3) = 2 at the 3 dB SNR threshold)
+        assert np.abs(x[both] - y[both]).max() <= 2e-4
+    np.testing.assert_allclose(a["Sv"].values, b["Sv"].values, atol=2e-4, equal_nan=True)
+
+
 @pytest.mark.parametrize("pn,rn", [(5, 30), (10, 20)])
 def test_fast_kernel_vs_oracle_benchmark_shape(ep, pn, rn):
     """Benchmark-shaped tile geometry (R = 4096, 20 s bins) through the fast kernel against the oracle: ping_num 5 (u in
