@@ -620,157 +620,345 @@ __global__ void __launch_bounds__(128) transient_median_depth_kernel(const float
   }
 }
 
-// ---- transient noise as ONE strip kernel (rows of up to 4096 samples): no (sum, count) intermediate -------------------
-// A CTA walks a (channel, ping-chunk) strip ping by ping.  Each of its 512 threads owns 8 adjacent columns and keeps,
-// in float64 registers, the running sum over the 2 k + 1 pings of the window (reflected at the ends of the ping axis)
-// of the valid 10^(Sv/10) of its columns, plus the count: per output ping one row enters and one row leaves.  The
-// range window [n - w, n + w] of the array sliced at m0 (reflected at its ends) is then a difference of an inclusive
-// prefix sum ACROSS the columns, rebuilt per ping in shared memory (thread-local prefix over the 8 columns, warp scan,
-// 16 warp totals).  Reading the entering, the leaving and the centre row is all the traffic there is: the two-pass
-// form wrote a float2 per sample and read it twice (ncu: 39 GB of DRAM traffic for 8.2 GB algorithmic).
-constexpr int kStripThreads = 512, kStripCols = 8;
+// ---- transient noise as ONE strip kernel (rows of up to 4096 samples past exclude_above): no (sum, count) intermediate
+// A CTA walks a (channel, ping-chunk) strip ping by ping.  Each thread owns 16 adjacent columns (the first thread starts
+// at the 16-aligned column at or below m0; columns above exclude_above are never loaded) and keeps, in float64
+// registers, the running sum over the 2 k + 1 pings of the window (reflected at the ends of the ping axis) of the valid
+// 10^(Sv/10) of its columns: per output ping one row enters and one row leaves.  The range window [n - w, n + w] of the
+// array sliced at m0 (reflected at its ends) is a difference of an inclusive prefix sum ACROSS the columns, rebuilt per
+// ping in shared memory (thread-local sums, warp scan, warp totals).  The per-ping scan makes a CTA latency / barrier
+// bound, so the CTA is kept at <= 256 threads x 128 registers: TWO CTAs per SM work on independent strips.
+//  * prefix layout: column x (relative to the first thread's first column, negative / past the row in the mirror zones)
+//    at [x & 15][(x >> 4) + TL] with a compile-time row pitch - a warp's accesses to one j are consecutive, so writes and
+//    window reads are bank-conflict free, and for a given w & 15 (a 16-way switch per strip) every access of the window
+//    phase is ONE base register plus an immediate
+//  * reflection at the ends of the sliced axis without a special window path: the owners of the first / last w columns
+//    also store the prefix of the MIRRORED sequence (-I(x) before the axis, 2 I(last) - I(x) past it), so every window
+//    is one difference of two entries
+//  * NaN samples are counted as per-column DEFICITS (in shared memory: touched only when a NaN enters or leaves); while
+//    no column of the CTA carries one (the usual case, tracked with the barrier's OR) the window count is the constant
+//    (2 k + 1)(2 w + 1) and the count prefix is skipped
+//  * the count prefix is rebuilt only on pings where a deficit CHANGED; between those, a thread whose 16 windows hold no
+//    deficit (one difference of the count prefix) still takes the constant-count path
+//  * the per-ping chain (scan, two barriers) is shorter than a DRAM round trip: the three rows of the ping kPrefetch
+//    steps ahead are prefetched into L2 by TMA (cp.async.bulk.prefetch.L2, one instruction each), so that the register
+//    loads issued one ping ahead hit L2
+//  * NaN detection is one float add per sample (the sum of the raw dB values is NaN iff one of them is); NaN -> 0 by
+//    fmaxf(ex2(NaN), 0)
+// Reading the entering, the leaving and the centre row is all the traffic there is.
+constexpr int kStripThreads = 256, kStripCols = 16, kStripPitch = 320;  // pitch: threads + both mirror zones
+constexpr int kStripPrefetch = 4;                                         // pings of L2 prefetch distance
+__device__ __forceinline__ void strip_prefetch_l2(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 
-__global__ void __launch_bounds__(kStripThreads, 1)
+// one step of an inclusive warp scan: v + (v of lane - o) where that lane exists (the shuffle's own predicate)
+__device__ __forceinline__ double scan_up(double v, int o) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b32 lo, hi, a, b;\n\t.reg .f64 t;\n\t"
+      "mov.b64 {lo, hi}, %0;\n\t"
+      "shfl.sync.up.b32 a|p, lo, %1, 0, 0xffffffff;\n\t"
+      "shfl.sync.up.b32 b, hi, %1, 0, 0xffffffff;\n\t"
+      "mov.b64 t, {a, b};\n\t"
+      "@p add.f64 %0, %0, t;\n\t}"
+      : "+d"(v)
+      : "r"(o));
+  return v;
+}
+__device__ __forceinline__ int scan_up(int v, int o) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b32 a;\n\t"
+      "shfl.sync.up.b32 a|p, %0, %1, 0, 0xffffffff;\n\t"
+      "@p add.s32 %0, %0, a;\n\t}"
+      : "+r"(v)
+      : "r"(o));
+  return v;
+}
+
+// float <-> double without F2F: on B200 the 64-bit conversions share the XU pipe with MUFU and run at ~1 / clk / SM (ncu:
+// pipe_xu 124 % of "peak" with three of them per sample - every earlier form of this kernel sat at ~10 ms whatever its
+// instruction count).  Integer forms on the ALU pipe: exact for +0 / positive normal floats (ex2.ftz never returns a
+// denormal; +inf is not expected), truncating double -> float (1 ulp = 2.6e-7 dB) with everything below 2^-126 -> 0.
+__device__ __forceinline__ double f2d_pos(float f) {
+  const unsigned b = __float_as_uint(f);
+  return __hiloint2double((int)(b ? (b >> 3) + 0x38000000u : 0u), (int)(b << 29));
+}
+__device__ __forceinline__ float d2f_trunc(double d) {
+  const int hi = __double2hiint(d);
+  const unsigned r = __funnelshift_l((unsigned)__double2loint(d), (unsigned)(hi - 0x38000000), 3);
+  return hi >= 0x38100000 ? __uint_as_float(r) : 0.f;
+}
+
+template <int W15>
+__device__ __forceinline__ void strip_windows(const double* __restrict__ sph, const double* __restrict__ spl, float inv_full,
+                                              float (&pv)[kStripCols]) {
+  constexpr int L15 = 15 - W15;  // (-w - 1) & 15
+#pragma unroll
+  for (int j = 0; j < kStripCols; ++j) {
+    const double hi = sph[((j + W15) & 15) * kStripPitch + ((j + W15) >> 4)], lo = spl[((j + L15) & 15) * kStripPitch + ((j + L15) >> 4)];
+    pv[j] = kLog2ToDb * fast_log2(d2f_trunc(hi - lo) * inv_full);
+  }
+}
+
+template <bool kPooled>
+__global__ void __launch_bounds__(kStripThreads, 2)
     transient_strip_kernel(const float* __restrict__ Sv, const int* __restrict__ nsamp, unsigned char* __restrict__ mask,
                            float* __restrict__ pooled, long long P, int R, int m0, int k, float thr, int chunk, int nchunks,
-                           long long nstrips) {
-  // one pad element per 8: a thread's 8 adjacent columns and its neighbours' fall into different banks (pidx)
-  extern __shared__ double s_pre[];                        // [pidx(L) + 1] inclusive prefix of the running column sums (sliced axis)
-  const int L = R - m0;
-  auto pidx = [](int e) { return e + (e >> 3); };
-  int* s_cpre = reinterpret_cast<int*>(s_pre + (pidx(L) + 2));   // [pidx(L) + 1]
+                           long long nstrips, int TL) {
+  constexpr int TS = kStripPitch;
+  extern __shared__ double s_pre[];                              // [16][TS] inclusive prefix of the running column sums
+  int* s_cnt = reinterpret_cast<int*>(s_pre + kStripCols * TS);  // [16][TS] inclusive prefix of the deficits
+  int* s_cc = s_cnt + kStripCols * TS;                           // [16][kStripThreads] deficits per column
   __shared__ double s_ws[kStripThreads / 32];
   __shared__ int s_wc[kStripThreads / 32];
+  const int T = blockDim.x, NW = T >> 5;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int n0 = tid * kStripCols;  // first absolute column of this thread
+  const int col0 = m0 & ~15, Pi = (int)P;
+  const int n0 = col0 + tid * kStripCols;  // first absolute column of this thread
+  const bool active = n0 < R;
+  // Leading columns of the first thread above the sliced axis: they run through the scan like the others (no patching
+  // of loaded values); the prefix then carries the base B = I(m0 - 1), which cancels in every window and enters the
+  // mirrored entries before the axis as 2 B - I(x).  Their writers (all in the first warp: w <= 480) read B from the
+  // first thread's own entry after a __syncwarp.  Threads past the row load nothing and add nothing.
+  const int nkill = m0 - n0 > 0 ? m0 - n0 : 0;
+  auto slot = [&](int x) { return (x & 15) * TS + (x >> 4) + TL; };
+  if (tid == 0) s_pre[slot(-1)] = 0.0, s_cnt[slot(-1)] = 0;  // "before the first column" when m0 is 16-aligned
+  double* const my_pre = s_pre + tid + TL;
+  int* const my_cnt = s_cnt + tid + TL;
+  int* const my_cc = s_cc + tid;
   for (long long strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
     const long long c = strip / nchunks;
-    const long long p0 = (strip - c * nchunks) * chunk, p1 = (p0 + chunk < P) ? p0 + chunk : P;
+    const int p0 = (int)((strip - c * nchunks) * chunk), p1 = (p0 + chunk < Pi) ? p0 + chunk : Pi;
     const int w = nsamp[c];
-    const float* base = Sv + c * P * (long long)R;
-    auto refl = [&](long long q) { return q < 0 ? -q - 1 : (q >= P ? 2 * P - q - 1 : q); };
-    // the thread's 8 columns of a row as linear values; columns outside [m0, R) count as invalid
-    auto load8 = [&](long long q, float (&v)[kStripCols]) {
-      if (n0 < R) {
-        const float4* r4 = reinterpret_cast<const float4*>(base + q * (long long)R + n0);
-        const float4 a = __ldg(r4), b = __ldg(r4 + 1);
-        v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
-      } else {
+    const float* colbase = Sv + c * P * (long long)R + (active ? n0 : 0);
+    auto refl = [&](int q) { return q < 0 ? -q - 1 : (q >= Pi ? 2 * Pi - q - 1 : q); };
+    auto load16 = [&](int q, float (&v)[kStripCols]) {
+      const float4* r4 = reinterpret_cast<const float4*>(colbase + (long long)q * R);
 #pragma unroll
-        for (int j = 0; j < kStripCols; ++j) v[j] = CUDART_NAN_F;
+      for (int g = 0; g < 4; ++g) {
+        const float4 a = __ldg(r4 + g);
+        v[4 * g] = a.x, v[4 * g + 1] = a.y, v[4 * g + 2] = a.z, v[4 * g + 3] = a.w;
       }
     };
     double cs[kStripCols];
-    int cc[kStripCols];
+    int tchg = 0;      // a deficit of this thread's columns changed since the count prefix was built
+    int has_def = 0;   // CTA-uniform: the count prefix in shared memory is valid and holds deficits
 #pragma unroll
-    for (int j = 0; j < kStripCols; ++j) cs[j] = 0.0, cc[j] = 0;
-    auto add_row = [&](const float (&v)[kStripCols], int sign) {
+    for (int j = 0; j < kStripCols; ++j) cs[j] = 0.0, my_cc[j * kStripThreads] = 0;
+    auto lin = [](float v) { return f2d_pos(fmaxf(fast_exp2(v * kDb2Log2), 0.f)); };
+    // deficits of this thread's columns: +1 per NaN that enters, -1 per NaN that leaves (rare path)
+    auto count_nans = [&](const float (&vi)[kStripCols], const float (&vo)[kStripCols]) {
 #pragma unroll
       for (int j = 0; j < kStripCols; ++j) {
-        const float q = fast_exp2(v[j] * kDb2Log2);
-        const bool ok = (q == q) && (n0 + j >= m0);
-        cs[j] += ok ? (sign > 0 ? (double)q : -(double)q) : 0.0;
-        cc[j] += ok ? sign : 0;
+        const int d = (vi[j] != vi[j] ? 1 : 0) - (vo[j] != vo[j] ? 1 : 0);
+        if (d) my_cc[j * kStripThreads] += d, tchg = 1;
       }
     };
     // window of the first output ping, minus the row that enters in the first step
-    for (long long q = p0 - k; q < p0 + k; ++q) {
-      float v[kStripCols];
-      load8(refl(q), v);
-      add_row(v, +1);
+    if (active) {
+      float none[kStripCols];
+#pragma unroll
+      for (int j = 0; j < kStripCols; ++j) none[j] = 0.f;
+      for (int q = p0 - k; q < p0 + k; ++q) {
+        float v[kStripCols];
+        load16(refl(q), v);
+        float chk = 0.f;
+#pragma unroll
+        for (int j = 0; j < kStripCols; ++j) cs[j] += lin(v[j]), chk += v[j];
+        if (chk != chk) count_nans(v, none);
+      }
     }
-    // software pipeline: the three rows of the NEXT ping are requested before this ping's scan and barriers
-    float nin[kStripCols], nout[kStripCols], nc[kStripCols];
-    load8(refl(p0 + k), nin);
-    load8(p0, nc);
+    const int ifull = (2 * k + 1) * (2 * w + 1);
+    const float inv_full = 1.f / (float)ifull;
+    // owners of the first / last w columns of the sliced axis also write the mirrored prefix
+    const bool mirror = active && (n0 - m0 + 1 <= w || R - 1 - (n0 + kStripCols - 1) <= w);
+    const double* const sph = my_pre + (w >> 4);
+    const double* const spl = my_pre + ((-w - 1) >> 4);
+    // software pipeline: the entering and leaving rows of the NEXT ping are requested right after this ping's were used
+    float nin[kStripCols], nout[kStripCols];
+    if (active) load16(refl(p0 + k), nin);
 #pragma unroll
-    for (int j = 0; j < kStripCols; ++j) nout[j] = CUDART_NAN_F;  // nothing leaves in the first step
-    for (long long p = p0; p < p1; ++p) {
-      float vin[kStripCols], vout[kStripCols], vc[kStripCols];
-#pragma unroll
-      for (int j = 0; j < kStripCols; ++j) vin[j] = nin[j], vout[j] = nout[j], vc[j] = nc[j];
-      if (p + 1 < p1) {
-        load8(refl(p + 1 + k), nin);
-        load8(p + 1, nc);
-        load8(refl(p - k), nout);
+    for (int j = 0; j < kStripCols; ++j) nout[j] = -CUDART_INF_F;  // nothing leaves in the first step
+    // rows of the sliced axis as TMA prefetches: bytes from the first thread's first column to the end of the row
+    const float* rowbase = Sv + c * P * (long long)R + col0;
+    const unsigned rowbytes = (unsigned)(R - col0) * 4u;
+    auto prefetch_ping = [&](int pp) {  // the three rows ping pp will read
+      if (pp < p1) {
+        const int qi = pp + k, qo = pp - k - 1;
+        strip_prefetch_l2(rowbase + (long long)(qi >= Pi ? 2 * Pi - qi - 1 : qi) * R, rowbytes);
+        strip_prefetch_l2(rowbase + (long long)(qo < 0 ? -qo - 1 : qo) * R, rowbytes);
+        strip_prefetch_l2(rowbase + (long long)pp * R, rowbytes);
       }
-      add_row(vin, +1);
-      add_row(vout, -1);  // NaN (first step) adds nothing
-      // inclusive prefix across the columns: thread-local, warp scan, warp totals
-      double lp[kStripCols];
-      int lc[kStripCols];
+    };
+    if (tid == 0)
+      for (int d = 1; d < kStripPrefetch; ++d) prefetch_ping(p0 + d);
+    for (int p = p0; p < p1; ++p) {
+      if (tid == 0) prefetch_ping(p + kStripPrefetch);
       double run = 0.0;
-      int crun = 0;
-#pragma unroll
-      for (int j = 0; j < kStripCols; ++j) {
-        run += cs[j], crun += cc[j];
-        lp[j] = run, lc[j] = crun;
-      }
-      double inc = run;
-      int cinc = crun;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const double t = __shfl_up_sync(0xffffffffu, inc, o);
-        const int tc = __shfl_up_sync(0xffffffffu, cinc, o);
-        if (lane >= o) inc += t, cinc += tc;
-      }
-      if (lane == 31) s_ws[wid] = inc, s_wc[wid] = cinc;
-      __syncthreads();  // also: the previous ping's window reads of s_pre are done
-      // exclusive offset of this warp: lanes 0..15 scan the 16 warp totals with shuffles (a serial walk over shared
-      // memory put ~15 dependent loads on the critical path of every ping)
-      double wt = (lane < kStripThreads / 32) ? s_ws[lane] : 0.0;
-      int wtc = (lane < kStripThreads / 32) ? s_wc[lane] : 0;
-      double wi = wt;
-      int wic = wtc;
-#pragma unroll
-      for (int o = 1; o < kStripThreads / 32; o <<= 1) {
-        const double t = __shfl_up_sync(0xffffffffu, wi, o);
-        const int tc = __shfl_up_sync(0xffffffffu, wic, o);
-        if (lane >= o) wi += t, wic += tc;
-      }
-      const double off = (inc - run) + __shfl_sync(0xffffffffu, wi - wt, wid);
-      const int coff = (cinc - crun) + __shfl_sync(0xffffffffu, wic - wtc, wid);
-#pragma unroll
-      for (int j = 0; j < kStripCols; ++j) {
-        const int jj = n0 + j - m0;  // index on the sliced axis
-        if (jj >= 0 && jj < L) s_pre[pidx(jj + 1)] = off + lp[j], s_cpre[pidx(jj + 1)] = coff + lc[j];
-      }
-      if (tid == 0) s_pre[0] = 0.0, s_cpre[0] = 0;
-      __syncthreads();
-      // range windows, pooled Sv, mask: 8 outputs per thread
-      if (n0 < R) {
-        unsigned mlo = 0u, mhi = 0u;
-        float pv[kStripCols];
+      if (active) {
+        float chk = 0.f;
 #pragma unroll
         for (int j = 0; j < kStripCols; ++j) {
-          const int jj = n0 + j - m0;
-          float pooled_db = CUDART_NAN_F;
-          if (jj >= 0) {
-            const int lo = jj - w, hi = jj + w;
-            const int ca = lo < 0 ? 0 : lo, cb = hi >= L ? L - 1 : hi;
-            double ws = s_pre[pidx(cb + 1)] - s_pre[pidx(ca)];
-            int wc = s_cpre[pidx(cb + 1)] - s_cpre[pidx(ca)];
-            if (lo < 0) ws += s_pre[pidx(-lo)] - s_pre[0], wc += s_cpre[pidx(-lo)] - s_cpre[0];               // [0, -lo - 1]
-            if (hi >= L)                                                                                       // [2L-hi-1, L-1]
-              ws += s_pre[pidx(L)] - s_pre[pidx(2 * L - hi - 1)], wc += s_cpre[pidx(L)] - s_cpre[pidx(2 * L - hi - 1)];
-            if (wc > 0) pooled_db = kLog2ToDb * fast_log2(__fdividef((float)ws, (float)wc));
-          }
-          pv[j] = pooled_db;
-          const unsigned bit = (jj >= 0 && vc[j] - pooled_db > thr) ? 1u : 0u;
-          if (j < 4)
-            mlo |= bit << (8 * j);
-          else
-            mhi |= bit << (8 * (j - 4));
+          chk += nin[j] + nout[j];
+          cs[j] += lin(nin[j]);
+          cs[j] -= lin(nout[j]);
         }
-        *reinterpret_cast<uint2*>(mask + (c * P + p) * (long long)R + n0) = make_uint2(mlo, mhi);
-        if (pooled) {
+        if (chk != chk) count_nans(nin, nout);
+        if (p + 1 < p1) {
+          const int qi = p + 1 + k, qo = p - k;  // reflected at the ends of the ping axis
+          load16(qi >= Pi ? 2 * Pi - qi - 1 : qi, nin);
+          load16(qo < 0 ? -qo - 1 : qo, nout);
+        }
+#pragma unroll
+        for (int j = 0; j < kStripCols; ++j) run += cs[j];
+      }
+      // inclusive prefix across the columns: thread totals, warp scan, warp totals
+      double inc = run;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) inc = scan_up(inc, o);
+      if (lane == 31) s_ws[wid] = inc;
+      const int chg = __syncthreads_or(tchg);  // also: the previous ping's window reads are done
+      tchg = 0;
+      float vc[kStripCols];
+      if (active) load16(p, vc);
+      {
+        // exclusive offset of this warp: every group of 8 lanes adds up the totals of the warps before it
+        const double wt = ((lane & 7) < NW) ? s_ws[lane & 7] : 0.0;
+        double ex = ((lane & 7) < wid) ? wt : 0.0;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) ex += __shfl_xor_sync(0xffffffffu, ex, o);
+        const double off = (inc - run) + ex;
+        if (active) {
+          double acc = off;
+          if (nkill == 0) {
+#pragma unroll
+            for (int j = 0; j < kStripCols; ++j) acc += cs[j], my_pre[j * TS] = acc;
+          } else {  // the first thread: nothing above the column before the sliced axis (mirror zone)
+#pragma unroll
+            for (int j = 0; j < kStripCols; ++j) {
+              acc += cs[j];
+              if (j >= nkill - 1) my_pre[j * TS] = acc;
+            }
+          }
+        }
+        __syncwarp();
+        if (mirror) {
+          double tot2 = 0.0;
+          for (int i = 0; i < NW; ++i) tot2 += s_ws[i];
+          tot2 *= 2.0;
+          const double base2 = 2.0 * s_pre[slot(m0 - 1 - col0)];
+          double acc = off;
+#pragma unroll
+          for (int j = 0; j < kStripCols; ++j) {
+            acc += cs[j];
+            const int i1 = n0 + j - m0 + 1, i2 = R - 1 - (n0 + j);
+            if (i1 >= 1 && i1 <= w) s_pre[slot(m0 - i1 - 1 - col0)] = base2 - acc;
+            if (i2 >= 1 && i2 <= w) s_pre[slot(R - 1 + i2 - col0)] = tot2 - acc;
+          }
+        }
+      }
+      if (chg) {  // CTA-uniform and rare: a deficit changed, rebuild the count prefix with the same scan
+        int crun = 0;
+        if (active) {
+#pragma unroll
+          for (int j = 0; j < kStripCols; ++j) crun += my_cc[j * kStripThreads];
+        }
+        int cinc = crun;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) cinc = scan_up(cinc, o);
+        if (lane == 31) s_wc[wid] = cinc;
+        __syncthreads();
+        const int wtc = ((lane & 7) < NW) ? s_wc[lane & 7] : 0;
+        int cex = ((lane & 7) < wid) ? wtc : 0;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) cex += __shfl_xor_sync(0xffffffffu, cex, o);
+        const int coff = (cinc - crun) + cex;
+        int ctot = 0;
+        for (int i = 0; i < NW; ++i) ctot += s_wc[i];
+        has_def = ctot != 0;
+        if (active) {
+          int acc = coff;
+#pragma unroll
+          for (int j = 0; j < kStripCols; ++j) {
+            acc += my_cc[j * kStripThreads];
+            if (j >= nkill - 1) my_cnt[j * TS] = acc;
+          }
+        }
+        __syncwarp();
+        if (mirror) {
+          const int tot2 = 2 * ctot, base2 = 2 * s_cnt[slot(m0 - 1 - col0)];
+          int acc = coff;
+#pragma unroll
+          for (int j = 0; j < kStripCols; ++j) {
+            acc += my_cc[j * kStripThreads];
+            const int i1 = n0 + j - m0 + 1, i2 = R - 1 - (n0 + j);
+            if (i1 >= 1 && i1 <= w) s_cnt[slot(m0 - i1 - 1 - col0)] = base2 - acc;
+            if (i2 >= 1 && i2 <= w) s_cnt[slot(R - 1 + i2 - col0)] = tot2 - acc;
+          }
+        }
+      }
+      __syncthreads();
+      // range windows, pooled Sv, mask: 16 outputs per thread
+      unsigned char* mrow = mask + (c * P + p) * (long long)R;
+      if (active) {
+        float pv[kStripCols];
+        // no deficit in any of this thread's windows: one difference of the count prefix over their union
+        const bool plain = (!has_def || my_cnt[((15 + w) & 15) * TS + ((15 + w) >> 4)] == my_cnt[((-w - 1) & 15) * TS + ((-w - 1) >> 4)]);
+        if (plain) {
+          switch (w & 15) {
+            case 0: strip_windows<0>(sph, spl, inv_full, pv); break;
+            case 1: strip_windows<1>(sph, spl, inv_full, pv); break;
+            case 2: strip_windows<2>(sph, spl, inv_full, pv); break;
+            case 3: strip_windows<3>(sph, spl, inv_full, pv); break;
+            case 4: strip_windows<4>(sph, spl, inv_full, pv); break;
+            case 5: strip_windows<5>(sph, spl, inv_full, pv); break;
+            case 6: strip_windows<6>(sph, spl, inv_full, pv); break;
+            case 7: strip_windows<7>(sph, spl, inv_full, pv); break;
+            case 8: strip_windows<8>(sph, spl, inv_full, pv); break;
+            case 9: strip_windows<9>(sph, spl, inv_full, pv); break;
+            case 10: strip_windows<10>(sph, spl, inv_full, pv); break;
+            case 11: strip_windows<11>(sph, spl, inv_full, pv); break;
+            case 12: strip_windows<12>(sph, spl, inv_full, pv); break;
+            case 13: strip_windows<13>(sph, spl, inv_full, pv); break;
+            case 14: strip_windows<14>(sph, spl, inv_full, pv); break;
+            default: strip_windows<15>(sph, spl, inv_full, pv); break;
+          }
+        } else {  // deficits in this thread's windows: run-time offsets, counts from the deficit prefix
+#pragma unroll
+          for (int j = 0; j < kStripCols; ++j) {
+            const int hi = ((j + w) & 15) * TS + ((j + w) >> 4), lo = ((j - w - 1) & 15) * TS + ((j - w - 1) >> 4);
+            const int wc = ifull - (my_cnt[hi] - my_cnt[lo]);
+            float rc;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"((float)wc));
+            const float m = d2f_trunc(my_pre[hi] - my_pre[lo]) * rc;
+            pv[j] = wc > 0 ? kLog2ToDb * fast_log2(m) : CUDART_NAN_F;
+          }
+        }
+        unsigned mw[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int j = 0; j < kStripCols; ++j)  // (the first thread's columns above m0 are rewritten below)
+          mw[j >> 2] |= ((vc[j] - pv[j] > thr) ? 1u : 0u) << (8 * (j & 3));
+        *reinterpret_cast<uint4*>(mrow + n0) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+        if (kPooled) {
           float4* o4 = reinterpret_cast<float4*>(pooled + (c * P + p) * (long long)R + n0);
-          o4[0] = make_float4(pv[0], pv[1], pv[2], pv[3]);
-          o4[1] = make_float4(pv[4], pv[5], pv[6], pv[7]);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) o4[g] = make_float4(pv[4 * g], pv[4 * g + 1], pv[4 * g + 2], pv[4 * g + 3]);
+        }
+        for (int j = 0; j < nkill; ++j) {  // the first thread's columns above the sliced axis (same thread: ordered stores)
+          mrow[n0 + j] = 0;
+          if (kPooled) pooled[(c * P + p) * (long long)R + n0 + j] = CUDART_NAN_F;
+        }
+      }
+      // columns above the first thread's: outside the sliced axis
+      for (int i = tid; i < (col0 >> 4); i += T) {
+        *reinterpret_cast<uint4*>(mrow + 16 * i) = make_uint4(0u, 0u, 0u, 0u);
+        if (kPooled) {
+          float4* o4 = reinterpret_cast<float4*>(pooled + (c * P + p) * (long long)R + 16 * i);
+          o4[0] = o4[1] = o4[2] = o4[3] = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
         }
       }
     }
-    __syncthreads();  // next strip rewrites s_ws / s_pre
+    __syncthreads();  // next strip rewrites s_ws / s_pre / the deficits
   }
 }
 
@@ -827,23 +1015,27 @@ extern "C" int epb_transient_noise_mask(const float* Sv, const int* nsamp, float
   const int L = (int)R - min_range_sample;
   const size_t smem = (size_t)(L + 1) * 12 + 8;
   EPB_REQUIRE(smem <= 200 * 1024, "range_sample dimension too long for the shared-memory prefix sums");
-  // rows of up to 4096 samples (8 columns x 512 threads), 16-byte aligned: the single-pass strip kernel
-  if (R % 8 == 0 && R <= kStripThreads * kStripCols && L > 0 && ((uintptr_t)Sv % 16) == 0 && ((uintptr_t)mask % 8) == 0 &&
-      ((uintptr_t)pooled_Sv % 16) == 0) {
-    // strips: at least ~3 per SM, chunks not shorter than 8 windows (the 2 k pings of warm-up are read twice)
-    const long long want = ((long long)epb_num_sms() * 3 + C - 1) / C;
+  // up to 4096 samples past exclude_above (16 columns x 256 threads), 16-byte aligned rows: the single-pass strip kernel
+  const int col0 = min_range_sample & ~15;
+  const int TL = (max_nsamp + 16) / 16 + 1, TH = (max_nsamp + 15) / 16 + 1;  // mirror zones on both sides
+  const int threads = (int)(((R - col0) / kStripCols + 31) / 32 * 32);
+  if (R % 16 == 0 && R - col0 <= kStripThreads * kStripCols && L > 0 && ((uintptr_t)Sv % 16) == 0 && ((uintptr_t)mask % 16) == 0 &&
+      ((uintptr_t)pooled_Sv % 16) == 0 && (long long)(2 * num_side_pings + 1) * (2 * max_nsamp + 1) < (1LL << 24) && max_nsamp < L && max_nsamp <= 480 &&
+      P < (1LL << 30) && TL + threads + TH <= kStripPitch) {
+    // strips: ~2 per resident CTA (two CTAs per SM), chunks not shorter than 8 windows (the 2 k pings of warm-up are read twice)
+    const long long want = ((long long)epb_num_sms() * 4 + C - 1) / C;
     long long chunk = (P + want - 1) / want;
     const long long min_chunk = 8LL * (2 * num_side_pings + 1);
     if (chunk < min_chunk) chunk = min_chunk;
     if (chunk > P) chunk = P;
     const long long nchunks = (P + chunk - 1) / chunk;
-    const size_t sm = (size_t)(L + L / 8 + 4) * 12 + 32;
-    if (sm > 48 * 1024 &&
-        cudaFuncSetAttribute(transient_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess)
+    const size_t sm = (size_t)kStripCols * kStripPitch * 12 + (size_t)kStripCols * kStripThreads * 4;
+    auto kern = pooled_Sv ? transient_strip_kernel<true> : transient_strip_kernel<false>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess)
       return epb_check_launch("epb_transient_noise_mask(smem)");
-    const long long nstrips = nchunks * C, capg = (long long)epb_num_sms();
-    transient_strip_kernel<<<(unsigned)(nstrips < capg ? nstrips : capg), kStripThreads, sm, (cudaStream_t)stream>>>(
-        Sv, nsamp, mask, pooled_Sv, P, (int)R, min_range_sample, num_side_pings, threshold, (int)chunk, (int)nchunks, nstrips);
+    const long long nstrips = nchunks * C, capg = (long long)epb_num_sms() * 2;
+    kern<<<(unsigned)(nstrips < capg ? nstrips : capg), threads, sm, (cudaStream_t)stream>>>(
+        Sv, nsamp, mask, pooled_Sv, P, (int)R, min_range_sample, num_side_pings, threshold, (int)chunk, (int)nchunks, nstrips, TL);
     return epb_check_launch("epb_transient_noise_mask(strip)");
   }
   EPB_REQUIRE(window_sums, "window_sums scratch is needed for rows longer than 4096 samples");

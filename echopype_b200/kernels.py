@@ -378,7 +378,13 @@ def transient_noise_mask_depth(Sv, depth, C, P, R, dmin, dmax, depth_bin, exclud
 def transient_noise_mask(Sv, nsamp, C, P, R, min_range_sample, num_side_pings, threshold, want_pooled=False, out=None):
     """out: optional (mask, window_sums) buffers to reuse."""
     ns = torch.from_numpy(np.ascontiguousarray(nsamp, dtype=np.int32)).to(Sv.device)
-    strip = R % 8 == 0 and R <= 4096  # the single-pass strip kernel needs no (sum, count) scratch (8 bytes per sample)
+    # the single-pass strip kernel (up to 4096 samples past exclude_above) needs no (sum, count) scratch (8 bytes per sample);
+    # same conditions as epb_transient_noise_mask (masknoise.cu)
+    m0, wmax = int(min_range_sample), int(max(nsamp))
+    threads = ((R - (m0 & ~15)) // 16 + 31) // 32 * 32
+    strip = (R % 16 == 0 and 0 < R - (m0 & ~15) <= 4096 and wmax < R - m0 and wmax <= 480 and P < (1 << 30)
+             and (2 * int(num_side_pings) + 1) * (2 * wmax + 1) < (1 << 24)
+             and (wmax + 16) // 16 + 1 + threads + (wmax + 15) // 16 + 1 <= 320)
     if out is not None:
         mask, sums = out
     else:

@@ -163,6 +163,53 @@ def test_mask_transient_noise_vs_oracle(ep, shape, depth_bin, k, excl):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("C,P,R,depth_bin,k,excl,nan_frac", [
+    (2, 60, 4096, 5.0, 4, 100.0, 0.0),      # full-width strip (512 threads), no NaN: constant-count path only
+    (2, 60, 4096, 5.0, 4, 100.0, 0.001),    # deficits in most windows
+    (1, 70, 2048, 10.0, 25, 0.0, 0.0005),   # m0 = 0: the zero slot serves n - w - 1 = -1; k close to P / 2
+    (3, 33, 1008, 3.0, 7, 31.3, 0.01),      # m0 not a multiple of 16; R / 16 not a multiple of 32 (inactive threads)
+    (2, 33, 1008, 3.0, 7, 31.3, 0.0),       # the same without NaN: base correction on the constant-count path
+    (1, 20, 4112, 2.0, 2, 5.0, 0.0),        # R > 4096 served because exclude_above leaves <= 4096 columns
+    (1, 40, 512, 40.0, 3, 9.0, 0.003),      # long range windows (w > 128: mirror zones of several threads)
+    (2, 15, 64, 4.0, 14, 2.5, 0.05),        # windows as long as the sliced axis allows, k ~ P
+    (1, 400, 256, 2.0, 3, 0.0, 0.002),      # several chunks per channel (warm-up windows at chunk starts)
+])
+def test_transient_strip_kernel_stress(ep, C, P, R, depth_bin, k, excl, nan_frac):
+    """The single-pass strip kernel (masknoise.cu transient_strip_kernel) against the oracle: conflict-free prefix layout,
+    constant-count path vs deficit path, reflection at both ends of the sliced axis, unaligned exclude_above."""
+    import torch
+
+    from echopype_b200 import kernels
+
+    rng = np.random.default_rng(R + P)
+    Sv = rng.normal(-70.0, 6.0, size=(C, P, R))
+    Sv[:, rng.integers(0, P, 3), :] += 18.0 * (rng.random((C, 3, R)) < 0.5)
+    if nan_frac:
+        Sv[rng.random(Sv.shape) < nan_frac] = np.nan
+        Sv[0, P // 3, R // 2:] = np.nan  # a short ping
+        Sv[-1, P // 2:P // 2 + 2, :] = np.nan  # all-NaN pings
+    depth = np.stack([np.broadcast_to(1.0 + s * np.arange(R), (P, R)) for s in np.resize((0.19, 0.23, 0.31), C)]).copy()
+    Sv32 = Sv.astype(np.float32).astype(np.float64)
+    thr = 6.0
+    want, pooled = oclean.mask_transient_noise_index_binning(Sv32, depth, depth_bin, k, excl, thr)
+    nsamp = oclean.samples_per_depth_bin(depth, depth_bin)
+    m0 = int(np.argmin(depth <= excl))
+    assert R % 16 == 0 and R - (m0 & ~15) <= 4096  # the strip kernel's domain
+    mask, pl = kernels.transient_noise_mask(torch.from_numpy(Sv.astype(np.float32)).cuda(), nsamp, C, P, R, m0, k, thr, want_pooled=True)
+    mask2, _ = kernels.transient_noise_mask(torch.from_numpy(Sv.astype(np.float32)).cuda(), nsamp, C, P, R, m0, k, thr)
+    assert torch.equal(mask, mask2)  # the instantiation without the pooled output
+    pl, g = pl.cpu().numpy(), mask.cpu().numpy().astype(bool)
+    np.testing.assert_array_equal(np.isnan(pl), np.isnan(pooled))
+    assert np.nanmax(np.abs(pl - pooled)) < 1e-4
+    with np.errstate(invalid="ignore"):
+        margin = np.abs((Sv32 - pooled) - thr)
+    sure = np.isnan(margin) | (margin > 1e-3)
+    assert sure.mean() > 0.99
+    np.testing.assert_array_equal(g[sure], want[sure])
+    assert not g[:, :, :m0].any()
+
+
+@pytest.mark.gpu
 def test_mask_noise_argument_errors(ep):
     Sv, depth = _mock(1, 8, 40)
     ds = _ds(ep, Sv, depth)
