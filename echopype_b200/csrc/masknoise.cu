@@ -4,6 +4,7 @@
 // of 10^(Sv/10) over range_sample INDEX windows whose length comes from the mean sample spacing of the range variable
 // of each channel: the tile-mean machinery of the noise estimate with disjoint blocks (impulse) or sliding windows
 // with reflected borders (transient).  HBM-bound passes; window sums are accumulated in float64.
+#include <cstdlib>
 #include "epb_common.cuh"
 
 namespace {
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(256) block_mean_kernel(const float* __restrict
     const int n = nsamp[row / P];
     const int nb = (R + n - 1) / n;
     const float* sv = Sv + row * (long long)R;
+    float chk = 0.f;  // NaN iff the thread staged a NaN sample (the sum of the dB values)
     if ((R & 3) == 0) {  // 16-byte loads, four in flight per thread
       const float4* sv4 = reinterpret_cast<const float4*>(sv);
       const int R4 = R >> 2;
@@ -77,15 +79,37 @@ __global__ void __launch_bounds__(256) block_mean_kernel(const float* __restrict
           if (j + i * (int)blockDim.x < R4) v[i] = ld_stream4(sv4 + j + i * blockDim.x);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          if (j + i * (int)blockDim.x < R4)
+          if (j + i * (int)blockDim.x < R4) {
+            chk += (v[i].x + v[i].y) + (v[i].z + v[i].w);
             *reinterpret_cast<float4*>(s_row + 4 * (j + i * blockDim.x)) =
                 make_float4(fast_exp2(v[i].x * kDb2Log2), fast_exp2(v[i].y * kDb2Log2), fast_exp2(v[i].z * kDb2Log2),
                             fast_exp2(v[i].w * kDb2Log2));
+          }
       }
     } else {
-      for (int j = threadIdx.x; j < R; j += blockDim.x) s_row[j] = fast_exp2(ld_stream(sv + j) * kDb2Log2);
+      for (int j = threadIdx.x; j < R; j += blockDim.x) {
+        const float v = ld_stream(sv + j);
+        chk += v;
+        s_row[j] = fast_exp2(v * kDb2Log2);
+      }
     }
-    __syncthreads();
+    const int row_has_nan = __syncthreads_or(chk != chk);
+    if (!row_has_nan) {  // the usual row: plain sums, the member count is the block length
+      for (int b = threadIdx.x; b < nbmax; b += blockDim.x) {
+        float u = CUDART_NAN_F;
+        if (b < nb) {
+          const int j0 = b * n, j1 = (j0 + n < R) ? j0 + n : R;
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};
+          int j = j0;
+          for (; j + 4 <= j1; j += 4) s4[0] += s_row[j], s4[1] += s_row[j + 1], s4[2] += s_row[j + 2], s4[3] += s_row[j + 3];
+          for (; j < j1; ++j) s4[0] += s_row[j];
+          u = kLog2ToDb * fast_log2(__fdividef((s4[0] + s4[1]) + (s4[2] + s4[3]), (float)(j1 - j0)));
+        }
+        U[row * nbmax + b] = u;
+      }
+      __syncthreads();
+      continue;
+    }
     for (int b = threadIdx.x; b < nbmax; b += blockDim.x) {
       float u = CUDART_NAN_F;
       if (b < nb) {
@@ -155,6 +179,146 @@ __global__ void __launch_bounds__(256) impulse_mask_kernel(const float* __restri
       }
     }
     __syncthreads();
+  }
+}
+
+// Step 2 for blocks of at least 16 samples (the usual case: a depth bin of metres at centimetre sample spacing): thread
+// per 16 consecutive samples, which touch at most two blocks.  The two block flags come straight from U (three rows, L1 /
+// L2 resident: nbmax floats per row), the 16 mask bytes are two byte patterns spliced at the block boundary - no shared
+// memory, no barrier, one 16-byte store per thread (the shared-memory forward fill above: 2.6 ms on cfg2 at 8 % of DRAM).
+__global__ void __launch_bounds__(256) impulse_mask_wide_kernel(const float* __restrict__ U, const int* __restrict__ nsamp,
+                                                                unsigned char* __restrict__ mask, long long nrows, long long P,
+                                                                int R, int nbmax, int k, float thr) {
+  // CTA per row (grid-stride): the row's channel / ping split and block length are CTA-uniform
+  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const long long c = row / P, p = row - c * P;
+    const int n = __ldg(nsamp + c);
+    const int nb = (R + n - 1) / n;
+    const float* u0 = U + row * nbmax;
+    const bool hasf = p + k < P, hasb = p - k >= 0;
+    for (int j0 = threadIdx.x << 4; j0 < R; j0 += blockDim.x << 4) {
+    const int b = j0 / n, t = n - (j0 - b * n);  // samples j0 .. j0 + t - 1 belong to block b, the rest to b + 1
+    auto flag = [&](int bb) -> unsigned {
+      if (bb >= nb) return 0u;
+      const float v = __ldg(u0 + bb);
+      float f = v - (hasf ? __ldg(u0 + (long long)k * nbmax + bb) : CUDART_NAN_F);
+      float w = v - (hasb ? __ldg(u0 - (long long)k * nbmax + bb) : CUDART_NAN_F);
+      f = (f == f) ? f : CUDART_INF_F;
+      w = (w == w) ? w : CUDART_INF_F;
+      return (f > thr && w > thr) ? 0x01010101u : 0u;
+    };
+    unsigned wv[4] = {0u, 0u, 0u, 0u};
+    if (n >= 16) {
+      const unsigned f0 = flag(b), f1 = (t < 16) ? flag(b + 1) : 0u;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int tt = t - 4 * q;  // bytes of this word that belong to block b
+        const unsigned lo = tt >= 4 ? 0xffffffffu : (tt <= 0 ? 0u : (1u << (8 * tt)) - 1u);
+        wv[q] = (f0 & lo) | (f1 & ~lo);
+      }
+    } else {  // blocks shorter than 16 samples: flag per sample
+      for (int i = 0; i < 16; ++i) wv[i >> 2] |= (flag((j0 + i) / n) & 1u) << (8 * (i & 3));
+    }
+    *reinterpret_cast<uint4*>(mask + row * (long long)R + j0) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+    }
+  }
+}
+
+// ---- impulse noise in ONE pass (rows of up to 4096 samples, blocks of at least 16): a CTA walks a (channel, ping-chunk)
+// strip ping by ping with the block means of the 2 k + 1 pings around the output ping in a shared-memory ring, so Sv is
+// read once and the mask written once (5 bytes per sample; the two kernels above read the block means back from L2 and
+// serialise row load -> barrier -> sums -> barrier per row).  The next row is in flight in registers while the current
+// one is summed; rows without NaN (detected with one float add per sample) take plain sums.
+constexpr int kImpThreads = 256;
+__global__ void __launch_bounds__(kImpThreads) impulse_fused_kernel(const float* __restrict__ Sv, const int* __restrict__ nsamp,
+                                                                    float* __restrict__ U, unsigned char* __restrict__ mask,
+                                                                    long long P, int R, int nbmax, int k, float thr, int chunk,
+                                                                    int nchunks, long long nstrips) {
+  extern __shared__ __align__(16) float s_imp[];  // [R] linear row, [(2 k + 1)][nbmax] block means (dB) of the window pings
+  float* s_row = s_imp;
+  float* s_u = s_imp + R;
+  const int W = 2 * k + 1, tid = threadIdx.x, R4 = R >> 2, Pi = (int)P;
+  for (long long strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
+    const long long c = strip / nchunks;
+    const int p0 = (int)((strip - c * nchunks) * chunk), p1 = (p0 + chunk < Pi) ? p0 + chunk : Pi;
+    const int n = __ldg(nsamp + c), nb = (R + n - 1) / n;
+    const float4* base4 = reinterpret_cast<const float4*>(Sv + c * P * (long long)R);
+    const int q0 = (p0 - k > 0) ? p0 - k : 0, q1 = (p1 + k < Pi) ? p1 + k : Pi;  // rows whose block means are needed
+    float4 v[4];
+    auto load_row = [&](int q) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (tid + i * kImpThreads < R4) v[i] = ld_stream4(base4 + (long long)q * R4 + tid + i * kImpThreads);
+    };
+    load_row(q0);
+    for (int q = q0; q < q1 + k; ++q) {  // the last k steps only emit masks
+      if (q < q1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (tid + i * kImpThreads < R4) {
+            *reinterpret_cast<float4*>(s_row + 4 * (tid + i * kImpThreads)) =
+                make_float4(fast_exp2(v[i].x * kDb2Log2), fast_exp2(v[i].y * kDb2Log2), fast_exp2(v[i].z * kDb2Log2),
+                            fast_exp2(v[i].w * kDb2Log2));
+          }
+        if (q + 1 < q1) load_row(q + 1);
+        __syncthreads();
+        float* su = s_u + (q % W) * nbmax;
+        for (int b = tid; b < nb; b += kImpThreads) {
+          const int j0 = b * n, j1 = (j0 + n < R) ? j0 + n : R;
+          // plain sums (four interleaved float32 partial sums); a NaN member shows in the result, the block is then redone
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          int j = j0;
+          for (; j + 4 <= j1; j += 4) s0 += s_row[j], s1 += s_row[j + 1], s2 += s_row[j + 2], s3 += s_row[j + 3];
+          for (; j < j1; ++j) s0 += s_row[j];
+          float tot = (s0 + s1) + (s2 + s3);
+          int m = j1 - j0;
+          if (tot != tot) {
+            s0 = s1 = s2 = s3 = 0.f, m = 0;
+            for (j = j0; j < j1; j += 4) {
+              const float x0 = s_row[j], x1 = (j + 1 < j1) ? s_row[j + 1] : CUDART_NAN_F, x2 = (j + 2 < j1) ? s_row[j + 2] : CUDART_NAN_F,
+                          x3 = (j + 3 < j1) ? s_row[j + 3] : CUDART_NAN_F;
+              s0 += (x0 == x0) ? x0 : 0.f, s1 += (x1 == x1) ? x1 : 0.f, s2 += (x2 == x2) ? x2 : 0.f, s3 += (x3 == x3) ? x3 : 0.f;
+              m += (x0 == x0) + (x1 == x1) + (x2 == x2) + (x3 == x3);
+            }
+            tot = (s0 + s1) + (s2 + s3);
+          }
+          const float u = (m > 0) ? kLog2ToDb * fast_log2(__fdividef(tot, (float)m)) : CUDART_NAN_F;
+          su[b] = u;
+          if (q >= p0 && q < p1) U[(c * P + q) * nbmax + b] = u;
+        }
+        if (q >= p0 && q < p1)
+          for (int b = nb + tid; b < nbmax; b += kImpThreads) U[(c * P + q) * nbmax + b] = CUDART_NAN_F;
+      }
+      __syncthreads();  // block means of row q visible; s_row free for the next row
+      const int p = q - k;  // output ping: its window p - k .. p + k is in the ring (rows outside the ping axis: missing)
+      if (p >= p0 && p < p1) {
+        const float* u0 = s_u + (p % W) * nbmax;
+        const float* uf = (p + k < Pi) ? s_u + ((p + k) % W) * nbmax : nullptr;
+        const float* ub = (p - k >= 0) ? s_u + ((p - k) % W) * nbmax : nullptr;
+        auto flag = [&](int bb) -> unsigned {
+          if (bb >= nb) return 0u;
+          const float x = u0[bb];
+          float f = x - (uf ? uf[bb] : CUDART_NAN_F), w = x - (ub ? ub[bb] : CUDART_NAN_F);
+          f = (f == f) ? f : CUDART_INF_F;
+          w = (w == w) ? w : CUDART_INF_F;
+          return (f > thr && w > thr) ? 0x01010101u : 0u;
+        };
+        unsigned char* mrow = mask + (c * P + p) * (long long)R;
+        for (int j0 = tid << 4; j0 < R; j0 += kImpThreads << 4) {
+          const int b = j0 / n, t = n - (j0 - b * n);  // samples j0 .. j0 + t - 1 belong to block b, the rest to b + 1
+          const unsigned f0 = flag(b), f1 = (t < 16) ? flag(b + 1) : 0u;
+          unsigned wv[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int tt = t - 4 * g;
+            const unsigned lo = tt >= 4 ? 0xffffffffu : (tt <= 0 ? 0u : (1u << (8 * tt)) - 1u);
+            wv[g] = (f0 & lo) | (f1 & ~lo);
+          }
+          *reinterpret_cast<uint4*>(mrow + j0) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+        }
+      }
+    }
+    __syncthreads();  // the next strip rewrites the ring
   }
 }
 
@@ -809,8 +973,8 @@ __global__ void __launch_bounds__(kStripThreads, 2)
           load16(qi >= Pi ? 2 * Pi - qi - 1 : qi, nin);
           load16(qo < 0 ? -qo - 1 : qo, nout);
         }
-#pragma unroll
-        for (int j = 0; j < kStripCols; ++j) run += cs[j];
+        run = (((cs[0] + cs[1]) + (cs[2] + cs[3])) + ((cs[4] + cs[5]) + (cs[6] + cs[7]))) +
+              (((cs[8] + cs[9]) + (cs[10] + cs[11])) + ((cs[12] + cs[13]) + (cs[14] + cs[15])));
       }
       // inclusive prefix across the columns: thread totals, warp scan, warp totals
       double inc = run;
@@ -830,9 +994,15 @@ __global__ void __launch_bounds__(kStripThreads, 2)
         const double off = (inc - run) + ex;
         if (active) {
           double acc = off;
-          if (nkill == 0) {
+          if (nkill == 0) {  // four independent chains of four (a 16-long chain of dependent DADDs is ~150 cycles)
+            const double b1 = off + ((cs[0] + cs[1]) + (cs[2] + cs[3])), b2 = b1 + ((cs[4] + cs[5]) + (cs[6] + cs[7])),
+                         b3 = b2 + ((cs[8] + cs[9]) + (cs[10] + cs[11]));
+            double a0 = off, a1 = b1, a2 = b2, a3 = b3;
 #pragma unroll
-            for (int j = 0; j < kStripCols; ++j) acc += cs[j], my_pre[j * TS] = acc;
+            for (int j = 0; j < 4; ++j) {
+              a0 += cs[j], a1 += cs[4 + j], a2 += cs[8 + j], a3 += cs[12 + j];
+              my_pre[j * TS] = a0, my_pre[(4 + j) * TS] = a1, my_pre[(8 + j) * TS] = a2, my_pre[(12 + j) * TS] = a3;
+            }
           } else {  // the first thread: nothing above the column before the sliced axis (mirror zone)
 #pragma unroll
             for (int j = 0; j < kStripCols; ++j) {
@@ -992,12 +1162,40 @@ extern "C" int epb_impulse_noise_mask(const float* Sv, const int* nsamp, float* 
   const long long nrows = C * P, cap = (long long)epb_num_sms() * 8;
   const unsigned grid = (unsigned)(nrows < cap ? nrows : cap);
   const size_t smem = (size_t)R * 4;
+  // single pass: rows of up to 4096 samples in 16-byte units, blocks of at least 16 samples (nbmax = max ceil(R / nsamp))
+  const size_t fsm = (size_t)R * 4 + (size_t)(2 * num_side_pings + 1) * nbmax * 4;
+  if ((R & 15) == 0 && R <= 16 * kImpThreads && nbmax <= R / 16 && fsm <= 64 * 1024 && P < (1LL << 30) && ((uintptr_t)Sv % 16) == 0 &&
+      ((uintptr_t)mask % 16) == 0 && !getenv("EPB_IMPULSE_TWO_PASS")) {
+    const long long want = ((long long)epb_num_sms() * 16 + C - 1) / C;
+    long long chunk = (P + want - 1) / want;
+    const long long min_chunk = 16LL * (2 * num_side_pings + 1);
+    if (chunk < min_chunk) chunk = min_chunk;
+    if (chunk > P) chunk = P;
+    const long long nchunks = (P + chunk - 1) / chunk, nstrips = nchunks * C;
+    if (cudaFuncSetAttribute(impulse_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm) != cudaSuccess)
+      return epb_check_launch("epb_impulse_noise_mask(smem)");
+    impulse_fused_kernel<<<(unsigned)(nstrips < cap ? nstrips : cap), kImpThreads, fsm, (cudaStream_t)stream>>>(
+        Sv, nsamp, block_means, mask, P, (int)R, nbmax, num_side_pings, threshold, (int)chunk, (int)nchunks, nstrips);
+    return epb_check_launch("epb_impulse_noise_mask(fused)");
+  }
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(block_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return epb_check_launch("epb_impulse_noise_mask(smem)");
-  block_mean_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(Sv, nsamp, block_means, nrows, P, (int)R, nbmax);
-  impulse_mask_kernel<<<grid, 256, (size_t)((nbmax + 15) & ~15), (cudaStream_t)stream>>>(block_means, nsamp, mask, nrows, P, (int)R, nbmax,
-                                                              num_side_pings, threshold);
+  {  // 128 threads per row: the CTAs an SM holds are bounded by the 2048 threads before the shared-memory rows (13 rows of 16 KB)
+    const char* ev = getenv("EPB_BM_THREADS");
+    const int bt = ev ? atoi(ev) : 128;
+    const long long capb = (long long)epb_num_sms() * (2048 / bt);
+    block_mean_kernel<<<(unsigned)(nrows < capb ? nrows : capb), bt, smem, (cudaStream_t)stream>>>(Sv, nsamp, block_means, nrows, P, (int)R, nbmax);
+  }
+  if ((R & 15) == 0 && ((uintptr_t)mask % 16) == 0) {
+    const long long capw = (long long)epb_num_sms() * 8;
+    const int wt = R >= 4096 ? 256 : (int)((R / 16 + 31) / 32 * 32);
+    impulse_mask_wide_kernel<<<(unsigned)(nrows < capw ? nrows : capw), wt, 0, (cudaStream_t)stream>>>(
+        block_means, nsamp, mask, nrows, P, (int)R, nbmax, num_side_pings, threshold);
+  } else {
+    impulse_mask_kernel<<<grid, 256, (size_t)((nbmax + 15) & ~15), (cudaStream_t)stream>>>(block_means, nsamp, mask, nrows, P, (int)R, nbmax,
+                                                                                         num_side_pings, threshold);
+  }
   return epb_check_launch("epb_impulse_noise_mask");
 }
 

@@ -89,7 +89,10 @@ def _ds(ep, Sv, depth, range_var="depth"):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape,depth_bin,k", [((2, 40, 200), "2m", 2), ((3, 33, 1001), "5m", 3), ((1, 7, 64), "1m", 1)])
+@pytest.mark.parametrize("shape,depth_bin,k", [((2, 40, 200), "2m", 2), ((3, 33, 1001), "5m", 3), ((1, 7, 64), "1m", 1),
+                                               # the single-pass kernel (rows in 16-sample units, blocks >= 16 samples): several
+                                               # chunks per channel, k up to the chunk scale, a full-width row
+                                               ((2, 300, 512), "5m", 2), ((1, 90, 4096), "7m", 5), ((3, 21, 1024), "4m", 10)])
 def test_mask_impulse_noise_vs_oracle(ep, shape, depth_bin, k):
     Sv, depth = _mock(*shape)
     Sv32 = Sv.astype(np.float32).astype(np.float64)
@@ -117,17 +120,18 @@ def test_impulse_block_means_within_tolerance(ep):
 
     from echopype_b200 import kernels
 
-    Sv, depth = _mock(2, 25, 333)
-    Sv32 = Sv.astype(np.float32)
-    up = oclean.index_binning_downsample_upsample(Sv32.astype(np.float64), depth, 2.0)
-    nsamp = oclean.samples_per_depth_bin(depth, 2.0)
-    _, blocks = kernels.impulse_noise_mask(torch.from_numpy(Sv32).cuda(), nsamp, 2, 25, 333, 2, 10.0)
-    blocks = blocks.cpu().numpy()
-    for c, n in enumerate(nsamp):
-        ref = up[c][:, ::n]
-        got = blocks[c][:, : ref.shape[1]]
-        np.testing.assert_array_equal(np.isnan(got), np.isnan(ref))
-        assert np.nanmax(np.abs(got - ref)) < 1e-4  # dB, the tolerance of the path
+    for P, R, db in ((25, 333, 2.0), (130, 512, 5.0)):  # two-kernel path; single-pass kernel
+        Sv, depth = _mock(2, P, R)
+        Sv32 = Sv.astype(np.float32)
+        up = oclean.index_binning_downsample_upsample(Sv32.astype(np.float64), depth, db)
+        nsamp = oclean.samples_per_depth_bin(depth, db)
+        _, blocks = kernels.impulse_noise_mask(torch.from_numpy(Sv32).cuda(), nsamp, 2, P, R, 2, 10.0)
+        blocks = blocks.cpu().numpy()
+        for c, n in enumerate(nsamp):
+            ref = up[c][:, ::n]
+            got = blocks[c][:, : ref.shape[1]]
+            np.testing.assert_array_equal(np.isnan(got), np.isnan(ref))
+            assert np.nanmax(np.abs(got - ref)) < 1e-4  # dB, the tolerance of the path
 
 
 @pytest.mark.gpu
