@@ -405,12 +405,17 @@ int epb_pipeline_fast_try(const void* x, int x_i16, const epb_row* rows, const i
 void epb_range_max_init_launch(double* out_max, cudaStream_t s);
 void epb_range_max_gated_launch(const float* x, const epb_row* rows, long long nrows, int R, double* out_max, const int* gate,
                                 cudaStream_t s);
-long long epb_pipeline_fast_workspace(long long C, long long P, int ping_num);
+long long epb_pipeline_fast_workspace(long long C, long long P, long long R, int ping_num);
 void epb_ingest_gated_launch(const short* counts, float* out, long long n, const int* gate, cudaStream_t s);
 
 extern "C" epb_i64 epb_pipeline_workspace_bytes(epb_i64 C, epb_i64 P, int ping_num) {
   if (C <= 0 || P <= 0 || ping_num < 0) return 256;
-  return epb_pipeline_fast_workspace(C, P, ping_num);
+  return epb_pipeline_fast_workspace(C, P, 0, ping_num);
+}
+
+extern "C" epb_i64 epb_pipeline_workspace_bytes_r(epb_i64 C, epb_i64 P, epb_i64 R, int ping_num) {
+  if (C <= 0 || P <= 0 || ping_num < 0) return 256;
+  return epb_pipeline_fast_workspace(C, P, R, ping_num);
 }
 
 // counts: NULL, or the int16 raw power counts of which backscatter_r (then a scratch buffer) is the float32 image that

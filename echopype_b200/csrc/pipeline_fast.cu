@@ -11,6 +11,7 @@ int epb_fast_launch_i16c(const void* pr, int T, int G, int noise, int threads, s
 int epb_fast_launch_f32ka(const void* pr, int T, int G, int noise, int threads, size_t smem, cudaStream_t s);
 int epb_fast_launch_f32kb(const void* pr, int T, int G, int noise, int threads, size_t smem, cudaStream_t s);
 int epb_fast_launch_f32kc(const void* pr, int T, int G, int noise, int threads, size_t smem, cudaStream_t s);
+int epb_fast_launch_f32w(const void* pr, int T, int G, int noise, int threads, size_t smem, cudaStream_t s);
 
 namespace {
 constexpr int kMaxPingNum = 64;  // two-sweep mode: up to 8 sub-tiles of 8 rows
@@ -32,14 +33,19 @@ int epb_pipeline_fast_try(const void* x, int x_i16, const epb_row* rows, const i
   const bool noise = ping_num > 0;
   const bool keep = o_sv || o_rng || o_svn || o_svc;  // full-size outputs: the kKeep instantiations (float32 input only)
   if (keep && (x_i16 || sv_input)) return 0;
-  const bool sweep = noise && ping_num > kMaxT;  // the noise tile streams through the ring twice in sub-tiles
+  // rows of 4097 .. 8192 samples (float32 input, no full-size outputs): four column groups per thread, single-row tiles;
+  // the noise tile then always streams through the ring twice (one row per sub-tile)
+  const bool wide = R > 4096;
+  if (wide && (x_i16 || keep)) return 0;
+  const bool sweep = noise && (ping_num > kMaxT || wide);  // the noise tile streams through the ring twice in sub-tiles
   int S = 1, T = noise ? ping_num : 4;
   if (sweep) sweep_shape(ping_num, &S, &T);
-  if (ping_num > kMaxPingNum || R % 4 != 0 || R > 4096 || R < 128 || C * nX >= (1LL << 31) || nR > 32000) return 0;
+  if (wide) S = noise ? ping_num : 1, T = 1;
+  if (ping_num > kMaxPingNum || R % 4 != 0 || R > 8192 || R < 128 || C * nX >= (1LL << 31) || nR > 32000) return 0;
   if (x_i16 && (R % 8 != 0 || sv_input)) return 0;  // 16-byte rows for the bulk copies
   const int xb = x_i16 ? 2 : 4;
   if (noise && range_sample_num < 4) return 0;  // a column group of four may touch at most two range tiles
-  const int G = (R / 4 > EPB_G1_THREADS) ? EPB_GBIG : 1;  // column groups per thread
+  const int G = wide ? 4 : (R / 4 > EPB_G1_THREADS) ? EPB_GBIG : 1;  // column groups per thread
   const int threads = (int)(((R / 4 + G - 1) / G + 31) / 32 * 32);
   const int nRt = noise ? (int)((R + range_sample_num - 1) / range_sample_num) : 0;
   // ring: as many tile slots as fit (at least one, at most kMaxTilesInFlight; more than 4 buys nothing)
@@ -85,7 +91,9 @@ int epb_pipeline_fast_try(const void* x, int x_i16, const epb_row* rows, const i
   prepare_kernel<<<(unsigned)((ndesc + 127) / 128), 128, 0, s>>>(rows, xbin, P, nX, T, pr.PN, S, pr.nPt, ndesc, sv_input,
                                                                  const_cast<TileInfo*>(pr.tiles), irregular);
   int rc = -2;
-  if (keep) {
+  if (wide) {
+    rc = epb_fast_launch_f32w(&pr, T, G, noise ? 1 : 0, threads, smem, s);
+  } else if (keep) {
     if (sweep) {
       rc = epb_fast_launch_f32kc(&pr, T, G, 1, threads, smem, s);
     } else {
@@ -106,9 +114,10 @@ int epb_pipeline_fast_try(const void* x, int x_i16, const epb_row* rows, const i
   return 1;
 }
 
-long long epb_pipeline_fast_workspace(long long C, long long P, int ping_num) {
-  const int PN = ping_num > 0 ? ping_num : 4;
+long long epb_pipeline_fast_workspace(long long C, long long P, long long R, int ping_num) {
+  int PN = ping_num > 0 ? ping_num : 4;
   int S = 1, T = PN;
   if (ping_num > kMaxT && ping_num <= kMaxPingNum) sweep_shape(ping_num, &S, &T);
+  if (R > 4096) S = ping_num > 0 ? ping_num : 1, PN = ping_num > 0 ? ping_num : 1;  // one descriptor per row
   return 256 + C * ((P + PN - 1) / PN) * S * (long long)sizeof(TileInfo);
 }

@@ -193,7 +193,7 @@ def bin_reduce(Sv, range_var, xbin, r_edges, acc, C, P, R, nX, closed_right=Fals
 def bin_reduce_law(Sv, rows, xbin, r_edges, acc, C, P, R, nX, closed_right=False, depth_off=None, depth_scale=None, fast=True):
     """fast=False forces the warp-per-row kernel (no workspace -> no dispatch to the persistent kernel)."""
     nR = int(r_edges.numel()) - 1
-    nws = int(_lib.load().epb_pipeline_workspace_bytes(int(C), int(P), 0)) if fast else 0
+    nws = int(_lib.load().epb_pipeline_workspace_bytes_r(int(C), int(P), int(R), 0)) if fast else 0
     ws = torch.empty(nws, dtype=torch.uint8, device=Sv.device) if fast else None
     _lib.call(
         "epb_bin_reduce_law", ptr(Sv), ptr(rows), ptr(depth_off), ptr(depth_scale), ptr(xbin), ptr(r_edges), nR,
@@ -286,7 +286,7 @@ def pipeline_power_mvbs(x, rows, xbin, r_edges, acc, C, P, R, nX, ping_num, rang
     """fast=False forces the general kernel (no workspace -> no fast-path dispatch)."""
     nm = float("nan") if noise_max is None else float(noise_max)
     nR = int(r_edges.numel()) - 1
-    nws = int(_lib.load().epb_pipeline_workspace_bytes(int(C), int(P), int(ping_num))) if fast else 0
+    nws = int(_lib.load().epb_pipeline_workspace_bytes_r(int(C), int(P), int(R), int(ping_num))) if fast else 0
     ws = torch.empty(nws, dtype=torch.uint8, device=x.device) if fast else None
     _lib.call(
         "epb_pipeline_power_mvbs", ptr(x), ptr(rows), ptr(xbin), ptr(r_edges), nR, int(closed_right), ptr(acc),

@@ -212,7 +212,7 @@ int epb_coarsen(const float* Sv, const float* echo_range, float* out, float* er_
  * workspace: NULL or a 16-byte aligned device scratch buffer of workspace_bytes >=
  * epb_pipeline_workspace_bytes(C, P, ping_num) bytes owned by the caller and private to this launch (it receives
  * one 144-byte descriptor per ping tile); with a workspace, regular volumes (every ping tile shares one range law, finite
- * calibration constants, R <= 4096, ping_num <= 8, no full-size outputs) run on the persistent
+ * calibration constants, R <= 8192 (float32 input; full-size outputs and int16 counts: R <= 4096), ping_num <= 64) run on the persistent
  * register-resident kernel (pipeline_fast_impl.cuh), decided on the device without a host synchronisation. */
 int epb_pipeline_power_mvbs(const float* backscatter_r, const epb_row* rows, const int* xbin,
                             const double* r_edges, int nR, int closed_right, double* acc, float* noise_out,
@@ -232,6 +232,10 @@ int epb_pipeline_power_mvbs_i16(const short* counts, float* scratch, const epb_r
                                 float noise_max, float snr_threshold, double* range_max_out, void* workspace,
                                 epb_i64 workspace_bytes, void* stream);
 epb_i64 epb_pipeline_workspace_bytes(epb_i64 C, epb_i64 P, int ping_num);
+/* The same for a given row length: rows of 4097 .. 8192 samples run on the persistent kernel with single-row tiles (one
+ * descriptor per ping), which needs a larger workspace than epb_pipeline_workspace_bytes (R <= 4096) reports; with the
+ * smaller workspace such volumes take the general kernel. */
+epb_i64 epb_pipeline_workspace_bytes_r(epb_i64 C, epb_i64 P, epb_i64 R, int ping_num);
 epb_i64 epb_pipeline_smem_bytes(epb_i64 R, int nR, int tile, int do_noise, int staged);
 
 /* ---- ping-sharded execution: pack / unpack around the ONE all-reduce(sum) that merges the ping bins two

@@ -224,6 +224,12 @@ FAST_CASES = [
     ("ek80", (3, 131, 1024), False, 32, 40, None, "20m", "12s", "left"),    # 4 sub-tiles of 8; P ends inside a sub-tile
     ("ek60", (2, 61, 2048), True, 12, 30, None, "10m", "7s", "left"),       # law changes inside noise tiles -> general kernel via gate
     ("azfp", (2, 143, 512), False, 20, 16, None, "2m", "10s", "left"),      # 3 sub-tiles of 7 (7 + 7 + 6)
+    # rows of 4097 .. 8192 samples: four column groups per thread, single-row tiles, the noise tile streams twice
+    ("ek60", (2, 103, 8192), False, 5, 30, None, "20m", "20s", "left"),     # cfg3-sized rows; partial last noise tile
+    ("ek60", (2, 64, 6000), False, 10, 20, "-125.0dB", "10m", "7s", "right"),  # threads past the row end; ping bins straddle
+    ("ek60", (2, 45, 8192), False, None, None, None, "20m", "20s", "left"),  # no noise removal
+    ("ek80", (2, 37, 5120), False, 3, 40, None, "20m", "12s", "left"),
+    ("ek60", (2, 41, 8192), True, 5, 30, None, "50m", "20s", "left"),       # law changes -> general kernel via gate
 ]
 
 
