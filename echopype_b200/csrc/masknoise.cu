@@ -864,15 +864,23 @@ __device__ __forceinline__ void strip_windows(const double* __restrict__ sph, co
   }
 }
 
-template <bool kPooled>
+// kDepth: windows of depth VALUES (clean/utils.py:28-105 pool_Sv, use_index_binning=False) on volumes whose depth rows are
+// the same for every ping of a channel: the samples with |depth - d| <= depth_bin then form the SAME index interval
+// [i0(n), i1(n)) in every ping of the window, so the pooled value is again one difference of the prefix of the running
+// column sums - with per-column interval ends (tables from depth_window_table_kernel, staged in shared memory) instead
+// of n -+ w, no reflection (pings / depths too close to the ends of their axes give NaN, the window is cut at the last
+// ping) and no slicing at exclude_above (it enters through the validity of a column).
+template <bool kPooled, bool kDepth = false>
 __global__ void __launch_bounds__(kStripThreads, 2)
     transient_strip_kernel(const float* __restrict__ Sv, const int* __restrict__ nsamp, unsigned char* __restrict__ mask,
                            float* __restrict__ pooled, long long P, int R, int m0, int k, float thr, int chunk, int nchunks,
-                           long long nstrips, int TL) {
+                           long long nstrips, int TL, const unsigned short* __restrict__ wtab = nullptr,
+                           const float* __restrict__ depth = nullptr) {
   constexpr int TS = kStripPitch;
   extern __shared__ double s_pre[];                              // [16][TS] inclusive prefix of the running column sums
   int* s_cnt = reinterpret_cast<int*>(s_pre + kStripCols * TS);  // [16][TS] inclusive prefix of the deficits
   int* s_cc = s_cnt + kStripCols * TS;                           // [16][kStripThreads] deficits per column
+  unsigned short* s_wt = reinterpret_cast<unsigned short*>(s_cc + kStripCols * kStripThreads);  // kDepth: [3][R] lo slot, hi slot, width
   __shared__ double s_ws[kStripThreads / 32];
   __shared__ int s_wc[kStripThreads / 32];
   const int T = blockDim.x, NW = T >> 5;
@@ -893,10 +901,20 @@ __global__ void __launch_bounds__(kStripThreads, 2)
   for (long long strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
     const long long c = strip / nchunks;
     const int p0 = (int)((strip - c * nchunks) * chunk), p1 = (p0 + chunk < Pi) ? p0 + chunk : Pi;
-    const int w = nsamp[c];
+    const int w = kDepth ? 0 : nsamp[c];
+    if (kDepth) {  // the channel's window tables (the previous strip's readers are past its final barrier)
+      const uint4* src = reinterpret_cast<const uint4*>(wtab + c * 3 * (long long)R);
+      for (int i = tid; i < (3 * R) >> 3; i += T) reinterpret_cast<uint4*>(s_wt)[i] = __ldg(src + i);
+    }
     const float* colbase = Sv + c * P * (long long)R + (active ? n0 : 0);
-    auto refl = [&](int q) { return q < 0 ? -q - 1 : (q >= Pi ? 2 * Pi - q - 1 : q); };
+    // index windows: pings reflect at the ends of the axis; depth windows: pings outside the axis do not exist
+    auto refl = [&](int q) { return kDepth ? q : (q < 0 ? -q - 1 : (q >= Pi ? 2 * Pi - q - 1 : q)); };
     auto load16 = [&](int q, float (&v)[kStripCols]) {
+      if (kDepth && (q < 0 || q >= Pi)) {  // CTA-uniform
+#pragma unroll
+        for (int j = 0; j < kStripCols; ++j) v[j] = -CUDART_INF_F;  // contributes nothing, never a deficit
+        return;
+      }
       const float4* r4 = reinterpret_cast<const float4*>(colbase + (long long)q * R);
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -935,7 +953,7 @@ __global__ void __launch_bounds__(kStripThreads, 2)
     const int ifull = (2 * k + 1) * (2 * w + 1);
     const float inv_full = 1.f / (float)ifull;
     // owners of the first / last w columns of the sliced axis also write the mirrored prefix
-    const bool mirror = active && (n0 - m0 + 1 <= w || R - 1 - (n0 + kStripCols - 1) <= w);
+    const bool mirror = !kDepth && active && (n0 - m0 + 1 <= w || R - 1 - (n0 + kStripCols - 1) <= w);
     const double* const sph = my_pre + (w >> 4);
     const double* const spl = my_pre + ((-w - 1) >> 4);
     // software pipeline: the entering and leaving rows of the NEXT ping are requested right after this ping's were used
@@ -949,8 +967,8 @@ __global__ void __launch_bounds__(kStripThreads, 2)
     auto prefetch_ping = [&](int pp) {  // the three rows ping pp will read
       if (pp < p1) {
         const int qi = pp + k, qo = pp - k - 1;
-        strip_prefetch_l2(rowbase + (long long)(qi >= Pi ? 2 * Pi - qi - 1 : qi) * R, rowbytes);
-        strip_prefetch_l2(rowbase + (long long)(qo < 0 ? -qo - 1 : qo) * R, rowbytes);
+        if (!kDepth || qi < Pi) strip_prefetch_l2(rowbase + (long long)(qi >= Pi ? 2 * Pi - qi - 1 : qi) * R, rowbytes);
+        if (!kDepth || qo >= 0) strip_prefetch_l2(rowbase + (long long)(qo < 0 ? -qo - 1 : qo) * R, rowbytes);
         strip_prefetch_l2(rowbase + (long long)pp * R, rowbytes);
       }
     };
@@ -969,9 +987,9 @@ __global__ void __launch_bounds__(kStripThreads, 2)
         }
         if (chk != chk) count_nans(nin, nout);
         if (p + 1 < p1) {
-          const int qi = p + 1 + k, qo = p - k;  // reflected at the ends of the ping axis
-          load16(qi >= Pi ? 2 * Pi - qi - 1 : qi, nin);
-          load16(qo < 0 ? -qo - 1 : qo, nout);
+          const int qi = p + 1 + k, qo = p - k;  // reflected at the ends of the ping axis (index windows)
+          load16(kDepth ? qi : (qi >= Pi ? 2 * Pi - qi - 1 : qi), nin);
+          load16(kDepth ? qo : (qo < 0 ? -qo - 1 : qo), nout);
         }
         run = (((cs[0] + cs[1]) + (cs[2] + cs[3])) + ((cs[4] + cs[5]) + (cs[6] + cs[7]))) +
               (((cs[8] + cs[9]) + (cs[10] + cs[11])) + ((cs[12] + cs[13]) + (cs[14] + cs[15])));
@@ -1073,7 +1091,41 @@ __global__ void __launch_bounds__(kStripThreads, 2)
       if (active) {
         float pv[kStripCols];
         // no deficit in any of this thread's windows: one difference of the count prefix over their union
-        const bool plain = (!has_def || my_cnt[((15 + w) & 15) * TS + ((15 + w) >> 4)] == my_cnt[((-w - 1) & 15) * TS + ((-w - 1) >> 4)]);
+        if (kDepth) {
+          // clean/utils.py:78-84: the ping keeps p - k >= 0 and p + k <= P; the window holds pings p - k .. min(p + k, P - 1)
+          const bool pvalid = (p - k >= 0) && (p + k <= Pi);
+          const int nrow = ((p + k < Pi) ? p + k : Pi - 1) - (p - k) + 1;
+          unsigned tw[3][8];  // this thread's 16 entries of the three tables, two 16-bit values per word
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const uint4 q = *reinterpret_cast<const uint4*>(s_wt + a * R + n0 + 8 * g);
+              tw[a][4 * g] = q.x, tw[a][4 * g + 1] = q.y, tw[a][4 * g + 2] = q.z, tw[a][4 * g + 3] = q.w;
+            }
+#pragma unroll
+          for (int j = 0; j < kStripCols; ++j) {
+            const int sh = 16 * (j & 1);
+            const int lo = (tw[0][j >> 1] >> sh) & 0xffff, hi = (tw[1][j >> 1] >> sh) & 0xffff, wd = (tw[2][j >> 1] >> sh) & 0xffff;
+            const int wc = nrow * wd - (has_def ? s_cnt[hi] - s_cnt[lo] : 0);
+            float rc;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"((float)wc));
+            const float m = d2f_trunc(s_pre[hi] - s_pre[lo]) * rc;
+            pv[j] = (pvalid && wd != 0 && wc > 0) ? kLog2ToDb * fast_log2(m) : CUDART_NAN_F;
+          }
+          if (kPooled) {  // a sample without a depth of its own has no window (its Sv is NaN: the mask is False either way)
+            const float4* dq = reinterpret_cast<const float4*>(depth + (c * P + p) * (long long)R + n0);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float4 dv = __ldg(dq + g);
+              if (!(dv.x == dv.x)) pv[4 * g] = CUDART_NAN_F;
+              if (!(dv.y == dv.y)) pv[4 * g + 1] = CUDART_NAN_F;
+              if (!(dv.z == dv.z)) pv[4 * g + 2] = CUDART_NAN_F;
+              if (!(dv.w == dv.w)) pv[4 * g + 3] = CUDART_NAN_F;
+            }
+          }
+        }
+        const bool plain = !kDepth && (!has_def || my_cnt[((15 + w) & 15) * TS + ((15 + w) >> 4)] == my_cnt[((-w - 1) & 15) * TS + ((-w - 1) >> 4)]);
         if (plain) {
           switch (w & 15) {
             case 0: strip_windows<0>(sph, spl, inv_full, pv); break;
@@ -1093,7 +1145,7 @@ __global__ void __launch_bounds__(kStripThreads, 2)
             case 14: strip_windows<14>(sph, spl, inv_full, pv); break;
             default: strip_windows<15>(sph, spl, inv_full, pv); break;
           }
-        } else {  // deficits in this thread's windows: run-time offsets, counts from the deficit prefix
+        } else if (!kDepth) {  // deficits in this thread's windows: run-time offsets, counts from the deficit prefix
 #pragma unroll
           for (int j = 0; j < kStripCols; ++j) {
             const int hi = ((j + w) & 15) * TS + ((j + w) >> 4), lo = ((j - w - 1) & 15) * TS + ((j - w - 1) >> 4);
@@ -1233,7 +1285,8 @@ extern "C" int epb_transient_noise_mask(const float* Sv, const int* nsamp, float
       return epb_check_launch("epb_transient_noise_mask(smem)");
     const long long nstrips = nchunks * C, capg = (long long)epb_num_sms() * 2;
     kern<<<(unsigned)(nstrips < capg ? nstrips : capg), threads, sm, (cudaStream_t)stream>>>(
-        Sv, nsamp, mask, pooled_Sv, P, (int)R, min_range_sample, num_side_pings, threshold, (int)chunk, (int)nchunks, nstrips, TL);
+        Sv, nsamp, mask, pooled_Sv, P, (int)R, min_range_sample, num_side_pings, threshold, (int)chunk, (int)nchunks, nstrips, TL,
+        nullptr, nullptr);
     return epb_check_launch("epb_transient_noise_mask(strip)");
   }
   EPB_REQUIRE(window_sums, "window_sums scratch is needed for rows longer than 4096 samples");
@@ -1281,6 +1334,145 @@ extern "C" int epb_impulse_noise_mask_depth(const float* Sv, const float* depth,
                                                                      upsampled, nrows, (int)R);
   impulse_mask_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(upsampled, mask, nrows, P, (int)R, num_side_pings, threshold);
   return epb_check_launch("epb_impulse_noise_mask_depth");
+}
+
+namespace {
+// A channel's depth rows are "uniform" when every ping has the same depth at a column wherever its depth is defined, and
+// samples without a depth (NaN: the padding of shorter pings, calibrate/range.py:143-148) carry no Sv either - such
+// samples are members of no window in the reference (NaN fails both comparisons) and contribute nothing here (NaN Sv).
+// Pass 1: the channel's reference row = column-wise maximum of the defined depths (ordered-int atomic maximum).
+__device__ __forceinline__ int float_order(float f) {
+  const int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__global__ void __launch_bounds__(256) depth_ref_row_kernel(const float* __restrict__ depth, long long P, int R, int pchunk,
+                                                            int* __restrict__ ref_ord) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long c = blockIdx.z;
+  const long long p0 = (long long)blockIdx.y * pchunk, p1 = (p0 + pchunk < P) ? p0 + pchunk : P;
+  if (n >= R) return;
+  float m = -CUDART_INF_F;
+  for (long long p = p0; p < p1; ++p) m = fmaxf(m, __ldg(depth + (c * P + p) * R + n));  // fmaxf skips NaN
+  atomicMax(ref_ord + c * R + n, float_order(m));
+}
+__global__ void __launch_bounds__(256) depth_ref_decode_kernel(int* __restrict__ ref, long long total) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int o = ref[i];
+  const float f = __int_as_float(o >= 0 ? o : o ^ 0x7fffffff);
+  ref[i] = __float_as_int(f == -CUDART_INF_F ? CUDART_NAN_F : f);  // a column without any depth
+}
+// Pass 2: *mismatch != 0 when a defined depth differs from the reference row, or a sample without depth has an Sv
+__global__ void __launch_bounds__(256) depth_rows_uniform_kernel(const float* __restrict__ depth, const float* __restrict__ Sv,
+                                                                 const float* __restrict__ ref, long long P, long long R4,
+                                                                 long long total4, int* __restrict__ mismatch) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float4* d4 = reinterpret_cast<const float4*>(depth);
+  const float4* s4 = reinterpret_cast<const float4*>(Sv);
+  const float4* r4 = reinterpret_cast<const float4*>(ref);
+  bool bad = false;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += stride) {
+    const long long row = i / R4, c = row / P;
+    const float4 a = __ldg(d4 + i), v = __ldg(s4 + i), b = __ldg(r4 + c * R4 + (i - row * R4));
+    const float av[4] = {a.x, a.y, a.z, a.w}, vv[4] = {v.x, v.y, v.z, v.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) bad |= (av[q] == av[q]) ? (av[q] != bv[q]) : (vv[q] == vv[q]);
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) *mismatch = 1;
+}
+
+// per (channel, column): the index interval of the samples with |depth - d| <= depth_bin in the channel's depth row
+// (clean/utils.py:86-93, float64 comparisons of the float32 depths; NaN depths count as beyond every value) as
+// prefix slots of the strip kernel (slot(i0 - 1), slot(i1 - 1)) and its width i1 - i0; width 0 where the column's own
+// conditions fail (:78-84: d - bin >= min depth, d + bin <= max depth, d - bin >= exclude_above; NaN fails all)
+__global__ void __launch_bounds__(256) depth_window_table_kernel(const float* __restrict__ ref, int R, double dmin,
+                                                                 double dmax, double bin, double exclude_above, int TL,
+                                                                 unsigned short* __restrict__ wtab, long long total) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long c = i / R;
+  const int n = (int)(i - c * R);
+  const float* dr = ref + c * (long long)R;  // the channel's reference depth row
+  const double d = (double)dr[n];
+  int i0 = 0, i1 = 0;
+  if ((d - bin >= dmin) && (d + bin <= dmax) && (d - bin >= exclude_above)) {
+    const double lo_v = d - bin, hi_v = d + bin;
+    int lo = 0, hi = R;  // first sample with depth >= lo_v
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      const float v = dr[mid];
+      if (!(v == v) || (double)v >= lo_v)
+        hi = mid;
+      else
+        lo = mid + 1;
+    }
+    i0 = lo;
+    hi = R;  // first sample with depth > hi_v
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      const float v = dr[mid];
+      if (!(v == v) || (double)v > hi_v)
+        hi = mid;
+      else
+        lo = mid + 1;
+    }
+    i1 = lo;
+  }
+  auto slot = [&](int x) { return (x & 15) * kStripPitch + (x >> 4) + TL; };
+  unsigned short* t = wtab + c * 3 * (long long)R;
+  t[n] = (unsigned short)slot(i0 - 1);
+  t[R + n] = (unsigned short)slot(i1 - 1);
+  t[2 * R + n] = (unsigned short)(i1 - i0);
+}
+}  // namespace
+
+extern "C" int epb_depth_rows_uniform(const float* depth, const float* Sv, float* ref_rows, int* mismatch, epb_i64 C, epb_i64 P,
+                                      epb_i64 R, void* stream) {
+  EPB_REQUIRE(depth && Sv && ref_rows && mismatch && C > 0 && C < 65536 && P > 0 && R > 0 && R % 4 == 0, "bad pointer / shape");
+  EPB_REQUIRE((((uintptr_t)depth | (uintptr_t)Sv | (uintptr_t)ref_rows) % 16) == 0, "arrays must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cudaMemsetAsync(mismatch, 0, sizeof(int), s) != cudaSuccess || cudaMemsetAsync(ref_rows, 0x80, (size_t)(C * R) * 4, s) != cudaSuccess)
+    return epb_check_launch("epb_depth_rows_uniform(memset)");  // 0x80808080: below every ordered float
+  const int pchunk = 256;
+  dim3 g1((unsigned)((R + 255) / 256), (unsigned)((P + pchunk - 1) / pchunk), (unsigned)C);
+  EPB_REQUIRE(g1.y < 65536, "too many pings");
+  depth_ref_row_kernel<<<g1, 256, 0, s>>>(depth, P, (int)R, pchunk, reinterpret_cast<int*>(ref_rows));
+  depth_ref_decode_kernel<<<(unsigned)((C * R + 255) / 256), 256, 0, s>>>(reinterpret_cast<int*>(ref_rows), C * R);
+  const long long total4 = C * P * (R / 4), cap = (long long)epb_num_sms() * 8, gb = (total4 + 255) / 256;
+  depth_rows_uniform_kernel<<<(unsigned)(gb < cap ? gb : cap), 256, 0, s>>>(depth, Sv, ref_rows, P, R / 4, total4, mismatch);
+  return epb_check_launch("epb_depth_rows_uniform");
+}
+
+extern "C" int epb_transient_noise_mask_depth_uniform(const float* Sv, const float* depth, const float* ref_rows, unsigned short* tables, unsigned char* mask,
+                                                      float* pooled_Sv, epb_i64 C, epb_i64 P, epb_i64 R, double depth_min,
+                                                      double depth_max, double depth_bin, double exclude_above, int num_side_pings,
+                                                      float threshold, void* stream) {
+  EPB_REQUIRE(Sv && depth && ref_rows && tables && mask, "NULL pointer");
+  EPB_REQUIRE(C > 0 && P > 0 && R > 0 && num_side_pings >= 0, "bad shape / argument");
+  const int threads = (int)((R / kStripCols + 31) / 32 * 32), TL = 1;
+  if (!(R % 16 == 0 && R <= kStripThreads * kStripCols && P < (1LL << 30) && ((uintptr_t)Sv % 16) == 0 && ((uintptr_t)mask % 16) == 0 &&
+        ((uintptr_t)pooled_Sv % 16) == 0 && ((uintptr_t)tables % 16) == 0 && (long long)(2 * num_side_pings + 1) * R < (1LL << 24) &&
+        TL + threads + 1 <= kStripPitch)) {
+    epb_set_error("%s: %s", __func__, "needs range_sample % 16 == 0, range_sample <= 4096, 16-byte aligned arrays");
+    return EPB_E_UNSUPPORTED;
+  }
+  const long long totc = C * R;
+  depth_window_table_kernel<<<(unsigned)((totc + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ref_rows, (int)R, depth_min, depth_max, depth_bin,
+                                                                                               exclude_above, TL, tables, totc);
+  const long long want = ((long long)epb_num_sms() * 4 + C - 1) / C;
+  long long chunk = (P + want - 1) / want;
+  const long long min_chunk = 8LL * (2 * num_side_pings + 1);
+  if (chunk < min_chunk) chunk = min_chunk;
+  if (chunk > P) chunk = P;
+  const long long nchunks = (P + chunk - 1) / chunk;
+  const size_t sm = (size_t)kStripCols * kStripPitch * 12 + (size_t)kStripCols * kStripThreads * 4 + (size_t)R * 6;
+  auto kern = pooled_Sv ? transient_strip_kernel<true, true> : transient_strip_kernel<false, true>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess)
+    return epb_check_launch("epb_transient_noise_mask_depth_uniform(smem)");
+  const long long nstrips = nchunks * C, capg = (long long)epb_num_sms() * 2;
+  kern<<<(unsigned)(nstrips < capg ? nstrips : capg), threads, sm, (cudaStream_t)stream>>>(
+      Sv, nullptr, mask, pooled_Sv, P, (int)R, 0, num_side_pings, threshold, (int)chunk, (int)nchunks, nstrips, TL, tables, depth);
+  return epb_check_launch("epb_transient_noise_mask_depth_uniform");
 }
 
 extern "C" int epb_transient_noise_mask_depth(const float* Sv, const float* depth, double* prefix_sums, int* prefix_counts,

@@ -364,7 +364,22 @@ def impulse_noise_mask_depth(Sv, depth, edges, C, P, R, num_side_pings, threshol
 
 
 def transient_noise_mask_depth(Sv, depth, C, P, R, dmin, dmax, depth_bin, exclude_above, num_side_pings, threshold, want_pooled=False):
-    """Depth-value window variant (use_index_binning=False)."""
+    """Depth-value window variant (use_index_binning=False).  Volumes whose depth rows are the same for every ping of a
+    channel (checked on the device) take the single-pass strip kernel; others the per-sample bisection kernels, which need
+    12 bytes of scratch per sample."""
+    k = int(num_side_pings)
+    if R % 16 == 0 and R <= 4096 and P < (1 << 30) and (2 * k + 1) * R < (1 << 24) and depth.data_ptr() % 16 == 0 and Sv.data_ptr() % 16 == 0:
+        flag = torch.empty(1, dtype=torch.int32, device=Sv.device)
+        ref = torch.empty((C, R), dtype=torch.float32, device=Sv.device)
+        _lib.call("epb_depth_rows_uniform", ptr(depth), ptr(Sv), ptr(ref), ptr(flag), C, P, R, stream())
+        if int(flag.item()) == 0:
+            tables = torch.empty(C * 3 * R, dtype=torch.int16, device=Sv.device)
+            mask = torch.empty((C, P, R), dtype=torch.uint8, device=Sv.device)
+            pooled = torch.empty((C, P, R), dtype=torch.float32, device=Sv.device) if want_pooled else None
+            _lib.call("epb_transient_noise_mask_depth_uniform", ptr(Sv), ptr(depth), ptr(ref), ptr(tables), ptr(mask), ptr(pooled),
+                      C, P, R, ctypes.c_double(float(dmin)), ctypes.c_double(float(dmax)), ctypes.c_double(float(depth_bin)),
+                      ctypes.c_double(float(exclude_above)), k, ctypes.c_float(float(threshold)), stream())
+            return mask, pooled
     pre = torch.empty((C, P, R + 1), dtype=torch.float64, device=Sv.device)
     cnt = torch.empty((C, P, R + 1), dtype=torch.int32, device=Sv.device)
     mask = torch.empty((C, P, R), dtype=torch.uint8, device=Sv.device)

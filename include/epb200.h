@@ -301,6 +301,22 @@ int epb_transient_noise_mask_depth(const float* Sv, const float* depth, double* 
                                    unsigned char* mask, float* pooled_Sv, epb_i64 C, epb_i64 P, epb_i64 R, double depth_min,
                                    double depth_max, double depth_bin, double exclude_above, int num_side_pings, float threshold,
                                    void* stream);
+/* The same result for volumes whose depth rows are UNIFORM per channel: every ping has the same depth at a column wherever
+ * its depth is defined (a fixed transducer depth and one sample interval / sound speed per channel - the usual case), and
+ * samples without a depth (NaN: the padding of shorter pings) carry no Sv either.  The window of a sample is then the same
+ * index interval in every ping and the pooled value is a difference of the prefix of the running column sums (the
+ * single-pass strip kernel of epb_transient_noise_mask with per-column interval ends): one pass over Sv, no [C,P,R+1]
+ * scratch - cfg2: milliseconds instead of 1.6 s.
+ * epb_depth_rows_uniform writes the channels' reference depth rows (ref_rows [C,R] float32: column-wise maximum of the
+ * defined depths) and sets *mismatch (device int) to non-zero when the volume is not uniform (then use
+ * epb_transient_noise_mask_depth).  epb_transient_noise_mask_depth_uniform: ref_rows from that call, tables [C,3,R]
+ * uint16 scratch; returns EPB_E_UNSUPPORTED unless R % 16 == 0, R <= 4096 and the arrays are 16-byte aligned. */
+int epb_depth_rows_uniform(const float* depth, const float* Sv, float* ref_rows, int* mismatch, epb_i64 C, epb_i64 P, epb_i64 R,
+                           void* stream);
+int epb_transient_noise_mask_depth_uniform(const float* Sv, const float* depth, const float* ref_rows, unsigned short* tables,
+                                           unsigned char* mask, float* pooled_Sv, epb_i64 C, epb_i64 P, epb_i64 R,
+                                           double depth_min, double depth_max, double depth_bin, double exclude_above,
+                                           int num_side_pings, float threshold, void* stream);
 
 /* ---- raw power ingest (convert/parse_base.py:24,302 `power = counts.astype(float32) * INDEX2POWER`, :686-730
  *      pad_shorter_ping): n int16 counts -> float32 dB, -32768 (padding marker) -> NaN. -------------------------- */

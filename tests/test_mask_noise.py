@@ -371,3 +371,72 @@ def test_mask_transient_noise_depth_windows_vs_oracle(ep, k, depth_bin, excl):
     pl = pl.cpu().numpy()
     np.testing.assert_array_equal(np.isnan(pl), np.isnan(pooled))
     assert np.nanmax(np.abs(pl - pooled)) < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,P,R,k,depth_bin,excl,nan_frac", [
+    (2, 30, 256, 2, 2.0, 4.0, 0.02),     # NaN samples: deficit counts; pings near both ends of the axis are NaN
+    (1, 12, 512, 5, 1.0, 0.0, 0.0),      # p + k == P: the window loses its last ping; no NaN: constant counts
+    (2, 9, 64, 6, 3.0, 5.0, 0.05),       # 2 k + 1 > P: no ping qualifies, everything NaN / False
+    (1, 40, 4096, 3, 10.0, 100.0, 0.001),  # full-width rows
+])
+def test_transient_depth_windows_uniform_rows(ep, C, P, R, k, depth_bin, excl, nan_frac):
+    """Depth-value windows on volumes whose depth rows do not change with the ping (the single-pass strip kernel with
+    per-column interval tables, masknoise.cu kDepth) against the oracle's pool_Sv (clean/utils.py:28-105), and against the
+    per-sample bisection kernels on the same input."""
+    import torch
+
+    from echopype_b200 import kernels
+
+    rng = np.random.default_rng(C * 1000 + R)
+    Sv = rng.normal(-70.0, 6.0, size=(C, P, R))
+    Sv[:, rng.integers(0, P, 3), :] += 12.0 * (rng.random((C, 3, R)) < 0.5)
+    if nan_frac:
+        Sv[rng.random(Sv.shape) < nan_frac] = np.nan
+        Sv[0, P // 3, R // 2:] = np.nan
+    spacing = np.resize((0.19, 0.23), C)
+    depth = np.ascontiguousarray(np.stack([np.broadcast_to((2.0 + s * np.arange(R)).astype(np.float32), (P, R)) for s in spacing]), dtype=np.float64)
+    Sv32 = Sv.astype(np.float32).astype(np.float64)
+    thr = 3.0
+    Svt, dt = torch.from_numpy(Sv.astype(np.float32)).cuda(), torch.from_numpy(np.ascontiguousarray(depth, dtype=np.float32)).cuda()
+    assert dt.is_contiguous()
+    if nan_frac:  # a short ping: no depth where the samples are padding (calibrate/range.py:143-148)
+        depth[0, P // 3, R // 2:] = np.nan
+        dt[0, P // 3, R // 2:] = float("nan")
+    flag = torch.empty(1, dtype=torch.int32, device="cuda")
+    ref = torch.empty((C, R), dtype=torch.float32, device="cuda")
+    kernels._lib.call("epb_depth_rows_uniform", kernels.ptr(dt), kernels.ptr(Svt), kernels.ptr(ref), kernels.ptr(flag), C, P, R, kernels.stream())
+    assert int(flag.item()) == 0
+    mask, pl = kernels.transient_noise_mask_depth(Svt, dt, C, P, R, np.nanmin(depth), np.nanmax(depth), depth_bin, excl, k, thr, want_pooled=True)
+    mask2, _ = kernels.transient_noise_mask_depth(Svt, dt, C, P, R, np.nanmin(depth), np.nanmax(depth), depth_bin, excl, k, thr)
+    assert torch.equal(mask, mask2)
+    # the general kernels on the same volume (a perturbed copy of one depth value makes the rows non-uniform)
+    d2 = dt.clone()
+    d2[0, P - 1, R - 1] = torch.nextafter(d2[0, P - 1, R - 1], torch.tensor(float("inf"), device="cuda"))
+    kernels._lib.call("epb_depth_rows_uniform", kernels.ptr(d2), kernels.ptr(Svt), kernels.ptr(ref), kernels.ptr(flag), C, P, R, kernels.stream())
+    assert int(flag.item()) != 0
+    if R <= 512:
+        want, pooled = oclean.mask_transient_noise_depth_binning(Sv32, depth, depth_bin, k, excl, thr)
+        d3 = dt.clone()  # a sample with an Sv but no depth: not uniform
+        d3[C - 1, 0, 3] = float("nan")
+        Sv3 = Svt.clone()
+        Sv3[C - 1, 0, 3] = -60.0
+        kernels._lib.call("epb_depth_rows_uniform", kernels.ptr(d3), kernels.ptr(Sv3), kernels.ptr(ref), kernels.ptr(flag), C, P, R, kernels.stream())
+        assert int(flag.item()) != 0
+    else:  # the oracle's Python loops need minutes here: the per-sample bisection kernels stand in (themselves oracle-tested)
+        mg, pg = kernels.transient_noise_mask_depth(Svt, d2, C, P, R, np.nanmin(depth), np.nanmax(depth), depth_bin, excl, k, thr, want_pooled=True)
+        pooled = pg.cpu().numpy().astype(np.float64)
+        pooled[0, P - 1 - k:, :] = np.nan  # rows whose windows see the perturbed value: not compared
+        with np.errstate(invalid="ignore"):
+            want = (Sv32 - pooled) > thr
+    pl, g = pl.cpu().numpy(), mask.cpu().numpy().astype(bool)
+    cmp = np.ones(pooled.shape, bool)
+    if R > 512:
+        cmp[0, P - 1 - k:, :] = False
+    np.testing.assert_array_equal(np.isnan(pl)[cmp], np.isnan(pooled)[cmp])
+    if (~np.isnan(pooled[cmp])).any():
+        assert np.nanmax(np.abs(pl - pooled)[cmp]) < 1e-4
+    with np.errstate(invalid="ignore"):
+        margin = np.abs((Sv32 - pooled) - thr)
+    sure = (np.isnan(margin) | (margin > 1e-3)) & cmp
+    np.testing.assert_array_equal(g[sure], want[sure])

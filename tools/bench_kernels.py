@@ -194,6 +194,9 @@ def extra(a, which, C, P, R, n, x, rows, out, rng, ed):
         tbuf = (mbuf[0], torch.empty((C, P, R, 2), dtype=torch.float32, device=dev))
         ms, mn = timeit(lambda: kernels.transient_noise_mask(out, nsamp, C, P, R, 1300, 25, 12.0, out=tbuf), max(3, a.iters // 2))
         report("mask_transient_noise(10m, 25 pings)", ms, mn, 5 * n, n)
+        dmin, dmax = float(rng.nan_to_num(nan=1e30).min()), float(rng.nan_to_num(nan=0.0).max())
+        ms, mn = timeit(lambda: kernels.transient_noise_mask_depth(out, rng, C, P, R, dmin, dmax, 10.0, 250.0, 25, 12.0), 3)
+        report("mask_transient_noise(10m, 25 pings, depth-value windows)", ms, mn, 9 * n, n)
     if "pipex" in which:  # cost of the optional outputs of the fused launch
         nz = torch.empty((C, -(-P // 5)), dtype=torch.float32, device=dev)
         rm = torch.empty(1, dtype=torch.float64, device=dev)
