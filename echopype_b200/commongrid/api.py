@@ -207,10 +207,16 @@ def _coarsen_time_mean(ping_time, ping_num):
     t = np.asarray(ping_time).astype("datetime64[ns]").astype(np.int64)
     n = t.shape[0]
     nP = -(-n // ping_num)
-    out = np.empty(nP, dtype=np.int64)
-    for i in range(nP):
-        seg = t[i * ping_num : (i + 1) * ping_num]
-        out[i] = seg[0] + int(np.mean((seg - seg[0]).astype(np.float64)))  # xarray: float mean of the offsets, truncated to ns
+    # vectorised over the tiles (a Python loop over 10^4 tiles cost 50 ms): offsets from each tile's first ping as float64
+    # (integers far below 2^53: their sum is exact in any order, so the mean equals xarray's), padding excluded
+    first = t[::ping_num]
+    pad = np.full(nP * ping_num, np.iinfo(np.int64).min, dtype=np.int64)
+    pad[:n] = t
+    tiles = pad.reshape(nP, ping_num)
+    valid = np.arange(nP * ping_num).reshape(nP, ping_num) < n
+    off = np.where(valid, (tiles - first[:, None]).astype(np.float64), 0.0)
+    mean = off.sum(axis=1) / valid.sum(axis=1)
+    out = first + mean.astype(np.int64)  # truncated to ns like int(np.mean(...))
     return out.astype("datetime64[ns]")
 
 

@@ -21,9 +21,20 @@ __global__ void __launch_bounds__(256) range_diff_kernel(const float* __restrict
     const float* r = rng + row * (long long)R;
     double s = 0.0;
     unsigned n = 0;
-    for (int j = threadIdx.x; j + 1 < R; j += blockDim.x) {
-      const float d = r[j + 1] - r[j];
-      if (d == d) s += (double)d, ++n;
+    if ((R & 3) == 0 && (((uintptr_t)rng) & 15) == 0) {  // four differences per 16-byte load plus the next row element
+      for (int j4 = threadIdx.x; j4 < (R >> 2); j4 += blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(r) + j4);
+        const float nx = (4 * j4 + 4 < R) ? __ldg(r + 4 * j4 + 4) : CUDART_NAN_F;
+        const float d[4] = {v.y - v.x, v.z - v.y, v.w - v.z, nx - v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (d[k] == d[k]) s += (double)d[k], ++n;
+      }
+    } else {
+      for (int j = threadIdx.x; j + 1 < R; j += blockDim.x) {
+        const float d = r[j + 1] - r[j];
+        if (d == d) s += (double)d, ++n;
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

@@ -437,6 +437,20 @@ __global__ void __launch_bounds__(256) apply_mask_kernel(const float* __restrict
                                                          float* __restrict__ out, long long n, long long plane,
                                                          int mask_has_channel, float fill, const float* __restrict__ fill_plane) {
   const long long stride = (long long)gridDim.x * blockDim.x;
+  if ((plane & 3) == 0 && ((((uintptr_t)src) | ((uintptr_t)out) | ((uintptr_t)fill_plane)) & 15) == 0 && (((uintptr_t)mask) & 3) == 0) {
+    // four samples per thread and step: 16-byte loads / stores, one 4-byte mask load (the scalar form ran at 0.39 of HBM)
+    const long long n4 = n >> 2, plane4 = plane >> 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += stride) {
+      const long long pi = i % plane4;
+      const unsigned m = __ldg(reinterpret_cast<const unsigned*>(mask) + (mask_has_channel ? i : pi));
+      const float4 v = ld_stream4(reinterpret_cast<const float4*>(src) + i);
+      float4 f = make_float4(fill, fill, fill, fill);
+      if (fill_plane) f = __ldg(reinterpret_cast<const float4*>(fill_plane) + pi);
+      st_stream4(reinterpret_cast<float4*>(out) + i, make_float4((m & 0xffu) ? v.x : f.x, (m & 0xff00u) ? v.y : f.y,
+                                                                  (m & 0xff0000u) ? v.z : f.z, (m & 0xff000000u) ? v.w : f.w));
+    }
+    return;
+  }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
     const long long pi = i % plane;
     const long long mi = mask_has_channel ? i : pi;
