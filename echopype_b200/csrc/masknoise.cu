@@ -262,7 +262,9 @@ __global__ void __launch_bounds__(kImpThreads) impulse_fused_kernel(const float*
         if (tid + i * kImpThreads < R4) v[i] = ld_stream4(base4 + (long long)q * R4 + tid + i * kImpThreads);
     };
     load_row(q0);
-    for (int q = q0; q < q1 + k; ++q) {  // the last k steps only emit masks
+    const unsigned ninv = (unsigned)((0x100000000ULL + (unsigned)n - 1) / (unsigned)n);  // j / n = umulhi(j, ninv) for j n < 2^32
+    int sq = q0 % W;  // ring slot of row q, advanced with q (a modulo per row and warp cost ~25 % of the instructions)
+    for (int q = q0; q < q1 + k; ++q, sq = (sq + 1 == W) ? 0 : sq + 1) {  // the last k steps only emit masks
       if (q < q1) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(kImpThreads) impulse_fused_kernel(const float*
           }
         if (q + 1 < q1) load_row(q + 1);
         __syncthreads();
-        float* su = s_u + (q % W) * nbmax;
+        float* su = s_u + sq * nbmax;
         for (int b = tid; b < nb; b += kImpThreads) {
           const int j0 = b * n, j1 = (j0 + n < R) ? j0 + n : R;
           // plain sums (four interleaved float32 partial sums); a NaN member shows in the result, the block is then redone
@@ -303,9 +305,10 @@ __global__ void __launch_bounds__(kImpThreads) impulse_fused_kernel(const float*
       __syncthreads();  // block means of row q visible; s_row free for the next row
       const int p = q - k;  // output ping: its window p - k .. p + k is in the ring (rows outside the ping axis: missing)
       if (p >= p0 && p < p1) {
-        const float* u0 = s_u + (p % W) * nbmax;
-        const float* uf = (p + k < Pi) ? s_u + ((p + k) % W) * nbmax : nullptr;
-        const float* ub = (p - k >= 0) ? s_u + ((p - k) % W) * nbmax : nullptr;
+        // rows p + k, p, p - k sit in slots sq, sq - k, sq - 2 k = sq + 1 (mod W = 2 k + 1)
+        const float* u0 = s_u + (sq >= k ? sq - k : sq - k + W) * nbmax;
+        const float* uf = (p + k < Pi) ? s_u + sq * nbmax : nullptr;
+        const float* ub = (p - k >= 0) ? s_u + (sq + 1 == W ? 0 : sq + 1) * nbmax : nullptr;
         auto flag = [&](int bb) -> unsigned {
           if (bb >= nb) return 0u;
           const float x = u0[bb];
@@ -316,7 +319,7 @@ __global__ void __launch_bounds__(kImpThreads) impulse_fused_kernel(const float*
         };
         unsigned char* mrow = mask + (c * P + p) * (long long)R;
         for (int j0 = tid << 4; j0 < R; j0 += kImpThreads << 4) {
-          const int b = j0 / n, t = n - (j0 - b * n);  // samples j0 .. j0 + t - 1 belong to block b, the rest to b + 1
+          const int b = (int)__umulhi((unsigned)j0, ninv), t = n - (j0 - b * n);  // samples j0 .. j0 + t - 1: block b, the rest: b + 1
           const unsigned f0 = flag(b), f1 = (t < 16) ? flag(b + 1) : 0u;
           unsigned wv[4];
 #pragma unroll
