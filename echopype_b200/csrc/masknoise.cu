@@ -967,7 +967,11 @@ __global__ void __launch_bounds__(kStripThreads, 2)
     const int ifull = (2 * k + 1) * (2 * w + 1);
     const float inv_full = 1.f / (float)ifull;
     // owners of the first / last w columns of the sliced axis also write the mirrored prefix
-    const bool mirror = !kDepth && active && (n0 - m0 + 1 <= w || R - 1 - (n0 + kStripCols - 1) <= w);
+    // columns of this WARP among the first w (sources of the mirrored entries before the axis: [m0, m0 + w - 1]) and among
+    // the last w before the final column ([R - 1 - w, R - 2]); empty ranges (lo > hi) for the other warps / depth windows
+    const int wx0 = col0 + wid * 32 * kStripCols, wx1 = (wx0 + 32 * kStripCols - 1 < R - 1) ? wx0 + 32 * kStripCols - 1 : R - 1;
+    const int mir_lo0 = kDepth ? 1 : (m0 > wx0 ? m0 : wx0), mir_lo1 = kDepth ? 0 : (m0 + w - 1 < wx1 ? m0 + w - 1 : wx1);
+    const int mir_hi0 = kDepth ? 1 : (R - 1 - w > wx0 ? R - 1 - w : wx0), mir_hi1 = kDepth ? 0 : (R - 2 < wx1 ? R - 2 : wx1);
     const double* const sph = my_pre + (w >> 4);
     const double* const spl = my_pre + ((-w - 1) >> 4);
     // software pipeline: the entering and leaving rows of the NEXT ping are requested right after this ping's were used
@@ -1043,20 +1047,18 @@ __global__ void __launch_bounds__(kStripThreads, 2)
             }
           }
         }
-        __syncwarp();
-        if (mirror) {
+        __syncwarp();  // the warp's own entries are visible to its lanes
+        // Mirrored entries: the 32 lanes of a warp copy the entries of the warp's columns among the first / last w of the
+        // sliced axis (the owners writing their 16 columns each kept the two edge warps ~30 % behind the others)
+        if (mir_lo0 <= mir_lo1) {  // warp-uniform
+          const double base2 = 2.0 * s_pre[slot(m0 - 1 - col0)];
+          for (int x = mir_lo0 + lane; x <= mir_lo1; x += 32) s_pre[slot(2 * m0 - 2 - x - col0)] = base2 - s_pre[slot(x - col0)];
+        }
+        if (mir_hi0 <= mir_hi1) {
           double tot2 = 0.0;
           for (int i = 0; i < NW; ++i) tot2 += s_ws[i];
           tot2 *= 2.0;
-          const double base2 = 2.0 * s_pre[slot(m0 - 1 - col0)];
-          double acc = off;
-#pragma unroll
-          for (int j = 0; j < kStripCols; ++j) {
-            acc += cs[j];
-            const int i1 = n0 + j - m0 + 1, i2 = R - 1 - (n0 + j);
-            if (i1 >= 1 && i1 <= w) s_pre[slot(m0 - i1 - 1 - col0)] = base2 - acc;
-            if (i2 >= 1 && i2 <= w) s_pre[slot(R - 1 + i2 - col0)] = tot2 - acc;
-          }
+          for (int x = mir_hi0 + lane; x <= mir_hi1; x += 32) s_pre[slot(2 * R - 2 - x - col0)] = tot2 - s_pre[slot(x - col0)];
         }
       }
       if (chg) {  // CTA-uniform and rare: a deficit changed, rebuild the count prefix with the same scan
@@ -1087,17 +1089,12 @@ __global__ void __launch_bounds__(kStripThreads, 2)
           }
         }
         __syncwarp();
-        if (mirror) {
-          const int tot2 = 2 * ctot, base2 = 2 * s_cnt[slot(m0 - 1 - col0)];
-          int acc = coff;
-#pragma unroll
-          for (int j = 0; j < kStripCols; ++j) {
-            acc += my_cc[j * kStripThreads];
-            const int i1 = n0 + j - m0 + 1, i2 = R - 1 - (n0 + j);
-            if (i1 >= 1 && i1 <= w) s_cnt[slot(m0 - i1 - 1 - col0)] = base2 - acc;
-            if (i2 >= 1 && i2 <= w) s_cnt[slot(R - 1 + i2 - col0)] = tot2 - acc;
-          }
+        if (mir_lo0 <= mir_lo1) {
+          const int base2 = 2 * s_cnt[slot(m0 - 1 - col0)];
+          for (int x = mir_lo0 + lane; x <= mir_lo1; x += 32) s_cnt[slot(2 * m0 - 2 - x - col0)] = base2 - s_cnt[slot(x - col0)];
         }
+        if (mir_hi0 <= mir_hi1)
+          for (int x = mir_hi0 + lane; x <= mir_hi1; x += 32) s_cnt[slot(2 * R - 2 - x - col0)] = 2 * ctot - s_cnt[slot(x - col0)];
       }
       __syncthreads();
       // range windows, pooled Sv, mask: 16 outputs per thread
