@@ -1351,47 +1351,39 @@ namespace {
 // A channel's depth rows are "uniform" when every ping has the same depth at a column wherever its depth is defined, and
 // samples without a depth (NaN: the padding of shorter pings, calibrate/range.py:143-148) carry no Sv either - such
 // samples are members of no window in the reference (NaN fails both comparisons) and contribute nothing here (NaN Sv).
-// Pass 1: the channel's reference row = column-wise maximum of the defined depths (ordered-int atomic maximum).
+// One pass over depth and Sv: column-wise maximum AND minimum of the defined depths (ordered-int atomics; uniform <=>
+// they agree in every column) and the Sv condition; the decode kernel compares the two and leaves the reference row.
 __device__ __forceinline__ int float_order(float f) {
   const int i = __float_as_int(f);
   return i >= 0 ? i : i ^ 0x7fffffff;
 }
-__global__ void __launch_bounds__(256) depth_ref_row_kernel(const float* __restrict__ depth, long long P, int R, int pchunk,
-                                                            int* __restrict__ ref_ord) {
+__global__ void __launch_bounds__(256) depth_ref_row_kernel(const float* __restrict__ depth, const float* __restrict__ Sv, long long P,
+                                                            int R, int pchunk, int* __restrict__ max_ord, int* __restrict__ min_ord,
+                                                            int* __restrict__ mismatch) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const long long c = blockIdx.z;
   const long long p0 = (long long)blockIdx.y * pchunk, p1 = (p0 + pchunk < P) ? p0 + pchunk : P;
   if (n >= R) return;
-  float m = -CUDART_INF_F;
-  for (long long p = p0; p < p1; ++p) m = fmaxf(m, __ldg(depth + (c * P + p) * R + n));  // fmaxf skips NaN
-  atomicMax(ref_ord + c * R + n, float_order(m));
+  float mx = -CUDART_INF_F, mn = CUDART_INF_F;
+  bool bad = false;
+  for (long long p = p0; p < p1; ++p) {
+    const float d = __ldg(depth + (c * P + p) * R + n), v = __ldg(Sv + (c * P + p) * R + n);
+    mx = fmaxf(mx, d), mn = fminf(mn, d);  // both skip NaN
+    bad |= !(d == d) && (v == v);          // an Sv without a depth
+  }
+  atomicMax(max_ord + c * R + n, float_order(mx));
+  atomicMin(min_ord + c * R + n, float_order(mn));
+  if (bad) *mismatch = 1;
 }
-__global__ void __launch_bounds__(256) depth_ref_decode_kernel(int* __restrict__ ref, long long total) {
+__global__ void __launch_bounds__(256) depth_ref_decode_kernel(int* __restrict__ ref, const int* __restrict__ min_ord, long long total,
+                                                               int* __restrict__ mismatch) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int o = ref[i];
-  const float f = __int_as_float(o >= 0 ? o : o ^ 0x7fffffff);
+  const int o = ref[i], q = min_ord[i];
+  const float f = __int_as_float(o >= 0 ? o : o ^ 0x7fffffff), g = __int_as_float(q >= 0 ? q : q ^ 0x7fffffff);
+  if (f != -CUDART_INF_F && f != g) *mismatch = 1;  // two pings disagree on the depth of this column
   ref[i] = __float_as_int(f == -CUDART_INF_F ? CUDART_NAN_F : f);  // a column without any depth
 }
-// Pass 2: *mismatch != 0 when a defined depth differs from the reference row, or a sample without depth has an Sv
-__global__ void __launch_bounds__(256) depth_rows_uniform_kernel(const float* __restrict__ depth, const float* __restrict__ Sv,
-                                                                 const float* __restrict__ ref, long long P, long long R4,
-                                                                 long long total4, int* __restrict__ mismatch) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const float4* d4 = reinterpret_cast<const float4*>(depth);
-  const float4* s4 = reinterpret_cast<const float4*>(Sv);
-  const float4* r4 = reinterpret_cast<const float4*>(ref);
-  bool bad = false;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += stride) {
-    const long long row = i / R4, c = row / P;
-    const float4 a = __ldg(d4 + i), v = __ldg(s4 + i), b = __ldg(r4 + c * R4 + (i - row * R4));
-    const float av[4] = {a.x, a.y, a.z, a.w}, vv[4] = {v.x, v.y, v.z, v.w}, bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) bad |= (av[q] == av[q]) ? (av[q] != bv[q]) : (vv[q] == vv[q]);
-  }
-  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) *mismatch = 1;
-}
-
 // per (channel, column): the index interval of the samples with |depth - d| <= depth_bin in the channel's depth row
 // (clean/utils.py:86-93, float64 comparisons of the float32 depths; NaN depths count as beyond every value) as
 // prefix slots of the strip kernel (slot(i0 - 1), slot(i1 - 1)) and its width i1 - i0; width 0 where the column's own
@@ -1439,18 +1431,18 @@ __global__ void __launch_bounds__(256) depth_window_table_kernel(const float* __
 
 extern "C" int epb_depth_rows_uniform(const float* depth, const float* Sv, float* ref_rows, int* mismatch, epb_i64 C, epb_i64 P,
                                       epb_i64 R, void* stream) {
-  EPB_REQUIRE(depth && Sv && ref_rows && mismatch && C > 0 && C < 65536 && P > 0 && R > 0 && R % 4 == 0, "bad pointer / shape");
-  EPB_REQUIRE((((uintptr_t)depth | (uintptr_t)Sv | (uintptr_t)ref_rows) % 16) == 0, "arrays must be 16-byte aligned");
+  EPB_REQUIRE(depth && Sv && ref_rows && mismatch && C > 0 && C < 65536 && P > 0 && R > 0, "bad pointer / shape");
   cudaStream_t s = (cudaStream_t)stream;
-  if (cudaMemsetAsync(mismatch, 0, sizeof(int), s) != cudaSuccess || cudaMemsetAsync(ref_rows, 0x80, (size_t)(C * R) * 4, s) != cudaSuccess)
-    return epb_check_launch("epb_depth_rows_uniform(memset)");  // 0x80808080: below every ordered float
+  int* mx = reinterpret_cast<int*>(ref_rows);
+  int* mn = mx + C * R;  // second half of ref_rows: scratch for the column minima
+  if (cudaMemsetAsync(mismatch, 0, sizeof(int), s) != cudaSuccess || cudaMemsetAsync(mx, 0x80, (size_t)(C * R) * 4, s) != cudaSuccess ||
+      cudaMemsetAsync(mn, 0x7f, (size_t)(C * R) * 4, s) != cudaSuccess)  // 0x80808080 / 0x7f7f7f7f: below / above every ordered float
+    return epb_check_launch("epb_depth_rows_uniform(memset)");
   const int pchunk = 256;
   dim3 g1((unsigned)((R + 255) / 256), (unsigned)((P + pchunk - 1) / pchunk), (unsigned)C);
   EPB_REQUIRE(g1.y < 65536, "too many pings");
-  depth_ref_row_kernel<<<g1, 256, 0, s>>>(depth, P, (int)R, pchunk, reinterpret_cast<int*>(ref_rows));
-  depth_ref_decode_kernel<<<(unsigned)((C * R + 255) / 256), 256, 0, s>>>(reinterpret_cast<int*>(ref_rows), C * R);
-  const long long total4 = C * P * (R / 4), cap = (long long)epb_num_sms() * 8, gb = (total4 + 255) / 256;
-  depth_rows_uniform_kernel<<<(unsigned)(gb < cap ? gb : cap), 256, 0, s>>>(depth, Sv, ref_rows, P, R / 4, total4, mismatch);
+  depth_ref_row_kernel<<<g1, 256, 0, s>>>(depth, Sv, P, (int)R, pchunk, mx, mn, mismatch);
+  depth_ref_decode_kernel<<<(unsigned)((C * R + 255) / 256), 256, 0, s>>>(mx, mn, C * R, mismatch);
   return epb_check_launch("epb_depth_rows_uniform");
 }
 

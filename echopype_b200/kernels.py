@@ -370,7 +370,7 @@ def transient_noise_mask_depth(Sv, depth, C, P, R, dmin, dmax, depth_bin, exclud
     k = int(num_side_pings)
     if R % 16 == 0 and R <= 4096 and P < (1 << 30) and (2 * k + 1) * R < (1 << 24) and depth.data_ptr() % 16 == 0 and Sv.data_ptr() % 16 == 0:
         flag = torch.empty(1, dtype=torch.int32, device=Sv.device)
-        ref = torch.empty((C, R), dtype=torch.float32, device=Sv.device)
+        ref = torch.empty((2, C, R), dtype=torch.float32, device=Sv.device)  # [0]: reference rows, [1]: scratch
         _lib.call("epb_depth_rows_uniform", ptr(depth), ptr(Sv), ptr(ref), ptr(flag), C, P, R, stream())
         if int(flag.item()) == 0:
             tables = torch.empty(C * 3 * R, dtype=torch.int16, device=Sv.device)

@@ -307,8 +307,8 @@ int epb_transient_noise_mask_depth(const float* Sv, const float* depth, double* 
  * index interval in every ping and the pooled value is a difference of the prefix of the running column sums (the
  * single-pass strip kernel of epb_transient_noise_mask with per-column interval ends): one pass over Sv, no [C,P,R+1]
  * scratch - cfg2: milliseconds instead of 1.6 s.
- * epb_depth_rows_uniform writes the channels' reference depth rows (ref_rows [C,R] float32: column-wise maximum of the
- * defined depths) and sets *mismatch (device int) to non-zero when the volume is not uniform (then use
+ * epb_depth_rows_uniform writes the channels' reference depth rows (ref_rows [2,C,R] float32: [0] = column-wise maximum
+ * of the defined depths, [1] = scratch) and sets *mismatch (device int) to non-zero when the volume is not uniform (then use
  * epb_transient_noise_mask_depth).  epb_transient_noise_mask_depth_uniform: ref_rows from that call, tables [C,3,R]
  * uint16 scratch; returns EPB_E_UNSUPPORTED unless R % 16 == 0, R <= 4096 and the arrays are 16-byte aligned. */
 int epb_depth_rows_uniform(const float* depth, const float* Sv, float* ref_rows, int* mismatch, epb_i64 C, epb_i64 P, epb_i64 R,

@@ -404,7 +404,7 @@ def test_transient_depth_windows_uniform_rows(ep, C, P, R, k, depth_bin, excl, n
         depth[0, P // 3, R // 2:] = np.nan
         dt[0, P // 3, R // 2:] = float("nan")
     flag = torch.empty(1, dtype=torch.int32, device="cuda")
-    ref = torch.empty((C, R), dtype=torch.float32, device="cuda")
+    ref = torch.empty((2, C, R), dtype=torch.float32, device="cuda")
     kernels._lib.call("epb_depth_rows_uniform", kernels.ptr(dt), kernels.ptr(Svt), kernels.ptr(ref), kernels.ptr(flag), C, P, R, kernels.stream())
     assert int(flag.item()) == 0
     mask, pl = kernels.transient_noise_mask_depth(Svt, dt, C, P, R, np.nanmin(depth), np.nanmax(depth), depth_bin, excl, k, thr, want_pooled=True)
