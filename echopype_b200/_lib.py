@@ -77,7 +77,7 @@ SIGNATURES = {
     "epb_impulse_noise_mask": (c_int, [vp, vp, vp, vp, i64, i64, i64, c_int, c_int, c_float, vp]),
     "epb_transient_noise_mask_depth": (c_int, [vp, vp, vp, vp, vp, vp, i64, i64, i64, c_double, c_double, c_double, c_double, c_int, c_float, vp]),
     "epb_depth_rows_uniform": (c_int, [vp, vp, vp, vp, i64, i64, i64, vp]),
-    "epb_transient_noise_mask_depth_uniform": (c_int, [vp, vp, vp, vp, vp, vp, i64, i64, i64, c_double, c_double, c_double, c_double, c_int, c_float, vp]),
+    "epb_transient_noise_mask_depth_uniform": (c_int, [vp, vp, vp, vp, vp, vp, i64, i64, i64, c_double, c_double, c_double, c_double, c_int, c_float, i64, vp]),
     "epb_impulse_noise_mask_depth": (c_int, [vp, vp, vp, c_int, vp, vp, vp, vp, i64, i64, i64, c_int, c_float, vp, vp]),
     "epb_transient_noise_mask": (c_int, [vp, vp, vp, vp, vp, i64, i64, i64, c_int, c_int, c_int, c_float, vp]),
     "epb_transient_noise_mask_median": (c_int, [vp, vp, vp, vp, i64, i64, i64, c_int, c_int, c_int, c_float, vp]),

@@ -1389,7 +1389,7 @@ __global__ void __launch_bounds__(256) depth_ref_decode_kernel(int* __restrict__
 // prefix slots of the strip kernel (slot(i0 - 1), slot(i1 - 1)) and its width i1 - i0; width 0 where the column's own
 // conditions fail (:78-84: d - bin >= min depth, d + bin <= max depth, d - bin >= exclude_above; NaN fails all)
 __global__ void __launch_bounds__(256) depth_window_table_kernel(const float* __restrict__ ref, int R, double dmin,
-                                                                 double dmax, double bin, double exclude_above, int TL,
+                                                                 double dmax, double bin, double exclude_above, int TL, int col0,
                                                                  unsigned short* __restrict__ wtab, long long total) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -1421,10 +1421,12 @@ __global__ void __launch_bounds__(256) depth_window_table_kernel(const float* __
     }
     i1 = lo;
   }
-  auto slot = [&](int x) { return (x & 15) * kStripPitch + (x >> 4) + TL; };
+  // columns before col0 (the caller's bound: shallower than every window) are not part of the strip: no window there
+  if (n < col0 || i0 < col0) i0 = i1 = col0;
+  auto slot = [&](int x) { return (x & 15) * kStripPitch + (x >> 4) + TL; };  // x relative to col0
   unsigned short* t = wtab + c * 3 * (long long)R;
-  t[n] = (unsigned short)slot(i0 - 1);
-  t[R + n] = (unsigned short)slot(i1 - 1);
+  t[n] = (unsigned short)slot(i0 - 1 - col0);
+  t[R + n] = (unsigned short)slot(i1 - 1 - col0);
   t[2 * R + n] = (unsigned short)(i1 - i0);
 }
 }  // namespace
@@ -1449,10 +1451,12 @@ extern "C" int epb_depth_rows_uniform(const float* depth, const float* Sv, float
 extern "C" int epb_transient_noise_mask_depth_uniform(const float* Sv, const float* depth, const float* ref_rows, unsigned short* tables, unsigned char* mask,
                                                       float* pooled_Sv, epb_i64 C, epb_i64 P, epb_i64 R, double depth_min,
                                                       double depth_max, double depth_bin, double exclude_above, int num_side_pings,
-                                                      float threshold, void* stream) {
+                                                      float threshold, epb_i64 first_column, void* stream) {
   EPB_REQUIRE(Sv && depth && ref_rows && tables && mask, "NULL pointer");
   EPB_REQUIRE(C > 0 && P > 0 && R > 0 && num_side_pings >= 0, "bad shape / argument");
-  const int threads = (int)((R / kStripCols + 31) / 32 * 32), TL = 1;
+  EPB_REQUIRE(first_column >= 0 && first_column < R && first_column % 16 == 0, "first_column must be a multiple of 16 inside the row");
+  const int col0 = (int)first_column;
+  const int threads = (int)(((R - col0) / kStripCols + 31) / 32 * 32), TL = 1;
   if (!(R % 16 == 0 && R <= kStripThreads * kStripCols && P < (1LL << 30) && ((uintptr_t)Sv % 16) == 0 && ((uintptr_t)mask % 16) == 0 &&
         ((uintptr_t)pooled_Sv % 16) == 0 && ((uintptr_t)tables % 16) == 0 && (long long)(2 * num_side_pings + 1) * R < (1LL << 24) &&
         TL + threads + 1 <= kStripPitch)) {
@@ -1461,7 +1465,7 @@ extern "C" int epb_transient_noise_mask_depth_uniform(const float* Sv, const flo
   }
   const long long totc = C * R;
   depth_window_table_kernel<<<(unsigned)((totc + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ref_rows, (int)R, depth_min, depth_max, depth_bin,
-                                                                                               exclude_above, TL, tables, totc);
+                                                                                               exclude_above, TL, col0, tables, totc);
   const long long want = ((long long)epb_num_sms() * 4 + C - 1) / C;
   long long chunk = (P + want - 1) / want;
   const long long min_chunk = 8LL * (2 * num_side_pings + 1);
@@ -1474,7 +1478,7 @@ extern "C" int epb_transient_noise_mask_depth_uniform(const float* Sv, const flo
     return epb_check_launch("epb_transient_noise_mask_depth_uniform(smem)");
   const long long nstrips = nchunks * C, capg = (long long)epb_num_sms() * 2;
   kern<<<(unsigned)(nstrips < capg ? nstrips : capg), threads, sm, (cudaStream_t)stream>>>(
-      Sv, nullptr, mask, pooled_Sv, P, (int)R, 0, num_side_pings, threshold, (int)chunk, (int)nchunks, nstrips, TL, tables, depth);
+      Sv, nullptr, mask, pooled_Sv, P, (int)R, col0, num_side_pings, threshold, (int)chunk, (int)nchunks, nstrips, TL, tables, depth);
   return epb_check_launch("epb_transient_noise_mask_depth_uniform");
 }
 

@@ -368,17 +368,23 @@ def transient_noise_mask_depth(Sv, depth, C, P, R, dmin, dmax, depth_bin, exclud
     channel (checked on the device) take the single-pass strip kernel; others the per-sample bisection kernels, which need
     12 bytes of scratch per sample."""
     k = int(num_side_pings)
-    if R % 16 == 0 and R <= 4096 and P < (1 << 30) and (2 * k + 1) * R < (1 << 24) and depth.data_ptr() % 16 == 0 and Sv.data_ptr() % 16 == 0:
+    if R % 16 == 0 and P < (1 << 30) and (2 * k + 1) * R < (1 << 24) and depth.data_ptr() % 16 == 0 and Sv.data_ptr() % 16 == 0:
         flag = torch.empty(1, dtype=torch.int32, device=Sv.device)
         ref = torch.empty((2, C, R), dtype=torch.float32, device=Sv.device)  # [0]: reference rows, [1]: scratch
         _lib.call("epb_depth_rows_uniform", ptr(depth), ptr(Sv), ptr(ref), ptr(flag), C, P, R, stream())
-        if int(flag.item()) == 0:
+        # columns shallower than exclude_above in every channel belong to no window (d - bin >= exclude_above): the strip
+        # starts at the 16-aligned column at or before the first deeper one (one host read together with the flag)
+        deep = ref[0] >= float(exclude_above)
+        first = torch.where(deep.any(dim=1), deep.float().argmax(dim=1), torch.full((C,), R - 16, device=Sv.device)).min()
+        nonuniform, first = (int(v) for v in torch.stack([flag[0].long(), first.long()]).tolist())
+        col0 = (min(first, R - 16) // 16) * 16
+        if nonuniform == 0 and R - col0 <= 4096:
             tables = torch.empty(C * 3 * R, dtype=torch.int16, device=Sv.device)
             mask = torch.empty((C, P, R), dtype=torch.uint8, device=Sv.device)
             pooled = torch.empty((C, P, R), dtype=torch.float32, device=Sv.device) if want_pooled else None
             _lib.call("epb_transient_noise_mask_depth_uniform", ptr(Sv), ptr(depth), ptr(ref), ptr(tables), ptr(mask), ptr(pooled),
                       C, P, R, ctypes.c_double(float(dmin)), ctypes.c_double(float(dmax)), ctypes.c_double(float(depth_bin)),
-                      ctypes.c_double(float(exclude_above)), k, ctypes.c_float(float(threshold)), stream())
+                      ctypes.c_double(float(exclude_above)), k, ctypes.c_float(float(threshold)), col0, stream())
             return mask, pooled
     pre = torch.empty((C, P, R + 1), dtype=torch.float64, device=Sv.device)
     cnt = torch.empty((C, P, R + 1), dtype=torch.int32, device=Sv.device)

@@ -310,13 +310,15 @@ int epb_transient_noise_mask_depth(const float* Sv, const float* depth, double* 
  * epb_depth_rows_uniform writes the channels' reference depth rows (ref_rows [2,C,R] float32: [0] = column-wise maximum
  * of the defined depths, [1] = scratch) and sets *mismatch (device int) to non-zero when the volume is not uniform (then use
  * epb_transient_noise_mask_depth).  epb_transient_noise_mask_depth_uniform: ref_rows from that call, tables [C,3,R]
- * uint16 scratch; returns EPB_E_UNSUPPORTED unless R % 16 == 0, R <= 4096 and the arrays are 16-byte aligned. */
+ * uint16 scratch; first_column: 0, or a multiple of 16 not beyond the first column of ref_rows that is at or below
+ * exclude_above in any channel (shallower columns belong to no window: they are then neither loaded nor scanned);
+ * returns EPB_E_UNSUPPORTED unless R % 16 == 0, R - first_column <= 4096 and the arrays are 16-byte aligned. */
 int epb_depth_rows_uniform(const float* depth, const float* Sv, float* ref_rows, int* mismatch, epb_i64 C, epb_i64 P, epb_i64 R,
                            void* stream);
 int epb_transient_noise_mask_depth_uniform(const float* Sv, const float* depth, const float* ref_rows, unsigned short* tables,
                                            unsigned char* mask, float* pooled_Sv, epb_i64 C, epb_i64 P, epb_i64 R,
                                            double depth_min, double depth_max, double depth_bin, double exclude_above,
-                                           int num_side_pings, float threshold, void* stream);
+                                           int num_side_pings, float threshold, epb_i64 first_column, void* stream);
 
 /* ---- raw power ingest (convert/parse_base.py:24,302 `power = counts.astype(float32) * INDEX2POWER`, :686-730
  *      pad_shorter_ping): n int16 counts -> float32 dB, -32768 (padding marker) -> NaN. -------------------------- */
