@@ -821,6 +821,7 @@ __global__ void __launch_bounds__(128) transient_median_depth_kernel(const float
 //  * the per-ping chain (scan, two barriers) is shorter than a DRAM round trip: the three rows of the ping kPrefetch
 //    steps ahead are prefetched into L2 by TMA (cp.async.bulk.prefetch.L2, one instruction each), so that the register
 //    loads issued one ping ahead hit L2
+//  * (three CTAs per SM at 192 threads x 112 registers, for rows of <= 3072 columns, measured SLOWER: 8.5 vs 6.6 ms - spills)
 //  * NaN detection is one float add per sample (the sum of the raw dB values is NaN iff one of them is); NaN -> 0 by
 //    fmaxf(ex2(NaN), 0)
 // Reading the entering, the leaving and the centre row is all the traffic there is.
@@ -1457,7 +1458,7 @@ extern "C" int epb_transient_noise_mask_depth_uniform(const float* Sv, const flo
   EPB_REQUIRE(first_column >= 0 && first_column < R && first_column % 16 == 0, "first_column must be a multiple of 16 inside the row");
   const int col0 = (int)first_column;
   const int threads = (int)(((R - col0) / kStripCols + 31) / 32 * 32), TL = 1;
-  if (!(R % 16 == 0 && R <= kStripThreads * kStripCols && P < (1LL << 30) && ((uintptr_t)Sv % 16) == 0 && ((uintptr_t)mask % 16) == 0 &&
+  if (!(R % 16 == 0 && R - col0 <= kStripThreads * kStripCols && P < (1LL << 30) && ((uintptr_t)Sv % 16) == 0 && ((uintptr_t)mask % 16) == 0 &&
         ((uintptr_t)pooled_Sv % 16) == 0 && ((uintptr_t)tables % 16) == 0 && (long long)(2 * num_side_pings + 1) * R < (1LL << 24) &&
         TL + threads + 1 <= kStripPitch)) {
     epb_set_error("%s: %s", __func__, "needs range_sample % 16 == 0, range_sample <= 4096, 16-byte aligned arrays");
