@@ -372,12 +372,15 @@ def transient_noise_mask_depth(Sv, depth, C, P, R, dmin, dmax, depth_bin, exclud
         flag = torch.empty(1, dtype=torch.int32, device=Sv.device)
         ref = torch.empty((2, C, R), dtype=torch.float32, device=Sv.device)  # [0]: reference rows, [1]: scratch
         _lib.call("epb_depth_rows_uniform", ptr(depth), ptr(Sv), ptr(ref), ptr(flag), C, P, R, stream())
-        # columns shallower than exclude_above in every channel belong to no window (d - bin >= exclude_above): the strip
-        # starts at the 16-aligned column at or before the first deeper one (one host read together with the flag)
-        deep = ref[0] >= float(exclude_above)
-        first = torch.where(deep.any(dim=1), deep.float().argmax(dim=1), torch.full((C,), R - 16, device=Sv.device)).min()
-        nonuniform, first = (int(v) for v in torch.stack([flag[0].long(), first.long()]).tolist())
-        col0 = (min(first, R - 16) // 16) * 16
+        nonuniform = int(flag.item())
+        col0 = 0
+        if nonuniform == 0:
+            # columns shallower than exclude_above in every channel belong to no window (d - bin >= exclude_above): the strip
+            # starts at the 16-aligned column at or before the first deeper one (64 KB of reference rows read back)
+            with np.errstate(invalid="ignore"):
+                deep = ref[0].cpu().numpy() >= float(exclude_above)
+            first = min((int(np.argmax(row)) if row.any() else R - 16) for row in deep)
+            col0 = (min(first, R - 16) // 16) * 16
         if nonuniform == 0 and R - col0 <= 4096:
             tables = torch.empty(C * 3 * R, dtype=torch.int16, device=Sv.device)
             mask = torch.empty((C, P, R), dtype=torch.uint8, device=Sv.device)
