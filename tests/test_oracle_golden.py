@@ -355,6 +355,16 @@ def test_geodesic_known_values():
     assert ogrid.geodesic_m(0, 0, 0, 1) == pytest.approx(111319.4908, abs=1e-3)  # 1 deg of equator
     assert ogrid.geodesic_m(0, 0, 1, 0) == pytest.approx(110574.3886, abs=1e-3)  # meridian 0->1 deg
     assert ogrid.geodesic_m(42.0, -124.0, 42.0, -124.0) == 0.0
+    # geopy's own documented example (geopy.distance docs: geodesic(newport_ri, cleveland_oh) -> 866.4554329098687 km =
+    # 538.390445368 miles; Karney's algorithm via geographiclib, the function the reference calls in
+    # commongrid/utils.py:160-207): Vincenty's inverse agrees to ~5 micrometres
+    newport_ri, cleveland_oh = (41.49008, -71.312796), (41.499498, -81.695391)
+    assert ogrid.geodesic_m(*newport_ri, *cleveland_oh) == pytest.approx(866455.4329098687, abs=1e-4)
+    from echopype_b200.commongrid.utils import geodesic_nmi  # the product's host function (no device needed)
+
+    got = float(geodesic_nmi(np.array([newport_ri[0]]), np.array([newport_ri[1]]), np.array([cleveland_oh[0]]), np.array([cleveland_oh[1]]))[0])
+    assert got * 1852.0 == pytest.approx(866455.4329098687, abs=1e-4)
+    assert got * 1852.0 / 1609.344 == pytest.approx(538.390445368, abs=1e-8)
 
 
 # ------------------------------------------------------------- closed-form guards for K1 (unpinned) ----
