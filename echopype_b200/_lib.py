@@ -65,6 +65,7 @@ SIGNATURES = {
     "epb_synth_fill_i16": (c_int, [vp, i64, i64, i64, c_ulonglong, i64, c_uint, vp]),
     "epb_pipeline_workspace_bytes": (i64, [i64, i64, c_int]),
     "epb_pipeline_workspace_bytes_r": (i64, [i64, i64, i64, c_int]),
+    "epb_set_grid_reserve": (c_int, [c_int]),
     "epb_pipeline_smem_bytes": (i64, [i64, c_int, c_int, c_int, c_int]),
     "epb_add_depth": (c_int, [vp, epb_cp, epb_cp, vp, i64, i64, i64, vp]),
     "epb_freq_diff_mask": (c_int, [vp, c_int, c_int, c_int, c_float, vp, i64, i64, i64, vp]),

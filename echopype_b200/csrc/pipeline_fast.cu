@@ -13,6 +13,16 @@ int epb_fast_launch_f32kb(const void* pr, int T, int G, int noise, int threads, 
 int epb_fast_launch_f32kc(const void* pr, int T, int G, int noise, int threads, size_t smem, cudaStream_t s);
 int epb_fast_launch_f32w(const void* pr, int T, int G, int noise, int threads, size_t smem, cudaStream_t s);
 
+static int g_grid_reserve = 0;
+int epb_grid_reserve() { return g_grid_reserve; }
+// SMs the persistent fused kernel leaves free (process-wide; 0 by default): with a ping-sharded plan whose straddle exchange
+// runs on a side stream, the NCCL send / recv kernels of step s need somewhere to run while the fused kernel of step s + 1
+// holds the rest of the chip.
+extern "C" int epb_set_grid_reserve(int sms) {
+  g_grid_reserve = sms < 0 ? 0 : sms;
+  return 0;
+}
+
 namespace {
 constexpr int kMaxPingNum = 64;  // two-sweep mode: up to 8 sub-tiles of 8 rows
 // sub-tiles per noise tile and rows per sub-tile

@@ -33,6 +33,8 @@
 #pragma once
 #include "pipeline_common.cuh"
 
+int epb_grid_reserve();  // pipeline_fast.cu
+
 namespace {
 using namespace epb;
 
@@ -1015,7 +1017,8 @@ int launch_fast(const FastParams& pr, int threads, size_t smem, cudaStream_t s) 
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) return -1;
-  long long grid = (long long)epb_num_sms() * per_sm;
+  // (epb_set_grid_reserve: SMs left to concurrent kernels of other streams, e.g. the NCCL exchange of the previous step)
+  long long grid = (long long)(epb_num_sms() > epb_grid_reserve() ? epb_num_sms() - epb_grid_reserve() : 1) * per_sm;
   if (grid > pr.ntiles) grid = pr.ntiles;
   kern<<<(unsigned)grid, threads, smem, s>>>(pr);
   return 0;

@@ -22,6 +22,7 @@ straddle shard boundaries (:func:`straddle_reduce`).  Two scalar all-reduces (ma
 """
 
 import ctypes
+import os
 from typing import Optional, Sequence
 
 import numpy as np
@@ -300,7 +301,11 @@ class FusedPlan:
         # is persistent and holds every SM (one 216 KB CTA each), so the NCCL send/recv kernels of step s cannot start
         # before the fused kernel of step s + 1 retires its CTAs, and the small kernels of both streams interleave.  Off by
         # default; the result is identical either way (bench.py verification, N > 1).
-        self.async_exchange = False
+        self.async_exchange = os.environ.get("EPB_ASYNC_EXCHANGE", "0") == "1" and group is not None
+        if self.async_exchange:  # experiment knob: leave SMs to the NCCL kernels of the side stream
+            from . import _lib as _l
+
+            _l.call("epb_set_grid_reserve", int(os.environ.get("EPB_GRID_RESERVE", "4")))
         self._comm_stream = None
         self._pending = None  # event: the side-stream work of the last run() is complete
 

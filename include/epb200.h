@@ -237,6 +237,9 @@ epb_i64 epb_pipeline_workspace_bytes(epb_i64 C, epb_i64 P, int ping_num);
  * smaller workspace such volumes take the general kernel. */
 epb_i64 epb_pipeline_workspace_bytes_r(epb_i64 C, epb_i64 P, epb_i64 R, int ping_num);
 epb_i64 epb_pipeline_smem_bytes(epb_i64 R, int nR, int tile, int do_noise, int staged);
+/* SMs the persistent fused kernel leaves free from now on (process-wide, default 0): room for kernels of other streams
+ * (the NCCL neighbour exchange of the previous step of a ping-sharded job) next to the persistent grid. */
+int epb_set_grid_reserve(int sms);
 
 /* ---- ping-sharded execution: pack / unpack around the ONE all-reduce(sum) that merges the ping bins two
  *      ranks share.  acc [C,nXl,nR,4] float64 (this rank's window of the global ping bins); buf [world][2*C*nR*4 + 1]
