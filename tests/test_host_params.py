@@ -61,3 +61,19 @@ def test_ek80_params(mode, encode):
         gain = g - Bm
         _same(_cp(cal.cal_params["equivalent_beam_angle"], chan), want["equivalent_beam_angle"])
     _same(gain, want["gain_correction"])
+
+
+def test_index_binning_ping_time_is_the_tile_mean():
+    """compute_MVBS_index_binning: the ping_time of a tile is the mean time of its pings (DataArray.coarsen(...).mean() with
+    coord_func="mean", commongrid/api.py:219-238), the short last tile averaged over its real members; the vectorised form
+    equals the per-tile float64 mean truncated to nanoseconds."""
+    from echopype_b200.commongrid.api import _coarsen_time_mean
+
+    rng = np.random.default_rng(0)
+    t = np.datetime64("2024-01-01", "ns") + np.cumsum(rng.integers(1, 3_000_000_000, size=1003)).astype("timedelta64[ns]")
+    ti = t.astype(np.int64)
+    for pn in (1, 3, 10, 100, 1003, 2000):
+        nP = -(-len(t) // pn)
+        want = np.array([ti[i * pn] + int(np.mean((ti[i * pn:(i + 1) * pn] - ti[i * pn]).astype(np.float64))) for i in range(nP)])
+        got = _coarsen_time_mean(t, pn).astype(np.int64)
+        np.testing.assert_array_equal(got, want)
