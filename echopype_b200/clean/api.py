@@ -151,7 +151,7 @@ def mask_impulse_noise(ds_Sv, depth_bin: str = "5m", num_side_pings: int = 2, im
         if not (np.isfinite(lo) and np.isfinite(hi)):
             raise ValueError(f"`{range_var}` has no valid values")
         edges = np.arange(float(lo), float(hi) + depth_bin, depth_bin)
-        mask, _, _, _ = kernels.impulse_noise_mask_depth(Sv, rng, edges, C, P, R, int(num_side_pings), thr)
+        mask, _, _, _ = kernels.impulse_noise_mask_depth(Sv, rng, edges, C, P, R, int(num_side_pings), thr, want_upsampled=False)
         return DataArray(mask, DIMS, coords=_mask_coords(ds_Sv), name="Sv")
     nsamp = _samples_per_bin(rng, depth_bin, C, P, R)
     mask, _ = kernels.impulse_noise_mask(Sv, nsamp, C, P, R, int(num_side_pings), thr)

@@ -431,6 +431,155 @@ __global__ void __launch_bounds__(256) depth_bin_mean_kernel(const float* __rest
   }
 }
 
+// ---- impulse noise with depth-VALUE binning in ONE pass (rows of up to 4096 samples in 16-sample units; the upsampled
+// array is not materialised): a CTA walks a (channel, ping-chunk) strip ping by ping, stages the row's depth and linear
+// Sv in shared memory (the next row is in flight in registers), bisects the interval starts, sums the intervals, and
+// keeps (starts, means) of the 2 k + 1 window pings in a shared-memory ring.  The mask of ping p - k is then formed from
+// the ring: every thread walks its 16 samples through the interval starts of the three pings involved (each ping has
+// its own starts: np.digitize + forward fill per ping).  9 bytes per sample (Sv, depth, mask) instead of the ~25 of
+// depth_bin_mean_kernel + impulse_mask_rows_kernel (which write the upsampled array and read it back three times).
+__global__ void __launch_bounds__(kImpThreads) impulse_depth_fused_kernel(const float* __restrict__ Sv, const float* __restrict__ depth,
+                                                                          const float* __restrict__ t32, int nb, float* __restrict__ U,
+                                                                          int* __restrict__ F, unsigned char* __restrict__ mask, long long P,
+                                                                          int R, int k, float thr, int chunk, int nchunks, long long nstrips) {
+  extern __shared__ __align__(16) float s_idf[];  // [R] depth (NaN -> +inf), [R] linear Sv, [nb + 1] thresholds, ring [W][2 nb + 1]
+  float* s_d = s_idf;
+  float* s_l = s_idf + R;
+  float* s_t = s_idf + 2 * R;
+  int* s_ring = reinterpret_cast<int*>(s_t + nb + 1);  // per window ping: [nb + 1] interval starts, then [nb] means (float bits)
+  const int W = 2 * k + 1, RS = 2 * nb + 1, tid = threadIdx.x, R4 = R >> 2, Pi = (int)P;
+  for (int b = tid; b <= nb; b += kImpThreads) s_t[b] = t32[b];
+  for (long long strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
+    const long long c = strip / nchunks;
+    const int p0 = (int)((strip - c * nchunks) * chunk), p1 = (p0 + chunk < Pi) ? p0 + chunk : Pi;
+    const float4* sv4 = reinterpret_cast<const float4*>(Sv + c * P * (long long)R);
+    const float4* dp4 = reinterpret_cast<const float4*>(depth + c * P * (long long)R);
+    const int q0 = (p0 - k > 0) ? p0 - k : 0, q1 = (p1 + k < Pi) ? p1 + k : Pi;  // rows whose intervals are needed
+    float4 v[4], d[4];
+    auto load_row = [&](int q) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (tid + i * kImpThreads < R4) {
+          v[i] = ld_stream4(sv4 + (long long)q * R4 + tid + i * kImpThreads);
+          d[i] = ld_stream4(dp4 + (long long)q * R4 + tid + i * kImpThreads);
+        }
+    };
+    load_row(q0);
+    int sq = q0 % W;  // ring slot of row q
+    for (int q = q0; q < q1 + k; ++q, sq = (sq + 1 == W) ? 0 : sq + 1) {  // the last k steps only emit masks
+      if (q < q1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (tid + i * kImpThreads < R4) {
+            const int o = 4 * (tid + i * kImpThreads);
+            *reinterpret_cast<float4*>(s_d + o) = make_float4((d[i].x == d[i].x) ? d[i].x : CUDART_INF_F, (d[i].y == d[i].y) ? d[i].y : CUDART_INF_F,
+                                                              (d[i].z == d[i].z) ? d[i].z : CUDART_INF_F, (d[i].w == d[i].w) ? d[i].w : CUDART_INF_F);
+            *reinterpret_cast<float4*>(s_l + o) = make_float4(fast_exp2(v[i].x * kDb2Log2), fast_exp2(v[i].y * kDb2Log2),
+                                                              fast_exp2(v[i].z * kDb2Log2), fast_exp2(v[i].w * kDb2Log2));
+          }
+        if (q + 1 < q1) load_row(q + 1);
+        __syncthreads();
+        int* sj = s_ring + sq * RS;
+        for (int b = tid; b <= nb; b += kImpThreads) {  // first sample at or beyond every edge
+          const float t = s_t[b];
+          int lo = 0, hi = R;
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (s_d[mid] >= t)
+              hi = mid;
+            else
+              lo = mid + 1;
+          }
+          sj[b] = lo;
+        }
+        __syncthreads();
+        for (int b = tid; b < nb; b += kImpThreads) {
+          const int j0 = sj[b], j1 = sj[b + 1];
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          int j = j0;
+          for (; j + 4 <= j1; j += 4) s0 += s_l[j], s1 += s_l[j + 1], s2 += s_l[j + 2], s3 += s_l[j + 3];
+          for (; j < j1; ++j) s0 += s_l[j];
+          float tot = (s0 + s1) + (s2 + s3);
+          int m = j1 - j0;
+          if (tot != tot) {  // a NaN member: redo NaN-aware
+            s0 = 0.f, m = 0;
+            for (j = j0; j < j1; ++j) {
+              const float x = s_l[j];
+              if (x == x) s0 += x, ++m;
+            }
+            tot = s0;
+          }
+          const float u = (m > 0) ? kLog2ToDb * log2f(tot / (float)m) : CUDART_NAN_F;
+          sj[nb + 1 + b] = __float_as_int(u);
+          if (q >= p0 && q < p1) {
+            U[(c * P + q) * nb + b] = u;
+            F[(c * P + q) * nb + b] = j0;
+          }
+        }
+      }
+      __syncthreads();  // intervals of row q visible; s_d / s_l free for the next row
+      const int p = q - k;
+      if (p >= p0 && p < p1) {
+        const int* r0 = s_ring + (sq >= k ? sq - k : sq - k + W) * RS;                     // row p
+        const int* rf = (p + k < Pi) ? s_ring + sq * RS : nullptr;                         // row p + k
+        const int* rb = (p - k >= 0) ? s_ring + (sq + 1 == W ? 0 : sq + 1) * RS : nullptr;  // row p - k
+        // per row: the interval a sample lies in (the last one that starts at or before it; -1: none), its mean and the
+        // start of the next interval are kept in registers - an interval holds tens of samples, so the ring is touched
+        // again only when a sample crosses into the next one (a dependent shared-memory load per sample and row made the
+        // first form of this kernel slower than the two-kernel path)
+        struct Cur {
+          const int* r;
+          int b, nx;
+          float v;
+        };
+        const int kNone = 0x7fffffff;
+        auto open = [&](const int* r, int j) {
+          Cur cu;
+          cu.r = r, cu.b = -1, cu.nx = kNone, cu.v = CUDART_NAN_F;
+          if (r) {
+            int lo = 0, hi = nb;  // number of interval starts <= j
+            while (lo < hi) {
+              const int mid = (lo + hi) >> 1;
+              if (r[mid] <= j)
+                lo = mid + 1;
+              else
+                hi = mid;
+            }
+            cu.b = lo - 1;
+            cu.nx = (lo < nb) ? r[lo] : kNone;
+            if (cu.b >= 0) cu.v = __int_as_float(r[nb + 1 + cu.b]);
+          }
+          return cu;
+        };
+        auto at = [&](Cur& cu, int j) {
+          while (j >= cu.nx) {  // rare
+            ++cu.b;
+            cu.nx = (cu.b + 1 < nb) ? cu.r[cu.b + 1] : kNone;
+            cu.v = __int_as_float(cu.r[nb + 1 + cu.b]);
+          }
+          return cu.v;
+        };
+        unsigned char* mrow = mask + (c * P + p) * (long long)R;
+        for (int j0 = tid << 4; j0 < R; j0 += kImpThreads << 4) {
+          Cur c0 = open(r0, j0), cf = open(rf, j0), cb = open(rb, j0);
+          unsigned wv[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int j = j0 + i;
+            const float x = at(c0, j);
+            float f = x - at(cf, j), w = x - at(cb, j);  // a missing neighbour ping gives NaN
+            f = (f == f) ? f : CUDART_INF_F;
+            w = (w == w) ? w : CUDART_INF_F;
+            wv[i >> 2] |= ((f > thr && w > thr) ? 1u : 0u) << (8 * (i & 3));
+          }
+          *reinterpret_cast<uint4*>(mrow + j0) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+        }
+      }
+    }
+    __syncthreads();  // the next strip rewrites the ring
+  }
+}
+
 // echopy_impulse_noise_mask (clean/utils.py:320-337) on a materialised (channel, ping, range_sample) array of
 // downsampled-upsampled Sv: elementwise on the rows p, p + k, p - k; 16 samples per thread, one 16-byte store
 __global__ void __launch_bounds__(256) impulse_mask_rows_kernel(const float* __restrict__ up, unsigned char* __restrict__ mask,
@@ -1331,14 +1480,33 @@ extern "C" int epb_impulse_noise_mask_depth(const float* Sv, const float* depth,
                                             float* bin_means, int* bin_first, float* upsampled, unsigned char* mask, epb_i64 C,
                                             epb_i64 P, epb_i64 R, int num_side_pings, float threshold, float* thresholds_scratch,
                                             void* stream) {
-  EPB_REQUIRE(Sv && depth && edges && bin_means && bin_first && upsampled && mask && thresholds_scratch, "NULL pointer");
+  EPB_REQUIRE(Sv && depth && edges && bin_means && bin_first && mask && thresholds_scratch, "NULL pointer");
   EPB_REQUIRE(C > 0 && P > 0 && R > 0 && R <= 24576 && nbins > 0 && nbins <= 8192 && num_side_pings >= 1, "bad shape / argument");
   // float32 thresholds of the float64 edges (closed-left intervals): computed on the device by a tiny kernel
   edges_ceil32_kernel<<<(nbins + 1 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(edges, thresholds_scratch, nbins + 1);
   const long long nrows = C * P, cap = (long long)epb_num_sms() * 8;
+  EPB_REQUIRE(nbins <= R, "more depth intervals than range samples");
+  // the upsampled array is not asked for: single pass (rows of up to 4096 samples in 16-sample units)
+  const size_t fsm = (size_t)R * 8 + (size_t)(nbins + 1) * 4 + (size_t)(2 * num_side_pings + 1) * (2 * nbins + 1) * 4;
+  if (!upsampled) {
+    EPB_REQUIRE((R & 15) == 0 && R <= 16 * kImpThreads && fsm <= 96 * 1024 && P < (1LL << 30) &&
+                    (((uintptr_t)Sv | (uintptr_t)depth | (uintptr_t)mask) % 16) == 0,
+                "without the upsampled array: range_sample % 16 == 0, range_sample <= 4096, 16-byte aligned arrays, a window ring of <= 96 KB");
+    const long long want = ((long long)epb_num_sms() * 16 + C - 1) / C;
+    long long chunk = (P + want - 1) / want;
+    const long long min_chunk = 16LL * (2 * num_side_pings + 1);
+    if (chunk < min_chunk) chunk = min_chunk;
+    if (chunk > P) chunk = P;
+    const long long nchunks = (P + chunk - 1) / chunk, nstrips = nchunks * C;
+    if (cudaFuncSetAttribute(impulse_depth_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm) != cudaSuccess)
+      return epb_check_launch("epb_impulse_noise_mask_depth(smem)");
+    impulse_depth_fused_kernel<<<(unsigned)(nstrips < cap ? nstrips : cap), kImpThreads, fsm, (cudaStream_t)stream>>>(
+        Sv, depth, thresholds_scratch, nbins, bin_means, bin_first, mask, P, (int)R, num_side_pings, threshold, (int)chunk, (int)nchunks,
+        nstrips);
+    return epb_check_launch("epb_impulse_noise_mask_depth(fused)");
+  }
   const unsigned grid = (unsigned)(nrows < cap ? nrows : cap);
   const size_t smem_a = (size_t)R * 8 + (size_t)(nbins + 1) * 4;
-  EPB_REQUIRE(nbins <= R, "more depth intervals than range samples");
   if (smem_a > 48 * 1024 &&
       cudaFuncSetAttribute(depth_bin_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a) != cudaSuccess)
     return epb_check_launch("epb_impulse_noise_mask_depth(smem)");

@@ -349,14 +349,17 @@ def impulse_noise_mask(Sv, nsamp, C, P, R, num_side_pings, threshold, out=None):
     return mask, blocks
 
 
-def impulse_noise_mask_depth(Sv, depth, edges, C, P, R, num_side_pings, threshold):
-    """Depth-value binning variant (use_index_binning=False); edges: host float64 array of interval edges."""
+def impulse_noise_mask_depth(Sv, depth, edges, C, P, R, num_side_pings, threshold, want_upsampled=True):
+    """Depth-value binning variant (use_index_binning=False); edges: host float64 array of interval edges.
+    want_upsampled=False: the reference's upsampled_Sv is not materialised (single-pass kernel when the shape allows it)."""
     nb = len(edges) - 1
     e = torch.from_numpy(np.ascontiguousarray(edges, dtype=np.float64)).to(Sv.device)
     means = torch.empty((C, P, nb), dtype=torch.float32, device=Sv.device)
     first = torch.empty((C, P, nb), dtype=torch.int32, device=Sv.device)
     mask = torch.empty((C, P, R), dtype=torch.uint8, device=Sv.device)
-    up = torch.empty((C, P, R), dtype=torch.float32, device=Sv.device)  # the reference's upsampled_Sv
+    fused = (not want_upsampled and R % 16 == 0 and R <= 4096 and P < (1 << 30) and Sv.data_ptr() % 16 == 0 and depth.data_ptr() % 16 == 0
+             and R * 8 + (nb + 1) * 4 + (2 * int(num_side_pings) + 1) * (2 * nb + 1) * 4 <= 96 * 1024)
+    up = None if fused else torch.empty((C, P, R), dtype=torch.float32, device=Sv.device)  # the reference's upsampled_Sv
     scratch = torch.empty(nb + 1, dtype=torch.float32, device=Sv.device)
     _lib.call("epb_impulse_noise_mask_depth", ptr(Sv), ptr(depth), ptr(e), nb, ptr(means), ptr(first), ptr(up), ptr(mask),
               C, P, R, int(num_side_pings), ctypes.c_float(float(threshold)), ptr(scratch), stream())

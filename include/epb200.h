@@ -271,7 +271,9 @@ int epb_impulse_noise_mask(const float* Sv, const int* nsamp, float* block_means
  * over the samples of each interval [e_b, e_b+1) (bin_means [C,P,nbins] float32, dB) and the first sample at or below
  * e_b (bin_first [C,P,nbins] int32); every sample takes the mean of its interval (np.digitize + forward fill: upsampled
  * [C,P,R] float32, the reference's upsampled_Sv) and the mask is the two-sided ping comparison of those values.  depth
- * must increase along range_sample (NaN tails allowed).  thresholds_scratch: [nbins+1] float32. */
+ * must increase along range_sample (NaN tails allowed).  thresholds_scratch: [nbins+1] float32.
+ * upsampled may be NULL: the array is then not materialised and the call is ONE pass over Sv and depth (9 bytes per sample
+ * instead of ~25; needs range_sample % 16 == 0, range_sample <= 4096, 16-byte aligned arrays). */
 int epb_impulse_noise_mask_depth(const float* Sv, const float* depth, const double* edges, int nbins, float* bin_means,
                                  int* bin_first, float* upsampled, unsigned char* mask, epb_i64 C, epb_i64 P, epb_i64 R,
                                  int num_side_pings, float threshold, float* thresholds_scratch, void* stream);

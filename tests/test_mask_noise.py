@@ -440,3 +440,46 @@ def test_transient_depth_windows_uniform_rows(ep, C, P, R, k, depth_bin, excl, n
         margin = np.abs((Sv32 - pooled) - thr)
     sure = (np.isnan(margin) | (margin > 1e-3)) & cmp
     np.testing.assert_array_equal(g[sure], want[sure])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,P,R,k,db", [(2, 47, 256, 2, 2.0), (1, 120, 1024, 3, 5.0), (2, 12, 4096, 1, 5.0), (1, 9, 64, 4, 1.0)])
+def test_impulse_depth_single_pass_equals_two_kernel_path(ep, C, P, R, k, db):
+    """mask_impulse_noise on its default (depth-value) path without the upsampled array (impulse_depth_fused_kernel: one
+    pass, interval starts and means of the window pings in a shared-memory ring) against the two-kernel path that
+    materialises upsampled_Sv (itself checked against the oracle above): same interval starts, same mask, means to 1e-5 dB."""
+    import torch
+
+    from echopype_b200 import kernels
+
+    rng = np.random.default_rng(R + k)
+    Sv = rng.normal(-70.0, 6.0, size=(C, P, R))
+    Sv[:, rng.integers(0, P, 4), :] += 18.0 * (rng.random((C, 4, R)) < 0.5)
+    Sv[rng.random(Sv.shape) < 0.02] = np.nan
+    off = rng.choice([0.0, 0.07, 0.13], size=(C, P))  # the transducer depth changes from ping to ping
+    depth = (3.0 + off[:, :, None] + 0.19 * np.arange(R)[None, None, :]).astype(np.float32)
+    Sv[0, P // 3, R // 2:] = np.nan
+    depth[0, P // 3, R // 2:] = np.nan  # a short ping: no depth where the samples are padding
+    edges = np.arange(np.nanmin(depth), np.nanmax(depth) + db, db, dtype=np.float64)
+    Svt, dt = torch.from_numpy(Sv.astype(np.float32)).cuda(), torch.from_numpy(depth).cuda()
+    m2, u2, f2, up = kernels.impulse_noise_mask_depth(Svt, dt, edges, C, P, R, k, 10.0)
+    m1, u1, f1, none = kernels.impulse_noise_mask_depth(Svt, dt, edges, C, P, R, k, 10.0, want_upsampled=False)
+    assert none is None and up is not None
+    assert torch.equal(f1, f2)
+    a, b = u1.cpu().numpy(), u2.cpu().numpy()
+    np.testing.assert_array_equal(np.isnan(a), np.isnan(b))
+    assert np.nanmax(np.abs(a - b)) < 1e-5
+    # masks: equal except where a comparison sits within float rounding of the threshold (the NaN-aware sums of the two
+    # paths add in a different order)
+    upn = up.cpu().numpy().astype(np.float64)
+    fwd = np.full(upn.shape, np.inf)
+    bwd = np.full(upn.shape, np.inf)
+    fwd[:, : P - k] = upn[:, : P - k] - upn[:, k:]
+    bwd[:, k:] = upn[:, k:] - upn[:, : P - k]
+    fwd[np.isnan(fwd)] = np.inf
+    bwd[np.isnan(bwd)] = np.inf
+    sure = (np.abs(fwd - 10.0) > 1e-4) & (np.abs(bwd - 10.0) > 1e-4)
+    assert sure.mean() > 0.999
+    g1, g2 = m1.cpu().numpy().astype(bool), m2.cpu().numpy().astype(bool)
+    np.testing.assert_array_equal(g1[sure], g2[sure])
+    assert g2.any() and not g2.all()
