@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(256) depth_bin_mean_kernel(const float* __rest
 // the ring: every thread walks its 16 samples through the interval starts of the three pings involved (each ping has
 // its own starts: np.digitize + forward fill per ping).  9 bytes per sample (Sv, depth, mask) instead of the ~25 of
 // depth_bin_mean_kernel + impulse_mask_rows_kernel (which write the upsampled array and read it back three times).
-__global__ void __launch_bounds__(kImpThreads) impulse_depth_fused_kernel(const float* __restrict__ Sv, const float* __restrict__ depth,
+__global__ void __launch_bounds__(kImpThreads, 4) impulse_depth_fused_kernel(const float* __restrict__ Sv, const float* __restrict__ depth,
                                                                           const float* __restrict__ t32, int nb, float* __restrict__ U,
                                                                           int* __restrict__ F, unsigned char* __restrict__ mask, long long P,
                                                                           int R, int k, float thr, int chunk, int nchunks, long long nstrips) {
@@ -455,29 +455,25 @@ __global__ void __launch_bounds__(kImpThreads) impulse_depth_fused_kernel(const 
     const float4* sv4 = reinterpret_cast<const float4*>(Sv + c * P * (long long)R);
     const float4* dp4 = reinterpret_cast<const float4*>(depth + c * P * (long long)R);
     const int q0 = (p0 - k > 0) ? p0 - k : 0, q1 = (p1 + k < Pi) ? p1 + k : Pi;  // rows whose intervals are needed
-    float4 v[4], d[4];
-    auto load_row = [&](int q) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (tid + i * kImpThreads < R4) {
-          v[i] = ld_stream4(sv4 + (long long)q * R4 + tid + i * kImpThreads);
-          d[i] = ld_stream4(dp4 + (long long)q * R4 + tid + i * kImpThreads);
-        }
-    };
-    load_row(q0);
     int sq = q0 % W;  // ring slot of row q
     for (int q = q0; q < q1 + k; ++q, sq = (sq + 1 == W) ? 0 : sq + 1) {  // the last k steps only emit masks
       if (q < q1) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (tid + i * kImpThreads < R4) {
-            const int o = 4 * (tid + i * kImpThreads);
-            *reinterpret_cast<float4*>(s_d + o) = make_float4((d[i].x == d[i].x) ? d[i].x : CUDART_INF_F, (d[i].y == d[i].y) ? d[i].y : CUDART_INF_F,
-                                                              (d[i].z == d[i].z) ? d[i].z : CUDART_INF_F, (d[i].w == d[i].w) ? d[i].w : CUDART_INF_F);
-            *reinterpret_cast<float4*>(s_l + o) = make_float4(fast_exp2(v[i].x * kDb2Log2), fast_exp2(v[i].y * kDb2Log2),
-                                                              fast_exp2(v[i].z * kDb2Log2), fast_exp2(v[i].w * kDb2Log2));
-          }
-        if (q + 1 < q1) load_row(q + 1);
+        // (no register prefetch of the next row: four CTAs per SM at 64 registers overlap the loads of one strip with
+        //  the bisections / sums / mask of the others - with 32 registers of prefetch only two CTAs fit: 12.6 ms)
+        for (int i4 = tid; i4 < R4; i4 += 2 * kImpThreads) {
+          const bool two = i4 + kImpThreads < R4;
+          const float4 d0 = ld_stream4(dp4 + (long long)q * R4 + i4), v0 = ld_stream4(sv4 + (long long)q * R4 + i4);
+          float4 d1 = d0, v1 = v0;
+          if (two) d1 = ld_stream4(dp4 + (long long)q * R4 + i4 + kImpThreads), v1 = ld_stream4(sv4 + (long long)q * R4 + i4 + kImpThreads);
+          auto put = [&](int i, const float4& dd, const float4& vv) {
+            *reinterpret_cast<float4*>(s_d + 4 * i) = make_float4((dd.x == dd.x) ? dd.x : CUDART_INF_F, (dd.y == dd.y) ? dd.y : CUDART_INF_F,
+                                                                  (dd.z == dd.z) ? dd.z : CUDART_INF_F, (dd.w == dd.w) ? dd.w : CUDART_INF_F);
+            *reinterpret_cast<float4*>(s_l + 4 * i) = make_float4(fast_exp2(vv.x * kDb2Log2), fast_exp2(vv.y * kDb2Log2),
+                                                                  fast_exp2(vv.z * kDb2Log2), fast_exp2(vv.w * kDb2Log2));
+          };
+          put(i4, d0, v0);
+          if (two) put(i4 + kImpThreads, d1, v1);
+        }
         __syncthreads();
         int* sj = s_ring + sq * RS;
         for (int b = tid; b <= nb; b += kImpThreads) {  // first sample at or beyond every edge
@@ -529,25 +525,31 @@ __global__ void __launch_bounds__(kImpThreads) impulse_depth_fused_kernel(const 
         // first form of this kernel slower than the two-kernel path)
         struct Cur {
           const int* r;
-          int b, nx;
-          float v;
+          int b, nx, nx2;  // current interval, start of the next one and of the one after it
+          float v, v1;     // mean of the current interval and of the next one
         };
         const int kNone = 0x7fffffff;
-        auto open = [&](const int* r, int j) {
+        auto open = [&](const int* r, int j, int hint) {  // hint: the interval index found for a neighbouring ping, or -2
           Cur cu;
-          cu.r = r, cu.b = -1, cu.nx = kNone, cu.v = CUDART_NAN_F;
+          cu.r = r, cu.b = -1, cu.nx = kNone, cu.nx2 = kNone, cu.v = CUDART_NAN_F, cu.v1 = CUDART_NAN_F;
           if (r) {
-            int lo = 0, hi = nb;  // number of interval starts <= j
-            while (lo < hi) {
-              const int mid = (lo + hi) >> 1;
-              if (r[mid] <= j)
-                lo = mid + 1;
-              else
-                hi = mid;
+            int lo = hint + 1, hi = nb;  // number of interval starts <= j
+            // neighbouring pings start their intervals within a sample or two of each other: usually the hint is right
+            if (!(hint >= -1 && (lo == 0 || r[lo - 1] <= j) && (lo == nb || r[lo] > j))) {
+              lo = 0;
+              while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (r[mid] <= j)
+                  lo = mid + 1;
+                else
+                  hi = mid;
+              }
             }
             cu.b = lo - 1;
             cu.nx = (lo < nb) ? r[lo] : kNone;
+            cu.nx2 = (lo + 1 < nb) ? r[lo + 1] : kNone;
             if (cu.b >= 0) cu.v = __int_as_float(r[nb + 1 + cu.b]);
+            if (lo < nb) cu.v1 = __int_as_float(r[nb + 1 + lo]);
           }
           return cu;
         };
@@ -561,16 +563,30 @@ __global__ void __launch_bounds__(kImpThreads) impulse_depth_fused_kernel(const 
         };
         unsigned char* mrow = mask + (c * P + p) * (long long)R;
         for (int j0 = tid << 4; j0 < R; j0 += kImpThreads << 4) {
-          Cur c0 = open(r0, j0), cf = open(rf, j0), cb = open(rb, j0);
+          Cur c0 = open(r0, j0, -2), cf = open(rf, j0, c0.b), cb = open(rb, j0, c0.b);
           unsigned wv[4] = {0u, 0u, 0u, 0u};
+          if (c0.nx2 >= j0 + 16 && cf.nx2 >= j0 + 16 && cb.nx2 >= j0 + 16) {
+            // the usual case (intervals of at least 16 samples): the 16 samples touch at most two intervals of each ping -
+            // branch-free selects (the interval walk below runs its loop body whenever ANY lane crosses a boundary,
+            // which with 32 lanes x 16 samples is almost always: 14 000 instructions per row)
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int j = j0 + i;
-            const float x = at(c0, j);
-            float f = x - at(cf, j), w = x - at(cb, j);  // a missing neighbour ping gives NaN
-            f = (f == f) ? f : CUDART_INF_F;
-            w = (w == w) ? w : CUDART_INF_F;
-            wv[i >> 2] |= ((f > thr && w > thr) ? 1u : 0u) << (8 * (i & 3));
+            for (int i = 0; i < 16; ++i) {
+              const int j = j0 + i;
+              const float x = (j >= c0.nx) ? c0.v1 : c0.v;
+              float f = x - ((j >= cf.nx) ? cf.v1 : cf.v), w = x - ((j >= cb.nx) ? cb.v1 : cb.v);  // missing ping: NaN
+              f = (f == f) ? f : CUDART_INF_F;
+              w = (w == w) ? w : CUDART_INF_F;
+              wv[i >> 2] |= ((f > thr && w > thr) ? 1u : 0u) << (8 * (i & 3));
+            }
+          } else {
+            for (int i = 0; i < 16; ++i) {
+              const int j = j0 + i;
+              const float x = at(c0, j);
+              float f = x - at(cf, j), w = x - at(cb, j);
+              f = (f == f) ? f : CUDART_INF_F;
+              w = (w == w) ? w : CUDART_INF_F;
+              wv[i >> 2] |= ((f > thr && w > thr) ? 1u : 0u) << (8 * (i & 3));
+            }
           }
           *reinterpret_cast<uint4*>(mrow + j0) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
         }
