@@ -446,8 +446,9 @@ __global__ void __launch_bounds__(kImpThreads, 4) impulse_depth_fused_kernel(con
   float* s_d = s_idf;
   float* s_l = s_idf + R;
   float* s_t = s_idf + 2 * R;
-  int* s_ring = reinterpret_cast<int*>(s_t + nb + 1);  // per window ping: [nb + 1] interval starts, then [nb] means (float bits)
-  const int W = 2 * k + 1, RS = 2 * nb + 1, tid = threadIdx.x, R4 = R >> 2, Pi = (int)P;
+  // per window ping: [nb + 1] interval starts, [nb] means (float bits), [R / 16] interval of every 16th sample
+  int* s_ring = reinterpret_cast<int*>(s_t + nb + 1);
+  const int W = 2 * k + 1, RS = 2 * nb + 1 + (R >> 4), tid = threadIdx.x, R4 = R >> 2, Pi = (int)P;
   for (int b = tid; b <= nb; b += kImpThreads) s_t[b] = t32[b];
   for (long long strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
     const long long c = strip / nchunks;
@@ -512,6 +513,20 @@ __global__ void __launch_bounds__(kImpThreads, 4) impulse_depth_fused_kernel(con
             F[(c * P + q) * nb + b] = j0;
           }
         }
+        // the interval of every 16th sample (the last one that starts at or before it; -1: none): one bisection per
+        // thread here instead of three per thread in the mask phase of each of the three pings that use this row
+        for (int g = tid; g < (R >> 4); g += kImpThreads) {
+          const int j = g << 4;
+          int lo = 0, hi = nb;  // number of interval starts <= j
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (sj[mid] <= j)
+              lo = mid + 1;
+            else
+              hi = mid;
+          }
+          sj[2 * nb + 1 + g] = lo - 1;
+        }
       }
       __syncthreads();  // intervals of row q visible; s_d / s_l free for the next row
       const int p = q - k;
@@ -529,22 +544,11 @@ __global__ void __launch_bounds__(kImpThreads, 4) impulse_depth_fused_kernel(con
           float v, v1;     // mean of the current interval and of the next one
         };
         const int kNone = 0x7fffffff;
-        auto open = [&](const int* r, int j, int hint) {  // hint: the interval index found for a neighbouring ping, or -2
+        auto open = [&](const int* r, int j) {  // j: a multiple of 16
           Cur cu;
           cu.r = r, cu.b = -1, cu.nx = kNone, cu.nx2 = kNone, cu.v = CUDART_NAN_F, cu.v1 = CUDART_NAN_F;
           if (r) {
-            int lo = hint + 1, hi = nb;  // number of interval starts <= j
-            // neighbouring pings start their intervals within a sample or two of each other: usually the hint is right
-            if (!(hint >= -1 && (lo == 0 || r[lo - 1] <= j) && (lo == nb || r[lo] > j))) {
-              lo = 0;
-              while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (r[mid] <= j)
-                  lo = mid + 1;
-                else
-                  hi = mid;
-              }
-            }
+            const int lo = r[2 * nb + 1 + (j >> 4)] + 1;  // number of interval starts <= j (table built with the row)
             cu.b = lo - 1;
             cu.nx = (lo < nb) ? r[lo] : kNone;
             cu.nx2 = (lo + 1 < nb) ? r[lo + 1] : kNone;
@@ -563,7 +567,7 @@ __global__ void __launch_bounds__(kImpThreads, 4) impulse_depth_fused_kernel(con
         };
         unsigned char* mrow = mask + (c * P + p) * (long long)R;
         for (int j0 = tid << 4; j0 < R; j0 += kImpThreads << 4) {
-          Cur c0 = open(r0, j0, -2), cf = open(rf, j0, c0.b), cb = open(rb, j0, c0.b);
+          Cur c0 = open(r0, j0), cf = open(rf, j0), cb = open(rb, j0);
           unsigned wv[4] = {0u, 0u, 0u, 0u};
           if (c0.nx2 >= j0 + 16 && cf.nx2 >= j0 + 16 && cb.nx2 >= j0 + 16) {
             // the usual case (intervals of at least 16 samples): the 16 samples touch at most two intervals of each ping -
@@ -1503,7 +1507,7 @@ extern "C" int epb_impulse_noise_mask_depth(const float* Sv, const float* depth,
   const long long nrows = C * P, cap = (long long)epb_num_sms() * 8;
   EPB_REQUIRE(nbins <= R, "more depth intervals than range samples");
   // the upsampled array is not asked for: single pass (rows of up to 4096 samples in 16-sample units)
-  const size_t fsm = (size_t)R * 8 + (size_t)(nbins + 1) * 4 + (size_t)(2 * num_side_pings + 1) * (2 * nbins + 1) * 4;
+  const size_t fsm = (size_t)R * 8 + (size_t)(nbins + 1) * 4 + (size_t)(2 * num_side_pings + 1) * (2 * nbins + 1 + R / 16) * 4;
   if (!upsampled) {
     EPB_REQUIRE((R & 15) == 0 && R <= 16 * kImpThreads && fsm <= 96 * 1024 && P < (1LL << 30) &&
                     (((uintptr_t)Sv | (uintptr_t)depth | (uintptr_t)mask) % 16) == 0,

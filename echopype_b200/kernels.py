@@ -358,7 +358,7 @@ def impulse_noise_mask_depth(Sv, depth, edges, C, P, R, num_side_pings, threshol
     first = torch.empty((C, P, nb), dtype=torch.int32, device=Sv.device)
     mask = torch.empty((C, P, R), dtype=torch.uint8, device=Sv.device)
     fused = (not want_upsampled and R % 16 == 0 and R <= 4096 and P < (1 << 30) and Sv.data_ptr() % 16 == 0 and depth.data_ptr() % 16 == 0
-             and R * 8 + (nb + 1) * 4 + (2 * int(num_side_pings) + 1) * (2 * nb + 1) * 4 <= 96 * 1024)
+             and R * 8 + (nb + 1) * 4 + (2 * int(num_side_pings) + 1) * (2 * nb + 1 + R // 16) * 4 <= 96 * 1024)
     up = None if fused else torch.empty((C, P, R), dtype=torch.float32, device=Sv.device)  # the reference's upsampled_Sv
     scratch = torch.empty(nb + 1, dtype=torch.float32, device=Sv.device)
     _lib.call("epb_impulse_noise_mask_depth", ptr(Sv), ptr(depth), ptr(e), nb, ptr(means), ptr(first), ptr(up), ptr(mask),

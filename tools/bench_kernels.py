@@ -190,6 +190,8 @@ def extra(a, which, C, P, R, n, x, rows, out, rng, ed):
         edges = np.arange(0.0, float(rng.nan_to_num(nan=0.0).max()) + 5.0, 5.0)
         ms, mn = timeit(lambda: kernels.impulse_noise_mask_depth(out, rng, edges, C, P, R, 2, 10.0), max(3, a.iters // 2))
         report("mask_impulse_noise(5m, depth-value bins)", ms, mn, 9 * n, n)
+        ms, mn = timeit(lambda: kernels.impulse_noise_mask_depth(out, rng, edges, C, P, R, 2, 10.0, want_upsampled=False), max(3, a.iters // 2))
+        report("mask_impulse_noise(5m, depth-value bins, single pass: no upsampled array)", ms, mn, 9 * n, n)
         nsamp = np.full(C, 53, dtype=np.int64)
         tbuf = (mbuf[0], torch.empty((C, P, R, 2), dtype=torch.float32, device=dev))
         ms, mn = timeit(lambda: kernels.transient_noise_mask(out, nsamp, C, P, R, 1300, 25, 12.0, out=tbuf), max(3, a.iters // 2))
