@@ -481,15 +481,31 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) bin_reduce_law_kernel(
   const bool is_depth = depth_off != nullptr;
   const long long nrows = C * P;
   const long long warp0 = (long long)blockIdx.x * kWarpsPerCta + w;
+  const bool vec = (R & 3) == 0 && ((uintptr_t)Sv & 15) == 0;
+  long long prev_row = -1;  // the row whose boundaries are in bnd
+  double prev_off = 0.0, prev_scale = 0.0;
   for (long long row = warp0; row < nrows; row += (long long)gridDim.x * kWarpsPerCta) {
     const long long c = row / P, p = row % P;
     const int xb = __ldg(xbin + p);
     if (xb < 0 || xb >= nX) continue;
-    const epb_row r = rows[row];
     const double off = is_depth ? depth_off[p] : 0.0, scale = is_depth ? depth_scale[p] : 1.0;
-    __syncwarp();
-    for (int k = lane; k <= nR; k += 32) bnd[k] = first_at_or_above(r, R, s_edges[k], closed_right, off, scale, is_depth);
-    __syncwarp();
+    // The boundaries depend on the row's range law and (depth) offset / scale only: a row whose first 128 bytes (the
+    // float64 law block of epb_row) and offset / scale equal those of the row the warp did last keeps them - the usual
+    // case (one law per channel, a constant transducer depth): no 12-step float64 bisection per edge and row.
+    bool same = false;
+    if (prev_row >= 0) {
+      const unsigned long long* ra = reinterpret_cast<const unsigned long long*>(rows + row);
+      const unsigned long long* rb = reinterpret_cast<const unsigned long long*>(rows + prev_row);
+      const bool eq = lane < 16 ? (__ldg(ra + lane) == __ldg(rb + lane)) : true;
+      same = __all_sync(0xffffffffu, eq) && off == prev_off && scale == prev_scale && row / P == prev_row / P;
+    }
+    if (!same) {
+      const epb_row r = rows[row];
+      __syncwarp();
+      for (int k = lane; k <= nR; k += 32) bnd[k] = first_at_or_above(r, R, s_edges[k], closed_right, off, scale, is_depth);
+      __syncwarp();
+      prev_row = row, prev_off = off, prev_scale = scale;
+    }
     double* acc_row = acc + ((c * nX + xb) * (long long)nR) * 4;
     const float* sv = Sv + row * (long long)R;
     const int n_lo = bnd[0], n_hi = bnd[nR];  // members are n_lo <= n < n_hi
@@ -498,6 +514,11 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) bin_reduce_law_kernel(
       const int nb = n0 + 4 * lane;
       int keys[4];
       Acc3 a[4];
+      float sv4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (vec && nb < R) {  // one 16-byte load (R % 4 == 0: the four samples are inside the row)
+        const float4 q = ld_stream4(reinterpret_cast<const float4*>(sv + nb));
+        sv4[0] = q.x, sv4[1] = q.y, sv4[2] = q.z, sv4[3] = q.w;
+      }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int n = nb + k;
@@ -506,7 +527,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) bin_reduce_law_kernel(
         if (n >= n_lo && n < n_hi) {
           while (bnd[kcur + 1] <= n) ++kcur;  // bnd is non-decreasing; kcur only moves forward
           keys[k] = kcur;
-          add_sample(a[k], ld_stream(sv + n));
+          add_sample(a[k], vec ? sv4[k] : ld_stream(sv + n));
         }
       }
       const bool same = (keys[0] == keys[1]) && (keys[1] == keys[2]) && (keys[2] == keys[3]);
