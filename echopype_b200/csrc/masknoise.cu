@@ -17,6 +17,9 @@ __global__ void __launch_bounds__(256) range_diff_kernel(const float* __restrict
                                                          double* __restrict__ sum, unsigned long long* __restrict__ cnt) {
   __shared__ double s_s[8];
   __shared__ unsigned s_n[8];
+  long long acc_c = -1;  // thread 0: running (sum, count) of the channel the CTA is in
+  double acc_s = 0.0;
+  unsigned long long acc_n = 0;
   for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
     const float* r = rng + row * (long long)R;
     double s = 0.0;
@@ -47,13 +50,18 @@ __global__ void __launch_bounds__(256) range_diff_kernel(const float* __restrict
       double ts = 0.0;
       unsigned long long tn = 0;
       for (int w = 0; w < 8; ++w) ts += s_s[w], tn += s_n[w];
-      if (tn) {
-        atomicAdd(sum + row / P, ts);
-        atomicAdd(cnt + row / P, tn);
+      // the CTA's rows come in increasing order: one atomic pair per (CTA, channel) instead of one per row (400 000 rows
+      // adding to four addresses serialised in L2)
+      const long long c = row / P;
+      if (c != acc_c) {
+        if (acc_n) atomicAdd(sum + acc_c, acc_s), atomicAdd(cnt + acc_c, acc_n);
+        acc_c = c, acc_s = 0.0, acc_n = 0;
       }
+      acc_s += ts, acc_n += tn;
     }
     __syncthreads();
   }
+  if (threadIdx.x == 0 && acc_n) atomicAdd(sum + acc_c, acc_s), atomicAdd(cnt + acc_c, acc_n);
 }
 
 // ---- first flat index i with !(a[i] <= thr)  (clean/utils.py:141: np.argmin((range_var <= exclude_above).data)) ----
