@@ -485,15 +485,22 @@ __global__ void __launch_bounds__(kImpThreads, 4) impulse_depth_fused_kernel(con
         }
         __syncthreads();
         int* sj = s_ring + sq * RS;
+        const int* sprev = (q > q0) ? s_ring + (sq == 0 ? W - 1 : sq - 1) * RS : nullptr;  // the previous ping's starts
         for (int b = tid; b <= nb; b += kImpThreads) {  // first sample at or beyond every edge
           const float t = s_t[b];
-          int lo = 0, hi = R;
-          while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (s_d[mid] >= t)
-              hi = mid;
-            else
-              lo = mid + 1;
+          // neighbouring pings start their intervals within a sample or two of each other: try the previous ping's start
+          // (two loads) before the 12-step bisection
+          int lo = sprev ? sprev[b] : -1;
+          if (!(lo >= 0 && (lo == 0 || !(s_d[lo - 1] >= t)) && (lo == R || s_d[lo] >= t))) {
+            lo = 0;
+            int hi = R;
+            while (lo < hi) {
+              const int mid = (lo + hi) >> 1;
+              if (s_d[mid] >= t)
+                hi = mid;
+              else
+                lo = mid + 1;
+            }
           }
           sj[b] = lo;
         }
