@@ -1038,13 +1038,14 @@ __device__ __forceinline__ int scan_up(int v, int o) {
   return v;
 }
 
-// float <-> double without F2F: on B200 the 64-bit conversions share the XU pipe with MUFU and run at ~1 / clk / SM (ncu:
-// pipe_xu 124 % of "peak" with three of them per sample - every earlier form of this kernel sat at ~10 ms whatever its
-// instruction count).  Integer forms on the ALU pipe: exact for +0 / positive normal floats (ex2.ftz never returns a
-// denormal; +inf is not expected), truncating double -> float (1 ulp = 2.6e-7 dB) with everything below 2^-126 -> 0.
-__device__ __forceinline__ double f2d_pos(float f) {
+// float <-> double without F2F: the conversions share the XU pipe with MUFU, which this kernel already loads with three
+// operations per sample (ncu showed the XU pipe as the busiest one).  Integer forms on the ALU pipe: exact for positive
+// normal floats (ex2.ftz never returns a denormal; +inf is not expected), truncating double -> float (1 ulp = 2.6e-7 dB)
+// with everything below 2^-126 -> 0.
+// float -> double for floats known to be positive normal (a zero case costs two more instructions per sample)
+__device__ __forceinline__ double f2d_norm(float f) {
   const unsigned b = __float_as_uint(f);
-  return __hiloint2double((int)(b ? (b >> 3) + 0x38000000u : 0u), (int)(b << 29));
+  return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
 }
 __device__ __forceinline__ float d2f_trunc(double d) {
   const int hi = __double2hiint(d);
@@ -1126,7 +1127,10 @@ __global__ void __launch_bounds__(kStripThreads, 2)
     int has_def = 0;   // CTA-uniform: the count prefix in shared memory is valid and holds deficits
 #pragma unroll
     for (int j = 0; j < kStripCols; ++j) cs[j] = 0.0, my_cc[j * kStripThreads] = 0;
-    auto lin = [](float v) { return f2d_pos(fmaxf(fast_exp2(v * kDb2Log2), 0.f)); };
+    // NaN (and anything below the float range) becomes the smallest normal float, 1.2e-38 (-379 dB): it enters and leaves
+    // the running sums as the same value, 28 orders of magnitude below a -100 dB sample, and never reaches an output
+    // that has no valid member (the count decides that); in exchange the conversion needs no zero case
+    auto lin = [](float v) { return f2d_norm(fmaxf(fast_exp2(v * kDb2Log2), 1.17549435e-38f)); };
     // deficits of this thread's columns: +1 per NaN that enters, -1 per NaN that leaves (rare path)
     auto count_nans = [&](const float (&vi)[kStripCols], const float (&vo)[kStripCols]) {
 #pragma unroll
