@@ -83,6 +83,7 @@ SIGNATURES = {
     "epb_transient_noise_mask": (c_int, [vp, vp, vp, vp, vp, i64, i64, i64, c_int, c_int, c_int, c_float, vp]),
     "epb_transient_noise_mask_median": (c_int, [vp, vp, vp, vp, i64, i64, i64, c_int, c_int, c_int, c_float, vp]),
     "epb_transient_noise_mask_depth_median": (c_int, [vp, vp, vp, vp, i64, i64, i64, c_double, c_double, c_double, c_double, c_int, c_float, vp]),
+    "epb_attenuated_signal_mask": (c_int, [vp, vp, vp, vp, i64, i64, i64, c_double, c_double, c_int, c_double, vp]),
     "epb_zero": (c_int, [vp, i64, vp]),
     "epb_minmax_init": (c_int, [vp, vp]),
     "epb_minmax": (c_int, [vp, i64, vp, vp]),

@@ -4,6 +4,7 @@ runs in two kernels of libepb200 (epb_noise_estimate: tile means + block min, ep
 SNR gate and the actual_range extrema) - 16 B read + 8 B written per sample."""
 
 import numpy as np
+import torch
 
 from .. import kernels
 from ..dataset import DataArray, Dataset, as_dataset
@@ -200,4 +201,40 @@ def mask_transient_noise(ds_Sv, func: str = "nanmean", depth_bin: str = "10m", n
         m0 = R
     pool = kernels.transient_noise_mask_median if median else kernels.transient_noise_mask
     mask, _ = pool(Sv, nsamp, C, P, R, m0, int(num_side_pings), thr)
+    return DataArray(mask, DIMS, coords=_mask_coords(ds_Sv), name="Sv")
+
+
+def mask_attenuated_signal(ds_Sv, upper_limit_sl: str = "400.0m", lower_limit_sl: str = "500.0m", num_side_pings: int = 15,
+                           attenuation_signal_threshold: str = "8.0dB", range_var: str = "depth") -> DataArray:
+    """
+    Locate attenuated signals and create an attenuated-signal mask (Ryan et al. 2015; arguments as
+    echopype.clean.mask_attenuated_signal, clean/api.py:269-359).
+
+    Per channel and ping the median Sv (linear domain) of the scattering layer between ``upper_limit_sl`` and
+    ``lower_limit_sl`` - the samples from the one nearest to the upper limit up to, not including, the one nearest to the
+    lower limit - is compared with the median over the ``num_side_pings`` pings before and the ``num_side_pings - 1``
+    pings after it; the WHOLE ping is masked when it lies less than ``attenuation_signal_threshold`` above the block
+    median (so with the default +8 dB every ping that can be assessed and is not 8 dB above its neighbours is masked, as
+    in the reference).  Pings within ``num_side_pings`` of either end, and pings without valid samples in the layer, are
+    not masked.  Returns a boolean (uint8 on the device) DataArray with dims (channel, ping_time, range_sample); all
+    False when the limits lie outside the extent of ``range_var``.
+    """
+    ds_Sv = as_dataset(ds_Sv)
+    if range_var not in ["echo_range", "depth"]:
+        raise ValueError("`range_var` must be either `echo_range` or `depth`.")
+    if range_var not in ds_Sv:
+        raise ValueError(f"Masking attenuated signal requires `{range_var}` data variable in `ds_Sv`.")
+    # clean/api.py:318: the reference compares the two limit STRINGS here, before parsing them; kept as it is
+    if upper_limit_sl > lower_limit_sl:
+        raise ValueError("Minimum range has to be shorter than maximum range")
+    thr = extract_dB(attenuation_signal_threshold)
+    lower = _parse_x_bin(lower_limit_sl, "range_bin")
+    upper = _parse_x_bin(upper_limit_sl, "range_bin")
+    if not (isinstance(num_side_pings, (int, np.integer)) and num_side_pings >= 0):
+        raise ValueError("num_side_pings must be a non-negative integer")
+    Sv, rng, C, P, R = _index_binning_inputs(ds_Sv, range_var, "attenuated signal")
+    lo, hi, _ = kernels.minmax(rng)
+    if (upper > hi) or (lower < lo):  # searching range outside the echosounder range: nothing is masked
+        return DataArray(torch.zeros((C, P, R), dtype=torch.uint8, device=Sv.device), DIMS, coords=_mask_coords(ds_Sv), name=range_var)
+    mask, _ = kernels.attenuated_signal_mask(Sv, rng, C, P, R, upper, lower, int(num_side_pings), thr)
     return DataArray(mask, DIMS, coords=_mask_coords(ds_Sv), name="Sv")

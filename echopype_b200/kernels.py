@@ -443,6 +443,16 @@ def transient_noise_mask_depth_median(Sv, depth, C, P, R, dmin, dmax, depth_bin,
     return mask, pooled
 
 
+def attenuated_signal_mask(Sv, rng, C, P, R, upper_limit_sl, lower_limit_sl, num_side_pings, threshold):
+    """(mask [C,P,R] uint8, limits [C,P,2] int32 = the up / lw sample indices of every ping)."""
+    mask = torch.empty((C, P, R), dtype=torch.uint8, device=Sv.device)
+    limits = torch.empty((C, P, 2), dtype=torch.int32, device=Sv.device)
+    _lib.call("epb_attenuated_signal_mask", ptr(Sv), ptr(rng), ptr(limits), ptr(mask), C, P, R,
+              ctypes.c_double(float(upper_limit_sl)), ctypes.c_double(float(lower_limit_sl)), int(num_side_pings),
+              ctypes.c_double(float(threshold)), stream())
+    return mask, limits
+
+
 def is_raw_counts(x):
     """True for int16 raw power counts (the ingest format: -32768 = padding), host array or tensor."""
     return getattr(x, "dtype", None) in (torch.int16, np.dtype("int16"))

@@ -296,6 +296,17 @@ int epb_transient_noise_mask_depth_median(const float* Sv, const float* depth, u
                                           double depth_bin, double exclude_above, int num_side_pings, float threshold,
                                           void* stream);
 
+/* Attenuated-signal mask (clean/api.py:269-359 mask_attenuated_signal; clean/utils.py:337-377
+ * echopy_attenuated_signal_mask): per (channel, ping) up / lw = np.argmin |range_var - upper_limit_sl| / |range_var -
+ * lower_limit_sl| (first minimum, a NaN wins; written to limits [C,P,2] int32), the ping is masked - mask [C,P,R] uint8 =
+ * 1 over the WHOLE ping - when 10 log10 nanmedian(10^(Sv[p, up:lw]/10)) - 10 log10 nanmedian(10^(Sv[p-n : p+n, up:lw]/10))
+ * < threshold; never within n = num_side_pings pings of either end of the ping axis, nor when Sv[p, up:lw] is empty or
+ * all NaN.  The medians are radix selections on the float32 values; the two middle values are averaged in the linear
+ * domain in float64.  The "limits outside the range extent" early return (clean/api.py:330-334) is the caller's. */
+int epb_attenuated_signal_mask(const float* Sv, const float* range_var, int* limits, unsigned char* mask, epb_i64 C,
+                               epb_i64 P, epb_i64 R, double upper_limit_sl, double lower_limit_sl, int num_side_pings,
+                               double threshold, void* stream);
+
 /* Transient noise with depth-VALUE windows (use_index_binning=False, clean/utils.py:28-105 pool_Sv, func = nanmean): for
  * every sample whose depth d keeps [d - depth_bin, d + depth_bin] inside [depth_min, depth_max] (the extent of the range
  * variable) and below exclude_above, and whose ping keeps p - k >= 0 and p + k <= P: pooled Sv = dB of the nanmean of

@@ -276,3 +276,59 @@ def mask_transient_noise_depth_binning(Sv, range_var, depth_bin, num_side_pings,
     pooled = pool_Sv(Sv, range_var, depth_bin, num_side_pings, exclude_above, func)
     with np.errstate(invalid="ignore"):
         return (Sv - pooled) > transient_noise_threshold, pooled
+
+
+# ---- attenuated-signal mask (clean/api.py:269-359, clean/utils.py:337-377) ------------------------------------------
+def echopy_attenuated_signal_mask(Sv, range_var, upper_limit_sl, lower_limit_sl, num_side_pings, attenuation_signal_threshold):
+    """clean/utils.py:337-377 for one channel, Sv and range_var laid out (ping_time, range_sample).  The layer is
+    Sv[p, up:lw] with up / lw the samples nearest to the limits (np.argmin: first minimum; the first NaN when the range
+    row has one); ping p is assessed when p - n >= 0, p + n <= P - 1 and the layer holds a valid sample; it is masked as
+    a whole when its linear-domain median is less than the threshold (dB) above the median of pings p - n .. p + n - 1."""
+    P = Sv.shape[0]
+    n = num_side_pings
+    mask = np.zeros(Sv.shape, dtype=bool)
+    for p in range(P):
+        up = int(np.argmin(np.abs(range_var[p] - upper_limit_sl)))
+        lw = int(np.argmin(np.abs(range_var[p] - lower_limit_sl)))
+        if p - n < 0 or p + n > P - 1:
+            continue
+        layer = Sv[p, up:lw]
+        if np.all(np.isnan(layer)):
+            continue
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                ping_median = lin2log(np.nanmedian(log2lin(layer)))
+                block_median = lin2log(np.nanmedian(log2lin(Sv[p - n : p + n, up:lw])))
+                if ping_median - block_median < attenuation_signal_threshold:
+                    mask[p, :] = True
+    return mask
+
+
+def attenuated_signal_margin(Sv, range_var, upper_limit_sl, lower_limit_sl, num_side_pings, attenuation_signal_threshold):
+    """(ping median - block median) - threshold per ping of one channel (NaN where the ping is not assessed): the tests
+    use it to set aside pings that sit on the threshold to within rounding."""
+    P = Sv.shape[0]
+    n = num_side_pings
+    out = np.full(P, np.nan)
+    for p in range(n, P - n):
+        up = int(np.argmin(np.abs(range_var[p] - upper_limit_sl)))
+        lw = int(np.argmin(np.abs(range_var[p] - lower_limit_sl)))
+        layer = Sv[p, up:lw]
+        if np.all(np.isnan(layer)) or n == 0:
+            continue
+        with np.errstate(divide="ignore", invalid="ignore"):
+            out[p] = lin2log(np.nanmedian(log2lin(layer))) - lin2log(np.nanmedian(log2lin(Sv[p - n : p + n, up:lw]))) \
+                - attenuation_signal_threshold
+    return out
+
+
+def mask_attenuated_signal(Sv, range_var, upper_limit_sl, lower_limit_sl, num_side_pings, attenuation_signal_threshold):
+    """clean/api.py:269-359 on (C, P, R) arrays, limits in metres and threshold in dB already parsed: all False when the
+    searching range lies outside the extent of range_var (:330-334), else the per-channel mask (apply_ufunc, vectorize)."""
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        if (upper_limit_sl > np.nanmax(range_var)) or (lower_limit_sl < np.nanmin(range_var)):
+            return np.zeros(range_var.shape, dtype=bool)
+    return np.stack([echopy_attenuated_signal_mask(Sv[c], range_var[c], upper_limit_sl, lower_limit_sl, num_side_pings,
+                                                   attenuation_signal_threshold) for c in range(Sv.shape[0])])

@@ -139,6 +139,8 @@ class DataArray:
         self._data = data
         self.dims = dims
         self._coords = {}
+        if coords is not None and not hasattr(coords, "keys"):  # a list of coordinates, one per dimension
+            coords = {d: (c._data if isinstance(c, DataArray) else c) for d, c in zip(dims, coords)}
         if coords is not None:
             for k in coords.keys():
                 c = _as_coord(k, coords[k])
@@ -481,8 +483,11 @@ class DataArray:
                 if k in coords:
                     o = coords[k]
                     if o.dims != c.dims or not _index_equal(o.data, c.data):
-                        if c.dims == (k,):
+                        if c.dims == (k,) and o.dims == (k,):
                             raise ValueError(f"index conflict on {k!r} after alignment")
+                        if c.dims == (k,) or o.dims == (k,):  # an index wins over a scalar coordinate of the same name
+                            coords[k] = c if c.dims == (k,) else o
+                            continue
                         del coords[k]
                         conflict.add(k)
                 else:
@@ -844,6 +849,15 @@ class DataArray:
     def coarsen(self, dim=None, boundary="exact", side="left", coord_func="mean", **kw):
         return _Coarsen(self, dict(dim or {}, **kw), boundary, side, coord_func)
 
+    def pipe(self, func, *args, **kw):
+        return func(self, *args, **kw)
+
+    def chunk(self, chunks=None, **kw):
+        return self
+
+    def reindex_like(self, other, method=None):
+        return self.reindex({d: other._coords[d].data for d in self.dims if d in other._coords and other._coords[d].dims == (d,)}, method=method)
+
     def to_dataset(self, name=None):
         n = name or self.name
         if n is None:
@@ -1172,7 +1186,7 @@ class Dataset:
                 raise ValueError(f"cannot drop {n!r}: not in the dataset")
         return out
 
-    def drop_dims(self, dims):
+    def drop_dims(self, dims, errors="raise"):
         if isinstance(dims, str):
             dims = [dims]
         out = self.copy()
@@ -1299,18 +1313,23 @@ def where(cond, x, y, keep_attrs=None):
 
 def apply_ufunc(func, *args, input_core_dims=None, output_core_dims=((),), vectorize=False, dask=None,
                 output_dtypes=None, **kw):
-    """the one form compress_pulse uses: a single labelled argument, core dims moved last, python loop over
-    the remaining dims (vectorize=True), output core dims appended (ek80_complex.py:352-360)."""
-    if len(args) != 1 or not vectorize or input_core_dims is None or len(output_core_dims) != 1:
+    """the vectorize=True form: labelled arguments with identical loop dims, core dims moved last, python loop over the
+    remaining dims, output core dims appended (ek80_complex.py:352-360, clean/api.py:253-263, 348-357)."""
+    if not args or not vectorize or input_core_dims is None or len(output_core_dims) != 1 or len(input_core_dims) != len(args):
         raise NotImplementedError("apply_ufunc form not supported by xrlite")
-    (a,) = args
-    core = list(input_core_dims[0])
-    loop = [d for d in a.dims if d not in core]
-    arr = a.transpose(*loop, *core)._data
-    lshape = arr.shape[: len(loop)]
+    a = args[0]
+    loop = [d for d in a.dims if d not in input_core_dims[0]]
+    arrs = []
+    for x, core in zip(args, input_core_dims):
+        if [d for d in x.dims if d not in core] != loop and sorted(d for d in x.dims if d not in core) != sorted(loop):
+            raise NotImplementedError("apply_ufunc: arguments with different loop dims")
+        arrs.append(x.transpose(*loop, *core)._data)
+    lshape = arrs[0].shape[: len(loop)]
+    if any(r.shape[: len(loop)] != lshape for r in arrs):
+        raise ValueError("apply_ufunc: loop dimensions differ in size")
     out = None
     for ix in np.ndindex(*lshape):
-        r = np.asarray(func(arr[ix]))
+        r = np.asarray(func(*[r[ix] for r in arrs]))
         if out is None:
             out = np.empty(lshape + r.shape, dtype=(output_dtypes[0] if output_dtypes else r.dtype))
         out[ix] = r
@@ -1318,8 +1337,29 @@ def apply_ufunc(func, *args, input_core_dims=None, output_core_dims=((),), vecto
     return DataArray(out, {k: c for k, c in a._coords.items() if set(c.dims) <= set(dims)}, dims, a.name)
 
 
+def full_like(other, fill_value, dtype=None):
+    return other._new(np.full(other.shape, fill_value, dtype=dtype if dtype is not None else other.dtype))
+
+
+def zeros_like(other, dtype=None):
+    return full_like(other, 0, dtype)
+
+
+def ones_like(other, dtype=None):
+    return full_like(other, 1, dtype)
+
+
 def concat(objs, dim, **kw):
-    raise NotImplementedError("xrlite.concat")
+    """DataArrays that each carry `dim` as a scalar coordinate (the result of isel(dim=i)) stacked along a new leading
+    dimension `dim` (clean/utils.py:181, 313)."""
+    objs = list(objs)
+    first = objs[0]
+    if not all(isinstance(o, DataArray) and o.dims == first.dims and dim not in o.dims and dim in o._coords for o in objs):
+        raise NotImplementedError("xrlite.concat: only scalar-coordinate stacking of equally shaped DataArrays")
+    data = np.stack([o._data for o in objs])
+    coords = {k: c for k, c in first._coords.items() if k != dim and c.dims}
+    coords[dim] = _Coord((dim,), np.array([np.asarray(o._coords[dim].data)[()] for o in objs]))
+    return DataArray(data, coords, (dim,) + tuple(first.dims), first.name)
 
 
 def set_options(**kw):

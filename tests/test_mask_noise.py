@@ -483,3 +483,94 @@ def test_impulse_depth_single_pass_equals_two_kernel_path(ep, C, P, R, k, db):
     g1, g2 = m1.cpu().numpy().astype(bool), m2.cpu().numpy().astype(bool)
     np.testing.assert_array_equal(g1[sure], g2[sure])
     assert g2.any() and not g2.all()
+
+
+# ---- clean.mask_attenuated_signal (clean/api.py:269-359) ---------------------------------------------------------------
+def _host_ds(Sv, depth, range_var="depth"):
+    from echopype_b200.dataset import Dataset
+
+    C, P, R = Sv.shape
+    dims = ("channel", "ping_time", "range_sample")
+    return Dataset({"Sv": (dims, Sv.astype(np.float32)), range_var: (dims, depth.astype(np.float32))},
+                   coords={"channel": np.array([f"ch{i}" for i in range(C)], dtype=object),
+                           "ping_time": np.datetime64("2024-01-01") + np.arange(P) * np.timedelta64(1, "s"), "range_sample": np.arange(R)})
+
+
+def test_mask_attenuated_signal_argument_errors():
+    """tests/clean/test_noise.py:46-68 (range variable missing), :772-789 (upper limit below lower limit): ValueError
+    before any device work."""
+    import echopype_b200 as ep
+
+    Sv, depth = _mock(1, 8, 32)
+    with pytest.raises(ValueError, match="`range_var` must be either `echo_range` or `depth`."):
+        ep.clean.mask_attenuated_signal(_host_ds(Sv, depth), range_var="range")
+    with pytest.raises(ValueError, match="Masking attenuated signal requires `depth` data variable in `ds_Sv`."):
+        ep.clean.mask_attenuated_signal(_host_ds(Sv, depth, "echo_range"))
+    with pytest.raises(ValueError, match="Minimum range has to be shorter than maximum range"):
+        ep.clean.mask_attenuated_signal(_host_ds(Sv, depth), upper_limit_sl="180m", lower_limit_sl="170m")
+    with pytest.raises(ValueError, match="Decibal string"):
+        ep.clean.mask_attenuated_signal(_host_ds(Sv, depth), attenuation_signal_threshold="8")
+
+
+def test_oracle_attenuated_properties():
+    """Whole pings only; nothing within num_side_pings of the ends; a ping 20 dB below its neighbours in the layer is
+    masked with a negative threshold and its neighbours are not (the block median hardly moves)."""
+    P, R, n = 30, 120, 4
+    depth = np.broadcast_to(1.0 + 0.5 * np.arange(R), (1, P, R)).copy()
+    Sv = np.full((1, P, R), -60.0) + np.random.default_rng(0).normal(0, 0.1, (1, P, R))
+    Sv[0, 12] -= 20.0
+    m = oclean.mask_attenuated_signal(Sv, depth, 20.0, 40.0, n, -6.0)
+    assert m[0, 12].all() and m.sum() == R
+    m8 = oclean.mask_attenuated_signal(Sv, depth, 20.0, 40.0, n, 8.0)  # the reference's default sign: everything assessable
+    assert m8[0, n:P - n].all() and not m8[0, :n].any() and not m8[0, P - n:].any()
+    assert not oclean.mask_attenuated_signal(Sv, depth, 400.0, 500.0, n, 8.0).any()  # outside the searching range
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,P,R,n,upper,lower,thr", [
+    (2, 80, 512, 5, 20.0, 60.0, -2.0),       # staged windows (10 x ~210 / ~160 keys)
+    (1, 64, 4096, 15, 100.0, 400.0, -1.5),   # 30 x 1579 keys > staging buffer: selection from global memory
+    (2, 33, 203, 2, 10.0, 30.0, -3.0),       # R not a multiple of 16: byte stores
+    (3, 41, 256, 1, 10.0, 10.3, 0.5),        # one- or two-sample layers
+    (1, 20, 128, 0, 15.0, 20.0, 8.0),        # num_side_pings = 0: empty block, nothing masked
+    (1, 9, 64, 6, 5.0, 9.0, 8.0),            # no ping has num_side_pings neighbours on both sides
+])
+def test_mask_attenuated_signal_vs_oracle(ep, C, P, R, n, upper, lower, thr):
+    Sv, depth = _mock(C, P, R, seed=R + n)
+    rng = np.random.default_rng(P)
+    Sv[:, rng.integers(0, P, max(2, P // 6)), :] -= 8.0  # attenuated pings
+    depth[0, 5, R // 2:] = np.nan  # the short ping has no depth where it has no samples: np.argmin lands on the first NaN
+    Sv32, d32 = Sv.astype(np.float32).astype(np.float64), depth.astype(np.float32).astype(np.float64)
+    want = oclean.mask_attenuated_signal(Sv32, d32, upper, lower, n, thr)
+    got = ep.clean.mask_attenuated_signal(_ds(ep, Sv, depth), f"{upper}m", f"{lower}m", n, f"{thr}dB")
+    assert tuple(got.dims) == ("channel", "ping_time", "range_sample") and got.values.shape == (C, P, R)
+    g = got.values.astype(bool)
+    assert np.all(g == g[:, :, :1])
+    sure = np.ones((C, P), dtype=bool)
+    for c in range(C):
+        sure[c] = ~(np.abs(oclean.attenuated_signal_margin(Sv32[c], d32[c], upper, lower, n, thr)) < 1e-9)
+    assert sure.mean() > 0.98
+    np.testing.assert_array_equal(g[sure], want[sure])
+    if n in (2, 5, 15, 1):
+        assert want.any() and not want.all()
+    else:
+        assert not want.any()
+    # the limits the kernel found are np.argmin's
+    from echopype_b200 import kernels
+    import torch
+
+    _, lim = kernels.attenuated_signal_mask(torch.from_numpy(Sv.astype(np.float32)).cuda(), torch.from_numpy(depth.astype(np.float32)).cuda(),
+                                            C, P, R, upper, lower, n, thr)
+    lim = lim.cpu().numpy()
+    with np.errstate(invalid="ignore"):
+        np.testing.assert_array_equal(lim[..., 0], np.argmin(np.abs(d32 - upper), axis=2))
+        np.testing.assert_array_equal(lim[..., 1], np.argmin(np.abs(d32 - lower), axis=2))
+
+
+@pytest.mark.gpu
+def test_mask_attenuated_signal_outside_searching_range(ep):
+    """tests/clean/test_noise.py:792-815: limits beyond the echosounder range give an all-False mask."""
+    Sv, depth = _mock(2, 12, 64)
+    got = ep.clean.mask_attenuated_signal(_ds(ep, Sv, depth), "1800m", "2800m", 15, "-6dB")
+    assert got.values.shape == (2, 12, 64) and not got.values.any()
+    assert not ep.clean.mask_attenuated_signal(_ds(ep, Sv, depth)).values.any()  # the defaults (400 m .. 500 m) as well

@@ -70,6 +70,8 @@ def main():
     if want("transient"):
         timed("clean.mask_transient_noise(index binning)", lambda: ep.clean.mask_transient_noise(ds, "nanmean", "10m", 25, "250.0m", "12.0dB", "echo_range", use_index_binning=True), n)
         timed("clean.mask_transient_noise(default: depth values)", lambda: ep.clean.mask_transient_noise(ds, "nanmean", "10m", 25, "250.0m", "12.0dB", "echo_range"), n)
+    if want("attenuated"):
+        timed("clean.mask_attenuated_signal(400m, 500m, 15, 8dB)", lambda: ep.clean.mask_attenuated_signal(ds, "400.0m", "500.0m", 15, "8.0dB", "echo_range"), n)
 
 
 if __name__ == "__main__":
