@@ -11,15 +11,18 @@
 //   attenuated_limits_kernel : one warp per (channel, ping) row, one pass over the range variable (4 B per sample)
 //   attenuated_ping_kernel   : one CTA per (channel, ping); the 2 n x (lw - up) window is staged once into shared
 //                              memory as keys (it is read from L2: neighbouring pings share all but one row) and the
-//                              middle elements are found by a 32-step bitwise radix select with one barrier per step;
-//                              windows larger than the staging buffer are selected straight from global memory.
+//                              middle elements are found by a 32-step bitwise radix select - 16-byte shared-memory
+//                              reads, one xor-and-compare per key, one barrier per step; the ping's own layer is
+//                              selected from a second staged copy.  Windows larger than the staging buffer are
+//                              selected straight from global memory.
 #include "epb_common.cuh"
 
 namespace {
 using namespace epb;
 
 constexpr unsigned kNaNKey = 0xffffffffu;  // sorts above every value (incl. +inf = 0xff800000)
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;  // 16 warps: the selection passes are shared-memory latency bound
+constexpr int kWarps = kThreads / 32;
 
 __device__ __forceinline__ unsigned to_key(float v) {
   if (!(v == v)) return kNaNKey;
@@ -66,25 +69,25 @@ __global__ void __launch_bounds__(256) attenuated_limits_kernel(const float* __r
   }
 }
 
-// sum over the CTA; s_red is [2][8], `parity` alternates between consecutive calls so that one barrier per call suffices
+// sum over the CTA; s_red is [2][kWarps], `parity` alternates between consecutive calls so that one barrier per call suffices
 __device__ __forceinline__ int block_sum(int v, int* s_red, int parity) {
   v = __reduce_add_sync(0xffffffffu, v);
-  int* s = s_red + 8 * parity;
+  int* s = s_red + kWarps * parity;
   if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
   __syncthreads();
   int t = 0;
 #pragma unroll
-  for (int i = 0; i < kThreads / 32; ++i) t += s[i];
+  for (int i = 0; i < kWarps; ++i) t += s[i];
   return t;
 }
 __device__ __forceinline__ unsigned block_min(unsigned v, int* s_red, int parity) {
   v = __reduce_min_sync(0xffffffffu, v);
-  unsigned* s = reinterpret_cast<unsigned*>(s_red) + 8 * parity;
+  unsigned* s = reinterpret_cast<unsigned*>(s_red) + kWarps * parity;
   if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
   __syncthreads();
   unsigned t = kNaNKey;
 #pragma unroll
-  for (int i = 0; i < kThreads / 32; ++i) t = min(t, s[i]);
+  for (int i = 0; i < kWarps; ++i) t = min(t, s[i]);
   return t;
 }
 
@@ -101,10 +104,12 @@ __device__ int block_median_keys(Scan scan, int* s_red, int& parity, unsigned& k
   int k = (m - 1) >> 1;
   unsigned prefix = 0u;
   for (int bit = 31; bit >= 0; --bit) {
-    const unsigned hi_mask = (bit == 31) ? 0u : (0xffffffffu << (bit + 1));
+    // candidates share the bits above `bit` with the prefix; those with a zero at `bit` differ from the prefix in none of
+    // the bits >= bit (the prefix is still zero there).  NaN keys are all ones: never counted, and k < m keeps the
+    // selection among the valid keys
+    const unsigned test = 0xffffffffu << bit;
     int zeros = 0;
-    // NaN keys are all ones: never counted as a zero bit, and k < m keeps the selection among the valid keys
-    scan([&](unsigned key) { zeros += (((key & hi_mask) == prefix) && !((key >> bit) & 1u)) ? 1 : 0; });
+    scan([&](unsigned key) { zeros += (((key ^ prefix) & test) == 0u) ? 1 : 0; });
     const int z = block_sum(zeros, s_red, parity);
     parity ^= 1;
     if (k >= z) {
@@ -137,53 +142,87 @@ __device__ __forceinline__ double median_db(unsigned ka, unsigned kb) {
   return 10.0 * log10((a + b) * 0.5);
 }
 
+// keys staged in shared memory, padded with NaN keys to a multiple of 4 * kThreads: every thread reads 16 bytes per step
+struct StagedScan {
+  const uint4* keys;
+  int steps;  // padded length / (4 * kThreads)
+  template <typename F>
+  __device__ __forceinline__ void operator()(F&& f) const {
+#pragma unroll 2
+    for (int i = 0; i < steps; ++i) {
+      const uint4 v = keys[threadIdx.x + i * kThreads];
+      f(v.x), f(v.y), f(v.z), f(v.w);
+    }
+  }
+};
+// keys converted on the fly from `rows` rows of `w` samples in global memory (windows beyond the staging buffer)
+struct GlobalScan {
+  const float* base;
+  int rows, w;
+  long long pitch;
+  template <typename F>
+  __device__ __forceinline__ void operator()(F&& f) const {
+    for (int q = 0; q < rows; ++q)
+      for (int j = threadIdx.x; j < w; j += kThreads) f(to_key(__ldg(base + q * pitch + j)));
+  }
+};
+
+// stage `rows` rows of `w` samples as keys, row after row, NaN keys up to the next multiple of 4 * kThreads; returns the
+// number of 16-byte steps per thread.  The caller has made sure that nobody still reads s_keys.
+__device__ __forceinline__ int stage_keys(unsigned* s_keys, const float* base, int rows, int w, long long pitch) {
+  const int n = rows * w, padded = (n + 4 * kThreads - 1) / (4 * kThreads) * (4 * kThreads);
+  for (int q = 0; q < rows; ++q)
+    for (int j = threadIdx.x; j < w; j += kThreads) s_keys[q * w + j] = to_key(__ldg(base + q * pitch + j));
+  for (int e = n + threadIdx.x; e < padded; e += kThreads) s_keys[e] = kNaNKey;
+  __syncthreads();
+  return padded / (4 * kThreads);
+}
+
 __global__ void __launch_bounds__(kThreads) attenuated_ping_kernel(const float* __restrict__ Sv, const int* __restrict__ limits,
                                                                    unsigned char* __restrict__ mask, long long nrows, long long P,
                                                                    int R, int n_side, double thr, int cap_keys) {
-  extern __shared__ unsigned s_keys[];
-  __shared__ int s_red[16];
+  extern __shared__ __align__(16) unsigned s_keys[];
+  __shared__ int s_red[2 * kWarps];
   const int tid = threadIdx.x;
   int parity = 0;
   const bool wide = ((R & 15) == 0) && ((reinterpret_cast<uintptr_t>(mask) & 15) == 0);
+  constexpr int kQuantum = 4 * kThreads;
   for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
     const long long p = row % P;
     const int up = limits[2 * row], lw = limits[2 * row + 1];
     const int w = lw - up;  // Sv[p, up:lw] is empty when lw <= up: np.all(np.isnan(empty)) is True, the ping is skipped
     bool flag = false;
-    if (w > 0 && p - n_side >= 0 && p + n_side <= P - 1) {
-      unsigned pa, pb, ba, bb;
+    // n_side == 0: the block Sv[p:p] is empty, its median NaN, the comparison False
+    if (w > 0 && n_side > 0 && p - n_side >= 0 && p + n_side <= P - 1) {
+      unsigned pa = 0, pb = 0, ba = 0, bb = 0;
+      int mp, mb = 0;
       const float* prow = Sv + row * (long long)R + up;
-      const int mp = block_median_keys(
-          [&](auto&& f) {
-            for (int j = tid; j < w; j += kThreads) f(to_key(__ldg(prow + j)));
-          },
-          s_red, parity, pa, pb);
-      if (mp > 0 && n_side > 0) {  // n_side == 0: the block Sv[p:p] is empty, its median NaN, the comparison False
-        const float* brow = Sv + (row - n_side) * (long long)R + up;
-        const int rows = 2 * n_side;
-        const long long nkeys = (long long)rows * w;
-        int mb;
-        if (nkeys <= cap_keys) {
-          __syncthreads();  // the previous row's selection has finished reading s_keys
-          for (int q = 0; q < rows; ++q)
-            for (int j = tid; j < w; j += kThreads) s_keys[q * w + j] = to_key(__ldg(brow + q * (long long)R + j));
-          __syncthreads();
-          const int n = (int)nkeys;
-          mb = block_median_keys(
-              [&](auto&& f) {
-                for (int e = tid; e < n; e += kThreads) f(s_keys[e]);
-              },
-              s_red, parity, ba, bb);
+      const float* brow = prow - n_side * (long long)R;
+      const int rows = 2 * n_side;
+      const long long nkeys = (long long)rows * w;
+      __syncthreads();  // the previous ping's passes have finished reading s_keys
+      if ((nkeys + kQuantum - 1) / kQuantum * kQuantum <= cap_keys) {
+        // the whole block in shared memory; the ping's own row is row n_side of it, selected from a second, padded copy
+        // behind the block when that fits as well, else from global memory
+        const int bsteps = stage_keys(s_keys, brow, rows, w, R);
+        const int boff = bsteps * kQuantum;
+        if (boff + (w + kQuantum - 1) / kQuantum * kQuantum <= cap_keys) {
+          const int psteps = stage_keys(s_keys + boff, prow, 1, w, R);
+          mp = block_median_keys(StagedScan{reinterpret_cast<const uint4*>(s_keys + boff), psteps}, s_red, parity, pa, pb);
         } else {
-          mb = block_median_keys(
-              [&](auto&& f) {
-                for (int q = 0; q < rows; ++q)
-                  for (int j = tid; j < w; j += kThreads) f(to_key(__ldg(brow + q * (long long)R + j)));
-              },
-              s_red, parity, ba, bb);
+          mp = block_median_keys(GlobalScan{prow, 1, w, R}, s_red, parity, pa, pb);
         }
-        if (mb > 0) flag = (median_db(pa, pb) - median_db(ba, bb)) < thr;  // NaN (-inf - -inf) compares False
+        if (mp > 0) mb = block_median_keys(StagedScan{reinterpret_cast<const uint4*>(s_keys), bsteps}, s_red, parity, ba, bb);
+      } else {
+        if ((w + kQuantum - 1) / kQuantum * kQuantum <= cap_keys) {
+          const int psteps = stage_keys(s_keys, prow, 1, w, R);
+          mp = block_median_keys(StagedScan{reinterpret_cast<const uint4*>(s_keys), psteps}, s_red, parity, pa, pb);
+        } else {
+          mp = block_median_keys(GlobalScan{prow, 1, w, R}, s_red, parity, pa, pb);
+        }
+        if (mp > 0) mb = block_median_keys(GlobalScan{brow, rows, w, R}, s_red, parity, ba, bb);
       }
+      if (mp > 0 && mb > 0) flag = (median_db(pa, pb) - median_db(ba, bb)) < thr;  // NaN (-inf - -inf) compares False
     }
     unsigned char* out = mask + row * (long long)R;
     if (wide) {

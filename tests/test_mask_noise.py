@@ -533,6 +533,8 @@ def test_oracle_attenuated_properties():
     (2, 33, 203, 2, 10.0, 30.0, -3.0),       # R not a multiple of 16: byte stores
     (3, 41, 256, 1, 10.0, 10.3, 0.5),        # one- or two-sample layers
     (1, 20, 128, 0, 15.0, 20.0, 8.0),        # num_side_pings = 0: empty block, nothing masked
+    (1, 6, 16384, 1, 100.0, 2400.0, 0.2),    # block staged (24 210 keys), the ping's copy does not fit behind it: from global
+    (1, 7, 32768, 1, 100.0, 6000.0, 0.2),    # layer longer than the staging buffer: both selections from global memory
     (1, 9, 64, 6, 5.0, 9.0, 8.0),            # no ping has num_side_pings neighbours on both sides
 ])
 def test_mask_attenuated_signal_vs_oracle(ep, C, P, R, n, upper, lower, thr):
