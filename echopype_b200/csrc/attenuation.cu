@@ -69,37 +69,50 @@ __global__ void __launch_bounds__(256) attenuated_limits_kernel(const float* __r
   }
 }
 
-// sum over the CTA; s_red is [2][kWarps], `parity` alternates between consecutive calls so that one barrier per call suffices
-__device__ __forceinline__ int block_sum(int v, int* s_red, int parity) {
+// CTA-wide reductions.  The scratch lives in shared memory; the slot / parity cursors are per-thread registers that
+// advance identically in every thread (all calls sit in CTA-uniform control flow), so ONE barrier per call suffices:
+//  * sums: the warp leaders add into cnt[slot]; thread 0 clears cnt[slot + 1] for the next call (its last readers passed
+//    the previous barrier, its next writers come after this one); three slots in rotation
+//  * min / max: per-warp values in one of two buffers, every thread combines them after the barrier
+struct Scratch {
+  int cnt[3];
+  int cursor;  // compaction write position
+  unsigned ext[2][kWarps];
+};
+struct Cursor {
+  int slot = 0, parity = 0;
+};
+__device__ __forceinline__ int block_sum(int v, Scratch* sc, Cursor& cu) {
   v = __reduce_add_sync(0xffffffffu, v);
-  int* s = s_red + kWarps * parity;
-  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+  const int nxt = (cu.slot == 2) ? 0 : cu.slot + 1;
+  if (threadIdx.x == 0) sc->cnt[nxt] = 0;
+  if ((threadIdx.x & 31) == 0 && v != 0) atomicAdd(&sc->cnt[cu.slot], v);
   __syncthreads();
-  int t = 0;
-#pragma unroll
-  for (int i = 0; i < kWarps; ++i) t += s[i];
+  const int t = sc->cnt[cu.slot];
+  cu.slot = nxt;
   return t;
 }
-__device__ __forceinline__ unsigned block_min(unsigned v, int* s_red, int parity) {
-  v = __reduce_min_sync(0xffffffffu, v);
-  unsigned* s = reinterpret_cast<unsigned*>(s_red) + kWarps * parity;
+template <bool kMax>
+__device__ __forceinline__ unsigned block_extreme(unsigned v, Scratch* sc, Cursor& cu) {
+  v = kMax ? __reduce_max_sync(0xffffffffu, v) : __reduce_min_sync(0xffffffffu, v);
+  unsigned* s = sc->ext[cu.parity];
   if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
   __syncthreads();
-  unsigned t = kNaNKey;
+  unsigned t = s[0];
 #pragma unroll
-  for (int i = 0; i < kWarps; ++i) t = min(t, s[i]);
+  for (int i = 1; i < kWarps; ++i) t = kMax ? max(t, s[i]) : min(t, s[i]);
+  cu.parity ^= 1;
   return t;
 }
 
 // The middle element(s) of the valid keys `scan` enumerates (every thread of the CTA calls scan(f); f(key) is invoked once
 // per element the thread owns).  m = number of valid keys; ka / kb = keys of rank (m-1)/2 and m/2 (np.nanmedian averages
-// them).  Returns m; ka, kb undefined when m == 0.  `parity` is the running barrier parity of block_sum.
+// them).  Returns m; ka, kb undefined when m == 0.  Bitwise radix select: one counting pass per bit.
 template <typename Scan>
-__device__ int block_median_keys(Scan scan, int* s_red, int& parity, unsigned& ka, unsigned& kb) {
+__device__ int block_median_keys(Scan scan, Scratch* sc, Cursor& cu, unsigned& ka, unsigned& kb) {
   int cnt = 0;
   scan([&](unsigned key) { cnt += (key != kNaNKey) ? 1 : 0; });
-  const int m = block_sum(cnt, s_red, parity);
-  parity ^= 1;
+  const int m = block_sum(cnt, sc, cu);
   if (m == 0) return 0;
   int k = (m - 1) >> 1;
   unsigned prefix = 0u;
@@ -110,8 +123,7 @@ __device__ int block_median_keys(Scan scan, int* s_red, int& parity, unsigned& k
     const unsigned test = 0xffffffffu << bit;
     int zeros = 0;
     scan([&](unsigned key) { zeros += (((key ^ prefix) & test) == 0u) ? 1 : 0; });
-    const int z = block_sum(zeros, s_red, parity);
-    parity ^= 1;
+    const int z = block_sum(zeros, sc, cu);
     if (k >= z) {
       prefix |= 1u << bit;
       k -= z;
@@ -127,10 +139,8 @@ __device__ int block_median_keys(Scan scan, int* s_red, int& parity, unsigned& k
       eq += (key == prefix) ? 1 : 0;
       if (key > prefix && key != kNaNKey) above = min(above, key);
     });
-    const int neq = block_sum(eq, s_red, parity);
-    parity ^= 1;
-    const unsigned mn = block_min(above, s_red, parity);
-    parity ^= 1;
+    const int neq = block_sum(eq, sc, cu);
+    const unsigned mn = block_extreme<false>(above, sc, cu);
     if (k + 1 >= neq) kb = mn;
   }
   return m;
@@ -167,26 +177,126 @@ struct GlobalScan {
   }
 };
 
-// stage `rows` rows of `w` samples as keys, row after row, NaN keys up to the next multiple of 4 * kThreads; returns the
+constexpr int kQuantum = 4 * kThreads;  // staged arrays are NaN-padded to a multiple of this many keys
+__device__ __forceinline__ int round_up_quantum(long long n) { return (int)((n + kQuantum - 1) / kQuantum * kQuantum); }
+
+// stage `rows` rows of `w` samples as keys, row after row, NaN keys up to the next multiple of kQuantum; returns the
 // number of 16-byte steps per thread.  The caller has made sure that nobody still reads s_keys.
 __device__ __forceinline__ int stage_keys(unsigned* s_keys, const float* base, int rows, int w, long long pitch) {
-  const int n = rows * w, padded = (n + 4 * kThreads - 1) / (4 * kThreads) * (4 * kThreads);
+  const int n = rows * w, padded = round_up_quantum(n);
   for (int q = 0; q < rows; ++q)
     for (int j = threadIdx.x; j < w; j += kThreads) s_keys[q * w + j] = to_key(__ldg(base + q * pitch + j));
   for (int e = n + threadIdx.x; e < padded; e += kThreads) s_keys[e] = kNaNKey;
   __syncthreads();
-  return padded / (4 * kThreads);
+  return padded / kQuantum;
+}
+
+// copy the valid keys of `cur` that agree with `prefix` in the bits >= bit to dst (any order), NaN-pad to the quantum.
+// `cand` = their number (known from the counting passes).  Warp-aggregated: one shared atomic per warp and group of 32 keys.
+__device__ __forceinline__ void compact_keys(const uint4* cur, int steps, unsigned prefix, int bit, unsigned* dst, int cand,
+                                             Scratch* sc) {
+  if (threadIdx.x == 0) sc->cursor = 0;
+  __syncthreads();
+  const unsigned test = 0xffffffffu << bit;
+  const unsigned lower_lanes = (1u << (threadIdx.x & 31)) - 1u;
+  for (int i = 0; i < steps; ++i) {
+    const uint4 v = cur[threadIdx.x + i * kThreads];
+    const unsigned keys4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const unsigned key = keys4[q];
+      const bool take = (((key ^ prefix) & test) == 0u) && (key != kNaNKey);
+      const unsigned ballot = __ballot_sync(0xffffffffu, take);
+      if (ballot != 0u) {  // warp-uniform
+        int base = 0;
+        if ((threadIdx.x & 31) == 0) base = atomicAdd(&sc->cursor, __popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (take) dst[base + __popc(ballot & lower_lanes)] = key;
+      }
+    }
+  }
+  for (int e = cand + threadIdx.x; e < round_up_quantum(cand); e += kThreads) dst[e] = kNaNKey;  // disjoint from the copies
+  __syncthreads();
+}
+
+// block_median_keys for keys staged at s_keys[src_off, src_off + steps * kQuantum): the same selection with two short cuts.
+//  * the bits that the smallest and the largest valid key share are the median's too: the bit loop starts at the highest
+//    bit in which they differ (Sv values of one layer share sign and exponent: nine passes less);
+//  * once the candidates (keys agreeing with the prefix so far) are a quarter of the array being scanned they are copied
+//    to the scratch region [scr_off, cap) and the remaining passes scan only them; again when they are a quarter of that.
+// The staged array itself stays intact (the even-count step needs the smallest key ABOVE the median, which need not be a
+// candidate).
+__device__ int staged_median_keys(unsigned* s_keys, int src_off, int steps, int scr_off, int cap, Scratch* sc, Cursor& cu,
+                                  unsigned& ka, unsigned& kb) {
+  const uint4* src = reinterpret_cast<const uint4*>(s_keys + src_off);
+  int cnt = 0;
+  unsigned lo = kNaNKey, hi = 0u;
+  StagedScan{src, steps}([&](unsigned key) {
+    const bool ok = key != kNaNKey;
+    cnt += ok ? 1 : 0;
+    lo = min(lo, key);
+    hi = max(hi, ok ? key : 0u);
+  });
+  const int m = block_sum(cnt, sc, cu);
+  if (m == 0) return 0;
+  lo = block_extreme<false>(lo, sc, cu);
+  hi = block_extreme<true>(hi, sc, cu);
+  int k = (m - 1) >> 1;
+  unsigned prefix = lo;
+  int bit = -1;  // all valid keys equal: nothing to select
+  if (lo != hi) {
+    bit = 31 - __clz(lo ^ hi);
+    prefix = lo & ~((2u << bit) - 1u);  // the shared bits above `bit` (2u << 31 == 0: no shared bit, prefix 0)
+  }
+  const uint4* cur = src;
+  int cur_steps = steps, cand = m, free_off = scr_off;
+  for (; bit >= 0; --bit) {
+    const unsigned test = 0xffffffffu << bit;
+    int zeros = 0;
+    StagedScan{cur, cur_steps}([&](unsigned key) { zeros += (((key ^ prefix) & test) == 0u) ? 1 : 0; });
+    const int z = block_sum(zeros, sc, cu);
+    if (k >= z) {
+      prefix |= 1u << bit;
+      k -= z;
+      cand -= z;
+    } else {
+      cand = z;
+    }
+    if (bit > 0 && cur_steps > 1 && cand * 4 <= cur_steps * kQuantum && free_off + round_up_quantum(cand) <= cap) {
+      compact_keys(cur, cur_steps, prefix, bit, s_keys + free_off, cand, sc);
+      cur = reinterpret_cast<const uint4*>(s_keys + free_off);
+      cur_steps = round_up_quantum(cand) / kQuantum;
+      free_off += cur_steps * kQuantum;
+    }
+  }
+  ka = kb = prefix;
+  if (!(m & 1)) {
+    // copies of the median value are all candidates (count them in `cur`); the smallest key above it is looked for in
+    // the whole staged array
+    int eq = 0;
+    unsigned above = kNaNKey;
+    StagedScan{cur, cur_steps}([&](unsigned key) { eq += (key == prefix) ? 1 : 0; });
+    StagedScan{src, steps}([&](unsigned key) {
+      if (key > prefix && key != kNaNKey) above = min(above, key);
+    });
+    const int neq = block_sum(eq, sc, cu);
+    const unsigned mn = block_extreme<false>(above, sc, cu);
+    if (k + 1 >= neq) kb = mn;
+  }
+  return m;
 }
 
 __global__ void __launch_bounds__(kThreads) attenuated_ping_kernel(const float* __restrict__ Sv, const int* __restrict__ limits,
                                                                    unsigned char* __restrict__ mask, long long nrows, long long P,
                                                                    int R, int n_side, double thr, int cap_keys) {
   extern __shared__ __align__(16) unsigned s_keys[];
-  __shared__ int s_red[2 * kWarps];
+  __shared__ Scratch s_scratch;
+  Scratch* sc = &s_scratch;
+  Cursor cu;
   const int tid = threadIdx.x;
-  int parity = 0;
+  if (tid < 3) sc->cnt[tid] = 0;
+  __syncthreads();
   const bool wide = ((R & 15) == 0) && ((reinterpret_cast<uintptr_t>(mask) & 15) == 0);
-  constexpr int kQuantum = 4 * kThreads;
   for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
     const long long p = row % P;
     const int up = limits[2 * row], lw = limits[2 * row + 1];
@@ -201,26 +311,27 @@ __global__ void __launch_bounds__(kThreads) attenuated_ping_kernel(const float* 
       const int rows = 2 * n_side;
       const long long nkeys = (long long)rows * w;
       __syncthreads();  // the previous ping's passes have finished reading s_keys
-      if ((nkeys + kQuantum - 1) / kQuantum * kQuantum <= cap_keys) {
+      if (nkeys <= cap_keys && round_up_quantum(nkeys) <= cap_keys) {
         // the whole block in shared memory; the ping's own row is row n_side of it, selected from a second, padded copy
         // behind the block when that fits as well, else from global memory
         const int bsteps = stage_keys(s_keys, brow, rows, w, R);
         const int boff = bsteps * kQuantum;
-        if (boff + (w + kQuantum - 1) / kQuantum * kQuantum <= cap_keys) {
+        if (boff + round_up_quantum(w) <= cap_keys) {
           const int psteps = stage_keys(s_keys + boff, prow, 1, w, R);
-          mp = block_median_keys(StagedScan{reinterpret_cast<const uint4*>(s_keys + boff), psteps}, s_red, parity, pa, pb);
+          mp = staged_median_keys(s_keys, boff, psteps, boff + psteps * kQuantum, cap_keys, sc, cu, pa, pb);
         } else {
-          mp = block_median_keys(GlobalScan{prow, 1, w, R}, s_red, parity, pa, pb);
+          mp = block_median_keys(GlobalScan{prow, 1, w, R}, sc, cu, pa, pb);
         }
-        if (mp > 0) mb = block_median_keys(StagedScan{reinterpret_cast<const uint4*>(s_keys), bsteps}, s_red, parity, ba, bb);
+        // the ping's copy is dead now: the block's candidates may be compacted over it
+        if (mp > 0) mb = staged_median_keys(s_keys, 0, bsteps, boff, cap_keys, sc, cu, ba, bb);
       } else {
-        if ((w + kQuantum - 1) / kQuantum * kQuantum <= cap_keys) {
+        if (w <= cap_keys && round_up_quantum(w) <= cap_keys) {
           const int psteps = stage_keys(s_keys, prow, 1, w, R);
-          mp = block_median_keys(StagedScan{reinterpret_cast<const uint4*>(s_keys), psteps}, s_red, parity, pa, pb);
+          mp = staged_median_keys(s_keys, 0, psteps, psteps * kQuantum, cap_keys, sc, cu, pa, pb);
         } else {
-          mp = block_median_keys(GlobalScan{prow, 1, w, R}, s_red, parity, pa, pb);
+          mp = block_median_keys(GlobalScan{prow, 1, w, R}, sc, cu, pa, pb);
         }
-        if (mp > 0) mb = block_median_keys(GlobalScan{brow, rows, w, R}, s_red, parity, ba, bb);
+        if (mp > 0) mb = block_median_keys(GlobalScan{brow, rows, w, R}, sc, cu, ba, bb);
       }
       if (mp > 0 && mb > 0) flag = (median_db(pa, pb) - median_db(ba, bb)) < thr;  // NaN (-inf - -inf) compares False
     }

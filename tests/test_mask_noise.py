@@ -529,6 +529,7 @@ def test_oracle_attenuated_properties():
 @pytest.mark.gpu
 @pytest.mark.parametrize("C,P,R,n,upper,lower,thr", [
     (2, 80, 512, 5, 20.0, 60.0, -2.0),       # staged windows (10 x ~210 / ~160 keys)
+    (1, 40, 2048, 10, 100.0, 250.0, -1.0),   # 20 x 789 keys = 8 staged steps: the candidates are compacted twice
     (1, 64, 4096, 15, 100.0, 400.0, -1.5),   # 30 x 1579 keys > staging buffer: selection from global memory
     (2, 33, 203, 2, 10.0, 30.0, -3.0),       # R not a multiple of 16: byte stores
     (3, 41, 256, 1, 10.0, 10.3, 0.5),        # one- or two-sample layers
@@ -553,7 +554,7 @@ def test_mask_attenuated_signal_vs_oracle(ep, C, P, R, n, upper, lower, thr):
         sure[c] = ~(np.abs(oclean.attenuated_signal_margin(Sv32[c], d32[c], upper, lower, n, thr)) < 1e-9)
     assert sure.mean() > 0.98
     np.testing.assert_array_equal(g[sure], want[sure])
-    if n in (2, 5, 15, 1):
+    if n in (2, 5, 10, 15, 1):
         assert want.any() and not want.all()
     else:
         assert not want.any()
