@@ -9,12 +9,12 @@ root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = os.path.join(root, "echopype_b200", "libepb200.so")
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 archs = sorted(set(re.findall(r"arch = (sm_\w+)", out)))
-WANT = ["UBLKCP", "SYNCS", "UBLKPF", "FFMA2", "FADD2", "FMUL2", "LDGSTS", "MUFU.EX2", "MUFU.LG2", "MUFU.RCP", "LDS.128", "LDG.E.128", "STG.E", "ATOMS",
+WANT = ["UBLKCP", "SYNCS", "UBLKPF", "FFMA2", "FADD2", "FMUL2", "LDGSTS", "MUFU.EX2", "MUFU.LG2", "MUFU.RCP", "LDS.128", "LDG.E.128", "STG.E", "ATOMS", "REDUX", "VOTE",
         "REDG", "DADD", "F2F", "PRMT", "VIMNMX3", "SHFL", "BAR", "STL", "LDL", "UTCHMMA", "UTCQMMA", "HMMA"]
 KEEP = ["pipeline_fast_kernelILi5ELi2ELb1ELb0ELb0ELb0", "pipeline_fast_kernelILi5ELi2ELb1ELb0ELb1ELb0", "pipeline_fast_kernelILi5ELi2ELb1ELb1ELb0ELb0",
         "pipeline_fast_kernelILi5ELi2ELb1ELb0ELb0ELb1", "pipeline_fast_kernelILi1ELi4ELb1ELb0ELb1ELb0", "bin_reduce_staged_kernelIfLb0", "transient_strip_kernelILb0ELb0",
         "transient_strip_kernelILb0ELb1", "impulse_fused_kernel", "impulse_mask_wide_kernel", "pulse_fft_kernelILi4ELi4", "sv_power_vec4ILb1ELb1Ef", "sv_complex_kernel",
-        "noise_estimate_kernel", "coarsen_kernel", "apply_mask_kernel"]
+        "noise_estimate_kernel", "coarsen_kernel", "apply_mask_kernel", "attenuated_ping_kernel", "attenuated_limits_kernel"]
 print("# SASS evidence (cuobjdump -sass echopype_b200/libepb200.so; tools/sass_counts.py): counts of the mnemonics that show the")
 print("# Blackwell-specific paths each kernel uses.  UBLKCP = cp.async.bulk (TMA bulk copy), SYNCS = mbarrier, UBLKPF = TMA L2 prefetch,")
 print("# FFMA2 / FADD2 / FMUL2 = packed FP32 (two lanes per instruction), LDGSTS = cp.async, MUFU.EX2 / LG2 = single-MUFU exp2 / log2.")
