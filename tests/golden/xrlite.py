@@ -81,6 +81,12 @@ class _CoordsView:
     def __getitem__(self, k):
         return self._o._coord_da(k)
 
+    def __setitem__(self, k, v):  # ds.coords["x"] = (dims, data[, attrs]): replaces the coordinate in place
+        c = _as_coord(k, v)
+        if hasattr(self._o, "_check_fits"):
+            self._o._check_fits(k, c)
+        self._o._coords[k] = c
+
 
 def _index_equal(a, b):
     a, b = np.asarray(a), np.asarray(b)

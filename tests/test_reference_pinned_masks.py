@@ -163,3 +163,65 @@ def test_cuda_transient_mask_equals_reference(ep, vec, which, i):
         margin = _f64(Sv) - pooled - thr
     sure = ~(np.abs(margin) < MARGIN_DB)  # NaN margins (no pooled value / NaN Sv) compare False on both sides: kept
     assert sure.mean() > 0.98 and np.array_equal(got[sure], want[sure])
+
+
+# ---- compute_MVBS_index_binning (K7) against the executed reference function (tests/golden/make_golden_commongrid.py) ---
+IB_KEYS = ["ib_a", "ib_b", "ib_c", "ib_d"]
+
+
+@pytest.fixture(scope="module")
+def gvec():
+    return np.load(os.path.join(HERE, "golden", "commongrid_vectors.npz"))
+
+
+@pytest.mark.parametrize("key", IB_KEYS)
+def test_oracle_equals_reference_index_binning(gvec, key):
+    from oracle import commongrid as ogrid
+
+    rsn, pn = (int(v) for v in gvec[f"{key}__args"])
+    got = ogrid.compute_MVBS_index_binning(_f64(gvec[f"{key}__Sv_in"]), _f64(gvec[f"{key}__echo_range_in"]), rsn, pn)
+    want = gvec[f"{key}__Sv"]
+    assert got["Sv"].shape == want.shape and np.array_equal(np.isnan(got["Sv"]), np.isnan(want))
+    np.testing.assert_allclose(got["Sv"], want, rtol=0, atol=1e-11, equal_nan=True)
+    # the coarsened echo_range as the reference computes it (before xarray's index alignment, see the generator's docstring)
+    np.testing.assert_allclose(got["echo_range"], gvec[f"{key}__echo_range_coarsened"], rtol=1e-15, equal_nan=True)
+    np.testing.assert_array_equal(got["actual_range"], gvec[f"{key}__actual_range"])
+    np.testing.assert_array_equal(gvec[f"{key}__range_sample"], np.arange(want.shape[2]))
+
+
+@pytest.mark.parametrize("key", IB_KEYS)
+def test_host_tile_mean_ping_time_equals_coarsened_coordinate(gvec, key):
+    """The ping_time coordinate of the output is the coarsened one (coord_func="mean"): the tile's mean time, NaT padding
+    of a short last tile skipped.  The stored values went through a float64 mean of absolute nanoseconds (256 ns grain)
+    in the labelled-array stand-in, hence the 1 us tolerance; the product averages offsets from the tile's first ping."""
+    from echopype_b200.commongrid.api import _coarsen_time_mean
+
+    pn = int(gvec[f"{key}__args"][1])
+    t_in = gvec[f"{key}__ping_time_in"].astype("datetime64[ns]")
+    got = _coarsen_time_mean(t_in, pn).astype(np.int64)
+    want = gvec[f"{key}__ping_time"]
+    assert got.shape == want.shape and np.max(np.abs(got - want)) < 1000
+    if len(t_in) >= 2 * pn:
+        assert not np.array_equal(got, t_in[::pn].astype(np.int64))  # it is NOT the first ping of the tile
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", IB_KEYS)
+def test_cuda_index_binning_equals_reference(ep, gvec, key):
+    from echopype_b200.dataset import Dataset
+
+    rsn, pn = (int(v) for v in gvec[f"{key}__args"])
+    Sv, er = gvec[f"{key}__Sv_in"], gvec[f"{key}__echo_range_in"]
+    C, P, R = Sv.shape
+    ds = Dataset({"Sv": (DIMS, Sv), "echo_range": (DIMS, er), "frequency_nominal": (("channel",), 38e3 * (1 + np.arange(C)))},
+                 coords={"channel": np.array([f"ch{i}" for i in range(C)], dtype=object),
+                         "ping_time": gvec[f"{key}__ping_time_in"].astype("datetime64[ns]"), "range_sample": np.arange(R)})
+    got = ep.commongrid.compute_MVBS_index_binning(ds, range_sample_num=rsn, ping_num=pn)
+    want = gvec[f"{key}__Sv"]
+    g = np.asarray(got["Sv"].values, dtype=np.float64)
+    assert g.shape == want.shape and np.array_equal(np.isnan(g), np.isnan(want))
+    assert np.nanmax(np.abs(g - want)) < 1e-4  # dB (north_star)
+    np.testing.assert_allclose(np.asarray(got["echo_range"].values), gvec[f"{key}__echo_range_coarsened"], rtol=2e-7, equal_nan=True)
+    assert np.max(np.abs(np.asarray(got["ping_time"].values).astype("datetime64[ns]").astype(np.int64) - gvec[f"{key}__ping_time"])) < 1000
+    np.testing.assert_array_equal(np.asarray(got["range_sample"].values), gvec[f"{key}__range_sample"])
+    np.testing.assert_allclose(got["Sv"].attrs["actual_range"], gvec[f"{key}__actual_range"], atol=0.011)
