@@ -789,8 +789,8 @@ class DataArray:
         from scipy.interpolate import interp1d
 
         ind = dict(coords or {}, **kw)
-        if len(ind) != 1 or method != "linear":
-            raise NotImplementedError("interp: one dim, linear only")
+        if len(ind) != 1 or method not in ("linear", "nearest"):
+            raise NotImplementedError("interp: one dim, linear / nearest only")
         (d, new), = ind.items()
         x = self._coords[d].data
         new_da = new if isinstance(new, DataArray) else None
@@ -804,7 +804,7 @@ class DataArray:
         order = np.argsort(xf, kind="stable")
         ax = self.dims.index(d)
         y = np.take(self._data.astype(np.float64), order, axis=ax)
-        f = interp1d(xf[order], y, kind="linear", axis=ax, bounds_error=False, **dict(kwargs or {}))
+        f = interp1d(xf[order], y, kind=method, axis=ax, bounds_error=False, **dict(kwargs or {}))  # as xarray's missing.py does
         out = f(xnf)
         if new_da is not None and new_da.ndim == 1:
             nd = new_da.dims[0]

@@ -1,0 +1,118 @@
+"""consolidate.add_depth: the oracle, the product's host-side alignment / scaling functions AND the CUDA result against
+outputs of the reference's own code (utils/align.py and consolidate/ek_depth_utils.py imported unmodified, add_depth
+lifted from consolidate/api.py:66-247 and executed by tests/golden/make_golden_consolidate.py)."""
+
+import os
+
+import numpy as np
+import pytest
+
+from oracle import consolidate as ocons
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DIMS = ("channel", "ping_time", "range_sample")
+
+
+@pytest.fixture(scope="module")
+def vec():
+    return np.load(os.path.join(HERE, "golden", "consolidate_vectors.npz"))
+
+
+def _check(got, want, rtol=1e-14):
+    assert got.shape == want.shape and np.array_equal(np.isnan(got), np.isnan(want))
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=0, equal_nan=True)
+
+
+# ---- CPU: oracle == reference --------------------------------------------------------------------------------------------
+def test_oracle_equals_reference_add_depth(vec):
+    er, pt = vec["echo_range"], vec["ping_time"]
+    _check(ocons.add_depth(er), vec["plain__depth"])
+    _check(ocons.add_depth(er, 7.5, np.cos(np.deg2rad(12.0))), vec["numbers__depth"])
+    _check(ocons.add_depth(er, 250.0, np.cos(np.deg2rad(3.0)), downward=False), vec["upward__depth"])
+    t3 = vec["series__t3"]
+    off = ocons.align_nearest(vec["series__off"], t3, pt)
+    np.testing.assert_array_equal(off, vec["series__off_aligned"])
+    _check(ocons.add_depth(er, off, np.cos(np.deg2rad(ocons.align_nearest(vec["series__tilt"], t3, pt)))), vec["series__depth"])
+    _check(ocons.add_depth(er, ocons.align_nearest(vec["onping__off"], pt, pt)), vec["onping__depth"])
+    _check(ocons.add_depth(er, ocons.align_nearest([4.25], pt[3:4], pt), np.cos(np.deg2rad(ocons.align_nearest([20.0], pt[5:6], pt)))),
+           vec["single__depth"])
+    t2 = vec["platform__t2"]
+    td = vec["platform__transducer_offset_z"] - (vec["platform__water_level"] + vec["platform__vertical_offset"])
+    sc = ocons.platform_angle_scaling(vec["platform__pitch"], vec["platform__roll"])
+    np.testing.assert_allclose(ocons.align_nearest(td, t2, pt), vec["platform__transducer_depth"], rtol=1e-15)
+    np.testing.assert_allclose(ocons.align_nearest(sc, t2, pt), vec["platform__scaling"], rtol=1e-15)
+    _check(ocons.add_depth(er, ocons.align_nearest(td, t2, pt), ocons.align_nearest(sc, t2, pt)), vec["platform__depth"])
+    _check(ocons.add_depth(er, ocons.align_nearest(td, t2, pt)), vec["platform_offsets_only__depth"])
+    bs = ocons.beam_angle_scaling(vec["beam__x"], vec["beam__y"], vec["beam__z"])
+    np.testing.assert_allclose(bs, vec["beam__scaling"], rtol=1e-15, equal_nan=True)
+    _check(ocons.add_depth(er, 0.0, bs, per_channel=True), vec["beam__depth"])
+
+
+# ---- CPU: the product's host-side functions == reference ----------------------------------------------------------------
+def _platform(vec):
+    from echopype_b200.dataset import Dataset
+
+    return Dataset({k: (("time2",), vec[f"platform__{k}"]) for k in ("water_level", "vertical_offset", "transducer_offset_z", "pitch", "roll")},
+                   coords={"time2": vec["platform__t2"].astype("datetime64[ns]")})
+
+
+def _beam(vec):
+    from echopype_b200.dataset import Dataset
+
+    return Dataset({f"beam_direction_{n}": (("channel",), vec[f"beam__{n}"]) for n in "xyz"}, coords={"channel": np.array(vec["channel"], dtype=object)})
+
+
+def test_host_alignment_and_scaling_equal_reference(vec):
+    from echopype_b200.consolidate import api as capi
+
+    pt = vec["ping_time"].astype("datetime64[ns]")
+    got = capi.align_to_ping_time(vec["series__off"], vec["series__t3"].astype("datetime64[ns]"), pt)
+    np.testing.assert_array_equal(got, vec["series__off_aligned"])
+    np.testing.assert_allclose(capi.ek_use_platform_vertical_offsets(_platform(vec), pt), vec["platform__transducer_depth"], rtol=1e-15)
+    # cos(pitch) cos(roll) against scipy's rotation matrix element: equal to a few ulp
+    np.testing.assert_allclose(capi.ek_use_platform_angles(_platform(vec), pt), vec["platform__scaling"], rtol=1e-14)
+    np.testing.assert_allclose(capi.ek_use_beam_angles(_beam(vec)), vec["beam__scaling"], rtol=1e-15, equal_nan=True)
+
+
+# ---- GPU: the product == reference ----------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def ep():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import echopype_b200 as ep
+
+    return ep
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["plain", "numbers", "upward", "series", "onping", "single", "platform", "platform_offsets_only", "beam"])
+def test_cuda_add_depth_equals_reference(ep, vec, mode):
+    from echopype_b200.dataset import Dataset, EchoData
+
+    er = vec["echo_range"]
+    C, P, R = er.shape
+    pt = vec["ping_time"].astype("datetime64[ns]")
+    ds = Dataset({"echo_range": (DIMS, er.astype(np.float32)), "Sv": (DIMS, np.zeros((C, P, R), np.float32))},
+                 coords={"channel": np.array(vec["channel"], dtype=object), "ping_time": pt, "range_sample": np.arange(R)})
+
+    def series(values, t_ns, dim="time3"):
+        return ep.DataArray(np.asarray(values, dtype=np.float64), dims=(dim,), coords={dim: np.asarray(t_ns).astype("datetime64[ns]")})
+
+    ed = EchoData("EK60", {"Platform": _platform(vec), "Sonar/Beam_group1": _beam(vec)})
+    kw = {
+        "plain": {},
+        "numbers": dict(depth_offset=7.5, tilt=12.0),
+        "upward": dict(depth_offset=250.0, tilt=3.0, downward=False),
+        "series": dict(depth_offset=series(vec["series__off"], vec["series__t3"]), tilt=series(vec["series__tilt"], vec["series__t3"])),
+        "onping": dict(depth_offset=series(vec["onping__off"], vec["ping_time"], "time_x")),
+        "single": dict(depth_offset=series([4.25], vec["ping_time"][3:4]), tilt=series([20.0], vec["ping_time"][5:6])),
+        "platform": dict(echodata=ed, use_platform_vertical_offsets=True, use_platform_angles=True),
+        "platform_offsets_only": dict(echodata=ed, use_platform_vertical_offsets=True),
+        "beam": dict(echodata=ed, use_beam_angles=True),
+    }[mode]
+    got = np.asarray(ep.consolidate.add_depth(ds, **kw)["depth"].values, dtype=np.float64)
+    want = vec[f"{mode}__depth"]
+    assert got.shape == want.shape and np.array_equal(np.isnan(got), np.isnan(want))
+    np.testing.assert_allclose(got, want, rtol=2.5e-7, atol=1e-6, equal_nan=True)  # float32 depth against the float64 reference
