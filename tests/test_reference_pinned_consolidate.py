@@ -116,3 +116,70 @@ def test_cuda_add_depth_equals_reference(ep, vec, mode):
     want = vec[f"{mode}__depth"]
     assert got.shape == want.shape and np.array_equal(np.isnan(got), np.isnan(want))
     np.testing.assert_allclose(got, want, rtol=2.5e-7, atol=1e-6, equal_nan=True)  # float32 depth against the float64 reference
+
+
+# ---- mask.frequency_differencing against the executed reference function (tests/golden/make_golden_mask.py) ------------
+FD_KEYS = ["f_gt", "f_le", "f_eq", "f_ge", "c_lt", "c_ge"]
+
+
+@pytest.fixture(scope="module")
+def fvec():
+    return np.load(os.path.join(HERE, "golden", "freqdiff_vectors.npz"))
+
+
+def _fd_dataset(fvec):
+    from echopype_b200.dataset import Dataset
+
+    Sv = fvec["Sv"]
+    C, P, R = Sv.shape
+    return Dataset({"Sv": (DIMS, Sv), "frequency_nominal": (("channel",), fvec["frequency_nominal"])},
+                   coords={"channel": np.array(fvec["channel"], dtype=object),
+                           "ping_time": np.datetime64("2024-01-01") + np.arange(P) * np.timedelta64(1, "s"), "range_sample": np.arange(R)})
+
+
+def _fd_kw(fvec, key):
+    import ast
+
+    return ast.literal_eval(str(fvec[f"{key}__kw"]))
+
+
+@pytest.mark.parametrize("key", FD_KEYS)
+def test_oracle_and_host_parser_equal_reference_frequency_differencing(fvec, key):
+    import re
+
+    from echopype_b200.mask.freq_diff import _parse_freq_diff_eq
+    from oracle import mask as omask
+
+    kw = _fd_kw(fvec, key)
+    freqAB, chanAB, operator, diff = _parse_freq_diff_eq(kw.get("freqABEq"), kw.get("chanABEq"))
+    chans, freqs = list(fvec["channel"]), list(fvec["frequency_nominal"])
+    a, b = ([freqs.index(f) for f in freqAB] if freqAB is not None else [chans.index(c) for c in chanAB])
+    # the operation string of the reference's history attribute names the same channels, operator and threshold
+    m = re.fullmatch(r"Sv\['(.+)'\] - Sv\['(.+)'\] (\S+) (\S+)", str(fvec[f"{key}__operation"]))
+    assert (m.group(1), m.group(2), m.group(3), float(m.group(4))) == (chans[a], chans[b], operator, diff)
+    got = omask.frequency_differencing(np.asarray(fvec["Sv"], dtype=np.float64), a, b, operator, diff)
+    assert np.array_equal(got, fvec[f"{key}__mask"])
+
+
+def test_host_frequency_differencing_rejects_what_the_reference_rejects(fvec):
+    """Same exception type and message, before any device work (a negative right-hand side is not accepted by the
+    reference's equation pattern: its operator group swallows the sign)."""
+    import ast
+
+    import echopype_b200 as ep
+
+    ds = _fd_dataset(fvec)
+    for kw_repr, etype, msg in fvec["bad__cases"]:
+        kw = ast.literal_eval(str(kw_repr))
+        assert str(etype) != "ok"
+        with pytest.raises({"ValueError": ValueError, "TypeError": TypeError}[str(etype)]) as ei:
+            ep.mask.frequency_differencing(source_Sv=ds, **kw)
+        assert str(ei.value) == str(msg), (kw, str(ei.value), str(msg))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", FD_KEYS)
+def test_cuda_frequency_differencing_equals_reference(ep, fvec, key):
+    got = ep.mask.frequency_differencing(source_Sv=_fd_dataset(fvec), **_fd_kw(fvec, key))
+    assert tuple(got.dims) == ("ping_time", "range_sample")
+    assert np.array_equal(np.asarray(got.values).astype(bool), fvec[f"{key}__mask"])  # float32 differences of 0.5 dB steps are exact
