@@ -4,8 +4,11 @@ TEST INFRASTRUCTURE (see oracle/__init__.py).  Follows echopype/clean/api.py:362
 (estimate_background_noise), :436-511 (remove_background_noise) and echopype/clean/utils.py:13-26
 (extract_dB), :380-401 (attrs incl. actual_range).  xarray's ``coarsen(..., boundary="pad").mean()``
 is restated as NaN-pad + reshape + nanmean; ``reindex(method="ffill")`` as index // ping_num.
-Pinned by the reference's known-answer test tests/clean/test_noise.py:902-987 (restated in
-tests/test_oracle_golden.py).
+Pinned by outputs of the reference's own estimate_ / remove_background_noise (tests/golden/make_golden_calibrate.py,
+tests/test_reference_pinned.py) and by its known-answer test tests/clean/test_noise.py:902-987 (restated in
+tests/test_oracle_golden.py).  The noise masks further down (impulse, transient, attenuated signal) are pinned by outputs of
+the reference's own mask functions and workers (tests/golden/make_golden_masks.py, tests/test_reference_pinned_masks.py);
+downsample_upsample_along_depth (flox) is the one restated worker.
 """
 
 import re

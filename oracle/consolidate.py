@@ -4,6 +4,8 @@ depth = transducer_depth + orientation * echo_range * echo_range_scaling, with t
 per-ping series aligned to ping_time (utils/align.py:5-61, interp "nearest" with extrapolation), and the scaling
 cos(tilt) (number / per-ping series), the platform pitch-roll rotation (ek_depth_utils.py:55-75) or the normalised
 beam z direction per channel (:78-120).
+Pinned: reproduces the outputs of the reference's own add_depth / align_to_ping_time / ek_use_* functions
+(tests/golden/make_golden_consolidate.py -> consolidate_vectors.npz, tests/test_reference_pinned_consolidate.py).
 """
 
 import numpy as np
