@@ -54,7 +54,8 @@ def frequency_differencing(source_Sv, storage_options: dict = {}, freqABEq: str 
 
 
 def _mask_tensor(m, dev):
-    """DataArray / ndarray / tensor -> (uint8 device tensor, has_channel).  NaN counts as False (api.py:431-435)."""
+    """DataArray / ndarray / tensor -> (uint8 device tensor, has_channel).  Masks arrive validated (_validate_mask: no NaN,
+    0 / 1 only); the NaN -> False rule of api.py:431-435 is kept for callers of this helper that skip the validation."""
     if isinstance(m, DataArray):  # align by dimension NAME like the reference (its own maskers return
         # (channel, range_sample, ping_time)): transpose to ([channel,] ping_time, range_sample)
         unknown = [d for d in m.dims if d not in ("channel", "ping_time", "range_sample")]
@@ -81,6 +82,53 @@ def _mask_tensor(m, dev):
     return t.contiguous(), has_channel
 
 
+_ALLOWED_MASK_DIMS = [
+    {"ping_time", "range_sample"}, {"ping_time", "depth"}, {"ping_time", "echo_range"},
+    {"channel", "ping_time", "range_sample"}, {"channel", "ping_time", "depth"}, {"channel", "ping_time", "echo_range"},
+]
+
+
+def _validate_mask(m, target_dims):
+    """The checks of mask/api.py:131-160 (_validate_and_collect_mask_input) and :41-71 (_check_mask_dim_alignment) for one
+    mask, with the reference's exception types and messages: allowed dimension sets, no NaN, only 0 / 1 / True / False,
+    dimensions equal to those of the source variable when 'channel' is set aside.  uint8 / bool DEVICE tensors (the masks
+    this package produces) hold 0 / 1 by construction and are not read back."""
+    if isinstance(m, DataArray):
+        if set(m.dims) not in _ALLOWED_MASK_DIMS:
+            raise ValueError(
+                "Masks must have one of the following dimensions: "
+                "{'ping_time', 'range_sample'}, "
+                "{'ping_time', 'depth'}, "
+                "{'ping_time', 'echo_range'}, "
+                "{'channel', 'ping_time', 'range_sample'}, "
+                "{'channel', 'ping_time', 'depth'}"
+                "{'channel', 'ping_time', 'echo_range'}"
+            )
+    data = m.data if isinstance(m, DataArray) else m
+    if isinstance(data, torch.Tensor):
+        if data.dtype not in (torch.uint8, torch.bool):
+            if data.is_floating_point() and bool(torch.isnan(data).any()):
+                raise TypeError("Mask cannot contain NaN")
+            if not bool(((data == 0) | (data == 1)).all()):
+                raise TypeError("Mask must be boolean (True/False or 1/0)")
+    else:
+        a = np.asarray(data)
+        if a.dtype.kind == "f" and np.any(np.isnan(a)):
+            raise TypeError("Mask cannot contain NaN")
+        if a.dtype.kind != "b" and not np.all(np.isin(np.unique(a), [0, 1, True, False])):
+            raise TypeError("Mask must be boolean (True/False or 1/0)")
+    if isinstance(m, DataArray):
+        mask_dims, want = set(m.dims) - {"channel"}, set(target_dims) - {"channel"}
+        if "channel" in m.dims and "channel" not in target_dims:
+            raise ValueError("'channel' is a dimension in mask but not a dimension in source.")
+        if mask_dims != want:
+            raise ValueError(
+                f"The dimensions of mask: ({mask_dims}) do not match "
+                f"the dimensions of source ({want}) "
+                "when not considering 'channel'."
+            )
+
+
 def apply_mask(source_ds, mask: Union[DataArray, List[DataArray]], var_name: str = "Sv",
                fill_value: Union[int, float] = np.nan, storage_options_ds: dict = {}, storage_options_mask=None) -> Dataset:
     """``source_ds[var_name]`` where the mask(s) hold, ``fill_value`` elsewhere (echopype.mask.apply_mask).  Several
@@ -95,6 +143,8 @@ def apply_mask(source_ds, mask: Union[DataArray, List[DataArray]], var_name: str
     if not masks:
         raise ValueError("mask must contain at least one mask")
     src = source_ds[var_name]
+    for m in masks:  # the reference validates every mask before it touches the data (mask/api.py:380-381)
+        _validate_mask(m, tuple(src.dims))
     if tuple(src.dims) != ("channel", "ping_time", "range_sample"):
         raise ValueError(f"source_ds[{var_name}] must have dims ('channel', 'ping_time', 'range_sample')")
     dev = require_cuda()

@@ -85,8 +85,7 @@ def test_apply_mask_gpu():
     ds, Sv = _mock_ds(ep, seed=3)
     rs = np.random.default_rng(1)
     m2 = rs.random(Sv.shape[1:]) < 0.6            # (ping_time, range_sample), host bool
-    m3 = (rs.random(Sv.shape) < 0.7).astype(np.float64)  # (channel, ping, range) float with NaN entries
-    m3[rs.random(Sv.shape) < 0.05] = np.nan
+    m3 = (rs.random(Sv.shape) < 0.7).astype(np.float64)  # (channel, ping, range) float 0 / 1 (NaN entries are rejected, below)
     mfd = ep.mask.frequency_differencing(ds, chanABEq='"chan1" - "chan2" > 1.0dB')  # device uint8
     masks = [mfd, ep.DataArray(m2, ("ping_time", "range_sample")), ep.DataArray(m3, ("channel", "ping_time", "range_sample"))]
     out = ep.mask.apply_mask(ds, masks, fill_value=-999.0)
@@ -115,3 +114,31 @@ def test_apply_mask_gpu():
         ep.mask.apply_mask(ds, mfd, fill_value=ep.DataArray(fill[:, :-1], ("ping_time", "range_sample")))
     with pytest.raises(TypeError, match="The input fill_value must be of type int, float, or xr.DataArray!"):
         ep.mask.apply_mask(ds, mfd, fill_value="nan")
+
+
+def test_apply_mask_rejects_what_the_reference_rejects():
+    """mask/api.py:131-160 (_validate_and_collect_mask_input) and :41-71 (_check_mask_dim_alignment): same exception types
+    and messages, raised before any device work."""
+    import echopype_b200 as ep
+
+    C, P, R = 2, 4, 5
+    dims = ("channel", "ping_time", "range_sample")
+    ds = ep.Dataset({"Sv": (dims, np.zeros((C, P, R), np.float32))},
+                    coords={"channel": np.array(["a", "b"], dtype=object), "ping_time": np.arange(P), "range_sample": np.arange(R)})
+    nanmask = np.ones((P, R))
+    nanmask[1, 2] = np.nan
+    with pytest.raises(TypeError, match="Mask cannot contain NaN"):
+        ep.mask.apply_mask(ds, ep.DataArray(nanmask, ("ping_time", "range_sample")))
+    with pytest.raises(TypeError, match=r"Mask must be boolean \(True/False or 1/0\)"):
+        ep.mask.apply_mask(ds, ep.DataArray(np.full((P, R), 2.0), ("ping_time", "range_sample")))
+    with pytest.raises(TypeError, match=r"Mask must be boolean \(True/False or 1/0\)"):
+        ep.mask.apply_mask(ds, [ep.DataArray(np.ones((P, R), bool), ("ping_time", "range_sample")),
+                                ep.DataArray(np.arange(P * R).reshape(P, R), ("ping_time", "range_sample"))])
+    with pytest.raises(ValueError, match="Masks must have one of the following dimensions"):
+        ep.mask.apply_mask(ds, ep.DataArray(np.ones((P, R), bool), ("time", "range_sample")))
+    with pytest.raises(ValueError, match="Masks must have one of the following dimensions"):
+        ep.mask.apply_mask(ds, ep.DataArray(np.ones(P, bool), ("ping_time",)))
+    with pytest.raises(ValueError, match="do not match the dimensions of source"):
+        ep.mask.apply_mask(ds, ep.DataArray(np.ones((P, R), bool), ("ping_time", "depth")))
+    with pytest.raises(ValueError, match="The Dataset source_ds does not contain the variable var_name!"):
+        ep.mask.apply_mask(ds, ep.DataArray(np.ones((P, R), bool), ("ping_time", "range_sample")), var_name="Sv_corrected")
