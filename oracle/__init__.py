@@ -22,11 +22,11 @@ Pinning status (see DESIGN.md "Oracle"): PINNED.
     bin-string parsers: pinned against outputs of the reference's own functions (tests/golden/make_golden.py);
   * the impulse / transient / attenuated-signal noise masks (clean/api.py:30-359 and their workers in clean/utils.py),
     consolidate.add_depth (consolidate/api.py:66-247 with utils/align.py and consolidate/ek_depth_utils.py),
-    mask.frequency_differencing (mask/api.py:467-676 with its equation parser) and compute_MVBS_index_binning
+    mask.frequency_differencing / apply_mask (mask/api.py:41-676 with the equation parser and helpers) and compute_MVBS_index_binning
     (commongrid/api.py:195-266): executed the same way by tests/golden/make_golden_{masks,consolidate,mask,commongrid}.py;
     tests/test_reference_pinned_masks.py and tests/test_reference_pinned_consolidate.py assert that the oracle reproduces
     those outputs (masks exactly, values to 1e-9 dB or better) and compare the CUDA results with them directly;
-  * MVBS, NASC, pulse-length lookup, env-param interpolation, mask.apply_mask and impulse noise on depth VALUES (flox):
+  * MVBS, NASC, pulse-length lookup, env-param interpolation and impulse noise on depth VALUES (flox):
     pinned against the reference's own known-answer tests (restated in tests/test_oracle_*.py, tests/test_mask*.py); the
     bin reduction itself is flox's (a third-party dependency absent here), anchored on the reference's brute-force mock test.
 

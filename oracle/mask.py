@@ -4,7 +4,8 @@ frequency_differencing, echopype/mask/api.py:593-608: mask = (Sv[chanA] - Sv[cha
 apply_mask, echopype/mask/api.py:395-438: masks broadcast over channel, combined with logical AND, NaN mask entries
 count as False, result = where(mask, var, fill_value).
 frequency_differencing is pinned to the outputs of the reference's own function (tests/golden/make_golden_mask.py ->
-freqdiff_vectors.npz, tests/test_reference_pinned_consolidate.py); apply_mask is a restatement.
+freqdiff_vectors.npz, tests/test_reference_pinned_consolidate.py), and so is apply_mask (lifted with its helpers, four mask /
+fill combinations).
 """
 
 import operator as _op

@@ -56,6 +56,18 @@ def reference_frequency_differencing():
     return ns["frequency_differencing"]
 
 
+def reference_apply_mask():
+    """apply_mask and its four helpers (mask/api.py:41-464), executed unmodified; provenance helpers are no-ops"""
+    import pathlib
+
+    ns = {"np": np, "xr": xrlite, "pathlib": pathlib, "datetime": datetime, "sys": sys, "List": None, "Optional": None, "Union": None,
+          "validate_source": lambda obj, storage_options: (obj, None), "echopype_prov_attrs": lambda **k: {},
+          "insert_input_processing_level": lambda ds, input_ds=None: ds}
+    _lift("mask/api.py", {"_check_mask_dim_alignment", "_validate_and_collect_mask_input", "_check_var_name_fill_value",
+                          "_variable_prov_attrs", "apply_mask"}, ns)
+    return ns["apply_mask"]
+
+
 def main():
     warnings.simplefilter("ignore", RuntimeWarning)
     if not hasattr(xrlite.DataArray, "variable"):  # frequency_differencing looks at Sv.variable._data to tell dask from numpy
@@ -99,6 +111,57 @@ def main():
         except Exception as e:  # noqa
             bad[i] = (repr(kw), type(e).__name__, str(e))
     out["bad__cases"] = np.array([list(v) for v in bad.values()])
+    # ---- apply_mask: values for several mask / fill combinations, and what it rejects --------------------------------------
+    am = reference_apply_mask()
+    coords3 = {k: ds._coords[k].data for k in DIMS3}
+
+    def da(a, dims, attrs=None):
+        return xrlite.DataArray(np.asarray(a), {d: coords3[d] for d in dims}, dims, attrs=attrs)
+
+    m2 = rng.random((P, R)) < 0.6
+    m3 = (rng.random((C, P, R)) < 0.7).astype(np.float64)
+    mfd = fd(ds, storage_options={}, chanABEq='"chA 18" - "chB 38" > 1.0dB')
+    fill_arr = rng.normal(-90.0, 1.0, (P, R)).astype(np.float32).astype(np.float64)
+    out["am__m2"], out["am__m3"], out["am__mfd"], out["am__fill_arr"] = m2, m3, np.asarray(mfd.values).astype(bool), fill_arr
+    am_cases = {
+        "am_single_nan": (mfd, {}),
+        "am_list_fill": ([mfd, da(m2, DIMS3[1:]), da(m3, DIMS3)], dict(fill_value=-999.0)),
+        "am_int_fill": (da(m3, DIMS3), dict(fill_value=0)),
+        # an array fill needs the channel dimension in the final mask: xr.where broadcasts the plain fill array positionally
+        "am_fill_array": ([da(m3, DIMS3), mfd], dict(fill_value=xrlite.DataArray(fill_arr[None], {"ping_time": coords3["ping_time"], "range_sample": coords3["range_sample"]},
+                                                                                 ("channel", "ping_time", "range_sample")))),
+    }
+    for key, (mask, kw) in am_cases.items():
+        res = am(ds, mask, var_name="Sv", storage_options_ds={}, storage_options_mask={}, **kw)
+        assert tuple(res["Sv"].dims) == DIMS3
+        out[f"{key}__Sv"] = np.asarray(res["Sv"].values, dtype=np.float64)
+        a = res["Sv"].attrs
+        out[f"{key}__long_name"], out[f"{key}__actual_range"] = np.array(a["long_name"]), np.asarray(a["actual_range"], dtype=np.float64)
+        out[f"{key}__mask_type"] = np.array(a.get("mask_type", ""))
+        print(key, "kept", int(np.isfinite(out[f"{key}__Sv"]).sum()), a["actual_range"], a.get("mask_type"))
+    nanmask = np.ones((P, R))
+    nanmask[1, 2] = np.nan
+    bad_am = []
+    for label, mask, kw in [
+        ("transposed", da(m3.transpose(0, 2, 1), ("channel", "range_sample", "ping_time")), {}),
+        ("nan", da(nanmask, DIMS3[1:]), {}),
+        ("two", da(np.full((P, R), 2.0), DIMS3[1:]), {}),
+        ("ints_in_list", [da(np.ones((P, R), bool), DIMS3[1:]), da(np.arange(P * R).reshape(P, R), DIMS3[1:])], {}),
+        ("bad_dim_name", xrlite.DataArray(np.ones((P, R), bool), {"range_sample": coords3["range_sample"]}, ("time", "range_sample")), {}),
+        ("one_dim", da(np.ones(P, bool), ("ping_time",)), {}),
+        ("depth_dim", xrlite.DataArray(np.ones((P, R), bool), {"ping_time": coords3["ping_time"]}, ("ping_time", "depth")), {}),
+        ("short", xrlite.DataArray(np.ones((P, R - 1), bool), {"ping_time": coords3["ping_time"]}, ("ping_time", "range_sample")), {}),
+        ("no_var", da(np.ones((P, R), bool), DIMS3[1:]), dict(var_name="Sv_corrected")),
+        ("fill_str", da(np.ones((P, R), bool), DIMS3[1:]), dict(fill_value="nan")),
+        ("fill_shape", da(np.ones((P, R), bool), DIMS3[1:]), dict(fill_value=xrlite.DataArray(fill_arr[:, :-1], None, ("ping_time", "range_sample")))),
+    ]:
+        kw = dict(dict(var_name="Sv"), **kw)
+        try:
+            am(ds, mask, storage_options_ds={}, storage_options_mask={}, **kw)
+            bad_am.append([label, "ok", ""])
+        except Exception as e:  # noqa
+            bad_am.append([label, type(e).__name__, str(e)])
+    out["am_bad__cases"] = np.array(bad_am)
     np.savez_compressed(os.path.join(HERE, "freqdiff_vectors.npz"), **out)
     print("wrote", len(out), "arrays")
 

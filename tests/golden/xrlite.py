@@ -515,8 +515,8 @@ class DataArray:
                 if not isinstance(a, (str, bytes)) and arr.ndim > 0:
                     if arr.ndim > len(dims):
                         raise ValueError("plain array with more dims than the labelled operand")
-                    if len(das) != 1 or tuple(dims) != ref.dims:
-                        raise NotImplementedError("plain ndarray operand next to several labelled operands")
+                    if any(tuple(d.dims) != tuple(dims) for d in aligned):  # positional broadcasting would be ambiguous
+                        raise NotImplementedError("plain ndarray operand next to labelled operands with different dims")
                 ins.append(a if isinstance(a, (str, bytes)) else arr)
         with np.errstate(all="ignore"):
             out = f(*ins)
@@ -1353,6 +1353,20 @@ def zeros_like(other, dtype=None):
 
 def ones_like(other, dtype=None):
     return full_like(other, 1, dtype)
+
+
+def broadcast(*arrays):
+    """xr.broadcast for DataArrays: every array expanded to the union of the dims (first-appearance order)."""
+    aligned, dims = DataArray._align(list(arrays))
+    sizes = {}
+    for a in aligned:
+        sizes.update(a.sizes)
+    coords = DataArray._merge_coords(aligned, dims)
+    out = []
+    for a in aligned:
+        data = np.broadcast_to(a._broadcast_data(dims), [sizes[d] for d in dims]).copy()
+        out.append(DataArray(data, coords, dims, a.name, a.attrs))
+    return tuple(out)
 
 
 def concat(objs, dim, **kw):

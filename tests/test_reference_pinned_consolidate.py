@@ -183,3 +183,64 @@ def test_cuda_frequency_differencing_equals_reference(ep, fvec, key):
     got = ep.mask.frequency_differencing(source_Sv=_fd_dataset(fvec), **_fd_kw(fvec, key))
     assert tuple(got.dims) == ("ping_time", "range_sample")
     assert np.array_equal(np.asarray(got.values).astype(bool), fvec[f"{key}__mask"])  # float32 differences of 0.5 dB steps are exact
+
+
+# ---- mask.apply_mask against the executed reference function (tests/golden/make_golden_mask.py) -------------------------
+def test_oracle_equals_reference_apply_mask(fvec):
+    from oracle import mask as omask
+
+    Sv = np.asarray(fvec["Sv"], dtype=np.float64)
+    mfd, m2, m3, fill = fvec["am__mfd"], fvec["am__m2"], fvec["am__m3"], fvec["am__fill_arr"]
+    for key, masks, fv in [("am_single_nan", [mfd], np.nan), ("am_list_fill", [mfd, m2, m3], -999.0), ("am_int_fill", [m3], 0),
+                           ("am_fill_array", [m3, mfd], fill)]:
+        got = omask.apply_mask(Sv, masks, fv)
+        want = fvec[f"{key}__Sv"]
+        assert np.array_equal(np.isnan(got), np.isnan(want)), key
+        np.testing.assert_array_equal(np.nan_to_num(got, nan=1.0), np.nan_to_num(want, nan=1.0))
+        lo, hi = fvec[f"{key}__actual_range"]
+        assert [round(float(np.nanmin(got)), 2), round(float(np.nanmax(got)), 2)] == [lo, hi]
+        assert str(fvec[f"{key}__long_name"]) == "Volume backscattering strength, masked (Sv re 1 m-1)"
+    # the attributes of the FIRST mask travel to the masked variable (mask/api.py:290-297)
+    assert str(fvec["am_single_nan__mask_type"]) == "frequency differencing" and str(fvec["am_int_fill__mask_type"]) == ""
+
+
+def test_host_apply_mask_rejects_what_the_reference_rejects(fvec):
+    """Every mask the reference's own apply_mask refused when it was executed (NaN entries, values other than 0 / 1, dimension
+    sets outside the allowed list, dimensions that do not match the source) is refused here with the same exception type and
+    message, before any device work.  Three recorded cases are deliberately different (known deviations):
+    a (channel, range_sample, ping_time) mask is aligned by NAME here instead of failing the positional shape check, a
+    missing var_name raises the helper's ValueError instead of xarray's KeyError, and the two shape checks that need the
+    device-side shapes are exercised in the GPU test."""
+    import echopype_b200 as ep
+
+    ds = _fd_dataset(fvec)
+    C, P, R = fvec["Sv"].shape
+    nanmask = np.ones((P, R))
+    nanmask[1, 2] = np.nan
+    ours = {
+        "nan": ep.DataArray(nanmask, ("ping_time", "range_sample")),
+        "two": ep.DataArray(np.full((P, R), 2.0), ("ping_time", "range_sample")),
+        "ints_in_list": [ep.DataArray(np.ones((P, R), bool), ("ping_time", "range_sample")),
+                         ep.DataArray(np.arange(P * R).reshape(P, R), ("ping_time", "range_sample"))],
+        "bad_dim_name": ep.DataArray(np.ones((P, R), bool), ("time", "range_sample")),
+        "one_dim": ep.DataArray(np.ones(P, bool), ("ping_time",)),
+        "depth_dim": ep.DataArray(np.ones((P, R), bool), ("ping_time", "depth")),
+    }
+    seen = set()
+    for label, etype, msg in fvec["am_bad__cases"]:
+        label, etype, msg = str(label), str(etype), str(msg)
+        assert etype != "ok", label
+        if label not in ours:
+            continue
+        seen.add(label)
+        with pytest.raises({"ValueError": ValueError, "TypeError": TypeError}[etype]) as ei:
+            ep.mask.apply_mask(ds, ours[label])
+        if label == "depth_dim":  # the message prints two Python sets, whose element order is not fixed
+            assert str(ei.value).startswith("The dimensions of mask: (") and str(ei.value).endswith("when not considering 'channel'.")
+            assert msg.startswith("The dimensions of mask: (") and msg.endswith("when not considering 'channel'.")
+        else:
+            assert str(ei.value) == msg, (label, str(ei.value), msg)
+    assert seen == set(ours)
+    with pytest.raises(TypeError) as ei:
+        ep.mask.apply_mask(ds, ep.DataArray(np.ones((P, R), bool), ("ping_time", "range_sample")), fill_value="nan")
+    assert str(ei.value) == [str(m) for l, t, m in fvec["am_bad__cases"] if str(l) == "fill_str"][0]
