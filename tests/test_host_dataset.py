@@ -80,3 +80,56 @@ def test_dataset_surface_of_the_documented_chain():
     sub = ds.isel(ping_time=slice(1, 4), range_sample=slice(0, 3))
     assert sub["Sv"].shape == (2, 3, 3) and len(sub["ping_time"].values) == 3
     np.testing.assert_array_equal(sub["Sv"].values, ds["Sv"].values[:, 1:4, :3])
+
+
+# ---- processing-level attributes against the EXECUTED reference decorator (tests/golden/make_golden_prov.py) ------------
+def _prov_ds(latlon, input_level):
+    ds = Dataset({"Sv": (("ping_time",), np.zeros(4))}, coords={"ping_time": np.arange(4)})
+    if latlon in ("valid", "all_nan", "lat_only"):
+        ds["latitude"] = (("ping_time",), np.full(4, np.nan) if latlon == "all_nan" else np.array([44.0, np.nan, 44.2, 44.3]))
+    if latlon in ("valid", "all_nan"):
+        ds["longitude"] = (("ping_time",), np.full(4, np.nan) if latlon == "all_nan" else np.array([-124.0, -124.1, np.nan, -124.3]))
+    if input_level is not None:
+        ds.attrs["input_processing_level"] = input_level
+    ds.attrs["keep"] = "me"
+    return ds
+
+
+_PROV_STATE = {}
+
+
+def produce():  # module level and named like the generator's function: the error messages quote the qualified name
+    return _prov_ds(_PROV_STATE["ll"], _PROV_STATE["lev"])
+
+
+def produce_number():
+    return 3
+
+
+def test_processing_level_decorator_equals_reference():
+    import json
+
+    from echopype_b200.utils import prov
+
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "prov_cases.json")))
+    n_ok = n_err = 0
+    for c in cases["add_processing_level"]:
+        _PROV_STATE["ll"], _PROV_STATE["lev"] = c["latlon"], c["input_level"]
+        if "error" in c:
+            etype = {"ValueError": ValueError, "RuntimeError": RuntimeError}[c["error"][0]]
+            with pytest.raises(etype) as ei:
+                prov.add_processing_level(c["code"])(produce)()
+            assert str(ei.value) == c["error"][1], c
+            n_err += 1
+        else:
+            out = prov.add_processing_level(c["code"])(produce)()
+            assert dict(out.attrs) == c["attrs"], c
+            n_ok += 1
+    assert n_ok == 140 and n_err == 68
+    for c in cases["insert_input_processing_level"]:
+        out = prov.insert_input_processing_level(Dataset(attrs={"a": 1}), input_ds=Dataset(attrs=dict(c["input_attrs"])))
+        assert dict(out.attrs) == c["attrs"]
+    assert sorted(prov.echopype_prov_attrs(process_type="processing")) == cases["prov_attr_keys"]
+    with pytest.raises(RuntimeError) as ei:
+        prov.add_processing_level("L2A")(produce_number)()
+    assert str(ei.value) == cases["not_a_dataset_error"][1]
