@@ -858,6 +858,25 @@ class DataArray:
     def pipe(self, func, *args, **kw):
         return func(self, *args, **kw)
 
+    def resample(self, indexer=None, skipna=None, **kw):
+        """1-D time series only; pandas resampling (origin="start_day", closed / label "left"), like xarray's wrapper."""
+        import pandas as pd
+
+        (dim, freq), = dict(indexer or {}, **kw).items()
+        if self.dims != (dim,):
+            raise NotImplementedError("resample: 1-D series along the resampled dimension only")
+        series = pd.Series(np.asarray(self._data), index=pd.DatetimeIndex(self._coords[dim].data))
+        owner = self
+
+        class _Resampled:
+            def first(self_inner, **k):
+                r = series.resample(freq).first()
+                out = DataArray(r.to_numpy(), {dim: r.index.to_numpy()}, (dim,), owner.name)
+                out.indexes = {dim: r.index}
+                return out
+
+        return _Resampled()
+
     def chunk(self, chunks=None, **kw):
         return self
 

@@ -225,3 +225,59 @@ def test_cuda_index_binning_equals_reference(ep, gvec, key):
     assert np.max(np.abs(np.asarray(got["ping_time"].values).astype("datetime64[ns]").astype(np.int64) - gvec[f"{key}__ping_time"])) < 1000
     np.testing.assert_array_equal(np.asarray(got["range_sample"].values), gvec[f"{key}__range_sample"])
     np.testing.assert_allclose(got["Sv"].attrs["actual_range"], gvec[f"{key}__actual_range"], atol=0.011)
+
+
+# ---- compute_MVBS: the bin grids and argument checks around the flox group-by, from the executed reference ---------------
+GRID_KEYS = ["grid_a", "grid_b", "grid_c", "grid_d", "grid_e", "grid_f"]
+
+
+@pytest.mark.parametrize("key", GRID_KEYS)
+def test_oracle_and_host_bin_grids_equal_reference(gvec, key):
+    """compute_MVBS (commongrid/api.py:31-191) was executed with only compute_raw_MVBS (the flox group-by) replaced by a recorder:
+    the range grid (from range_var.max(skipna=True) or from range_var_max + 1e-8), the ping grid (pandas resample plus one closing
+    edge, whatever `closed` is) and the output coordinates (interval LEFT ends, also for closed="right") are the reference's."""
+    from echopype_b200.commongrid import utils as gutils
+    from oracle import commongrid as ogrid
+
+    kw = ast.literal_eval(str(gvec[f"{key}__kw"]))
+    rb = parse_x_bin(kw["range_bin"], "range_bin")
+    if "range_var_max" in kw:
+        rmax = parse_x_bin(kw["range_var_max"], "range_bin") + 1e-8
+    else:
+        rmax = float(np.nanmax(_f64(gvec[f"{key}__range_in"])))
+    want_r, want_p = gvec[f"{key}__range_edges"], gvec[f"{key}__ping_edges"]
+    t_in = gvec[f"{key}__ping_time_in"]
+    for edges_r, edges_p in [(ogrid.range_edges(rmax, rb), ogrid.ping_edges(t_in, kw["ping_time_bin"])),
+                             (gutils.range_edges(rmax, gutils._parse_x_bin(kw["range_bin"])),
+                              gutils.ping_time_edges(t_in.astype("datetime64[ns]"), kw["ping_time_bin"]).astype(np.int64))]:
+        np.testing.assert_array_equal(np.asarray(edges_r, dtype=np.float64), want_r)
+        np.testing.assert_array_equal(np.asarray(edges_p), want_p)
+    np.testing.assert_array_equal(gvec[f"{key}__out_range"], want_r[:-1])
+    np.testing.assert_array_equal(gvec[f"{key}__out_ping_time"], want_p[:-1])
+    assert list(gvec[f"{key}__closed"]) == [kw.get("closed", "left")] * 2
+    # attribute strings of the reference for this setting
+    val, unit = gutils.ping_time_bin_parsing_and_conversion(kw["ping_time_bin"])
+    rv = kw.get("range_var", "echo_range")
+    assert str(gvec[f"{key}__cell_methods"]) == (f"ping_time: mean (interval: {val} {unit} comment: ping_time is the interval start) "
+                                                  f"{rv}: mean (interval: {rb} meter comment: {rv} is the interval start)")
+    assert str(gvec[f"{key}__range_meter_interval"]) == str(rb) + "m" and str(gvec[f"{key}__ping_time_interval"]) == kw["ping_time_bin"]
+
+
+def test_host_compute_MVBS_rejects_what_the_reference_rejects(gvec):
+    import echopype_b200 as ep
+    from echopype_b200.dataset import Dataset
+
+    C, P, R = 2, 6, 8
+    ds = Dataset({"Sv": (DIMS, np.zeros((C, P, R), np.float32)), "echo_range": (DIMS, np.ones((C, P, R), np.float32)),
+                  "frequency_nominal": (("channel",), np.array([38e3, 120e3]))},
+                 coords={"channel": np.array(["ch0", "ch1"], dtype=object), "ping_time": np.datetime64("2024-03-01") + np.arange(P) * np.timedelta64(1, "s"),
+                         "range_sample": np.arange(R)})
+    kws = {"range_var": dict(range_var="range"), "missing_depth": dict(range_var="depth"), "range_bin_type": dict(range_bin=10),
+           "range_bin_unit": dict(range_bin="10km"), "range_bin_nounit": dict(range_bin="10"), "closed": dict(closed="both"),
+           "ping_time_bin_type": dict(ping_time_bin=10), "reindex": dict(method="cohorts", reindex=True)}
+    for label, etype, msg in gvec["grid_bad__cases"]:
+        label, etype, msg = str(label), str(etype), str(msg)
+        assert etype != "ok"
+        with pytest.raises({"ValueError": ValueError, "TypeError": TypeError}[etype]) as ei:
+            ep.commongrid.compute_MVBS(ds, **kws[label])
+        assert str(ei.value) == msg, (label, str(ei.value), msg)
