@@ -577,3 +577,88 @@ def test_mask_attenuated_signal_outside_searching_range(ep):
     got = ep.clean.mask_attenuated_signal(_ds(ep, Sv, depth), "1800m", "2800m", 15, "-6dB")
     assert got.values.shape == (2, 12, 64) and not got.values.any()
     assert not ep.clean.mask_attenuated_signal(_ds(ep, Sv, depth)).values.any()  # the defaults (400 m .. 500 m) as well
+
+
+# ---- the selection algorithm of attenuated_ping_kernel, emulated step by step (CPU) -------------------------------------
+def _emulated_staged_median(keys, scratch_capacity, quantum=2048):
+    """staged_median_keys of csrc/attenuation.cu in numpy, one array operation per CTA-wide pass: order-preserving keys with
+    NaN = all ones, the bit loop starting at the highest bit in which the smallest and the largest valid key differ,
+    candidates compacted (in arbitrary order) once they are a quarter of the scanned array, the even-count step looking
+    for the smallest key above the median in the WHOLE array.  Returns (m, ka, kb, scanned keys / array length)."""
+    NAN = np.uint32(0xFFFFFFFF)
+    rup = lambda n: (n + quantum - 1) // quantum * quantum  # noqa: E731
+    src = np.concatenate([keys, np.full(rup(len(keys)) - len(keys), NAN, np.uint32)])
+    valid = src != NAN
+    m = int(valid.sum())
+    if m == 0:
+        return 0, None, None, 1.0
+    lo, hi = int(src.min()), int(np.where(valid, src, 0).max())
+    k, prefix, bit = (m - 1) >> 1, lo, -1
+    if lo != hi:
+        bit = int(lo ^ hi).bit_length() - 1
+        prefix = lo & ~(((2 << bit) - 1) & 0xFFFFFFFF) & 0xFFFFFFFF
+    cur, cand, free, scanned = src, m, 0, len(src)
+    rng = np.random.default_rng(len(keys))
+    while bit >= 0:
+        test = (0xFFFFFFFF << bit) & 0xFFFFFFFF
+        match = ((cur.astype(np.uint64) ^ prefix) & test) == 0
+        z = int(match.sum())
+        scanned += len(cur)
+        if k >= z:
+            prefix |= 1 << bit
+            k -= z
+            cand -= z
+        else:
+            cand = z
+        if bit > 0 and len(cur) // quantum > 1 and cand * 4 <= len(cur) and free + rup(cand) <= scratch_capacity:
+            take = (((cur.astype(np.uint64) ^ prefix) & test) == 0) & (cur != NAN)
+            got = cur[take]
+            assert len(got) == cand  # the padding written behind the copies relies on this count
+            rng.shuffle(got)
+            scanned += len(cur)
+            cur = np.concatenate([got, np.full(rup(cand) - cand, NAN, np.uint32)])
+            free += len(cur)
+        bit -= 1
+    ka = kb = prefix
+    if m % 2 == 0:
+        eq = int((cur == prefix).sum())
+        above = src[(src > prefix) & (src != NAN)]
+        if k + 1 >= eq:
+            kb = int(above.min())
+    return m, ka, kb, scanned / len(src)
+
+
+def _to_key(v):
+    u = np.asarray(v, np.float32).view(np.uint32)
+    k = np.where(u & np.uint32(0x80000000), ~u, u | np.uint32(0x80000000)).astype(np.uint32)
+    k[np.isnan(v)] = np.uint32(0xFFFFFFFF)
+    return k
+
+
+def _from_key(k):
+    k = np.uint32(k)
+    u = (k ^ np.uint32(0x80000000)) if (k & np.uint32(0x80000000)) else np.uint32(~k)
+    return np.array([u], np.uint32).view(np.float32)[0]
+
+
+def test_attenuated_selection_algorithm_emulation():
+    """The radix selection with its two short cuts returns the two middle elements of the sorted valid values for clustered
+    Sv, duplicates, a single repeated value, both signs, +-inf / +-0 and every NaN fraction; on a default-sized window of
+    clustered Sv (30 pings x 526 samples) it scans about a third of what 34 full passes would."""
+    rng = np.random.default_rng(0)
+    work = []
+    for trial in range(240):
+        n = int(rng.choice([1, 2, 3, 5, 17, 100, 526, 2048, 2049, 5000, 15780, 16384]))
+        kind = trial % 6
+        v = [rng.normal(-70, 6, n), rng.normal(-70, 6, n).round(0), np.full(n, -66.5), rng.normal(0, 50, n),
+             rng.choice([-np.inf, np.inf, -70.0, -60.0, 0.0, -0.0], n), rng.normal(-64, 3, n)][kind].astype(np.float32)
+        v[rng.random(n) < rng.choice([0, 0.02, 0.5, 1.0])] = np.nan
+        m, ka, kb, w = _emulated_staged_median(_to_key(v), 24576 - (n + 2047) // 2048 * 2048)
+        ok = np.sort(v[~np.isnan(v)])
+        assert m == len(ok)
+        if m == 0:
+            continue
+        assert _from_key(ka) == ok[(m - 1) // 2] and _from_key(kb) == ok[m // 2], (trial, n, kind)
+        if n == 15780 and kind in (0, 5) and m > 15000:
+            work.append(w)
+    assert work and max(work) < 16.0  # against 1 + 32 (+ 1) full passes of the plain loop
